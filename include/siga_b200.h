@@ -1,0 +1,184 @@
+/*
+ * siga_b200 -- C ABI of the B200-native SIGA hot path (`siga index` + `siga overlap`).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, `extern "C"`, no C++/torch types.  Every entry point
+ * names the reference interface it replaces (paths relative to the chungongyu/siga tree).  The reference has no
+ * FFI of its own; the seams are SuffixArrayBuilder::build (+ BWT ctor), FMIndex::load/getOcc
+ * and the body of parallel::foreach in OverlapBuilder::build.  INTEGRATION.md shows the C++ stubs a maintainer adds.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative SGX_E* code on failure; sgx_last_error() gives the text.
+ *   - there is NO CPU fallback: if no CUDA device / kernel image is usable, sgx_init fails with SGX_ENODEV.
+ *   - one sgx_ctx per GPU (one process or thread per GPU); calls on one ctx are not re-entrant.
+ *   - inputs are borrowed for the duration of the call; outputs are owned by the library (pinned host memory)
+ *     and released with the matching *_free.
+ *   - symbol ranks follow src/alphabet.h:13-39: '$'=0 'A'=1 'C'=2 'G'=3 'T'=4.
+ */
+#ifndef SIGA_B200_H_
+#define SIGA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGX_ABI_VERSION 1
+
+enum {
+  SGX_OK = 0,
+  SGX_EINVAL = -1,   /* bad argument (null pointer, empty read, non-ACGT base, ...)        */
+  SGX_ENODEV = -2,   /* no usable CUDA device / sm_100a kernel image -- never falls back    */
+  SGX_ECUDA = -3,    /* a CUDA runtime call or kernel failed                                */
+  SGX_ENOMEM = -4,   /* device or pinned-host allocation failed                             */
+  SGX_EOVERFLOW = -5 /* an on-device work area overflowed even after the regrow-and-retry   */
+};
+
+/* Suffix ordering models of the two reference builders. */
+enum {
+  SGX_ORDER_SAIS = 0, /* `-a sais`  (SAISBuilder, src/suffix_array_builder.cpp:31-282): ties by read index   */
+  SGX_ORDER_SAIS2 = 1 /* `-a sais2` (NewSAISBuilder, src/suffix_array_builder.cpp:474-673, the default):
+                         plain suffix array of R0$R1$...$, all '$' equal, end of text smallest                */
+};
+
+/* AlignFlags bits, src/overlap_builder.cpp:42-44. */
+enum { SGX_AF_QUERYREV = 1, SGX_AF_TARGETREV = 2, SGX_AF_QUERYCOMP = 4 };
+
+typedef struct sgx_ctx sgx_ctx;
+typedef struct sgx_reads sgx_reads;
+typedef struct sgx_fm sgx_fm;
+
+/* ---- context ------------------------------------------------------------------------------------------ */
+
+int sgx_abi_version(void);
+/* Create a context on CUDA device `device`.  Replaces nothing in the reference (it has no device). */
+int sgx_init(int device, sgx_ctx** out);
+void sgx_shutdown(sgx_ctx* ctx);
+/* Text of the last error on this context (or of the last failed sgx_init when ctx == NULL). */
+const char* sgx_last_error(const sgx_ctx* ctx);
+/* Streaming-multiprocessor count of the context's device. */
+int sgx_sm_count(const sgx_ctx* ctx);
+
+/* ---- reads -------------------------------------------------------------------------------------------- */
+
+/*
+ * Pack `n` reads into the device read store (2 bits/base + lengths).  `ascii` holds the bases of all reads
+ * back to back, read i occupying [off[i], off[i+1]).  Replaces the in-memory DNASeqList produced by
+ * ReadDNASequences (src/kseq.cpp:230-257) as the input of both hot paths.
+ * Deviation (documented): bytes other than A/C/G/T and empty reads are rejected with
+ * SGX_EINVAL instead of being mapped to rank 0.
+ */
+int sgx_reads_pack(sgx_ctx* ctx, const char* ascii, const uint64_t* off, uint64_t n, sgx_reads** out);
+void sgx_reads_free(sgx_reads* reads);
+uint64_t sgx_reads_count(const sgx_reads* reads);
+uint64_t sgx_reads_bases(const sgx_reads* reads);
+
+/* ---- index construction (`siga index`) ------------------------------------------------------------------ */
+
+typedef struct sgx_index_out {
+  uint64_t n_strings;  /* reads                                   (.bwt header field 2, src/bwt.cpp:139-150)   */
+  uint64_t n_suffixes; /* bases + reads = BWT length              (.bwt header field 3)                        */
+  uint64_t n_runs;     /* run bytes                               (.bwt header field 4)                        */
+  uint8_t* rle;        /* n_runs bytes, (rank<<5)|count, greedy-31 (src/rlstring.h:10-13, src/bwt.cpp:16-27)   */
+  uint32_t* sai;       /* n_strings read ids in the order of the read-start suffixes = the `<i> 0` lines of the
+                          .sai file (src/suffix_array.cpp:16-43)                                               */
+  double ms_total;     /* device time of the whole build (CUDA events on the ctx stream)                       */
+  double ms_sort;      /* read ordering (sentinel order / .sai)                                                */
+  double ms_bcr;       /* column-insertion passes                                                              */
+  double ms_emit;      /* run-length encoding + copies out                                                     */
+  uint64_t launches;   /* kernels launched by this call                                                        */
+  uint64_t merge_launches; /* launches of the dominant (merge) kernel                                          */
+  double ms_merge;     /* device time spent in the merge kernel                                                */
+  uint64_t merge_bytes;/* bytes it read + wrote (algorithmic traffic of the merge passes)                      */
+} sgx_index_out;
+
+/*
+ * Build the BWT and the lexicographic read index of `reads` (or of the reversed reads when reversed != 0,
+ * the reference's .rbwt/.rsai, src/indexer.cpp:60-64).  Replaces SuffixArrayBuilder::create(name)->build()
+ * (src/suffix_array_builder.h:10-16, .cpp:684-693) + BWT::BWT(sa, reads) (src/bwt.cpp:7-32): the caller writes
+ * the 30-byte header + rle as .bwt and the sai list as .sai and obtains files byte-identical to the reference.
+ */
+int sgx_index_build(sgx_ctx* ctx, const sgx_reads* reads, int order, int reversed, sgx_index_out* out);
+void sgx_index_out_free(sgx_index_out* out);
+
+/* ---- FM-index (`FMIndex::load`, rank queries) ----------------------------------------------------------- */
+
+/*
+ * Build the device rank structure from the run bytes of a .bwt file.  Replaces FMIndex::load / initialize
+ * (src/fmindex.cpp:124-161, 347-366): the reference's large/small markers are never stored on disk, so the
+ * in-memory layout is free; ours is one 128-byte block per 256 symbols.
+ */
+int sgx_fm_create(sgx_ctx* ctx, const uint8_t* rle, uint64_t n_runs, uint64_t n_suffixes, sgx_fm** out);
+void sgx_fm_free(sgx_fm* fm);
+uint64_t sgx_fm_length(const sgx_fm* fm);
+/* C[] of FMIndex::getPC (src/fmindex.h:129-131): pred[c] = number of symbols with rank < c. */
+int sgx_fm_pred(const sgx_fm* fm, uint64_t pred[5]);
+/*
+ * Batched FMIndex::getOcc(i) (src/fmindex.cpp:320-323): counts[5*k..5*k+4] = occurrences of $,A,C,G,T in
+ * BWT[0..pos[k]] inclusive; pos == UINT64_MAX gives zeros exactly as the reference's wrap-around does.
+ */
+int sgx_fm_occ(sgx_ctx* ctx, const sgx_fm* fm, const uint64_t* pos, uint64_t n, uint64_t* counts);
+/*
+ * Batched FMIndex::Interval::occurrences (src/fmindex.h:67-86): number of occurrences of each query string
+ * (queries given like sgx_reads_pack's input).  Used by `correct`/`match`/`preqc` style callers.
+ */
+int sgx_fm_count(sgx_ctx* ctx, const sgx_fm* fm, const char* ascii, const uint64_t* off, uint64_t n, uint64_t* counts);
+
+/* ---- overlap search (`siga overlap`) -------------------------------------------------------------------- */
+
+/* One OverlapBlock (src/overlap_builder.cpp:151-196) exactly as the reference serialises it into .hits. */
+typedef struct sgx_block {
+  uint64_t capped[4]; /* capped[0].lower, capped[0].upper, capped[1].lower, capped[1].upper */
+  uint64_t raw[4];    /* raw[0].lower,    raw[0].upper,    raw[1].lower,    raw[1].upper    */
+  uint32_t length;    /* overlap length                                                     */
+  uint32_t af;        /* SGX_AF_* bits                                                      */
+} sgx_block;
+
+typedef struct sgx_hits {
+  uint64_t n_reads;
+  uint8_t* substring;   /* n_reads flags: OverlapResult.substring (src/overlap_builder.cpp:211-216)            */
+  uint64_t* block_off;  /* n_reads + 1 offsets into blocks                                                     */
+  sgx_block* blocks;    /* blocks of read i: [block_off[i], block_off[i+1]) (order within a read is free)      */
+  uint64_t n_blocks;
+  double ms_total;      /* device time of the call incl. copies (CUDA events)                                  */
+  double ms_search;     /* the four-way backward search kernel                                                 */
+  double ms_extract;    /* sub-maximal filter + irreducible extraction kernel                                  */
+  uint64_t lookups_search;  /* executed 128-byte rank-block fetches in the search kernel                       */
+  uint64_t lookups_extract; /* executed rank-block fetches in filter/extraction                                */
+  uint64_t launches;    /* kernels launched by this call                                                       */
+  uint64_t search_launches;
+} sgx_hits;
+
+/*
+ * Overlap blocks of reads [first, first+count) of `reads` against the forward and reverse FM-indices.
+ * Replaces the body of parallel::foreach in OverlapBuilder::build (src/overlap_builder.cpp:453-457), i.e.
+ * OverlapBuilder::overlap (src/overlap_builder.cpp:1113-1182) per read: four OverlapBlockFinder::find passes,
+ * SubMaximalBlockFilter, ContainmentBlockRemover, and (irreducible != 0) IrreducibleBlockListExtractor.
+ * rc != 0 searches the reverse complement too (the default; `--no-opposite-strand` clears it).
+ */
+int sgx_overlap_batch(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const sgx_reads* reads, uint64_t first,
+                      uint64_t count, uint32_t min_overlap, int irreducible, int rc, sgx_hits* out);
+void sgx_hits_free(sgx_hits* hits);
+
+/*
+ * Same, with the reads given in HOST memory (end-to-end entry: pack + H2D + search + D2H inside the call).
+ */
+int sgx_overlap_host(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const char* ascii, const uint64_t* off,
+                     uint64_t n, uint32_t min_overlap, int irreducible, int rc, sgx_hits* out);
+
+/* ---- measurement helpers --------------------------------------------------------------------------------- */
+
+/*
+ * Random 128-byte gather micro-benchmark: `n_loads` independent uniformly random
+ * 128-byte-aligned block fetches over a `bytes`-sized buffer; returns fetches per second.
+ */
+int sgx_bench_gather(sgx_ctx* ctx, uint64_t bytes, uint64_t n_loads, double* fetches_per_s);
+/* Write > L2-size bytes so that the next timed kernel starts with a cold L2. */
+int sgx_flush_l2(sgx_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SIGA_B200_H_ */

@@ -1,0 +1,141 @@
+"""SGA/SIGA on-disk formats of the hot path: readers, writers and the hits -> ED step.
+
+Host-side mirror in Python of what the reference's writers/readers do; used by the tests and bench.  The product
+CLI (siga_b200/csrc/host) implements the same formats in C++.
+"""
+import gzip
+import struct
+
+import numpy as np
+
+BWT_MAGIC = 0xCACA
+AF_QUERYREV, AF_TARGETREV, AF_QUERYCOMP = 1, 2, 4
+
+
+def read_bwt(path):
+    """-> (n_strings, n_suffixes, runs uint8 array).  Layout: src/bwt.cpp:34-39, 121-178."""
+    with open(path, "rb") as f:
+        data = f.read()
+    magic, n_strings, n_suffixes, n_runs, flag = struct.unpack_from("<HQQQi", data, 0)
+    if magic != BWT_MAGIC:
+        raise ValueError("bad .bwt magic")
+    runs = np.frombuffer(data, dtype=np.uint8, offset=30, count=n_runs).copy()
+    return n_strings, n_suffixes, runs
+
+
+def bwt_bytes(n_strings, n_suffixes, runs):
+    """The exact byte image BWTWriter produces (src/bwt.cpp:121-178)."""
+    runs = np.ascontiguousarray(runs, dtype=np.uint8)
+    return struct.pack("<HQQQi", BWT_MAGIC, n_strings, n_suffixes, len(runs), 0) + runs.tobytes()
+
+
+def decode_runs(runs):
+    """Run bytes -> symbol ranks (uint8, 0..4)."""
+    runs = np.asarray(runs, dtype=np.uint8)
+    return np.repeat(runs >> 5, runs & 31).astype(np.uint8)
+
+
+def encode_runs(sym):
+    """Greedy run-length coding with runs capped at 31 (src/bwt.cpp:16-27, src/rlstring.h:10-13)."""
+    sym = np.asarray(sym, dtype=np.uint8)
+    if len(sym) == 0:
+        return np.zeros(0, dtype=np.uint8)
+    starts = np.flatnonzero(np.concatenate(([True], sym[1:] != sym[:-1])))
+    lens = np.diff(np.concatenate((starts, [len(sym)])))
+    full, rem = lens // 31, lens % 31
+    per = full + (rem > 0)
+    out = np.empty(int(per.sum()), dtype=np.uint8)
+    pos = np.concatenate(([0], np.cumsum(per)))[:-1]
+    s = sym[starts].astype(np.uint8) << 5
+    idx = np.repeat(np.arange(len(starts)), per)
+    k = np.arange(len(out)) - np.repeat(pos, per)
+    cnt = np.where(k < full[idx], 31, rem[idx]).astype(np.uint8)
+    out[:] = s[idx] | cnt
+    return out
+
+
+def read_sai(path):
+    """-> uint32 array of read ids (the `<i> 0` lines).  Layout: src/suffix_array.cpp:16-43."""
+    with open(path, "rb") as f:
+        tok = f.read().split()
+    if int(tok[0]) != BWT_MAGIC:
+        raise ValueError("bad .sai magic")
+    n = int(tok[1])
+    ids = np.array(tok[3::2], dtype=np.uint64).astype(np.uint32)
+    assert len(ids) == n
+    return ids
+
+
+def sai_bytes(ids):
+    """The exact text image SAWriter produces: magic, n, n, then `<i> 0` per read (src/suffix_array.cpp:16-43)."""
+    ids = np.asarray(ids)
+    head = b"%d\n%d\n%d\n" % (BWT_MAGIC, len(ids), len(ids))
+    body = b"".join(b"%d 0\n" % int(i) for i in ids)
+    return head + body
+
+
+def read_hits(paths):
+    """Parse reference `<prefix>-thread<t>.hits.gz` files (src/overlap_builder.cpp:138-141,198-201,234-254).
+
+    -> dict read_idx -> (substring flag, list of (c0lo,c0hi,c1lo,c1hi,r0lo,r0hi,r1lo,r1hi,len,af))"""
+    out = {}
+    for p in paths:
+        with gzip.open(p, "rt") as f:
+            for line in f:
+                t = line.split()
+                if not t:
+                    continue
+                idx, sub, nb = int(t[0]), int(t[1]), int(t[2])
+                blocks = []
+                k = 3
+                for _ in range(nb):
+                    v = [int(x) for x in t[k:k + 9]]
+                    af = int(t[k + 9], 2)  # bitset<3> prints QC TR QR (MSB first)
+                    blocks.append(tuple(v) + (af,))
+                    k += 10
+                out[idx] = (sub, blocks)
+    return out
+
+
+def hits_to_edges(names, lengths, substring, block_off, blocks, sai, rsai):
+    """Hit2OverlapConverter::convert + OverlapBlock::overlap (src/overlap_builder.cpp:158-175, 345-375).
+
+    blocks: structured array with fields capped(4), raw(4), length, af.  -> list of ED payload strings."""
+    edges = []
+    for q in range(len(names)):
+        qn, ql = names[q], int(lengths[q])
+        for b in blocks[int(block_off[q]):int(block_off[q + 1])]:
+            ln, af = int(b["length"]), int(b["af"])
+            lo, hi = int(b["capped"][0]), int(b["capped"][1])
+            sa = rsai if af & AF_TARGETREV else sai
+            for j in range(lo, hi + 1):
+                t = int(sa[j])
+                tn, tl = names[t], int(lengths[t])
+                if qn == tn:
+                    continue
+                s0, e0 = ql - ln, ql - 1
+                s1, e1 = 0, ln - 1
+                if af & AF_QUERYREV:
+                    s0, e0 = ql - 1 - e0, ql - 1 - s0
+                if af & AF_TARGETREV:
+                    s1, e1 = tl - 1 - e1, tl - 1 - s1
+                contained = (s0 == 0 and e0 + 1 == ql) or (s1 == 0 and e1 + 1 == tl)
+                if qn < tn or (contained and (af & AF_QUERYREV)):
+                    continue
+                edges.append("%s %s %d %d %d %d %d %d %d 0" % (qn, tn, s0, e0, ql, s1, e1, tl, 1 if af & AF_QUERYCOMP else 0))
+    return edges
+
+
+def asqg_lines(names, seqs, substring, edges, min_overlap):
+    """HT / VT / ED lines exactly as OverlapBuilder::build emits them (src/overlap_builder.cpp:428-437, 301-322,
+    410-413; src/asqg.cpp:93-124, 171-186, 228-237)."""
+    out = ["HT\tVN:i:1\tOL:i:%d\tCN:i:1" % min_overlap]
+    for n, s, ss in zip(names, seqs, substring):
+        out.append("VT\t%s\t%s\tSS:i:%d" % (n, s, 1 if ss else 0))
+    out.extend("ED\t" + e for e in edges)
+    return out
+
+
+def read_asqg(path):
+    with gzip.open(path, "rt") as f:
+        return [l.rstrip("\n") for l in f]
