@@ -1,0 +1,43 @@
+# Build of the siga_b200 product library, the host CLI, the test-only host stand-in and the oracle.
+#   make            -> siga_b200/libsiga_b200.so + siga_b200/bin/siga
+#   make hostemu    -> build/libhostemu.so (tests only)
+#   make oracle     -> oracle/liboracle.so (+ oracle/_ref/siga when /root/reference is present)
+NVCC      ?= /usr/local/cuda/bin/nvcc
+HOSTCXX   ?= /usr/bin/g++
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := -std=c++17 -O3 -lineinfo $(ARCH) -ccbin $(HOSTCXX) -Xcompiler -fPIC,-Wall,-Wextra -Xptxas -v --expt-relaxed-constexpr
+CSRC      := siga_b200/csrc
+CU        := $(CSRC)/abi.cu $(CSRC)/reads.cu $(CSRC)/fm.cu $(CSRC)/overlap.cu $(CSRC)/index.cu
+OBJ       := $(patsubst $(CSRC)/%.cu,build/obj/%.o,$(CU))
+HDR       := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh include/*.h)
+LIB       := siga_b200/libsiga_b200.so
+
+all: $(LIB) cli
+
+build/obj/%.o: $(CSRC)/%.cu $(HDR)
+	@mkdir -p build/obj
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/obj/$*.ptxas.log || (cat build/obj/$*.ptxas.log; exit 1)
+	@grep -E "error|warning" build/obj/$*.ptxas.log | grep -v "ptxas info" || true
+
+$(LIB): $(OBJ)
+	$(NVCC) -shared $(ARCH) -ccbin $(HOSTCXX) -o $@ $(OBJ) -lcudart_static -lpthread -ldl -lrt
+
+cli: siga_b200/bin/siga
+siga_b200/bin/siga: $(wildcard $(CSRC)/host/*.cpp $(CSRC)/host/*.h) include/siga_b200.h $(LIB)
+	@mkdir -p siga_b200/bin
+	@if ls $(CSRC)/host/*.cpp >/dev/null 2>&1; then \
+	  $(HOSTCXX) -std=c++17 -O2 -Wall -Wextra -Iinclude $(CSRC)/host/*.cpp -o $@ -Lsiga_b200 -lsiga_b200 -lz -lpthread -Wl,-rpath,'$$ORIGIN/..'; \
+	else echo "no host CLI sources yet"; fi
+
+hostemu: build/libhostemu.so
+build/libhostemu.so: tests/hostemu/hostemu.cpp $(HDR)
+	@mkdir -p build
+	$(HOSTCXX) -std=c++14 -O2 -Wall -Wextra -shared -fPIC $< -o $@
+
+oracle:
+	$(MAKE) -C oracle
+
+clean:
+	rm -rf build/obj $(LIB) siga_b200/bin build/libhostemu.so
+
+.PHONY: all cli hostemu oracle clean

@@ -1,0 +1,257 @@
+"""ctypes binding of libsiga_b200.so (include/siga_b200.h) -- the only way Python reaches the hot path.
+
+There is no CPU fallback: if the shared library is missing, or no B200-class device is usable, this module raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsiga_b200.so")
+
+ORDER_SAIS, ORDER_SAIS2 = 0, 1
+AF_QUERYREV, AF_TARGETREV, AF_QUERYCOMP = 1, 2, 4
+
+BLOCK_DTYPE = np.dtype([("capped", "<u8", (4,)), ("raw", "<u8", (4,)), ("length", "<u4"), ("af", "<u4")])
+assert BLOCK_DTYPE.itemsize == 72
+
+# Every symbol include/siga_b200.h declares (checked by the CPU tests against the built library).
+ABI_SYMBOLS = [
+    "sgx_abi_version", "sgx_init", "sgx_shutdown", "sgx_last_error", "sgx_sm_count",
+    "sgx_reads_pack", "sgx_reads_free", "sgx_reads_count", "sgx_reads_bases",
+    "sgx_index_build", "sgx_index_out_free",
+    "sgx_fm_create", "sgx_fm_free", "sgx_fm_length", "sgx_fm_pred", "sgx_fm_occ", "sgx_fm_count",
+    "sgx_overlap_batch", "sgx_overlap_host", "sgx_hits_free",
+    "sgx_bench_gather", "sgx_flush_l2",
+]
+
+
+class SgxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("siga_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class _IndexOut(ctypes.Structure):
+    _fields_ = [("n_strings", ctypes.c_uint64), ("n_suffixes", ctypes.c_uint64), ("n_runs", ctypes.c_uint64),
+                ("rle", ctypes.POINTER(ctypes.c_uint8)), ("sai", ctypes.POINTER(ctypes.c_uint32)),
+                ("ms_total", ctypes.c_double), ("ms_sort", ctypes.c_double), ("ms_bcr", ctypes.c_double),
+                ("ms_emit", ctypes.c_double), ("launches", ctypes.c_uint64), ("merge_launches", ctypes.c_uint64),
+                ("ms_merge", ctypes.c_double), ("merge_bytes", ctypes.c_uint64)]
+
+
+class _Hits(ctypes.Structure):
+    _fields_ = [("n_reads", ctypes.c_uint64), ("substring", ctypes.POINTER(ctypes.c_uint8)),
+                ("block_off", ctypes.POINTER(ctypes.c_uint64)), ("blocks", ctypes.c_void_p),
+                ("n_blocks", ctypes.c_uint64), ("ms_total", ctypes.c_double), ("ms_search", ctypes.c_double),
+                ("ms_extract", ctypes.c_double), ("lookups_search", ctypes.c_uint64),
+                ("lookups_extract", ctypes.c_uint64), ("launches", ctypes.c_uint64),
+                ("search_launches", ctypes.c_uint64)]
+
+
+_lib = None
+
+
+def load_library():
+    """Load libsiga_b200.so; raises (loudly) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError("%s is missing: build it with `make` (or __graft_entry__.build()); "
+                          "siga_b200 has no CPU fallback" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, u64, u32, i32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int
+    lib.sgx_abi_version.restype = i32
+    lib.sgx_init.argtypes = [i32, ctypes.POINTER(vp)]
+    lib.sgx_shutdown.argtypes = [vp]
+    lib.sgx_shutdown.restype = None
+    lib.sgx_last_error.argtypes = [vp]
+    lib.sgx_last_error.restype = ctypes.c_char_p
+    lib.sgx_sm_count.argtypes = [vp]
+    lib.sgx_reads_pack.argtypes = [vp, vp, vp, u64, ctypes.POINTER(vp)]
+    lib.sgx_reads_free.argtypes = [vp]
+    lib.sgx_reads_free.restype = None
+    lib.sgx_reads_count.argtypes = [vp]
+    lib.sgx_reads_count.restype = u64
+    lib.sgx_reads_bases.argtypes = [vp]
+    lib.sgx_reads_bases.restype = u64
+    lib.sgx_index_build.argtypes = [vp, vp, i32, i32, ctypes.POINTER(_IndexOut)]
+    lib.sgx_index_out_free.argtypes = [ctypes.POINTER(_IndexOut)]
+    lib.sgx_index_out_free.restype = None
+    lib.sgx_fm_create.argtypes = [vp, vp, u64, u64, ctypes.POINTER(vp)]
+    lib.sgx_fm_free.argtypes = [vp]
+    lib.sgx_fm_free.restype = None
+    lib.sgx_fm_length.argtypes = [vp]
+    lib.sgx_fm_length.restype = u64
+    lib.sgx_fm_pred.argtypes = [vp, ctypes.POINTER(u64 * 5)]
+    lib.sgx_fm_occ.argtypes = [vp, vp, vp, u64, vp]
+    lib.sgx_fm_count.argtypes = [vp, vp, vp, vp, u64, vp]
+    lib.sgx_overlap_batch.argtypes = [vp, vp, vp, vp, u64, u64, u32, i32, i32, ctypes.POINTER(_Hits)]
+    lib.sgx_overlap_host.argtypes = [vp, vp, vp, vp, vp, u64, u32, i32, i32, ctypes.POINTER(_Hits)]
+    lib.sgx_hits_free.argtypes = [ctypes.POINTER(_Hits)]
+    lib.sgx_hits_free.restype = None
+    lib.sgx_bench_gather.argtypes = [vp, u64, u64, ctypes.POINTER(ctypes.c_double)]
+    lib.sgx_flush_l2.argtypes = [vp]
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class IndexResult:
+    """Run bytes + read-start order of one index (what the .bwt / .sai files are written from)."""
+
+    def __init__(self, o):
+        self.n_strings = int(o.n_strings)
+        self.n_suffixes = int(o.n_suffixes)
+        self.runs = np.ctypeslib.as_array(o.rle, shape=(max(int(o.n_runs), 1),))[:int(o.n_runs)].copy()
+        self.sai = np.ctypeslib.as_array(o.sai, shape=(self.n_strings,)).copy()
+        self.stats = dict(ms_total=o.ms_total, ms_sort=o.ms_sort, ms_bcr=o.ms_bcr, ms_emit=o.ms_emit,
+                          launches=int(o.launches), merge_launches=int(o.merge_launches), ms_merge=o.ms_merge,
+                          merge_bytes=int(o.merge_bytes))
+
+
+class Hits:
+    def __init__(self, h, copy=True):
+        n = int(h.n_reads)
+        nb = int(h.n_blocks)
+        self.n_reads = n
+        sub = np.ctypeslib.as_array(h.substring, shape=(max(n, 1),))[:n]
+        off = np.ctypeslib.as_array(h.block_off, shape=(n + 1,))
+        buf = (ctypes.c_uint8 * (max(nb, 1) * BLOCK_DTYPE.itemsize)).from_address(h.blocks)
+        blocks = np.frombuffer(buf, dtype=BLOCK_DTYPE)[:nb]
+        if copy:
+            sub, off, blocks = sub.copy(), off.copy(), blocks.copy()
+        self.substring, self.block_off, self.blocks = sub, off, blocks
+        self.stats = dict(ms_total=h.ms_total, ms_search=h.ms_search, ms_extract=h.ms_extract,
+                          lookups_search=int(h.lookups_search), lookups_extract=int(h.lookups_extract),
+                          launches=int(h.launches), search_launches=int(h.search_launches), n_blocks=nb)
+
+    def read_blocks(self, i):
+        """Sorted tuples (capped x4, raw x4, length, af) of read i -- the form the reference's .hits lines parse to."""
+        b = self.blocks[int(self.block_off[i]):int(self.block_off[i + 1])]
+        return sorted(tuple(int(x) for x in r["capped"]) + tuple(int(x) for x in r["raw"]) + (int(r["length"]), int(r["af"]))
+                      for r in b)
+
+
+class Context:
+    """One sgx_ctx = one GPU."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = ctypes.c_void_p()
+        rc = self.lib.sgx_init(int(device), ctypes.byref(h))
+        if rc != 0:
+            raise SgxError(rc, self.lib.sgx_last_error(None).decode())
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sgx_shutdown(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise SgxError(rc, self.lib.sgx_last_error(self.h).decode())
+
+    @property
+    def sm_count(self):
+        return int(self.lib.sgx_sm_count(self.h))
+
+    # ---- reads
+    def pack_reads(self, flat, off):
+        flat = np.ascontiguousarray(flat, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        r = ctypes.c_void_p()
+        self._check(self.lib.sgx_reads_pack(self.h, _ptr(flat), _ptr(off), len(off) - 1, ctypes.byref(r)))
+        return r
+
+    def free_reads(self, r):
+        self.lib.sgx_reads_free(r)
+
+    # ---- index
+    def index_build(self, reads, order=ORDER_SAIS2, reversed=False):
+        o = _IndexOut()
+        self._check(self.lib.sgx_index_build(self.h, reads, int(order), 1 if reversed else 0, ctypes.byref(o)))
+        res = IndexResult(o)
+        self.lib.sgx_index_out_free(ctypes.byref(o))
+        return res
+
+    # ---- FM-index
+    def fm_create(self, runs, n_suffixes):
+        runs = np.ascontiguousarray(runs, dtype=np.uint8)
+        f = ctypes.c_void_p()
+        self._check(self.lib.sgx_fm_create(self.h, _ptr(runs), len(runs), int(n_suffixes), ctypes.byref(f)))
+        return f
+
+    def free_fm(self, f):
+        self.lib.sgx_fm_free(f)
+
+    def fm_pred(self, f):
+        p = (ctypes.c_uint64 * 5)()
+        self._check(self.lib.sgx_fm_pred(f, ctypes.byref(p)))
+        return [int(x) for x in p]
+
+    def fm_occ(self, f, pos):
+        pos = np.ascontiguousarray(pos, dtype=np.uint64)
+        out = np.zeros((len(pos), 5), dtype=np.uint64)
+        self._check(self.lib.sgx_fm_occ(self.h, f, _ptr(pos), len(pos), _ptr(out)))
+        return out
+
+    def fm_count(self, f, flat, off):
+        flat = np.ascontiguousarray(flat, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        out = np.zeros(len(off) - 1, dtype=np.uint64)
+        self._check(self.lib.sgx_fm_count(self.h, f, _ptr(flat), _ptr(off), len(off) - 1, _ptr(out)))
+        return out
+
+    # ---- overlap
+    def overlap(self, fwd, rev, reads, first, count, min_overlap, irreducible=True, rc=True, copy=True):
+        h = _Hits()
+        self._check(self.lib.sgx_overlap_batch(self.h, fwd, rev, reads, int(first), int(count), int(min_overlap),
+                                               1 if irreducible else 0, 1 if rc else 0, ctypes.byref(h)))
+        res = Hits(h, copy=copy)
+        if copy:
+            self.lib.sgx_hits_free(ctypes.byref(h))
+        else:
+            res._raw = h  # caller releases with free_hits
+        return res
+
+    def overlap_host(self, fwd, rev, flat, off, min_overlap, irreducible=True, rc=True, copy=True):
+        flat = np.ascontiguousarray(flat, dtype=np.uint8) if not isinstance(flat, int) else flat
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        h = _Hits()
+        p = ctypes.c_void_p(flat) if isinstance(flat, int) else _ptr(flat)
+        self._check(self.lib.sgx_overlap_host(self.h, fwd, rev, p, _ptr(off), len(off) - 1, int(min_overlap),
+                                              1 if irreducible else 0, 1 if rc else 0, ctypes.byref(h)))
+        res = Hits(h, copy=copy)
+        if copy:
+            self.lib.sgx_hits_free(ctypes.byref(h))
+        else:
+            res._raw = h
+        return res
+
+    def free_hits(self, hits):
+        if getattr(hits, "_raw", None) is not None:
+            self.lib.sgx_hits_free(ctypes.byref(hits._raw))
+            hits._raw = None
+
+    # ---- measurement helpers
+    def bench_gather(self, nbytes, n_loads):
+        out = ctypes.c_double()
+        self._check(self.lib.sgx_bench_gather(self.h, int(nbytes), int(n_loads), ctypes.byref(out)))
+        return out.value
+
+    def flush_l2(self):
+        self._check(self.lib.sgx_flush_l2(self.h))

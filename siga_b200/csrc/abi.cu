@@ -1,0 +1,309 @@
+// extern "C" entry points of libsiga_b200.so (include/siga_b200.h).  Thin: argument checks, error mapping, timing.
+#include <mutex>
+#include <new>
+#include <unordered_map>
+
+#include "index.cuh"
+#include "overlap.cuh"
+
+static std::string g_init_error;
+static std::mutex g_pin_mutex;
+static std::unordered_map<void*, std::pair<sgx_ctx*, size_t> > g_pin_owner;
+
+void sgx_set_error(sgx_ctx* ctx, const char* msg) {
+  if (ctx) {
+    ctx->err = msg;
+  } else {
+    g_init_error = msg;
+  }
+}
+
+namespace sgx {
+
+void* pinned_get(sgx_ctx* ctx, size_t bytes) {
+  if (bytes == 0) bytes = 1;
+  {
+    std::lock_guard<std::mutex> lk(g_pin_mutex);
+    size_t best = (size_t)-1;
+    for (size_t i = 0; i < ctx->pinned_free.size(); ++i) {
+      if (ctx->pinned_free[i].second >= bytes &&
+          (best == (size_t)-1 || ctx->pinned_free[i].second < ctx->pinned_free[best].second))
+        best = i;
+    }
+    if (best != (size_t)-1 && ctx->pinned_free[best].second <= 2 * bytes + (1u << 20)) {
+      void* p = ctx->pinned_free[best].first;
+      ctx->pinned_free.erase(ctx->pinned_free.begin() + best);
+      return p;
+    }
+  }
+  void* p = nullptr;
+  SGX_CUDA(cudaMallocHost(&p, bytes));
+  std::lock_guard<std::mutex> lk(g_pin_mutex);
+  g_pin_owner[p] = std::make_pair(ctx, bytes);
+  return p;
+}
+
+void pinned_put(void* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_pin_mutex);
+  auto it = g_pin_owner.find(p);
+  if (it == g_pin_owner.end()) return;
+  it->second.first->pinned_free.push_back(std::make_pair(p, it->second.second));
+}
+
+__global__ void probe_kernel(int* out) {
+  if (out) *out = 1;
+}
+
+// Each thread issues `per_thread` dependent-free random 16-byte loads, 8 consecutive lanes covering one 128-byte
+// line, i.e. the access shape of a rank query without the arithmetic.
+__global__ void __launch_bounds__(256) gather_kernel(const uint4* __restrict__ buf, uint64_t n_lines, uint64_t per_group,
+                                                     uint64_t seed, unsigned long long* __restrict__ sink) {
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t gid = tid >> 3;
+  const int lane = (int)(tid & 7);
+  uint64_t x = seed ^ (gid * 0x9E3779B97F4A7C15ull);
+  uint32_t acc = 0;
+  for (uint64_t i = 0; i < per_group; i += 4) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      x ^= x << 13;
+      x ^= x >> 7;
+      x ^= x << 17;
+      const uint64_t line = x % n_lines;
+      v[u] = __ldg(buf + line * 8 + lane);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc += v[u].x ^ v[u].w;
+  }
+  if (acc == 0x12345678u) atomicAdd(sink, 1ull);
+}
+
+__global__ void fill_kernel(uint4* buf, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t k = i; k < n; k += stride) buf[k] = make_uint4((uint32_t)k, 1u, 2u, 3u);
+}
+
+}  // namespace sgx
+
+using namespace sgx;
+
+extern "C" {
+
+int sgx_abi_version(void) { return SGX_ABI_VERSION; }
+
+int sgx_init(int device, sgx_ctx** out) {
+  if (!out) return SGX_EINVAL;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_init_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libsiga_b200 has no CPU fallback)";
+    cudaGetLastError();
+    return SGX_ENODEV;
+  }
+  if (device < 0 || device >= count) {
+    g_init_error = "device index out of range";
+    return SGX_EINVAL;
+  }
+  sgx_ctx* ctx = nullptr;
+  try {
+    SGX_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SGX_CUDA(cudaGetDeviceProperties(&prop, device));
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, probe_kernel);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      char b[256];
+      snprintf(b, sizeof(b), "device %d (%s, sm_%d%d) cannot run the sm_100a kernel image: %s (no fallback)", device,
+               prop.name, prop.major, prop.minor, cudaGetErrorString(e));
+      g_init_error = b;
+      return SGX_ENODEV;
+    }
+    ctx = new sgx_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->l2_bytes = (size_t)prop.l2CacheSize;
+    ctx->launches = 0;
+    ctx->flush_buf = nullptr;
+    ctx->flush_bytes = 0;
+    SGX_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    probe_kernel<<<1, 1, 0, ctx->stream>>>(nullptr);
+    SGX_CUDA(cudaGetLastError());
+    SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+  } catch (const sgx::Error& err) {
+    g_init_error = err.msg;
+    delete ctx;
+    cudaGetLastError();
+    return err.code == SGX_ECUDA ? SGX_ENODEV : err.code;
+  }
+  *out = ctx;
+  return SGX_OK;
+}
+
+void sgx_shutdown(sgx_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  {
+    std::lock_guard<std::mutex> lk(g_pin_mutex);
+    for (auto it = g_pin_owner.begin(); it != g_pin_owner.end();) {
+      if (it->second.first == ctx) {
+        cudaFreeHost(it->first);
+        it = g_pin_owner.erase(it);
+      } else {
+        ++it;
+      }
+    }
+  }
+  if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* sgx_last_error(const sgx_ctx* ctx) { return ctx ? ctx->err.c_str() : g_init_error.c_str(); }
+
+int sgx_sm_count(const sgx_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+int sgx_reads_pack(sgx_ctx* ctx, const char* ascii, const uint64_t* off, uint64_t n, sgx_reads** out) {
+  if (!ctx || !out) return SGX_EINVAL;
+  SGX_ENTRY_BEGIN(ctx)
+  *out = reads_pack(ctx, ascii, off, n);
+  SGX_ENTRY_END(ctx)
+}
+
+void sgx_reads_free(sgx_reads* reads) {
+  if (reads) cudaSetDevice(reads->ctx->device);
+  reads_destroy(reads);
+}
+
+uint64_t sgx_reads_count(const sgx_reads* reads) { return reads ? reads->n : 0; }
+uint64_t sgx_reads_bases(const sgx_reads* reads) { return reads ? reads->bases : 0; }
+
+int sgx_index_build(sgx_ctx* ctx, const sgx_reads* reads, int order, int reversed, sgx_index_out* out) {
+  if (!ctx || !reads || !out) return SGX_EINVAL;
+  SGX_ENTRY_BEGIN(ctx)
+  SGX_REQUIRE(order == SGX_ORDER_SAIS || order == SGX_ORDER_SAIS2, SGX_EINVAL, "sgx_index_build: unknown order");
+  index_build(ctx, reads, order, reversed != 0, out);
+  SGX_ENTRY_END(ctx)
+}
+
+void sgx_index_out_free(sgx_index_out* out) {
+  if (!out) return;
+  pinned_put(out->rle);
+  pinned_put(out->sai);
+  out->rle = nullptr;
+  out->sai = nullptr;
+}
+
+int sgx_fm_create(sgx_ctx* ctx, const uint8_t* rle, uint64_t n_runs, uint64_t n_suffixes, sgx_fm** out) {
+  if (!ctx || !out || (!rle && n_runs)) return SGX_EINVAL;
+  SGX_ENTRY_BEGIN(ctx)
+  DevBuf<uint8_t> d_rle(n_runs ? n_runs : 1), d_sym(n_suffixes ? n_suffixes + 32 : 32);
+  if (n_runs) SGX_CUDA(cudaMemcpyAsync(d_rle.p, rle, n_runs, cudaMemcpyHostToDevice, ctx->stream));
+  rle_expand(ctx, d_rle.p, n_runs, n_suffixes, d_sym.p);
+  *out = fm_build_from_symbols(ctx, d_sym.p, n_suffixes);
+  SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+  SGX_ENTRY_END(ctx)
+}
+
+void sgx_fm_free(sgx_fm* fm) {
+  if (!fm) return;
+  cudaSetDevice(fm->ctx->device);
+  cudaFree(fm->blocks);
+  delete fm;
+}
+
+uint64_t sgx_fm_length(const sgx_fm* fm) { return fm ? fm->n : 0; }
+
+int sgx_fm_pred(const sgx_fm* fm, uint64_t pred[5]) {
+  if (!fm || !pred) return SGX_EINVAL;
+  for (int i = 0; i < 5; ++i) pred[i] = fm->pred[i];
+  return SGX_OK;
+}
+
+int sgx_fm_occ(sgx_ctx* ctx, const sgx_fm* fm, const uint64_t* pos, uint64_t n, uint64_t* counts) {
+  if (!ctx || !fm || (!pos && n) || (!counts && n)) return SGX_EINVAL;
+  SGX_ENTRY_BEGIN(ctx)
+  fm_occ_batch(ctx, fm, pos, n, counts);
+  SGX_ENTRY_END(ctx)
+}
+
+int sgx_fm_count(sgx_ctx* ctx, const sgx_fm* fm, const char* ascii, const uint64_t* off, uint64_t n, uint64_t* counts) {
+  if (!ctx || !fm || !ascii || !off || (!counts && n)) return SGX_EINVAL;
+  SGX_ENTRY_BEGIN(ctx)
+  fm_count_batch(ctx, fm, ascii, off, n, counts);
+  SGX_ENTRY_END(ctx)
+}
+
+int sgx_overlap_batch(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const sgx_reads* reads, uint64_t first,
+                      uint64_t count, uint32_t min_overlap, int irreducible, int rc, sgx_hits* out) {
+  if (!ctx || !out) return SGX_EINVAL;
+  SGX_ENTRY_BEGIN(ctx)
+  overlap_run(ctx, fwd, rev, reads, first, count, min_overlap, irreducible, rc, out);
+  SGX_ENTRY_END(ctx)
+}
+
+int sgx_overlap_host(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const char* ascii, const uint64_t* off,
+                     uint64_t n, uint32_t min_overlap, int irreducible, int rc, sgx_hits* out) {
+  if (!ctx || !out) return SGX_EINVAL;
+  sgx_reads* reads = nullptr;
+  int rcode = sgx_reads_pack(ctx, ascii, off, n, &reads);
+  if (rcode != SGX_OK) return rcode;
+  rcode = sgx_overlap_batch(ctx, fwd, rev, reads, 0, n, min_overlap, irreducible, rc, out);
+  sgx_reads_free(reads);
+  return rcode;
+}
+
+void sgx_hits_free(sgx_hits* hits) {
+  if (!hits) return;
+  pinned_put(hits->substring);
+  pinned_put(hits->block_off);
+  pinned_put(hits->blocks);
+  hits->substring = nullptr;
+  hits->block_off = nullptr;
+  hits->blocks = nullptr;
+}
+
+int sgx_bench_gather(sgx_ctx* ctx, uint64_t bytes, uint64_t n_loads, double* fetches_per_s) {
+  if (!ctx || !fetches_per_s || bytes < 4096) return SGX_EINVAL;
+  SGX_ENTRY_BEGIN(ctx)
+  const uint64_t n_lines = bytes / 128;
+  DevBuf<uint4> buf(n_lines * 8);
+  DevBuf<unsigned long long> sink(1);
+  SGX_CUDA(cudaMemsetAsync(sink.p, 0, sizeof(unsigned long long), ctx->stream));
+  SGX_LAUNCH(ctx, fill_kernel, (unsigned)ctx->sm_count * 8, 256, 0, buf.p, n_lines * 8);
+  const unsigned grid = (unsigned)ctx->sm_count * 8;
+  const uint64_t groups = (uint64_t)grid * 256 / 8;
+  uint64_t per_group = (n_loads + groups - 1) / groups;
+  per_group = (per_group + 3) & ~3ull;
+  if (per_group < 4) per_group = 4;
+  SGX_LAUNCH(ctx, gather_kernel, grid, 256, 0, (const uint4*)buf.p, n_lines, per_group, 0x1234567ull, sink.p);  // warm-up
+  EventTimer t(ctx->stream);
+  t.start();
+  SGX_LAUNCH(ctx, gather_kernel, grid, 256, 0, (const uint4*)buf.p, n_lines, per_group, 0xABCDEF01ull, sink.p);
+  t.stop();
+  SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+  *fetches_per_s = (double)(groups * per_group) / (t.ms() * 1e-3);
+  SGX_ENTRY_END(ctx)
+}
+
+int sgx_flush_l2(sgx_ctx* ctx) {
+  if (!ctx) return SGX_EINVAL;
+  SGX_ENTRY_BEGIN(ctx)
+  const size_t want = std::max<size_t>(2 * ctx->l2_bytes, (size_t)256 << 20);
+  if (ctx->flush_bytes < want) {
+    if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+    ctx->flush_buf = nullptr;
+    SGX_CUDA(cudaMalloc(&ctx->flush_buf, want));
+    ctx->flush_bytes = want;
+  }
+  SGX_LAUNCH(ctx, fill_kernel, (unsigned)ctx->sm_count * 8, 256, 0, (uint4*)ctx->flush_buf, (uint64_t)(want / 16));
+  SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+  SGX_ENTRY_END(ctx)
+}
+
+}  // extern "C"

@@ -1,0 +1,222 @@
+// FM-index construction on the device: run bytes -> symbols -> 128-byte rank blocks (fm_layout.h).
+// Replaces FMIndex::initialize / MarkerFill (src/fmindex.cpp:17-161 of the reference).
+#include "fm.cuh"
+
+#include <algorithm>
+
+#include "reads.cuh"
+
+namespace sgx {
+
+__global__ void rle_count_kernel(const uint8_t* __restrict__ rle, uint64_t n_runs, uint64_t* __restrict__ cnt) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_runs) cnt[i] = rle[i] & 31u;
+}
+
+// One thread per run: writes its (<= 31) symbols.  Neighbouring threads write neighbouring byte ranges.
+__global__ void rle_expand_kernel(const uint8_t* __restrict__ rle, const uint64_t* __restrict__ start, uint64_t n_runs,
+                                  uint64_t n, uint8_t* __restrict__ sym) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_runs) return;
+  const uint8_t r = rle[i];
+  const uint8_t s = r >> 5;
+  const uint32_t c = r & 31u;
+  const uint64_t at = start[i];
+  for (uint32_t k = 0; k < c; ++k)
+    if (at + k < n) sym[at + k] = s;
+}
+
+void rle_expand(sgx_ctx* ctx, const uint8_t* rle_dev, uint64_t n_runs, uint64_t n_suffixes, uint8_t* sym_dev) {
+  if (n_runs == 0) {
+    SGX_REQUIRE(n_suffixes == 0, SGX_EINVAL, "rle_expand: no runs but n_suffixes != 0");
+    return;
+  }
+  DevBuf<uint64_t> start(n_runs), ws(scan_ws_elems(n_runs)), total(1);
+  SGX_LAUNCH(ctx, rle_count_kernel, grid_for(n_runs, 256), 256, 0, rle_dev, n_runs, start.p);
+  scan_exclusive(ctx, start.p, n_runs, ws.p, total.p);
+  uint64_t tot = 0;
+  SGX_CUDA(cudaMemcpyAsync(&tot, total.p, sizeof(tot), cudaMemcpyDeviceToHost, ctx->stream));
+  SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+  SGX_REQUIRE(tot == n_suffixes, SGX_EINVAL, "rle_expand: run lengths do not add up to n_suffixes");
+  SGX_LAUNCH(ctx, rle_expand_kernel, grid_for(n_runs, 256), 256, 0, rle_dev, (const uint64_t*)start.p, n_runs,
+             n_suffixes, sym_dev);
+}
+
+// Thread t builds lane t (32 symbols) of the block array and the groups of 8 threads reduce the block's A/C/G/T
+// counts into cnt[c*nb + b].
+__global__ void __launch_bounds__(256) fm_pack_kernel(const uint8_t* __restrict__ sym, uint64_t n, uint64_t nb,
+                                                      FmBlockLane* __restrict__ blocks, uint64_t* __restrict__ cnt) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t nlanes = nb * kGroup;
+  uint32_t p0 = 0, p1 = 0, p2 = 0;
+  uint32_t ca = 0, cc = 0, cg = 0, ct = 0;
+  if (t < nlanes) {
+    const uint64_t base = t * 32;
+    if (base + 32 <= n) {
+      const uint4 a = *reinterpret_cast<const uint4*>(sym + base);
+      const uint4 b = *reinterpret_cast<const uint4*>(sym + base + 16);
+      const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t s = (w[q] >> (8 * j)) & 0xffu;
+          const uint32_t bit = 1u << (4 * q + j);
+          if (s == 0) {
+            p2 |= bit;
+          } else {
+            const uint32_t code = s - 1;
+            if (code & 1) p0 |= bit;
+            if (code & 2) p1 |= bit;
+          }
+        }
+      }
+    } else {
+      for (int j = 0; j < 32; ++j) {
+        if (base + j >= n) break;
+        const uint32_t s = sym[base + j];
+        const uint32_t bit = 1u << j;
+        if (s == 0) {
+          p2 |= bit;
+        } else {
+          const uint32_t code = s - 1;
+          if (code & 1) p0 |= bit;
+          if (code & 2) p1 |= bit;
+        }
+      }
+    }
+    uint32_t valid = 0xffffffffu;
+    if (base + 32 > n) valid = base >= n ? 0u : ((1u << (uint32_t)(n - base)) - 1u);
+    const uint32_t nd = ~p2 & valid;
+    ca = __popc(nd & ~p1 & ~p0);
+    cc = __popc(nd & ~p1 & p0);
+    cg = __popc(nd & p1 & ~p0);
+    ct = __popc(nd & p1 & p0);
+    FmBlockLane l;
+    l.p0 = p0;
+    l.p1 = p1;
+    l.p2 = p2;
+    l.h = 0;
+    blocks[t] = l;
+  }
+  uint32_t w1 = ca | (cc << 16), w2 = cg | (ct << 16);
+#pragma unroll
+  for (int m = 1; m < kGroup; m <<= 1) {
+    w1 += __shfl_xor_sync(0xffffffffu, w1, m);
+    w2 += __shfl_xor_sync(0xffffffffu, w2, m);
+  }
+  if (t < nlanes && (t & (kGroup - 1)) == 0) {
+    const uint64_t b = t / kGroup;
+    cnt[0 * nb + b] = w1 & 0xffffu;
+    cnt[1 * nb + b] = w1 >> 16;
+    cnt[2 * nb + b] = w2 & 0xffffu;
+    cnt[3 * nb + b] = w2 >> 16;
+  }
+}
+
+// After the in-place scan of cnt (flattened [4][nb]), header word k of block b = 32-bit half of the count of symbol
+// k>>1 before block b.
+__global__ void fm_header_kernel(FmBlockLane* __restrict__ blocks, uint64_t nb, const uint64_t* __restrict__ scanned) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nb * kGroup) return;
+  const uint64_t b = t / kGroup;
+  const int k = (int)(t & (kGroup - 1));
+  const int c = k >> 1;
+  const uint64_t v = scanned[(uint64_t)c * nb + b] - scanned[(uint64_t)c * nb];
+  blocks[t].h = (k & 1) ? (uint32_t)(v >> 32) : (uint32_t)(v & 0xffffffffu);
+}
+
+sgx_fm* fm_build_from_symbols(sgx_ctx* ctx, const uint8_t* sym_dev, uint64_t n) {
+  const uint64_t nb = fm_num_blocks(n);
+  DevBuf<FmBlockLane> blocks(nb * kGroup);
+  DevBuf<uint64_t> cnt(4 * nb), ws(scan_ws_elems(4 * nb)), total(1);
+  SGX_LAUNCH(ctx, fm_pack_kernel, grid_for(nb * kGroup, 256), 256, 0, sym_dev, n, nb, blocks.p, cnt.p);
+  scan_exclusive(ctx, cnt.p, 4 * nb, ws.p, total.p);
+  SGX_LAUNCH(ctx, fm_header_kernel, grid_for(nb * kGroup, 256), 256, 0, blocks.p, nb, (const uint64_t*)cnt.p);
+  uint64_t b4[5];
+  for (int c = 0; c < 4; ++c)
+    SGX_CUDA(cudaMemcpyAsync(&b4[c], cnt.p + (uint64_t)c * nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  SGX_CUDA(cudaMemcpyAsync(&b4[4], total.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+  sgx_fm* fm = new sgx_fm();
+  fm->ctx = ctx;
+  fm->n = n;
+  uint64_t acgt = 0;
+  uint64_t cntc[5];
+  for (int c = 0; c < 4; ++c) {
+    cntc[c + 1] = b4[c + 1] - b4[c];
+    acgt += cntc[c + 1];
+  }
+  cntc[0] = n - acgt;
+  fm->pred[0] = 0;
+  for (int c = 1; c <= 5; ++c) fm->pred[c] = fm->pred[c - 1] + cntc[c - 1];
+  fm->blocks = blocks.take();
+  return fm;
+}
+
+
+// One 8-lane group per query position.
+__global__ void __launch_bounds__(256) fm_occ_kernel(FmView fm, const uint64_t* __restrict__ pos, uint64_t n,
+                                                     uint64_t* __restrict__ counts) {
+  const DevGroup g;
+  const uint64_t gid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / kGroup;
+  const uint64_t ngroups = ((uint64_t)gridDim.x * blockDim.x) / kGroup;
+  for (uint64_t i = gid; i < n; i += ngroups) {
+    uint64_t c[5];
+    fm_occ(fm, pos[i], c, g);
+    if (g.leader())
+      for (int b = 0; b < 5; ++b) counts[5 * i + b] = c[b];
+  }
+}
+
+void fm_occ_batch(sgx_ctx* ctx, const sgx_fm* fm, const uint64_t* pos, uint64_t n, uint64_t* counts) {
+  if (n == 0) return;
+  for (uint64_t i = 0; i < n; ++i)
+    SGX_REQUIRE(pos[i] == kNoPos || pos[i] < fm->n, SGX_EINVAL, "sgx_fm_occ: position beyond the BWT");
+  DevBuf<uint64_t> d_pos(n), d_cnt(5 * n);
+  SGX_CUDA(cudaMemcpyAsync(d_pos.p, pos, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  const unsigned grid = (unsigned)std::min<uint64_t>((n * kGroup + 255) / 256, (uint64_t)ctx->sm_count * 8);
+  SGX_LAUNCH(ctx, fm_occ_kernel, grid, 256, 0, fm->view(), (const uint64_t*)d_pos.p, n, d_cnt.p);
+  SGX_CUDA(cudaMemcpyAsync(counts, d_cnt.p, 5 * n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+// FMIndex::Interval::get + occurrences (src/fmindex.h:67-86): plain backward search, one group per query.
+__global__ void __launch_bounds__(256) fm_count_kernel(FmView fm, ReadsView q, uint64_t* __restrict__ counts) {
+  const DevGroup g;
+  const uint64_t gid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / kGroup;
+  const uint64_t ngroups = ((uint64_t)gridDim.x * blockDim.x) / kGroup;
+  for (uint64_t i = gid; i < q.n; i += ngroups) {
+    const uint32_t* rw = q.words + q.woff[i];
+    uint32_t j = q.len[i];
+    int c = read_rank(rw, j - 1);
+    pos_t lo = fm.pred[c], hi = fm.pred[c + 1] - 1;
+    uint64_t L[5], U[5];
+    while (--j > 0 && ival_valid(lo, hi)) {
+      c = read_rank(rw, j - 1);
+      fm_occ(fm, lo - 1, L, g);
+      fm_occ(fm, hi, U, g);
+      lo = fm.pred[c] + L[c];
+      hi = fm.pred[c] + U[c] - 1;
+    }
+    if (g.leader()) counts[i] = ival_valid(lo, hi) ? hi - lo + 1 : 0;
+  }
+}
+
+void fm_count_batch(sgx_ctx* ctx, const sgx_fm* fm, const char* ascii, const uint64_t* off, uint64_t n, uint64_t* counts) {
+  if (n == 0) return;
+  sgx_reads* q = reads_pack(ctx, ascii, off, n);
+  try {
+    DevBuf<uint64_t> d_cnt(n);
+    const unsigned grid = (unsigned)std::min<uint64_t>((n * kGroup + 255) / 256, (uint64_t)ctx->sm_count * 8);
+    SGX_LAUNCH(ctx, fm_count_kernel, grid, 256, 0, fm->view(), q->view(), d_cnt.p);
+    SGX_CUDA(cudaMemcpyAsync(counts, d_cnt.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+  } catch (...) {
+    reads_destroy(q);
+    throw;
+  }
+  reads_destroy(q);
+}
+
+}  // namespace sgx

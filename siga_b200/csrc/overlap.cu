@@ -1,0 +1,278 @@
+// Overlap search on the device: the body of parallel::foreach in OverlapBuilder::build
+// (src/overlap_builder.cpp:453-457 of the reference), i.e. OverlapBuilder::overlap per read, as two kernels:
+//
+//   ov_search_kernel  four OverlapBlockFinder::find passes per read.  One 8-lane group per read; every backward
+//                     step is one pair of 128-byte rank-block fetches (fm_layout.h).  All groups of a warp walk
+//                     the same search mode in lock-step (fixed-length reads), so the warp stays converged.
+//   ov_post_kernel    SubMaximalBlockFilter + ContainmentBlockRemover + IrreducibleBlockListExtractor per read on
+//                     a per-group work area (data dependent, divergent between groups by nature).
+//   ov_gather_kernel  compacts the per-read outputs into one array for the copy out.
+//
+// The per-read control logic lives in overlap_logic.h and is the same text the host stand-in of the tests runs.
+#include "overlap.cuh"
+
+#include <algorithm>
+
+#include "overlap_logic.h"
+
+namespace sgx {
+
+static const int kOvThreads = 256;
+
+struct OvBatch {
+  sgx_block* cand;     // [count][4][find_cap]
+  uint32_t* ncand;     // [count][4]
+  sgx_block* contain;  // [count][4]
+  uint32_t* ncontain;  // [count][4]
+  uint8_t* substring;  // [count]
+  sgx_block* out;      // [count][out_cap]
+  uint32_t* nout;      // [count]
+  uint32_t find_cap;
+  uint32_t out_cap;
+};
+
+__global__ void __launch_bounds__(kOvThreads)
+ov_search_kernel(FmView fwd, FmView rev, ReadsView reads, uint64_t first, uint64_t count, uint32_t min_ov, int rc,
+                 OvBatch bt, uint32_t* __restrict__ status, unsigned long long* __restrict__ lookups) {
+  const DevGroup g;
+  const uint64_t gid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / kGroup;
+  const uint64_t ngroups = ((uint64_t)gridDim.x * blockDim.x) / kGroup;
+  uint64_t nlook = 0;
+  uint32_t st = 0;
+  for (uint64_t r = gid; r < count; r += ngroups) {
+    const uint32_t* rw = reads.words + reads.woff[first + r];
+    const uint32_t l = reads.len[first + r];
+#pragma unroll 1
+    for (int mode = 0; mode < 4; ++mode) {
+      uint32_t nc = 0, nk = 0;
+      if (rc || mode == 0 || mode == 2) {
+        const bool on_fwd = mode < 2;
+        ov_find(on_fwd ? fwd : rev, on_fwd ? rev : fwd, rw, l, mode, min_ov,
+                bt.cand + ((size_t)r * 4 + mode) * bt.find_cap, bt.find_cap, &nc, bt.contain + (size_t)r * 4 + mode, &nk,
+                bt.substring + r, &st, &nlook, g);
+      }
+      if (g.leader()) {
+        bt.ncand[r * 4 + mode] = nc;
+        bt.ncontain[r * 4 + mode] = nk;
+      }
+    }
+  }
+  if (g.leader()) {
+    if (nlook) atomicAdd(lookups, (unsigned long long)nlook);
+    if (st) atomicOr(status, st);
+  }
+}
+
+struct OvArenaCfg {
+  sgx_block* blocks;  // per group: 4*list_cap + r_cap + st_cap blocks
+  uint32_t* gd;       // per group: 4*g_cap words
+  uint32_t list_cap, r_cap, st_cap, g_cap;
+};
+
+__global__ void __launch_bounds__(kOvThreads)
+ov_post_kernel(FmView fwd, FmView rev, ReadsView reads, uint64_t first, uint64_t count, int irreducible, OvBatch bt,
+               OvArenaCfg ac, uint32_t* __restrict__ status, unsigned long long* __restrict__ lookups) {
+  const DevGroup g;
+  const uint64_t gid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / kGroup;
+  const uint64_t ngroups = ((uint64_t)gridDim.x * blockDim.x) / kGroup;
+  const size_t per_group = (size_t)4 * ac.list_cap + ac.r_cap + ac.st_cap;
+  OvArena ar;
+  ar.lists = ac.blocks + gid * per_group;
+  ar.list_cap = ac.list_cap;
+  ar.R = ar.lists + (size_t)4 * ac.list_cap;
+  ar.r_cap = ac.r_cap;
+  ar.st = ar.R + ac.r_cap;
+  ar.st_cap = ac.st_cap;
+  ar.gd = ac.gd + gid * (size_t)4 * ac.g_cap;
+  ar.g_cap = ac.g_cap;
+  uint64_t nlook = 0;
+  uint32_t st = 0;
+  for (uint64_t r = gid; r < count; r += ngroups) {
+    const uint32_t l = reads.len[first + r];
+    const sgx_block* cp[4];
+    uint32_t nc[4], nk[4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      cp[f] = bt.cand + ((size_t)r * 4 + f) * bt.find_cap;
+      nc[f] = bt.ncand[r * 4 + f];
+      nk[f] = bt.ncontain[r * 4 + f];
+    }
+    uint32_t nout = 0;
+    ov_post(fwd, rev, l, irreducible, cp, nc, bt.contain + (size_t)r * 4, nk, ar, bt.out + (size_t)r * bt.out_cap, &nout,
+            bt.out_cap, &st, &nlook, g);
+    g.sync();
+    if (g.leader()) bt.nout[r] = nout;
+  }
+  if (g.leader()) {
+    if (nlook) atomicAdd(lookups, (unsigned long long)nlook);
+    if (st) atomicOr(status, st);
+  }
+}
+
+__global__ void ov_widen_kernel(const uint32_t* __restrict__ in, uint64_t n, uint64_t* __restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+  if (i == n) out[i] = 0;
+}
+
+// One warp per read: copies its blocks (9 x 8 bytes each) to the compact array.
+__global__ void ov_gather_kernel(const sgx_block* __restrict__ out, const uint32_t* __restrict__ nout, uint32_t out_cap,
+                                 const uint64_t* __restrict__ off, uint64_t count, sgx_block* __restrict__ dst) {
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= count) return;
+  const uint64_t* src = reinterpret_cast<const uint64_t*>(out + warp * (size_t)out_cap);
+  uint64_t* d = reinterpret_cast<uint64_t*>(dst + off[warp]);
+  const uint32_t words = nout[warp] * (uint32_t)(sizeof(sgx_block) / 8);
+  for (uint32_t w = lane; w < words; w += 32) d[w] = src[w];
+}
+
+void overlap_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const sgx_reads* reads, uint64_t first,
+                 uint64_t count, uint32_t min_ov, int irreducible, int rc, sgx_hits* hits) {
+  static_assert(sizeof(sgx_block) == 72, "sgx_block layout");
+  SGX_REQUIRE(fwd && rev && reads && hits, SGX_EINVAL, "sgx_overlap_batch: null argument");
+  SGX_REQUIRE(first <= reads->n && count <= reads->n - first, SGX_EINVAL, "sgx_overlap_batch: read range out of bounds");
+  SGX_REQUIRE(min_ov >= 1, SGX_EINVAL, "sgx_overlap_batch: min_overlap must be >= 1");
+  memset(hits, 0, sizeof(*hits));
+  const uint64_t launches0 = ctx->launches;
+  EventTimer t_all(ctx->stream);
+  KernelClock k_search(ctx->stream), k_post(ctx->stream);
+  t_all.start();
+
+  const uint32_t lmax = reads->max_len;
+  const uint32_t find_cap = lmax > min_ov ? lmax - min_ov : 1;
+  uint32_t out_cap = 4 * find_cap + 4;
+  // batch size: keep candidate + output regions within ~6 GB
+  const size_t per_read = ((size_t)4 * find_cap + 4 + out_cap) * sizeof(sgx_block);
+  uint64_t batch = std::max<uint64_t>(1024, std::min<uint64_t>((6ull << 30) / per_read, 1u << 20));
+  batch = std::min<uint64_t>(batch, std::max<uint64_t>(count, 1));
+
+  DevBuf<sgx_block> d_cand(batch * 4 * find_cap), d_contain(batch * 4), d_out(batch * out_cap);
+  DevBuf<uint32_t> d_ncand(batch * 4), d_ncontain(batch * 4), d_nout(batch), d_status(1);
+  DevBuf<uint8_t> d_sub(std::max<uint64_t>(count, 1));
+  DevBuf<uint64_t> d_off(batch + 1), d_ws(scan_ws_elems(batch + 1)), d_total(1);
+  DevBuf<unsigned long long> d_look(2);
+  SGX_CUDA(cudaMemsetAsync(d_sub.p, 0, std::max<uint64_t>(count, 1), ctx->stream));
+  SGX_CUDA(cudaMemsetAsync(d_look.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
+
+  // grids: a few resident CTAs per SM, groups stride over the reads of the batch
+  const unsigned grid_search = (unsigned)ctx->sm_count * 8;
+  const unsigned grid_post = (unsigned)ctx->sm_count * 4;
+  const uint64_t post_groups = (uint64_t)grid_post * kOvThreads / kGroup;
+  OvArenaCfg ac;
+  ac.list_cap = find_cap + 4 + 28;
+  ac.r_cap = ac.list_cap;
+  ac.st_cap = 4 * ac.list_cap;
+  ac.g_cap = 256;
+  DevBuf<sgx_block> d_arena;
+  DevBuf<uint32_t> d_gd;
+  auto alloc_arena = [&]() {
+    d_arena.alloc(post_groups * ((size_t)4 * ac.list_cap + ac.r_cap + ac.st_cap));
+    d_gd.alloc(post_groups * (size_t)4 * ac.g_cap);
+    ac.blocks = d_arena.p;
+    ac.gd = d_gd.p;
+  };
+  alloc_arena();
+
+  DevBuf<sgx_block> d_compact;           // all blocks of all batches
+  uint64_t compact_cap = 0, compact_n = 0;
+  std::vector<uint64_t> h_off(count + 1, 0);
+  PinnedBuf<uint64_t> h_batch_off;
+  h_batch_off.alloc(batch + 1);
+
+  const FmView vf = fwd->view(), vr = rev->view();
+  const ReadsView rv = reads->view();
+  for (uint64_t b0 = 0; b0 < count; b0 += batch) {
+    const uint64_t bn = std::min<uint64_t>(batch, count - b0);
+    OvBatch bt;
+    bt.cand = d_cand.p;
+    bt.ncand = d_ncand.p;
+    bt.contain = d_contain.p;
+    bt.ncontain = d_ncontain.p;
+    bt.substring = d_sub.p + b0;
+    bt.out = d_out.p;
+    bt.nout = d_nout.p;
+    bt.find_cap = find_cap;
+    bt.out_cap = out_cap;
+    SGX_CUDA(cudaMemsetAsync(d_status.p, 0, sizeof(uint32_t), ctx->stream));
+    k_search.tick();
+    SGX_LAUNCH(ctx, ov_search_kernel, grid_search, kOvThreads, 0, vf, vr, rv, first + b0, bn, min_ov, rc, bt,
+               d_status.p, d_look.p);
+    k_search.tick();
+    hits->search_launches++;
+    for (int attempt = 0;; ++attempt) {
+      if (attempt > 0) SGX_CUDA(cudaMemsetAsync(d_status.p, 0, sizeof(uint32_t), ctx->stream));
+      k_post.tick();
+      SGX_LAUNCH(ctx, ov_post_kernel, grid_post, kOvThreads, 0, vf, vr, rv, first + b0, bn, irreducible, bt, ac,
+                 d_status.p, d_look.p + 1);
+      k_post.tick();
+      uint32_t st = 0;
+      SGX_CUDA(cudaMemcpyAsync(&st, d_status.p, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+      SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+      SGX_REQUIRE(!(st & kOvAssert), SGX_EINVAL,
+                  "overlap: blocks of equal length with different coordinates (the reference asserts here)");
+      if (!(st & kOvOverflow)) break;
+      // a work area was too small: regrow it and redo the post stage of this batch on the GPU
+      SGX_REQUIRE(attempt < 4, SGX_EOVERFLOW, "overlap: work area overflow persists after regrowing");
+      ac.list_cap *= 2;
+      ac.r_cap *= 4;
+      ac.st_cap *= 4;
+      ac.g_cap *= 4;
+      alloc_arena();
+      if (attempt >= 1) {
+        out_cap *= 2;
+        d_out.alloc(batch * (size_t)out_cap);
+        bt.out = d_out.p;
+        bt.out_cap = out_cap;
+      }
+    }
+    // compact
+    SGX_LAUNCH(ctx, ov_widen_kernel, grid_for(bn + 1, 256), 256, 0, (const uint32_t*)d_nout.p, bn, d_off.p);
+    scan_exclusive(ctx, d_off.p, bn + 1, d_ws.p, (uint64_t*)nullptr);
+    SGX_CUDA(cudaMemcpyAsync(h_batch_off.p, d_off.p, (bn + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+    const uint64_t btotal = h_batch_off.p[bn];
+    if (compact_n + btotal > compact_cap) {
+      uint64_t ncap = std::max<uint64_t>(compact_n + btotal, compact_cap * 2);
+      if (b0 == 0 && bn < count) ncap = std::max<uint64_t>(ncap, (uint64_t)((double)btotal / bn * count * 1.1) + 1024);
+      DevBuf<sgx_block> nbuf(ncap);
+      if (compact_n)
+        SGX_CUDA(cudaMemcpyAsync(nbuf.p, d_compact.p, compact_n * sizeof(sgx_block), cudaMemcpyDeviceToDevice, ctx->stream));
+      SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+      sgx_block* old = d_compact.take();
+      cudaFree(old);
+      d_compact.p = nbuf.take();
+      d_compact.n = ncap;
+      compact_cap = ncap;
+    }
+    if (btotal)
+      SGX_LAUNCH(ctx, ov_gather_kernel, grid_for(bn * 32, 256), 256, 0, (const sgx_block*)bt.out,
+                 (const uint32_t*)d_nout.p, bt.out_cap, (const uint64_t*)d_off.p, bn, d_compact.p + compact_n);
+    for (uint64_t i = 0; i < bn; ++i) h_off[b0 + i] = compact_n + h_batch_off.p[i];
+    compact_n += btotal;
+  }
+  h_off[count] = compact_n;
+
+  // copy out
+  hits->n_reads = count;
+  hits->n_blocks = compact_n;
+  hits->substring = (uint8_t*)pinned_get(ctx, std::max<uint64_t>(count, 1));
+  hits->block_off = (uint64_t*)pinned_get(ctx, (count + 1) * sizeof(uint64_t));
+  hits->blocks = (sgx_block*)pinned_get(ctx, std::max<uint64_t>(compact_n, 1) * sizeof(sgx_block));
+  memcpy(hits->block_off, h_off.data(), (count + 1) * sizeof(uint64_t));
+  if (count) SGX_CUDA(cudaMemcpyAsync(hits->substring, d_sub.p, count, cudaMemcpyDeviceToHost, ctx->stream));
+  if (compact_n)
+    SGX_CUDA(cudaMemcpyAsync(hits->blocks, d_compact.p, compact_n * sizeof(sgx_block), cudaMemcpyDeviceToHost, ctx->stream));
+  unsigned long long look[2] = {0, 0};
+  SGX_CUDA(cudaMemcpyAsync(look, d_look.p, sizeof(look), cudaMemcpyDeviceToHost, ctx->stream));
+  t_all.stop();
+  SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+  hits->ms_total = t_all.ms();
+  hits->ms_search = k_search.total_ms();
+  hits->ms_extract = k_post.total_ms();
+  hits->lookups_search = look[0];
+  hits->lookups_extract = look[1];
+  hits->launches = ctx->launches - launches0;
+}
+
+}  // namespace sgx

@@ -69,7 +69,7 @@ SGX_LOGIC void ov_store_block(sgx_block* dst, pos_t c0lo, pos_t c0hi, pos_t c1lo
 template <class G>
 SGX_LOGIC void ov_find(const FmView& P, const FmView& S, const uint32_t* rw, uint32_t l, int mode, uint32_t min_ov,
                        sgx_block* cand, uint32_t cap, uint32_t* ncand, sgx_block* contain, uint32_t* ncontain,
-                       uint32_t* substring, uint32_t* status, uint64_t* lookups, const G& g) {
+                       uint8_t* substring, uint32_t* status, uint64_t* lookups, const G& g) {
   const uint32_t af = ov_mode_af(mode);
   uint32_t n = 0;
   uint64_t nlook = 0;

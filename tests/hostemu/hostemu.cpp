@@ -114,7 +114,8 @@ int hemu_overlap(void* fwd_, void* rev_, const char* ascii, const uint64_t* off,
         }
         rw[j >> 4] |= (uint32_t)code << (2 * (j & 15));
       }
-      uint32_t ncand[4] = {0, 0, 0, 0}, ncontain[4] = {0, 0, 0, 0}, substring = 0;
+      uint32_t ncand[4] = {0, 0, 0, 0}, ncontain[4] = {0, 0, 0, 0};
+      uint8_t substring = 0;
       for (int mode = 0; mode < 4; ++mode) {
         if (!rc && (mode == 1 || mode == 3)) continue;
         const FmView& P = mode < 2 ? fwd : rev;
@@ -136,7 +137,7 @@ int hemu_overlap(void* fwd_, void* rev_, const char* ascii, const uint64_t* off,
       uint32_t nout = 0;
       ov_post(fwd, rev, l, irreducible, cp, ncand, contain.data(), ncontain, ar, outb.data(), &nout, st_cap, &status,
               &lookups_e, g);
-      sub[i] = (uint8_t)substring;
+      sub[i] = substring;
       boff[i] = all.size();
       all.insert(all.end(), outb.begin(), outb.begin() + nout);
     }

@@ -1,0 +1,284 @@
+"""GPU parity tests: every call goes through the C ABI (siga_b200/api.py -> libsiga_b200.so)."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+import refrun
+from oracle import pyoracle
+from siga_b200 import api, formats, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_reads(rng, n, lmin, lmax, genome_len, err=0.0, dup=0.0, both=True):
+    g = synth.random_genome(genome_len, rng)
+    reads = []
+    for _ in range(n):
+        l = int(rng.integers(lmin, lmax + 1))
+        s = int(rng.integers(0, genome_len - l + 1))
+        r = g[s:s + l].copy()
+        if err > 0:
+            m = rng.random(l) < err
+            r[m] = synth.random_genome(int(m.sum()), rng)
+        if both and rng.random() < 0.5:
+            r = synth.revcomp(r)
+        reads.append(np.ascontiguousarray(r).tobytes())
+    for _ in range(int(n * dup)):
+        reads[int(rng.integers(0, n))] = reads[int(rng.integers(0, n))]
+    return reads
+
+
+# ---------------------------------------------------------------------------------------------- rank structure
+
+@pytest.mark.parametrize("n", [1, 31, 255, 256, 257, 4096, 100_003])
+def test_fm_occ_matches_cumulative_counts(ctx, n):
+    rng = np.random.default_rng(n)
+    sym = rng.choice(5, size=n, p=[0.02, 0.3, 0.2, 0.2, 0.28]).astype(np.uint8)
+    if n > 1000:  # long runs, including > 31
+        sym[100:400] = 1
+        sym[5000:5100] = 0
+    runs = formats.encode_runs(sym)
+    fm = ctx.fm_create(runs, n)
+    try:
+        occ = pyoracle.occ_table(sym)
+        pos = np.unique(np.concatenate([np.arange(min(n, 600)), rng.integers(0, n, size=2000), [n - 1]])).astype(np.uint64)
+        got = ctx.fm_occ(fm, np.concatenate([pos, np.array([2**64 - 1], dtype=np.uint64)]))
+        assert np.array_equal(got[:-1], occ[pos.astype(np.int64)])
+        assert not got[-1].any()  # getOcc(-1) == 0 (src/fmindex.cpp:188-231: ++i wraps to 0)
+        cnt = np.bincount(sym, minlength=5)
+        assert ctx.fm_pred(fm) == [int(x) for x in np.concatenate([[0], np.cumsum(cnt)[:-1]])]
+    finally:
+        ctx.free_fm(fm)
+
+
+def test_fm_count_matches_bruteforce(ctx):
+    rng = np.random.default_rng(5)
+    reads = _rand_reads(rng, 60, 20, 30, 300)
+    bwt, _ = pyoracle.bwt_and_sai(reads, "B")
+    fm = ctx.fm_create(formats.encode_runs(bwt), len(bwt))
+    try:
+        qs = [reads[int(rng.integers(0, 60))][a:a + k] for a, k in zip(rng.integers(0, 10, 200), rng.integers(1, 12, 200))]
+        qs += [b"ACGTACGTACGTACGT", b"A", b"T"]
+        flat, off = synth.reads_to_flat(qs)
+        got = ctx.fm_count(fm, flat, off)
+        text = b"$".join(reads)
+        want = []
+        for q in qs:
+            c, s = 0, text.find(q)
+            while s >= 0:
+                c += 1
+                s = text.find(q, s + 1)
+            want.append(c)
+        assert got.tolist() == want
+    finally:
+        ctx.free_fm(fm)
+
+
+# ---------------------------------------------------------------------------------------------- index construction
+
+def _check_index(ctx, reads, label):
+    flat, off = synth.reads_to_flat(reads)
+    r = ctx.pack_reads(flat, off)
+    try:
+        for model, order in (("B", api.ORDER_SAIS2), ("A", api.ORDER_SAIS)):
+            for rev in (False, True):
+                res = ctx.index_build(r, order=order, reversed=rev)
+                bwt, sai = pyoracle.bwt_and_sai(reads, model, reversed_reads=rev)
+                assert res.n_strings == len(reads) and res.n_suffixes == len(bwt)
+                got = formats.decode_runs(res.runs)
+                assert len(got) == len(bwt), (label, model, rev)
+                bad = np.flatnonzero(got != bwt)
+                assert len(bad) == 0, (label, model, rev, "first bad row", int(bad[0]), got[max(0, bad[0] - 5):bad[0] + 5], bwt[max(0, bad[0] - 5):bad[0] + 5])
+                assert np.array_equal(res.sai, sai), (label, model, rev)
+                assert np.array_equal(res.runs, formats.encode_runs(bwt)), (label, model, rev, "run bytes")
+    finally:
+        ctx.free_reads(r)
+
+
+def test_index_golden_f1(ctx):
+    reads = ("CAGATTTTCATATTATGCAG TTTCATATTATGCAGAAAAT TATTATGCAGAAAATCTACT TGCAGAAAATCTACTTCGCC AAAATCTACTTCGCCTGATA "
+             "CTACTTCGCCTGATACGAGT TCGCCTGATACGAGTCGGTT TGATACGAGTCGGTTATCTT CGAGTCGGTTATCTTCGGAT").split()
+    flat, off = synth.reads_to_flat(reads)
+    r = ctx.pack_reads(flat, off)
+    try:
+        res = ctx.index_build(r)
+        assert res.sai.tolist() == [4, 0, 8, 5, 2, 6, 7, 3, 1]
+        assert "".join("$ACGT"[s] for s in formats.decode_runs(res.runs)).startswith("TCTATTTTGTGGG$AAAAAAAATTTTTTTCCCCC")
+        assert len(res.runs) == 71
+        rres = ctx.index_build(r, reversed=True)
+        assert rres.sai.tolist() == [4, 3, 0, 1, 8, 2, 5, 7, 6]  # .rsai
+        assert len(rres.runs) == 74
+    finally:
+        ctx.free_reads(r)
+    _check_index(ctx, reads, "f1")
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_index_random_sets_both_models(ctx, seed):
+    rng = np.random.default_rng(100 + seed)
+    kind = seed % 4
+    if kind == 0:
+        reads = _rand_reads(rng, 80, 30, 30, 400, err=0.02)
+    elif kind == 1:  # heavy duplication: few distinct strings, ties resolved by the following reads
+        base = _rand_reads(rng, 6, 12, 12, 40, both=False)
+        reads = [base[int(rng.integers(0, 6))] for _ in range(70)]
+    elif kind == 2:  # variable length incl. reads that are prefixes / substrings of others
+        reads = _rand_reads(rng, 90, 5, 40, 200, dup=0.1)
+    else:  # low complexity, runs > 31
+        reads = [b"A" * int(rng.integers(1, 70)) for _ in range(12)] + [b"AC" * 20, b"CA" * 20, b"T" * 64, b"T" * 64]
+    _check_index(ctx, reads, "seed%d" % seed)
+
+
+@pytest.mark.skipif(not refrun.have_ref(), reason="compiled reference (oracle/_ref/siga) not present")
+@pytest.mark.parametrize("case", ["cfg1_small", "cfg2_small", "varlen"])
+def test_index_bytes_match_reference_files(ctx, case):
+    rng = np.random.default_rng(7)
+    if case == "cfg1_small":
+        g = synth.random_genome(60_000, rng)
+        reads = synth.paired_reads(g, 600, 100, rng)
+    elif case == "cfg2_small":
+        g = synth.random_genome(20_000, rng)
+        reads = synth.sample_reads(g, 13_000, 150, rng, err=0.01)
+    else:
+        reads = _rand_reads(rng, 3000, 30, 120, 30_000, err=0.01, dup=0.05)
+    flat, off = synth.reads_to_flat(reads)
+    with tempfile.TemporaryDirectory() as d:
+        fa = os.path.join(d, "x.fa")
+        synth.write_fasta(fa, reads)
+        r = ctx.pack_reads(flat, off)
+        try:
+            for algo, order in ((None, api.ORDER_SAIS2), ("sais", api.ORDER_SAIS)):
+                refrun.ref_index(fa, d, algo=algo)
+                for rev, be, se in ((False, ".bwt", ".sai"), (True, ".rbwt", ".rsai")):
+                    res = ctx.index_build(r, order=order, reversed=rev)
+                    want_bwt = open(os.path.join(d, "x" + be), "rb").read()
+                    want_sai = open(os.path.join(d, "x" + se), "rb").read()
+                    assert formats.bwt_bytes(res.n_strings, res.n_suffixes, res.runs) == want_bwt, (case, algo, be)
+                    assert formats.sai_bytes(res.sai) == want_sai, (case, algo, se)
+        finally:
+            ctx.free_reads(r)
+
+
+# ---------------------------------------------------------------------------------------------- overlap search
+
+def _overlap_vs_ref(ctx, reads, m, exhaustive=False, no_rc=False, names=None):
+    flat, off = synth.reads_to_flat(reads)
+    with tempfile.TemporaryDirectory() as d:
+        fa = os.path.join(d, "x.fa")
+        synth.write_fasta(fa, reads, names=names)
+        refrun.ref_index(fa, d)
+        hitfiles, asqg = refrun.ref_overlap(fa, d, m, threads=4, exhaustive=exhaustive, no_rc=no_rc)
+        ref_hits = formats.read_hits(hitfiles)
+        ref_asqg = formats.read_asqg(asqg)
+        n_str, n_suf, fr = formats.read_bwt(os.path.join(d, "x.bwt"))
+        _, _, rr = formats.read_bwt(os.path.join(d, "x.rbwt"))
+        sai = formats.read_sai(os.path.join(d, "x.sai"))
+        rsai = formats.read_sai(os.path.join(d, "x.rsai"))
+    fwd = ctx.fm_create(fr, n_suf)
+    rev = ctx.fm_create(rr, n_suf)
+    r = ctx.pack_reads(flat, off)
+    try:
+        h = ctx.overlap(fwd, rev, r, 0, len(off) - 1, m, irreducible=not exhaustive, rc=not no_rc)
+        hh = ctx.overlap_host(fwd, rev, flat, off, m, irreducible=not exhaustive, rc=not no_rc)
+    finally:
+        ctx.free_reads(r)
+        ctx.free_fm(fwd)
+        ctx.free_fm(rev)
+    n = len(off) - 1
+    bad = []
+    for i in range(n):
+        sub, blocks = ref_hits[i]
+        if h.read_blocks(i) != sorted(blocks) or int(h.substring[i]) != sub:
+            bad.append(i)
+    assert not bad, ("reads with different blocks", bad[:5], h.read_blocks(bad[0]), sorted(ref_hits[bad[0]][1]))
+    assert np.array_equal(h.block_off, hh.block_off) and np.array_equal(h.substring, hh.substring)
+    assert all(h.read_blocks(i) == hh.read_blocks(i) for i in range(0, n, max(1, n // 50)))
+    # hits -> ASQG through the host-side converter: identical to the reference after canonical sorting
+    nm = names if names is not None else ["r%d" % i for i in range(n)]
+    seqs = [bytes(x).decode() for x in reads]
+    lens = [len(s) for s in seqs]
+    edges = formats.hits_to_edges(nm, lens, h.substring, h.block_off, h.blocks, sai, rsai)
+    mine = formats.asqg_lines(nm, seqs, h.substring, edges, m)
+    assert sorted(mine) == sorted(ref_asqg)
+    assert mine[:1 + n] == ref_asqg[:1 + n]  # HT + VT lines come in input order
+    return h
+
+
+@pytest.mark.skipif(not refrun.have_ref(), reason="compiled reference (oracle/_ref/siga) not present")
+@pytest.mark.parametrize("seed", range(6))
+def test_overlap_blocks_match_reference_hits(ctx, seed):
+    rng = np.random.default_rng(200 + seed)
+    g = synth.random_genome(int(rng.integers(500, 3000)), rng)
+    L = int(rng.integers(30, 80))
+    reads = synth.sample_reads(g, int(rng.integers(200, 900)), L, rng, err=0.01 if seed % 2 else 0.0)
+    reads[rng.integers(0, len(reads), 20)] = reads[rng.integers(0, len(reads), 20)]  # duplicates -> containments
+    _overlap_vs_ref(ctx, reads, int(rng.integers(12, L - 5)), exhaustive=(seed == 4), no_rc=(seed == 5))
+
+
+@pytest.mark.skipif(not refrun.have_ref(), reason="compiled reference (oracle/_ref/siga) not present")
+def test_overlap_periodic_and_variable_length(ctx):
+    rng = np.random.default_rng(31)
+    unit = synth.random_genome(3, rng)
+    g = np.tile(unit, 150)
+    mut = rng.random(len(g)) < 0.03
+    g[mut] = synth.random_genome(int(mut.sum()), rng)
+    reads = synth.sample_reads(g, 60, 30, rng)
+    _overlap_vs_ref(ctx, reads, 10)  # exercises SubMaximalBlockFilter::resolve's tracing path
+    reads = _rand_reads(rng, 150, 12, 40, 400)
+    _overlap_vs_ref(ctx, reads, 8)   # substring reads: SS flags and the extraction abort order
+
+
+@pytest.mark.skipif(not refrun.have_ref(), reason="compiled reference (oracle/_ref/siga) not present")
+def test_golden_f2_names_and_containment(ctx):
+    # duplicates, reverse complement, substring; names decide which end is id0
+    reads = [b"ACGTTGCAAGGCTTAACCGGATTACA", b"TTGCAAGGCTTAACCGGATTACAGGC", b"ACGTTGCAAGGCTTAACCGGATTACA", b"GCAAGGCTTAACCGG",
+             b"TGTAATCCGGTTAAGCCTTGCAACGT", b"CCGGATTACAGGCTTTTGACCA"]
+    h = _overlap_vs_ref(ctx, reads, 8, names=list("abcdef"))
+    assert h.substring.tolist() == [0, 0, 0, 1, 0, 0]
+
+
+@pytest.mark.skipif(not refrun.have_ref(), reason="compiled reference (oracle/_ref/siga) not present")
+def test_config1_full_pipeline_bit_exact(ctx):
+    """BASELINE.json configs[0]: 1 Mbp genome, 20k error-free 100 bp reads, index + overlap -m 45."""
+    reads = synth.config_reads("cfg1")
+    assert reads.shape == (20_000, 100)
+    flat, off = synth.reads_to_flat(reads)
+    with tempfile.TemporaryDirectory() as d:
+        fa = os.path.join(d, "cfg1.fa")
+        synth.write_fasta(fa, reads)
+        refrun.ref_index(fa, d)
+        _, asqg = refrun.ref_overlap(fa, d, 45, threads=os.cpu_count() or 1)
+        ref_asqg = formats.read_asqg(asqg)
+        want = {e: open(os.path.join(d, "cfg1" + e), "rb").read() for e in (".bwt", ".rbwt", ".sai", ".rsai")}
+    r = ctx.pack_reads(flat, off)
+    try:
+        fi = ctx.index_build(r)
+        ri = ctx.index_build(r, reversed=True)
+        assert formats.bwt_bytes(fi.n_strings, fi.n_suffixes, fi.runs) == want[".bwt"]
+        assert formats.bwt_bytes(ri.n_strings, ri.n_suffixes, ri.runs) == want[".rbwt"]
+        assert formats.sai_bytes(fi.sai) == want[".sai"]
+        assert formats.sai_bytes(ri.sai) == want[".rsai"]
+        fwd = ctx.fm_create(fi.runs, fi.n_suffixes)
+        rev = ctx.fm_create(ri.runs, ri.n_suffixes)
+        try:
+            h = ctx.overlap(fwd, rev, r, 0, 20_000, 45)
+        finally:
+            ctx.free_fm(fwd)
+            ctx.free_fm(rev)
+    finally:
+        ctx.free_reads(r)
+    names = ["r%d" % i for i in range(20_000)]
+    seqs = [x.tobytes().decode() for x in reads]
+    edges = formats.hits_to_edges(names, [100] * 20_000, h.substring, h.block_off, h.blocks, fi.sai, ri.sai)
+    assert sorted(formats.asqg_lines(names, seqs, h.substring, edges, 45)) == sorted(ref_asqg)
+
+
+def test_rejects_bad_input(ctx):
+    flat, off = synth.reads_to_flat([b"ACGT", b"ACNT"])
+    with pytest.raises(api.SgxError) as e:
+        ctx.pack_reads(flat, off)
+    assert e.value.code == -1
+    with pytest.raises(api.SgxError):
+        ctx.pack_reads(np.frombuffer(b"ACGT", dtype=np.uint8), np.array([0, 0, 4], dtype=np.uint64))  # empty read
