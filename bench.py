@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Benchmark of the SIGA hot path on B200 (contract: see the task statement / DESIGN.md "Measurement").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA, through the C ABI)
+  python bench.py --impl reference [--steps K] [--warmup W]      the reference's own CPU code (oracle/_ref/siga)
+
+Workload: BASELINE.json configs[1] -- synthetic E. coli-sized 4.6 Mbp genome, 100x coverage of 150 bp reads with
+1 % substitution errors, both strands (3 066 666 reads), `index` + `overlap -m 45`.
+Headline metric: overlap reads/s (a step = one overlap pass over the whole read set, index resident);
+the BWT-build Gbases/s of the same read set is reported in the "index" object of the same JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+from siga_b200 import synth  # noqa: E402
+
+MIN_OVERLAP = 45
+WORKLOAD = "cfg2: 4.6 Mbp random genome, 100x, 150 bp reads, 1% substitutions, both strands, 3066666 reads; index + overlap -m 45"
+
+
+def measured_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nm in enumerate(names):
+                if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference_sample(scale, threads, workdir, want_index=True):
+    """Times the compiled reference (`siga index`, `siga overlap -m 45 -t threads`) on a scaled-down cfg2 sample."""
+    ref = os.path.join(REPO, "oracle", "_ref", "siga")
+    if not os.path.isfile(ref):
+        return None
+    reads = synth.config_reads("cfg2", scale)
+    fa = os.path.join(workdir, "sample.fa")
+    synth.write_fasta(fa, reads)
+    env = dict(os.environ, ORACLE_LOG_LEVEL="5")
+    out = {"reads": int(reads.shape[0]), "bases": int(reads.size), "threads": threads}
+    t0 = time.perf_counter()
+    subprocess.run([ref, "index", fa], cwd=workdir, env=env, check=True, capture_output=True)
+    out["index_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    subprocess.run([ref, "overlap", "-m", str(MIN_OVERLAP), "-t", str(threads), fa], cwd=workdir, env=env, check=True,
+                   capture_output=True)
+    out["overlap_s"] = time.perf_counter() - t0
+    return out
+
+
+def reference_arm(args):
+    """`--impl reference`: the reference's own CPU implementation, all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    scale = args.ref_scale
+    ref = os.path.join(REPO, "oracle", "_ref", "siga")
+    if not os.path.isfile(ref):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/siga was not built (no /root/reference at build time)"}))
+        return 0
+    with tempfile.TemporaryDirectory() as d:
+        reads = synth.config_reads("cfg2", scale)
+        fa = os.path.join(d, "sample.fa")
+        synth.write_fasta(fa, reads)
+        env = dict(os.environ, ORACLE_LOG_LEVEL="5")
+        t0 = time.perf_counter()
+        subprocess.run([ref, "index", fa], cwd=d, env=env, check=True, capture_output=True)
+        index_s = time.perf_counter() - t0
+        cmd = [ref, "overlap", "-m", str(MIN_OVERLAP), "-t", str(threads), fa]
+        for _ in range(args.warmup):
+            subprocess.run(cmd, cwd=d, env=env, check=True, capture_output=True)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            subprocess.run(cmd, cwd=d, env=env, check=True, capture_output=True)
+        dt = (time.perf_counter() - t0) / args.steps
+    n = int(reads.shape[0])
+    value = n / dt
+    sample = "cfg2 at genome scale %g: %d reads x 150 bp, same coverage and error rate; `siga overlap -m 45 -t %d` end to end" % (scale, n, threads)
+    line = {
+        "impl": "reference", "metric": "overlap_reads_per_s", "value": value, "unit": "reads/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "reads/s", "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "index": {"metric": "bwt_build_gbases_per_s", "value": reads.size / index_s / 1e9, "unit": "Gbases/s",
+                  "seconds": index_s, "cores": 1, "note": "`siga index` (default sais2 is single-threaded), fwd + rev index of the sample"},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="genome scale of cfg2 (1.0 = the named workload)")
+    ap.add_argument("--ref-scale", type=float, default=0.01, help="genome scale of the CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--index-steps", type=int, default=0, help="timed index builds (default: min(steps, 3))")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from siga_b200 import api, formats
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    peaks, peak_kind = measured_peaks()
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+
+    # ---- synthetic input, resident in pinned host memory (every rank holds the same read set)
+    reads = synth.config_reads("cfg2", args.scale)
+    n_reads, read_len = reads.shape
+    host = torch.empty(reads.size, dtype=torch.uint8).pin_memory()
+    host.numpy()[:] = reads.reshape(-1)
+    off = (np.arange(n_reads + 1, dtype=np.uint64) * np.uint64(read_len))
+    flat = host.numpy()
+    h2d_bytes = int(flat.nbytes + off.nbytes)
+
+    ctx = api.Context(local)
+    sampler = ClockSampler(local)
+
+    # ---- index (both strands) : build once for the overlap stage, then time it
+    r_dev = ctx.pack_reads(flat, off)
+    fi = ctx.index_build(r_dev, order=api.ORDER_SAIS2, reversed=False)
+    ri = ctx.index_build(r_dev, order=api.ORDER_SAIS2, reversed=True)
+    fwd = ctx.fm_create(fi.runs, fi.n_suffixes)
+    rev = ctx.fm_create(ri.runs, ri.n_suffixes)
+    # size-independent checks on the full-size index: '$' count, symbol counts = base counts, sai is a permutation
+    for idx in (fi, ri):
+        sym_counts = np.bincount(idx.runs >> 5, weights=(idx.runs & 31).astype(np.float64), minlength=5).astype(np.int64)
+        assert sym_counts[0] == n_reads and sym_counts.sum() == idx.n_suffixes
+        assert np.array_equal(np.sort(idx.sai), np.arange(n_reads, dtype=np.uint32))
+        base_counts = np.bincount(flat, minlength=256)[[65, 67, 71, 84]]
+        assert np.array_equal(sym_counts[1:], base_counts)
+
+    sampler.start()
+    # ---- overlap, inputs resident in HBM ("value")
+    for _ in range(args.warmup):
+        h = ctx.overlap(fwd, rev, r_dev, 0, n_reads, MIN_OVERLAP, copy=False)
+        ctx.free_hits(h)
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms = search_ms = extract_ms = 0.0
+    look_s = look_e = launches = search_launches = 0
+    d2h_bytes = 0
+    for _ in range(args.steps):
+        h = ctx.overlap(fwd, rev, r_dev, 0, n_reads, MIN_OVERLAP, copy=False)
+        st = h.stats
+        dev_ms += st["ms_total"]
+        search_ms += st["ms_search"]
+        extract_ms += st["ms_extract"]
+        look_s += st["lookups_search"]
+        look_e += st["lookups_extract"]
+        launches += st["launches"]
+        search_launches += st["search_launches"]
+        d2h_bytes = int(h.blocks.nbytes + h.block_off.nbytes + h.substring.nbytes)
+        n_blocks = st["n_blocks"]
+        ctx.free_hits(h)
+    barrier()
+    ms_step = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+    total_reads = n_reads * world
+    value = total_reads / (ms_step * 1e-3)
+
+    # ---- overlap end to end through the C ABI with HOST buffers ("e2e")
+    for _ in range(2):
+        h = ctx.overlap_host(fwd, rev, flat, off, MIN_OVERLAP, copy=False)
+        ctx.free_hits(h)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        h = ctx.overlap_host(fwd, rev, flat, off, MIN_OVERLAP, copy=False)
+        ctx.free_hits(h)
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+    e2e_value = total_reads / (e2e_ms * 1e-3)
+
+    # ---- index build (fwd + rev), resident and end to end
+    isteps = args.index_steps or min(args.steps, 3)
+    barrier()
+    t0 = time.perf_counter()
+    idx_dev_ms = idx_merge_ms = 0.0
+    idx_merge_bytes = idx_launches = idx_merge_launches = 0
+    for _ in range(isteps):
+        for rv in (False, True):
+            o = ctx.index_build(r_dev, order=api.ORDER_SAIS2, reversed=rv)
+            idx_dev_ms += o.stats["ms_total"]
+            idx_merge_ms += o.stats["ms_merge"]
+            idx_merge_bytes += o.stats["merge_bytes"]
+            idx_launches += o.stats["launches"]
+            idx_merge_launches += o.stats["merge_launches"]
+    barrier()
+    idx_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / isteps)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(isteps):
+        rr = ctx.pack_reads(flat, off)
+        for rv in (False, True):
+            o = ctx.index_build(rr, order=api.ORDER_SAIS2, reversed=rv)
+        ctx.free_reads(rr)
+    barrier()
+    idx_e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / isteps)
+    clocks = sampler.stop()
+
+    bases = n_reads * read_len
+    # random-access roofline of the search kernel: executed rank lookups x 128 B over its device time
+    search_s = search_ms * 1e-3 / args.steps
+    ach_gbs = (look_s / args.steps) * 128 / search_s / 1e9 if search_s > 0 else 0.0
+    gather = None
+    try:
+        gather = ctx.bench_gather(8 << 30, 1 << 27)
+    except Exception:
+        gather = None
+    idx_suffix_bytes = {100: 31, 150: 37, 250: 50}.get(read_len, (read_len + 1 + 7) // 8 + 18)
+    merge_s = idx_merge_ms * 1e-3 / max(idx_merge_launches, 1)
+    merge_ach = (idx_merge_bytes / max(idx_merge_launches, 1)) / merge_s / 1e9 if merge_s > 0 else 0.0
+
+    line = {
+        "metric": "overlap_reads_per_s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": WORKLOAD if args.scale == 1.0 else WORKLOAD + " [genome scale %g]" % args.scale,
+                   "reads_per_gpu": n_reads, "read_len": read_len, "min_overlap": MIN_OVERLAP,
+                   "sharding": "FM-indices replicated per GPU, every rank searches its own %d-read shard, no data-path collective" % n_reads,
+                   "l2": "index (2 x %.0f MB rank blocks) + candidate buffers exceed the 126 MB L2; no flush needed" %
+                         (fi.n_suffixes / 256 * 128 / 1e6)},
+        "device_ms_per_step": dev_ms / args.steps,
+        "gpu_launches": int(launches),
+        "e2e": {"value": e2e_value, "unit": "reads/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": d2h_bytes, "entry": "sgx_overlap_host (pinned host reads in, hit blocks out)"},
+        "roofline": {"bound": "hbm", "kernel": "ov_search_kernel", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": ach_gbs / hbm_peak, "traffic": None, "peak_kind": peak_kind + " STREAM copy",
+                     "lookups_per_read": look_s / args.steps / n_reads, "lookups_per_s": look_s / args.steps / search_s if search_s else 0,
+                     "random_gather_128B_per_s": gather,
+                     "frac_of_random_gather": (look_s / args.steps / search_s) / gather if gather and search_s else None,
+                     "search_ms": search_ms / args.steps, "extract_ms": extract_ms / args.steps,
+                     "extract_lookups_per_read": look_e / args.steps / n_reads, "blocks_per_read": n_blocks / n_reads},
+        "index": {"metric": "bwt_build_gbases_per_s", "value": bases * world / (idx_ms * 1e-3) / 1e9, "unit": "Gbases/s",
+                  "ms_per_step": idx_ms, "steps": isteps, "device_ms_per_step": idx_dev_ms / isteps, "scaling": "replicas only (round 1)",
+                  "e2e": {"value": bases * world / (idx_e2e_ms * 1e-3) / 1e9, "unit": "Gbases/s", "ms_per_step": idx_e2e_ms,
+                          "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(len(fi.runs) + len(ri.runs) + 8 * n_reads)},
+                  "gpu_launches": int(idx_launches),
+                  "roofline": {"bound": "hbm", "kernel": "bcr_merge_kernel", "achieved": merge_ach, "peak": hbm_peak, "unit": "GB/s",
+                               "frac": merge_ach / hbm_peak, "traffic": None,
+                               "merge_ms_per_build": idx_merge_ms / (2 * isteps),
+                               "floor_bytes_per_suffix": idx_suffix_bytes,
+                               "floor_frac": idx_suffix_bytes * 2 * fi.n_suffixes / (idx_dev_ms / isteps * 1e-3) / 1e9 / hbm_peak}},
+        "clocks": clocks,
+    }
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        with tempfile.TemporaryDirectory() as d:
+            cpu = run_reference_sample(args.ref_scale * 2.5, os.cpu_count() or 1, d)
+        if cpu:
+            sample = "cfg2 at genome scale %g: %d reads x 150 bp (same coverage/error); reference binary, end to end" % (
+                args.ref_scale * 2.5, cpu["reads"])
+            line["cpu_baseline"] = {"value": cpu["reads"] / cpu["overlap_s"], "unit": "reads/s", "cores": cpu["threads"],
+                                    "kind": "reference", "sample": sample, "seconds": cpu["overlap_s"],
+                                    "index_gbases_per_s": cpu["bases"] / cpu["index_s"] / 1e9, "index_seconds": cpu["index_s"],
+                                    "index_cores": 1}
+    ctx.free_fm(fwd)
+    ctx.free_fm(rev)
+    ctx.free_reads(r_dev)
+    ctx.close()
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

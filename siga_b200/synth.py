@@ -29,24 +29,30 @@ def revcomp(arr):
     return _COMP[arr][..., ::-1]
 
 
-def sample_reads(genome, n_reads, read_len, rng, err=0.0, both_strands=True):
-    """n_reads x read_len uint8 matrix of ASCII bases: uniform starts, strand uniform, iid substitutions."""
+def sample_reads(genome, n_reads, read_len, rng, err=0.0, both_strands=True, chunk=262144):
+    """n_reads x read_len uint8 matrix of ASCII bases: uniform starts, strand uniform, iid substitutions.
+
+    Generated in fixed-size chunks (bounded memory at config-2..5 sizes); the chunk size is part of the recipe."""
     g = len(genome)
-    starts = rng.integers(0, g - read_len + 1, size=n_reads)
-    idx = starts[:, None] + np.arange(read_len)[None, :]
-    reads = genome[idx]
-    if err > 0:
-        mask = rng.random(reads.shape) < err
-        k = int(mask.sum())
-        if k:
-            # substitute with one of the three other bases, uniformly
-            code = np.searchsorted(_ACGT, reads[mask])
-            code = (code + rng.integers(1, 4, size=k)) & 3
-            reads[mask] = _ACGT[code]
-    if both_strands:
-        flip = rng.random(n_reads) < 0.5
-        reads[flip] = revcomp(reads[flip])
-    return np.ascontiguousarray(reads)
+    out = np.empty((n_reads, read_len), dtype=np.uint8)
+    ar = np.arange(read_len, dtype=np.int64)[None, :]
+    for s in range(0, n_reads, chunk):
+        e = min(n_reads, s + chunk)
+        starts = rng.integers(0, g - read_len + 1, size=e - s)
+        reads = genome[starts[:, None] + ar]
+        if err > 0:
+            mask = rng.random(reads.shape, dtype=np.float32) < err
+            k = int(mask.sum())
+            if k:
+                # substitute with one of the three other bases, uniformly
+                code = np.searchsorted(_ACGT, reads[mask])
+                code = (code + rng.integers(1, 4, size=k)) & 3
+                reads[mask] = _ACGT[code]
+        if both_strands:
+            flip = rng.random(e - s) < 0.5
+            reads[flip] = revcomp(reads[flip])
+        out[s:e] = reads
+    return out
 
 
 def config_reads(name, scale=1.0):
@@ -57,7 +63,7 @@ def config_reads(name, scale=1.0):
     genome = random_genome(g, rng)
     if c.get("paired"):
         return paired_reads(genome, int(c["n_reads"] * scale) // 2, c["read_len"], rng)
-    n = int(round(g * c["coverage"] / c["read_len"]))
+    n = int(g * c["coverage"] // c["read_len"])
     return sample_reads(genome, n, c["read_len"], rng, err=c["err"], both_strands=True)
 
 
