@@ -217,6 +217,8 @@ def main():
     ri = ctx.index_build(r_dev, order=api.ORDER_SAIS2, reversed=True)
     fwd = ctx.fm_create(fi.runs, fi.n_suffixes)
     rev = ctx.fm_create(ri.runs, ri.n_suffixes)
+    ctx.fm_attach_reads(fwd, fi.sai, r_dev)
+    ctx.fm_attach_reads(rev, ri.sai, r_dev)
     # size-independent checks on the full-size index: '$' count, symbol counts = base counts, sai is a permutation
     for idx in (fi, ri):
         sym_counts = np.bincount(idx.runs >> 5, weights=(idx.runs & 31).astype(np.float64), minlength=5).astype(np.int64)
@@ -247,6 +249,7 @@ def main():
         search_launches += st["search_launches"]
         d2h_bytes = int(h.blocks.nbytes + h.block_off.nbytes + h.substring.nbytes)
         n_blocks = st["n_blocks"]
+        slow_reads = st["slow_reads"]
         ctx.free_hits(h)
     barrier()
     ms_step = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
@@ -325,7 +328,8 @@ def main():
                      "random_gather_128B_per_s": gather,
                      "frac_of_random_gather": (look_s / args.steps / search_s) / gather if gather and search_s else None,
                      "search_ms": search_ms / args.steps, "extract_ms": extract_ms / args.steps,
-                     "extract_lookups_per_read": look_e / args.steps / n_reads, "blocks_per_read": n_blocks / n_reads},
+                     "extract_lookups_per_read": look_e / args.steps / n_reads, "blocks_per_read": n_blocks / n_reads,
+                     "slow_path_reads": slow_reads},
         "index": {"metric": "bwt_build_gbases_per_s", "value": bases * world / (idx_ms * 1e-3) / 1e9, "unit": "Gbases/s",
                   "ms_per_step": idx_ms, "steps": isteps, "device_ms_per_step": idx_dev_ms / isteps, "scaling": "replicas only (round 1)",
                   "e2e": {"value": bases * world / (idx_e2e_ms * 1e-3) / 1e9, "unit": "Gbases/s", "ms_per_step": idx_e2e_ms,

@@ -111,6 +111,15 @@ void sgx_index_out_free(sgx_index_out* out);
  */
 int sgx_fm_create(sgx_ctx* ctx, const uint8_t* rle, uint64_t n_runs, uint64_t n_suffixes, sgx_fm** out);
 void sgx_fm_free(sgx_fm* fm);
+/*
+ * Attach the read-start order of the index (the ids of its .sai / .rsai file, SuffixArray::load,
+ * src/suffix_array.cpp:103-118) and the indexed read set.  The reference loads both for the hits -> ED step
+ * (src/overlap_builder.cpp:464-480); with them on the device the irreducible extraction reads the extension
+ * symbols of a candidate from the target read itself instead of walking the BWT one rank query per base
+ * (identical blocks, DESIGN.md "post stage").  Without it sgx_overlap_batch uses the BWT-walking path.
+ * `indexed_reads` is borrowed and must outlive the fm object.
+ */
+int sgx_fm_attach_reads(sgx_ctx* ctx, sgx_fm* fm, const uint32_t* sai, uint64_t n_strings, const sgx_reads* indexed_reads);
 uint64_t sgx_fm_length(const sgx_fm* fm);
 /* C[] of FMIndex::getPC (src/fmindex.h:129-131): pred[c] = number of symbols with rank < c. */
 int sgx_fm_pred(const sgx_fm* fm, uint64_t pred[5]);
@@ -148,6 +157,7 @@ typedef struct sgx_hits {
   uint64_t lookups_extract; /* executed rank-block fetches in filter/extraction                                */
   uint64_t launches;    /* kernels launched by this call                                                       */
   uint64_t search_launches;
+  uint64_t slow_reads;  /* reads whose post stage took the general BWT-walking path                            */
 } sgx_hits;
 
 /*

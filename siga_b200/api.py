@@ -21,7 +21,7 @@ ABI_SYMBOLS = [
     "sgx_abi_version", "sgx_init", "sgx_shutdown", "sgx_last_error", "sgx_sm_count",
     "sgx_reads_pack", "sgx_reads_free", "sgx_reads_count", "sgx_reads_bases",
     "sgx_index_build", "sgx_index_out_free",
-    "sgx_fm_create", "sgx_fm_free", "sgx_fm_length", "sgx_fm_pred", "sgx_fm_occ", "sgx_fm_count",
+    "sgx_fm_create", "sgx_fm_free", "sgx_fm_attach_reads", "sgx_fm_length", "sgx_fm_pred", "sgx_fm_occ", "sgx_fm_count",
     "sgx_overlap_batch", "sgx_overlap_host", "sgx_hits_free",
     "sgx_bench_gather", "sgx_flush_l2",
 ]
@@ -47,7 +47,7 @@ class _Hits(ctypes.Structure):
                 ("n_blocks", ctypes.c_uint64), ("ms_total", ctypes.c_double), ("ms_search", ctypes.c_double),
                 ("ms_extract", ctypes.c_double), ("lookups_search", ctypes.c_uint64),
                 ("lookups_extract", ctypes.c_uint64), ("launches", ctypes.c_uint64),
-                ("search_launches", ctypes.c_uint64)]
+                ("search_launches", ctypes.c_uint64), ("slow_reads", ctypes.c_uint64)]
 
 
 _lib = None
@@ -83,6 +83,7 @@ def load_library():
     lib.sgx_fm_create.argtypes = [vp, vp, u64, u64, ctypes.POINTER(vp)]
     lib.sgx_fm_free.argtypes = [vp]
     lib.sgx_fm_free.restype = None
+    lib.sgx_fm_attach_reads.argtypes = [vp, vp, vp, u64, vp]
     lib.sgx_fm_length.argtypes = [vp]
     lib.sgx_fm_length.restype = u64
     lib.sgx_fm_pred.argtypes = [vp, ctypes.POINTER(u64 * 5)]
@@ -129,7 +130,8 @@ class Hits:
         self.substring, self.block_off, self.blocks = sub, off, blocks
         self.stats = dict(ms_total=h.ms_total, ms_search=h.ms_search, ms_extract=h.ms_extract,
                           lookups_search=int(h.lookups_search), lookups_extract=int(h.lookups_extract),
-                          launches=int(h.launches), search_launches=int(h.search_launches), n_blocks=nb)
+                          launches=int(h.launches), search_launches=int(h.search_launches), n_blocks=nb,
+                          slow_reads=int(h.slow_reads))
 
     def read_blocks(self, i):
         """Sorted tuples (capped x4, raw x4, length, af) of read i -- the form the reference's .hits lines parse to."""
@@ -194,6 +196,11 @@ class Context:
         f = ctypes.c_void_p()
         self._check(self.lib.sgx_fm_create(self.h, _ptr(runs), len(runs), int(n_suffixes), ctypes.byref(f)))
         return f
+
+    def fm_attach_reads(self, f, sai, reads):
+        """Attach the .sai order + indexed read set (enables the read-based extraction path)."""
+        sai = np.ascontiguousarray(sai, dtype=np.uint32)
+        self._check(self.lib.sgx_fm_attach_reads(self.h, f, _ptr(sai), len(sai), reads))
 
     def free_fm(self, f):
         self.lib.sgx_fm_free(f)

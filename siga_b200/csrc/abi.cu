@@ -214,7 +214,16 @@ void sgx_fm_free(sgx_fm* fm) {
   if (!fm) return;
   cudaSetDevice(fm->ctx->device);
   cudaFree(fm->blocks);
+  if (fm->sai) cudaFree(fm->sai);
+  if (fm->inv) cudaFree(fm->inv);
   delete fm;
+}
+
+int sgx_fm_attach_reads(sgx_ctx* ctx, sgx_fm* fm, const uint32_t* sai, uint64_t n_strings, const sgx_reads* indexed_reads) {
+  if (!ctx || !fm) return SGX_EINVAL;
+  SGX_ENTRY_BEGIN(ctx)
+  fm_attach(ctx, fm, sai, n_strings, indexed_reads);
+  SGX_ENTRY_END(ctx)
 }
 
 uint64_t sgx_fm_length(const sgx_fm* fm) { return fm ? fm->n : 0; }

@@ -141,6 +141,10 @@ sgx_fm* fm_build_from_symbols(sgx_ctx* ctx, const uint8_t* sym_dev, uint64_t n) 
   sgx_fm* fm = new sgx_fm();
   fm->ctx = ctx;
   fm->n = n;
+  fm->sai = nullptr;
+  fm->inv = nullptr;
+  fm->n_strings = 0;
+  fm->indexed = nullptr;
   uint64_t acgt = 0;
   uint64_t cntc[5];
   for (int c = 0; c < 4; ++c) {
@@ -154,6 +158,37 @@ sgx_fm* fm_build_from_symbols(sgx_ctx* ctx, const uint8_t* sym_dev, uint64_t n) 
   return fm;
 }
 
+
+__global__ void sai_inverse_kernel(const uint32_t* __restrict__ sai, uint64_t n, uint32_t* __restrict__ inv,
+                                   uint32_t* __restrict__ bad) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t id = sai[k];
+  if (id >= n) {
+    atomicOr(bad, 1u);
+    return;
+  }
+  inv[id] = (uint32_t)k;
+}
+
+void fm_attach(sgx_ctx* ctx, sgx_fm* fm, const uint32_t* sai, uint64_t n, const sgx_reads* indexed) {
+  SGX_REQUIRE(sai && indexed && n == indexed->n, SGX_EINVAL, "sgx_fm_attach_reads: sai / read set size mismatch");
+  SGX_REQUIRE(n + indexed->bases == fm->n, SGX_EINVAL, "sgx_fm_attach_reads: read set does not match the BWT length");
+  DevBuf<uint32_t> d_sai(n), d_inv(n), d_bad(1);
+  SGX_CUDA(cudaMemcpyAsync(d_sai.p, sai, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  SGX_CUDA(cudaMemsetAsync(d_bad.p, 0, sizeof(uint32_t), ctx->stream));
+  SGX_LAUNCH(ctx, sai_inverse_kernel, grid_for(n, 256), 256, 0, (const uint32_t*)d_sai.p, n, d_inv.p, d_bad.p);
+  uint32_t bad = 0;
+  SGX_CUDA(cudaMemcpyAsync(&bad, d_bad.p, sizeof(bad), cudaMemcpyDeviceToHost, ctx->stream));
+  SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+  SGX_REQUIRE(bad == 0, SGX_EINVAL, "sgx_fm_attach_reads: read id out of range in sai");
+  if (fm->sai) cudaFree(fm->sai);
+  if (fm->inv) cudaFree(fm->inv);
+  fm->sai = d_sai.take();
+  fm->inv = d_inv.take();
+  fm->n_strings = n;
+  fm->indexed = indexed;
+}
 
 // One 8-lane group per query position.
 __global__ void __launch_bounds__(256) fm_occ_kernel(FmView fm, const uint64_t* __restrict__ pos, uint64_t n,

@@ -5,11 +5,18 @@
 #include "fm_layout.h"
 #include "prims.cuh"
 
+struct sgx_reads;
+
 struct sgx_fm {
   sgx_ctx* ctx;
   sgx::FmBlockLane* blocks;  // device
   uint64_t n;
   uint64_t pred[6];
+  // optional (sgx_fm_attach_reads): read-start order of this index, its inverse, and the indexed read set
+  uint32_t* sai;   // device, n_strings
+  uint32_t* inv;   // device, inv[sai[k]] = k
+  uint64_t n_strings;
+  const sgx_reads* indexed;
   sgx::FmView view() const {
     sgx::FmView v;
     v.blocks = blocks;
@@ -26,6 +33,8 @@ sgx_fm* fm_build_from_symbols(sgx_ctx* ctx, const uint8_t* sym_dev, uint64_t n);
 // Expands run bytes (device) into a fresh device symbol array of n_suffixes bytes.
 void rle_expand(sgx_ctx* ctx, const uint8_t* rle_dev, uint64_t n_runs, uint64_t n_suffixes, uint8_t* sym_dev);
 
+// Uploads the read-start order and builds its inverse.
+void fm_attach(sgx_ctx* ctx, sgx_fm* fm, const uint32_t* sai, uint64_t n, const sgx_reads* indexed);
 // Batched FMIndex::getOcc(i): host positions in, host counts (5 per position) out.
 void fm_occ_batch(sgx_ctx* ctx, const sgx_fm* fm, const uint64_t* pos, uint64_t n, uint64_t* counts);
 // Batched FMIndex::Interval::occurrences of host query strings.

@@ -31,6 +31,12 @@ struct OvBatch {
   uint32_t out_cap;
 };
 
+}  // namespace sgx
+
+#include "overlap_reduce.cuh"
+
+namespace sgx {
+
 __global__ void __launch_bounds__(kOvThreads)
 ov_search_kernel(FmView fwd, FmView rev, ReadsView reads, uint64_t first, uint64_t count, uint32_t min_ov, int rc,
                  OvBatch bt, uint32_t* __restrict__ status, unsigned long long* __restrict__ lookups) {
@@ -71,7 +77,8 @@ struct OvArenaCfg {
 
 __global__ void __launch_bounds__(kOvThreads)
 ov_post_kernel(FmView fwd, FmView rev, ReadsView reads, uint64_t first, uint64_t count, int irreducible, OvBatch bt,
-               OvArenaCfg ac, uint32_t* __restrict__ status, unsigned long long* __restrict__ lookups) {
+               OvArenaCfg ac, const uint32_t* __restrict__ list, uint32_t* __restrict__ status,
+               unsigned long long* __restrict__ lookups) {
   const DevGroup g;
   const uint64_t gid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / kGroup;
   const uint64_t ngroups = ((uint64_t)gridDim.x * blockDim.x) / kGroup;
@@ -87,7 +94,9 @@ ov_post_kernel(FmView fwd, FmView rev, ReadsView reads, uint64_t first, uint64_t
   ar.g_cap = ac.g_cap;
   uint64_t nlook = 0;
   uint32_t st = 0;
-  for (uint64_t r = gid; r < count; r += ngroups) {
+  // `count` work items: all reads of the batch, or (list != nullptr) the reads the fast path handed back
+  for (uint64_t wi = gid; wi < count; wi += ngroups) {
+    const uint64_t r = list ? (uint64_t)list[wi] : wi;
     const uint32_t l = reads.len[first + r];
     const sgx_block* cp[4];
     uint32_t nc[4], nk[4];
@@ -155,6 +164,9 @@ void overlap_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const sgx_r
   SGX_CUDA(cudaMemsetAsync(d_sub.p, 0, std::max<uint64_t>(count, 1), ctx->stream));
   SGX_CUDA(cudaMemsetAsync(d_look.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
 
+  const FmView vf = fwd->view(), vr = rev->view();
+  const ReadsView rv = reads->view();
+  const ReadsView rv0 = rv;
   // grids: a few resident CTAs per SM, groups stride over the reads of the batch
   const unsigned grid_search = (unsigned)ctx->sm_count * 8;
   const unsigned grid_post = (unsigned)ctx->sm_count * 4;
@@ -174,14 +186,36 @@ void overlap_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const sgx_r
   };
   alloc_arena();
 
+  // fast post path: needs the read-start orders and the indexed read set on the device (sgx_fm_attach_reads)
+  const bool fast = fwd->sai && rev->sai && fwd->indexed && fwd->indexed == rev->indexed &&
+                    fwd->indexed->max_len < 65536 && fwd->indexed->ctx == ctx;
+  ReadsView treads = rv0;
+  SaView sf{nullptr, nullptr}, sr{nullptr, nullptr};
+  uint32_t rows_cap = 128, extw = 1;
+  size_t reduce_smem = 0;
+  unsigned grid_reduce = 1;
+  DevBuf<uint32_t> d_slow, d_nslow(1);
+  if (fast) {
+    treads = fwd->indexed->view();
+    sf.sa = fwd->sai;
+    sf.inv = fwd->inv;
+    sr.sa = rev->sai;
+    sr.inv = rev->inv;
+    const uint32_t tmax = fwd->indexed->max_len;
+    extw = tmax > min_ov ? (tmax - min_ov + 31) / 32 : 1;
+    while (rows_cap > 32 && reduce_smem_per_warp(rows_cap, extw) * kRdWarps > (size_t)200 * 1024) rows_cap /= 2;
+    reduce_smem = reduce_smem_per_warp(rows_cap, extw) * kRdWarps;
+    SGX_CUDA(cudaFuncSetAttribute(ov_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)reduce_smem));
+    grid_reduce = (unsigned)ctx->sm_count * 16;
+    d_slow.alloc(batch);
+  }
+
   DevBuf<sgx_block> d_compact;           // all blocks of all batches
   uint64_t compact_cap = 0, compact_n = 0;
   std::vector<uint64_t> h_off(count + 1, 0);
   PinnedBuf<uint64_t> h_batch_off;
   h_batch_off.alloc(batch + 1);
 
-  const FmView vf = fwd->view(), vr = rev->view();
-  const ReadsView rv = reads->view();
   for (uint64_t b0 = 0; b0 < count; b0 += batch) {
     const uint64_t bn = std::min<uint64_t>(batch, count - b0);
     OvBatch bt;
@@ -200,11 +234,30 @@ void overlap_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const sgx_r
                d_status.p, d_look.p);
     k_search.tick();
     hits->search_launches++;
-    for (int attempt = 0;; ++attempt) {
+    // ---- post stage.  Fast path (read store + .sai attached): string-based reduction, the few reads outside its
+    //      preconditions are handed back on a list.  Otherwise / for that list: the literal BWT-walking kernel.
+    const uint32_t* work_list = nullptr;
+    uint64_t work_n = bn;
+    if (fast) {
+      SGX_CUDA(cudaMemsetAsync(d_nslow.p, 0, sizeof(uint32_t), ctx->stream));
+      k_post.tick();
+      SGX_LAUNCH(ctx, ov_reduce_kernel, grid_reduce, kRdWarps * 32, reduce_smem, treads, sf, sr, bn, irreducible, bt,
+                 rows_cap, extw, d_slow.p, d_nslow.p);
+      k_post.tick();
+      uint32_t ns = 0;
+      SGX_CUDA(cudaMemcpyAsync(&ns, d_nslow.p, sizeof(ns), cudaMemcpyDeviceToHost, ctx->stream));
+      SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+      work_list = d_slow.p;
+      work_n = ns;
+      hits->slow_reads += ns;
+    } else {
+      hits->slow_reads += bn;
+    }
+    for (int attempt = 0; work_n > 0; ++attempt) {
       if (attempt > 0) SGX_CUDA(cudaMemsetAsync(d_status.p, 0, sizeof(uint32_t), ctx->stream));
       k_post.tick();
-      SGX_LAUNCH(ctx, ov_post_kernel, grid_post, kOvThreads, 0, vf, vr, rv, first + b0, bn, irreducible, bt, ac,
-                 d_status.p, d_look.p + 1);
+      SGX_LAUNCH(ctx, ov_post_kernel, grid_post, kOvThreads, 0, vf, vr, rv, first + b0, work_n, irreducible, bt, ac,
+                 work_list, d_status.p, d_look.p + 1);
       k_post.tick();
       uint32_t st = 0;
       SGX_CUDA(cudaMemcpyAsync(&st, d_status.p, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
@@ -212,7 +265,7 @@ void overlap_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const sgx_r
       SGX_REQUIRE(!(st & kOvAssert), SGX_EINVAL,
                   "overlap: blocks of equal length with different coordinates (the reference asserts here)");
       if (!(st & kOvOverflow)) break;
-      // a work area was too small: regrow it and redo the post stage of this batch on the GPU
+      // a work area was too small: regrow it and redo the post stage of these reads on the GPU
       SGX_REQUIRE(attempt < 4, SGX_EOVERFLOW, "overlap: work area overflow persists after regrowing");
       ac.list_cap *= 2;
       ac.r_cap *= 4;
@@ -220,10 +273,13 @@ void overlap_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const sgx_r
       ac.g_cap *= 4;
       alloc_arena();
       if (attempt >= 1) {
+        // the output regions are too small as well: this also invalidates what the fast path wrote, redo everything
         out_cap *= 2;
         d_out.alloc(batch * (size_t)out_cap);
         bt.out = d_out.p;
         bt.out_cap = out_cap;
+        work_list = nullptr;
+        work_n = bn;
       }
     }
     // compact

@@ -180,8 +180,17 @@ def _overlap_vs_ref(ctx, reads, m, exhaustive=False, no_rc=False, names=None):
     rev = ctx.fm_create(rr, n_suf)
     r = ctx.pack_reads(flat, off)
     try:
+        # general path: extension by BWT walks (no read store attached)
+        h_walk = ctx.overlap(fwd, rev, r, 0, len(off) - 1, m, irreducible=not exhaustive, rc=not no_rc)
+        assert h_walk.stats["slow_reads"] == len(off) - 1
+        # fast path: .sai/.rsai + read store attached, extension read from the target reads
+        ctx.fm_attach_reads(fwd, sai, r)
+        ctx.fm_attach_reads(rev, rsai, r)
         h = ctx.overlap(fwd, rev, r, 0, len(off) - 1, m, irreducible=not exhaustive, rc=not no_rc)
         hh = ctx.overlap_host(fwd, rev, flat, off, m, irreducible=not exhaustive, rc=not no_rc)
+        assert np.array_equal(h.block_off, h_walk.block_off) and np.array_equal(h.substring, h_walk.substring)
+        diff = [i for i in range(len(off) - 1) if h.read_blocks(i) != h_walk.read_blocks(i)]
+        assert not diff, ("fast path differs from the BWT-walking path", diff[:5], h.read_blocks(diff[0]), h_walk.read_blocks(diff[0]))
     finally:
         ctx.free_reads(r)
         ctx.free_fm(fwd)
@@ -214,7 +223,8 @@ def test_overlap_blocks_match_reference_hits(ctx, seed):
     L = int(rng.integers(30, 80))
     reads = synth.sample_reads(g, int(rng.integers(200, 900)), L, rng, err=0.01 if seed % 2 else 0.0)
     reads[rng.integers(0, len(reads), 20)] = reads[rng.integers(0, len(reads), 20)]  # duplicates -> containments
-    _overlap_vs_ref(ctx, reads, int(rng.integers(12, L - 5)), exhaustive=(seed == 4), no_rc=(seed == 5))
+    h = _overlap_vs_ref(ctx, reads, int(rng.integers(12, L - 5)), exhaustive=(seed == 4), no_rc=(seed == 5))
+    assert h.stats["slow_reads"] <= len(reads) // 20
 
 
 @pytest.mark.skipif(not refrun.have_ref(), reason="compiled reference (oracle/_ref/siga) not present")
@@ -225,9 +235,11 @@ def test_overlap_periodic_and_variable_length(ctx):
     mut = rng.random(len(g)) < 0.03
     g[mut] = synth.random_genome(int(mut.sum()), rng)
     reads = synth.sample_reads(g, 60, 30, rng)
-    _overlap_vs_ref(ctx, reads, 10)  # exercises SubMaximalBlockFilter::resolve's tracing path
+    h = _overlap_vs_ref(ctx, reads, 10)  # exercises SubMaximalBlockFilter::resolve's tracing path
+    assert h.stats["slow_reads"] > 0     # periodic reads are handed to the literal path
     reads = _rand_reads(rng, 150, 12, 40, 400)
-    _overlap_vs_ref(ctx, reads, 8)   # substring reads: SS flags and the extraction abort order
+    h = _overlap_vs_ref(ctx, reads, 8)   # substring reads: SS flags and the extraction abort order
+    assert h.stats["slow_reads"] > 0     # variable-length targets are handed to the literal path
 
 
 @pytest.mark.skipif(not refrun.have_ref(), reason="compiled reference (oracle/_ref/siga) not present")
@@ -263,7 +275,10 @@ def test_config1_full_pipeline_bit_exact(ctx):
         fwd = ctx.fm_create(fi.runs, fi.n_suffixes)
         rev = ctx.fm_create(ri.runs, ri.n_suffixes)
         try:
+            ctx.fm_attach_reads(fwd, fi.sai, r)
+            ctx.fm_attach_reads(rev, ri.sai, r)
             h = ctx.overlap(fwd, rev, r, 0, 20_000, 45)
+            assert h.stats["slow_reads"] == 0  # fixed-length, non-periodic reads all take the read-based path
         finally:
             ctx.free_fm(fwd)
             ctx.free_fm(rev)
