@@ -20,6 +20,8 @@ void sgx_set_error(sgx_ctx* ctx, const char* msg) {
 
 namespace sgx {
 
+thread_local cudaStream_t g_stream = nullptr;
+
 void* pinned_get(sgx_ctx* ctx, size_t bytes) {
   if (bytes == 0) bytes = 1;
   {
@@ -131,6 +133,13 @@ int sgx_init(int device, sgx_ctx** out) {
     ctx->flush_buf = nullptr;
     ctx->flush_bytes = 0;
     SGX_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    {
+      // keep freed device memory in the pool (see DevBuf)
+      cudaMemPool_t pool;
+      SGX_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+      uint64_t keep = UINT64_MAX;
+      SGX_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     probe_kernel<<<1, 1, 0, ctx->stream>>>(nullptr);
     SGX_CUDA(cudaGetLastError());
     SGX_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -159,7 +168,8 @@ void sgx_shutdown(sgx_ctx* ctx) {
       }
     }
   }
-  if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+  if (ctx->flush_buf) cudaFreeAsync(ctx->flush_buf, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -213,9 +223,9 @@ int sgx_fm_create(sgx_ctx* ctx, const uint8_t* rle, uint64_t n_runs, uint64_t n_
 void sgx_fm_free(sgx_fm* fm) {
   if (!fm) return;
   cudaSetDevice(fm->ctx->device);
-  cudaFree(fm->blocks);
-  if (fm->sai) cudaFree(fm->sai);
-  if (fm->inv) cudaFree(fm->inv);
+  cudaFreeAsync(fm->blocks, fm->ctx->stream);
+  if (fm->sai) cudaFreeAsync(fm->sai, fm->ctx->stream);
+  if (fm->inv) cudaFreeAsync(fm->inv, fm->ctx->stream);
   delete fm;
 }
 
@@ -305,9 +315,9 @@ int sgx_flush_l2(sgx_ctx* ctx) {
   SGX_ENTRY_BEGIN(ctx)
   const size_t want = std::max<size_t>(2 * ctx->l2_bytes, (size_t)256 << 20);
   if (ctx->flush_bytes < want) {
-    if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+    if (ctx->flush_buf) cudaFreeAsync(ctx->flush_buf, ctx->stream);
     ctx->flush_buf = nullptr;
-    SGX_CUDA(cudaMalloc(&ctx->flush_buf, want));
+    SGX_CUDA(cudaMallocAsync(&ctx->flush_buf, want, ctx->stream));
     ctx->flush_bytes = want;
   }
   SGX_LAUNCH(ctx, fill_kernel, (unsigned)ctx->sm_count * 8, 256, 0, (uint4*)ctx->flush_buf, (uint64_t)(want / 16));

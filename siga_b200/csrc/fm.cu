@@ -182,8 +182,8 @@ void fm_attach(sgx_ctx* ctx, sgx_fm* fm, const uint32_t* sai, uint64_t n, const 
   SGX_CUDA(cudaMemcpyAsync(&bad, d_bad.p, sizeof(bad), cudaMemcpyDeviceToHost, ctx->stream));
   SGX_CUDA(cudaStreamSynchronize(ctx->stream));
   SGX_REQUIRE(bad == 0, SGX_EINVAL, "sgx_fm_attach_reads: read id out of range in sai");
-  if (fm->sai) cudaFree(fm->sai);
-  if (fm->inv) cudaFree(fm->inv);
+  if (fm->sai) cudaFreeAsync(fm->sai, ctx->stream);
+  if (fm->inv) cudaFreeAsync(fm->inv, ctx->stream);
   fm->sai = d_sai.take();
   fm->inv = d_inv.take();
   fm->n_strings = n;

@@ -296,7 +296,7 @@ void overlap_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const sgx_r
         SGX_CUDA(cudaMemcpyAsync(nbuf.p, d_compact.p, compact_n * sizeof(sgx_block), cudaMemcpyDeviceToDevice, ctx->stream));
       SGX_CUDA(cudaStreamSynchronize(ctx->stream));
       sgx_block* old = d_compact.take();
-      cudaFree(old);
+      if (old) cudaFreeAsync(old, ctx->stream);
       d_compact.p = nbuf.take();
       d_compact.n = ncap;
       compact_cap = ncap;

@@ -124,9 +124,9 @@ sgx_reads* reads_pack(sgx_ctx* ctx, const char* ascii, const uint64_t* off, uint
 
 void reads_destroy(sgx_reads* r) {
   if (!r) return;
-  cudaFree(r->words);
-  cudaFree(r->woff);
-  cudaFree(r->len);
+  cudaFreeAsync(r->words, r->ctx->stream);
+  cudaFreeAsync(r->woff, r->ctx->stream);
+  cudaFreeAsync(r->len, r->ctx->stream);
   delete r;
 }
 

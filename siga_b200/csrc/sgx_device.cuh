@@ -55,6 +55,12 @@ struct Error {
     SGX_CUDA(cudaGetLastError());                                               \
   } while (0)
 
+// Stream of the context whose entry point is executing on this thread (set by SGX_ENTRY_BEGIN); device buffers are
+// allocated stream-ordered from the device's memory pool, whose release threshold sgx_init raises so that the
+// multi-GB work areas of one call are reused by the next instead of going back to the driver (cudaMalloc/cudaFree
+// of those sizes cost up to hundreds of milliseconds each).
+extern thread_local cudaStream_t g_stream;
+
 // RAII device buffer.
 template <class T>
 struct DevBuf {
@@ -68,10 +74,10 @@ struct DevBuf {
   void alloc(size_t count) {
     release();
     n = count;
-    if (count) SGX_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+    if (count) SGX_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), g_stream));
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, g_stream);
     p = nullptr;
     n = 0;
   }
@@ -167,9 +173,12 @@ inline unsigned grid_for(uint64_t n, unsigned per_block) {
 }  // namespace sgx
 
 // Entry-point wrapper: turns sgx::Error / std::bad_alloc into an ABI status + message.
-#define SGX_ENTRY_BEGIN(ctx) \
-  try {                      \
-    if (ctx) SGX_CUDA(cudaSetDevice((ctx)->device));
+#define SGX_ENTRY_BEGIN(ctx)                          \
+  try {                                               \
+    if (ctx) {                                        \
+      SGX_CUDA(cudaSetDevice((ctx)->device));         \
+      sgx::g_stream = (ctx)->stream;                  \
+    }
 #define SGX_ENTRY_END(ctx)                      \
   }                                             \
   catch (const sgx::Error& e) {                 \
