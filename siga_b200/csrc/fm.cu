@@ -114,16 +114,16 @@ __global__ void __launch_bounds__(256) fm_pack_kernel(const uint8_t* __restrict_
   }
 }
 
-// After the in-place scan of cnt (flattened [4][nb]), header word k of block b = 32-bit half of the count of symbol
-// k>>1 before block b.
+// After the in-place scan of cnt (flattened [4][nb]), header word k of block b = low (k < 4) or high (k >= 4) half of
+// the count of symbol k & 3 before block b.
 __global__ void fm_header_kernel(FmBlockLane* __restrict__ blocks, uint64_t nb, const uint64_t* __restrict__ scanned) {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nb * kGroup) return;
   const uint64_t b = t / kGroup;
   const int k = (int)(t & (kGroup - 1));
-  const int c = k >> 1;
+  const int c = k & 3;
   const uint64_t v = scanned[(uint64_t)c * nb + b] - scanned[(uint64_t)c * nb];
-  blocks[t].h = (k & 1) ? (uint32_t)(v >> 32) : (uint32_t)(v & 0xffffffffu);
+  blocks[t].h = (k >= 4) ? (uint32_t)(v >> 32) : (uint32_t)(v & 0xffffffffu);
 }
 
 sgx_fm* fm_build_from_symbols(sgx_ctx* ctx, const uint8_t* sym_dev, uint64_t n) {

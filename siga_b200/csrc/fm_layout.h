@@ -7,8 +7,9 @@
 //     .x plane0 : low  bit of (rank-1) for symbols [32k, 32k+32) of the block      (A=00 C=01 G=10 T=11)
 //     .y plane1 : high bit of (rank-1)
 //     .z plane2 : 1 where the symbol is '$'
-//     .w header word k of {A_lo, A_hi, C_lo, C_hi, G_lo, G_hi, T_lo, T_hi}: the 64-bit counts of A,C,G,T in all
-//        symbols BEFORE this block ('$' before the block = 256*b - A - C - G - T)
+//     .w header word k of {A_lo, C_lo, G_lo, T_lo, A_hi, C_hi, G_hi, T_hi}: the 64-bit counts of A,C,G,T in all
+//        symbols BEFORE this block ('$' before the block = 256*b - A - C - G - T); lanes q and q+4 together hold
+//        the full count of symbol q+1, which is what the 4-lane search kernel exploits
 //
 // A rank query getOcc(pos) (all five symbols, BWT[0..pos] inclusive) is therefore ONE aligned 128-byte fetch: the
 // 8 lanes of a group load one uint4 each (a single fully used cache line per group), popcount their own 32
@@ -93,10 +94,10 @@ __device__ __forceinline__ void fm_occ(const FmView& fm, pos_t pos, uint64_t out
   uint32_t h[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) h[k] = __shfl_sync(g.mask, w.w, base + k);
-  uint64_t a = ((uint64_t)h[1] << 32 | h[0]) + (w1 & 0xffffu);
-  uint64_t c = ((uint64_t)h[3] << 32 | h[2]) + (w1 >> 16);
-  uint64_t gg = ((uint64_t)h[5] << 32 | h[4]) + (w2 & 0xffffu);
-  uint64_t t = ((uint64_t)h[7] << 32 | h[6]) + (w2 >> 16);
+  uint64_t a = ((uint64_t)h[4] << 32 | h[0]) + (w1 & 0xffffu);
+  uint64_t c = ((uint64_t)h[5] << 32 | h[1]) + (w1 >> 16);
+  uint64_t gg = ((uint64_t)h[6] << 32 | h[2]) + (w2 & 0xffffu);
+  uint64_t t = ((uint64_t)h[7] << 32 | h[3]) + (w2 >> 16);
   out[1] = a;
   out[2] = c;
   out[3] = gg;
@@ -137,10 +138,10 @@ inline void fm_occ(const FmView& fm, pos_t pos, uint64_t out[5], const HostGroup
     w1 += a1;
     w2 += a2;
   }
-  uint64_t a = ((uint64_t)blk[1].h << 32 | blk[0].h) + (w1 & 0xffffu);
-  uint64_t c = ((uint64_t)blk[3].h << 32 | blk[2].h) + (w1 >> 16);
-  uint64_t gg = ((uint64_t)blk[5].h << 32 | blk[4].h) + (w2 & 0xffffu);
-  uint64_t t = ((uint64_t)blk[7].h << 32 | blk[6].h) + (w2 >> 16);
+  uint64_t a = ((uint64_t)blk[4].h << 32 | blk[0].h) + (w1 & 0xffffu);
+  uint64_t c = ((uint64_t)blk[5].h << 32 | blk[1].h) + (w1 >> 16);
+  uint64_t gg = ((uint64_t)blk[6].h << 32 | blk[2].h) + (w2 & 0xffffu);
+  uint64_t t = ((uint64_t)blk[7].h << 32 | blk[3].h) + (w2 >> 16);
   out[1] = a;
   out[2] = c;
   out[3] = gg;

@@ -1,11 +1,12 @@
 // Overlap search on the device: the body of parallel::foreach in OverlapBuilder::build
 // (src/overlap_builder.cpp:453-457 of the reference), i.e. OverlapBuilder::overlap per read, as two kernels:
 //
-//   ov_search_kernel  four OverlapBlockFinder::find passes per read.  One 8-lane group per read; every backward
-//                     step is one pair of 128-byte rank-block fetches (fm_layout.h).  All groups of a warp walk
-//                     the same search mode in lock-step (fixed-length reads), so the warp stays converged.
-//   ov_post_kernel    SubMaximalBlockFilter + ContainmentBlockRemover + IrreducibleBlockListExtractor per read on
-//                     a per-group work area (data dependent, divergent between groups by nature).
+//   ov_search_quad_kernel  the four OverlapBlockFinder::find passes of every read, one 4-lane quad per (read, mode)
+//                     (overlap_search.cuh); every backward step is one pair of 128-byte rank-block fetches.
+//   ov_reduce_kernel  post stage, common case: irreducible extraction by comparing target-read extensions
+//                     (overlap_reduce.cuh), one warp per read.
+//   ov_post_kernel    post stage, general case: the literal SubMaximalBlockFilter + ContainmentBlockRemover +
+//                     IrreducibleBlockListExtractor on a per-group work area (BWT walks; data dependent).
 //   ov_gather_kernel  compacts the per-read outputs into one array for the copy out.
 //
 // The per-read control logic lives in overlap_logic.h and is the same text the host stand-in of the tests runs.
@@ -34,40 +35,9 @@ struct OvBatch {
 }  // namespace sgx
 
 #include "overlap_reduce.cuh"
+#include "overlap_search.cuh"
 
 namespace sgx {
-
-__global__ void __launch_bounds__(kOvThreads)
-ov_search_kernel(FmView fwd, FmView rev, ReadsView reads, uint64_t first, uint64_t count, uint32_t min_ov, int rc,
-                 OvBatch bt, uint32_t* __restrict__ status, unsigned long long* __restrict__ lookups) {
-  const DevGroup g;
-  const uint64_t gid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / kGroup;
-  const uint64_t ngroups = ((uint64_t)gridDim.x * blockDim.x) / kGroup;
-  uint64_t nlook = 0;
-  uint32_t st = 0;
-  for (uint64_t r = gid; r < count; r += ngroups) {
-    const uint32_t* rw = reads.words + reads.woff[first + r];
-    const uint32_t l = reads.len[first + r];
-#pragma unroll 1
-    for (int mode = 0; mode < 4; ++mode) {
-      uint32_t nc = 0, nk = 0;
-      if (rc || mode == 0 || mode == 2) {
-        const bool on_fwd = mode < 2;
-        ov_find(on_fwd ? fwd : rev, on_fwd ? rev : fwd, rw, l, mode, min_ov,
-                bt.cand + ((size_t)r * 4 + mode) * bt.find_cap, bt.find_cap, &nc, bt.contain + (size_t)r * 4 + mode, &nk,
-                bt.substring + r, &st, &nlook, g);
-      }
-      if (g.leader()) {
-        bt.ncand[r * 4 + mode] = nc;
-        bt.ncontain[r * 4 + mode] = nk;
-      }
-    }
-  }
-  if (g.leader()) {
-    if (nlook) atomicAdd(lookups, (unsigned long long)nlook);
-    if (st) atomicOr(status, st);
-  }
-}
 
 struct OvArenaCfg {
   sgx_block* blocks;  // per group: 4*list_cap + r_cap + st_cap blocks
@@ -167,6 +137,14 @@ void overlap_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const sgx_r
   const FmView vf = fwd->view(), vr = rev->view();
   const ReadsView rv = reads->view();
   const ReadsView rv0 = rv;
+  FmPair fmp;
+  fmp.blocks[0] = vf.blocks;
+  fmp.blocks[1] = vr.blocks;
+  for (int i = 0; i < 6; ++i) {
+    fmp.pred[0][i] = vf.pred[i];
+    fmp.pred[1][i] = vr.pred[i];
+  }
+  const bool narrow = fwd->n < 0xffffffffull && rev->n < 0xffffffffull;  // 32-bit positions suffice
   // grids: a few resident CTAs per SM, groups stride over the reads of the batch
   const unsigned grid_search = (unsigned)ctx->sm_count * 8;
   const unsigned grid_post = (unsigned)ctx->sm_count * 4;
@@ -230,8 +208,13 @@ void overlap_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const sgx_r
     bt.out_cap = out_cap;
     SGX_CUDA(cudaMemsetAsync(d_status.p, 0, sizeof(uint32_t), ctx->stream));
     k_search.tick();
-    SGX_LAUNCH(ctx, ov_search_kernel, grid_search, kOvThreads, 0, vf, vr, rv, first + b0, bn, min_ov, rc, bt,
-               d_status.p, d_look.p);
+    if (narrow) {
+      SGX_LAUNCH(ctx, ov_search_quad_kernel<uint32_t>, grid_search, kOvThreads, 0, fmp, rv, first + b0, bn, min_ov, rc,
+                 bt, d_look.p);
+    } else {
+      SGX_LAUNCH(ctx, ov_search_quad_kernel<uint64_t>, grid_search, kOvThreads, 0, fmp, rv, first + b0, bn, min_ov, rc,
+                 bt, d_look.p);
+    }
     k_search.tick();
     hits->search_launches++;
     // ---- post stage.  Fast path (read store + .sai attached): string-based reduction, the few reads outside its

@@ -1,0 +1,218 @@
+// The search kernel: OverlapBlockFinder::find (src/overlap_builder.cpp:846-906 of the reference) for every
+// (read, search mode) pair, tuned for issue rate.  Same arithmetic as ov_find() in overlap_logic.h (the validated
+// restatement the slow path and the host stand-in run), different work split:
+//
+//   * FOUR lanes per chain, eight chains per warp.  Lane q of a quad loads uint4 q and q+4 of a rank block, i.e. a
+//     quarter of its symbols plus the low and high header word of symbol q+1 (fm_layout.h), for BOTH ends of the
+//     interval (lower-1 and upper).  When both ends fall into the same block the second pair of loads is predicated
+//     off, so a narrow interval costs one 128-byte line per backward step.
+//   * partial popcounts are packed two per register and summed with two xor-shuffles per word; each lane then owns
+//     the complete rank of "its" symbol at both ends, and only the three quantities the interval update needs
+//     (ranks of the stepped symbol, the '$' difference, the sum of differences below the symbol) are exchanged.
+//   * positions are 32-bit when the BWT has < 2^32 symbols (IdxT), 64-bit otherwise; no local memory.
+//   * all quads of a warp walk reads of the same length in lock-step, so there is no divergence on fixed-length input.
+#ifndef SGX_OVERLAP_SEARCH_CUH_
+#define SGX_OVERLAP_SEARCH_CUH_
+
+#include "overlap_logic.h"
+
+namespace sgx {
+
+static const int kQuad = 4;
+
+template <class IdxT>
+struct QuadRank {
+  IdxT Lq, Uq;      // rank of this lane's symbol (q+1) in [0, plo) and [0, phi)
+  IdxT Ld, Ud;      // rank of '$' at both ends (same on all lanes)
+};
+
+// Ranks of all symbols at prefix lengths plo <= phi, distributed over the quad.
+template <class IdxT>
+__device__ __forceinline__ QuadRank<IdxT> quad_rank(const FmBlockLane* __restrict__ blocks, IdxT plo, IdxT phi, int q,
+                                                    unsigned qmask) {
+  const uint64_t b1 = (uint64_t)plo >> kBlockShift, b2 = (uint64_t)phi >> kBlockShift;
+  const int r1 = (int)(plo & (kBlockSyms - 1)), r2 = (int)(phi & (kBlockSyms - 1));
+  const uint4* pa = reinterpret_cast<const uint4*>(blocks + b1 * kGroup + q);
+  const uint4 a0 = __ldg(pa), a1 = __ldg(pa + 4);
+  uint4 c0 = a0, c1 = a1;
+  if (b2 != b1) {
+    const uint4* pb = reinterpret_cast<const uint4*>(blocks + b2 * kGroup + q);
+    c0 = __ldg(pb);
+    c1 = __ldg(pb + 4);
+  }
+  uint32_t x1, x2, y1, y2, la1, la2, lb1, lb2;
+  fm_lane_counts(a0.x, a0.y, a0.z, q, r1, x1, x2);
+  fm_lane_counts(a1.x, a1.y, a1.z, q + 4, r1, y1, y2);
+  la1 = x1 + y1;
+  la2 = x2 + y2;
+  fm_lane_counts(c0.x, c0.y, c0.z, q, r2, x1, x2);
+  fm_lane_counts(c1.x, c1.y, c1.z, q + 4, r2, y1, y2);
+  lb1 = x1 + y1;
+  lb2 = x2 + y2;
+#pragma unroll
+  for (int m = 1; m < kQuad; m <<= 1) {
+    la1 += __shfl_xor_sync(qmask, la1, m);
+    la2 += __shfl_xor_sync(qmask, la2, m);
+    lb1 += __shfl_xor_sync(qmask, lb1, m);
+    lb2 += __shfl_xor_sync(qmask, lb2, m);
+  }
+  // in-block count of this lane's symbol: q=0 A (la1 low), 1 C (la1 high), 2 G (la2 low), 3 T (la2 high)
+  const uint32_t wa = (q & 2) ? la2 : la1, wb = (q & 2) ? lb2 : lb1;
+  const uint32_t ia = (q & 1) ? (wa >> 16) : (wa & 0xffffu), ib = (q & 1) ? (wb >> 16) : (wb & 0xffffu);
+  QuadRank<IdxT> out;
+  if (sizeof(IdxT) == 8) {
+    out.Lq = (IdxT)(((uint64_t)a1.w << 32 | a0.w) + ia);
+    out.Uq = (IdxT)(((uint64_t)c1.w << 32 | c0.w) + ib);
+  } else {
+    out.Lq = (IdxT)(a0.w + ia);
+    out.Uq = (IdxT)(c0.w + ib);
+  }
+  IdxT sl = out.Lq, su = out.Uq;
+#pragma unroll
+  for (int m = 1; m < kQuad; m <<= 1) {
+    sl += __shfl_xor_sync(qmask, sl, m);
+    su += __shfl_xor_sync(qmask, su, m);
+  }
+  out.Ld = plo - sl;
+  out.Ud = phi - su;
+  return out;
+}
+
+template <class IdxT>
+__device__ __forceinline__ void quad_store_block(sgx_block* dst, IdxT c0lo, IdxT c0hi, IdxT c1lo, IdxT c1hi, IdxT r0lo,
+                                                 IdxT r0hi, IdxT r1lo, IdxT r1hi, uint32_t len, uint32_t af) {
+  // positions are stored as the reference prints them: 64-bit, with -1 staying -1
+  const bool wide = sizeof(IdxT) == 8;
+  auto ext = [wide](IdxT v) -> uint64_t { return (!wide && v == (IdxT)-1) ? (uint64_t)-1 : (uint64_t)v; };
+  ov_store_block(dst, ext(c0lo), ext(c0hi), ext(c1lo), ext(c1hi), ext(r0lo), ext(r0hi), ext(r1lo), ext(r1hi), len, af);
+}
+
+// Both indices in one kernel parameter, so that "the searched index" is a dynamic subscript into parameter space
+// (a constant-bank load) rather than a pointer to a parameter copy in local memory.
+struct FmPair {
+  const FmBlockLane* blocks[2];  // 0 = forward index, 1 = reverse index
+  uint64_t pred[2][6];
+};
+
+template <class IdxT>
+__global__ void __launch_bounds__(256, 4)
+ov_search_quad_kernel(FmPair fm, ReadsView reads, uint64_t first, uint64_t count, uint32_t min_ov, int rc,
+                      OvBatch bt, unsigned long long* __restrict__ lookups) {
+  const int wl = threadIdx.x & 31;
+  const int q = wl & (kQuad - 1);
+  const unsigned qmask = 0xfu << (wl & ~(kQuad - 1));
+  const int qbase = wl & ~(kQuad - 1);
+  const uint64_t quad = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / kQuad;
+  const uint64_t nquads = ((uint64_t)gridDim.x * blockDim.x) / kQuad;
+  const int nmodes = rc ? 4 : 2;
+  const uint64_t nwork = count * nmodes;
+  unsigned long long nlook = 0;
+  const IdxT kNone = (IdxT)-1;
+
+  for (uint64_t wk = quad; wk < nwork; wk += nquads) {
+    const uint64_t r = wk / nmodes;
+    const int mode = rc ? (int)(wk % nmodes) : (int)(wk % nmodes) * 2;  // without rc only modes 0 and 2 run
+    const int pi = mode < 2 ? 0 : 1, si = 1 - pi;  // searched index / its opposite
+    const FmBlockLane* __restrict__ Pb = fm.blocks[pi];
+    const FmBlockLane* __restrict__ Sb = fm.blocks[si];
+#define Ppred fm.pred[pi]
+#define Spred fm.pred[si]
+    const uint32_t* rw = reads.words + reads.woff[first + r];
+    const uint32_t l = reads.len[first + r];
+    const uint32_t af = ov_mode_af(mode);
+    sgx_block* cand = bt.cand + ((size_t)r * 4 + mode) * bt.find_cap;
+    uint32_t n = 0;
+
+    // C[] of the searched index in registers (selected by symbol without indexing memory inside the loop)
+    const IdxT pc0 = (IdxT)Ppred[0], pc1 = (IdxT)Ppred[1], pc2 = (IdxT)Ppred[2], pc3 = (IdxT)Ppred[3], pc4 = (IdxT)Ppred[4];
+    int c = ov_sym(rw, l, mode, l - 1);
+    IdxT lo0 = (IdxT)Ppred[c], hi0 = (IdxT)(Ppred[c + 1] - 1);
+    IdxT lo1 = (IdxT)Spred[c], hi1 = (IdxT)(Spred[c + 1] - 1);
+    int cnext = l > 1 ? ov_sym(rw, l, mode, l - 2) : 0;
+#pragma unroll 1
+    for (uint32_t i = l - 1; i > 0; --i) {
+      const bool valid = hi0 != kNone && hi0 >= lo0;
+      if (!valid) break;  // an empty interval stays empty and emits nothing (see ov_find)
+      c = cnext;
+      if (i > 1) cnext = ov_sym(rw, l, mode, i - 2);  // prefetch the symbol of the next step
+      const QuadRank<IdxT> k = quad_rank<IdxT>(Pb, lo0, (IdxT)(hi0 + 1), q, qmask);
+      nlook += 2;
+      const IdxT dd = k.Ud - k.Ld;
+      const uint32_t olen = l - i;
+      if (olen >= min_ov && dd >= 1) {
+        if (n < bt.find_cap && q == 0)
+          quad_store_block<IdxT>(cand + n, pc0 + k.Ld, pc0 + k.Ud - 1, lo1, lo1 + dd - 1, lo0, hi0,
+                                 lo1, hi1, olen, af);
+        ++n;
+      }
+      // ranks of the stepped symbol and the sum of differences of the smaller symbols
+      const IdxT Lc = __shfl_sync(qmask, k.Lq, qbase + c - 1);
+      const IdxT Uc = __shfl_sync(qmask, k.Uq, qbase + c - 1);
+      IdxT below = (q < c - 1) ? (IdxT)(k.Uq - k.Lq) : (IdxT)0;
+#pragma unroll
+      for (int m = 1; m < kQuad; m <<= 1) below += __shfl_xor_sync(qmask, below, m);
+      below += dd;
+      lo1 = lo1 + below;
+      hi1 = lo1 + (Uc - Lc) - 1;
+      const IdxT pc = c == 1 ? pc1 : (c == 2 ? pc2 : (c == 3 ? pc3 : pc4));
+      lo0 = pc + Lc;
+      hi0 = pc + Uc - 1;
+    }
+    uint32_t ncontain = 0;
+    if (hi0 != kNone && hi0 >= lo0) {
+      // containment handling (src/overlap_builder.cpp:877-905)
+      const QuadRank<IdxT> kp = quad_rank<IdxT>(Pb, lo0, (IdxT)(hi0 + 1), q, qmask);
+      const QuadRank<IdxT> ks = quad_rank<IdxT>(Sb, lo1, (IdxT)(hi1 + 1), q, qmask);
+      nlook += 4;
+      // any non-'$' extension on either side?
+      const bool mydna = (kp.Uq - kp.Lq) > 0 || (ks.Uq - ks.Lq) > 0;
+      const bool dna = __ballot_sync(qmask, mydna) != 0;
+      if (dna) {
+        if (q == 0) bt.substring[r] = 1;
+      } else {
+        const IdxT d = kp.Ud - kp.Ld;
+        const IdxT p0lo = (IdxT)Ppred[0] + kp.Ld;
+        IdxT p0hi = (IdxT)Ppred[0] + kp.Ud - 1;
+        IdxT p1lo = lo1, p1hi = lo1 + d - 1;
+        const bool v0 = p0hi != kNone && p0hi >= p0lo, v1 = p1hi != kNone && p1hi >= p1lo;
+        if (v0 && v1) {
+          IdxT U3d = ks.Ud;
+          if (p1hi != hi1) {
+            const QuadRank<IdxT> k3 = quad_rank<IdxT>(Sb, lo1, (IdxT)(p1hi + 1), q, qmask);
+            U3d = k3.Ud;
+            nlook += 1;
+          }
+          const IdxT d3 = U3d - ks.Ld;
+          p0hi = p0lo + d3 - 1;
+          p1lo = (IdxT)Spred[0] + ks.Ld;
+          p1hi = (IdxT)Spred[0] + U3d - 1;
+          if (q == 0)
+            quad_store_block<IdxT>(bt.contain + (size_t)r * 4 + mode, p0lo, p0hi, p1lo, p1hi, lo0, hi0, lo1, hi1, l, af);
+          ncontain = 1;
+        }
+      }
+    }
+    if (q == 0) {
+      bt.ncand[r * 4 + mode] = n < bt.find_cap ? n : bt.find_cap;
+      bt.ncontain[r * 4 + mode] = ncontain;
+    }
+  }
+#undef Ppred
+#undef Spred
+  // the modes a run without reverse complement skips still need their counters cleared
+  if (!rc) {
+    for (uint64_t r = quad; r < count; r += nquads) {
+      if (q == 0) {
+        bt.ncand[r * 4 + 1] = 0;
+        bt.ncand[r * 4 + 3] = 0;
+        bt.ncontain[r * 4 + 1] = 0;
+        bt.ncontain[r * 4 + 3] = 0;
+      }
+    }
+  }
+  if (q == 0 && nlook) atomicAdd(lookups, nlook);
+}
+
+}  // namespace sgx
+
+#endif  // SGX_OVERLAP_SEARCH_CUH_

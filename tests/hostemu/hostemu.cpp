@@ -28,8 +28,8 @@ static HemuFm* build_from_syms(const std::vector<uint8_t>& sym) {
   for (uint64_t b = 0; b < nb; ++b) {
     FmBlockLane* blk = &fm->blocks[b * kGroup];
     for (int c = 0; c < 4; ++c) {
-      blk[2 * c].h = (uint32_t)(cnt[c + 1] & 0xffffffffu);
-      blk[2 * c + 1].h = (uint32_t)(cnt[c + 1] >> 32);
+      blk[c].h = (uint32_t)(cnt[c + 1] & 0xffffffffu);
+      blk[c + 4].h = (uint32_t)(cnt[c + 1] >> 32);
     }
     for (int j = 0; j < kBlockSyms; ++j) {
       const uint64_t i = b * kBlockSyms + j;
