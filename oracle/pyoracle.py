@@ -53,3 +53,114 @@ def occ_table(bwt):
     """Inclusive cumulative counts: occ[i, c] = #c in bwt[0..i]."""
     onehot = (np.asarray(bwt)[:, None] == np.arange(5)[None, :]).astype(np.uint64)
     return np.cumsum(onehot, axis=0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Overlap models (validated there against the compiled reference on random fixed-length sets).
+# Brute force over all read pairs: small inputs only.
+# ---------------------------------------------------------------------------------------------------------------------
+
+_COMP = bytes.maketrans(b"ACGT", b"TGCA")
+
+
+def _rc(s):
+    return s.translate(_COMP)[::-1]
+
+
+def _candidates(reads, names, m):
+    """Per query: containment edges and the four candidate lists of OverlapBuilder::overlap
+    (src/overlap_builder.cpp:1113-1158) for FIXED-LENGTH reads: (orientation, target index, k), largest k only."""
+    out = []
+    for qi, Q in enumerate(reads):
+        rq = _rc(Q)
+        lists = {"SP": [], "PP": [], "PS": [], "SS": []}
+        contain = []
+        for ti, T in enumerate(reads):
+            if names[ti] == names[qi]:
+                continue  # self hits are dropped by name (src/overlap_builder.cpp:358)
+            if T == Q:
+                contain.append((ti, 0))
+                continue  # its length-|Q| block makes every shorter overlap with T sub-maximal (1137-1158)
+            if _rc(T) == Q:
+                contain.append((ti, 1))
+                continue
+            hi = min(len(Q), len(T)) - 1
+            for name, a, b in (("SP", Q, T), ("PP", rq, T)):
+                for k in range(hi, m - 1, -1):
+                    if a[len(a) - k:] == b[:k]:
+                        lists[name].append((ti, k))
+                        break
+            for name, a, b in (("PS", Q, T), ("SS", rq, T)):
+                for k in range(hi, m - 1, -1):
+                    if a[:k] == b[len(b) - k:]:
+                        lists[name].append((ti, k))
+                        break
+        out.append((lists, contain))
+    return out
+
+
+def _ed(names, lens, qi, ti, k, kind):
+    """ED payload of OverlapBlock::overlap + Overlap's writer (src/overlap_builder.cpp:158-175, src/coord.cpp:66-80)."""
+    lq, lt = lens[qi], lens[ti]
+    if kind == "SP":
+        c = (lq - k, lq - 1, lq, 0, k - 1, lt, 0)
+    elif kind == "PP":
+        c = (0, k - 1, lq, 0, k - 1, lt, 1)
+    elif kind == "PS":
+        c = (0, k - 1, lq, lt - k, lt - 1, lt, 0)
+    else:
+        c = (lq - k, lq - 1, lq, lt - k, lt - 1, lt, 1)
+    return "%s %s %d %d %d %d %d %d %d 0" % ((names[qi], names[ti]) + c)
+
+
+def _irreducible(cands, reads):
+    """IrreducibleBlockListExtractor::extract (src/overlap_builder.cpp:711-809) on explicit extension strings:
+    cands = [(kind, target, k, ext)]; groups split by the next extension symbol; a group ends when a top-length
+    candidate has no extension left, emitting the top-length candidates."""
+    keep = []
+    groups = [(list(cands), 0)]
+    while groups:
+        alive, p = groups.pop()
+        if not alive:
+            continue
+        top = max(c[2] for c in alive)
+        tl = [c for c in alive if c[2] == top]
+        if any(len(c[3]) == p for c in tl):
+            keep.extend(c for c in tl if len(c[3]) == p)
+            continue
+        by = {}
+        for c in alive:
+            if len(c[3]) > p:
+                by.setdefault(c[3][p], []).append(c)
+        for sym in by:
+            groups.append((by[sym], p + 1))
+    return keep
+
+
+def overlap_edges(reads, names, m, exhaustive=False):
+    """Sorted ED payloads `siga overlap -m m [-x]` writes for FIXED-LENGTH reads."""
+    reads = _as_bytes_list(reads)
+    lens = [len(r) for r in reads]
+    edges = []
+    for qi, (lists, contain) in enumerate(_candidates(reads, names, m)):
+        for ti, is_rc in contain:
+            if names[qi] > names[ti]:
+                l = lens[qi]
+                edges.append("%s %s 0 %d %d 0 %d %d %d 0" % (names[qi], names[ti], l - 1, l, l - 1, l, is_rc))
+        if exhaustive:
+            chosen = [(kind, ti, k) for kind in ("SP", "SS", "PP", "PS") for ti, k in lists[kind]]
+        else:
+            right, left = [], []
+            for kind in ("SP", "SS"):
+                for ti, k in lists[kind]:
+                    t = reads[ti] if kind == "SP" else _rc(reads[ti])
+                    right.append((kind, ti, k, t[k:]))
+            for kind in ("PS", "PP"):
+                for ti, k in lists[kind]:
+                    t = reads[ti] if kind == "PS" else _rc(reads[ti])
+                    left.append((kind, ti, k, t[:len(t) - k][::-1]))
+            chosen = [(c[0], c[1], c[2]) for c in _irreducible(right, reads) + _irreducible(left, reads)]
+        for kind, ti, k in chosen:
+            if names[qi] > names[ti]:
+                edges.append(_ed(names, lens, qi, ti, k, kind))
+    return sorted(edges)

@@ -68,13 +68,15 @@ def config_reads(name, scale=1.0):
 
 
 def paired_reads(genome, n_pairs, read_len, rng, insert=1000):
-    """Config-1 shape (paired_read_gen.py:37-54): forward-strand pairs, fixed insert, unique start positions;
-    mate 1 of pair i is read i, mate 2 is read i + n_pairs."""
+    """Config-1 shape (paired_read_gen.py:33-54): forward-strand pairs, mate 1 = ref[pos:pos+K], mate 2 =
+    ref[pos+K+insert : pos+2K+insert], pos uniform in [0, G-2K-insert] without repetition (so pairs are unique;
+    single reads may still coincide across pairs, exactly as with the reference generator).
+    Mate 1 of pair i is read i, mate 2 is read i + n_pairs."""
     g = len(genome)
-    starts = rng.choice(g - insert - read_len, size=n_pairs, replace=False)
+    starts = rng.choice(g - 2 * read_len - insert + 1, size=n_pairs, replace=False)
     ar = np.arange(read_len)[None, :]
     m1 = genome[starts[:, None] + ar]
-    m2 = genome[(starts + insert)[:, None] + ar]
+    m2 = genome[(starts + read_len + insert)[:, None] + ar]
     return np.ascontiguousarray(np.concatenate([m1, m2], axis=0))
 
 

@@ -1,0 +1,198 @@
+"""CPU tests (run with -m "not gpu"): the oracle against the golden vectors, the host-side format logic, the
+test-only host stand-in of the device control logic, and the C-ABI library surface (no compute without a GPU)."""
+import ctypes
+import glob
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle
+from siga_b200 import api, formats, shard, synth
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = sorted(glob.glob(os.path.join(REPO, "tests", "golden", "*.json")))
+
+
+def _load(path):
+    with open(path) as f:
+        return json.load(f)
+
+
+# ------------------------------------------------------------------------------------------------ reference unit tests
+
+def test_alphabet_and_rle_known_answers():
+    # test/index_test.cpp:13-31 : '$ACGT' <-> 0..4 ; test/index_test.cpp:33-84 : AAACGGGTA -> 5 greedy runs
+    sym = np.array([1, 1, 1, 2, 3, 3, 3, 4, 1], dtype=np.uint8)
+    runs = formats.encode_runs(sym)
+    assert [(int(r) >> 5, int(r) & 31) for r in runs] == [(1, 3), (2, 1), (3, 3), (4, 1), (1, 1)]
+    assert np.array_equal(formats.decode_runs(runs), sym)
+    long = np.array([4] * 70 + [0] + [4] * 31, dtype=np.uint8)  # runs are cut at 31 (src/bwt.cpp:16-27)
+    assert [(int(r) >> 5, int(r) & 31) for r in formats.encode_runs(long)] == [(4, 31), (4, 31), (4, 8), (0, 1), (4, 31)]
+
+
+def test_stem_rule_of_output_names():
+    # test/utils_test.cpp:32-36 : Utils::stem("a.txt.gz") == "a" ; restated by the CLI host code, mirrored here
+    def stem(p):
+        for ext in (".gz", ".bz2"):
+            if p.endswith(ext):
+                return stem(p[:-len(ext)])
+        b = os.path.basename(p)
+        return b[:b.rfind(".")] if b.rfind(".") > 0 else b
+    assert stem("a.txt.gz") == "a" and stem("/x/y/reads.fa") == "reads" and stem("reads") == "reads"
+
+
+# ------------------------------------------------------------------------------------------------ oracle vs golden
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-5] for p in GOLDEN])
+def test_oracle_index_matches_reference_bytes(path):
+    fx = _load(path)
+    for algo, model in (("sais2", "B"), ("sais", "A")):
+        for rev, bk, sk in ((False, "bwt_hex", "sai"), (True, "rbwt_hex", "rsai")):
+            bwt, sai = pyoracle.bwt_and_sai(fx["reads"], model, reversed_reads=rev)
+            got = formats.bwt_bytes(len(fx["reads"]), len(bwt), formats.encode_runs(bwt))
+            assert got.hex() == fx["index_" + algo][bk], (algo, bk)
+            assert sai.tolist() == fx["index_" + algo][sk], (algo, sk)
+
+
+@pytest.mark.parametrize("path", [p for p in GOLDEN if any(k in p for k in ("f1_", "random_fixed36", "long_runs"))],
+                         ids=lambda p: os.path.basename(p)[:-5])
+def test_oracle_overlap_model_matches_reference_edges(path):
+    fx = _load(path)
+    if fx["options"].get("no_rc"):
+        pytest.skip("the brute-force model restates the default (both strands) search")
+    if len(set(len(r) for r in fx["reads"])) != 1:
+        pytest.skip("the brute-force model is stated for fixed-length reads (SURVEY.md Appendix B)")
+    want = sorted(l[3:] for l in fx["asqg_sorted"] if l.startswith("ED\t"))
+    got = pyoracle.overlap_edges(fx["reads"], fx["names"], fx["min_overlap"], exhaustive=fx["options"].get("exhaustive", False))
+    assert got == want
+
+
+# ------------------------------------------------------------------------------------------------ host stand-in of the device logic
+
+class _Block(ctypes.Structure):
+    _fields_ = [("capped", ctypes.c_uint64 * 4), ("raw", ctypes.c_uint64 * 4), ("length", ctypes.c_uint32), ("af", ctypes.c_uint32)]
+
+
+def _hostemu():
+    p = os.path.join(REPO, "build", "libhostemu.so")
+    if not os.path.isfile(p):
+        pytest.skip("build/libhostemu.so not built (make hostemu)")
+    lib = ctypes.CDLL(p)
+    lib.hemu_fm_from_rle.restype = ctypes.c_void_p
+    lib.hemu_fm_from_rle.argtypes = [ctypes.c_void_p, ctypes.c_uint64]
+    lib.hemu_fm_free.argtypes = [ctypes.c_void_p]
+    lib.hemu_fm_occ.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p]
+    lib.hemu_overlap.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64,
+                                 ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.POINTER(api._Hits)]
+    lib.hemu_hits_free.argtypes = [ctypes.POINTER(api._Hits)]
+    return lib
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-5] for p in GOLDEN])
+def test_device_control_logic_on_host_matches_reference_hits(path):
+    """overlap_logic.h (the text the CUDA slow path runs) instantiated for one lane, against the reference's .hits."""
+    lib = _hostemu()
+    fx = _load(path)
+    idx = fx["index_sais2"]
+    fr = np.frombuffer(bytes.fromhex(idx["bwt_hex"]), dtype=np.uint8)[30:].copy()
+    rr = np.frombuffer(bytes.fromhex(idx["rbwt_hex"]), dtype=np.uint8)[30:].copy()
+    fwd = lib.hemu_fm_from_rle(fr.ctypes.data, len(fr))
+    rev = lib.hemu_fm_from_rle(rr.ctypes.data, len(rr))
+    # rank structure first: getOcc at every position against the cumulative counts of the decoded BWT
+    sym = formats.decode_runs(fr)
+    pos = np.arange(len(sym), dtype=np.uint64)
+    got = np.zeros((len(sym), 5), dtype=np.uint64)
+    lib.hemu_fm_occ(fwd, pos.ctypes.data, len(pos), got.ctypes.data)
+    assert np.array_equal(got, pyoracle.occ_table(sym))
+    flat, off = synth.reads_to_flat([r.encode() for r in fx["reads"]])
+    h = api._Hits()
+    rc = lib.hemu_overlap(fwd, rev, flat.ctypes.data, off.ctypes.data, len(off) - 1, fx["min_overlap"],
+                          0 if fx["options"].get("exhaustive") else 1, 0 if fx["options"].get("no_rc") else 1, ctypes.byref(h))
+    assert rc == 0
+    blocks = ctypes.cast(h.blocks, ctypes.POINTER(_Block))
+    for i, (sub, want) in enumerate(fx["hits"]):
+        mine = sorted(tuple(blocks[k].capped) + tuple(blocks[k].raw) + (blocks[k].length, blocks[k].af)
+                      for k in range(h.block_off[i], h.block_off[i + 1]))
+        assert mine == [tuple(b) for b in want], (fx["name"], i)
+        assert h.substring[i] == sub
+    lib.hemu_hits_free(ctypes.byref(h))
+    lib.hemu_fm_free(fwd)
+    lib.hemu_fm_free(rev)
+
+
+# ------------------------------------------------------------------------------------------------ host format logic
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-5] for p in GOLDEN])
+def test_hits_to_asqg_conversion_matches_reference(path):
+    """formats.hits_to_edges + asqg_lines = Hit2OverlapConverter + the ASQG writers, fed with the reference's own hits."""
+    fx = _load(path)
+    n = len(fx["reads"])
+    blocks, off = [], [0]
+    for sub, bl in fx["hits"]:
+        for b in bl:
+            blocks.append((tuple(b[0:4]), tuple(b[4:8]), b[8], b[9]))
+        off.append(len(blocks))
+    arr = np.array(blocks, dtype=api.BLOCK_DTYPE) if blocks else np.zeros(0, dtype=api.BLOCK_DTYPE)
+    sub = [s for s, _ in fx["hits"]]
+    idx = fx["index_sais2"]
+    edges = formats.hits_to_edges(fx["names"], [len(r) for r in fx["reads"]], sub, off, arr, idx["sai"], idx["rsai"])
+    lines = formats.asqg_lines(fx["names"], fx["reads"], sub, edges, fx["min_overlap"])
+    assert sorted(lines) == fx["asqg_sorted"]
+    assert lines[0] == "HT\tVN:i:1\tOL:i:%d\tCN:i:1" % fx["min_overlap"] and len([l for l in lines if l.startswith("VT")]) == n
+
+
+def test_bwt_and_sai_file_images_round_trip(tmp_path):
+    fx = _load(GOLDEN[0])
+    raw = bytes.fromhex(fx["index_sais2"]["bwt_hex"])
+    p = tmp_path / "x.bwt"
+    p.write_bytes(raw)
+    ns, nf, runs = formats.read_bwt(str(p))
+    assert formats.bwt_bytes(ns, nf, runs) == raw
+    q = tmp_path / "x.sai"
+    q.write_bytes(formats.sai_bytes(fx["index_sais2"]["sai"]))
+    assert formats.read_sai(str(q)).tolist() == fx["index_sais2"]["sai"]
+
+
+def test_synthetic_configs_have_the_named_shapes():
+    r = synth.config_reads("cfg1")
+    assert r.shape == (20_000, 100) and set(np.unique(r)) <= set(b"ACGT")
+    pairs = np.concatenate([r[:10_000], r[10_000:]], axis=1)
+    assert len(np.unique(pairs, axis=0)) == 10_000  # unique start positions => unique pairs (paired_read_gen.py:38-54)
+    r2 = synth.config_reads("cfg2", 0.01)
+    assert r2.shape == (30_666, 150)
+    assert np.array_equal(r2, synth.config_reads("cfg2", 0.01))  # seeded
+
+
+def test_read_ranges_partition_the_read_set():
+    for n, w in ((10, 3), (3_066_666, 8), (5, 8), (0, 2)):
+        spans = [shard.read_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and sum(c for _, c in spans) == n
+        assert all(spans[i][0] + spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+        assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+
+
+# ------------------------------------------------------------------------------------------------ C-ABI surface
+
+def test_header_and_binding_declare_the_same_symbols():
+    hdr = open(os.path.join(REPO, "include", "siga_b200.h")).read()
+    declared = set(re.findall(r"\b(sgx_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(api.ABI_SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol_and_refuses_to_run_without_a_gpu():
+    if not os.path.isfile(api.LIB_PATH):
+        pytest.skip("libsiga_b200.so not built (run __graft_entry__.build())")
+    lib = api.load_library()
+    for s in api.ABI_SYMBOLS:
+        assert hasattr(lib, s), s
+    assert lib.sgx_abi_version() == 1
+    import torch
+    if not torch.cuda.is_available():
+        h = ctypes.c_void_p()
+        assert lib.sgx_init(0, ctypes.byref(h)) == -2  # SGX_ENODEV: no CPU fallback
+        assert b"no CUDA device" in lib.sgx_last_error(None) or b"cannot run" in lib.sgx_last_error(None)
+        with pytest.raises(api.SgxError):
+            api.Context(0)

@@ -297,3 +297,50 @@ def test_rejects_bad_input(ctx):
     assert e.value.code == -1
     with pytest.raises(api.SgxError):
         ctx.pack_reads(np.frombuffer(b"ACGT", dtype=np.uint8), np.array([0, 0, 4], dtype=np.uint64))  # empty read
+
+
+# ---------------------------------------------------------------------------------------------- committed golden vectors
+
+import glob as _glob
+import json as _json
+
+_GOLDEN = sorted(_glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.json")))
+
+
+@pytest.mark.parametrize("path", _GOLDEN, ids=[os.path.basename(p)[:-5] for p in _GOLDEN])
+def test_cuda_path_reproduces_golden_fixture(ctx, path):
+    """Index bytes, hit blocks and ASQG of the committed reference outputs (tests/golden/make_golden.py)."""
+    fx = _json.load(open(path))
+    reads = [r.encode() for r in fx["reads"]]
+    flat, off = synth.reads_to_flat(reads)
+    n = len(reads)
+    r = ctx.pack_reads(flat, off)
+    try:
+        built = {}
+        for algo, order in (("sais2", api.ORDER_SAIS2), ("sais", api.ORDER_SAIS)):
+            for rev, bk, sk in ((False, "bwt_hex", "sai"), (True, "rbwt_hex", "rsai")):
+                res = ctx.index_build(r, order=order, reversed=rev)
+                assert formats.bwt_bytes(res.n_strings, res.n_suffixes, res.runs).hex() == fx["index_" + algo][bk], (algo, bk)
+                assert res.sai.tolist() == fx["index_" + algo][sk], (algo, sk)
+                built[(algo, rev)] = res
+        fi, ri = built[("sais2", False)], built[("sais2", True)]
+        fwd = ctx.fm_create(fi.runs, fi.n_suffixes)
+        rev = ctx.fm_create(ri.runs, ri.n_suffixes)
+        try:
+            opt = fx["options"]
+            kw = dict(irreducible=not opt.get("exhaustive", False), rc=not opt.get("no_rc", False))
+            for attach in (False, True):
+                if attach:
+                    ctx.fm_attach_reads(fwd, fi.sai, r)
+                    ctx.fm_attach_reads(rev, ri.sai, r)
+                h = ctx.overlap(fwd, rev, r, 0, n, fx["min_overlap"], **kw)
+                for i, (sub, want) in enumerate(fx["hits"]):
+                    assert h.read_blocks(i) == [tuple(b) for b in want], (fx["name"], "attach" if attach else "walk", i)
+                    assert int(h.substring[i]) == sub
+            edges = formats.hits_to_edges(fx["names"], [len(x) for x in reads], h.substring, h.block_off, h.blocks, fi.sai, ri.sai)
+            assert sorted(formats.asqg_lines(fx["names"], fx["reads"], h.substring, edges, fx["min_overlap"])) == fx["asqg_sorted"]
+        finally:
+            ctx.free_fm(fwd)
+            ctx.free_fm(rev)
+    finally:
+        ctx.free_reads(r)
