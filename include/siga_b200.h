@@ -177,6 +177,42 @@ void sgx_hits_free(sgx_hits* hits);
 int sgx_overlap_host(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const char* ascii, const uint64_t* off,
                      uint64_t n, uint32_t min_overlap, int irreducible, int rc, sgx_hits* out);
 
+/*
+ * One ASQG edge before formatting: Hit2OverlapConverter::convert + OverlapBlock::overlap
+ * (src/overlap_builder.cpp:158-175, 345-375) reduced to what the ED line is computed from.  With lq/lt the lengths
+ * of query/target:  c1 = [lq-length, lq-1], flipped when af & SGX_AF_QUERYREV;  c2 = [0, length-1], flipped when
+ * af & SGX_AF_TARGETREV;  isRC = (af & SGX_AF_QUERYCOMP) != 0;  line = "ED\t<q> <t> c1.s c1.e lq c2.s c2.e lt isRC 0".
+ */
+typedef struct sgx_edge {
+  uint32_t query;   /* index of the query read  (id0) */
+  uint32_t target;  /* index of the target read (id1) */
+  uint32_t length;  /* overlap length                 */
+  uint32_t af;      /* SGX_AF_* bits                  */
+} sgx_edge;
+
+typedef struct sgx_edges {
+  uint64_t n_reads;
+  uint8_t* substring;  /* n_reads flags (VT record SS:i tag)                                        */
+  uint64_t n_edges;
+  sgx_edge* edges;     /* grouped by query read, order within a read free                           */
+  uint64_t n_blocks;   /* overlap blocks the edges were expanded from                               */
+  double ms_total, ms_search, ms_extract;
+  uint64_t lookups_search, lookups_extract, launches, search_launches, slow_reads;
+} sgx_edges;
+
+/*
+ * sgx_overlap_batch followed by the reference's hits -> ED conversion, all on the device: replaces the
+ * parallel::foreach body AND the Hits2ASQGConverter pass over the .hits.gz files (src/overlap_builder.cpp:453-480),
+ * which the reference runs serially through text files.  Needs sgx_fm_attach_reads on both indices; `reads` must
+ * be the indexed read set.  name_rank[i] = rank of read i's name in std::string order (equal names, equal ranks):
+ * the reference drops self hits by name and keeps an edge only when id0 is not smaller than id1
+ * (src/overlap_builder.cpp:358-367).
+ */
+int sgx_overlap_edges(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const sgx_reads* reads, uint64_t first,
+                      uint64_t count, uint32_t min_overlap, int irreducible, int rc, const uint32_t* name_rank,
+                      sgx_edges* out);
+void sgx_edges_free(sgx_edges* edges);
+
 /* ---- measurement helpers --------------------------------------------------------------------------------- */
 
 /*

@@ -22,7 +22,7 @@ ABI_SYMBOLS = [
     "sgx_reads_pack", "sgx_reads_free", "sgx_reads_count", "sgx_reads_bases",
     "sgx_index_build", "sgx_index_out_free",
     "sgx_fm_create", "sgx_fm_free", "sgx_fm_attach_reads", "sgx_fm_length", "sgx_fm_pred", "sgx_fm_occ", "sgx_fm_count",
-    "sgx_overlap_batch", "sgx_overlap_host", "sgx_hits_free",
+    "sgx_overlap_batch", "sgx_overlap_host", "sgx_hits_free", "sgx_overlap_edges", "sgx_edges_free",
     "sgx_bench_gather", "sgx_flush_l2",
 ]
 
@@ -49,6 +49,16 @@ class _Hits(ctypes.Structure):
                 ("lookups_extract", ctypes.c_uint64), ("launches", ctypes.c_uint64),
                 ("search_launches", ctypes.c_uint64), ("slow_reads", ctypes.c_uint64)]
 
+
+class _Edges(ctypes.Structure):
+    _fields_ = [("n_reads", ctypes.c_uint64), ("substring", ctypes.POINTER(ctypes.c_uint8)),
+                ("n_edges", ctypes.c_uint64), ("edges", ctypes.c_void_p), ("n_blocks", ctypes.c_uint64),
+                ("ms_total", ctypes.c_double), ("ms_search", ctypes.c_double), ("ms_extract", ctypes.c_double),
+                ("lookups_search", ctypes.c_uint64), ("lookups_extract", ctypes.c_uint64), ("launches", ctypes.c_uint64),
+                ("search_launches", ctypes.c_uint64), ("slow_reads", ctypes.c_uint64)]
+
+
+EDGE_DTYPE = np.dtype([("query", "<u4"), ("target", "<u4"), ("length", "<u4"), ("af", "<u4")])
 
 _lib = None
 
@@ -93,6 +103,9 @@ def load_library():
     lib.sgx_overlap_host.argtypes = [vp, vp, vp, vp, vp, u64, u32, i32, i32, ctypes.POINTER(_Hits)]
     lib.sgx_hits_free.argtypes = [ctypes.POINTER(_Hits)]
     lib.sgx_hits_free.restype = None
+    lib.sgx_overlap_edges.argtypes = [vp, vp, vp, vp, u64, u64, u32, i32, i32, vp, ctypes.POINTER(_Edges)]
+    lib.sgx_edges_free.argtypes = [ctypes.POINTER(_Edges)]
+    lib.sgx_edges_free.restype = None
     lib.sgx_bench_gather.argtypes = [vp, u64, u64, ctypes.POINTER(ctypes.c_double)]
     lib.sgx_flush_l2.argtypes = [vp]
     _lib = lib
@@ -138,6 +151,31 @@ class Hits:
         b = self.blocks[int(self.block_off[i]):int(self.block_off[i + 1])]
         return sorted(tuple(int(x) for x in r["capped"]) + tuple(int(x) for x in r["raw"]) + (int(r["length"]), int(r["af"]))
                       for r in b)
+
+
+class Edges:
+    """Compact edge records (sgx_edge) + per-read SS flags of one sgx_overlap_edges call."""
+
+    def __init__(self, e, copy=True):
+        n, ne = int(e.n_reads), int(e.n_edges)
+        sub = np.ctypeslib.as_array(e.substring, shape=(max(n, 1),))[:n]
+        buf = (ctypes.c_uint8 * (max(ne, 1) * EDGE_DTYPE.itemsize)).from_address(e.edges)
+        edges = np.frombuffer(buf, dtype=EDGE_DTYPE)[:ne]
+        if copy:
+            sub, edges = sub.copy(), edges.copy()
+        self.n_reads, self.substring, self.edges = n, sub, edges
+        self.stats = dict(ms_total=e.ms_total, ms_search=e.ms_search, ms_extract=e.ms_extract,
+                          lookups_search=int(e.lookups_search), lookups_extract=int(e.lookups_extract),
+                          launches=int(e.launches), search_launches=int(e.search_launches),
+                          slow_reads=int(e.slow_reads), n_blocks=int(e.n_blocks), n_edges=ne)
+
+
+def name_ranks(names):
+    """Rank of every read name in std::string (byte-wise) order, equal names sharing a rank."""
+    enc = [n.encode() if isinstance(n, str) else bytes(n) for n in names]
+    order = sorted(set(enc))
+    lut = {nm: i for i, nm in enumerate(order)}
+    return np.array([lut[nm] for nm in enc], dtype=np.uint32)
 
 
 class Context:
@@ -248,6 +286,23 @@ class Context:
         else:
             res._raw = h
         return res
+
+    def overlap_edges(self, fwd, rev, reads, first, count, min_overlap, name_rank, irreducible=True, rc=True, copy=True):
+        name_rank = np.ascontiguousarray(name_rank, dtype=np.uint32)
+        e = _Edges()
+        self._check(self.lib.sgx_overlap_edges(self.h, fwd, rev, reads, int(first), int(count), int(min_overlap),
+                                               1 if irreducible else 0, 1 if rc else 0, _ptr(name_rank), ctypes.byref(e)))
+        res = Edges(e, copy=copy)
+        if copy:
+            self.lib.sgx_edges_free(ctypes.byref(e))
+        else:
+            res._raw = e
+        return res
+
+    def free_edges(self, edges):
+        if getattr(edges, "_raw", None) is not None:
+            self.lib.sgx_edges_free(ctypes.byref(edges._raw))
+            edges._raw = None
 
     def free_hits(self, hits):
         if getattr(hits, "_raw", None) is not None:

@@ -277,6 +277,23 @@ int sgx_overlap_host(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const c
   return rcode;
 }
 
+int sgx_overlap_edges(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const sgx_reads* reads, uint64_t first,
+                      uint64_t count, uint32_t min_overlap, int irreducible, int rc, const uint32_t* name_rank,
+                      sgx_edges* out) {
+  if (!ctx || !out) return SGX_EINVAL;
+  SGX_ENTRY_BEGIN(ctx)
+  overlap_edges_run(ctx, fwd, rev, reads, first, count, min_overlap, irreducible, rc, name_rank, out);
+  SGX_ENTRY_END(ctx)
+}
+
+void sgx_edges_free(sgx_edges* edges) {
+  if (!edges) return;
+  pinned_put(edges->substring);
+  pinned_put(edges->edges);
+  edges->substring = nullptr;
+  edges->edges = nullptr;
+}
+
 void sgx_hits_free(sgx_hits* hits) {
   if (!hits) return;
   pinned_put(hits->substring);

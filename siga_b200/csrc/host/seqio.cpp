@@ -1,0 +1,250 @@
+#include "seqio.h"
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+
+namespace sgxhost {
+
+namespace {
+
+bool ends_with(const std::string& s, const std::string& p) {
+  return s.size() >= p.size() && s.compare(s.size() - p.size(), p.size(), p) == 0;
+}
+
+void trim(std::string& s) {
+  size_t b = 0, e = s.size();
+  while (b < e && isspace((unsigned char)s[b])) ++b;
+  while (e > b && isspace((unsigned char)s[e - 1])) --e;
+  if (b > 0 || e < s.size()) s = s.substr(b, e - b);
+}
+
+// Line reader over gzread (plain files pass through zlib unchanged).
+class LineReader {
+ public:
+  explicit LineReader(const std::string& path) : buf_(1 << 20), pos_(0), len_(0) {
+    f_ = gzopen(path.c_str(), "rb");
+    if (f_) gzbuffer(f_, 1 << 20);
+  }
+  ~LineReader() {
+    if (f_) gzclose(f_);
+  }
+  bool ok() const { return f_ != NULL; }
+  int peek() {
+    if (pos_ >= len_ && !fill()) return -1;
+    return (unsigned char)buf_[pos_];
+  }
+  bool getline(std::string& line) {
+    line.clear();
+    bool any = false;
+    for (;;) {
+      if (pos_ >= len_ && !fill()) return any;
+      any = true;
+      const char* p = &buf_[pos_];
+      const char* nl = (const char*)memchr(p, '\n', len_ - pos_);
+      if (nl) {
+        line.append(p, nl - p);
+        pos_ += (nl - p) + 1;
+        return true;
+      }
+      line.append(p, len_ - pos_);
+      pos_ = len_;
+    }
+  }
+
+ private:
+  bool fill() {
+    int n = gzread(f_, buf_.data(), (unsigned)buf_.size());
+    if (n <= 0) return false;
+    pos_ = 0;
+    len_ = (size_t)n;
+    return true;
+  }
+  gzFile f_;
+  std::vector<char> buf_;
+  size_t pos_, len_;
+};
+
+void split_name(const std::string& header, std::string* name, std::string* comment) {
+  size_t i = header.find_first_of(" \t");
+  if (i != std::string::npos) {
+    *name = header.substr(0, i);
+    *comment = header.substr(i + 1);
+  } else {
+    *name = header;
+    comment->clear();
+  }
+}
+
+void push(ReadSet* rs, const std::string& header, const std::string& seq) {
+  std::string name, comment;
+  split_name(header, &name, &comment);
+  rs->names.push_back(name);
+  rs->comments.push_back(comment);
+  rs->bases += seq;
+  rs->off.push_back(rs->bases.size());
+}
+
+}  // namespace
+
+bool read_sequences(const std::string& path, ReadSet* out, std::string* err) {
+  LineReader in(path);
+  if (!in.ok()) {
+    *err = "Failed to open input file " + path;
+    return false;
+  }
+  out->names.clear();
+  out->comments.clear();
+  out->bases.clear();
+  out->off.assign(1, 0);
+  const int first = in.peek();
+  std::string line;
+  if (first == '>') {
+    std::string name, seq;
+    bool have = false;
+    while (in.getline(line)) {
+      trim(line);
+      if (line.empty()) continue;
+      if (line[0] == '>') {
+        if (have && !seq.empty()) push(out, name, seq);
+        else if (have) break;  // the reference stops at a header that follows an empty record (src/kseq.cpp:207-210)
+        name = line.substr(1);
+        seq.clear();
+        have = true;
+      } else {
+        seq += line;
+      }
+    }
+    if (have && !seq.empty()) push(out, name, seq);
+    return true;
+  }
+  if (first == '@') {
+    int state = 0;
+    std::string name, seq;
+    while (in.getline(line)) {
+      trim(line);
+      if (line.empty()) continue;
+      if (state == 0) {
+        if (line[0] != '@') break;
+        name = line.substr(1);
+        state = 1;
+      } else if (state == 1) {
+        seq = line;
+        state = 2;
+      } else if (state == 2) {
+        if (!(line[0] == '+' && (line.size() == 1 || ends_with(line, name)))) break;
+        state = 3;
+      } else {
+        if (line.size() != seq.size()) break;
+        push(out, name, seq);
+        state = 0;
+      }
+    }
+    return true;
+  }
+  *err = "failed to create dna reader (the file starts with neither '>' nor '@'): " + path;
+  return false;
+}
+
+std::string stem(const std::string& path) {
+  if (ends_with(path, ".gz")) return stem(path.substr(0, path.size() - 3));
+  if (ends_with(path, ".bz2")) return stem(path.substr(0, path.size() - 4));
+  std::string f = path;
+  size_t k = f.find_last_of('/');
+  if (k != std::string::npos) f = f.substr(k + 1);
+  k = f.find_last_of('.');
+  if (k != std::string::npos && k != 0) f = f.substr(0, k);
+  return f;
+}
+
+bool write_bwt(const std::string& path, uint64_t n_strings, uint64_t n_suffixes, const uint8_t* runs, uint64_t n_runs) {
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f) return false;
+  const uint16_t magic = 0xCACA;
+  const int32_t flag = 0;  // BWF_NOFMI
+  bool ok = fwrite(&magic, 2, 1, f) == 1 && fwrite(&n_strings, 8, 1, f) == 1 && fwrite(&n_suffixes, 8, 1, f) == 1 &&
+            fwrite(&n_runs, 8, 1, f) == 1 && fwrite(&flag, 4, 1, f) == 1;
+  if (ok && n_runs) ok = fwrite(runs, 1, n_runs, f) == n_runs;
+  return fclose(f) == 0 && ok;
+}
+
+bool write_sai(const std::string& path, const uint32_t* ids, uint64_t n) {
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f) return false;
+  std::string buf;
+  buf.reserve(1 << 22);
+  char tmp[64];
+  int k = snprintf(tmp, sizeof(tmp), "%u\n%llu\n%llu\n", 0xCACAu, (unsigned long long)n, (unsigned long long)n);
+  buf.append(tmp, k);
+  bool ok = true;
+  for (uint64_t i = 0; i < n && ok; ++i) {
+    // "<read> 0\n" : only full-length suffixes are listed (src/suffix_array.cpp:36-43)
+    char* p = tmp + sizeof(tmp);
+    *--p = '\n';
+    *--p = '0';
+    *--p = ' ';
+    uint32_t v = ids[i];
+    do {
+      *--p = (char)('0' + v % 10);
+      v /= 10;
+    } while (v);
+    buf.append(p, tmp + sizeof(tmp) - p);
+    if (buf.size() > (1 << 22) - 64) {
+      ok = fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+      buf.clear();
+    }
+  }
+  if (ok && !buf.empty()) ok = fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+  return fclose(f) == 0 && ok;
+}
+
+bool read_bwt(const std::string& path, uint64_t* n_strings, uint64_t* n_suffixes, std::vector<uint8_t>* runs) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  uint16_t magic = 0;
+  uint64_t n_runs = 0;
+  int32_t flag = 0;
+  bool ok = fread(&magic, 2, 1, f) == 1 && magic == 0xCACA && fread(n_strings, 8, 1, f) == 1 &&
+            fread(n_suffixes, 8, 1, f) == 1 && fread(&n_runs, 8, 1, f) == 1 && fread(&flag, 4, 1, f) == 1;
+  if (ok) {
+    runs->resize(n_runs);
+    if (n_runs) ok = fread(runs->data(), 1, n_runs, f) == n_runs;
+  }
+  fclose(f);
+  return ok;
+}
+
+bool read_sai(const std::string& path, std::vector<uint32_t>* ids) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  unsigned long long magic = 0, n = 0, m = 0;
+  bool ok = fscanf(f, "%llu %llu %llu", &magic, &n, &m) == 3 && magic == 0xCACA;
+  if (ok) {
+    ids->resize(n);
+    for (unsigned long long i = 0; i < n && ok; ++i) {
+      unsigned long long a = 0, b = 0;
+      ok = fscanf(f, "%llu %llu", &a, &b) == 2;
+      (*ids)[i] = (uint32_t)a;
+    }
+  }
+  fclose(f);
+  return ok;
+}
+
+std::vector<uint32_t> name_ranks(const std::vector<std::string>& names) {
+  std::vector<uint32_t> order(names.size());
+  std::iota(order.begin(), order.end(), 0u);
+  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return names[a] < names[b]; });
+  std::vector<uint32_t> rank(names.size());
+  uint32_t r = 0;
+  for (size_t i = 0; i < order.size(); ++i) {
+    if (i > 0 && names[order[i]] != names[order[i - 1]]) ++r;
+    rank[order[i]] = r;
+  }
+  return rank;
+}
+
+}  // namespace sgxhost

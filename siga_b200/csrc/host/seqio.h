@@ -1,0 +1,42 @@
+// Host-side sequence input and SGA-compatible output writers of the `siga` front-end.
+//
+// Mirrors, re-implemented on zlib, the behaviour of the reference's readers/writers on the index/overlap path:
+//   FASTA/FASTQ readers        src/kseq.cpp:127-228  (format chosen by the first byte; multi-line FASTA joined; name =
+//                              text up to the first blank/tab, the rest is the comment, src/kseq.cpp:71-79)
+//   Utils::stem                src/utils.cpp:128-135 (strip .gz/.bz2, directory and one extension)
+//   .bwt / .sai writers        src/bwt.cpp:121-178, src/suffix_array.cpp:16-43
+//   .bwt / .sai readers        src/bwt.cpp:59-98, src/suffix_array.cpp:56-95
+#ifndef SGX_HOST_SEQIO_H_
+#define SGX_HOST_SEQIO_H_
+
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+namespace sgxhost {
+
+struct ReadSet {
+  std::vector<std::string> names;
+  std::vector<std::string> comments;
+  std::string bases;            // all reads back to back
+  std::vector<uint64_t> off;    // n + 1 offsets into bases
+  size_t size() const { return names.size(); }
+};
+
+// Returns false (with a message in *err) when the file cannot be read or is not FASTA/FASTQ.
+bool read_sequences(const std::string& path, ReadSet* out, std::string* err);
+
+std::string stem(const std::string& path);
+
+bool write_bwt(const std::string& path, uint64_t n_strings, uint64_t n_suffixes, const uint8_t* runs, uint64_t n_runs);
+bool write_sai(const std::string& path, const uint32_t* ids, uint64_t n);
+bool read_bwt(const std::string& path, uint64_t* n_strings, uint64_t* n_suffixes, std::vector<uint8_t>* runs);
+bool read_sai(const std::string& path, std::vector<uint32_t>* ids);
+
+// Rank of every name in std::string order (equal names share a rank).
+std::vector<uint32_t> name_ranks(const std::vector<std::string>& names);
+
+}  // namespace sgxhost
+
+#endif  // SGX_HOST_SEQIO_H_

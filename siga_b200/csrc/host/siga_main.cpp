@@ -1,0 +1,418 @@
+// `siga` front-end of the B200 build: the reference's `index` and `overlap` sub-commands with the same options and
+// the same SGA-compatible outputs, the work itself done by libsiga_b200 (include/siga_b200.h).
+//
+//   siga index   [-a sais|sais2] [-t N] [-p PREFIX] [--no-forward] [--no-reverse] [--device D] READS
+//       mirrors Indexer::run (src/indexer.cpp:25-104): writes PREFIX.sai/.bwt (and .rsai/.rbwt for the reversed reads)
+//   siga overlap [-m LEN] [-t N] [--batch-size N] [-p PREFIX] [-x] [--no-opposite-strand] [--device D] READS
+//       mirrors Overlapping::run + OverlapBuilder::build (src/overlap.cpp:24-54, src/overlap_builder.cpp:423-509):
+//       loads PREFIX.bwt/.rbwt/.sai/.rsai, writes PREFIX.asqg.gz (HT, VT in input order, then ED)
+//
+// Option defaults are the reference's CODE defaults (min-overlap 10, algorithm sais2).
+// -t/--threads only sizes the host-side output formatting/compression pool; -c/--log4cxx and -s/--ini are accepted
+// and ignored (there is no log4cxx here).  The per-thread .hits.gz files of the reference are an internal detail
+// nothing downstream reads and are not produced.
+#include <getopt.h>
+#include <strings.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../../include/siga_b200.h"
+#include "seqio.h"
+
+using namespace sgxhost;
+
+namespace {
+
+double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+void info(const char* fmt, ...) __attribute__((format(printf, 1, 2)));
+void info(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  fprintf(stderr, "INFO siga - ");
+  vfprintf(stderr, fmt, ap);
+  fprintf(stderr, "\n");
+  va_end(ap);
+}
+
+int fail(sgx_ctx* ctx, const char* what, int rc) {
+  fprintf(stderr, "ERROR siga - %s failed (%d): %s\n", what, rc, sgx_last_error(ctx));
+  return -1;
+}
+
+// One gzip member per chunk, compressed on worker threads, written in order (multi-member gzip is what zlib's and
+// boost's readers, hence `siga assemble`, accept).
+class GzChunkWriter {
+ public:
+  GzChunkWriter(const std::string& path, unsigned threads) : f_(fopen(path.c_str(), "wb")), threads_(threads ? threads : 1) {}
+  ~GzChunkWriter() {
+    if (f_) fclose(f_);
+  }
+  bool ok() const { return f_ != NULL; }
+  // produce(i, &text) fills the text of chunk i in [0, n); chunks are emitted in index order.
+  template <class F>
+  bool write_chunks(size_t n, F produce) {
+    bool good = true;
+    for (size_t base = 0; base < n && good; base += threads_) {
+      const size_t m = std::min<size_t>(threads_, n - base);
+      std::vector<std::string> gz(m);
+      std::vector<std::thread> pool;
+      for (size_t t = 0; t < m; ++t) {
+        pool.emplace_back([&, t]() {
+          std::string text;
+          produce(base + t, &text);
+          gz[t] = deflate_member(text);
+        });
+      }
+      for (auto& th : pool) th.join();
+      for (size_t t = 0; t < m && good; ++t) good = fwrite(gz[t].data(), 1, gz[t].size(), f_) == gz[t].size();
+    }
+    return good;
+  }
+
+ private:
+  static std::string deflate_member(const std::string& text) {
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    deflateInit2(&zs, Z_DEFAULT_COMPRESSION, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY);
+    std::string out(deflateBound(&zs, text.size()) + 64, '\0');
+    zs.next_in = (Bytef*)text.data();
+    zs.avail_in = (uInt)text.size();
+    zs.next_out = (Bytef*)&out[0];
+    zs.avail_out = (uInt)out.size();
+    deflate(&zs, Z_FINISH);
+    out.resize(zs.total_out);
+    deflateEnd(&zs);
+    return out;
+  }
+  FILE* f_;
+  unsigned threads_;
+};
+
+void append_uint(std::string* s, uint64_t v) {
+  char tmp[24];
+  char* p = tmp + sizeof(tmp);
+  do {
+    *--p = (char)('0' + v % 10);
+    v /= 10;
+  } while (v);
+  s->append(p, tmp + sizeof(tmp) - p);
+}
+
+// CR:i / BX:Z / EX:Z tags carried in the read comment (src/overlap_builder.cpp:304-316, src/asqg.h:29-60).
+void append_comment_tags(const std::string& comment, std::string* line) {
+  if (comment.empty()) return;
+  std::string cr, bx, ex;
+  size_t b = 0;
+  while (b <= comment.size()) {
+    size_t e = comment.find(' ', b);
+    if (e == std::string::npos) e = comment.size();
+    const std::string tok = comment.substr(b, e - b);
+    b = e + 1;
+    if (tok.size() < 2) continue;
+    const std::string key = tok.substr(0, 2);
+    if (key != "CR" && key != "BX" && key != "EX") continue;
+    // TagValue::fromstring: exactly KEY:type:value with the right type code
+    size_t c1 = tok.find(':'), c2 = c1 == std::string::npos ? c1 : tok.find(':', c1 + 1);
+    if (c1 == std::string::npos || c2 == std::string::npos || tok.find(':', c2 + 1) != std::string::npos) continue;
+    if (c2 - c1 != 2) continue;
+    const char type = tok[c1 + 1];
+    const std::string val = tok.substr(c2 + 1);
+    if (key == "CR") {
+      if (type != 'i') continue;
+      cr = "CR:i:" + std::to_string(atoi(val.c_str()));
+    } else {
+      if (type != 'Z') continue;
+      (key == "BX" ? bx : ex) = key + ":Z:" + val;
+    }
+  }
+  // writer order: SS, CR, BX, EX (src/asqg.cpp:171-186)
+  for (const std::string* t : {&cr, &bx, &ex}) {
+    if (!t->empty()) {
+      *line += '\t';
+      *line += *t;
+    }
+  }
+}
+
+struct CommonOpts {
+  std::string prefix;
+  int threads = 1;
+  int device = 0;
+  bool help = false;
+};
+
+int usage_index() {
+  printf("siga index [OPTION] ... READSFILE\n"
+         "Index the reads in READSFILE using a suffixarray/bwt (built on the GPU)\n\n"
+         "      -h, --help                       display this help and exit\n\n"
+         "      -a, --algorithm=STR              suffix ordering of the BWT. STR can be:\n"
+         "                                       sais  - equal suffixes ordered by read index\n"
+         "                                       sais2 - plain suffix order of the concatenated reads (default)\n"
+         "      -t, --threads=NUM                host threads for output formatting (default: 1)\n"
+         "      -p, --prefix=PREFIX              write index to file using PREFIX instead of prefix of READSFILE\n"
+         "          --no-forward                 suppress construction of the forward BWT.\n"
+         "          --no-reverse                 suppress construction of the reverse BWT.\n"
+         "          --device=NUM                 CUDA device (default: 0)\n\n");
+  return 256;
+}
+
+int usage_overlap() {
+  printf("siga overlap [OPTION] ... READSFILE\n"
+         "Compute pairwise overlap between all the sequences in READS (searched on the GPU)\n\n"
+         "      -h, --help                       display this help and exit\n\n"
+         "      -t, --threads=NUM                host threads for output formatting/compression (default: 1)\n"
+         "          --batch-size=NUM             accepted for compatibility (batching is internal)\n"
+         "      -m, --min-overlap=LEN            minimum overlap required between two reads (default: 10)\n"
+         "      -p, --prefix=PREFIX              read the index from / write the graph to PREFIX instead of prefix of READSFILE\n"
+         "      -x, --exhaustive                 output all overlaps, including transitive edges\n"
+         "          --no-opposite-strand         treat all reads as forward strand\n"
+         "          --device=NUM                 CUDA device (default: 0)\n\n");
+  return 256;
+}
+
+int cmd_index(int argc, char** argv) {
+  enum { OPT_NO_REVERSE = 1000, OPT_NO_FORWARD, OPT_DEVICE };
+  static const option longopts[] = {{"log4cxx", required_argument, nullptr, 'c'}, {"ini", required_argument, nullptr, 's'},
+                                    {"prefix", required_argument, nullptr, 'p'},  {"threads", required_argument, nullptr, 't'},
+                                    {"algorithm", required_argument, nullptr, 'a'}, {"no-reverse", no_argument, nullptr, OPT_NO_REVERSE},
+                                    {"no-forward", no_argument, nullptr, OPT_NO_FORWARD}, {"device", required_argument, nullptr, OPT_DEVICE},
+                                    {"help", no_argument, nullptr, 'h'},          {nullptr, 0, nullptr, 0}};
+  CommonOpts o;
+  std::string algorithm = "sais2";
+  bool fwd = true, rev = true;
+  int c;
+  while ((c = getopt_long(argc, argv, "c:s:a:t:p:g:h", longopts, nullptr)) != -1) {
+    switch (c) {
+      case 'a': algorithm = optarg; break;
+      case 't': o.threads = atoi(optarg); break;
+      case 'p': o.prefix = optarg; break;
+      case OPT_NO_REVERSE: rev = false; break;
+      case OPT_NO_FORWARD: fwd = false; break;
+      case OPT_DEVICE: o.device = atoi(optarg); break;
+      case 'h': o.help = true; break;
+      default: break;
+    }
+  }
+  if (o.help || argc - optind != 1) return usage_index();
+  const std::string input = argv[optind];
+  const std::string output = o.prefix.empty() ? stem(input) : o.prefix;
+  info("input: %s", input.c_str());
+  info("output: %s.(.sai|.bwt|.rsai|.rbwt)", output.c_str());
+  info("algorithm: %s", algorithm.c_str());
+  int order;
+  if (strcasecmp(algorithm.c_str(), "sais") == 0) order = SGX_ORDER_SAIS;
+  else if (strcasecmp(algorithm.c_str(), "sais2") == 0) order = SGX_ORDER_SAIS2;
+  else {
+    // the reference accepts "rope" and silently writes nothing; refuse instead
+    fprintf(stderr, "ERROR siga - Failed to create suffix array builder algorithm %s\n", algorithm.c_str());
+    return -1;
+  }
+  const double t0 = now_s();
+  ReadSet rs;
+  std::string err;
+  info("loading reads: %s", input.c_str());
+  if (!read_sequences(input, &rs, &err)) {
+    fprintf(stderr, "ERROR siga - %s\n", err.c_str());
+    return -1;
+  }
+  sgx_ctx* ctx = nullptr;
+  int rc = sgx_init(o.device, &ctx);
+  if (rc != SGX_OK) return fail(nullptr, "sgx_init", rc);
+  sgx_reads* reads = nullptr;
+  rc = sgx_reads_pack(ctx, rs.bases.data(), rs.off.data(), rs.size(), &reads);
+  if (rc != SGX_OK) return fail(ctx, "sgx_reads_pack", rc);
+  for (int pass = 0; pass < 2; ++pass) {
+    if ((pass == 0 && !fwd) || (pass == 1 && !rev)) continue;
+    info("building %s index on device %d", pass == 0 ? "forward" : "reverse", o.device);
+    sgx_index_out out;
+    rc = sgx_index_build(ctx, reads, order, pass, &out);
+    if (rc != SGX_OK) return fail(ctx, "sgx_index_build", rc);
+    const std::string sa = output + (pass == 0 ? ".sai" : ".rsai"), bw = output + (pass == 0 ? ".bwt" : ".rbwt");
+    if (!write_sai(sa, out.sai, out.n_strings) || !write_bwt(bw, out.n_strings, out.n_suffixes, out.rle, out.n_runs)) {
+      fprintf(stderr, "ERROR siga - failed to write %s / %s\n", sa.c_str(), bw.c_str());
+      return -1;
+    }
+    info("%s: %llu strings, %llu suffixes, %llu runs; device %.1f ms (%llu kernel launches)", bw.c_str(),
+         (unsigned long long)out.n_strings, (unsigned long long)out.n_suffixes, (unsigned long long)out.n_runs, out.ms_total,
+         (unsigned long long)out.launches);
+    sgx_index_out_free(&out);
+  }
+  sgx_reads_free(reads);
+  sgx_shutdown(ctx);
+  info("wall: %.3f sec", now_s() - t0);
+  return 0;
+}
+
+int cmd_overlap(int argc, char** argv) {
+  enum { OPT_BATCH_SIZE = 1000, OPT_NO_RC, OPT_DEVICE };
+  static const option longopts[] = {{"log4cxx", required_argument, nullptr, 'c'},   {"ini", required_argument, nullptr, 's'},
+                                    {"prefix", required_argument, nullptr, 'p'},    {"threads", required_argument, nullptr, 't'},
+                                    {"batch-size", required_argument, nullptr, OPT_BATCH_SIZE},
+                                    {"min-overlap", required_argument, nullptr, 'm'}, {"exhaustive", no_argument, nullptr, 'x'},
+                                    {"no-opposite-strand", no_argument, nullptr, OPT_NO_RC},
+                                    {"device", required_argument, nullptr, OPT_DEVICE}, {"help", no_argument, nullptr, 'h'},
+                                    {nullptr, 0, nullptr, 0}};
+  CommonOpts o;
+  unsigned min_overlap = 10;
+  bool exhaustive = false, rcomp = true;
+  int c;
+  while ((c = getopt_long(argc, argv, "c:s:t:p:m:xh", longopts, nullptr)) != -1) {
+    switch (c) {
+      case 't': o.threads = atoi(optarg); break;
+      case 'p': o.prefix = optarg; break;
+      case 'm': min_overlap = (unsigned)atoi(optarg); break;
+      case 'x': exhaustive = true; break;
+      case OPT_NO_RC: rcomp = false; break;
+      case OPT_DEVICE: o.device = atoi(optarg); break;
+      case 'h': o.help = true; break;
+      default: break;
+    }
+  }
+  if (o.help || argc - optind != 1) return usage_overlap();
+  if (o.threads <= 0) o.threads = (int)std::thread::hardware_concurrency();
+  const std::string input = argv[optind];
+  const std::string output = o.prefix.empty() ? stem(input) : o.prefix;
+  info("input: %s", input.c_str());
+  info("output: %s.asqg.gz", output.c_str());
+  const double t0 = now_s();
+
+  uint64_t ns = 0, nf = 0, rns = 0, rnf = 0;
+  std::vector<uint8_t> runs, rruns;
+  std::vector<uint32_t> sai, rsai;
+  if (!read_bwt(output + ".bwt", &ns, &nf, &runs) || !read_bwt(output + ".rbwt", &rns, &rnf, &rruns)) {
+    fprintf(stderr, "ERROR siga - Failed to load FMIndex from %s\n", input.c_str());
+    return -1;
+  }
+  if (!read_sai(output + ".sai", &sai) || !read_sai(output + ".rsai", &rsai)) {
+    fprintf(stderr, "ERROR siga - failed to load suffix array index %s\n", output.c_str());
+    return -1;
+  }
+  ReadSet rs;
+  std::string err;
+  if (!read_sequences(input, &rs, &err)) {
+    fprintf(stderr, "ERROR siga - %s\n", err.c_str());
+    return -1;
+  }
+  if (rs.size() != ns || rs.size() != sai.size() || rs.size() != rsai.size()) {
+    fprintf(stderr, "ERROR siga - %s holds %zu reads but the index was built from %llu\n", input.c_str(), rs.size(),
+            (unsigned long long)ns);
+    return -1;
+  }
+  const double t_load = now_s();
+
+  sgx_ctx* ctx = nullptr;
+  int rc = sgx_init(o.device, &ctx);
+  if (rc != SGX_OK) return fail(nullptr, "sgx_init", rc);
+  sgx_reads* reads = nullptr;
+  sgx_fm *fwd = nullptr, *rev = nullptr;
+  if ((rc = sgx_reads_pack(ctx, rs.bases.data(), rs.off.data(), rs.size(), &reads)) != SGX_OK) return fail(ctx, "sgx_reads_pack", rc);
+  if ((rc = sgx_fm_create(ctx, runs.data(), runs.size(), nf, &fwd)) != SGX_OK) return fail(ctx, "sgx_fm_create", rc);
+  if ((rc = sgx_fm_create(ctx, rruns.data(), rruns.size(), rnf, &rev)) != SGX_OK) return fail(ctx, "sgx_fm_create", rc);
+  if ((rc = sgx_fm_attach_reads(ctx, fwd, sai.data(), sai.size(), reads)) != SGX_OK) return fail(ctx, "sgx_fm_attach_reads", rc);
+  if ((rc = sgx_fm_attach_reads(ctx, rev, rsai.data(), rsai.size(), reads)) != SGX_OK) return fail(ctx, "sgx_fm_attach_reads", rc);
+  info("fm-index: %llu symbols in %zu runs (%.4f symbols per run)", (unsigned long long)nf, runs.size(),
+       runs.empty() ? 0.0 : (double)nf / runs.size());
+  const std::vector<uint32_t> rank = name_ranks(rs.names);
+  sgx_edges ed;
+  rc = sgx_overlap_edges(ctx, fwd, rev, reads, 0, rs.size(), min_overlap, exhaustive ? 0 : 1, rcomp ? 1 : 0, rank.data(), &ed);
+  if (rc != SGX_OK) return fail(ctx, "sgx_overlap_edges", rc);
+  const double t_search = now_s();
+  info("processed %zu sequences: %llu blocks, %llu edges; device %.1f ms (search %.1f ms, post %.1f ms; %llu rank lookups)",
+       rs.size(), (unsigned long long)ed.n_blocks, (unsigned long long)ed.n_edges, ed.ms_total, ed.ms_search, ed.ms_extract,
+       (unsigned long long)(ed.lookups_search + ed.lookups_extract));
+
+  // ---- ASQG: HT, all VT (input order), all ED (src/bigraph.cpp:532-616 requires this order)
+  GzChunkWriter gz(output + ".asqg.gz", (unsigned)o.threads);
+  if (!gz.ok()) {
+    fprintf(stderr, "ERROR siga - Failed to create ASQG %s.asqg.gz\n", output.c_str());
+    return -1;
+  }
+  const size_t n = rs.size();
+  const size_t vt_chunk = 1 << 16, ed_chunk = 1 << 18;
+  const size_t n_vt = (n + vt_chunk - 1) / vt_chunk, n_ed = (ed.n_edges + ed_chunk - 1) / ed_chunk;
+  bool good = gz.write_chunks(1 + n_vt + n_ed, [&](size_t ci, std::string* text) {
+    if (ci == 0) {
+      *text = "HT\tVN:i:1\tOL:i:" + std::to_string(min_overlap) + "\tCN:i:1\n";  // IN/ER/TE are never set on this path
+    } else if (ci <= n_vt) {
+      const size_t b = (ci - 1) * vt_chunk, e = std::min(n, b + vt_chunk);
+      text->reserve((e - b) * 200);
+      for (size_t i = b; i < e; ++i) {
+        *text += "VT\t";
+        *text += rs.names[i];
+        *text += '\t';
+        text->append(rs.bases, rs.off[i], rs.off[i + 1] - rs.off[i]);
+        *text += ed.substring[i] ? "\tSS:i:1" : "\tSS:i:0";
+        append_comment_tags(rs.comments[i], text);
+        *text += '\n';
+      }
+    } else {
+      const size_t b = (ci - 1 - n_vt) * ed_chunk, e = std::min<size_t>(ed.n_edges, b + ed_chunk);
+      text->reserve((e - b) * 48);
+      for (size_t k = b; k < e; ++k) {
+        const sgx_edge& g = ed.edges[k];
+        const uint64_t lq = rs.off[g.query + 1] - rs.off[g.query], lt = rs.off[g.target + 1] - rs.off[g.target];
+        uint64_t s0 = lq - g.length, e0 = lq - 1, s1 = 0, e1 = g.length - 1;
+        if (g.af & SGX_AF_QUERYREV) {
+          const uint64_t t = s0;
+          s0 = lq - 1 - e0;
+          e0 = lq - 1 - t;
+        }
+        if (g.af & SGX_AF_TARGETREV) {
+          const uint64_t t = s1;
+          s1 = lt - 1 - e1;
+          e1 = lt - 1 - t;
+        }
+        *text += "ED\t";
+        *text += rs.names[g.query];
+        *text += ' ';
+        *text += rs.names[g.target];
+        for (uint64_t v : {s0, e0, lq, s1, e1, lt}) {
+          *text += ' ';
+          append_uint(text, v);
+        }
+        *text += (g.af & SGX_AF_QUERYCOMP) ? " 1 0\n" : " 0 0\n";
+      }
+    }
+  });
+  if (!good) {
+    fprintf(stderr, "ERROR siga - write to %s.asqg.gz failed\n", output.c_str());
+    return -1;
+  }
+  sgx_edges_free(&ed);
+  sgx_fm_free(fwd);
+  sgx_fm_free(rev);
+  sgx_reads_free(reads);
+  sgx_shutdown(ctx);
+  const double t1 = now_s();
+  info("wall: %.3f sec (load %.3f, gpu %.3f, write %.3f)", t1 - t0, t_load - t0, t_search - t_load, t1 - t_search);
+  return 0;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  if (argc < 2 || !strcmp(argv[1], "-h") || !strcmp(argv[1], "--help")) {
+    printf("siga (B200 build) -- Usage: siga <command> [<args>]\n\n"
+           "   index       build the BWT and FM-index for a set of reads\n"
+           "   overlap     compute overlaps between reads\n\n"
+           "See 'siga <command> -h' to read about a specific subcommand.\n");
+    return 256;
+  }
+  const std::string cmd = argv[1];
+  if (cmd == "index") return cmd_index(argc - 1, argv + 1);
+  if (cmd == "overlap") return cmd_overlap(argc - 1, argv + 1);
+  fprintf(stderr, "siga: '%s' is not provided by this build (only the index/overlap hot path is)\n", cmd.c_str());
+  return 256;
+}

@@ -106,17 +106,31 @@ __global__ void ov_gather_kernel(const sgx_block* __restrict__ out, const uint32
   for (uint32_t w = lane; w < words; w += 32) d[w] = src[w];
 }
 
-void overlap_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const sgx_reads* reads, uint64_t first,
-                 uint64_t count, uint32_t min_ov, int irreducible, int rc, sgx_hits* hits) {
+// all_off[b0 + i] = base + batch_off[i] for i in [0, bn] : per-read block offsets into the compact array
+__global__ void ov_offsets_kernel(const uint64_t* __restrict__ batch_off, uint64_t bn, uint64_t base,
+                                  uint64_t* __restrict__ all_off) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= bn) all_off[i] = base + batch_off[i];
+}
+
+// Device-resident result of the search + post stages (blocks of all reads, compacted).
+struct OvCore {
+  DevBuf<sgx_block> compact;
+  uint64_t n_blocks = 0;
+  DevBuf<uint8_t> sub;        // [count] substring flags
+  DevBuf<uint64_t> off;       // [count + 1] block offsets
+  sgx_hits stats;             // timing / counter fields only
+};
+
+static void overlap_core(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const sgx_reads* reads, uint64_t first,
+                         uint64_t count, uint32_t min_ov, int irreducible, int rc, OvCore& core,
+                         KernelClock& k_search, KernelClock& k_post) {
   static_assert(sizeof(sgx_block) == 72, "sgx_block layout");
-  SGX_REQUIRE(fwd && rev && reads && hits, SGX_EINVAL, "sgx_overlap_batch: null argument");
+  SGX_REQUIRE(fwd && rev && reads, SGX_EINVAL, "sgx_overlap_batch: null argument");
   SGX_REQUIRE(first <= reads->n && count <= reads->n - first, SGX_EINVAL, "sgx_overlap_batch: read range out of bounds");
   SGX_REQUIRE(min_ov >= 1, SGX_EINVAL, "sgx_overlap_batch: min_overlap must be >= 1");
+  sgx_hits* hits = &core.stats;
   memset(hits, 0, sizeof(*hits));
-  const uint64_t launches0 = ctx->launches;
-  EventTimer t_all(ctx->stream);
-  KernelClock k_search(ctx->stream), k_post(ctx->stream);
-  t_all.start();
 
   const uint32_t lmax = reads->max_len;
   const uint32_t find_cap = lmax > min_ov ? lmax - min_ov : 1;
@@ -128,7 +142,9 @@ void overlap_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const sgx_r
 
   DevBuf<sgx_block> d_cand(batch * 4 * find_cap), d_contain(batch * 4), d_out(batch * out_cap);
   DevBuf<uint32_t> d_ncand(batch * 4), d_ncontain(batch * 4), d_nout(batch), d_status(1);
-  DevBuf<uint8_t> d_sub(std::max<uint64_t>(count, 1));
+  DevBuf<uint8_t>& d_sub = core.sub;
+  d_sub.alloc(std::max<uint64_t>(count, 1));
+  core.off.alloc(count + 1);
   DevBuf<uint64_t> d_off(batch + 1), d_ws(scan_ws_elems(batch + 1)), d_total(1);
   DevBuf<unsigned long long> d_look(2);
   SGX_CUDA(cudaMemsetAsync(d_sub.p, 0, std::max<uint64_t>(count, 1), ctx->stream));
@@ -188,11 +204,9 @@ void overlap_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const sgx_r
     d_slow.alloc(batch);
   }
 
-  DevBuf<sgx_block> d_compact;           // all blocks of all batches
+  DevBuf<sgx_block>& d_compact = core.compact;  // all blocks of all batches
   uint64_t compact_cap = 0, compact_n = 0;
-  std::vector<uint64_t> h_off(count + 1, 0);
-  PinnedBuf<uint64_t> h_batch_off;
-  h_batch_off.alloc(batch + 1);
+  if (count == 0) SGX_CUDA(cudaMemsetAsync(core.off.p, 0, sizeof(uint64_t), ctx->stream));
 
   for (uint64_t b0 = 0; b0 < count; b0 += batch) {
     const uint64_t bn = std::min<uint64_t>(batch, count - b0);
@@ -268,9 +282,9 @@ void overlap_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const sgx_r
     // compact
     SGX_LAUNCH(ctx, ov_widen_kernel, grid_for(bn + 1, 256), 256, 0, (const uint32_t*)d_nout.p, bn, d_off.p);
     scan_exclusive(ctx, d_off.p, bn + 1, d_ws.p, (uint64_t*)nullptr);
-    SGX_CUDA(cudaMemcpyAsync(h_batch_off.p, d_off.p, (bn + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    uint64_t btotal = 0;
+    SGX_CUDA(cudaMemcpyAsync(&btotal, d_off.p + bn, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     SGX_CUDA(cudaStreamSynchronize(ctx->stream));
-    const uint64_t btotal = h_batch_off.p[bn];
     if (compact_n + btotal > compact_cap) {
       uint64_t ncap = std::max<uint64_t>(compact_n + btotal, compact_cap * 2);
       if (b0 == 0 && bn < count) ncap = std::max<uint64_t>(ncap, (uint64_t)((double)btotal / bn * count * 1.1) + 1024);
@@ -287,10 +301,32 @@ void overlap_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const sgx_r
     if (btotal)
       SGX_LAUNCH(ctx, ov_gather_kernel, grid_for(bn * 32, 256), 256, 0, (const sgx_block*)bt.out,
                  (const uint32_t*)d_nout.p, bt.out_cap, (const uint64_t*)d_off.p, bn, d_compact.p + compact_n);
-    for (uint64_t i = 0; i < bn; ++i) h_off[b0 + i] = compact_n + h_batch_off.p[i];
+    SGX_LAUNCH(ctx, ov_offsets_kernel, grid_for(bn + 1, 256), 256, 0, (const uint64_t*)d_off.p, bn, compact_n,
+               core.off.p + b0);
     compact_n += btotal;
   }
-  h_off[count] = compact_n;
+  core.n_blocks = compact_n;
+  unsigned long long look[2] = {0, 0};
+  SGX_CUDA(cudaMemcpyAsync(look, d_look.p, sizeof(look), cudaMemcpyDeviceToHost, ctx->stream));
+  SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+  hits->lookups_search = look[0];
+  hits->lookups_extract = look[1];
+}
+
+void overlap_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const sgx_reads* reads, uint64_t first,
+                 uint64_t count, uint32_t min_ov, int irreducible, int rc, sgx_hits* hits) {
+  SGX_REQUIRE(hits, SGX_EINVAL, "sgx_overlap_batch: null output");
+  memset(hits, 0, sizeof(*hits));
+  const uint64_t launches0 = ctx->launches;
+  EventTimer t_all(ctx->stream);
+  KernelClock k_search(ctx->stream), k_post(ctx->stream);
+  t_all.start();
+  OvCore core;
+  overlap_core(ctx, fwd, rev, reads, first, count, min_ov, irreducible, rc, core, k_search, k_post);
+  *hits = core.stats;
+  const uint64_t compact_n = core.n_blocks;
+  DevBuf<sgx_block>& d_compact = core.compact;
+  DevBuf<uint8_t>& d_sub = core.sub;
 
   // copy out
   hits->n_reads = count;
@@ -298,20 +334,107 @@ void overlap_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const sgx_r
   hits->substring = (uint8_t*)pinned_get(ctx, std::max<uint64_t>(count, 1));
   hits->block_off = (uint64_t*)pinned_get(ctx, (count + 1) * sizeof(uint64_t));
   hits->blocks = (sgx_block*)pinned_get(ctx, std::max<uint64_t>(compact_n, 1) * sizeof(sgx_block));
-  memcpy(hits->block_off, h_off.data(), (count + 1) * sizeof(uint64_t));
+  SGX_CUDA(cudaMemcpyAsync(hits->block_off, core.off.p, (count + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
   if (count) SGX_CUDA(cudaMemcpyAsync(hits->substring, d_sub.p, count, cudaMemcpyDeviceToHost, ctx->stream));
   if (compact_n)
     SGX_CUDA(cudaMemcpyAsync(hits->blocks, d_compact.p, compact_n * sizeof(sgx_block), cudaMemcpyDeviceToHost, ctx->stream));
-  unsigned long long look[2] = {0, 0};
-  SGX_CUDA(cudaMemcpyAsync(look, d_look.p, sizeof(look), cudaMemcpyDeviceToHost, ctx->stream));
   t_all.stop();
   SGX_CUDA(cudaStreamSynchronize(ctx->stream));
   hits->ms_total = t_all.ms();
   hits->ms_search = k_search.total_ms();
   hits->ms_extract = k_post.total_ms();
-  hits->lookups_search = look[0];
-  hits->lookups_extract = look[1];
   hits->launches = ctx->launches - launches0;
+}
+
+// ---- hits -> edges on the device: Hit2OverlapConverter::convert (src/overlap_builder.cpp:345-375) ------------------
+// One thread per query read walks its blocks and the rows of each capped[0] interval.  An edge survives when the
+// target is another read (by name), the query name is not smaller than the target name, and it is not a
+// containment seen from the reversed query (src/overlap_builder.cpp:358-367).  Names enter as ranks.
+template <bool WRITE>
+__global__ void ov_edges_kernel(const sgx_block* __restrict__ blocks, const uint64_t* __restrict__ off, uint64_t first,
+                                uint64_t count, const uint32_t* __restrict__ qlen, SaView sf, SaView sr,
+                                const uint32_t* __restrict__ tlen, const uint32_t* __restrict__ name_rank,
+                                uint64_t* __restrict__ cnt, sgx_edge* __restrict__ edges) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= count) return;
+  const uint32_t q = (uint32_t)(first + r);
+  const uint32_t lq = qlen[q];
+  const uint32_t rq = name_rank[q];
+  uint64_t n = 0;
+  uint64_t at = WRITE ? cnt[r] : 0;
+  for (uint64_t b = off[r]; b < off[r + 1]; ++b) {
+    const sgx_block blk = blocks[b];
+    const uint32_t k = blk.length, af = blk.af;
+    const uint32_t* sa = (af & SGX_AF_TARGETREV) ? sr.sa : sf.sa;
+    for (uint64_t j = blk.capped[0]; j <= blk.capped[1]; ++j) {
+      const uint32_t t = sa[j];
+      const uint32_t rt = name_rank[t];
+      if (rq == rt) continue;                       // query.name == target.name
+      const bool contain = k == lq || k == tlen[t];  // either coordinate spans its whole read
+      if (rq < rt || (contain && (af & SGX_AF_QUERYREV))) continue;
+      if (WRITE) {
+        sgx_edge e;
+        e.query = q;
+        e.target = t;
+        e.length = k;
+        e.af = af;
+        edges[at + n] = e;
+      }
+      ++n;
+    }
+  }
+  if (!WRITE) cnt[r] = n;
+}
+
+void overlap_edges_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const sgx_reads* reads, uint64_t first,
+                       uint64_t count, uint32_t min_ov, int irreducible, int rc, const uint32_t* name_rank,
+                       sgx_edges* out) {
+  SGX_REQUIRE(out && name_rank, SGX_EINVAL, "sgx_overlap_edges: null argument");
+  SGX_REQUIRE(fwd && rev && fwd->sai && rev->sai && fwd->indexed && fwd->indexed == rev->indexed, SGX_EINVAL,
+              "sgx_overlap_edges: both indices need sgx_fm_attach_reads");
+  SGX_REQUIRE(reads == fwd->indexed, SGX_EINVAL, "sgx_overlap_edges: the query reads must be the indexed read set");
+  memset(out, 0, sizeof(*out));
+  const uint64_t launches0 = ctx->launches;
+  EventTimer t_all(ctx->stream);
+  KernelClock k_search(ctx->stream), k_post(ctx->stream);
+  t_all.start();
+  OvCore core;
+  overlap_core(ctx, fwd, rev, reads, first, count, min_ov, irreducible, rc, core, k_search, k_post);
+  const uint64_t n_all = fwd->indexed->n;
+  DevBuf<uint32_t> d_rank(n_all);
+  SGX_CUDA(cudaMemcpyAsync(d_rank.p, name_rank, n_all * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  DevBuf<uint64_t> d_cnt(count + 1), d_ws(scan_ws_elems(count + 1)), d_total(1);
+  SGX_CUDA(cudaMemsetAsync(d_cnt.p, 0, (count + 1) * sizeof(uint64_t), ctx->stream));
+  SaView sf{fwd->sai, fwd->inv}, sr{rev->sai, rev->inv};
+  SGX_LAUNCH(ctx, ov_edges_kernel<false>, grid_for(count, 256), 256, 0, (const sgx_block*)core.compact.p,
+             (const uint64_t*)core.off.p, first, count, (const uint32_t*)reads->len, sf, sr,
+             (const uint32_t*)fwd->indexed->len, (const uint32_t*)d_rank.p, d_cnt.p, (sgx_edge*)nullptr);
+  scan_exclusive(ctx, d_cnt.p, count + 1, d_ws.p, (uint64_t*)nullptr);
+  uint64_t n_edges = 0;
+  SGX_CUDA(cudaMemcpyAsync(&n_edges, d_cnt.p + count, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+  DevBuf<sgx_edge> d_edges(std::max<uint64_t>(n_edges, 1));
+  SGX_LAUNCH(ctx, ov_edges_kernel<true>, grid_for(count, 256), 256, 0, (const sgx_block*)core.compact.p,
+             (const uint64_t*)core.off.p, first, count, (const uint32_t*)reads->len, sf, sr,
+             (const uint32_t*)fwd->indexed->len, (const uint32_t*)d_rank.p, d_cnt.p, d_edges.p);
+  out->n_reads = count;
+  out->n_edges = n_edges;
+  out->n_blocks = core.n_blocks;
+  out->substring = (uint8_t*)pinned_get(ctx, std::max<uint64_t>(count, 1));
+  out->edges = (sgx_edge*)pinned_get(ctx, std::max<uint64_t>(n_edges, 1) * sizeof(sgx_edge));
+  if (count) SGX_CUDA(cudaMemcpyAsync(out->substring, core.sub.p, count, cudaMemcpyDeviceToHost, ctx->stream));
+  if (n_edges)
+    SGX_CUDA(cudaMemcpyAsync(out->edges, d_edges.p, n_edges * sizeof(sgx_edge), cudaMemcpyDeviceToHost, ctx->stream));
+  t_all.stop();
+  SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+  out->ms_total = t_all.ms();
+  out->ms_search = k_search.total_ms();
+  out->ms_extract = k_post.total_ms();
+  out->lookups_search = core.stats.lookups_search;
+  out->lookups_extract = core.stats.lookups_extract;
+  out->slow_reads = core.stats.slow_reads;
+  out->search_launches = core.stats.search_launches;
+  out->launches = ctx->launches - launches0;
 }
 
 }  // namespace sgx

@@ -126,6 +126,25 @@ def hits_to_edges(names, lengths, substring, block_off, blocks, sai, rsai):
     return edges
 
 
+def edges_to_ed(names, lengths, edges):
+    """ED payload strings of compact edge records (sgx_edge): the coordinates of OverlapBlock::overlap
+    (src/overlap_builder.cpp:158-175) printed like Overlap's writer (src/coord.cpp:66-80)."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    q, t = edges["query"].astype(np.int64), edges["target"].astype(np.int64)
+    k, af = edges["length"].astype(np.int64), edges["af"].astype(np.int64)
+    lq, lt = lengths[q], lengths[t]
+    s0, e0 = lq - k, lq - 1
+    qr = (af & AF_QUERYREV) != 0
+    s0, e0 = np.where(qr, lq - 1 - e0, s0), np.where(qr, lq - 1 - (lq - k), e0)
+    s1, e1 = np.zeros_like(k), k - 1
+    tr = (af & AF_TARGETREV) != 0
+    s1, e1 = np.where(tr, lt - 1 - e1, s1), np.where(tr, lt - 1, e1)
+    rc = ((af & AF_QUERYCOMP) != 0).astype(np.int64)
+    return ["%s %s %d %d %d %d %d %d %d 0" % (names[a], names[b], c, d, e, f, g, h, i)
+            for a, b, c, d, e, f, g, h, i in zip(q.tolist(), t.tolist(), s0.tolist(), e0.tolist(), lq.tolist(),
+                                                 s1.tolist(), e1.tolist(), lt.tolist(), rc.tolist())]
+
+
 def asqg_lines(names, seqs, substring, edges, min_overlap):
     """HT / VT / ED lines exactly as OverlapBuilder::build emits them (src/overlap_builder.cpp:428-437, 301-322,
     410-413; src/asqg.cpp:93-124, 171-186, 228-237)."""

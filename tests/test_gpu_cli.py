@@ -1,0 +1,81 @@
+"""The `siga` front-end of this repo against the compiled reference binary: same sub-commands, same files."""
+import gzip
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import refrun
+from siga_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(REPO, "siga_b200", "bin", "siga")
+
+
+def _run(args, cwd):
+    r = subprocess.run([CLI] + args, cwd=cwd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return r
+
+
+def _asqg(path):
+    with gzip.open(path, "rt") as f:
+        return [l.rstrip("\n") for l in f]
+
+
+@pytest.mark.skipif(not refrun.have_ref(), reason="compiled reference (oracle/_ref/siga) not present")
+@pytest.mark.skipif(not os.path.isfile(CLI), reason="siga_b200/bin/siga not built")
+@pytest.mark.parametrize("case", ["fasta_fixed", "fastq_comments", "sais_exhaustive_norc"])
+def test_cli_outputs_match_reference(case):
+    rng = np.random.default_rng(17)
+    g = synth.random_genome(4000, rng)
+    reads = synth.sample_reads(g, 1500, 60, rng, err=0.01)
+    reads[rng.integers(0, 1500, 40)] = reads[rng.integers(0, 1500, 40)]
+    with tempfile.TemporaryDirectory() as d:
+        ours, ref = os.path.join(d, "ours"), os.path.join(d, "ref")
+        os.mkdir(ours)
+        os.mkdir(ref)
+        if case == "fastq_comments":
+            name = "reads.fq"
+            with open(os.path.join(d, name), "w") as f:
+                for i, r in enumerate(reads):
+                    tag = " CR:i:%d BX:Z:bc%d junk" % (i % 7, i % 3) if i % 2 else ""
+                    f.write("@q%d%s\n%s\n+\n%s\n" % (i, tag, r.tobytes().decode(), "I" * 60))
+        else:
+            name = "reads.fa"
+            with open(os.path.join(d, name), "w") as f:
+                for i, r in enumerate(reads):
+                    s = r.tobytes().decode()
+                    f.write(">r%d\n%s\n%s\n" % (i, s[:35], s[35:]))  # multi-line FASTA records are joined
+        src = os.path.join(d, name)
+        iargs = ["-a", "sais"] if case == "sais_exhaustive_norc" else []
+        oargs = ["-x", "--no-opposite-strand"] if case == "sais_exhaustive_norc" else []
+        refrun.run_ref(["index"] + iargs + [src], ref)
+        refrun.run_ref(["overlap", "-m", "20", "-t", "3"] + oargs + [src], ref)
+        _run(["index"] + iargs + [src], ours)
+        _run(["overlap", "-m", "20", "-t", "3"] + oargs + [src], ours)
+        for ext in (".bwt", ".rbwt", ".sai", ".rsai"):
+            a = open(os.path.join(ours, "reads" + ext), "rb").read()
+            b = open(os.path.join(ref, "reads" + ext), "rb").read()
+            assert a == b, ext
+        mine, want = _asqg(os.path.join(ours, "reads.asqg.gz")), _asqg(os.path.join(ref, "reads.asqg.gz"))
+        n = len(reads)
+        assert mine[:1 + n] == want[:1 + n]          # HT, then VT in input order (incl. SS/CR/BX tags)
+        assert sorted(mine[1 + n:]) == sorted(want[1 + n:])  # ED set (the reference emits them in thread order)
+        assert all(l.startswith("ED\t") for l in mine[1 + n:])
+
+
+@pytest.mark.skipif(not os.path.isfile(CLI), reason="siga_b200/bin/siga not built")
+def test_cli_prefix_and_errors(tmp_path):
+    fa = tmp_path / "x.fa"
+    fa.write_text(">a\nACGTACGTACGTAAAC\n>b\nGTACGTAAACTTTTGG\n")
+    _run(["index", "-p", "pfx", "--no-reverse", str(fa)], str(tmp_path))
+    assert (tmp_path / "pfx.bwt").exists() and (tmp_path / "pfx.sai").exists() and not (tmp_path / "pfx.rbwt").exists()
+    r = subprocess.run([CLI, "index", "-a", "rope", str(fa)], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode != 0  # the reference silently writes nothing here; we refuse
+    r = subprocess.run([CLI, "overlap", "-p", "missing", str(fa)], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode != 0 and "Failed to load FMIndex" in r.stderr

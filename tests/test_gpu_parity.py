@@ -188,6 +188,9 @@ def _overlap_vs_ref(ctx, reads, m, exhaustive=False, no_rc=False, names=None):
         ctx.fm_attach_reads(rev, rsai, r)
         h = ctx.overlap(fwd, rev, r, 0, len(off) - 1, m, irreducible=not exhaustive, rc=not no_rc)
         hh = ctx.overlap_host(fwd, rev, flat, off, m, irreducible=not exhaustive, rc=not no_rc)
+        nm0 = names if names is not None else ["r%d" % i for i in range(len(off) - 1)]
+        dev_edges = ctx.overlap_edges(fwd, rev, r, 0, len(off) - 1, m, api.name_ranks(nm0), irreducible=not exhaustive,
+                                      rc=not no_rc)
         assert np.array_equal(h.block_off, h_walk.block_off) and np.array_equal(h.substring, h_walk.substring)
         diff = [i for i in range(len(off) - 1) if h.read_blocks(i) != h_walk.read_blocks(i)]
         assert not diff, ("fast path differs from the BWT-walking path", diff[:5], h.read_blocks(diff[0]), h_walk.read_blocks(diff[0]))
@@ -212,6 +215,9 @@ def _overlap_vs_ref(ctx, reads, m, exhaustive=False, no_rc=False, names=None):
     mine = formats.asqg_lines(nm, seqs, h.substring, edges, m)
     assert sorted(mine) == sorted(ref_asqg)
     assert mine[:1 + n] == ref_asqg[:1 + n]  # HT + VT lines come in input order
+    # device-side hits -> ED conversion (sgx_overlap_edges) yields the same edge set
+    assert sorted(formats.edges_to_ed(nm, lens, dev_edges.edges)) == sorted(edges)
+    assert np.array_equal(dev_edges.substring, h.substring)
     return h
 
 
