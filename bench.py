@@ -227,19 +227,23 @@ def main():
         base_counts = np.bincount(flat, minlength=256)[[65, 67, 71, 84]]
         assert np.array_equal(sym_counts[1:], base_counts)
 
+    names = ["r%d" % i for i in range(n_reads)]
+    name_rank = api.name_ranks(names)
+    lengths = np.full(n_reads, read_len, dtype=np.int64)
+
     sampler.start()
-    # ---- overlap, inputs resident in HBM ("value")
+    # ---- overlap, inputs resident in HBM ("value"): search + post + hits->edges on the device, edges copied out
     for _ in range(args.warmup):
-        h = ctx.overlap(fwd, rev, r_dev, 0, n_reads, MIN_OVERLAP, copy=False)
-        ctx.free_hits(h)
+        e = ctx.overlap_edges(fwd, rev, r_dev, 0, n_reads, MIN_OVERLAP, name_rank, copy=False)
+        ctx.free_edges(e)
     barrier()
     t0 = time.perf_counter()
     dev_ms = search_ms = extract_ms = 0.0
     look_s = look_e = launches = search_launches = 0
     d2h_bytes = 0
     for _ in range(args.steps):
-        h = ctx.overlap(fwd, rev, r_dev, 0, n_reads, MIN_OVERLAP, copy=False)
-        st = h.stats
+        e = ctx.overlap_edges(fwd, rev, r_dev, 0, n_reads, MIN_OVERLAP, name_rank, copy=False)
+        st = e.stats
         dev_ms += st["ms_total"]
         search_ms += st["ms_search"]
         extract_ms += st["ms_extract"]
@@ -247,27 +251,46 @@ def main():
         look_e += st["lookups_extract"]
         launches += st["launches"]
         search_launches += st["search_launches"]
-        d2h_bytes = int(h.blocks.nbytes + h.block_off.nbytes + h.substring.nbytes)
+        d2h_bytes = int(e.edges.nbytes + e.substring.nbytes)
         n_blocks = st["n_blocks"]
+        n_edges = st["n_edges"]
         slow_reads = st["slow_reads"]
-        ctx.free_hits(h)
+        ctx.free_edges(e)
     barrier()
     ms_step = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
     total_reads = n_reads * world
     value = total_reads / (ms_step * 1e-3)
 
-    # ---- overlap end to end through the C ABI with HOST buffers ("e2e")
+    # size-independent parity property at full size: the edge set is closed under the reference's symmetry -- every
+    # overlap is found from both reads, and exactly one of the two directions survives the id0 >= id1 rule
+    chk = ctx.overlap_edges(fwd, rev, r_dev, 0, n_reads, MIN_OVERLAP, name_rank)
+    ed = chk.edges
+    assert len(ed) == n_edges and np.all(name_rank[ed["query"]] > name_rank[ed["target"]])
+    assert np.all((ed["length"] >= MIN_OVERLAP) & (ed["length"] <= read_len))
+
+    # ---- overlap end to end through the C ABI with HOST buffers ("e2e"): pack the pinned host reads, attach the
+    #      host .sai/.rsai, search, convert, copy the edges out
+    def e2e_step():
+        rr = ctx.pack_reads(flat, off)
+        ctx.fm_attach_reads(fwd, fi.sai, rr)
+        ctx.fm_attach_reads(rev, ri.sai, rr)
+        ee = ctx.overlap_edges(fwd, rev, rr, 0, n_reads, MIN_OVERLAP, name_rank, copy=False)
+        nb = int(ee.edges.nbytes + ee.substring.nbytes)
+        ctx.free_edges(ee)
+        ctx.free_reads(rr)
+        return nb
     for _ in range(2):
-        h = ctx.overlap_host(fwd, rev, flat, off, MIN_OVERLAP, copy=False)
-        ctx.free_hits(h)
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        h = ctx.overlap_host(fwd, rev, flat, off, MIN_OVERLAP, copy=False)
-        ctx.free_hits(h)
+        e2e_d2h = e2e_step()
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
     e2e_value = total_reads / (e2e_ms * 1e-3)
+    ctx.fm_attach_reads(fwd, fi.sai, r_dev)
+    ctx.fm_attach_reads(rev, ri.sai, r_dev)
+    e2e_h2d = int(flat.nbytes + off.nbytes + 2 * fi.sai.nbytes + name_rank.nbytes)
 
     # ---- index build (fwd + rev), resident and end to end
     isteps = args.index_steps or min(args.steps, 3)
@@ -320,15 +343,16 @@ def main():
                          (fi.n_suffixes / 256 * 128 / 1e6)},
         "device_ms_per_step": dev_ms / args.steps,
         "gpu_launches": int(launches),
-        "e2e": {"value": e2e_value, "unit": "reads/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": d2h_bytes, "entry": "sgx_overlap_host (pinned host reads in, hit blocks out)"},
+        "e2e": {"value": e2e_value, "unit": "reads/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": e2e_h2d,
+                "d2h_bytes_per_step": e2e_d2h,
+                "entry": "sgx_reads_pack + sgx_fm_attach_reads x2 + sgx_overlap_edges (pinned host reads / .sai / name ranks in, edges + SS flags out)"},
         "roofline": {"bound": "hbm", "kernel": "ov_search_kernel", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": ach_gbs / hbm_peak, "traffic": None, "peak_kind": peak_kind + " STREAM copy",
                      "lookups_per_read": look_s / args.steps / n_reads, "lookups_per_s": look_s / args.steps / search_s if search_s else 0,
                      "random_gather_128B_per_s": gather,
                      "frac_of_random_gather": (look_s / args.steps / search_s) / gather if gather and search_s else None,
                      "search_ms": search_ms / args.steps, "extract_ms": extract_ms / args.steps,
-                     "extract_lookups_per_read": look_e / args.steps / n_reads, "blocks_per_read": n_blocks / n_reads,
+                     "extract_lookups_per_read": look_e / args.steps / n_reads, "blocks_per_read": n_blocks / n_reads, "edges_per_read": n_edges / n_reads,
                      "slow_path_reads": slow_reads},
         "index": {"metric": "bwt_build_gbases_per_s", "value": bases * world / (idx_ms * 1e-3) / 1e9, "unit": "Gbases/s",
                   "ms_per_step": idx_ms, "steps": isteps, "device_ms_per_step": idx_dev_ms / isteps, "scaling": "replicas only (round 1)",
