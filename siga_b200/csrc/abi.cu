@@ -21,6 +21,47 @@ void sgx_set_error(sgx_ctx* ctx, const char* msg) {
 namespace sgx {
 
 thread_local cudaStream_t g_stream = nullptr;
+thread_local sgx_ctx* g_ctx = nullptr;
+
+void* ws_get(size_t bytes) {
+  sgx_ctx* ctx = g_ctx;
+  int best = -1;
+  for (size_t i = 0; i < ctx->ws_cache.size(); ++i) {
+    const sgx_ctx::WsEntry& e = ctx->ws_cache[i];
+    if (!e.in_use && e.bytes >= bytes && e.bytes <= bytes + bytes / 2 + (1u << 20) &&
+        (best < 0 || e.bytes < ctx->ws_cache[best].bytes))
+      best = (int)i;
+  }
+  if (best >= 0) {
+    ctx->ws_cache[best].in_use = true;
+    return ctx->ws_cache[best].p;
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {
+    // out of memory: drop every idle cached area and retry once
+    cudaGetLastError();
+    SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < ctx->ws_cache.size();) {
+      if (!ctx->ws_cache[i].in_use) {
+        cudaFree(ctx->ws_cache[i].p);
+        ctx->ws_cache.erase(ctx->ws_cache.begin() + i);
+      } else {
+        ++i;
+      }
+    }
+    SGX_CUDA(cudaMalloc(&p, bytes));
+  }
+  ctx->ws_cache.push_back(sgx_ctx::WsEntry{p, bytes, true});
+  return p;
+}
+
+void ws_put(void* p) {
+  sgx_ctx* ctx = g_ctx;
+  if (!ctx) return;
+  for (auto& e : ctx->ws_cache)
+    if (e.p == p) e.in_use = false;
+}
 
 void* pinned_get(sgx_ctx* ctx, size_t bytes) {
   if (bytes == 0) bytes = 1;
@@ -170,6 +211,9 @@ void sgx_shutdown(sgx_ctx* ctx) {
   }
   if (ctx->flush_buf) cudaFreeAsync(ctx->flush_buf, ctx->stream);
   cudaStreamSynchronize(ctx->stream);
+  for (auto& e : ctx->ws_cache) cudaFree(e.p);
+  ctx->ws_cache.clear();
+  if (sgx::g_ctx == ctx) sgx::g_ctx = nullptr;
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

@@ -128,7 +128,8 @@ __global__ void fm_header_kernel(FmBlockLane* __restrict__ blocks, uint64_t nb, 
 
 sgx_fm* fm_build_from_symbols(sgx_ctx* ctx, const uint8_t* sym_dev, uint64_t n) {
   const uint64_t nb = fm_num_blocks(n);
-  DevBuf<FmBlockLane> blocks(nb * kGroup);
+  DevBuf<FmBlockLane> blocks;  // becomes the fm object's storage
+  blocks.alloc_owned(nb * kGroup);
   DevBuf<uint64_t> cnt(4 * nb), ws(scan_ws_elems(4 * nb)), total(1);
   SGX_LAUNCH(ctx, fm_pack_kernel, grid_for(nb * kGroup, 256), 256, 0, sym_dev, n, nb, blocks.p, cnt.p);
   scan_exclusive(ctx, cnt.p, 4 * nb, ws.p, total.p);
@@ -174,7 +175,9 @@ __global__ void sai_inverse_kernel(const uint32_t* __restrict__ sai, uint64_t n,
 void fm_attach(sgx_ctx* ctx, sgx_fm* fm, const uint32_t* sai, uint64_t n, const sgx_reads* indexed) {
   SGX_REQUIRE(sai && indexed && n == indexed->n, SGX_EINVAL, "sgx_fm_attach_reads: sai / read set size mismatch");
   SGX_REQUIRE(n + indexed->bases == fm->n, SGX_EINVAL, "sgx_fm_attach_reads: read set does not match the BWT length");
-  DevBuf<uint32_t> d_sai(n), d_inv(n), d_bad(1);
+  DevBuf<uint32_t> d_sai, d_inv, d_bad(1);  // sai / inv become the fm object's storage
+  d_sai.alloc_owned(n);
+  d_inv.alloc_owned(n);
   SGX_CUDA(cudaMemcpyAsync(d_sai.p, sai, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   SGX_CUDA(cudaMemsetAsync(d_bad.p, 0, sizeof(uint32_t), ctx->stream));
   SGX_LAUNCH(ctx, sai_inverse_kernel, grid_for(n, 256), 256, 0, (const uint32_t*)d_sai.p, n, d_inv.p, d_bad.p);

@@ -291,11 +291,7 @@ static void overlap_core(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, con
       DevBuf<sgx_block> nbuf(ncap);
       if (compact_n)
         SGX_CUDA(cudaMemcpyAsync(nbuf.p, d_compact.p, compact_n * sizeof(sgx_block), cudaMemcpyDeviceToDevice, ctx->stream));
-      SGX_CUDA(cudaStreamSynchronize(ctx->stream));
-      sgx_block* old = d_compact.take();
-      if (old) cudaFreeAsync(old, ctx->stream);
-      d_compact.p = nbuf.take();
-      d_compact.n = ncap;
+      d_compact.swap(nbuf);  // the old area is released when nbuf goes out of scope (stream ordered)
       compact_cap = ncap;
     }
     if (btotal)

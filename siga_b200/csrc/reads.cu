@@ -77,8 +77,10 @@ sgx_reads* reads_pack(sgx_ctx* ctx, const char* ascii, const uint64_t* off, uint
   const uint64_t total = off[n] - off[0];
   SGX_REQUIRE(off[n] >= off[0] && total > 0, SGX_EINVAL, "sgx_reads_pack: bad offsets");
   DevBuf<char> d_ascii(total);
-  DevBuf<uint64_t> d_off(n + 1), d_woff(n + 1), ws(scan_ws_elems(n + 1));
-  DevBuf<uint32_t> d_len(n), d_flags(3);
+  DevBuf<uint64_t> d_off(n + 1), d_woff, ws(scan_ws_elems(n + 1));
+  DevBuf<uint32_t> d_len, d_flags(3);
+  d_woff.alloc_owned(n + 1);  // woff / len / words become the read store
+  d_len.alloc_owned(n);
   SGX_CUDA(cudaMemcpyAsync(d_ascii.p, ascii + off[0], total, cudaMemcpyHostToDevice, ctx->stream));
   SGX_CUDA(cudaMemcpyAsync(d_off.p, off, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
   const uint32_t init[3] = {0xffffffffu, 0u, 0u};  // min, max, bad
@@ -94,7 +96,8 @@ sgx_reads* reads_pack(sgx_ctx* ctx, const char* ascii, const uint64_t* off, uint
   SGX_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
   SGX_CUDA(cudaStreamSynchronize(ctx->stream));
   SGX_REQUIRE((flags[2] & 1u) == 0, SGX_EINVAL, "sgx_reads_pack: empty read or non-monotonic offsets");
-  DevBuf<uint32_t> d_words(n_words);
+  DevBuf<uint32_t> d_words;
+  d_words.alloc_owned(n_words);
   // the offsets handed to the pack kernel are relative to the uploaded slice
   const uint64_t base = off[0];
   if (base != 0) {

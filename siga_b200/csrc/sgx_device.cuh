@@ -23,6 +23,13 @@ struct sgx_ctx {
   size_t flush_bytes;
   // pinned host buffers handed back by *_free calls, reused by later calls (pinned allocation is slow)
   std::vector<std::pair<void*, size_t> > pinned_free;
+  // large device work areas, kept for the lifetime of the context and handed out again to later calls
+  struct WsEntry {
+    void* p;
+    size_t bytes;
+    bool in_use;
+  };
+  std::vector<WsEntry> ws_cache;
 };
 
 namespace sgx {
@@ -60,32 +67,70 @@ struct Error {
 // multi-GB work areas of one call are reused by the next instead of going back to the driver (cudaMalloc/cudaFree
 // of those sizes cost up to hundreds of milliseconds each).
 extern thread_local cudaStream_t g_stream;
+extern thread_local sgx_ctx* g_ctx;
+// Work areas of >= kWsMinBytes come from the context's cache (first use: cudaMalloc; afterwards reused, so a
+// repeated call allocates nothing); smaller ones from the stream-ordered pool.  Everything runs on the one stream
+// of the context, so handing a released area to the next user is ordered by the stream.
+static const size_t kWsMinBytes = (size_t)32 << 20;
+void* ws_get(size_t bytes);
+void ws_put(void* p);
 
 // RAII device buffer.
 template <class T>
 struct DevBuf {
   T* p;
   size_t n;
-  DevBuf() : p(nullptr), n(0) {}
-  explicit DevBuf(size_t count) : p(nullptr), n(0) { alloc(count); }
+  bool cached;
+  DevBuf() : p(nullptr), n(0), cached(false) {}
+  explicit DevBuf(size_t count) : p(nullptr), n(0), cached(false) { alloc(count); }
   ~DevBuf() { release(); }
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   void alloc(size_t count) {
     release();
     n = count;
-    if (count) SGX_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), g_stream));
+    cached = false;
+    if (!count) return;
+    if (g_ctx && count * sizeof(T) >= kWsMinBytes) {
+      p = (T*)ws_get(count * sizeof(T));
+      cached = true;
+    } else {
+      SGX_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), g_stream));
+    }
   }
   void release() {
-    if (p) cudaFreeAsync(p, g_stream);
+    if (p) {
+      if (cached) ws_put(p);
+      else cudaFreeAsync(p, g_stream);
+    }
     p = nullptr;
     n = 0;
+    cached = false;
   }
+  // Ownership leaves the buffer (long-lived objects: read store, rank blocks).  Such buffers must come from the
+  // stream-ordered pool because they are released with cudaFreeAsync: use alloc_owned() for them.
   T* take() {
     T* q = p;
     p = nullptr;
     n = 0;
     return q;
+  }
+  void swap(DevBuf& o) {
+    T* tp = p;
+    p = o.p;
+    o.p = tp;
+    size_t tn = n;
+    n = o.n;
+    o.n = tn;
+    bool tc = cached;
+    cached = o.cached;
+    o.cached = tc;
+  }
+  void alloc_owned(size_t count) {
+    release();
+    n = count;
+    cached = false;
+    if (count) SGX_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), g_stream));
   }
 };
 
@@ -178,6 +223,7 @@ inline unsigned grid_for(uint64_t n, unsigned per_block) {
     if (ctx) {                                        \
       SGX_CUDA(cudaSetDevice((ctx)->device));         \
       sgx::g_stream = (ctx)->stream;                  \
+      sgx::g_ctx = (ctx);                             \
     }
 #define SGX_ENTRY_END(ctx)                      \
   }                                             \
