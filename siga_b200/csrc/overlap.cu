@@ -20,7 +20,15 @@ namespace sgx {
 
 static const int kOvThreads = 256;
 
+// Candidate block reduced to what the edge pipeline needs: capped[0] (rows of the '$' block, always < 2^32 because
+// there are < 2^32 reads), overlap length (low 16 bits) and AlignFlags (bits 16..18).
+struct LeanCand {
+  uint32_t lo, hi, len_af;
+};
+
 struct OvBatch {
+  LeanCand* lean;          // [count][4][find_cap]   (lean mode instead of cand)
+  LeanCand* lean_contain;  // [count][4]             (lean mode instead of contain)
   sgx_block* cand;     // [count][4][find_cap]
   uint32_t* ncand;     // [count][4]
   sgx_block* contain;  // [count][4]
@@ -47,7 +55,7 @@ struct OvArenaCfg {
 
 __global__ void __launch_bounds__(kOvThreads)
 ov_post_kernel(FmView fwd, FmView rev, ReadsView reads, uint64_t first, uint64_t count, int irreducible, OvBatch bt,
-               OvArenaCfg ac, const uint32_t* __restrict__ list, uint32_t* __restrict__ status,
+               OvArenaCfg ac, const uint32_t* __restrict__ list, int by_item, uint32_t* __restrict__ status,
                unsigned long long* __restrict__ lookups) {
   const DevGroup g;
   const uint64_t gid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / kGroup;
@@ -66,8 +74,9 @@ ov_post_kernel(FmView fwd, FmView rev, ReadsView reads, uint64_t first, uint64_t
   uint32_t st = 0;
   // `count` work items: all reads of the batch, or (list != nullptr) the reads the fast path handed back
   for (uint64_t wi = gid; wi < count; wi += ngroups) {
-    const uint64_t r = list ? (uint64_t)list[wi] : wi;
-    const uint32_t l = reads.len[first + r];
+    const uint64_t rid = list ? (uint64_t)list[wi] : wi;  // which read (relative to `first`)
+    const uint64_t r = by_item ? wi : rid;                // where its candidates / outputs are stored
+    const uint32_t l = reads.len[first + rid];
     const sgx_block* cp[4];
     uint32_t nc[4], nk[4];
 #pragma unroll
@@ -113,171 +122,222 @@ __global__ void ov_offsets_kernel(const uint64_t* __restrict__ batch_off, uint64
   if (i <= bn) all_off[i] = base + batch_off[i];
 }
 
-// Device-resident result of the search + post stages (blocks of all reads, compacted).
-struct OvCore {
-  DevBuf<sgx_block> compact;
-  uint64_t n_blocks = 0;
-  DevBuf<uint8_t> sub;        // [count] substring flags
-  DevBuf<uint64_t> off;       // [count + 1] block offsets
-  sgx_hits stats;             // timing / counter fields only
-};
+// ---- shared driver state ------------------------------------------------------------------------------------------
 
-static void overlap_core(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const sgx_reads* reads, uint64_t first,
-                         uint64_t count, uint32_t min_ov, int irreducible, int rc, OvCore& core,
-                         KernelClock& k_search, KernelClock& k_post) {
-  static_assert(sizeof(sgx_block) == 72, "sgx_block layout");
-  SGX_REQUIRE(fwd && rev && reads, SGX_EINVAL, "sgx_overlap_batch: null argument");
-  SGX_REQUIRE(first <= reads->n && count <= reads->n - first, SGX_EINVAL, "sgx_overlap_batch: read range out of bounds");
-  SGX_REQUIRE(min_ov >= 1, SGX_EINVAL, "sgx_overlap_batch: min_overlap must be >= 1");
-  sgx_hits* hits = &core.stats;
-  memset(hits, 0, sizeof(*hits));
-
-  const uint32_t lmax = reads->max_len;
-  const uint32_t find_cap = lmax > min_ov ? lmax - min_ov : 1;
-  uint32_t out_cap = 4 * find_cap + 4;
-  // batch size: keep candidate + output regions within ~6 GB
-  const size_t per_read = ((size_t)4 * find_cap + 4 + out_cap) * sizeof(sgx_block);
-  uint64_t batch = std::max<uint64_t>(1024, std::min<uint64_t>((6ull << 30) / per_read, 1u << 20));
-  batch = std::min<uint64_t>(batch, std::max<uint64_t>(count, 1));
-
-  DevBuf<sgx_block> d_cand(batch * 4 * find_cap), d_contain(batch * 4), d_out(batch * out_cap);
-  DevBuf<uint32_t> d_ncand(batch * 4), d_ncontain(batch * 4), d_nout(batch), d_status(1);
-  DevBuf<uint8_t>& d_sub = core.sub;
-  d_sub.alloc(std::max<uint64_t>(count, 1));
-  core.off.alloc(count + 1);
-  DevBuf<uint64_t> d_off(batch + 1), d_ws(scan_ws_elems(batch + 1)), d_total(1);
-  DevBuf<unsigned long long> d_look(2);
-  SGX_CUDA(cudaMemsetAsync(d_sub.p, 0, std::max<uint64_t>(count, 1), ctx->stream));
-  SGX_CUDA(cudaMemsetAsync(d_look.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
-
-  const FmView vf = fwd->view(), vr = rev->view();
-  const ReadsView rv = reads->view();
-  const ReadsView rv0 = rv;
+struct OvPlan {
+  sgx_ctx* ctx;
+  const sgx_fm *fwd, *rev;
+  const sgx_reads* reads;
+  uint64_t first, count;
+  uint32_t min_ov;
+  int irreducible, rc;
+  FmView vf, vr;
   FmPair fmp;
-  fmp.blocks[0] = vf.blocks;
-  fmp.blocks[1] = vr.blocks;
-  for (int i = 0; i < 6; ++i) {
-    fmp.pred[0][i] = vf.pred[i];
-    fmp.pred[1][i] = vr.pred[i];
-  }
-  const bool narrow = fwd->n < 0xffffffffull && rev->n < 0xffffffffull;  // 32-bit positions suffice
-  // grids: a few resident CTAs per SM, groups stride over the reads of the batch
-  const unsigned grid_search = (unsigned)ctx->sm_count * 8;
-  const unsigned grid_post = (unsigned)ctx->sm_count * 4;
-  const uint64_t post_groups = (uint64_t)grid_post * kOvThreads / kGroup;
+  ReadsView rv, treads;
+  SaView sf, sr;
+  bool narrow, fast;
+  uint32_t find_cap, out_cap, rows_cap, extw;
+  unsigned grid_search, grid_post, grid_reduce;
+  // general-path work area (allocated on first use, regrown on overflow)
   OvArenaCfg ac;
-  ac.list_cap = find_cap + 4 + 28;
-  ac.r_cap = ac.list_cap;
-  ac.st_cap = 4 * ac.list_cap;
-  ac.g_cap = 256;
   DevBuf<sgx_block> d_arena;
   DevBuf<uint32_t> d_gd;
-  auto alloc_arena = [&]() {
+  bool arena_ready;
+  DevBuf<uint32_t> d_status;
+  DevBuf<unsigned long long> d_look;  // [0] search lookups, [1] general-path lookups
+
+  void init(sgx_ctx* c, const sgx_fm* f, const sgx_fm* r, const sgx_reads* rd, uint64_t fst, uint64_t cnt, uint32_t m,
+            int irr, int rcomp) {
+    static_assert(sizeof(sgx_block) == 72, "sgx_block layout");
+    SGX_REQUIRE(f && r && rd, SGX_EINVAL, "sgx_overlap: null argument");
+    SGX_REQUIRE(fst <= rd->n && cnt <= rd->n - fst, SGX_EINVAL, "sgx_overlap: read range out of bounds");
+    SGX_REQUIRE(m >= 1, SGX_EINVAL, "sgx_overlap: min_overlap must be >= 1");
+    ctx = c;
+    fwd = f;
+    rev = r;
+    reads = rd;
+    first = fst;
+    count = cnt;
+    min_ov = m;
+    irreducible = irr;
+    rc = rcomp;
+    vf = f->view();
+    vr = r->view();
+    rv = rd->view();
+    fmp.blocks[0] = vf.blocks;
+    fmp.blocks[1] = vr.blocks;
+    for (int i = 0; i < 6; ++i) {
+      fmp.pred[0][i] = vf.pred[i];
+      fmp.pred[1][i] = vr.pred[i];
+    }
+    narrow = f->n < 0xffffffffull && r->n < 0xffffffffull;  // 32-bit positions suffice
+    const uint32_t lmax = rd->max_len;
+    find_cap = lmax > m ? lmax - m : 1;
+    out_cap = 4 * find_cap + 4;
+    grid_search = (unsigned)c->sm_count * 8;
+    grid_post = (unsigned)c->sm_count * 4;
+    ac.list_cap = find_cap + 4 + 28;
+    ac.r_cap = ac.list_cap;
+    ac.st_cap = 4 * ac.list_cap;
+    ac.g_cap = 256;
+    arena_ready = false;
+    d_status.alloc(1);
+    d_look.alloc(2);
+    SGX_CUDA(cudaMemsetAsync(d_look.p, 0, 2 * sizeof(unsigned long long), c->stream));
+    // fast post path: needs the read-start orders and the indexed read set on the device (sgx_fm_attach_reads)
+    fast = f->sai && r->sai && f->indexed && f->indexed == r->indexed && f->indexed->max_len < 65536 &&
+           f->indexed->ctx == c && lmax < 65536;
+    treads = rv;
+    sf = SaView{nullptr, nullptr};
+    sr = SaView{nullptr, nullptr};
+    rows_cap = 128;
+    extw = 1;
+    grid_reduce = 1;
+    if (fast) {
+      treads = f->indexed->view();
+      sf = SaView{f->sai, f->inv};
+      sr = SaView{r->sai, r->inv};
+      const uint32_t tmax = f->indexed->max_len;
+      extw = tmax > m ? (tmax - m + 31) / 32 : 1;
+      grid_reduce = (unsigned)c->sm_count * 16;
+    }
+  }
+
+  size_t reduce_smem(bool edges) {
+    while (rows_cap > 32 && reduce_smem_per_warp(rows_cap, extw, edges) * kRdWarps > (size_t)200 * 1024) rows_cap /= 2;
+    return reduce_smem_per_warp(rows_cap, extw, edges) * kRdWarps;
+  }
+
+  void alloc_arena() {
+    const uint64_t post_groups = (uint64_t)grid_post * kOvThreads / kGroup;
     d_arena.alloc(post_groups * ((size_t)4 * ac.list_cap + ac.r_cap + ac.st_cap));
     d_gd.alloc(post_groups * (size_t)4 * ac.g_cap);
     ac.blocks = d_arena.p;
     ac.gd = d_gd.p;
-  };
-  alloc_arena();
-
-  // fast post path: needs the read-start orders and the indexed read set on the device (sgx_fm_attach_reads)
-  const bool fast = fwd->sai && rev->sai && fwd->indexed && fwd->indexed == rev->indexed &&
-                    fwd->indexed->max_len < 65536 && fwd->indexed->ctx == ctx;
-  ReadsView treads = rv0;
-  SaView sf{nullptr, nullptr}, sr{nullptr, nullptr};
-  uint32_t rows_cap = 128, extw = 1;
-  size_t reduce_smem = 0;
-  unsigned grid_reduce = 1;
-  DevBuf<uint32_t> d_slow, d_nslow(1);
-  if (fast) {
-    treads = fwd->indexed->view();
-    sf.sa = fwd->sai;
-    sf.inv = fwd->inv;
-    sr.sa = rev->sai;
-    sr.inv = rev->inv;
-    const uint32_t tmax = fwd->indexed->max_len;
-    extw = tmax > min_ov ? (tmax - min_ov + 31) / 32 : 1;
-    while (rows_cap > 32 && reduce_smem_per_warp(rows_cap, extw) * kRdWarps > (size_t)200 * 1024) rows_cap /= 2;
-    reduce_smem = reduce_smem_per_warp(rows_cap, extw) * kRdWarps;
-    SGX_CUDA(cudaFuncSetAttribute(ov_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)reduce_smem));
-    grid_reduce = (unsigned)ctx->sm_count * 16;
-    d_slow.alloc(batch);
+    arena_ready = true;
   }
 
-  DevBuf<sgx_block>& d_compact = core.compact;  // all blocks of all batches
-  uint64_t compact_cap = 0, compact_n = 0;
-  if (count == 0) SGX_CUDA(cudaMemsetAsync(core.off.p, 0, sizeof(uint64_t), ctx->stream));
-
-  for (uint64_t b0 = 0; b0 < count; b0 += batch) {
-    const uint64_t bn = std::min<uint64_t>(batch, count - b0);
-    OvBatch bt;
-    bt.cand = d_cand.p;
-    bt.ncand = d_ncand.p;
-    bt.contain = d_contain.p;
-    bt.ncontain = d_ncontain.p;
-    bt.substring = d_sub.p + b0;
-    bt.out = d_out.p;
-    bt.nout = d_nout.p;
-    bt.find_cap = find_cap;
-    bt.out_cap = out_cap;
-    SGX_CUDA(cudaMemsetAsync(d_status.p, 0, sizeof(uint32_t), ctx->stream));
-    k_search.tick();
+  // search of `n` work items starting at read `rfirst` (or the reads of `list`, relative to rfirst)
+  void search(bool lean, uint64_t rfirst, uint64_t n, const OvBatch& bt, const uint32_t* list) {
+    if (n == 0) return;
     if (narrow) {
-      SGX_LAUNCH(ctx, ov_search_quad_kernel<uint32_t>, grid_search, kOvThreads, 0, fmp, rv, first + b0, bn, min_ov, rc,
-                 bt, d_look.p);
+      if (lean) {
+        SGX_LAUNCH(ctx, (ov_search_quad_kernel<uint32_t, true>), grid_search, kOvThreads, 0, fmp, rv, rfirst, n, min_ov, rc, bt, list, d_look.p);
+      } else {
+        SGX_LAUNCH(ctx, (ov_search_quad_kernel<uint32_t, false>), grid_search, kOvThreads, 0, fmp, rv, rfirst, n, min_ov, rc, bt, list, d_look.p);
+      }
     } else {
-      SGX_LAUNCH(ctx, ov_search_quad_kernel<uint64_t>, grid_search, kOvThreads, 0, fmp, rv, first + b0, bn, min_ov, rc,
-                 bt, d_look.p);
+      if (lean) {
+        SGX_LAUNCH(ctx, (ov_search_quad_kernel<uint64_t, true>), grid_search, kOvThreads, 0, fmp, rv, rfirst, n, min_ov, rc, bt, list, d_look.p);
+      } else {
+        SGX_LAUNCH(ctx, (ov_search_quad_kernel<uint64_t, false>), grid_search, kOvThreads, 0, fmp, rv, rfirst, n, min_ov, rc, bt, list, d_look.p);
+      }
     }
-    k_search.tick();
-    hits->search_launches++;
-    // ---- post stage.  Fast path (read store + .sai attached): string-based reduction, the few reads outside its
-    //      preconditions are handed back on a list.  Otherwise / for that list: the literal BWT-walking kernel.
-    const uint32_t* work_list = nullptr;
-    uint64_t work_n = bn;
-    if (fast) {
-      SGX_CUDA(cudaMemsetAsync(d_nslow.p, 0, sizeof(uint32_t), ctx->stream));
-      k_post.tick();
-      SGX_LAUNCH(ctx, ov_reduce_kernel, grid_reduce, kRdWarps * 32, reduce_smem, treads, sf, sr, bn, irreducible, bt,
-                 rows_cap, extw, d_slow.p, d_nslow.p);
-      k_post.tick();
-      uint32_t ns = 0;
-      SGX_CUDA(cudaMemcpyAsync(&ns, d_nslow.p, sizeof(ns), cudaMemcpyDeviceToHost, ctx->stream));
-      SGX_CUDA(cudaStreamSynchronize(ctx->stream));
-      work_list = d_slow.p;
-      work_n = ns;
-      hits->slow_reads += ns;
-    } else {
-      hits->slow_reads += bn;
-    }
-    for (int attempt = 0; work_n > 0; ++attempt) {
-      if (attempt > 0) SGX_CUDA(cudaMemsetAsync(d_status.p, 0, sizeof(uint32_t), ctx->stream));
-      k_post.tick();
-      SGX_LAUNCH(ctx, ov_post_kernel, grid_post, kOvThreads, 0, vf, vr, rv, first + b0, work_n, irreducible, bt, ac,
-                 work_list, d_status.p, d_look.p + 1);
-      k_post.tick();
+  }
+
+  // General (BWT-walking) post stage for `n` work items; returns false when the per-read output regions are too
+  // small (the caller enlarges them and calls again); work-area overflows are handled here.
+  bool post_general(uint64_t rfirst, uint64_t n, const OvBatch& bt, const uint32_t* list, int by_item, KernelClock& clk) {
+    if (n == 0) return true;
+    if (!arena_ready) alloc_arena();
+    for (int attempt = 0;; ++attempt) {
+      SGX_CUDA(cudaMemsetAsync(d_status.p, 0, sizeof(uint32_t), ctx->stream));
+      clk.tick();
+      SGX_LAUNCH(ctx, ov_post_kernel, grid_post, kOvThreads, 0, vf, vr, rv, rfirst, n, irreducible, bt, ac, list, by_item,
+                 d_status.p, d_look.p + 1);
+      clk.tick();
       uint32_t st = 0;
       SGX_CUDA(cudaMemcpyAsync(&st, d_status.p, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
       SGX_CUDA(cudaStreamSynchronize(ctx->stream));
       SGX_REQUIRE(!(st & kOvAssert), SGX_EINVAL,
                   "overlap: blocks of equal length with different coordinates (the reference asserts here)");
-      if (!(st & kOvOverflow)) break;
-      // a work area was too small: regrow it and redo the post stage of these reads on the GPU
-      SGX_REQUIRE(attempt < 4, SGX_EOVERFLOW, "overlap: work area overflow persists after regrowing");
+      if (!(st & kOvOverflow)) return true;
+      SGX_REQUIRE(attempt < 5, SGX_EOVERFLOW, "overlap: work area overflow persists after regrowing");
+      if (attempt >= 1) return false;  // probably the output regions
       ac.list_cap *= 2;
       ac.r_cap *= 4;
       ac.st_cap *= 4;
       ac.g_cap *= 4;
       alloc_arena();
-      if (attempt >= 1) {
-        // the output regions are too small as well: this also invalidates what the fast path wrote, redo everything
-        out_cap *= 2;
-        d_out.alloc(batch * (size_t)out_cap);
-        bt.out = d_out.p;
-        bt.out_cap = out_cap;
-        work_list = nullptr;
-        work_n = bn;
+    }
+  }
+};
+
+// Device-resident result of the search + post stages (blocks of all reads, compacted).
+struct OvCore {
+  DevBuf<sgx_block> compact;
+  uint64_t n_blocks = 0;
+  DevBuf<uint8_t> sub;   // [count] substring flags
+  DevBuf<uint64_t> off;  // [count + 1] block offsets
+  uint64_t slow_reads = 0, search_launches = 0;
+};
+
+// ---- blocks API (sgx_overlap_batch): every block exactly as the reference serialises it ---------------------------
+
+static void overlap_core(OvPlan& pl, OvCore& core, KernelClock& k_search, KernelClock& k_post) {
+  sgx_ctx* ctx = pl.ctx;
+  const uint64_t count = pl.count;
+  // batch size: keep candidate + output regions within ~6 GB
+  const size_t per_read = ((size_t)4 * pl.find_cap + 4 + pl.out_cap) * sizeof(sgx_block);
+  uint64_t batch = std::max<uint64_t>(1024, std::min<uint64_t>((6ull << 30) / per_read, 1u << 20));
+  batch = std::min<uint64_t>(batch, std::max<uint64_t>(count, 1));
+
+  DevBuf<sgx_block> d_cand(batch * 4 * pl.find_cap), d_contain(batch * 4), d_out(batch * pl.out_cap);
+  DevBuf<uint32_t> d_ncand(batch * 4), d_ncontain(batch * 4), d_nout(batch), d_slow, d_nslow(1);
+  core.sub.alloc(std::max<uint64_t>(count, 1));
+  core.off.alloc(count + 1);
+  DevBuf<uint64_t> d_off(batch + 1), d_ws(scan_ws_elems(batch + 1));
+  SGX_CUDA(cudaMemsetAsync(core.sub.p, 0, std::max<uint64_t>(count, 1), ctx->stream));
+  if (count == 0) SGX_CUDA(cudaMemsetAsync(core.off.p, 0, sizeof(uint64_t), ctx->stream));
+  size_t smem = 0;
+  if (pl.fast) {
+    smem = pl.reduce_smem(false);
+    SGX_CUDA(cudaFuncSetAttribute(ov_reduce_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    d_slow.alloc(batch);
+  }
+  uint64_t compact_cap = 0, compact_n = 0;
+  for (uint64_t b0 = 0; b0 < count; b0 += batch) {
+    const uint64_t bn = std::min<uint64_t>(batch, count - b0);
+    OvBatch bt;
+    memset(&bt, 0, sizeof(bt));
+    bt.cand = d_cand.p;
+    bt.ncand = d_ncand.p;
+    bt.contain = d_contain.p;
+    bt.ncontain = d_ncontain.p;
+    bt.substring = core.sub.p + b0;
+    bt.out = d_out.p;
+    bt.nout = d_nout.p;
+    bt.find_cap = pl.find_cap;
+    bt.out_cap = pl.out_cap;
+    k_search.tick();
+    pl.search(false, pl.first + b0, bn, bt, nullptr);
+    k_search.tick();
+    core.search_launches++;
+    for (;;) {
+      const uint32_t* work_list = nullptr;
+      uint64_t work_n = bn;
+      if (pl.fast) {
+        SGX_CUDA(cudaMemsetAsync(d_nslow.p, 0, sizeof(uint32_t), ctx->stream));
+        EdgeSink none;
+        memset(&none, 0, sizeof(none));
+        k_post.tick();
+        SGX_LAUNCH(ctx, (ov_reduce_kernel<false, false>), pl.grid_reduce, kRdWarps * 32, smem, pl.rv, pl.treads, pl.sf, pl.sr,
+                   bn, pl.irreducible, bt, pl.rows_cap, pl.extw, (uint64_t)0, d_slow.p, d_nslow.p, none);
+        k_post.tick();
+        uint32_t ns = 0;
+        SGX_CUDA(cudaMemcpyAsync(&ns, d_nslow.p, sizeof(ns), cudaMemcpyDeviceToHost, ctx->stream));
+        SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+        work_list = d_slow.p;
+        work_n = ns;
       }
+      core.slow_reads += work_n;
+      if (pl.post_general(pl.first + b0, work_n, bt, work_list, 0, k_post)) break;
+      // the per-read output regions are too small: enlarge and redo the post stage of this batch
+      core.slow_reads -= work_n;
+      pl.out_cap *= 2;
+      d_out.alloc(batch * (size_t)pl.out_cap);
+      bt.out = d_out.p;
+      bt.out_cap = pl.out_cap;
     }
     // compact
     SGX_LAUNCH(ctx, ov_widen_kernel, grid_for(bn + 1, 256), 256, 0, (const uint32_t*)d_nout.p, bn, d_off.p);
@@ -290,23 +350,18 @@ static void overlap_core(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, con
       if (b0 == 0 && bn < count) ncap = std::max<uint64_t>(ncap, (uint64_t)((double)btotal / bn * count * 1.1) + 1024);
       DevBuf<sgx_block> nbuf(ncap);
       if (compact_n)
-        SGX_CUDA(cudaMemcpyAsync(nbuf.p, d_compact.p, compact_n * sizeof(sgx_block), cudaMemcpyDeviceToDevice, ctx->stream));
-      d_compact.swap(nbuf);  // the old area is released when nbuf goes out of scope (stream ordered)
+        SGX_CUDA(cudaMemcpyAsync(nbuf.p, core.compact.p, compact_n * sizeof(sgx_block), cudaMemcpyDeviceToDevice, ctx->stream));
+      core.compact.swap(nbuf);  // the old area is released when nbuf goes out of scope (stream ordered)
       compact_cap = ncap;
     }
     if (btotal)
-      SGX_LAUNCH(ctx, ov_gather_kernel, grid_for(bn * 32, 256), 256, 0, (const sgx_block*)bt.out,
-                 (const uint32_t*)d_nout.p, bt.out_cap, (const uint64_t*)d_off.p, bn, d_compact.p + compact_n);
+      SGX_LAUNCH(ctx, ov_gather_kernel, grid_for(bn * 32, 256), 256, 0, (const sgx_block*)bt.out, (const uint32_t*)d_nout.p,
+                 bt.out_cap, (const uint64_t*)d_off.p, bn, core.compact.p + compact_n);
     SGX_LAUNCH(ctx, ov_offsets_kernel, grid_for(bn + 1, 256), 256, 0, (const uint64_t*)d_off.p, bn, compact_n,
                core.off.p + b0);
     compact_n += btotal;
   }
   core.n_blocks = compact_n;
-  unsigned long long look[2] = {0, 0};
-  SGX_CUDA(cudaMemcpyAsync(look, d_look.p, sizeof(look), cudaMemcpyDeviceToHost, ctx->stream));
-  SGX_CUDA(cudaStreamSynchronize(ctx->stream));
-  hits->lookups_search = look[0];
-  hits->lookups_extract = look[1];
 }
 
 void overlap_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const sgx_reads* reads, uint64_t first,
@@ -317,69 +372,80 @@ void overlap_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const sgx_r
   EventTimer t_all(ctx->stream);
   KernelClock k_search(ctx->stream), k_post(ctx->stream);
   t_all.start();
+  OvPlan pl;
+  pl.init(ctx, fwd, rev, reads, first, count, min_ov, irreducible, rc);
   OvCore core;
-  overlap_core(ctx, fwd, rev, reads, first, count, min_ov, irreducible, rc, core, k_search, k_post);
-  *hits = core.stats;
-  const uint64_t compact_n = core.n_blocks;
-  DevBuf<sgx_block>& d_compact = core.compact;
-  DevBuf<uint8_t>& d_sub = core.sub;
-
-  // copy out
+  overlap_core(pl, core, k_search, k_post);
   hits->n_reads = count;
-  hits->n_blocks = compact_n;
+  hits->n_blocks = core.n_blocks;
+  hits->slow_reads = core.slow_reads;
+  hits->search_launches = core.search_launches;
   hits->substring = (uint8_t*)pinned_get(ctx, std::max<uint64_t>(count, 1));
   hits->block_off = (uint64_t*)pinned_get(ctx, (count + 1) * sizeof(uint64_t));
-  hits->blocks = (sgx_block*)pinned_get(ctx, std::max<uint64_t>(compact_n, 1) * sizeof(sgx_block));
+  hits->blocks = (sgx_block*)pinned_get(ctx, std::max<uint64_t>(core.n_blocks, 1) * sizeof(sgx_block));
   SGX_CUDA(cudaMemcpyAsync(hits->block_off, core.off.p, (count + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-  if (count) SGX_CUDA(cudaMemcpyAsync(hits->substring, d_sub.p, count, cudaMemcpyDeviceToHost, ctx->stream));
-  if (compact_n)
-    SGX_CUDA(cudaMemcpyAsync(hits->blocks, d_compact.p, compact_n * sizeof(sgx_block), cudaMemcpyDeviceToHost, ctx->stream));
+  if (count) SGX_CUDA(cudaMemcpyAsync(hits->substring, core.sub.p, count, cudaMemcpyDeviceToHost, ctx->stream));
+  if (core.n_blocks)
+    SGX_CUDA(cudaMemcpyAsync(hits->blocks, core.compact.p, core.n_blocks * sizeof(sgx_block), cudaMemcpyDeviceToHost, ctx->stream));
+  unsigned long long look[2] = {0, 0};
+  SGX_CUDA(cudaMemcpyAsync(look, pl.d_look.p, sizeof(look), cudaMemcpyDeviceToHost, ctx->stream));
   t_all.stop();
   SGX_CUDA(cudaStreamSynchronize(ctx->stream));
   hits->ms_total = t_all.ms();
   hits->ms_search = k_search.total_ms();
   hits->ms_extract = k_post.total_ms();
+  hits->lookups_search = look[0];
+  hits->lookups_extract = look[1];
   hits->launches = ctx->launches - launches0;
 }
 
-// ---- hits -> edges on the device: Hit2OverlapConverter::convert (src/overlap_builder.cpp:345-375) ------------------
-// One thread per query read walks its blocks and the rows of each capped[0] interval.  An edge survives when the
-// target is another read (by name), the query name is not smaller than the target name, and it is not a
-// containment seen from the reversed query (src/overlap_builder.cpp:358-367).  Names enter as ranks.
-template <bool WRITE>
-__global__ void ov_edges_kernel(const sgx_block* __restrict__ blocks, const uint64_t* __restrict__ off, uint64_t first,
-                                uint64_t count, const uint32_t* __restrict__ qlen, SaView sf, SaView sr,
-                                const uint32_t* __restrict__ tlen, const uint32_t* __restrict__ name_rank,
-                                uint64_t* __restrict__ cnt, sgx_edge* __restrict__ edges) {
-  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= count) return;
-  const uint32_t q = (uint32_t)(first + r);
-  const uint32_t lq = qlen[q];
-  const uint32_t rq = name_rank[q];
-  uint64_t n = 0;
-  uint64_t at = WRITE ? cnt[r] : 0;
-  for (uint64_t b = off[r]; b < off[r + 1]; ++b) {
-    const sgx_block blk = blocks[b];
-    const uint32_t k = blk.length, af = blk.af;
-    const uint32_t* sa = (af & SGX_AF_TARGETREV) ? sr.sa : sf.sa;
+// ---- edges API (sgx_overlap_edges) -------------------------------------------------------------------------------
+// Lean pipeline: the search writes 12-byte candidates, the reduce kernel applies the filter of
+// Hit2OverlapConverter::convert (src/overlap_builder.cpp:345-375) to the surviving rows and appends sgx_edge records
+// straight to the output; no blocks, no compaction, no host round trip per batch.  Reads outside the fast path's
+// preconditions are collected and redone at the end through the full-block kernels + ov_edges_items_kernel.
+
+// One thread per general-path work item: expands the blocks it produced into edges.
+__global__ void ov_edges_items_kernel(const sgx_block* __restrict__ out, const uint32_t* __restrict__ nout, uint32_t out_cap,
+                                      const uint32_t* __restrict__ list, uint64_t n_items, uint64_t first,
+                                      const uint32_t* __restrict__ qlen, SaView sf, SaView sr,
+                                      const uint32_t* __restrict__ tlen, EdgeSink sink) {
+  const uint64_t wi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (wi >= n_items) return;
+  const uint64_t q = first + (list ? (uint64_t)list[wi] : wi);
+  const uint32_t lq = qlen[q], rq = sink.name_rank[q];
+  const sgx_block* blocks = out + wi * (size_t)out_cap;
+  const uint32_t nb = nout[wi];
+  // count, reserve, write
+  unsigned long long n = 0;
+  for (uint32_t b = 0; b < nb; ++b) {
+    const sgx_block& blk = blocks[b];
+    const uint32_t* sa = (blk.af & SGX_AF_TARGETREV) ? sr.sa : sf.sa;
+    for (uint64_t j = blk.capped[0]; j <= blk.capped[1]; ++j)
+      if (rd_edge_ok(rq, lq, sa[j], blk.length, blk.af, sink.name_rank, tlen)) ++n;
+  }
+  if (n == 0) return;
+  const unsigned long long at = atomicAdd(sink.counter, n);
+  if (at + n > sink.cap) {
+    atomicOr(sink.overflow, 1u);
+    return;
+  }
+  unsigned long long w = 0;
+  for (uint32_t b = 0; b < nb; ++b) {
+    const sgx_block& blk = blocks[b];
+    const uint32_t* sa = (blk.af & SGX_AF_TARGETREV) ? sr.sa : sf.sa;
     for (uint64_t j = blk.capped[0]; j <= blk.capped[1]; ++j) {
       const uint32_t t = sa[j];
-      const uint32_t rt = name_rank[t];
-      if (rq == rt) continue;                       // query.name == target.name
-      const bool contain = k == lq || k == tlen[t];  // either coordinate spans its whole read
-      if (rq < rt || (contain && (af & SGX_AF_QUERYREV))) continue;
-      if (WRITE) {
-        sgx_edge e;
-        e.query = q;
-        e.target = t;
-        e.length = k;
-        e.af = af;
-        edges[at + n] = e;
-      }
-      ++n;
+      if (!rd_edge_ok(rq, lq, t, blk.length, blk.af, sink.name_rank, tlen)) continue;
+      sgx_edge e;
+      e.query = (uint32_t)q;
+      e.target = t;
+      e.length = blk.length;
+      e.af = blk.af;
+      sink.edges[at + w] = e;
+      ++w;
     }
   }
-  if (!WRITE) cnt[r] = n;
 }
 
 void overlap_edges_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const sgx_reads* reads, uint64_t first,
@@ -394,42 +460,146 @@ void overlap_edges_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const
   EventTimer t_all(ctx->stream);
   KernelClock k_search(ctx->stream), k_post(ctx->stream);
   t_all.start();
-  OvCore core;
-  overlap_core(ctx, fwd, rev, reads, first, count, min_ov, irreducible, rc, core, k_search, k_post);
+  OvPlan pl;
+  pl.init(ctx, fwd, rev, reads, first, count, min_ov, irreducible, rc);
   const uint64_t n_all = fwd->indexed->n;
   DevBuf<uint32_t> d_rank(n_all);
   SGX_CUDA(cudaMemcpyAsync(d_rank.p, name_rank, n_all * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-  DevBuf<uint64_t> d_cnt(count + 1), d_ws(scan_ws_elems(count + 1)), d_total(1);
-  SGX_CUDA(cudaMemsetAsync(d_cnt.p, 0, (count + 1) * sizeof(uint64_t), ctx->stream));
-  SaView sf{fwd->sai, fwd->inv}, sr{rev->sai, rev->inv};
-  SGX_LAUNCH(ctx, ov_edges_kernel<false>, grid_for(count, 256), 256, 0, (const sgx_block*)core.compact.p,
-             (const uint64_t*)core.off.p, first, count, (const uint32_t*)reads->len, sf, sr,
-             (const uint32_t*)fwd->indexed->len, (const uint32_t*)d_rank.p, d_cnt.p, (sgx_edge*)nullptr);
-  scan_exclusive(ctx, d_cnt.p, count + 1, d_ws.p, (uint64_t*)nullptr);
-  uint64_t n_edges = 0;
-  SGX_CUDA(cudaMemcpyAsync(&n_edges, d_cnt.p + count, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-  SGX_CUDA(cudaStreamSynchronize(ctx->stream));
-  DevBuf<sgx_edge> d_edges(std::max<uint64_t>(n_edges, 1));
-  SGX_LAUNCH(ctx, ov_edges_kernel<true>, grid_for(count, 256), 256, 0, (const sgx_block*)core.compact.p,
-             (const uint64_t*)core.off.p, first, count, (const uint32_t*)reads->len, sf, sr,
-             (const uint32_t*)fwd->indexed->len, (const uint32_t*)d_rank.p, d_cnt.p, d_edges.p);
+  DevBuf<uint8_t> d_sub(std::max<uint64_t>(count, 1));
+  DevBuf<uint32_t> d_slow(std::max<uint64_t>(count, 1)), d_flags(2);  // [0] n_slow, [1] overflow
+  DevBuf<unsigned long long> d_counter(2);
+  DevBuf<sgx_edge> d_edges;
+  uint64_t edge_cap = std::max<uint64_t>(count * 8, 1u << 16);
+  uint64_t n_edges = 0, n_slow = 0, search_launches = 0;
+
+  for (int round = 0;; ++round) {
+    SGX_REQUIRE(round < 8, SGX_EOVERFLOW, "sgx_overlap_edges: edge buffer overflow persists");
+    d_edges.alloc(edge_cap);
+    SGX_CUDA(cudaMemsetAsync(d_sub.p, 0, std::max<uint64_t>(count, 1), ctx->stream));
+    SGX_CUDA(cudaMemsetAsync(d_flags.p, 0, 2 * sizeof(uint32_t), ctx->stream));
+    SGX_CUDA(cudaMemsetAsync(d_counter.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    SGX_CUDA(cudaMemsetAsync(pl.d_look.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    EdgeSink sink;
+    sink.edges = d_edges.p;
+    sink.counter = d_counter.p;
+    sink.cap = edge_cap;
+    sink.overflow = d_flags.p + 1;
+    sink.name_rank = d_rank.p;
+    sink.qbase = 0;
+    search_launches = 0;
+    if (pl.fast) {
+      // ---- lean pass over all reads, batch after batch, nothing comes back to the host in between
+      const size_t per_read = ((size_t)4 * pl.find_cap + 4) * sizeof(LeanCand) + 32;
+      uint64_t batch = std::max<uint64_t>(1024, std::min<uint64_t>((4ull << 30) / per_read, 1u << 21));
+      batch = std::min<uint64_t>(batch, std::max<uint64_t>(count, 1));
+      DevBuf<LeanCand> d_lean(batch * 4 * pl.find_cap), d_lcontain(batch * 4);
+      DevBuf<uint32_t> d_ncand(batch * 4), d_ncontain(batch * 4);
+      const size_t smem = pl.reduce_smem(true);
+      SGX_CUDA(cudaFuncSetAttribute(ov_reduce_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      for (uint64_t b0 = 0; b0 < count; b0 += batch) {
+        const uint64_t bn = std::min<uint64_t>(batch, count - b0);
+        OvBatch bt;
+        memset(&bt, 0, sizeof(bt));
+        bt.lean = d_lean.p;
+        bt.lean_contain = d_lcontain.p;
+        bt.ncand = d_ncand.p;
+        bt.ncontain = d_ncontain.p;
+        bt.substring = d_sub.p + b0;
+        bt.find_cap = pl.find_cap;
+        bt.out_cap = pl.out_cap;
+        k_search.tick();
+        pl.search(true, first + b0, bn, bt, nullptr);
+        k_search.tick();
+        ++search_launches;
+        sink.qbase = first + b0;
+        k_post.tick();
+        SGX_LAUNCH(ctx, (ov_reduce_kernel<true, true>), pl.grid_reduce, kRdWarps * 32, smem, pl.rv, pl.treads, pl.sf, pl.sr, bn,
+                   irreducible, bt, pl.rows_cap, pl.extw, b0, d_slow.p, d_flags.p, sink);
+        k_post.tick();
+      }
+      uint32_t fl[2] = {0, 0};
+      SGX_CUDA(cudaMemcpyAsync(fl, d_flags.p, sizeof(fl), cudaMemcpyDeviceToHost, ctx->stream));
+      SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+      n_slow = fl[0];
+      if (fl[1]) {
+        edge_cap *= 4;
+        continue;
+      }
+    } else {
+      n_slow = count;  // no read store attached: everything takes the general path
+    }
+    // ---- general path for the reads the lean pass handed back (or all of them): full blocks -> edges
+    bool again = false;
+    if (n_slow) {
+      const size_t per_item = ((size_t)4 * pl.find_cap + 4 + pl.out_cap) * sizeof(sgx_block);
+      uint64_t chunk = std::max<uint64_t>(1024, std::min<uint64_t>((4ull << 30) / per_item, 1u << 20));
+      chunk = std::min<uint64_t>(chunk, n_slow);
+      DevBuf<sgx_block> d_cand(chunk * 4 * pl.find_cap), d_contain(chunk * 4), d_out(chunk * (size_t)pl.out_cap);
+      DevBuf<uint32_t> d_ncand(chunk * 4), d_ncontain(chunk * 4), d_nout(chunk);
+      sink.qbase = first;
+      for (uint64_t c0 = 0; c0 < n_slow && !again; c0 += chunk) {
+        const uint64_t cn = std::min<uint64_t>(chunk, n_slow - c0);
+        const uint32_t* list = pl.fast ? d_slow.p + c0 : nullptr;
+        const uint64_t rfirst = pl.fast ? first : first + c0;
+        OvBatch bt;
+        memset(&bt, 0, sizeof(bt));
+        bt.cand = d_cand.p;
+        bt.contain = d_contain.p;
+        bt.ncand = d_ncand.p;
+        bt.ncontain = d_ncontain.p;
+        bt.substring = pl.fast ? d_sub.p : d_sub.p + c0;
+        bt.out = d_out.p;
+        bt.nout = d_nout.p;
+        bt.find_cap = pl.find_cap;
+        bt.out_cap = pl.out_cap;
+        k_search.tick();
+        pl.search(false, rfirst, cn, bt, list);
+        k_search.tick();
+        ++search_launches;
+        while (!pl.post_general(rfirst, cn, bt, list, 1, k_post)) {
+          pl.out_cap *= 2;
+          d_out.alloc(chunk * (size_t)pl.out_cap);
+          bt.out = d_out.p;
+          bt.out_cap = pl.out_cap;
+        }
+        SGX_LAUNCH(ctx, ov_edges_items_kernel, grid_for(cn, 128), 128, 0, (const sgx_block*)bt.out, (const uint32_t*)d_nout.p,
+                   bt.out_cap, list, cn, rfirst, (const uint32_t*)reads->len, pl.sf, pl.sr,
+                   (const uint32_t*)fwd->indexed->len, sink);
+      }
+      uint32_t ov = 0;
+      SGX_CUDA(cudaMemcpyAsync(&ov, d_flags.p + 1, sizeof(ov), cudaMemcpyDeviceToHost, ctx->stream));
+      SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (ov) again = true;
+    }
+    if (again) {
+      edge_cap *= 4;
+      continue;
+    }
+    unsigned long long ne = 0;
+    SGX_CUDA(cudaMemcpyAsync(&ne, d_counter.p, sizeof(ne), cudaMemcpyDeviceToHost, ctx->stream));
+    SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+    n_edges = ne;
+    break;
+  }
   out->n_reads = count;
   out->n_edges = n_edges;
-  out->n_blocks = core.n_blocks;
+  out->n_blocks = 0;
+  out->slow_reads = n_slow;
+  out->search_launches = search_launches;
   out->substring = (uint8_t*)pinned_get(ctx, std::max<uint64_t>(count, 1));
   out->edges = (sgx_edge*)pinned_get(ctx, std::max<uint64_t>(n_edges, 1) * sizeof(sgx_edge));
-  if (count) SGX_CUDA(cudaMemcpyAsync(out->substring, core.sub.p, count, cudaMemcpyDeviceToHost, ctx->stream));
+  if (count) SGX_CUDA(cudaMemcpyAsync(out->substring, d_sub.p, count, cudaMemcpyDeviceToHost, ctx->stream));
   if (n_edges)
     SGX_CUDA(cudaMemcpyAsync(out->edges, d_edges.p, n_edges * sizeof(sgx_edge), cudaMemcpyDeviceToHost, ctx->stream));
+  unsigned long long look[2] = {0, 0};
+  SGX_CUDA(cudaMemcpyAsync(look, pl.d_look.p, sizeof(look), cudaMemcpyDeviceToHost, ctx->stream));
   t_all.stop();
   SGX_CUDA(cudaStreamSynchronize(ctx->stream));
   out->ms_total = t_all.ms();
   out->ms_search = k_search.total_ms();
   out->ms_extract = k_post.total_ms();
-  out->lookups_search = core.stats.lookups_search;
-  out->lookups_extract = core.stats.lookups_extract;
-  out->slow_reads = core.stats.slow_reads;
-  out->search_launches = core.stats.search_launches;
+  out->lookups_search = look[0];
+  out->lookups_extract = look[1];
   out->launches = ctx->launches - launches0;
 }
 

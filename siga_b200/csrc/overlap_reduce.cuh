@@ -15,13 +15,15 @@
 //             '$' branching): row a is transitive  <=>  some row b with k_b > k_a has ext(b) as a prefix of ext(a).
 //             (Group semantics: a group is dropped when its longest block ends; b ends while a is still in b's
 //             group exactly when ext(b) is a prefix of ext(a).)
-//   output    rows of one block with identical ext are identical reads and contiguous; each surviving class is one
-//             output block: capped[0] = its row range, capped[1] = the rank range of those reads in the opposite
-//             index (inverse .sai), raw/length/af copied -- bit-identical to what the '$'-terminated walk yields.
+//   output    BLOCKS: rows of one block with identical ext are identical reads and contiguous; each surviving class
+//             is one output block: capped[0] = its row range, capped[1] = the rank range of those reads in the
+//             opposite index (inverse .sai), raw/length/af copied -- bit-identical to what the '$'-terminated walk
+//             yields.  EDGES: every surviving row is one candidate edge; the filter of Hit2OverlapConverter::convert
+//             (src/overlap_builder.cpp:358-367) is applied on the spot and only sgx_edge records leave the kernel.
 //
 // Anything outside these preconditions (interval intersections inside a list = periodic sequence, targets of
-// different lengths, more rows than the shared-memory table holds) is NOT approximated: the read is put on the
-// slow list and redone by ov_post_kernel, the literal BWT-walking implementation.
+// different lengths, more rows / edges than the shared-memory tables hold) is NOT approximated: the read is put on
+// the slow list and redone by the literal BWT-walking implementation (ov_post_kernel).
 #ifndef SGX_OVERLAP_REDUCE_CUH_
 #define SGX_OVERLAP_REDUCE_CUH_
 
@@ -34,31 +36,113 @@ struct SaView {
   const uint32_t* inv;  // read id -> row
 };
 
-static const int kRdWarps = 4;  // warps (reads in flight) per CTA
+// Where EDGES mode puts its output.
+struct EdgeSink {
+  sgx_edge* edges;
+  unsigned long long* counter;  // edges written so far
+  uint64_t cap;
+  uint32_t* overflow;           // set when cap was too small (host regrows and reruns)
+  const uint32_t* name_rank;    // per indexed read
+  uint64_t qbase;               // global index of the first read of this launch
+};
+
+static const int kRdWarps = 4;     // warps (reads in flight) per CTA
+static const int kRdEdgeCap = 256; // staged edges per read in EDGES mode
 
 // Bytes of shared memory one warp needs for `rows_cap` rows of `extw` 64-bit extension words.
-__host__ __device__ inline size_t reduce_smem_per_warp(uint32_t rows_cap, uint32_t extw) {
-  return (size_t)rows_cap * extw * 8 + (size_t)rows_cap * (4 + 4 + 2 + 2 + 2 + 2);
+__host__ __device__ inline size_t reduce_smem_per_warp(uint32_t rows_cap, uint32_t extw, bool edges) {
+  return (size_t)rows_cap * extw * 8 + (size_t)rows_cap * (4 + 4 + 2 + 2 + 2 + 2) + (edges ? (size_t)kRdEdgeCap * 8 : 0);
 }
 
 __device__ __forceinline__ bool rd_intersect(uint64_t s1, uint64_t e1, uint64_t s2, uint64_t e2) {
   return !(s1 > e2 || s2 > e1);
 }
 
+struct RdEnt {
+  uint32_t lo, hi, len, af;
+};
+
+template <bool LEAN>
+__device__ __forceinline__ RdEnt rd_cand(const OvBatch& bt, uint64_t r, int f, uint32_t i) {
+  RdEnt e;
+  if (LEAN) {
+    const LeanCand c = bt.lean[((size_t)r * 4 + f) * bt.find_cap + i];
+    e.lo = c.lo;
+    e.hi = c.hi;
+    e.len = c.len_af & 0xffffu;
+    e.af = c.len_af >> 16;
+  } else {
+    const sgx_block* b = bt.cand + ((size_t)r * 4 + f) * bt.find_cap + i;
+    e.lo = (uint32_t)b->capped[0];
+    e.hi = (uint32_t)b->capped[1];
+    e.len = b->length;
+    e.af = b->af;
+  }
+  return e;
+}
+
+template <bool LEAN>
+__device__ __forceinline__ RdEnt rd_contain(const OvBatch& bt, uint64_t r, int q) {
+  RdEnt e;
+  if (LEAN) {
+    const LeanCand c = bt.lean_contain[(size_t)r * 4 + q];
+    e.lo = c.lo;
+    e.hi = c.hi;
+    e.len = c.len_af & 0xffffu;
+    e.af = c.len_af >> 16;
+  } else {
+    const sgx_block* b = bt.contain + (size_t)r * 4 + q;
+    e.lo = (uint32_t)b->capped[0];
+    e.hi = (uint32_t)b->capped[1];
+    e.len = b->length;
+    e.af = b->af;
+  }
+  return e;
+}
+
+// Hit2OverlapConverter::convert's filter (src/overlap_builder.cpp:358-367) for query (rank rq, length lq) and
+// target t with overlap k.
+__device__ __forceinline__ bool rd_edge_ok(uint32_t rq, uint32_t lq, uint32_t t, uint32_t k, uint32_t af,
+                                           const uint32_t* __restrict__ name_rank, const uint32_t* __restrict__ tlen) {
+  const uint32_t rt = name_rank[t];
+  if (rq == rt) return false;                    // query.name == target.name
+  const bool contain = k == lq || k == tlen[t];  // either coordinate spans its whole read
+  return !(rq < rt || (contain && (af & SGX_AF_QUERYREV)));
+}
+
+// Warp-cooperative append of up to 32 staged edges (one per lane with `ok`).  Returns false on staging overflow.
+__device__ __forceinline__ bool rd_stage(bool ok, uint32_t t, uint32_t k, uint32_t af, uint32_t* e_tgt, uint32_t* e_kaf,
+                                         uint32_t& ecount, int lane) {
+  const unsigned m = __ballot_sync(0xffffffffu, ok);
+  const uint32_t n = __popc(m);
+  if (ecount + n > (uint32_t)kRdEdgeCap) return false;
+  if (ok) {
+    const uint32_t at = ecount + __popc(m & ((1u << lane) - 1u));
+    e_tgt[at] = t;
+    e_kaf[at] = k | (af << 16);
+  }
+  ecount += n;
+  return true;
+}
+
+template <bool LEAN, bool EDGES>
 __global__ void __launch_bounds__(kRdWarps * 32)
-ov_reduce_kernel(ReadsView treads, SaView sf, SaView sr, uint64_t count, int irreducible, OvBatch bt, uint32_t rows_cap,
-                 uint32_t extw, uint32_t* __restrict__ slow_list, uint32_t* __restrict__ n_slow) {
+ov_reduce_kernel(ReadsView qreads, ReadsView treads, SaView sf, SaView sr, uint64_t count, int irreducible, OvBatch bt,
+                 uint32_t rows_cap, uint32_t extw, uint64_t slow_base, uint32_t* __restrict__ slow_list,
+                 uint32_t* __restrict__ n_slow, EdgeSink sink) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  unsigned char* base = smem_raw + (size_t)wib * reduce_smem_per_warp(rows_cap, extw);
-  uint64_t* ext = reinterpret_cast<uint64_t*>(base);                       // [rows_cap][extw]
+  unsigned char* base = smem_raw + (size_t)wib * reduce_smem_per_warp(rows_cap, extw, EDGES);
+  uint64_t* ext = reinterpret_cast<uint64_t*>(base);                             // [rows_cap][extw]
   uint32_t* r_row = reinterpret_cast<uint32_t*>(ext + (size_t)rows_cap * extw);  // row in the '$' block
-  uint32_t* r_tgt = r_row + rows_cap;                                      // target read id
-  uint16_t* r_ent = reinterpret_cast<uint16_t*>(r_tgt + rows_cap);         // entry index within the side
-  uint16_t* r_k = r_ent + rows_cap;                                        // overlap length
-  uint16_t* r_n = r_k + rows_cap;                                          // extension length (bases)
-  uint16_t* r_flag = r_n + rows_cap;                                       // bit0 transitive, bit1 class head
+  uint32_t* r_tgt = r_row + rows_cap;                                            // target read id
+  uint16_t* r_ent = reinterpret_cast<uint16_t*>(r_tgt + rows_cap);               // entry index within the side
+  uint16_t* r_k = r_ent + rows_cap;                                              // overlap length
+  uint16_t* r_n = r_k + rows_cap;                                                // extension length (bases)
+  uint16_t* r_flag = r_n + rows_cap;                                             // bit0 transitive, bit1 class head
+  uint32_t* e_tgt = reinterpret_cast<uint32_t*>(r_flag + rows_cap);              // EDGES: staged edges of this read
+  uint32_t* e_kaf = e_tgt + kRdEdgeCap;
 
   const uint64_t warp0 = (uint64_t)blockIdx.x * kRdWarps + wib;
   const uint64_t nwarps = (uint64_t)gridDim.x * kRdWarps;
@@ -69,10 +153,16 @@ ov_reduce_kernel(ReadsView treads, SaView sf, SaView sr, uint64_t count, int irr
       nc[f] = bt.ncand[r * 4 + f];
       nk[f] = bt.ncontain[r * 4 + f];
     }
-    const sgx_block* cand = bt.cand + (size_t)r * 4 * bt.find_cap;
-    const sgx_block* contain = bt.contain + (size_t)r * 4;
-    sgx_block* out = bt.out + (size_t)r * bt.out_cap;
+    sgx_block* out = EDGES ? nullptr : bt.out + (size_t)r * bt.out_cap;
     bool slow = false;
+    // query side of the edge filter (EDGES)
+    const uint64_t qglob = sink.qbase + r;
+    uint32_t lq = 0, rq = 0;
+    if (EDGES) {
+      lq = qreads.len[qglob];
+      rq = sink.name_rank[qglob];
+    }
+    uint32_t ecount = 0;
 
     // ---- SubMaximalBlockFilter precondition: no two capped[0] intervals of a list intersect (then the filter only
     //      reorders, src/overlap_builder.cpp:929-953).  Lists carry the containment blocks of their index side.
@@ -80,13 +170,11 @@ ov_reduce_kernel(ReadsView treads, SaView sf, SaView sr, uint64_t count, int irr
     for (int f = 0; f < 4; ++f) {
       const int q0 = f < 2 ? 0 : 2;
       const uint32_t n = nc[f] + nk[q0] + nk[q0 + 1];
-      const sgx_block* lst = cand + (size_t)f * bt.find_cap;
       for (uint32_t i = lane; i < n; i += 32) {
-        const sgx_block* bi = i < nc[f] ? lst + i : contain + (i - nc[f] == 0 && nk[q0] ? q0 : q0 + 1);
-        const uint64_t lo = bi->capped[0], hi = bi->capped[1];
+        const RdEnt bi = i < nc[f] ? rd_cand<LEAN>(bt, r, f, i) : rd_contain<LEAN>(bt, r, (i - nc[f] == 0 && nk[q0]) ? q0 : q0 + 1);
         for (uint32_t j = i + 1; j < n; ++j) {
-          const sgx_block* bj = j < nc[f] ? lst + j : contain + (j - nc[f] == 0 && nk[q0] ? q0 : q0 + 1);
-          if (rd_intersect(lo, hi, bj->capped[0], bj->capped[1])) slow = true;
+          const RdEnt bj = j < nc[f] ? rd_cand<LEAN>(bt, r, f, j) : rd_contain<LEAN>(bt, r, (j - nc[f] == 0 && nk[q0]) ? q0 : q0 + 1);
+          if (rd_intersect(bi.lo, bi.hi, bj.lo, bj.hi)) slow = true;
         }
       }
     }
@@ -95,9 +183,24 @@ ov_reduce_kernel(ReadsView treads, SaView sf, SaView sr, uint64_t count, int irr
     uint32_t nout = 0;
     if (!slow) {
       // containment blocks go straight out: containfwd then containrev (src/overlap_builder.cpp:1160-1162)
-      for (int q = 0; q < 4; ++q) {
-        if (nk[q]) {
-          if (lane == 0) out[nout] = contain[q];
+      for (int q = 0; q < 4 && !slow; ++q) {
+        if (!nk[q]) continue;
+        if (EDGES) {
+          const RdEnt c = rd_contain<LEAN>(bt, r, q);
+          const uint32_t* sa = (c.af & SGX_AF_TARGETREV) ? sr.sa : sf.sa;
+          for (uint32_t x0 = c.lo; x0 <= c.hi && !slow; x0 += 32) {
+            const uint32_t x = x0 + lane;
+            bool ok = false;
+            uint32_t t = 0;
+            if (x <= c.hi) {
+              t = sa[x];
+              ok = rd_edge_ok(rq, lq, t, c.len, c.af, sink.name_rank, treads.len);
+            }
+            if (!rd_stage(ok, t, c.len, c.af, e_tgt, e_kaf, ecount, lane)) slow = true;
+            if (x0 > 0xffffffffu - 32) break;
+          }
+        } else {
+          if (lane == 0) out[nout] = bt.contain[(size_t)r * 4 + q];
           ++nout;
         }
       }
@@ -105,36 +208,53 @@ ov_reduce_kernel(ReadsView treads, SaView sf, SaView sr, uint64_t count, int irr
     if (!slow && !irreducible) {
       // exhaustive mode: suffixfwd, suffixrev, prefixfwd, prefixrev (src/overlap_builder.cpp:1175-1178)
       const int order[4] = {0, 3, 1, 2};
-      for (int q = 0; q < 4; ++q) {
-        const sgx_block* lst = cand + (size_t)order[q] * bt.find_cap;
-        const uint32_t n = nc[order[q]];
-        if (nout + n > bt.out_cap) {
-          slow = true;
-          break;
+      for (int q = 0; q < 4 && !slow; ++q) {
+        const int f = order[q];
+        const uint32_t n = nc[f];
+        if (EDGES) {
+          for (uint32_t i = 0; i < n && !slow; ++i) {
+            const RdEnt c = rd_cand<LEAN>(bt, r, f, i);
+            const uint32_t* sa = (c.af & SGX_AF_TARGETREV) ? sr.sa : sf.sa;
+            for (uint32_t x0 = c.lo; x0 <= c.hi && !slow; x0 += 32) {
+              const uint32_t x = x0 + lane;
+              bool ok = false;
+              uint32_t t = 0;
+              if (x <= c.hi) {
+                t = sa[x];
+                ok = rd_edge_ok(rq, lq, t, c.len, c.af, sink.name_rank, treads.len);
+              }
+              if (!rd_stage(ok, t, c.len, c.af, e_tgt, e_kaf, ecount, lane)) slow = true;
+              if (x0 > 0xffffffffu - 32) break;
+            }
+          }
+        } else {
+          if (nout + n > bt.out_cap) {
+            slow = true;
+            break;
+          }
+          const sgx_block* lst = bt.cand + ((size_t)r * 4 + f) * bt.find_cap;
+          for (uint32_t i = lane; i < n; i += 32) out[nout + i] = lst[i];
+          nout += n;
         }
-        for (uint32_t i = lane; i < n; i += 32) out[nout + i] = lst[i];
-        nout += n;
       }
     }
     if (!slow && irreducible) {
 #pragma unroll 1
       for (int side = 0; side < 2 && !slow; ++side) {
         const int fa = side == 0 ? 0 : 1, fb = side == 0 ? 3 : 2;
-        const sgx_block* la = cand + (size_t)fa * bt.find_cap;
-        const sgx_block* lb = cand + (size_t)fb * bt.find_cap;
         const uint32_t na = nc[fa], ne = nc[fa] + nc[fb];
         // ---- rows: one per (entry, row of its capped[0] interval)
         uint32_t R = 0;
         for (uint32_t e0 = 0; e0 < ne && !slow; e0 += 32) {
           const uint32_t e = e0 + lane;
-          uint64_t lo = 0, w = 0;
+          uint32_t lo = 0, w = 0;
           if (e < ne) {
-            const sgx_block* b = e < na ? la + e : lb + (e - na);
-            lo = b->capped[0];
-            w = b->capped[1] - lo + 1;
-            if (w > rows_cap) w = rows_cap + 1;
+            const RdEnt b = e < na ? rd_cand<LEAN>(bt, r, fa, e) : rd_cand<LEAN>(bt, r, fb, e - na);
+            lo = b.lo;
+            const uint64_t ww = (uint64_t)b.hi - b.lo + 1;
+            w = ww > rows_cap ? rows_cap + 1 : (uint32_t)ww;
           }
-          uint32_t incl = (uint32_t)w;
+          uint32_t incl = w;
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) {
             const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
@@ -145,9 +265,9 @@ ov_reduce_kernel(ReadsView treads, SaView sf, SaView sr, uint64_t count, int irr
             slow = true;
             break;
           }
-          const uint32_t at = R + incl - (uint32_t)w;
-          for (uint32_t x = 0; x < (uint32_t)w; ++x) {
-            r_row[at + x] = (uint32_t)(lo + x);
+          const uint32_t at = R + incl - w;
+          for (uint32_t x = 0; x < w; ++x) {
+            r_row[at + x] = lo + x;
             r_ent[at + x] = (uint16_t)e;
           }
           R += tot;
@@ -159,8 +279,8 @@ ov_reduce_kernel(ReadsView treads, SaView sf, SaView sr, uint64_t count, int irr
         bool mixed = false;
         for (uint32_t s = lane; s < R; s += 32) {
           const uint32_t e = r_ent[s];
-          const sgx_block* b = e < na ? la + e : lb + (e - na);
-          const uint32_t k = b->length, af = b->af;
+          const RdEnt b = e < na ? rd_cand<LEAN>(bt, r, fa, e) : rd_cand<LEAN>(bt, r, fb, e - na);
+          const uint32_t k = b.len, af = b.af;
           const bool tr = (af & SGX_AF_TARGETREV) != 0;
           const uint32_t t = (tr ? sr.sa : sf.sa)[r_row[s]];
           const uint32_t lt = treads.len[t];
@@ -216,7 +336,7 @@ ov_reduce_kernel(ReadsView treads, SaView sf, SaView sr, uint64_t count, int irr
             red = eq;
           }
           bool head = true;
-          if (s > 0 && r_ent[s - 1] == r_ent[s]) {
+          if (!EDGES && s > 0 && r_ent[s - 1] == r_ent[s]) {
             const uint64_t* ep = ext + (size_t)(s - 1) * extw;
             bool same = true;
             for (uint32_t q = 0; q < extw && same; ++q) same = ea[q] == ep[q];
@@ -225,42 +345,81 @@ ov_reduce_kernel(ReadsView treads, SaView sf, SaView sr, uint64_t count, int irr
           r_flag[s] = (uint16_t)((red ? 1u : 0u) | (head ? 2u : 0u));
         }
         __syncwarp();
-        // ---- one output block per surviving class
-        for (uint32_t s0 = 0; s0 < R; s0 += 32) {
-          const uint32_t s = s0 + lane;
-          const bool emit = s < R && (r_flag[s] & 3u) == 2u;
-          const unsigned em = __ballot_sync(0xffffffffu, emit);
-          if (emit) {
-            const uint32_t at = nout + __popc(em & ((1u << lane) - 1u));
-            if (at < bt.out_cap) {
+        if (EDGES) {
+          // ---- every surviving row is one candidate edge
+          for (uint32_t s0 = 0; s0 < R && !slow; s0 += 32) {
+            const uint32_t s = s0 + lane;
+            bool ok = false;
+            uint32_t t = 0, k = 0, af = 0;
+            if (s < R && !(r_flag[s] & 1u)) {
               const uint32_t e = r_ent[s];
-              const sgx_block* b = e < na ? la + e : lb + (e - na);
-              const bool tr = (b->af & SGX_AF_TARGETREV) != 0;
-              const uint32_t* inv = tr ? sf.inv : sr.inv;  // opposite (right-extension) index
-              uint32_t size = 1;
-              uint32_t mn = inv[r_tgt[s]];
-              while (s + size < R && !(r_flag[s + size] & 2u)) {
-                mn = min(mn, inv[r_tgt[s + size]]);
-                ++size;
-              }
-              sgx_block o = *b;
-              o.capped[0] = r_row[s];
-              o.capped[1] = (uint64_t)r_row[s] + size - 1;
-              o.capped[2] = mn;
-              o.capped[3] = (uint64_t)mn + size - 1;
-              out[at] = o;
+              const RdEnt b = e < na ? rd_cand<LEAN>(bt, r, fa, e) : rd_cand<LEAN>(bt, r, fb, e - na);
+              t = r_tgt[s];
+              k = b.len;
+              af = b.af;
+              ok = rd_edge_ok(rq, lq, t, k, af, sink.name_rank, treads.len);
             }
+            if (!rd_stage(ok, t, k, af, e_tgt, e_kaf, ecount, lane)) slow = true;
           }
-          nout += __popc(em);
+        } else {
+          // ---- one output block per surviving class
+          const sgx_block* la = bt.cand + ((size_t)r * 4 + fa) * bt.find_cap;
+          const sgx_block* lb = bt.cand + ((size_t)r * 4 + fb) * bt.find_cap;
+          for (uint32_t s0 = 0; s0 < R; s0 += 32) {
+            const uint32_t s = s0 + lane;
+            const bool emit = s < R && (r_flag[s] & 3u) == 2u;
+            const unsigned em = __ballot_sync(0xffffffffu, emit);
+            if (emit) {
+              const uint32_t at = nout + __popc(em & ((1u << lane) - 1u));
+              if (at < bt.out_cap) {
+                const uint32_t e = r_ent[s];
+                const sgx_block* b = e < na ? la + e : lb + (e - na);
+                const bool tr = (b->af & SGX_AF_TARGETREV) != 0;
+                const uint32_t* inv = tr ? sf.inv : sr.inv;  // opposite (right-extension) index
+                uint32_t size = 1;
+                uint32_t mn = inv[r_tgt[s]];
+                while (s + size < R && !(r_flag[s + size] & 2u)) {
+                  mn = min(mn, inv[r_tgt[s + size]]);
+                  ++size;
+                }
+                sgx_block o = *b;
+                o.capped[0] = r_row[s];
+                o.capped[1] = (uint64_t)r_row[s] + size - 1;
+                o.capped[2] = mn;
+                o.capped[3] = (uint64_t)mn + size - 1;
+                out[at] = o;
+              }
+            }
+            nout += __popc(em);
+          }
+          if (nout > bt.out_cap) slow = true;
         }
-        if (nout > bt.out_cap) slow = true;
         __syncwarp();
+      }
+    }
+    if (EDGES && !slow) {
+      // one reservation per read, then a coalesced copy of the staged edges
+      __syncwarp();
+      unsigned long long at = 0;
+      if (lane == 0 && ecount) at = atomicAdd(sink.counter, (unsigned long long)ecount);
+      at = __shfl_sync(0xffffffffu, at, 0);
+      if (at + ecount > sink.cap) {
+        if (lane == 0 && ecount) atomicOr(sink.overflow, 1u);
+      } else {
+        for (uint32_t i = lane; i < ecount; i += 32) {
+          sgx_edge e;
+          e.query = (uint32_t)qglob;
+          e.target = e_tgt[i];
+          e.length = e_kaf[i] & 0xffffu;
+          e.af = e_kaf[i] >> 16;
+          sink.edges[at + i] = e;
+        }
       }
     }
     if (lane == 0) {
       if (slow) {
-        slow_list[atomicAdd(n_slow, 1u)] = (uint32_t)r;
-      } else {
+        slow_list[atomicAdd(n_slow, 1u)] = (uint32_t)(slow_base + r);
+      } else if (!EDGES) {
         bt.nout[r] = nout;
       }
     }

@@ -94,10 +94,12 @@ struct FmPair {
   uint64_t pred[2][6];
 };
 
-template <class IdxT>
+// LEAN: write 12-byte LeanCand records (capped[0], length, flags) instead of full 72-byte blocks.
+// list (optional): work item wi searches read list[wi]; its results are stored at item index wi.
+template <class IdxT, bool LEAN>
 __global__ void __launch_bounds__(256, 4)
 ov_search_quad_kernel(FmPair fm, ReadsView reads, uint64_t first, uint64_t count, uint32_t min_ov, int rc,
-                      OvBatch bt, unsigned long long* __restrict__ lookups) {
+                      OvBatch bt, const uint32_t* __restrict__ list, unsigned long long* __restrict__ lookups) {
   const int wl = threadIdx.x & 31;
   const int q = wl & (kQuad - 1);
   const unsigned qmask = 0xfu << (wl & ~(kQuad - 1));
@@ -110,7 +112,8 @@ ov_search_quad_kernel(FmPair fm, ReadsView reads, uint64_t first, uint64_t count
   const IdxT kNone = (IdxT)-1;
 
   for (uint64_t wk = quad; wk < nwork; wk += nquads) {
-    const uint64_t r = wk / nmodes;
+    const uint64_t wi = wk / nmodes;                      // where the results are stored
+    const uint64_t r = list ? (uint64_t)list[wi] : wi;  // which read (relative to `first`)
     const int mode = rc ? (int)(wk % nmodes) : (int)(wk % nmodes) * 2;  // without rc only modes 0 and 2 run
     const int pi = mode < 2 ? 0 : 1, si = 1 - pi;  // searched index / its opposite
     const FmBlockLane* __restrict__ Pb = fm.blocks[pi];
@@ -120,7 +123,8 @@ ov_search_quad_kernel(FmPair fm, ReadsView reads, uint64_t first, uint64_t count
     const uint32_t* rw = reads.words + reads.woff[first + r];
     const uint32_t l = reads.len[first + r];
     const uint32_t af = ov_mode_af(mode);
-    sgx_block* cand = bt.cand + ((size_t)r * 4 + mode) * bt.find_cap;
+    sgx_block* cand = LEAN ? nullptr : bt.cand + ((size_t)wi * 4 + mode) * bt.find_cap;
+    LeanCand* lean = LEAN ? bt.lean + ((size_t)wi * 4 + mode) * bt.find_cap : nullptr;
     uint32_t n = 0;
 
     // C[] of the searched index in registers (selected by symbol without indexing memory inside the loop)
@@ -140,9 +144,17 @@ ov_search_quad_kernel(FmPair fm, ReadsView reads, uint64_t first, uint64_t count
       const IdxT dd = k.Ud - k.Ld;
       const uint32_t olen = l - i;
       if (olen >= min_ov && dd >= 1) {
-        if (n < bt.find_cap && q == 0)
-          quad_store_block<IdxT>(cand + n, pc0 + k.Ld, pc0 + k.Ud - 1, lo1, lo1 + dd - 1, lo0, hi0,
-                                 lo1, hi1, olen, af);
+        if (n < bt.find_cap && q == 0) {
+          if (LEAN) {
+            LeanCand lc;
+            lc.lo = (uint32_t)(pc0 + k.Ld);
+            lc.hi = (uint32_t)(pc0 + k.Ud - 1);
+            lc.len_af = olen | (af << 16);
+            lean[n] = lc;
+          } else {
+            quad_store_block<IdxT>(cand + n, pc0 + k.Ld, pc0 + k.Ud - 1, lo1, lo1 + dd - 1, lo0, hi0, lo1, hi1, olen, af);
+          }
+        }
         ++n;
       }
       // ranks of the stepped symbol and the sum of differences of the smaller symbols
@@ -186,22 +198,31 @@ ov_search_quad_kernel(FmPair fm, ReadsView reads, uint64_t first, uint64_t count
           p0hi = p0lo + d3 - 1;
           p1lo = (IdxT)Spred[0] + ks.Ld;
           p1hi = (IdxT)Spred[0] + U3d - 1;
-          if (q == 0)
-            quad_store_block<IdxT>(bt.contain + (size_t)r * 4 + mode, p0lo, p0hi, p1lo, p1hi, lo0, hi0, lo1, hi1, l, af);
+          if (q == 0) {
+            if (LEAN) {
+              LeanCand lc;
+              lc.lo = (uint32_t)p0lo;
+              lc.hi = (uint32_t)p0hi;
+              lc.len_af = l | (af << 16);
+              bt.lean_contain[(size_t)wi * 4 + mode] = lc;
+            } else {
+              quad_store_block<IdxT>(bt.contain + (size_t)wi * 4 + mode, p0lo, p0hi, p1lo, p1hi, lo0, hi0, lo1, hi1, l, af);
+            }
+          }
           ncontain = 1;
         }
       }
     }
     if (q == 0) {
-      bt.ncand[r * 4 + mode] = n < bt.find_cap ? n : bt.find_cap;
-      bt.ncontain[r * 4 + mode] = ncontain;
+      bt.ncand[wi * 4 + mode] = n < bt.find_cap ? n : bt.find_cap;
+      bt.ncontain[wi * 4 + mode] = ncontain;
     }
   }
 #undef Ppred
 #undef Spred
   // the modes a run without reverse complement skips still need their counters cleared
   if (!rc) {
-    for (uint64_t r = quad; r < count; r += nquads) {
+    for (uint64_t r = quad; r < count; r += nquads) {  // item index
       if (q == 0) {
         bt.ncand[r * 4 + 1] = 0;
         bt.ncand[r * 4 + 3] = 0;
