@@ -13,7 +13,8 @@
 //      row of read i's new suffix is N + (#symbols < c before) + rank_c(row of its previous suffix); because that is
 //      monotone in the previous row for a fixed c, ordering the inserts is ONE stable 4-way partition by c
 //      (count -> scan -> scatter), and the insertion itself is a streaming merge of the old BWT with the sorted
-//      inserts.  The merge is the dominant kernel: it reads and writes the partial BWT once per column (HBM-bound).
+//      inserts.  The merge is the dominant kernel: it reads and writes the partial BWT (4 bits per symbol) once
+//      per column (HBM-bound).
 //   3. Greedy run-length encoding (runs capped at 31) of the final symbol array into .bwt run bytes.
 //
 // Positions are 32-bit while the BWT has < 2^32 rows and 64-bit otherwise (PosT template parameter).
@@ -132,49 +133,87 @@ __global__ void sentinel_order_kernel(const uint32_t* __restrict__ sai, uint64_t
 
 // ---- 2. column passes ---------------------------------------------------------------------------------------------
 
-static const int kBcrBlock = 256;   // rows per rank checkpoint
-static const int kMergeTile = 4096; // output rows per merge CTA
+static const int kBcrBlock = 256;    // rows per rank checkpoint
+static const int kMergeTile = 8192;  // output rows per merge CTA
 static const int kMergeThreads = 256;
-static const int kMergeRpt = kMergeTile / kMergeThreads;  // 16 rows per thread
+// The partial BWT is stored 4 bits per symbol (ranks 0..4), two rows per byte, row k in bits 4*(k&1) of byte k>>1.
 
+__device__ __forceinline__ uint32_t nib_get(const uint8_t* __restrict__ B, uint64_t k) {
+  return (B[k >> 1] >> (4 * (k & 1))) & 15u;
+}
+
+// One thread per byte (two rows) of the first BWT: the N sentinel rows in sentinel order; the symbol of a
+// sentinel row is the last base of its read.
 template <class PosT>
 __global__ void bcr_init_kernel(ReadAcc acc, const uint32_t* __restrict__ sord, uint64_t n, uint8_t* __restrict__ B,
                                 uint32_t* __restrict__ ID, PosT* __restrict__ NP) {
-  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t k = 2 * i;
   if (k >= n) return;
-  const uint32_t id = sord[k];
-  const uint32_t l = acc.rv.len[id];
-  B[k] = (uint8_t)(acc.code(id, l - 1, l) + 1);
-  ID[k] = id;
-  NP[k] = (PosT)k;
+  uint32_t byte = 0;
+  for (int h = 0; h < 2; ++h) {
+    if (k + h < n) {
+      const uint32_t id = sord[k + h];
+      const uint32_t l = acc.rv.len[id];
+      byte |= (acc.code(id, l - 1, l) + 1) << (4 * h);
+      ID[k + h] = id;
+      NP[k + h] = (PosT)(k + h);
+    }
+  }
+  B[i] = (uint8_t)byte;
 }
 
-// Per-256-row counts of A,C,G,T of a symbol array: cnt[c*nb + b].
+// A | C<<16 and G | T<<16 counts of the nibbles of a word (8 rows) selected by `keep` (a mask of nibble LSBs).
+__device__ __forceinline__ void nib_count_add(uint32_t w, uint32_t keep, uint32_t& accA, uint32_t& accC, uint32_t& accG,
+                                              uint32_t& accT) {
+  const uint32_t m1 = w & 0x11111111u & keep, m2 = (w >> 1) & 0x11111111u & keep, m4 = (w >> 2) & 0x11111111u & keep;
+  accT += m4;
+  accG += m1 & m2;
+  accA += m1 & ~m2;
+  accC += m2 & ~m1;
+}
+// sum of the eight 4-bit fields of an accumulator (each field <= 15)
+__device__ __forceinline__ uint32_t nib_sum(uint32_t acc) {
+  const uint32_t v = (acc & 0x0f0f0f0fu) + ((acc >> 4) & 0x0f0f0f0fu);
+  return (v * 0x01010101u) >> 24;
+}
+
+// Per-256-row counts of A,C,G,T of a nibble-packed symbol array: cnt[c*nb + b].  One warp per block, one word per lane.
 __global__ void __launch_bounds__(256) sym_block_count_kernel(const uint8_t* __restrict__ B, uint64_t n, uint64_t nb,
                                                               uint64_t* __restrict__ cnt) {
-  // one warp per block of 256 rows, 8 bytes per lane
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= nb) return;
-  const uint64_t base = warp * kBcrBlock + (uint64_t)lane * 8;
-  uint32_t c[4] = {0, 0, 0, 0};
-  for (int j = 0; j < 8; ++j) {
-    if (base + j < n) {
-      const uint32_t s = B[base + j];
-      if (s >= 1) c[s - 1]++;
-    }
+  const uint64_t row0 = warp * kBcrBlock + (uint64_t)lane * 8;
+  uint32_t a = 0, c = 0, g = 0, t = 0;
+  if (row0 < n) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(B + row0 / 2);  // the array is padded
+    const uint64_t left = n - row0;
+    const uint32_t keep = left >= 8 ? 0x11111111u : (0x11111111u & ((1u << (4 * (uint32_t)left)) - 1u));
+    nib_count_add(w, keep, a, c, g, t);
   }
+  uint32_t w1 = nib_sum(a) | (nib_sum(c) << 16), w2 = nib_sum(g) | (nib_sum(t) << 16);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c[q] += __shfl_xor_sync(0xffffffffu, c[q], o);
+  for (int o = 16; o > 0; o >>= 1) {
+    w1 += __shfl_xor_sync(0xffffffffu, w1, o);
+    w2 += __shfl_xor_sync(0xffffffffu, w2, o);
   }
-  if (lane == 0)
-    for (int q = 0; q < 4; ++q) cnt[(uint64_t)q * nb + warp] = c[q];
+  if (lane == 0) {
+    cnt[0 * nb + warp] = w1 & 0xffffu;
+    cnt[1 * nb + warp] = w1 >> 16;
+    cnt[2 * nb + warp] = w2 & 0xffffu;
+    cnt[3 * nb + warp] = w2 >> 16;
+  }
 }
 
-__device__ __forceinline__ uint32_t count_eq_bytes(uint32_t word, uint32_t pattern) {
-  return (uint32_t)__popc(__vcmpeq4(word, pattern)) >> 3;
+// number of nibbles equal to the pattern's nibble among the first `nn` (<= 8) nibbles of w
+__device__ __forceinline__ uint32_t nib_eq_count(uint32_t w, uint32_t pat, uint32_t nn) {
+  uint32_t x = w ^ pat;
+  x |= x >> 1;
+  x |= x >> 2;
+  const uint32_t eq = ~x & 0x11111111u;
+  const uint32_t m = nn >= 8 ? 0xffffffffu : ((1u << (4 * nn)) - 1u);
+  return (uint32_t)__popc(eq & m);
 }
 
 // For every active read (in current row order): the symbol c that starts its next suffix and the row that suffix
@@ -197,30 +236,18 @@ __global__ void __launch_bounds__(256) bcr_rank_kernel(ReadAcc acc, const uint8_
   const uint32_t c = acc.code(id, l - j, l);
   const uint64_t P = (uint64_t)NP[k];
   const uint64_t b = P / kBcrBlock;
-  const uint64_t bs = b * kBcrBlock;
-  const uint32_t r = (uint32_t)(P - bs);  // rows of this block before P
-  const uint32_t pat = (c + 1) * 0x01010101u;
+  const uint32_t r = (uint32_t)(P - b * kBcrBlock);  // rows of this block before P
+  const uint32_t pat = (c + 1) * 0x11111111u;
   uint32_t inblk = 0;
-  const uint4* v = reinterpret_cast<const uint4*>(B + bs);
-  const uint32_t full = r / 16;
-  for (uint32_t q = 0; q < full; ++q) {
+  const uint4* v = reinterpret_cast<const uint4*>(B + b * (kBcrBlock / 2));  // 128 bytes per block
+  const uint32_t nvec = (r + 31) / 32;
+  for (uint32_t q = 0; q < nvec; ++q) {
     const uint4 x = v[q];
-    inblk += count_eq_bytes(x.x, pat) + count_eq_bytes(x.y, pat) + count_eq_bytes(x.z, pat) + count_eq_bytes(x.w, pat);
-  }
-  const uint32_t rem = r - full * 16;
-  if (rem) {
-    const uint4 x = v[full];
-    const uint32_t w[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int nbytes = (int)rem - 4 * q;
-      if (nbytes >= 4) {
-        inblk += count_eq_bytes(w[q], pat);
-      } else if (nbytes > 0) {
-        const uint32_t m = (1u << (8 * nbytes)) - 1u;
-        inblk += (uint32_t)__popc(__vcmpeq4(w[q], pat) & m) >> 3;
-      }
-    }
+    const uint32_t left = r - q * 32;  // nibbles of this vector that count (may exceed 32)
+    inblk += nib_eq_count(x.x, pat, left);
+    if (left > 8) inblk += nib_eq_count(x.y, pat, left - 8);
+    if (left > 16) inblk += nib_eq_count(x.z, pat, left - 16);
+    if (left > 24) inblk += nib_eq_count(x.w, pat, left - 24);
   }
   tmpC[k] = (uint8_t)c;
   tmpPos[k] = (PosT)(n_reads + scanned[(uint64_t)c * nb + b] + inblk);
@@ -261,77 +288,99 @@ __global__ void bcr_tile_bounds_kernel(const PosT* __restrict__ NP, uint64_t nac
 }
 
 // Streaming merge of the old BWT (n_old rows) with the sorted inserts (rows NP[0..nact) of the NEW array, symbols
-// SYM) into Bn (n_new rows), plus the per-256-row symbol counts of Bn.
+// SYM) into Bn (n_new rows), plus the per-256-row symbol counts of Bn.  HBM-bound by design: a CTA produces 8192 rows
+// (4 KB), a thread 32 rows (one 16-byte store).  The old rows of the tile are staged in shared memory; a thread
+// first takes the 32 old nibbles that would land on its rows if it had no inserts (five shared-memory words and
+// four funnel shifts), then opens a 4-bit gap for each of its inserts (the bits of its word of the tile's insert
+// mask), which pushes the surplus old nibbles out at the top -- exactly the ones the next thread starts with.
 template <class PosT>
 __global__ void __launch_bounds__(kMergeThreads) bcr_merge_kernel(const uint8_t* __restrict__ Bo, uint64_t n_old,
                                                                   const PosT* __restrict__ NP, const uint8_t* __restrict__ SYM,
                                                                   uint64_t nact, const uint64_t* __restrict__ tile_k0,
                                                                   uint8_t* __restrict__ Bn, uint64_t n_new, uint64_t nb,
                                                                   uint64_t* __restrict__ cnt) {
-  __shared__ uint8_t flag[kMergeTile];
-  __shared__ __align__(16) uint8_t oldb[kMergeTile + 32];
+  __shared__ __align__(16) uint32_t oldw[kMergeTile / 8 + 16];
+  __shared__ uint32_t mask[kMergeTile / 32];
   __shared__ uint64_t sh[9];
   const uint64_t t0 = (uint64_t)blockIdx.x * kMergeTile;
   const uint64_t t1 = min(t0 + (uint64_t)kMergeTile, n_new);
   const uint64_t k0 = tile_k0[blockIdx.x], k1 = tile_k0[blockIdx.x + 1];
-  const uint64_t a0 = t0 - k0;                       // first old row of this tile
+  const uint64_t a0 = t0 - k0;  // first old row of this tile
   const uint32_t nold = (uint32_t)((t1 - t0) - (k1 - k0));
-  // flags
-  uint32_t* f32 = reinterpret_cast<uint32_t*>(flag);
-  for (int i = threadIdx.x; i < kMergeTile / 4; i += kMergeThreads) f32[i] = 0;
-  // old rows -> shared, 16-byte vectors from the aligned address at or below a0
-  const uint64_t a0al = a0 & ~(uint64_t)15;
-  const uint32_t shift = (uint32_t)(a0 - a0al);
-  const uint32_t nvec = (nold + shift + 15) / 16;
-  for (uint32_t q = threadIdx.x; q < nvec; q += kMergeThreads) {
-    // the source buffer is padded, so reading whole vectors is always in bounds
-    reinterpret_cast<uint4*>(oldb)[q] = *reinterpret_cast<const uint4*>(Bo + a0al + (uint64_t)q * 16);
+  mask[threadIdx.x] = 0;
+  // old rows -> shared, 16-byte vectors from the 32-row-aligned position at or below a0 (the arrays are padded)
+  const uint64_t a0al = a0 & ~(uint64_t)31;
+  const uint32_t shift = (uint32_t)(a0 - a0al);  // nibbles
+  const uint32_t nvec = (nold + shift + 31) / 32;
+  for (uint32_t q = threadIdx.x; q < nvec; q += kMergeThreads)
+    reinterpret_cast<uint4*>(oldw)[q] = *reinterpret_cast<const uint4*>(Bo + a0al / 2 + (uint64_t)q * 16);
+  __syncthreads();
+  for (uint64_t k = k0 + threadIdx.x; k < k1; k += kMergeThreads) {
+    const uint32_t r = (uint32_t)((uint64_t)NP[k] - t0);
+    atomicOr(&mask[r >> 5], 1u << (r & 31));
   }
   __syncthreads();
-  for (uint64_t k = k0 + threadIdx.x; k < k1; k += kMergeThreads) flag[(uint32_t)((uint64_t)NP[k] - t0)] = 1;
-  __syncthreads();
-  // rows of this thread
-  const uint32_t s0 = threadIdx.x * kMergeRpt;
-  uint32_t myflags = 0, cntf = 0;
-#pragma unroll
-  for (int i = 0; i < kMergeRpt; ++i) {
-    const uint32_t f = flag[s0 + i];
-    myflags |= f << i;
-    cntf += f;
-  }
+  const uint32_t m = mask[threadIdx.x];
   uint64_t total;
-  uint32_t pre = (uint32_t)block_excl_scan((uint64_t)cntf, sh, total);  // inserts before row s0 in this tile
-  uint32_t outw[4] = {0, 0, 0, 0};
-  uint32_t c4[4] = {0, 0, 0, 0};
+  const uint32_t pre = (uint32_t)block_excl_scan((uint64_t)__popc(m), sh, total);  // inserts before my first row
+  // the 32 old nibbles starting at the one that lands on my first row
+  const uint32_t o = shift + threadIdx.x * 32 - pre;
+  const uint32_t wi = o >> 3, sft = 4 * (o & 7);
+  uint32_t out[4];
+  {
+    const uint32_t w0 = oldw[wi], w1 = oldw[wi + 1], w2 = oldw[wi + 2], w3 = oldw[wi + 3], w4 = oldw[wi + 4];
+    out[0] = __funnelshift_r(w0, w1, sft);
+    out[1] = __funnelshift_r(w1, w2, sft);
+    out[2] = __funnelshift_r(w2, w3, sft);
+    out[3] = __funnelshift_r(w3, w4, sft);
+  }
+  // open a gap for every insert, lowest row first
+  uint32_t mm = m;
+  uint64_t kk = k0 + pre;
+  while (mm) {
+    const uint32_t p = (uint32_t)__ffs(mm) - 1;
+    mm &= mm - 1;
+    const uint32_t s = SYM[kk++];
+    const uint32_t wq = p >> 3, bit = 4 * (p & 7);
 #pragma unroll
-  for (int i = 0; i < kMergeRpt; ++i) {
-    const uint32_t s = s0 + i;
-    uint32_t v = 0;
-    if (t0 + s < t1) {
-      if ((myflags >> i) & 1u) {
-        v = SYM[k0 + pre];
-        ++pre;
-      } else {
-        v = oldb[shift + s - pre];
+    for (int i = 3; i >= 1; --i)
+      if ((uint32_t)i > wq) out[i] = (out[i] << 4) | (out[i - 1] >> 28);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if ((uint32_t)i == wq) {
+        const uint32_t lowm = (1u << bit) - 1u;
+        const uint32_t up = bit < 28 ? ((out[i] >> bit) << (bit + 4)) : 0u;
+        out[i] = (out[i] & lowm) | (s << bit) | up;
       }
-      if (v >= 1) c4[v - 1]++;
     }
-    outw[i >> 2] |= v << (8 * (i & 3));
   }
-  if (t0 + s0 < t1) {
-    // Bn is padded to a multiple of the tile, so the full vector store is in bounds
-    *reinterpret_cast<uint4*>(Bn + t0 + s0) = make_uint4(outw[0], outw[1], outw[2], outw[3]);
-  }
-  // 256-row block = 16 consecutive threads
+  // rows past the end of the array stay zero
+  const uint64_t row0 = t0 + (uint64_t)threadIdx.x * 32;
+  uint32_t valid = row0 >= t1 ? 0u : (uint32_t)min((uint64_t)32, t1 - row0);
+  uint32_t accA = 0, accC = 0, accG = 0, accT = 0;
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) c4[q] += __shfl_xor_sync(0xffffffffu, c4[q], o);
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t vw = valid >= 8u * (i + 1) ? 8u : (valid > 8u * i ? valid - 8u * i : 0u);
+    const uint32_t km = vw >= 8 ? 0xffffffffu : ((1u << (4 * vw)) - 1u);
+    out[i] &= km;
+    nib_count_add(out[i], 0x11111111u, accA, accC, accG, accT);
   }
-  if ((threadIdx.x & 15) == 0) {
-    const uint64_t b = (t0 + s0) / kBcrBlock;
-    if (b < nb)
-      for (int q = 0; q < 4; ++q) cnt[(uint64_t)q * nb + b] = c4[q];
+  if (valid) *reinterpret_cast<uint4*>(Bn + row0 / 2) = make_uint4(out[0], out[1], out[2], out[3]);
+  // 256-row block = 8 consecutive threads
+  uint32_t w1 = nib_sum(accA) | (nib_sum(accC) << 16), w2 = nib_sum(accG) | (nib_sum(accT) << 16);
+#pragma unroll
+  for (int oo = 4; oo > 0; oo >>= 1) {
+    w1 += __shfl_xor_sync(0xffffffffu, w1, oo);
+    w2 += __shfl_xor_sync(0xffffffffu, w2, oo);
+  }
+  if ((threadIdx.x & 7) == 0) {
+    const uint64_t b = row0 / kBcrBlock;
+    if (b < nb) {
+      cnt[0 * nb + b] = w1 & 0xffffu;
+      cnt[1 * nb + b] = w1 >> 16;
+      cnt[2 * nb + b] = w2 & 0xffffu;
+      cnt[3 * nb + b] = w2 >> 16;
+    }
   }
 }
 
@@ -339,7 +388,9 @@ __global__ void __launch_bounds__(kMergeThreads) bcr_merge_kernel(const uint8_t*
 
 struct HeadDigit {
   const uint8_t* B;
-  __device__ __forceinline__ int operator()(uint64_t k) const { return (k == 0 || B[k] != B[k - 1]) ? 0 : 1; }
+  __device__ __forceinline__ int operator()(uint64_t k) const {
+    return (k == 0 || nib_get(B, k) != nib_get(B, k - 1)) ? 0 : 1;
+  }
 };
 struct HeadOnlyMove {
   uint64_t* heads;
@@ -363,7 +414,7 @@ __global__ void run_emit_kernel(const uint8_t* __restrict__ B, const uint64_t* _
   if (r >= n_runs) return;
   const uint64_t start = heads[r];
   uint64_t len = (r + 1 < n_runs ? heads[r + 1] : n) - start;
-  const uint8_t s = (uint8_t)(B[start] << 5);
+  const uint8_t s = (uint8_t)(nib_get(B, start) << 5);
   uint64_t o = boff[r];
   while (len > 0) {
     const uint32_t c = len >= 31 ? 31u : (uint32_t)len;
@@ -400,7 +451,7 @@ static void bcr_passes(sgx_ctx* ctx, const sgx_reads* reads, const ReadAcc& acc,
   uint8_t* Bn = B1;
 
   uint64_t n_cur = N;
-  SGX_LAUNCH(ctx, (bcr_init_kernel<PosT>), grid_for(N, 256), 256, 0, acc, d_sord, N, B, ID, NP);
+  SGX_LAUNCH(ctx, (bcr_init_kernel<PosT>), grid_for((N + 1) / 2, 256), 256, 0, acc, d_sord, N, B, ID, NP);
   uint64_t nb = n_cur / kBcrBlock + 1;
   SGX_LAUNCH(ctx, sym_block_count_kernel, grid_for(nb * 32, 256), 256, 0, (const uint8_t*)B, n_cur, nb, cnt.p);
   scan_exclusive(ctx, cnt.p, 4 * nb, scan_ws.p, (uint64_t*)nullptr);
@@ -426,7 +477,7 @@ static void bcr_passes(sgx_ctx* ctx, const sgx_reads* reads, const ReadAcc& acc,
                (const PosT*)NP2, (const uint8_t*)SYM.p, nact, (const uint64_t*)tile_k0.p, Bn, n_new, nb_new, cnt.p);
     k_merge.tick();
     out->merge_launches++;
-    out->merge_bytes += n_cur + n_new + nact * (sizeof(PosT) + 1);
+    out->merge_bytes += (n_cur + n_new) / 2 + nact * (sizeof(PosT) + 1);
     scan_exclusive(ctx, cnt.p, 4 * nb_new, scan_ws.p, (uint64_t*)nullptr);
     std::swap(B, Bn);
     std::swap(ID, ID2);
@@ -524,7 +575,8 @@ void index_build(sgx_ctx* ctx, const sgx_reads* reads, int order, bool reversed,
       nact[l] = run;
     }
   }
-  const uint64_t padded = ((S + kMergeTile - 1) / kMergeTile + 1) * kMergeTile + 64;
+  // bytes of a 4-bit array of S rows, padded by a tile and a vector so that whole-vector accesses stay in bounds
+  const uint64_t padded = (((S + kMergeTile - 1) / kMergeTile + 2) * kMergeTile) / 2 + 128;
   DevBuf<uint8_t> B0(padded), B1(padded);
   SGX_CUDA(cudaMemsetAsync(B0.p, 0, padded, ctx->stream));
   SGX_CUDA(cudaMemsetAsync(B1.p, 0, padded, ctx->stream));
