@@ -581,7 +581,9 @@ void index_build(sgx_ctx* ctx, const sgx_reads* reads, int order, bool reversed,
   SGX_CUDA(cudaMemsetAsync(B0.p, 0, padded, ctx->stream));
   SGX_CUDA(cudaMemsetAsync(B1.p, 0, padded, ctx->stream));
   uint8_t* Bfinal = nullptr;
-  if (S < 0xffffffffull) {
+  // SGX_FORCE_WIDE=1 (tests): take the 64-bit position path on inputs that would fit 32 bits
+  const char* fw = getenv("SGX_FORCE_WIDE");
+  if (S < 0xffffffffull && !(fw && fw[0] == '1')) {
     bcr_passes<uint32_t>(ctx, reads, acc, d_sord.p, nact, S, B0.p, B1.p, &Bfinal, out, k_merge);
   } else {
     bcr_passes<uint64_t>(ctx, reads, acc, d_sord.p, nact, S, B0.p, B1.p, &Bfinal, out, k_merge);

@@ -170,7 +170,8 @@ struct OvPlan {
       fmp.pred[0][i] = vf.pred[i];
       fmp.pred[1][i] = vr.pred[i];
     }
-    narrow = f->n < 0xffffffffull && r->n < 0xffffffffull;  // 32-bit positions suffice
+    const char* fw = getenv("SGX_FORCE_WIDE");  // tests: exercise the 64-bit position path on small inputs
+    narrow = f->n < 0xffffffffull && r->n < 0xffffffffull && !(fw && fw[0] == '1');  // 32-bit positions suffice
     const uint32_t lmax = rd->max_len;
     find_cap = lmax > m ? lmax - m : 1;
     out_cap = 4 * find_cap + 4;

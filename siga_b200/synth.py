@@ -15,6 +15,7 @@ for _a, _b in zip(b"ACGT", b"TGCA"):
 CONFIGS = {
     "cfg1": dict(genome=1_000_000, read_len=100, n_reads=20_000, err=0.0, seed=101, paired=True),
     "cfg2": dict(genome=4_600_000, read_len=150, coverage=100, err=0.01, seed=202),
+    "cfg3": dict(genome=4_600_000, read_len=150, coverage=100, err=0.01, seed=202),  # same reads, min-overlap sweep
     "cfg4": dict(genome=100_000_000, read_len=150, coverage=50, err=0.0, seed=404),
     "cfg5": dict(genome=64_000_000, read_len=250, coverage=40, err=0.0, seed=505),
 }
@@ -113,3 +114,13 @@ def write_fasta(path, reads, names=None, prefix="r"):
                 nm = names[i] if names is not None else "%s%d" % (prefix, i)
                 seq = r if isinstance(r, (bytes, bytearray)) else (r.encode() if isinstance(r, str) else bytes(r))
                 f.write(b">" + nm.encode() + b"\n" + seq + b"\n")
+
+
+def default_name_ranks(n, prefix="r"):
+    """Rank of the default names r0..r(n-1) in std::string order (vectorised; equal to api.name_ranks of the list)."""
+    width = len(prefix) + len(str(max(n - 1, 0)))
+    names = np.char.add(prefix, np.arange(n).astype(str)).astype("S%d" % width)
+    order = np.argsort(names, kind="stable")
+    rank = np.empty(n, dtype=np.uint32)
+    rank[order] = np.arange(n, dtype=np.uint32)
+    return rank

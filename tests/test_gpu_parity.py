@@ -350,3 +350,11 @@ def test_cuda_path_reproduces_golden_fixture(ctx, path):
             ctx.free_fm(rev)
     finally:
         ctx.free_reads(r)
+
+
+def test_wide_position_paths_on_small_input(ctx, monkeypatch):
+    """The 64-bit position kernels (BWT >= 2^32 symbols, e.g. config 4) forced onto a golden fixture."""
+    monkeypatch.setenv("SGX_FORCE_WIDE", "1")
+    for path in _GOLDEN:
+        if any(k in path for k in ("random_fixed36_dups", "variable_length", "periodic30")):
+            test_cuda_path_reproduces_golden_fixture(ctx, path)
