@@ -110,6 +110,24 @@ __device__ __forceinline__ bool rd_edge_ok(uint32_t rq, uint32_t lq, uint32_t t,
   return !(rq < rt || (contain && (af & SGX_AF_QUERYREV)));
 }
 
+// 16 bases (32 bits) of a 2-bit packed read starting at base `pos` (the read store is padded by two words).
+__device__ __forceinline__ uint32_t rd_get16(const uint32_t* __restrict__ w, uint32_t pos) {
+  return __funnelshift_r(w[pos >> 4], w[(pos >> 4) + 1], 2 * (pos & 15));
+}
+// reverse the order of the sixteen 2-bit groups of a word
+__device__ __forceinline__ uint32_t rd_rev16(uint32_t x) {
+  x = __brev(x);
+  return ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+}
+// Bases [16*d, 16*d+16) of the extension string of a row: forward targets continue after the overlap
+// (t[k + p]); TARGETREV targets are read backwards (t[lt-1-k-p]).  Garbage beyond the extension is masked by the caller.
+__device__ __forceinline__ uint32_t rd_ext16(const uint32_t* __restrict__ w, uint32_t lt, uint32_t k, bool tr, uint32_t d) {
+  if (!tr) return rd_get16(w, k + 16 * d);
+  const int s0 = (int)lt - (int)k - 16 * (int)d - 16;  // first forward base of this chunk
+  const uint32_t x = s0 >= 0 ? rd_get16(w, (uint32_t)s0) : (s0 > -16 ? (w[0] << (2 * (uint32_t)(-s0))) : 0u);
+  return rd_rev16(x);
+}
+
 // Warp-cooperative append of up to 32 staged edges (one per lane with `ok`).  Returns false on staging overflow.
 __device__ __forceinline__ bool rd_stage(bool ok, uint32_t t, uint32_t k, uint32_t af, uint32_t* e_tgt, uint32_t* e_kaf,
                                          uint32_t& ecount, int lane) {
@@ -164,22 +182,9 @@ ov_reduce_kernel(ReadsView qreads, ReadsView treads, SaView sf, SaView sr, uint6
     }
     uint32_t ecount = 0;
 
-    // ---- SubMaximalBlockFilter precondition: no two capped[0] intervals of a list intersect (then the filter only
-    //      reorders, src/overlap_builder.cpp:929-953).  Lists carry the containment blocks of their index side.
-#pragma unroll 1
-    for (int f = 0; f < 4; ++f) {
-      const int q0 = f < 2 ? 0 : 2;
-      const uint32_t n = nc[f] + nk[q0] + nk[q0 + 1];
-      for (uint32_t i = lane; i < n; i += 32) {
-        const RdEnt bi = i < nc[f] ? rd_cand<LEAN>(bt, r, f, i) : rd_contain<LEAN>(bt, r, (i - nc[f] == 0 && nk[q0]) ? q0 : q0 + 1);
-        for (uint32_t j = i + 1; j < n; ++j) {
-          const RdEnt bj = j < nc[f] ? rd_cand<LEAN>(bt, r, f, j) : rd_contain<LEAN>(bt, r, (j - nc[f] == 0 && nk[q0]) ? q0 : q0 + 1);
-          if (rd_intersect(bi.lo, bi.hi, bj.lo, bj.hi)) slow = true;
-        }
-      }
-    }
-    slow = __any_sync(0xffffffffu, slow);
-
+    // The SubMaximalBlockFilter precondition (no two capped[0] intervals of a list intersect, so that the filter
+    // only reorders, src/overlap_builder.cpp:929-953) is checked on the row table of each side below: lists carry
+    // the containment blocks of their index side, and two entries of a list intersect iff they share a row.
     uint32_t nout = 0;
     if (!slow) {
       // containment blocks go straight out: containfwd then containrev (src/overlap_builder.cpp:1160-1162)
@@ -205,40 +210,7 @@ ov_reduce_kernel(ReadsView qreads, ReadsView treads, SaView sf, SaView sr, uint6
         }
       }
     }
-    if (!slow && !irreducible) {
-      // exhaustive mode: suffixfwd, suffixrev, prefixfwd, prefixrev (src/overlap_builder.cpp:1175-1178)
-      const int order[4] = {0, 3, 1, 2};
-      for (int q = 0; q < 4 && !slow; ++q) {
-        const int f = order[q];
-        const uint32_t n = nc[f];
-        if (EDGES) {
-          for (uint32_t i = 0; i < n && !slow; ++i) {
-            const RdEnt c = rd_cand<LEAN>(bt, r, f, i);
-            const uint32_t* sa = (c.af & SGX_AF_TARGETREV) ? sr.sa : sf.sa;
-            for (uint32_t x0 = c.lo; x0 <= c.hi && !slow; x0 += 32) {
-              const uint32_t x = x0 + lane;
-              bool ok = false;
-              uint32_t t = 0;
-              if (x <= c.hi) {
-                t = sa[x];
-                ok = rd_edge_ok(rq, lq, t, c.len, c.af, sink.name_rank, treads.len);
-              }
-              if (!rd_stage(ok, t, c.len, c.af, e_tgt, e_kaf, ecount, lane)) slow = true;
-              if (x0 > 0xffffffffu - 32) break;
-            }
-          }
-        } else {
-          if (nout + n > bt.out_cap) {
-            slow = true;
-            break;
-          }
-          const sgx_block* lst = bt.cand + ((size_t)r * 4 + f) * bt.find_cap;
-          for (uint32_t i = lane; i < n; i += 32) out[nout + i] = lst[i];
-          nout += n;
-        }
-      }
-    }
-    if (!slow && irreducible) {
+    if (!slow) {
 #pragma unroll 1
       for (int side = 0; side < 2 && !slow; ++side) {
         const int fa = side == 0 ? 0 : 1, fb = side == 0 ? 3 : 2;
@@ -273,11 +245,34 @@ ov_reduce_kernel(ReadsView qreads, ReadsView treads, SaView sf, SaView sr, uint6
           R += tot;
         }
         if (slow) break;
+        // containment blocks belong to both lists of their index side: rows tagged 0xfff0 + 2*(0: list fa, 1: list fb)
+        // + (0/1: which of the side's two containment blocks)
+        const uint32_t Rc = R;  // candidate rows are [0, Rc)
+        for (int h = 0; h < 2 && !slow; ++h) {
+          const int f = h == 0 ? fa : fb;
+          const int q0 = f < 2 ? 0 : 2;
+          for (int q = q0; q < q0 + 2 && !slow; ++q) {
+            if (!nk[q]) continue;
+            const RdEnt c = rd_contain<LEAN>(bt, r, q);
+            const uint64_t ww = (uint64_t)c.hi - c.lo + 1;
+            if (R + ww > rows_cap) {
+              slow = true;
+              break;
+            }
+            for (uint32_t x = lane; x < (uint32_t)ww; x += 32) {
+              r_row[R + x] = c.lo + x;
+              r_ent[R + x] = (uint16_t)(0xfff0u + 2 * h + (q - q0));
+            }
+            R += (uint32_t)ww;
+          }
+        }
+        if (slow) break;
         __syncwarp();
-        // ---- per row: target read, extension string in query orientation
+        // ---- per candidate row: target read, extension string in query orientation (word level)
+        //      (exhaustive mode, src/overlap_builder.cpp:1175-1178, only needs the rows and the intersection test)
         uint32_t len0 = 0;
         bool mixed = false;
-        for (uint32_t s = lane; s < R; s += 32) {
+        for (uint32_t s = lane; s < Rc && irreducible; s += 32) {
           const uint32_t e = r_ent[s];
           const RdEnt b = e < na ? rd_cand<LEAN>(bt, r, fa, e) : rd_cand<LEAN>(bt, r, fb, e - na);
           const uint32_t k = b.len, af = b.af;
@@ -291,39 +286,48 @@ ov_reduce_kernel(ReadsView qreads, ReadsView treads, SaView sf, SaView sr, uint6
           r_n[s] = (uint16_t)n;
           r_flag[s] = (uint16_t)lt;  // borrowed until the length check below
           const uint32_t* w = treads.words + treads.woff[t];
-          const uint32_t cmask = (af & SGX_AF_QUERYCOMP) ? 3u : 0u;
-          uint64_t acc = 0;
+          const uint32_t cm = (af & SGX_AF_QUERYCOMP) ? 0xffffffffu : 0u;
           uint64_t* dst = ext + (size_t)s * extw;
-          for (uint32_t p = 0; p < n && !mixed; ++p) {
-            const uint32_t j = tr ? lt - 1 - k - p : k + p;
-            const uint64_t code = ((w[j >> 4] >> (2 * (j & 15))) & 3u) ^ cmask;
-            acc |= code << (2 * (p & 31));
-            if ((p & 31) == 31) {
-              dst[p >> 5] = acc;
-              acc = 0;
-            }
-          }
           if (!mixed) {
-            if (n & 31) dst[n >> 5] = acc;
-            for (uint32_t q = (n + 31) >> 5; q < extw; ++q) dst[q] = 0;
+            for (uint32_t q = 0; q < extw; ++q) {
+              uint64_t v = 0;
+              if (32 * q < n) {
+                const uint32_t lo = rd_ext16(w, lt, k, tr, 2 * q) ^ cm;
+                const uint32_t hi = (32 * q + 16 < n) ? (rd_ext16(w, lt, k, tr, 2 * q + 1) ^ cm) : 0u;
+                v = ((uint64_t)hi << 32) | lo;
+                const uint32_t left = n - 32 * q;
+                if (left < 32) v &= (1ull << (2 * left)) - 1ull;
+              }
+              dst[q] = v;
+            }
           }
         }
         __syncwarp();
-        if (R) len0 = r_flag[0];
-        for (uint32_t s = lane; s < R; s += 32)
+        if (Rc && irreducible) len0 = r_flag[0];
+        for (uint32_t s = lane; s < Rc && irreducible; s += 32)
           if (r_flag[s] != len0) mixed = true;
         if (__any_sync(0xffffffffu, mixed)) {
           slow = true;  // targets of different lengths: group semantics are not the simple rule -> literal path
           break;
         }
         __syncwarp();
-        // ---- transitive rows and class heads
+        // ---- one pass over the other rows: shared row inside a list (intersection), transitive rows, class heads
+        bool inter = false;
         for (uint32_t s = lane; s < R; s += 32) {
-          const uint32_t ka = r_k[s];
+          const uint32_t es = r_ent[s];
+          const uint32_t ls = es >= 0xfff0u ? (es - 0xfff0u) >> 1 : (es < na ? 0u : 1u);  // 0 = list fa, 1 = list fb
+          const uint32_t rows = r_row[s];
+          const bool cand_row = s < Rc;
+          const uint32_t ka = (cand_row && irreducible) ? r_k[s] : 0;
           const uint64_t* ea = ext + (size_t)s * extw;
           bool red = false;
-          for (uint32_t b2 = 0; b2 < R && !red; ++b2) {
-            if (r_k[b2] <= ka) continue;
+          for (uint32_t b2 = 0; b2 < R; ++b2) {
+            if (b2 != s && r_row[b2] == rows) {
+              const uint32_t eb2 = r_ent[b2];
+              const uint32_t lb = eb2 >= 0xfff0u ? (eb2 - 0xfff0u) >> 1 : (eb2 < na ? 0u : 1u);
+              if (lb == ls && eb2 != es) inter = true;
+            }
+            if (!irreducible || !cand_row || red || b2 >= Rc || r_k[b2] <= ka) continue;
             const uint32_t nb = r_n[b2];
             const uint64_t* eb = ext + (size_t)b2 * extw;
             bool eq = true;
@@ -335,15 +339,22 @@ ov_reduce_kernel(ReadsView qreads, ReadsView treads, SaView sf, SaView sr, uint6
             }
             red = eq;
           }
-          bool head = true;
-          if (!EDGES && s > 0 && r_ent[s - 1] == r_ent[s]) {
-            const uint64_t* ep = ext + (size_t)(s - 1) * extw;
-            bool same = true;
-            for (uint32_t q = 0; q < extw && same; ++q) same = ea[q] == ep[q];
-            head = !same;
+          if (cand_row) {
+            bool head = true;
+            if (!EDGES && irreducible && s > 0 && r_ent[s - 1] == es) {
+              const uint64_t* ep = ext + (size_t)(s - 1) * extw;
+              bool same = true;
+              for (uint32_t q = 0; q < extw && same; ++q) same = ea[q] == ep[q];
+              head = !same;
+            }
+            r_flag[s] = (uint16_t)((red ? 1u : 0u) | (head ? 2u : 0u));
           }
-          r_flag[s] = (uint16_t)((red ? 1u : 0u) | (head ? 2u : 0u));
         }
+        if (__any_sync(0xffffffffu, inter)) {
+          slow = true;  // intervals of one list intersect (periodic sequence): SubMaximalBlockFilter must run
+          break;
+        }
+        R = Rc;  // the containment rows were only needed for the intersection test
         __syncwarp();
         if (EDGES) {
           // ---- every surviving row is one candidate edge
@@ -354,7 +365,7 @@ ov_reduce_kernel(ReadsView qreads, ReadsView treads, SaView sf, SaView sr, uint6
             if (s < R && !(r_flag[s] & 1u)) {
               const uint32_t e = r_ent[s];
               const RdEnt b = e < na ? rd_cand<LEAN>(bt, r, fa, e) : rd_cand<LEAN>(bt, r, fb, e - na);
-              t = r_tgt[s];
+              t = irreducible ? r_tgt[s] : ((b.af & SGX_AF_TARGETREV) ? sr.sa : sf.sa)[r_row[s]];
               k = b.len;
               af = b.af;
               ok = rd_edge_ok(rq, lq, t, k, af, sink.name_rank, treads.len);
@@ -362,10 +373,18 @@ ov_reduce_kernel(ReadsView qreads, ReadsView treads, SaView sf, SaView sr, uint6
             if (!rd_stage(ok, t, k, af, e_tgt, e_kaf, ecount, lane)) slow = true;
           }
         } else {
-          // ---- one output block per surviving class
+          // ---- one output block per surviving class (exhaustive mode: the candidate blocks themselves)
           const sgx_block* la = bt.cand + ((size_t)r * 4 + fa) * bt.find_cap;
           const sgx_block* lb = bt.cand + ((size_t)r * 4 + fb) * bt.find_cap;
-          for (uint32_t s0 = 0; s0 < R; s0 += 32) {
+          if (!irreducible) {
+            if (nout + ne > bt.out_cap) {
+              slow = true;
+              break;
+            }
+            for (uint32_t i = lane; i < ne; i += 32) out[nout + i] = i < na ? la[i] : lb[i - na];
+            nout += ne;
+          }
+          for (uint32_t s0 = 0; s0 < R && irreducible; s0 += 32) {
             const uint32_t s = s0 + lane;
             const bool emit = s < R && (r_flag[s] & 3u) == 2u;
             const unsigned em = __ballot_sync(0xffffffffu, emit);

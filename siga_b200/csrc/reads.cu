@@ -97,7 +97,8 @@ sgx_reads* reads_pack(sgx_ctx* ctx, const char* ascii, const uint64_t* off, uint
   SGX_CUDA(cudaStreamSynchronize(ctx->stream));
   SGX_REQUIRE((flags[2] & 1u) == 0, SGX_EINVAL, "sgx_reads_pack: empty read or non-monotonic offsets");
   DevBuf<uint32_t> d_words;
-  d_words.alloc_owned(n_words);
+  d_words.alloc_owned(n_words + 4);  // padded: word-level readers may touch one word past a read
+  SGX_CUDA(cudaMemsetAsync(d_words.p + n_words, 0, 4 * sizeof(uint32_t), ctx->stream));
   // the offsets handed to the pack kernel are relative to the uploaded slice
   const uint64_t base = off[0];
   if (base != 0) {
