@@ -26,10 +26,22 @@ struct QuadRank {
   IdxT Ld, Ud;      // rank of '$' at both ends (same on all lanes)
 };
 
-// Ranks of all symbols at prefix lengths plo <= phi, distributed over the quad.
+// fm_lane_counts with the prefix mask built from a clamped PTX shift (shl.b32 yields 0 for shift amounts >= 32).
+__device__ __forceinline__ void quad_lane_counts(uint32_t p0, uint32_t p1, uint32_t p2, int k, int r, uint32_t& w1, uint32_t& w2) {
+  const int nb = r - 32 * k;
+  uint32_t hi_mask;
+  asm("shl.b32 %0, %1, %2;" : "=r"(hi_mask) : "r"(0xffffffffu), "r"((uint32_t)max(nb, 0)));
+  const uint32_t nd = ~(p2 | hi_mask);
+  const uint32_t hi = nd & p1, lo = nd & ~p1;
+  w1 = (uint32_t)__popc(lo & ~p0) | ((uint32_t)__popc(lo & p0) << 16);
+  w2 = (uint32_t)__popc(hi & ~p0) | ((uint32_t)__popc(hi & p0) << 16);
+}
+
+// Ranks of all symbols at prefix lengths plo <= phi, distributed over the quad.  Every lane of the warp calls this
+// together (full-mask shuffles); the xor distances 1 and 2 keep the exchange inside each quad.
 template <class IdxT>
-__device__ __forceinline__ QuadRank<IdxT> quad_rank(const FmBlockLane* __restrict__ blocks, IdxT plo, IdxT phi, int q,
-                                                    unsigned qmask) {
+__device__ __forceinline__ QuadRank<IdxT> quad_rank(const FmBlockLane* __restrict__ blocks, IdxT plo, IdxT phi, int q) {
+  const unsigned qmask = 0xffffffffu;
   const uint64_t b1 = (uint64_t)plo >> kBlockShift, b2 = (uint64_t)phi >> kBlockShift;
   const int r1 = (int)(plo & (kBlockSyms - 1)), r2 = (int)(phi & (kBlockSyms - 1));
   const uint4* pa = reinterpret_cast<const uint4*>(blocks + b1 * kGroup + q);
@@ -41,12 +53,12 @@ __device__ __forceinline__ QuadRank<IdxT> quad_rank(const FmBlockLane* __restric
     c1 = __ldg(pb + 4);
   }
   uint32_t x1, x2, y1, y2, la1, la2, lb1, lb2;
-  fm_lane_counts(a0.x, a0.y, a0.z, q, r1, x1, x2);
-  fm_lane_counts(a1.x, a1.y, a1.z, q + 4, r1, y1, y2);
+  quad_lane_counts(a0.x, a0.y, a0.z, q, r1, x1, x2);
+  quad_lane_counts(a1.x, a1.y, a1.z, q + 4, r1, y1, y2);
   la1 = x1 + y1;
   la2 = x2 + y2;
-  fm_lane_counts(c0.x, c0.y, c0.z, q, r2, x1, x2);
-  fm_lane_counts(c1.x, c1.y, c1.z, q + 4, r2, y1, y2);
+  quad_lane_counts(c0.x, c0.y, c0.z, q, r2, x1, x2);
+  quad_lane_counts(c1.x, c1.y, c1.z, q + 4, r2, y1, y2);
   lb1 = x1 + y1;
   lb2 = x2 + y2;
 #pragma unroll
@@ -96,13 +108,18 @@ struct FmPair {
 
 // LEAN: write 12-byte LeanCand records (capped[0], length, flags) instead of full 72-byte blocks.
 // list (optional): work item wi searches read list[wi]; its results are stored at item index wi.
+//
+// Control flow is WARP-uniform: every loop runs while any quad of the warp still has work and finished quads ride
+// along with their loads pointed at block 0 and their state frozen.  That allows full-mask shuffles (a quad-mask
+// shuffle costs a MATCH/REDUX/VOTE/branch sequence per use to verify convergence) and costs nothing on fixed-length
+// input, where all quads of a warp finish together.
 template <class IdxT, bool LEAN>
 __global__ void __launch_bounds__(256, 4)
 ov_search_quad_kernel(FmPair fm, ReadsView reads, uint64_t first, uint64_t count, uint32_t min_ov, int rc,
                       OvBatch bt, const uint32_t* __restrict__ list, unsigned long long* __restrict__ lookups) {
+  const unsigned kFull = 0xffffffffu;
   const int wl = threadIdx.x & 31;
   const int q = wl & (kQuad - 1);
-  const unsigned qmask = 0xfu << (wl & ~(kQuad - 1));
   const int qbase = wl & ~(kQuad - 1);
   const uint64_t quad = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / kQuad;
   const uint64_t nquads = ((uint64_t)gridDim.x * blockDim.x) / kQuad;
@@ -111,11 +128,12 @@ ov_search_quad_kernel(FmPair fm, ReadsView reads, uint64_t first, uint64_t count
   unsigned long long nlook = 0;
   const IdxT kNone = (IdxT)-1;
 
-  for (uint64_t wk = quad; wk < nwork; wk += nquads) {
-    const uint64_t wi = wk / nmodes;                      // where the results are stored
+  for (uint64_t wk = quad; __any_sync(kFull, wk < nwork); wk += nquads) {
+    const bool have = wk < nwork;
+    const uint64_t wi = have ? wk / nmodes : 0;         // where the results are stored
     const uint64_t r = list ? (uint64_t)list[wi] : wi;  // which read (relative to `first`)
     const int mode = rc ? (int)(wk % nmodes) : (int)(wk % nmodes) * 2;  // without rc only modes 0 and 2 run
-    const int pi = mode < 2 ? 0 : 1, si = 1 - pi;  // searched index / its opposite
+    const int pi = mode < 2 ? 0 : 1, si = 1 - pi;       // searched index / its opposite
     const FmBlockLane* __restrict__ Pb = fm.blocks[pi];
     const FmBlockLane* __restrict__ Sb = fm.blocks[si];
 #define Ppred fm.pred[pi]
@@ -126,74 +144,91 @@ ov_search_quad_kernel(FmPair fm, ReadsView reads, uint64_t first, uint64_t count
     sgx_block* cand = LEAN ? nullptr : bt.cand + ((size_t)wi * 4 + mode) * bt.find_cap;
     LeanCand* lean = LEAN ? bt.lean + ((size_t)wi * 4 + mode) * bt.find_cap : nullptr;
     uint32_t n = 0;
-
+    // the searched string walks the stored read forwards or backwards, complemented or not (ov_sym)
+    const bool backwards = mode == 1 || mode == 2;  // string position k reads base l-1-k
+    const uint32_t cm = (mode == 1 || mode == 3) ? 3u : 0u;
     // C[] of the searched index in registers (selected by symbol without indexing memory inside the loop)
     const IdxT pc0 = (IdxT)Ppred[0], pc1 = (IdxT)Ppred[1], pc2 = (IdxT)Ppred[2], pc3 = (IdxT)Ppred[3], pc4 = (IdxT)Ppred[4];
     int c = ov_sym(rw, l, mode, l - 1);
     IdxT lo0 = (IdxT)Ppred[c], hi0 = (IdxT)(Ppred[c + 1] - 1);
     IdxT lo1 = (IdxT)Spred[c], hi1 = (IdxT)(Spred[c + 1] - 1);
-    int cnext = l > 1 ? ov_sym(rw, l, mode, l - 2) : 0;
+    // base index of string position l-2 and its step as the string position decreases
+    uint32_t j = backwards ? 1u : l - 2;
+    const uint32_t dj = backwards ? 1u : 0xffffffffu;
+    uint32_t i = have ? l - 1 : 0;  // remaining steps
+    bool live = have && i > 0 && hi0 != kNone && hi0 >= lo0;
+    int cnext = live ? (int)((((rw[j >> 4] >> (2 * (j & 15))) & 3u) ^ cm) + 1u) : 1;
 #pragma unroll 1
-    for (uint32_t i = l - 1; i > 0; --i) {
-      const bool valid = hi0 != kNone && hi0 >= lo0;
-      if (!valid) break;  // an empty interval stays empty and emits nothing (see ov_find)
+    while (__any_sync(kFull, live)) {
       c = cnext;
-      if (i > 1) cnext = ov_sym(rw, l, mode, i - 2);  // prefetch the symbol of the next step
-      const QuadRank<IdxT> k = quad_rank<IdxT>(Pb, lo0, (IdxT)(hi0 + 1), q, qmask);
-      nlook += 2;
-      const IdxT dd = k.Ud - k.Ld;
-      const uint32_t olen = l - i;
-      if (olen >= min_ov && dd >= 1) {
-        if (n < bt.find_cap && q == 0) {
-          if (LEAN) {
-            LeanCand lc;
-            lc.lo = (uint32_t)(pc0 + k.Ld);
-            lc.hi = (uint32_t)(pc0 + k.Ud - 1);
-            lc.len_af = olen | (af << 16);
-            lean[n] = lc;
-          } else {
-            quad_store_block<IdxT>(cand + n, pc0 + k.Ld, pc0 + k.Ud - 1, lo1, lo1 + dd - 1, lo0, hi0, lo1, hi1, olen, af);
-          }
-        }
-        ++n;
-      }
+      j += dj;
+      if (live && i > 1) cnext = (int)((((rw[j >> 4] >> (2 * (j & 15))) & 3u) ^ cm) + 1u);  // next step's symbol
+      // a finished quad keeps its state and points its loads at block 0
+      const QuadRank<IdxT> k = quad_rank<IdxT>(Pb, live ? lo0 : (IdxT)0, live ? (IdxT)(hi0 + 1) : (IdxT)0, q);
       // ranks of the stepped symbol and the sum of differences of the smaller symbols
-      const IdxT Lc = __shfl_sync(qmask, k.Lq, qbase + c - 1);
-      const IdxT Uc = __shfl_sync(qmask, k.Uq, qbase + c - 1);
+      const IdxT Lc = __shfl_sync(kFull, k.Lq, qbase + c - 1);
+      const IdxT Uc = __shfl_sync(kFull, k.Uq, qbase + c - 1);
       IdxT below = (q < c - 1) ? (IdxT)(k.Uq - k.Lq) : (IdxT)0;
 #pragma unroll
-      for (int m = 1; m < kQuad; m <<= 1) below += __shfl_xor_sync(qmask, below, m);
-      below += dd;
-      lo1 = lo1 + below;
-      hi1 = lo1 + (Uc - Lc) - 1;
-      const IdxT pc = c == 1 ? pc1 : (c == 2 ? pc2 : (c == 3 ? pc3 : pc4));
-      lo0 = pc + Lc;
-      hi0 = pc + Uc - 1;
-    }
-    uint32_t ncontain = 0;
-    if (hi0 != kNone && hi0 >= lo0) {
-      // containment handling (src/overlap_builder.cpp:877-905)
-      const QuadRank<IdxT> kp = quad_rank<IdxT>(Pb, lo0, (IdxT)(hi0 + 1), q, qmask);
-      const QuadRank<IdxT> ks = quad_rank<IdxT>(Sb, lo1, (IdxT)(hi1 + 1), q, qmask);
-      nlook += 4;
-      // any non-'$' extension on either side?
-      const bool mydna = (kp.Uq - kp.Lq) > 0 || (ks.Uq - ks.Lq) > 0;
-      const bool dna = __ballot_sync(qmask, mydna) != 0;
-      if (dna) {
-        if (q == 0) bt.substring[r] = 1;
-      } else {
-        const IdxT d = kp.Ud - kp.Ld;
-        const IdxT p0lo = (IdxT)Ppred[0] + kp.Ld;
-        IdxT p0hi = (IdxT)Ppred[0] + kp.Ud - 1;
-        IdxT p1lo = lo1, p1hi = lo1 + d - 1;
-        const bool v0 = p0hi != kNone && p0hi >= p0lo, v1 = p1hi != kNone && p1hi >= p1lo;
-        if (v0 && v1) {
-          IdxT U3d = ks.Ud;
-          if (p1hi != hi1) {
-            const QuadRank<IdxT> k3 = quad_rank<IdxT>(Sb, lo1, (IdxT)(p1hi + 1), q, qmask);
-            U3d = k3.Ud;
-            nlook += 1;
+      for (int m = 1; m < kQuad; m <<= 1) below += __shfl_xor_sync(kFull, below, m);
+      if (live) {
+        nlook += 2;
+        const IdxT dd = k.Ud - k.Ld;
+        const uint32_t olen = l - i;
+        if (olen >= min_ov && dd >= 1) {
+          if (n < bt.find_cap && q == 0) {
+            if (LEAN) {
+              LeanCand lc;
+              lc.lo = (uint32_t)(pc0 + k.Ld);
+              lc.hi = (uint32_t)(pc0 + k.Ud - 1);
+              lc.len_af = olen | (af << 16);
+              lean[n] = lc;
+            } else {
+              quad_store_block<IdxT>(cand + n, pc0 + k.Ld, pc0 + k.Ud - 1, lo1, lo1 + dd - 1, lo0, hi0, lo1, hi1, olen, af);
+            }
           }
+          ++n;
+        }
+        below += dd;
+        lo1 = lo1 + below;
+        hi1 = lo1 + (Uc - Lc) - 1;
+        const IdxT pc = c == 1 ? pc1 : (c == 2 ? pc2 : (c == 3 ? pc3 : pc4));
+        lo0 = pc + Lc;
+        hi0 = pc + Uc - 1;
+        --i;
+        // an empty interval stays empty and emits nothing (see ov_find): stop stepping
+        live = i > 0 && hi0 != kNone && hi0 >= lo0;
+      }
+    }
+    // ---- containment handling (src/overlap_builder.cpp:877-905), again warp-uniform
+    const bool tail = have && hi0 != kNone && hi0 >= lo0;  // only reachable with i == 0: an emptied walk has hi0 < lo0
+    uint32_t ncontain = 0;
+    if (__any_sync(kFull, tail)) {
+      const QuadRank<IdxT> kp = quad_rank<IdxT>(Pb, tail ? lo0 : (IdxT)0, tail ? (IdxT)(hi0 + 1) : (IdxT)0, q);
+      const QuadRank<IdxT> ks = quad_rank<IdxT>(Sb, tail ? lo1 : (IdxT)0, tail ? (IdxT)(hi1 + 1) : (IdxT)0, q);
+      // any non-'$' extension on either side?  (ballot over the warp, then this quad's four bits)
+      const bool mydna = (kp.Uq - kp.Lq) > 0 || (ks.Uq - ks.Lq) > 0;
+      const bool dna = ((__ballot_sync(kFull, mydna) >> qbase) & 0xfu) != 0;
+      const IdxT d = kp.Ud - kp.Ld;
+      const IdxT p0lo = pc0 + kp.Ld;
+      IdxT p0hi = pc0 + kp.Ud - 1;
+      IdxT p1lo = lo1, p1hi = lo1 + d - 1;
+      const bool v0 = p0hi != kNone && p0hi >= p0lo, v1 = p1hi != kNone && p1hi >= p1lo;
+      const bool want = tail && !dna && v0 && v1;
+      const bool need3 = want && p1hi != hi1;
+      IdxT U3d = ks.Ud;
+      if (__any_sync(kFull, need3)) {
+        const QuadRank<IdxT> k3 = quad_rank<IdxT>(Sb, need3 ? lo1 : (IdxT)0, need3 ? (IdxT)(p1hi + 1) : (IdxT)0, q);
+        if (need3) {
+          U3d = k3.Ud;
+          nlook += 1;
+        }
+      }
+      if (tail) {
+        nlook += 4;
+        if (dna) {
+          if (q == 0) bt.substring[r] = 1;
+        } else if (want) {
           const IdxT d3 = U3d - ks.Ld;
           p0hi = p0lo + d3 - 1;
           p1lo = (IdxT)Spred[0] + ks.Ld;
@@ -213,7 +248,7 @@ ov_search_quad_kernel(FmPair fm, ReadsView reads, uint64_t first, uint64_t count
         }
       }
     }
-    if (q == 0) {
+    if (have && q == 0) {
       bt.ncand[wi * 4 + mode] = n < bt.find_cap ? n : bt.find_cap;
       bt.ncontain[wi * 4 + mode] = ncontain;
     }
