@@ -1,0 +1,449 @@
+// Device kernels of the BWT / read-index construction, shared by the single-device build (index.cu) and the
+// bucket-sharded multi-GPU build (index_sharded.cu).  See index.cu for the algorithm.
+#ifndef SGX_INDEX_KERNELS_CUH_
+#define SGX_INDEX_KERNELS_CUH_
+
+#include "index.cuh"
+#include "prims.cuh"
+
+namespace sgx {
+
+// ---- read access ------------------------------------------------------------------------------------------------
+
+struct ReadAcc {
+  ReadsView rv;
+  int reversed;
+  // 2-bit code (A0 C1 G2 T3) of column `col` of read `id` in the indexed orientation
+  __device__ __forceinline__ uint32_t code(uint32_t id, uint32_t col, uint32_t l) const {
+    const uint32_t j = reversed ? l - 1 - col : col;
+    const uint32_t* w = rv.words + rv.woff[id];
+    return (w[j >> 4] >> (2 * (j & 15))) & 3u;
+  }
+};
+
+// ---- 1. read ordering ---------------------------------------------------------------------------------------------
+
+static __global__ void iota_kernel(uint32_t* a, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = (uint32_t)i;
+}
+
+// Digit of a read for columns [col0, col0+ncols): base-5 number, leftmost column most significant, '$' (=0) past the
+// end of the read so that a read that is a proper prefix of another sorts first.
+struct ColDigit {
+  ReadAcc acc;
+  const uint32_t* ids;
+  uint32_t col0;
+  int ncols;
+  __device__ __forceinline__ int operator()(uint64_t k) const {
+    const uint32_t id = ids[k];
+    const uint32_t l = acc.rv.len[id];
+    int d = 0;
+    for (int q = 0; q < ncols; ++q) {
+      const uint32_t col = col0 + q;
+      const int s = col < l ? (int)acc.code(id, col, l) + 1 : 0;
+      d = d * 5 + s;
+    }
+    return d;
+  }
+};
+struct IdMove {
+  const uint32_t* in;
+  uint32_t* out;
+  __device__ __forceinline__ void operator()(uint64_t k, uint64_t dest) const { out[dest] = in[k]; }
+};
+
+// heads[k] = 1 when the k-th read in content order differs from its predecessor.
+static __global__ void read_heads_kernel(ReadsView rv, const uint32_t* __restrict__ ids, uint64_t n, uint64_t* __restrict__ heads) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  uint64_t h = 1;
+  if (k > 0) {
+    const uint32_t a = ids[k - 1], b = ids[k];
+    const uint32_t la = rv.len[a], lb = rv.len[b];
+    if (la == lb) {
+      const uint32_t* wa = rv.words + rv.woff[a];
+      const uint32_t* wb = rv.words + rv.woff[b];
+      const uint32_t nw = (la + 15) / 16;
+      bool eq = true;
+      for (uint32_t w = 0; w < nw && eq; ++w) eq = wa[w] == wb[w];
+      if (eq) h = 0;
+    }
+  }
+  heads[k] = h;
+}
+
+// rank[ids[k]] = (heads before k) + heads[k]  (dense, 1-based) given the exclusive scan of the head flags.
+static __global__ void assign_rank_kernel(const uint32_t* __restrict__ ids, const uint64_t* __restrict__ excl, uint64_t n,
+                                   uint64_t total, uint32_t* __restrict__ rank) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint64_t next = k + 1 < n ? excl[k + 1] : total;
+  rank[ids[k]] = (uint32_t)next;  // == excl[k] + heads[k]
+}
+
+static __global__ void doubling_keys_kernel(const uint32_t* __restrict__ rank, uint64_t n, uint64_t h, int bits,
+                                     uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t r2 = i + h < n ? rank[i + h] : 0;  // end of text is smallest
+  keys[i] = ((uint64_t)rank[i] << bits) | r2;
+  vals[i] = (uint32_t)i;
+}
+
+static __global__ void key_heads_kernel(const uint64_t* __restrict__ keys, uint64_t n, uint64_t* __restrict__ heads) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  heads[k] = (k == 0 || keys[k] != keys[k - 1]) ? 1 : 0;
+}
+
+// Sentinel order of model B from the read-start order `sai`: '$' of read i sorts by the suffix that follows it,
+// i.e. by the rank of read i+1; the last read's '$' (end of text) is smallest.
+static __global__ void find_zero_kernel(const uint32_t* __restrict__ sai, uint64_t n, uint64_t* __restrict__ k0) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n && sai[k] == 0) *k0 = k;
+}
+static __global__ void sentinel_order_kernel(const uint32_t* __restrict__ sai, uint64_t n, const uint64_t* __restrict__ k0p,
+                                      uint32_t* __restrict__ sord) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint64_t k0 = *k0p;
+  if (k == 0) sord[0] = (uint32_t)(n - 1);
+  if (k == k0) return;
+  sord[1 + k - (k > k0 ? 1 : 0)] = sai[k] - 1;
+}
+
+// ---- 2. column passes ---------------------------------------------------------------------------------------------
+
+static const int kBcrBlock = 256;    // rows per rank checkpoint
+static const int kMergeTile = 8192;  // output rows per merge CTA
+static const int kMergeThreads = 256;
+// The partial BWT is stored 4 bits per symbol (ranks 0..4), two rows per byte, row k in bits 4*(k&1) of byte k>>1.
+
+__device__ __forceinline__ uint32_t nib_get(const uint8_t* __restrict__ B, uint64_t k) {
+  return (B[k >> 1] >> (4 * (k & 1))) & 15u;
+}
+
+// One thread per byte (two rows) of the first BWT: the N sentinel rows in sentinel order; the symbol of a
+// sentinel row is the last base of its read.
+template <class PosT>
+__global__ void bcr_init_kernel(ReadAcc acc, const uint32_t* __restrict__ sord, uint64_t n, uint8_t* __restrict__ B,
+                                uint32_t* __restrict__ ID, PosT* __restrict__ NP) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t k = 2 * i;
+  if (k >= n) return;
+  uint32_t byte = 0;
+  for (int h = 0; h < 2; ++h) {
+    if (k + h < n) {
+      const uint32_t id = sord[k + h];
+      const uint32_t l = acc.rv.len[id];
+      byte |= (acc.code(id, l - 1, l) + 1) << (4 * h);
+      ID[k + h] = id;
+      NP[k + h] = (PosT)(k + h);
+    }
+  }
+  B[i] = (uint8_t)byte;
+}
+
+// A | C<<16 and G | T<<16 counts of the nibbles of a word (8 rows) selected by `keep` (a mask of nibble LSBs).
+__device__ __forceinline__ void nib_count_add(uint32_t w, uint32_t keep, uint32_t& accA, uint32_t& accC, uint32_t& accG,
+                                              uint32_t& accT) {
+  const uint32_t m1 = w & 0x11111111u & keep, m2 = (w >> 1) & 0x11111111u & keep, m4 = (w >> 2) & 0x11111111u & keep;
+  accT += m4;
+  accG += m1 & m2;
+  accA += m1 & ~m2;
+  accC += m2 & ~m1;
+}
+// sum of the eight 4-bit fields of an accumulator (each field <= 15)
+__device__ __forceinline__ uint32_t nib_sum(uint32_t acc) {
+  const uint32_t v = (acc & 0x0f0f0f0fu) + ((acc >> 4) & 0x0f0f0f0fu);
+  return (v * 0x01010101u) >> 24;
+}
+
+// Per-256-row counts of A,C,G,T of a nibble-packed symbol array: cnt[c*nb + b].  One warp per block, one word per lane.
+static __global__ void __launch_bounds__(256) sym_block_count_kernel(const uint8_t* __restrict__ B, uint64_t n, uint64_t nb,
+                                                              uint64_t* __restrict__ cnt) {
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= nb) return;
+  const uint64_t row0 = warp * kBcrBlock + (uint64_t)lane * 8;
+  uint32_t a = 0, c = 0, g = 0, t = 0;
+  if (row0 < n) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(B + row0 / 2);  // the array is padded
+    const uint64_t left = n - row0;
+    const uint32_t keep = left >= 8 ? 0x11111111u : (0x11111111u & ((1u << (4 * (uint32_t)left)) - 1u));
+    nib_count_add(w, keep, a, c, g, t);
+  }
+  uint32_t w1 = nib_sum(a) | (nib_sum(c) << 16), w2 = nib_sum(g) | (nib_sum(t) << 16);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    w1 += __shfl_xor_sync(0xffffffffu, w1, o);
+    w2 += __shfl_xor_sync(0xffffffffu, w2, o);
+  }
+  if (lane == 0) {
+    cnt[0 * nb + warp] = w1 & 0xffffu;
+    cnt[1 * nb + warp] = w1 >> 16;
+    cnt[2 * nb + warp] = w2 & 0xffffu;
+    cnt[3 * nb + warp] = w2 >> 16;
+  }
+}
+
+// number of nibbles equal to the pattern's nibble among the first `nn` (<= 8) nibbles of w
+__device__ __forceinline__ uint32_t nib_eq_count(uint32_t w, uint32_t pat, uint32_t nn) {
+  uint32_t x = w ^ pat;
+  x |= x >> 1;
+  x |= x >> 2;
+  const uint32_t eq = ~x & 0x11111111u;
+  const uint32_t m = nn >= 8 ? 0xffffffffu : ((1u << (4 * nn)) - 1u);
+  return (uint32_t)__popc(eq & m);
+}
+
+// For every active read (in current row order): the symbol c that starts its next suffix and the row that suffix
+// takes in the next BWT:  N + (#symbols < c in B) + (#c in B[0..P)).
+//   scanned = exclusive scan of the flattened [4][nb] block counts, so scanned[c*nb + b] already equals
+//   (#symbols < c in B) + (#c before block b).
+template <class PosT>
+__global__ void __launch_bounds__(256) bcr_rank_kernel(ReadAcc acc, const uint8_t* __restrict__ B, const uint64_t* __restrict__ scanned,
+                                                       uint64_t nb, uint64_t n_reads, const uint32_t* __restrict__ ID,
+                                                       const PosT* __restrict__ NP, uint64_t nact, uint32_t j,
+                                                       uint8_t* __restrict__ tmpC, PosT* __restrict__ tmpPos) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nact) return;
+  const uint32_t id = ID[k];
+  const uint32_t l = acc.rv.len[id];
+  if (l < j) {
+    tmpC[k] = 255;  // finished in the previous pass: dropped
+    return;
+  }
+  const uint32_t c = acc.code(id, l - j, l);
+  const uint64_t P = (uint64_t)NP[k];
+  const uint64_t b = P / kBcrBlock;
+  const uint32_t r = (uint32_t)(P - b * kBcrBlock);  // rows of this block before P
+  const uint32_t pat = (c + 1) * 0x11111111u;
+  uint32_t inblk = 0;
+  const uint4* v = reinterpret_cast<const uint4*>(B + b * (kBcrBlock / 2));  // 128 bytes per block
+  const uint32_t nvec = (r + 31) / 32;
+  for (uint32_t q = 0; q < nvec; ++q) {
+    const uint4 x = v[q];
+    const uint32_t left = r - q * 32;  // nibbles of this vector that count (may exceed 32)
+    inblk += nib_eq_count(x.x, pat, left);
+    if (left > 8) inblk += nib_eq_count(x.y, pat, left - 8);
+    if (left > 16) inblk += nib_eq_count(x.z, pat, left - 16);
+    if (left > 24) inblk += nib_eq_count(x.w, pat, left - 24);
+  }
+  tmpC[k] = (uint8_t)c;
+  tmpPos[k] = (PosT)(n_reads + scanned[(uint64_t)c * nb + b] + inblk);
+}
+
+struct BcrDigit {
+  const uint8_t* tmpC;
+  __device__ __forceinline__ int operator()(uint64_t k) const { return (int)tmpC[k]; }
+};
+template <class PosT>
+struct BcrMove {
+  ReadAcc acc;
+  const uint32_t* ID;
+  const PosT* tmpPos;
+  uint32_t j;
+  uint32_t* ID2;
+  PosT* NP2;
+  uint8_t* SYM2;
+  __device__ __forceinline__ void operator()(uint64_t k, uint64_t dest) const {
+    const uint32_t id = ID[k];
+    const uint32_t l = acc.rv.len[id];
+    ID2[dest] = id;
+    NP2[dest] = tmpPos[k];
+    SYM2[dest] = (l == j) ? (uint8_t)0 : (uint8_t)(acc.code(id, l - j - 1, l) + 1);
+  }
+};
+
+// tile_k0[t] = number of inserts with row < t*kMergeTile, for t in [0, ntiles] (ntiles+1 entries).
+template <class PosT>
+__global__ void bcr_tile_bounds_kernel(const PosT* __restrict__ NP, uint64_t nact, uint64_t ntiles,
+                                       uint64_t* __restrict__ tile_k0) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > nact) return;
+  // inserts k-1 and k straddle tile starts in (prev_tile, this_tile]
+  const uint64_t lo = k == 0 ? 0 : (uint64_t)NP[k - 1] / kMergeTile + 1;
+  const uint64_t hi = k == nact ? ntiles : (uint64_t)NP[k] / kMergeTile;
+  for (uint64_t t = lo; t <= hi && t <= ntiles; ++t) tile_k0[t] = k;
+}
+
+// Streaming merge of the old BWT (n_old rows) with the sorted inserts (rows NP[0..nact) of the NEW array, symbols
+// SYM) into Bn (n_new rows), plus the per-256-row symbol counts of Bn.  HBM-bound by design: a CTA produces 8192 rows
+// (4 KB), a thread 32 rows (one 16-byte store).  The old rows of the tile are staged in shared memory; a thread
+// first takes the 32 old nibbles that would land on its rows if it had no inserts (five shared-memory words and
+// four funnel shifts), then opens a 4-bit gap for each of its inserts (the bits of its word of the tile's insert
+// mask), which pushes the surplus old nibbles out at the top -- exactly the ones the next thread starts with.
+template <class PosT>
+__global__ void __launch_bounds__(kMergeThreads) bcr_merge_kernel(const uint8_t* __restrict__ Bo, uint64_t n_old,
+                                                                  const PosT* __restrict__ NP, const uint8_t* __restrict__ SYM,
+                                                                  uint64_t nact, const uint64_t* __restrict__ tile_k0,
+                                                                  uint8_t* __restrict__ Bn, uint64_t n_new, uint64_t nb,
+                                                                  uint64_t* __restrict__ cnt) {
+  __shared__ __align__(16) uint32_t oldw[kMergeTile / 8 + 16];
+  __shared__ uint32_t mask[kMergeTile / 32];
+  __shared__ uint64_t sh[9];
+  const uint64_t t0 = (uint64_t)blockIdx.x * kMergeTile;
+  const uint64_t t1 = min(t0 + (uint64_t)kMergeTile, n_new);
+  const uint64_t k0 = tile_k0[blockIdx.x], k1 = tile_k0[blockIdx.x + 1];
+  const uint64_t a0 = t0 - k0;  // first old row of this tile
+  const uint32_t nold = (uint32_t)((t1 - t0) - (k1 - k0));
+  mask[threadIdx.x] = 0;
+  // old rows -> shared, 16-byte vectors from the 32-row-aligned position at or below a0 (the arrays are padded)
+  const uint64_t a0al = a0 & ~(uint64_t)31;
+  const uint32_t shift = (uint32_t)(a0 - a0al);  // nibbles
+  const uint32_t nvec = (nold + shift + 31) / 32;
+  for (uint32_t q = threadIdx.x; q < nvec; q += kMergeThreads)
+    reinterpret_cast<uint4*>(oldw)[q] = *reinterpret_cast<const uint4*>(Bo + a0al / 2 + (uint64_t)q * 16);
+  __syncthreads();
+  for (uint64_t k = k0 + threadIdx.x; k < k1; k += kMergeThreads) {
+    const uint32_t r = (uint32_t)((uint64_t)NP[k] - t0);
+    atomicOr(&mask[r >> 5], 1u << (r & 31));
+  }
+  __syncthreads();
+  const uint32_t m = mask[threadIdx.x];
+  uint64_t total;
+  const uint32_t pre = (uint32_t)block_excl_scan((uint64_t)__popc(m), sh, total);  // inserts before my first row
+  // the 32 old nibbles starting at the one that lands on my first row
+  const uint32_t o = shift + threadIdx.x * 32 - pre;
+  const uint32_t wi = o >> 3, sft = 4 * (o & 7);
+  uint32_t out[4];
+  {
+    const uint32_t w0 = oldw[wi], w1 = oldw[wi + 1], w2 = oldw[wi + 2], w3 = oldw[wi + 3], w4 = oldw[wi + 4];
+    out[0] = __funnelshift_r(w0, w1, sft);
+    out[1] = __funnelshift_r(w1, w2, sft);
+    out[2] = __funnelshift_r(w2, w3, sft);
+    out[3] = __funnelshift_r(w3, w4, sft);
+  }
+  // open a gap for every insert, lowest row first
+  uint32_t mm = m;
+  uint64_t kk = k0 + pre;
+  while (mm) {
+    const uint32_t p = (uint32_t)__ffs(mm) - 1;
+    mm &= mm - 1;
+    const uint32_t s = SYM[kk++];
+    const uint32_t wq = p >> 3, bit = 4 * (p & 7);
+#pragma unroll
+    for (int i = 3; i >= 1; --i)
+      if ((uint32_t)i > wq) out[i] = (out[i] << 4) | (out[i - 1] >> 28);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if ((uint32_t)i == wq) {
+        const uint32_t lowm = (1u << bit) - 1u;
+        const uint32_t up = bit < 28 ? ((out[i] >> bit) << (bit + 4)) : 0u;
+        out[i] = (out[i] & lowm) | (s << bit) | up;
+      }
+    }
+  }
+  // rows past the end of the array stay zero
+  const uint64_t row0 = t0 + (uint64_t)threadIdx.x * 32;
+  uint32_t valid = row0 >= t1 ? 0u : (uint32_t)min((uint64_t)32, t1 - row0);
+  uint32_t accA = 0, accC = 0, accG = 0, accT = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t vw = valid >= 8u * (i + 1) ? 8u : (valid > 8u * i ? valid - 8u * i : 0u);
+    const uint32_t km = vw >= 8 ? 0xffffffffu : ((1u << (4 * vw)) - 1u);
+    out[i] &= km;
+    nib_count_add(out[i], 0x11111111u, accA, accC, accG, accT);
+  }
+  if (valid) *reinterpret_cast<uint4*>(Bn + row0 / 2) = make_uint4(out[0], out[1], out[2], out[3]);
+  // 256-row block = 8 consecutive threads
+  uint32_t w1 = nib_sum(accA) | (nib_sum(accC) << 16), w2 = nib_sum(accG) | (nib_sum(accT) << 16);
+#pragma unroll
+  for (int oo = 4; oo > 0; oo >>= 1) {
+    w1 += __shfl_xor_sync(0xffffffffu, w1, oo);
+    w2 += __shfl_xor_sync(0xffffffffu, w2, oo);
+  }
+  if ((threadIdx.x & 7) == 0) {
+    const uint64_t b = row0 / kBcrBlock;
+    if (b < nb) {
+      cnt[0 * nb + b] = w1 & 0xffffu;
+      cnt[1 * nb + b] = w1 >> 16;
+      cnt[2 * nb + b] = w2 & 0xffffu;
+      cnt[3 * nb + b] = w2 >> 16;
+    }
+  }
+}
+
+// ---- 3. run-length encoding ------------------------------------------------------------------------------------------
+
+struct HeadDigit {
+  const uint8_t* B;
+  __device__ __forceinline__ int operator()(uint64_t k) const {
+    return (k == 0 || nib_get(B, k) != nib_get(B, k - 1)) ? 0 : 1;
+  }
+};
+struct HeadOnlyMove {
+  uint64_t* heads;
+  uint64_t n_heads;
+  __device__ __forceinline__ void operator()(uint64_t k, uint64_t dest) const {
+    if (dest < n_heads) heads[dest] = k;  // bucket 1 (non-heads) lands at dest >= n_heads and is dropped
+  }
+};
+
+// Length of run r of a segment of n rows.  Seams of the bucket-sharded build: a run that continues from the previous
+// segment belongs to the segment where it starts, so a segment may skip its first run (skip_first) and its last run
+// may be longer than its local rows (extend_last = rows of the following segments that continue it).
+__device__ __forceinline__ uint64_t run_length(const uint64_t* __restrict__ heads, uint64_t r, uint64_t n_runs, uint64_t n,
+                                               int skip_first, uint64_t extend_last) {
+  if (r == 0 && skip_first) return 0;
+  uint64_t len = (r + 1 < n_runs ? heads[r + 1] : n) - heads[r];
+  if (r + 1 == n_runs) len += extend_last;
+  return len;
+}
+
+// bytes needed by run r: ceil(len / 31)   (src/bwt.cpp:16-27: a run is cut whenever its count reaches 31)
+static __global__ void run_bytes_kernel(const uint64_t* __restrict__ heads, uint64_t n_runs, uint64_t n, int skip_first,
+                                        uint64_t extend_last, uint64_t* __restrict__ nbytes) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_runs) return;
+  nbytes[r] = (run_length(heads, r, n_runs, n, skip_first, extend_last) + 30) / 31;
+}
+
+static __global__ void run_emit_kernel(const uint8_t* __restrict__ B, const uint64_t* __restrict__ heads,
+                                       const uint64_t* __restrict__ boff, uint64_t n_runs, uint64_t n, int skip_first,
+                                       uint64_t extend_last, uint8_t* __restrict__ rle) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_runs) return;
+  uint64_t len = run_length(heads, r, n_runs, n, skip_first, extend_last);
+  const uint8_t s = (uint8_t)(nib_get(B, heads[r]) << 5);
+  uint64_t o = boff[r];
+  while (len > 0) {
+    const uint32_t c = len >= 31 ? 31u : (uint32_t)len;
+    rle[o++] = s | (uint8_t)c;
+    len -= c;
+  }
+}
+
+// histogram of read lengths clipped to lmax: hist[l] += 1
+static __global__ void len_hist_kernel(const uint32_t* __restrict__ len, uint64_t n, uint32_t* __restrict__ hist) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicAdd(&hist[len[i]], 1u);
+}
+
+// ---- host helpers defined in index.cu, shared with index_sharded.cu ------------------------------------------------
+
+// Order of the read-start suffixes (d_sai, the .sai file) and of the N sentinel rows (d_sord) under ordering model
+// `order`; both arrays hold N read ids.
+void index_read_order(sgx_ctx* ctx, const sgx_reads* reads, const ReadAcc& acc, int order, uint32_t* d_sai, uint32_t* d_sord);
+// nact[j] = reads with length >= j (the inserts of column pass j), j in [1, max_len].
+std::vector<uint64_t> index_active_counts(sgx_ctx* ctx, const sgx_reads* reads);
+// bytes of a 4-bit symbol array of `rows` rows, padded so that whole-tile / whole-vector accesses stay in bounds
+inline uint64_t bwt_array_bytes(uint64_t rows) { return (((rows + kMergeTile - 1) / kMergeTile + 2) * kMergeTile) / 2 + 128; }
+
+// Run heads of a segment (rows [0, n) of the nibble array B) and what its neighbours need to know about its ends.
+struct RleSegment {
+  DevBuf<uint64_t> heads;  // n_runs start rows
+  uint64_t n_runs = 0, n_rows = 0;
+  uint32_t first_sym = 0, last_sym = 0;
+  uint64_t first_len = 0, last_len = 0;  // rows of the first / last run (equal to n_rows when the segment is one run)
+};
+void rle_heads(sgx_ctx* ctx, const uint8_t* B, uint64_t n, RleSegment* seg);
+// Greedy-31 run bytes of the segment (src/bwt.cpp:16-27); see run_length() for skip_first / extend_last.
+void rle_emit(sgx_ctx* ctx, const uint8_t* B, const RleSegment& seg, int skip_first, uint64_t extend_last,
+              DevBuf<uint8_t>* d_rle, uint64_t* n_bytes);
+
+}  // namespace sgx
+
+#endif  // SGX_INDEX_KERNELS_CUH_
