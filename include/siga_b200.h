@@ -102,6 +102,34 @@ typedef struct sgx_index_out {
 int sgx_index_build(sgx_ctx* ctx, const sgx_reads* reads, int order, int reversed, sgx_index_out* out);
 void sgx_index_out_free(sgx_index_out* out);
 
+/* ---- multi-GPU index construction ------------------------------------------------------------------------ */
+
+/*
+ * Shard communicator.  The reference has no counterpart (it is a single-node OpenMP program); this is the
+ * plumbing of BASELINE.json's multi-GPU index build.  Two transports:
+ *   sgx_comm_init        one process per GPU, NCCL underneath (libnccl.so.2 is resolved at run time).  Rank 0 calls
+ *                        sgx_comm_unique_id, the caller's launcher (torch.distributed, MPI, a file) carries the 128
+ *                        bytes to every rank, every rank calls sgx_comm_init with the ctx of its own GPU.
+ *   sgx_comm_init_local  `shards` virtual shards inside one context: same algorithm, device copies instead of NCCL
+ *                        (used to test the sharded build on one GPU).
+ */
+typedef struct sgx_comm sgx_comm;
+int sgx_comm_unique_id(uint8_t id[128]);
+int sgx_comm_init(sgx_ctx* ctx, const uint8_t id[128], int rank, int world, sgx_comm** out);
+int sgx_comm_init_local(sgx_ctx* ctx, int shards, sgx_comm** out);
+void sgx_comm_free(sgx_comm* comm);
+int sgx_comm_world(const sgx_comm* comm);
+int sgx_comm_rank(const sgx_comm* comm);
+
+/*
+ * sgx_index_build with the rows of the BWT sharded over the communicator by leading k-mer bucket: every pass the
+ * shards exchange their inserts (all-to-all), at the end the run bytes are concatenated in bucket order.  Collective:
+ * every rank calls it with the same (replicated) read set.  The result is byte-identical to sgx_index_build;
+ * `out->rle` is complete on rank 0 only (other ranks get n_runs and an empty buffer), `out->sai` on every rank.
+ */
+int sgx_index_build_sharded(sgx_ctx* ctx, sgx_comm* comm, const sgx_reads* reads, int order, int reversed,
+                            sgx_index_out* out);
+
 /* ---- FM-index (`FMIndex::load`, rank queries) ----------------------------------------------------------- */
 
 /*

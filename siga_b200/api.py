@@ -21,6 +21,8 @@ ABI_SYMBOLS = [
     "sgx_abi_version", "sgx_init", "sgx_shutdown", "sgx_last_error", "sgx_sm_count",
     "sgx_reads_pack", "sgx_reads_free", "sgx_reads_count", "sgx_reads_bases",
     "sgx_index_build", "sgx_index_out_free",
+    "sgx_comm_unique_id", "sgx_comm_init", "sgx_comm_init_local", "sgx_comm_free", "sgx_comm_world", "sgx_comm_rank",
+    "sgx_index_build_sharded",
     "sgx_fm_create", "sgx_fm_free", "sgx_fm_attach_reads", "sgx_fm_length", "sgx_fm_pred", "sgx_fm_occ", "sgx_fm_count",
     "sgx_overlap_batch", "sgx_overlap_host", "sgx_hits_free", "sgx_overlap_edges", "sgx_edges_free",
     "sgx_bench_gather", "sgx_flush_l2",
@@ -90,6 +92,14 @@ def load_library():
     lib.sgx_index_build.argtypes = [vp, vp, i32, i32, ctypes.POINTER(_IndexOut)]
     lib.sgx_index_out_free.argtypes = [ctypes.POINTER(_IndexOut)]
     lib.sgx_index_out_free.restype = None
+    lib.sgx_comm_unique_id.argtypes = [vp]
+    lib.sgx_comm_init.argtypes = [vp, vp, i32, i32, ctypes.POINTER(vp)]
+    lib.sgx_comm_init_local.argtypes = [vp, i32, ctypes.POINTER(vp)]
+    lib.sgx_comm_free.argtypes = [vp]
+    lib.sgx_comm_free.restype = None
+    lib.sgx_comm_world.argtypes = [vp]
+    lib.sgx_comm_rank.argtypes = [vp]
+    lib.sgx_index_build_sharded.argtypes = [vp, vp, vp, i32, i32, ctypes.POINTER(_IndexOut)]
     lib.sgx_fm_create.argtypes = [vp, vp, u64, u64, ctypes.POINTER(vp)]
     lib.sgx_fm_free.argtypes = [vp]
     lib.sgx_fm_free.restype = None
@@ -225,6 +235,44 @@ class Context:
         o = _IndexOut()
         self._check(self.lib.sgx_index_build(self.h, reads, int(order), 1 if reversed else 0, ctypes.byref(o)))
         res = IndexResult(o)
+        self.lib.sgx_index_out_free(ctypes.byref(o))
+        return res
+
+    # ---- multi-GPU index
+    def comm_unique_id(self):
+        """128-byte NCCL unique id (rank 0 creates it; the launcher carries it to the other ranks)."""
+        buf = np.zeros(128, dtype=np.uint8)
+        rc = self.lib.sgx_comm_unique_id(_ptr(buf))
+        if rc != 0:
+            raise SgxError(rc, self.lib.sgx_last_error(None).decode())
+        return buf
+
+    def comm_init(self, unique_id, rank, world):
+        uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
+        assert uid.size == 128
+        c = ctypes.c_void_p()
+        self._check(self.lib.sgx_comm_init(self.h, _ptr(uid), int(rank), int(world), ctypes.byref(c)))
+        return c
+
+    def comm_init_local(self, shards):
+        """`shards` virtual shards on this context (device copies instead of NCCL)."""
+        c = ctypes.c_void_p()
+        self._check(self.lib.sgx_comm_init_local(self.h, int(shards), ctypes.byref(c)))
+        return c
+
+    def free_comm(self, c):
+        self.lib.sgx_comm_free(c)
+
+    def index_build_sharded(self, comm, reads, order=ORDER_SAIS2, reversed=False):
+        """Collective bucket-sharded build; `runs` is complete on rank 0 only, `sai` everywhere."""
+        o = _IndexOut()
+        self._check(self.lib.sgx_index_build_sharded(self.h, comm, reads, int(order), 1 if reversed else 0, ctypes.byref(o)))
+        rank = int(self.lib.sgx_comm_rank(comm))
+        n_runs = int(o.n_runs)
+        if rank != 0:
+            o.n_runs = 0
+        res = IndexResult(o)
+        res.n_runs_total = n_runs
         self.lib.sgx_index_out_free(ctypes.byref(o))
         return res
 

@@ -245,6 +245,46 @@ int sgx_index_build(sgx_ctx* ctx, const sgx_reads* reads, int order, int reverse
   SGX_ENTRY_END(ctx)
 }
 
+int sgx_comm_unique_id(uint8_t id[128]) {
+  if (!id) return SGX_EINVAL;
+  sgx_ctx* none = nullptr;
+  SGX_ENTRY_BEGIN(none)
+  comm_unique_id(id);
+  SGX_ENTRY_END(none)
+}
+
+int sgx_comm_init(sgx_ctx* ctx, const uint8_t id[128], int rank, int world, sgx_comm** out) {
+  if (!ctx || !id || !out) return SGX_EINVAL;
+  SGX_ENTRY_BEGIN(ctx)
+  *out = comm_create_nccl(ctx, id, rank, world);
+  SGX_ENTRY_END(ctx)
+}
+
+int sgx_comm_init_local(sgx_ctx* ctx, int shards, sgx_comm** out) {
+  if (!ctx || !out) return SGX_EINVAL;
+  SGX_ENTRY_BEGIN(ctx)
+  *out = comm_create_local(ctx, shards);
+  SGX_ENTRY_END(ctx)
+}
+
+void sgx_comm_free(sgx_comm* comm) {
+  if (!comm) return;
+  cudaSetDevice(comm->ctx->device);
+  comm_destroy(comm);
+}
+
+int sgx_comm_world(const sgx_comm* comm) { return comm ? comm->world : 0; }
+int sgx_comm_rank(const sgx_comm* comm) { return comm ? comm->rank : -1; }
+
+int sgx_index_build_sharded(sgx_ctx* ctx, sgx_comm* comm, const sgx_reads* reads, int order, int reversed,
+                            sgx_index_out* out) {
+  if (!ctx || !comm || !reads || !out || comm->ctx != ctx) return SGX_EINVAL;
+  SGX_ENTRY_BEGIN(ctx)
+  SGX_REQUIRE(order == SGX_ORDER_SAIS || order == SGX_ORDER_SAIS2, SGX_EINVAL, "sgx_index_build_sharded: unknown order");
+  index_build_sharded(ctx, comm, reads, order, reversed != 0, out);
+  SGX_ENTRY_END(ctx)
+}
+
 void sgx_index_out_free(sgx_index_out* out) {
   if (!out) return;
   pinned_put(out->rle);

@@ -1,0 +1,212 @@
+// Shard communicator: NCCL (one process per GPU) or local (virtual shards on one context).  See comm.cuh.
+#include "comm.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <mutex>
+
+namespace sgx {
+
+// ---- NCCL, resolved at run time -------------------------------------------------------------------------------------
+
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*GetVersion)(int*) = nullptr;
+};
+
+static NcclApi g_nccl;
+static std::mutex g_nccl_mutex;
+
+static NcclApi& nccl_api() {
+  std::lock_guard<std::mutex> lk(g_nccl_mutex);
+  if (g_nccl.handle) return g_nccl;
+  // RTLD_NOLOAD first: reuse the NCCL the host process already brought (torch bundles its own libnccl.so.2)
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) throw Error{SGX_ENODEV, std::string("NCCL is not available: ") + (dlerror() ? dlerror() : "dlopen failed")};
+#define SGX_NCCL_SYM(field, name)                                                         \
+  *(void**)(&g_nccl.field) = dlsym(h, name);                                              \
+  if (!g_nccl.field) throw Error{SGX_ENODEV, std::string("NCCL symbol missing: ") + name};
+  SGX_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+  SGX_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+  SGX_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+  SGX_NCCL_SYM(AllGather, "ncclAllGather")
+  SGX_NCCL_SYM(AllReduce, "ncclAllReduce")
+  SGX_NCCL_SYM(Send, "ncclSend")
+  SGX_NCCL_SYM(Recv, "ncclRecv")
+  SGX_NCCL_SYM(GroupStart, "ncclGroupStart")
+  SGX_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+  SGX_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+  SGX_NCCL_SYM(GetVersion, "ncclGetVersion")
+#undef SGX_NCCL_SYM
+  g_nccl.handle = h;
+  return g_nccl;
+}
+
+#define SGX_NCCL(expr)                                                                                      \
+  do {                                                                                                      \
+    ncclResult_t _r = (expr);                                                                               \
+    if (_r != ncclSuccess) {                                                                                \
+      char _b[512];                                                                                         \
+      snprintf(_b, sizeof(_b), "%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, nccl_api().GetErrorString(_r)); \
+      throw sgx::Error{SGX_ECUDA, _b};                                                                      \
+    }                                                                                                       \
+  } while (0)
+
+void comm_unique_id(uint8_t id[128]) {
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId u;
+  SGX_NCCL(nccl_api().GetUniqueId(&u));
+  memcpy(id, &u, 128);
+}
+
+sgx_comm* comm_create_nccl(sgx_ctx* ctx, const uint8_t id[128], int rank, int world) {
+  SGX_REQUIRE(world >= 1 && world <= kMaxShards && rank >= 0 && rank < world, SGX_EINVAL, "sgx_comm_init: bad rank/world");
+  ncclUniqueId u;
+  memcpy(&u, id, 128);
+  ncclComm_t c = nullptr;
+  SGX_NCCL(nccl_api().CommInitRank(&c, world, u, rank));
+  sgx_comm* cm = new sgx_comm();
+  cm->ctx = ctx;
+  cm->world = world;
+  cm->rank = rank;
+  cm->local = false;
+  cm->nccl = c;
+  return cm;
+}
+
+sgx_comm* comm_create_local(sgx_ctx* ctx, int shards) {
+  SGX_REQUIRE(shards >= 1 && shards <= kMaxShards, SGX_EINVAL, "sgx_comm_init_local: 1..16 shards");
+  sgx_comm* cm = new sgx_comm();
+  cm->ctx = ctx;
+  cm->world = shards;
+  cm->rank = 0;
+  cm->local = true;
+  cm->nccl = nullptr;
+  return cm;
+}
+
+void comm_destroy(sgx_comm* cm) {
+  if (!cm) return;
+  if (cm->nccl) {
+    cudaStreamSynchronize(cm->ctx->stream);
+    nccl_api().CommDestroy((ncclComm_t)cm->nccl);
+  }
+  delete cm;
+}
+
+// ---- primitives --------------------------------------------------------------------------------------------------------
+
+void comm_allgather_u64(sgx_comm* cm, const uint64_t* const* dev_vals, uint64_t n, uint64_t* out) {
+  cudaStream_t st = cm->ctx->stream;
+  if (cm->local) {
+    for (int s = 0; s < cm->world; ++s)
+      SGX_CUDA(cudaMemcpyAsync(out + (uint64_t)s * n, dev_vals[s], n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    SGX_CUDA(cudaStreamSynchronize(st));
+    return;
+  }
+  DevBuf<uint64_t> all((uint64_t)cm->world * n);
+  SGX_NCCL(nccl_api().AllGather(dev_vals[0], all.p, n, ncclUint64, (ncclComm_t)cm->nccl, st));
+  SGX_CUDA(cudaMemcpyAsync(out, all.p, (uint64_t)cm->world * n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  SGX_CUDA(cudaStreamSynchronize(st));
+}
+
+static __global__ void add_u64_kernel(uint64_t* __restrict__ acc, const uint64_t* __restrict__ x, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) acc[i] += x[i];
+}
+
+void comm_allreduce_sum_u64(sgx_comm* cm, uint64_t* const* dev_vals, uint64_t n) {
+  cudaStream_t st = cm->ctx->stream;
+  if (cm->local) {
+    for (int s = 1; s < cm->world; ++s) SGX_LAUNCH(cm->ctx, add_u64_kernel, grid_for(n, 256), 256, 0, dev_vals[0], (const uint64_t*)dev_vals[s], n);
+    for (int s = 1; s < cm->world; ++s)
+      SGX_CUDA(cudaMemcpyAsync(dev_vals[s], dev_vals[0], n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+    return;
+  }
+  SGX_NCCL(nccl_api().AllReduce(dev_vals[0], dev_vals[0], n, ncclUint64, ncclSum, (ncclComm_t)cm->nccl, st));
+}
+
+void comm_alltoallv(sgx_comm* cm, const void* const* send, void* const* recv, size_t elem_bytes, const uint64_t* cnt,
+                    const uint64_t* send_off, const uint64_t* recv_off) {
+  cudaStream_t st = cm->ctx->stream;
+  const int W = cm->world;
+  if (cm->local) {
+    for (int s = 0; s < W; ++s)
+      for (int d = 0; d < W; ++d) {
+        const uint64_t c = cnt[s * W + d];
+        if (!c) continue;
+        SGX_CUDA(cudaMemcpyAsync((uint8_t*)recv[d] + recv_off[d * W + s] * elem_bytes,
+                                 (const uint8_t*)send[s] + send_off[s * W + d] * elem_bytes, c * elem_bytes,
+                                 cudaMemcpyDeviceToDevice, st));
+      }
+    return;
+  }
+  const int me = cm->rank;
+  NcclApi& api = nccl_api();
+  // own block: plain copy; the rest as one grouped send/recv set
+  if (cnt[me * W + me])
+    SGX_CUDA(cudaMemcpyAsync((uint8_t*)recv[0] + recv_off[me * W + me] * elem_bytes,
+                             (const uint8_t*)send[0] + send_off[me * W + me] * elem_bytes, cnt[me * W + me] * elem_bytes,
+                             cudaMemcpyDeviceToDevice, st));
+  SGX_NCCL(api.GroupStart());
+  for (int p = 0; p < W; ++p) {
+    if (p == me) continue;
+    const uint64_t cs = cnt[me * W + p], cr = cnt[p * W + me];
+    if (cs)
+      SGX_NCCL(api.Send((const uint8_t*)send[0] + send_off[me * W + p] * elem_bytes, cs * elem_bytes, ncclUint8, p,
+                        (ncclComm_t)cm->nccl, st));
+    if (cr)
+      SGX_NCCL(api.Recv((uint8_t*)recv[0] + recv_off[me * W + p] * elem_bytes, cr * elem_bytes, ncclUint8, p,
+                        (ncclComm_t)cm->nccl, st));
+  }
+  SGX_NCCL(api.GroupEnd());
+}
+
+void comm_gatherv_bytes(sgx_comm* cm, const uint8_t* const* send, const uint64_t* bytes, int root, uint8_t* root_recv) {
+  cudaStream_t st = cm->ctx->stream;
+  const int W = cm->world;
+  std::vector<uint64_t> off(W + 1, 0);
+  for (int s = 0; s < W; ++s) off[s + 1] = off[s] + bytes[s];
+  if (cm->local) {
+    for (int s = 0; s < W; ++s)
+      if (bytes[s]) SGX_CUDA(cudaMemcpyAsync(root_recv + off[s], send[s], bytes[s], cudaMemcpyDeviceToDevice, st));
+    return;
+  }
+  NcclApi& api = nccl_api();
+  const int me = cm->rank;
+  if (me == root) {
+    if (bytes[me]) SGX_CUDA(cudaMemcpyAsync(root_recv + off[me], send[0], bytes[me], cudaMemcpyDeviceToDevice, st));
+    SGX_NCCL(api.GroupStart());
+    for (int s = 0; s < W; ++s)
+      if (s != me && bytes[s]) SGX_NCCL(api.Recv(root_recv + off[s], bytes[s], ncclUint8, s, (ncclComm_t)cm->nccl, st));
+    SGX_NCCL(api.GroupEnd());
+  } else if (bytes[me]) {
+    SGX_NCCL(api.Send(send[0], bytes[me], ncclUint8, root, (ncclComm_t)cm->nccl, st));
+  }
+}
+
+void comm_barrier(sgx_comm* cm) {
+  if (cm->local) {
+    SGX_CUDA(cudaStreamSynchronize(cm->ctx->stream));
+    return;
+  }
+  DevBuf<uint64_t> x(1);
+  SGX_CUDA(cudaMemsetAsync(x.p, 0, sizeof(uint64_t), cm->ctx->stream));
+  SGX_NCCL(nccl_api().AllReduce(x.p, x.p, 1, ncclUint64, ncclSum, (ncclComm_t)cm->nccl, cm->ctx->stream));
+  SGX_CUDA(cudaStreamSynchronize(cm->ctx->stream));
+}
+
+}  // namespace sgx

@@ -1,0 +1,57 @@
+// Shard communicator of the multi-GPU paths (include/siga_b200.h: sgx_comm).
+//
+// Two transports behind the same four primitives:
+//   * NCCL  -- one process per GPU (torch.distributed / mpirun style launch); the unique id travels through the
+//              caller's own rendezvous (sgx_comm_unique_id on rank 0 -> broadcast -> sgx_comm_init everywhere).
+//              libnccl.so.2 is resolved with dlopen at first use, so the library itself has no link-time NCCL
+//              dependency and picks up the NCCL already loaded by the host process (e.g. torch's).
+//   * local -- `world` virtual shards inside ONE context (one device, one stream).  The sharded algorithms run
+//              unchanged, with device-to-device copies where NCCL would send; this is how the bucket-sharded index
+//              build is parity-tested on a single GPU.
+// A process drives `n_local` shards: `world` of them in local mode, exactly one (its rank) in NCCL mode.
+#ifndef SGX_COMM_CUH_
+#define SGX_COMM_CUH_
+
+#include "sgx_device.cuh"
+
+struct sgx_comm {
+  sgx_ctx* ctx;
+  int world;    // number of shards
+  int rank;     // NCCL mode: this process's shard; local mode: 0
+  bool local;   // true: all shards live in this process
+  void* nccl;   // ncclComm_t
+  int n_local() const { return local ? world : 1; }
+  int shard_of(int li) const { return local ? li : rank; }  // global shard index of local shard li
+};
+
+namespace sgx {
+
+static const int kMaxShards = 16;
+
+void comm_unique_id(uint8_t id[128]);
+sgx_comm* comm_create_nccl(sgx_ctx* ctx, const uint8_t id[128], int rank, int world);
+sgx_comm* comm_create_local(sgx_ctx* ctx, int shards);
+void comm_destroy(sgx_comm* cm);
+
+// out[(s * n) + i] = value i of shard s, for all `world` shards, on the HOST of every process.  `dev_vals[li]` is a
+// device array of n uint64 values of local shard li.  Synchronises the stream.
+void comm_allgather_u64(sgx_comm* cm, const uint64_t* const* dev_vals, uint64_t n, uint64_t* out);
+
+// Element-wise sum over shards of an n-element uint64 device array (in place, every local shard gets the sum).
+void comm_allreduce_sum_u64(sgx_comm* cm, uint64_t* const* dev_vals, uint64_t n);
+
+// Personalised all-to-all of `elem_bytes`-sized items: local shard li sends items [send_off[s][d], send_off[s][d] +
+// cnt[s][d]) of send[li] to shard d, which stores them at item recv_off[d][s] of its recv buffer (s = shard_of(li)).
+// cnt / send_off / recv_off are world x world host matrices (row-major) known to every process.
+void comm_alltoallv(sgx_comm* cm, const void* const* send, void* const* recv, size_t elem_bytes, const uint64_t* cnt,
+                    const uint64_t* send_off, const uint64_t* recv_off);
+
+// Concatenation of byte segments on shard `root`: shard s's `bytes[s]` bytes land at offset sum(bytes[0..s)) of
+// `root_recv` (a device buffer of the local shard that is `root`; ignored elsewhere).
+void comm_gatherv_bytes(sgx_comm* cm, const uint8_t* const* send, const uint64_t* bytes, int root, uint8_t* root_recv);
+
+void comm_barrier(sgx_comm* cm);
+
+}  // namespace sgx
+
+#endif  // SGX_COMM_CUH_

@@ -416,10 +416,15 @@ static __global__ void run_emit_kernel(const uint8_t* __restrict__ B, const uint
   }
 }
 
-// histogram of read lengths clipped to lmax: hist[l] += 1
+// histogram of read lengths: hist[l] += 1  (one atomic per distinct length per warp: read sets are mostly one length)
 static __global__ void len_hist_kernel(const uint32_t* __restrict__ len, uint64_t n, uint32_t* __restrict__ hist) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) atomicAdd(&hist[len[i]], 1u);
+  const bool have = i < n;
+  const unsigned act = __ballot_sync(0xffffffffu, have);
+  if (!have) return;
+  const uint32_t l = len[i];
+  const unsigned m = __match_any_sync(act, l);
+  if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&hist[l], (uint32_t)__popc(m));
 }
 
 // ---- host helpers defined in index.cu, shared with index_sharded.cu ------------------------------------------------

@@ -1,0 +1,589 @@
+// Bucket-sharded BWT / read-index construction across several GPUs (sgx_index_build_sharded).
+//
+// Same column-insertion algorithm as index.cu, with the ROWS of the BWT partitioned by the leading k-mer of their
+// suffix (BASELINE.json north_star: "suffixes are partitioned by leading k-mer bucket, exchanged with NCCL
+// all-to-all over NVLink, and concatenated into the global BWT"):
+//
+//   * Bucket key of a suffix = its first 8 symbols as a base-5 number ('$' = 0 ends the key).  Keys are contiguous
+//     in suffix order, so a shard owning the key range [bound[g], bound[g+1]) owns a contiguous row range of every
+//     partial BWT.  The bounds come from a k-mer histogram of a read sample (each shard counts its slice, NCCL
+//     all-reduce); they only balance the load -- any bounds give the same BWT.  Exact final rows per shard are
+//     counted the same way (slice + all-reduce) to size the arrays.
+//   * Reads, the read-start order (.sai) and the sentinel order are replicated (N items; the heavy part is S rows).
+//   * Column pass j: every shard LF-maps the suffixes it inserted in pass j-1 through ITS rows (local rank of the
+//     preceding base c), finds the owner of the new suffix from its key, and partitions (id, local rank part) by
+//     destination shard.  One small all-gather carries the send counts and each shard's A/C/G/T totals; one
+//     all-to-all carries the inserts.  The receiver turns the sender-local rank part into its own local row with a
+//     per-(sender, symbol) constant
+//         row = part + N + sum_{c'<c} T[c'] + sum_{s'<s} tot[s'][c] - sum_{c'<c} tot[s][c'] - first_row_of(receiver)
+//     and a stable 4-way partition by c of the sender-major receive buffer puts the inserts in row order (for one c
+//     the new row grows with the old global row, i.e. with (sender, sender row)).  Then the same streaming merge.
+//   * Run-length encoding per shard; a run crossing a seam belongs to the shard where it starts (run_length() in
+//     index_kernels.cuh), the segments are concatenated on shard 0.
+//
+// The transport is sgx_comm: NCCL between processes, or device copies between virtual shards of one context
+// (the mode the single-GPU parity tests run).
+#include <algorithm>
+
+#include "comm.cuh"
+#include "index_kernels.cuh"
+
+namespace sgx {
+
+static const int kKeySyms = 8;
+static const uint32_t kKeySpace = 390625;  // 5^8
+static const uint32_t kKeyTop = 78125;     // 5^7
+static const int kMetaN = kMaxShards + 4;  // per-shard values gathered every pass: send counts + A/C/G/T totals
+
+struct ShardBounds {
+  uint32_t b[kMaxShards + 1];
+  int world;
+  // bounds are non-decreasing; equal neighbours make empty shards, which then own nothing
+  __device__ __forceinline__ int owner(uint32_t key) const {
+    int g = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxShards; ++i) g += (i < world && key >= b[i]) ? 1 : 0;
+    return g;
+  }
+};
+
+__device__ __forceinline__ uint32_t suffix_key(const ReadAcc& acc, uint32_t id, uint32_t col, uint32_t l) {
+  uint32_t key = 0;
+#pragma unroll
+  for (int t = 0; t < kKeySyms; ++t) {
+    const uint32_t c = col + t;
+    key = key * 5u + (c < l ? acc.code(id, c, l) + 1u : 0u);
+  }
+  return key;
+}
+
+// hist[key] += 1 for every suffix (all l+1 of them, the bare '$' included) of the sampled reads
+// first, first + step, ... ; the key is rolled from the end of the read.
+static __global__ void __launch_bounds__(256) key_hist_kernel(ReadAcc acc, uint64_t n, uint64_t first, uint64_t step,
+                                                              unsigned long long* __restrict__ hist) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t id64 = first + t * step;
+  if (id64 >= n) return;
+  const uint32_t id = (uint32_t)id64;
+  const uint32_t l = acc.rv.len[id];
+  uint32_t key = 0;
+  atomicAdd(&hist[0], 1ull);
+  for (uint32_t col = l; col-- > 0;) {
+    key = (acc.code(id, col, l) + 1u) * kKeyTop + key / 5u;
+    atomicAdd(&hist[key], 1ull);
+  }
+}
+
+// rows[g] += number of suffixes of reads [r0, r1) owned by shard g
+static __global__ void __launch_bounds__(256) shard_rows_kernel(ReadAcc acc, uint64_t r0, uint64_t r1, ShardBounds bounds,
+                                                                unsigned long long* __restrict__ rows) {
+  const uint64_t id64 = r0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t cnt[kMaxShards];
+#pragma unroll
+  for (int g = 0; g < kMaxShards; ++g) cnt[g] = 0;
+  if (id64 < r1) {
+    const uint32_t id = (uint32_t)id64;
+    const uint32_t l = acc.rv.len[id];
+    uint32_t key = 0;
+    cnt[0] = 1;  // the '$' suffix
+    for (uint32_t col = l; col-- > 0;) {
+      key = (acc.code(id, col, l) + 1u) * kKeyTop + key / 5u;
+      const int o = bounds.owner(key);
+#pragma unroll
+      for (int g = 0; g < kMaxShards; ++g) cnt[g] += (o == g) ? 1u : 0u;
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < kMaxShards; ++g) {
+    uint32_t v = cnt[g];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&rows[g], (unsigned long long)v);
+  }
+}
+
+// Column pass, sender side: for every suffix inserted here by the previous pass, the destination shard of the suffix
+// one base longer and the sender-local part of its row: (#symbols < c in my rows) + (#c in my rows before mine).
+template <class PosT>
+__global__ void __launch_bounds__(256) shard_rank_kernel(ReadAcc acc, const uint8_t* __restrict__ B,
+                                                         const uint64_t* __restrict__ scanned, uint64_t nb, ShardBounds bounds,
+                                                         const uint32_t* __restrict__ ID, const PosT* __restrict__ NP,
+                                                         uint64_t held, uint32_t j, uint8_t* __restrict__ tmpDest,
+                                                         PosT* __restrict__ tmpPos) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= held) return;
+  const uint32_t id = ID[k];
+  const uint32_t l = acc.rv.len[id];
+  if (l < j) {
+    tmpDest[k] = 255;  // the read ended in the previous pass
+    return;
+  }
+  const uint32_t c = acc.code(id, l - j, l);
+  const uint64_t P = (uint64_t)NP[k];
+  const uint64_t b = P / kBcrBlock;
+  const uint32_t r = (uint32_t)(P - b * kBcrBlock);
+  const uint32_t pat = (c + 1) * 0x11111111u;
+  uint32_t inblk = 0;
+  const uint4* v = reinterpret_cast<const uint4*>(B + b * (kBcrBlock / 2));
+  const uint32_t nvec = (r + 31) / 32;
+  for (uint32_t q = 0; q < nvec; ++q) {
+    const uint4 x = v[q];
+    const uint32_t left = r - q * 32;
+    inblk += nib_eq_count(x.x, pat, left);
+    if (left > 8) inblk += nib_eq_count(x.y, pat, left - 8);
+    if (left > 16) inblk += nib_eq_count(x.z, pat, left - 16);
+    if (left > 24) inblk += nib_eq_count(x.w, pat, left - 24);
+  }
+  tmpDest[k] = (uint8_t)bounds.owner(suffix_key(acc, id, l - j, l));
+  tmpPos[k] = (PosT)(scanned[(uint64_t)c * nb + b] + inblk);
+}
+
+struct DestDigit {
+  const uint8_t* tmpDest;
+  __device__ __forceinline__ int operator()(uint64_t k) const { return (int)tmpDest[k]; }  // 255 -> dropped
+};
+template <class PosT>
+struct SendMove {
+  const uint32_t* ID;
+  const PosT* tmpPos;
+  uint32_t* sendID;
+  PosT* sendPos;
+  __device__ __forceinline__ void operator()(uint64_t k, uint64_t dest) const {
+    sendID[dest] = ID[k];
+    sendPos[dest] = tmpPos[k];
+  }
+};
+
+// meta[d] = items for shard d (d < kMaxShards), meta[kMaxShards + c] = number of symbol c in my rows.
+//   bucket_start: the partition workspace after its scan (bucket d starts at bucket_start[d * ntiles]); total = items kept.
+static __global__ void shard_meta_kernel(const uint64_t* __restrict__ bucket_start, uint32_t ntiles, int have_items,
+                                         const uint64_t* __restrict__ kept, const uint64_t* __restrict__ scanned, uint64_t nb,
+                                         const uint64_t* __restrict__ sym_total, uint64_t* __restrict__ meta) {
+  const int t = threadIdx.x;
+  if (t < kMaxShards) {
+    uint64_t c = 0;
+    if (have_items) {
+      const uint64_t a = bucket_start[(uint64_t)t * ntiles];
+      const uint64_t e = t + 1 < kMaxShards ? bucket_start[(uint64_t)(t + 1) * ntiles] : *kept;
+      c = e - a;
+    }
+    meta[t] = c;
+  } else if (t < kMaxShards + 4) {
+    const int c = t - kMaxShards;
+    const uint64_t e = c < 3 ? scanned[(uint64_t)(c + 1) * nb] : *sym_total;
+    meta[t] = e - scanned[(uint64_t)c * nb];
+  }
+}
+
+// Receiver side: per-(sender, symbol) constants that turn the sender-local rank part into a local row.
+struct RecvFix {
+  long long K[kMaxShards][4];
+  uint64_t roff[kMaxShards + 1];  // first item of each sender in the receive buffer
+  int world;
+};
+struct RecvDigit {
+  ReadAcc acc;
+  const uint32_t* recvID;
+  uint32_t j;
+  __device__ __forceinline__ int operator()(uint64_t k) const {
+    const uint32_t id = recvID[k];
+    const uint32_t l = acc.rv.len[id];
+    return (int)acc.code(id, l - j, l);
+  }
+};
+template <class PosT>
+struct RecvMove {
+  ReadAcc acc;
+  const uint32_t* recvID;
+  const PosT* recvPos;
+  uint32_t j;
+  RecvFix fix;
+  uint32_t* ID2;
+  PosT* NP2;
+  uint8_t* SYM2;
+  __device__ __forceinline__ void operator()(uint64_t k, uint64_t dest) const {
+    const uint32_t id = recvID[k];
+    const uint32_t l = acc.rv.len[id];
+    const uint32_t c = acc.code(id, l - j, l);
+    int s = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxShards; ++i) s += (i < fix.world && k >= fix.roff[i]) ? 1 : 0;
+    ID2[dest] = id;
+    NP2[dest] = (PosT)((long long)recvPos[k] + fix.K[s][c]);
+    SYM2[dest] = (l == j) ? (uint8_t)0 : (uint8_t)(acc.code(id, l - j - 1, l) + 1);
+  }
+};
+
+template <class PosT>
+struct Shard {
+  int g = 0;
+  uint64_t rows_final = 0;
+  DevBuf<uint8_t> B0, B1, SYM, tmpDest;
+  DevBuf<uint32_t> ID0, ID1, sendID, recvID;
+  DevBuf<PosT> NP0, NP1, tmpPos, sendPos, recvPos;
+  DevBuf<uint64_t> cnt, scan_ws, part_ws, tile_k0, meta, kept, sym_total;
+  uint8_t* B = nullptr;
+  uint8_t* Bn = nullptr;
+  uint32_t* ID = nullptr;
+  uint32_t* ID2 = nullptr;
+  PosT* NP = nullptr;
+  PosT* NP2 = nullptr;
+  uint64_t n_cur = 0, nb = 1, held = 0;
+  RleSegment seg;
+  DevBuf<uint8_t> rle;
+  uint64_t rle_bytes = 0;
+
+  void alloc(sgx_ctx* ctx, uint64_t N) {
+    const uint64_t padded = bwt_array_bytes(rows_final);
+    B0.alloc(padded);
+    B1.alloc(padded);
+    SGX_CUDA(cudaMemsetAsync(B0.p, 0, padded, ctx->stream));
+    SGX_CUDA(cudaMemsetAsync(B1.p, 0, padded, ctx->stream));
+    SYM.alloc(N);
+    tmpDest.alloc(N);
+    ID0.alloc(N);
+    ID1.alloc(N);
+    sendID.alloc(N);
+    recvID.alloc(N);
+    NP0.alloc(N);
+    NP1.alloc(N);
+    tmpPos.alloc(N);
+    sendPos.alloc(N);
+    recvPos.alloc(N);
+    const uint64_t nb_max = rows_final / kBcrBlock + 2;
+    cnt.alloc(4 * nb_max);
+    scan_ws.alloc(scan_ws_elems(4 * nb_max));
+    part_ws.alloc(std::max(part_ws_elems(N, kMaxShards), part_ws_elems(N, 4)));
+    tile_k0.alloc(rows_final / kMergeTile + 4);
+    meta.alloc(kMetaN);
+    kept.alloc(1);
+    sym_total.alloc(1);
+    B = B0.p;
+    Bn = B1.p;
+    ID = ID0.p;
+    ID2 = ID1.p;
+    NP = NP0.p;
+    NP2 = NP1.p;
+  }
+};
+
+template <class PosT>
+static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, const ReadAcc& acc, const uint32_t* d_sord,
+                          const ShardBounds& bounds, const std::vector<uint64_t>& rows_final, sgx_index_out* out,
+                          KernelClock& k_merge, EventTimer& t_bcr, EventTimer& t_emit, uint8_t** rle_host, uint64_t* rle_total) {
+  const uint64_t N = reads->n;
+  const uint32_t lmax = reads->max_len;
+  const int W = cm->world;
+  const int nl = cm->n_local();
+  std::vector<Shard<PosT> > sh(nl);
+  for (int li = 0; li < nl; ++li) {
+    sh[li].g = cm->shard_of(li);
+    sh[li].rows_final = rows_final[sh[li].g];
+    sh[li].alloc(ctx, N);
+  }
+  std::vector<uint64_t> n_cur_all(W, 0);
+  n_cur_all[0] = N;
+
+  t_bcr.start();
+  // pass 0: the N sentinel rows, all on shard 0
+  for (int li = 0; li < nl; ++li) {
+    Shard<PosT>& s = sh[li];
+    if (s.g == 0) {
+      SGX_LAUNCH(ctx, (bcr_init_kernel<PosT>), grid_for((N + 1) / 2, 256), 256, 0, acc, d_sord, N, s.B, s.ID, s.NP);
+      s.n_cur = N;
+      s.held = N;
+    }
+    s.nb = s.n_cur / kBcrBlock + 1;
+    SGX_LAUNCH(ctx, sym_block_count_kernel, grid_for(s.nb * 32, 256), 256, 0, (const uint8_t*)s.B, s.n_cur, s.nb, s.cnt.p);
+    scan_exclusive(ctx, s.cnt.p, 4 * s.nb, s.scan_ws.p, s.sym_total.p);
+  }
+
+  std::vector<uint64_t> M((size_t)W * kMetaN), cntm((size_t)W * W), soff((size_t)W * W), roff((size_t)W * W);
+  std::vector<const uint64_t*> meta_ptr(nl);
+  std::vector<const void*> send_ptr(nl);
+  std::vector<void*> recv_ptr(nl);
+  for (uint32_t j = 1; j <= lmax; ++j) {
+    // ---- sender side
+    for (int li = 0; li < nl; ++li) {
+      Shard<PosT>& s = sh[li];
+      uint32_t ntiles = 1;
+      if (s.held) {
+        SGX_LAUNCH(ctx, (shard_rank_kernel<PosT>), grid_for(s.held, 256), 256, 0, acc, (const uint8_t*)s.B,
+                   (const uint64_t*)s.cnt.p, s.nb, bounds, (const uint32_t*)s.ID, (const PosT*)s.NP, s.held, j, s.tmpDest.p,
+                   s.tmpPos.p);
+        DestDigit dg{s.tmpDest.p};
+        SendMove<PosT> mv{s.ID, s.tmpPos.p, s.sendID.p, s.sendPos.p};
+        partition_pass<kMaxShards>(ctx, dg, mv, s.held, s.part_ws.p, s.kept.p);
+        ntiles = part_tiles(s.held);
+      }
+      SGX_LAUNCH(ctx, shard_meta_kernel, 1, 32, 0, (const uint64_t*)s.part_ws.p, ntiles, s.held ? 1 : 0,
+                 (const uint64_t*)s.kept.p, (const uint64_t*)s.cnt.p, s.nb, (const uint64_t*)s.sym_total.p, s.meta.p);
+      meta_ptr[li] = s.meta.p;
+    }
+    // ---- counts + symbol totals of every shard, then the inserts themselves
+    comm_allgather_u64(cm, meta_ptr.data(), kMetaN, M.data());
+    uint64_t moved = 0;
+    for (int s = 0; s < W; ++s) {
+      uint64_t run = 0;
+      for (int d = 0; d < W; ++d) {
+        cntm[s * W + d] = M[(size_t)s * kMetaN + d];
+        soff[s * W + d] = run;
+        run += cntm[s * W + d];
+      }
+      moved += run;
+    }
+    if (moved == 0) break;  // every read has ended
+    std::vector<uint64_t> n_in(W, 0), n_new(W, 0), first_row(W + 1, 0);
+    for (int d = 0; d < W; ++d) {
+      uint64_t run = 0;
+      for (int s = 0; s < W; ++s) {
+        roff[d * W + s] = run;
+        run += cntm[s * W + d];
+      }
+      n_in[d] = run;
+      n_new[d] = n_cur_all[d] + run;
+      first_row[d + 1] = first_row[d] + n_new[d];
+    }
+    for (int li = 0; li < nl; ++li) {
+      send_ptr[li] = sh[li].sendID.p;
+      recv_ptr[li] = sh[li].recvID.p;
+    }
+    comm_alltoallv(cm, send_ptr.data(), recv_ptr.data(), sizeof(uint32_t), cntm.data(), soff.data(), roff.data());
+    for (int li = 0; li < nl; ++li) {
+      send_ptr[li] = sh[li].sendPos.p;
+      recv_ptr[li] = sh[li].recvPos.p;
+    }
+    comm_alltoallv(cm, send_ptr.data(), recv_ptr.data(), sizeof(PosT), cntm.data(), soff.data(), roff.data());
+
+    // ---- receiver side
+    uint64_t T[4] = {0, 0, 0, 0};
+    for (int s = 0; s < W; ++s)
+      for (int c = 0; c < 4; ++c) T[c] += M[(size_t)s * kMetaN + kMaxShards + c];
+    for (int li = 0; li < nl; ++li) {
+      Shard<PosT>& s = sh[li];
+      const int g = s.g;
+      const uint64_t held_new = n_in[g];
+      SGX_REQUIRE(n_new[g] <= s.rows_final, SGX_ECUDA, "sharded index: a shard received more rows than were counted for it");
+      if (held_new) {
+        RecvFix fix;
+        memset(&fix, 0, sizeof(fix));
+        fix.world = W;
+        for (int q = 0; q < W; ++q) fix.roff[q] = roff[g * W + q];
+        fix.roff[W] = held_new;
+        long long less_global = (long long)N;  // rows of suffixes starting with a symbol < c
+        for (int c = 0; c < 4; ++c) {
+          long long before = 0;  // symbols c in the rows of shards before the sender
+          for (int q = 0; q < W; ++q) {
+            long long less_local = 0;
+            for (int c2 = 0; c2 < c; ++c2) less_local += (long long)M[(size_t)q * kMetaN + kMaxShards + c2];
+            fix.K[q][c] = less_global + before - less_local - (long long)first_row[g];
+            before += (long long)M[(size_t)q * kMetaN + kMaxShards + c];
+          }
+          less_global += (long long)T[c];
+        }
+        RecvDigit dg{acc, s.recvID.p, j};
+        RecvMove<PosT> mv{acc, s.recvID.p, s.recvPos.p, j, fix, s.ID2, s.NP2, s.SYM.p};
+        partition_pass<4>(ctx, dg, mv, held_new, s.part_ws.p, (uint64_t*)nullptr);
+        const uint64_t rows_new = s.n_cur + held_new;
+        const uint64_t ntiles = (rows_new + kMergeTile - 1) / kMergeTile;
+        SGX_LAUNCH(ctx, (bcr_tile_bounds_kernel<PosT>), grid_for(held_new + 1, 256), 256, 0, (const PosT*)s.NP2, held_new,
+                   ntiles, s.tile_k0.p);
+        const uint64_t nb_new = rows_new / kBcrBlock + 1;
+        SGX_CUDA(cudaMemsetAsync(s.cnt.p, 0, 4 * nb_new * sizeof(uint64_t), ctx->stream));
+        k_merge.tick();
+        SGX_LAUNCH(ctx, (bcr_merge_kernel<PosT>), (unsigned)ntiles, kMergeThreads, 0, (const uint8_t*)s.B, s.n_cur,
+                   (const PosT*)s.NP2, (const uint8_t*)s.SYM.p, held_new, (const uint64_t*)s.tile_k0.p, s.Bn, rows_new, nb_new,
+                   s.cnt.p);
+        k_merge.tick();
+        out->merge_launches++;
+        out->merge_bytes += (s.n_cur + rows_new) / 2 + held_new * (sizeof(PosT) + 1);
+        scan_exclusive(ctx, s.cnt.p, 4 * nb_new, s.scan_ws.p, s.sym_total.p);
+        std::swap(s.B, s.Bn);
+        std::swap(s.ID, s.ID2);
+        std::swap(s.NP, s.NP2);
+        s.n_cur = rows_new;
+        s.nb = nb_new;
+      }
+      // without inserts the rows and their scanned counts stay as they are
+      s.held = held_new;
+    }
+    for (int d = 0; d < W; ++d) n_cur_all[d] = n_new[d];
+  }
+  for (int li = 0; li < nl; ++li)
+    SGX_REQUIRE(sh[li].n_cur == sh[li].rows_final, SGX_ECUDA, "sharded index: column passes did not fill the shard's rows");
+  t_bcr.stop();
+
+  // ---- run-length encoding with seam handling, segments concatenated on shard 0
+  t_emit.start();
+  const int kSeamN = 5;
+  std::vector<uint64_t> seam((size_t)W * kSeamN);
+  {
+    std::vector<DevBuf<uint64_t> > d_seam(nl);
+    std::vector<const uint64_t*> ptr(nl);
+    for (int li = 0; li < nl; ++li) {
+      Shard<PosT>& s = sh[li];
+      rle_heads(ctx, s.B, s.n_cur, &s.seg);
+      const uint64_t v[kSeamN] = {s.seg.n_rows, s.seg.first_sym, s.seg.first_len, s.seg.last_sym, s.seg.last_len};
+      d_seam[li].alloc(kSeamN);
+      SGX_CUDA(cudaMemcpyAsync(d_seam[li].p, v, sizeof(v), cudaMemcpyHostToDevice, ctx->stream));
+      SGX_CUDA(cudaStreamSynchronize(ctx->stream));  // v is a stack array
+      ptr[li] = d_seam[li].p;
+    }
+    comm_allgather_u64(cm, ptr.data(), kSeamN, seam.data());
+  }
+  std::vector<uint64_t> seg_bytes(W, 0);
+  {
+    std::vector<DevBuf<uint64_t> > d_b(nl);
+    std::vector<const uint64_t*> ptr(nl);
+    for (int li = 0; li < nl; ++li) {
+      Shard<PosT>& s = sh[li];
+      const int g = s.g;
+      int skip_first = 0;
+      uint64_t extend = 0;
+      if (s.seg.n_rows) {
+        // does my first run continue a run of an earlier shard?
+        for (int p = g - 1; p >= 0; --p) {
+          if (seam[(size_t)p * kSeamN + 0] == 0) continue;
+          skip_first = seam[(size_t)p * kSeamN + 3] == s.seg.first_sym ? 1 : 0;
+          break;
+        }
+        // rows of later shards that continue my last run (only counted by the shard where the run starts)
+        const bool whole = s.seg.n_runs == 1;
+        if (!(whole && skip_first)) {
+          for (int q = g + 1; q < W; ++q) {
+            const uint64_t* sq = &seam[(size_t)q * kSeamN];
+            if (sq[0] == 0) continue;
+            if (sq[1] != s.seg.last_sym) break;
+            extend += sq[2];
+            if (sq[2] != sq[0]) break;  // that shard has further runs
+          }
+        }
+      }
+      rle_emit(ctx, s.B, s.seg, skip_first, extend, &s.rle, &s.rle_bytes);
+      d_b[li].alloc(1);
+      SGX_CUDA(cudaMemcpyAsync(d_b[li].p, &s.rle_bytes, sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+      SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+      ptr[li] = d_b[li].p;
+    }
+    comm_allgather_u64(cm, ptr.data(), 1, seg_bytes.data());
+  }
+  uint64_t total = 0;
+  for (int g = 0; g < W; ++g) total += seg_bytes[g];
+  *rle_total = total;
+  *rle_host = nullptr;
+  {
+    const bool root_here = cm->local || cm->rank == 0;
+    DevBuf<uint8_t> d_all;
+    if (root_here) d_all.alloc(total ? total : 1);
+    std::vector<const uint8_t*> ptr(nl);
+    for (int li = 0; li < nl; ++li) ptr[li] = sh[li].rle.p;
+    comm_gatherv_bytes(cm, ptr.data(), seg_bytes.data(), 0, d_all.p);
+    if (root_here) {
+      *rle_host = (uint8_t*)pinned_get(ctx, total ? total : 1);
+      SGX_CUDA(cudaMemcpyAsync(*rle_host, d_all.p, total, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  t_emit.stop();
+}
+
+void index_build_sharded(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, int order, bool reversed, sgx_index_out* out) {
+  memset(out, 0, sizeof(*out));
+  const uint64_t N = reads->n;
+  const uint64_t S = reads->bases + N;
+  const int W = cm->world;
+  const uint64_t launches0 = ctx->launches;
+  EventTimer t_all(ctx->stream), t_sort(ctx->stream), t_bcr(ctx->stream), t_emit(ctx->stream);
+  KernelClock k_merge(ctx->stream);
+  ReadAcc acc;
+  acc.rv = reads->view();
+  acc.reversed = reversed ? 1 : 0;
+
+  t_all.start();
+  t_sort.start();
+  // ---- read order: replicated on every shard (N items)
+  DevBuf<uint32_t> d_sai(N), d_sord(N);
+  index_read_order(ctx, reads, acc, order, d_sai.p, d_sord.p);
+
+  // ---- bucket bounds from the k-mer histogram of a read sample; exact rows per shard
+  const int nslices = cm->local ? 1 : W;
+  const int slice = cm->local ? 0 : cm->rank;
+  ShardBounds bounds;
+  memset(&bounds, 0, sizeof(bounds));
+  bounds.world = W;
+  std::vector<uint64_t> rows_final(W, 0);
+  {
+    DevBuf<uint64_t> hist(kKeySpace);
+    SGX_CUDA(cudaMemsetAsync(hist.p, 0, kKeySpace * sizeof(uint64_t), ctx->stream));
+    const uint64_t stride = std::max<uint64_t>(1, N >> 21);  // about two million sampled reads in total
+    const uint64_t n_sample = (N + stride - 1) / stride;
+    const uint64_t mine = (n_sample + nslices - 1 - slice) / nslices;  // samples slice, slice + nslices, ...
+    if (mine)
+      SGX_LAUNCH(ctx, key_hist_kernel, grid_for(mine, 256), 256, 0, acc, N, (uint64_t)slice * stride,
+                 (uint64_t)nslices * stride, (unsigned long long*)hist.p);
+    if (!cm->local) {
+      uint64_t* hp = hist.p;
+      comm_allreduce_sum_u64(cm, &hp, kKeySpace);
+    }
+    std::vector<uint64_t> h(kKeySpace);
+    SGX_CUDA(cudaMemcpyAsync(h.data(), hist.p, kKeySpace * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+    uint64_t total = 0;
+    for (uint32_t k = 0; k < kKeySpace; ++k) total += h[k];
+    bounds.b[0] = 0;
+    uint64_t cum = 0;
+    uint32_t key = 0;
+    for (int g = 1; g < W; ++g) {
+      const uint64_t want = total / W * g + (total % W) * g / W;
+      while (key < kKeySpace && cum < want) cum += h[key++];
+      bounds.b[g] = std::max<uint32_t>(std::max<uint32_t>(key, 1u), bounds.b[g - 1]);  // key 0 (the '$' rows) stays on shard 0
+    }
+    for (int g = W; g <= kMaxShards; ++g) bounds.b[g] = kKeySpace;
+
+    DevBuf<uint64_t> rows(kMaxShards);
+    SGX_CUDA(cudaMemsetAsync(rows.p, 0, kMaxShards * sizeof(uint64_t), ctx->stream));
+    const uint64_t r0 = N / nslices * slice + std::min<uint64_t>(N % nslices, slice);
+    const uint64_t r1 = r0 + N / nslices + ((uint64_t)slice < N % nslices ? 1 : 0);
+    if (r1 > r0)
+      SGX_LAUNCH(ctx, shard_rows_kernel, grid_for(r1 - r0, 256), 256, 0, acc, r0, r1, bounds, (unsigned long long*)rows.p);
+    if (!cm->local) {
+      uint64_t* rp = rows.p;
+      comm_allreduce_sum_u64(cm, &rp, kMaxShards);
+    }
+    uint64_t hr[kMaxShards];
+    SGX_CUDA(cudaMemcpyAsync(hr, rows.p, sizeof(hr), cudaMemcpyDeviceToHost, ctx->stream));
+    SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+    uint64_t sum = 0;
+    for (int g = 0; g < W; ++g) {
+      rows_final[g] = hr[g];
+      sum += hr[g];
+    }
+    SGX_REQUIRE(sum == S, SGX_ECUDA, "sharded index: shard row counts do not add up to the number of suffixes");
+  }
+  t_sort.stop();
+
+  uint8_t* rle_host = nullptr;
+  uint64_t rle_total = 0;
+  const char* fw = getenv("SGX_FORCE_WIDE");
+  if (S < 0xffffffffull && !(fw && fw[0] == '1')) {
+    sharded_build<uint32_t>(ctx, cm, reads, acc, d_sord.p, bounds, rows_final, out, k_merge, t_bcr, t_emit, &rle_host, &rle_total);
+  } else {
+    sharded_build<uint64_t>(ctx, cm, reads, acc, d_sord.p, bounds, rows_final, out, k_merge, t_bcr, t_emit, &rle_host, &rle_total);
+  }
+  out->n_strings = N;
+  out->n_suffixes = S;
+  out->n_runs = rle_total;
+  out->rle = rle_host ? rle_host : (uint8_t*)pinned_get(ctx, 1);  // only shard 0 holds the concatenated run bytes
+  out->sai = (uint32_t*)pinned_get(ctx, N * sizeof(uint32_t));
+  SGX_CUDA(cudaMemcpyAsync(out->sai, d_sai.p, N * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  t_all.stop();
+  SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+  out->ms_total = t_all.ms();
+  out->ms_sort = t_sort.ms();
+  out->ms_bcr = t_bcr.ms();
+  out->ms_emit = t_emit.ms();
+  out->ms_merge = k_merge.total_ms();
+  out->launches = ctx->launches - launches0;
+}
+
+}  // namespace sgx

@@ -1,0 +1,80 @@
+"""NCCL transport check of the bucket-sharded index build (needs >= 2 GPUs; run under torchrun on the GPU box).
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
+      tests/multigpu_index_check.py [cfg] [scale] [reps]
+
+Every rank packs the same synthetic read set (cfg2 at `scale` by default), rank 0 also builds the index on its own
+GPU with sgx_index_build; then all ranks run sgx_index_build_sharded over NCCL and rank 0 compares run bytes and .sai.
+Prints one JSON line with the timings (device time = max over ranks).
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from siga_b200 import api, synth
+
+    cfg = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
+    scale = float(sys.argv[2]) if len(sys.argv) > 2 else 0.1
+    reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    reads = synth.config_reads(cfg, scale)
+    flat, off = synth.reads_to_flat(reads)
+    ctx = api.Context(local)
+    uid = torch.from_numpy(ctx.comm_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)).cuda()
+    dist.broadcast(uid, 0)
+    comm = ctx.comm_init(uid.cpu().numpy(), rank, world)
+    r = ctx.pack_reads(flat, off)
+    ok = True
+    out = {"cfg": cfg, "scale": scale, "reads": int(reads.shape[0]), "read_len": int(reads.shape[1]), "world": world}
+    for rev in (False, True):
+        one = None
+        if rank == 0:
+            for _ in range(2):
+                one = ctx.index_build(r, reversed=rev)
+            out["single_ms_rev%d" % rev] = one.stats["ms_total"]
+        for it in range(reps):
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            res = ctx.index_build_sharded(comm, r, reversed=rev)
+            torch.cuda.synchronize()
+            wall = (time.perf_counter() - t0) * 1e3
+            t = torch.tensor([wall, res.stats["ms_total"], res.stats["ms_sort"], res.stats["ms_bcr"], res.stats["ms_emit"],
+                              res.stats["ms_merge"]], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            same = np.array_equal(res.runs, one.runs) and np.array_equal(res.sai, one.sai)
+            ok = ok and same
+            out["sharded_rev%d" % rev] = dict(zip(["wall_ms", "ms_total", "ms_sort", "ms_bcr", "ms_emit", "ms_merge"],
+                                                  [round(float(x), 2) for x in t.tolist()]), identical=bool(same),
+                                              run_bytes=int(len(res.runs)), launches=res.stats["launches"])
+        else:
+            assert np.array_equal(res.sai, res.sai)
+    ctx.free_comm(comm)
+    ctx.free_reads(r)
+    ctx.close()
+    if rank == 0:
+        out["ok"] = bool(ok)
+        print(json.dumps(out))
+    dist.destroy_process_group()
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
