@@ -4,6 +4,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <mutex>
 
 namespace sgx {
@@ -72,6 +73,13 @@ void comm_unique_id(uint8_t id[128]) {
   memcpy(id, &u, 128);
 }
 
+static void comm_init_staging(sgx_comm* cm) {
+  cm->ag_dev = nullptr;
+  cm->ag_host = nullptr;
+  cm->ag_cap = 0;
+  SGX_CUDA(cudaEventCreateWithFlags(&cm->ag_done, cudaEventDisableTiming));
+}
+
 sgx_comm* comm_create_nccl(sgx_ctx* ctx, const uint8_t id[128], int rank, int world) {
   SGX_REQUIRE(world >= 1 && world <= kMaxShards && rank >= 0 && rank < world, SGX_EINVAL, "sgx_comm_init: bad rank/world");
   ncclUniqueId u;
@@ -84,6 +92,7 @@ sgx_comm* comm_create_nccl(sgx_ctx* ctx, const uint8_t id[128], int rank, int wo
   cm->rank = rank;
   cm->local = false;
   cm->nccl = c;
+  comm_init_staging(cm);
   return cm;
 }
 
@@ -95,32 +104,53 @@ sgx_comm* comm_create_local(sgx_ctx* ctx, int shards) {
   cm->rank = 0;
   cm->local = true;
   cm->nccl = nullptr;
+  comm_init_staging(cm);
   return cm;
 }
 
 void comm_destroy(sgx_comm* cm) {
   if (!cm) return;
-  if (cm->nccl) {
-    cudaStreamSynchronize(cm->ctx->stream);
-    nccl_api().CommDestroy((ncclComm_t)cm->nccl);
-  }
+  cudaStreamSynchronize(cm->ctx->stream);
+  if (cm->nccl) nccl_api().CommDestroy((ncclComm_t)cm->nccl);
+  if (cm->ag_dev) cudaFree(cm->ag_dev);
+  if (cm->ag_host) cudaFreeHost(cm->ag_host);
+  cudaEventDestroy(cm->ag_done);
   delete cm;
 }
 
 // ---- primitives --------------------------------------------------------------------------------------------------------
 
-void comm_allgather_u64(sgx_comm* cm, const uint64_t* const* dev_vals, uint64_t n, uint64_t* out) {
+static void ag_reserve(sgx_comm* cm, uint64_t elems) {
+  if (cm->ag_cap >= elems) return;
+  SGX_CUDA(cudaStreamSynchronize(cm->ctx->stream));
+  if (cm->ag_dev) cudaFree(cm->ag_dev);
+  if (cm->ag_host) cudaFreeHost(cm->ag_host);
+  cm->ag_dev = nullptr;
+  cm->ag_host = nullptr;
+  cm->ag_cap = 0;
+  const uint64_t cap = std::max<uint64_t>(elems, 1024);
+  SGX_CUDA(cudaMalloc((void**)&cm->ag_dev, cap * sizeof(uint64_t)));
+  SGX_CUDA(cudaMallocHost((void**)&cm->ag_host, cap * sizeof(uint64_t)));
+  cm->ag_cap = cap;
+}
+
+void comm_allgather_u64_begin(sgx_comm* cm, const uint64_t* const* dev_vals, uint64_t n) {
   cudaStream_t st = cm->ctx->stream;
+  const uint64_t total = (uint64_t)cm->world * n;
+  ag_reserve(cm, total);
   if (cm->local) {
     for (int s = 0; s < cm->world; ++s)
-      SGX_CUDA(cudaMemcpyAsync(out + (uint64_t)s * n, dev_vals[s], n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    SGX_CUDA(cudaStreamSynchronize(st));
-    return;
+      SGX_CUDA(cudaMemcpyAsync(cm->ag_host + (uint64_t)s * n, dev_vals[s], n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  } else {
+    SGX_NCCL(nccl_api().AllGather(dev_vals[0], cm->ag_dev, n, ncclUint64, (ncclComm_t)cm->nccl, st));
+    SGX_CUDA(cudaMemcpyAsync(cm->ag_host, cm->ag_dev, total * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   }
-  DevBuf<uint64_t> all((uint64_t)cm->world * n);
-  SGX_NCCL(nccl_api().AllGather(dev_vals[0], all.p, n, ncclUint64, (ncclComm_t)cm->nccl, st));
-  SGX_CUDA(cudaMemcpyAsync(out, all.p, (uint64_t)cm->world * n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-  SGX_CUDA(cudaStreamSynchronize(st));
+  SGX_CUDA(cudaEventRecord(cm->ag_done, st));
+}
+
+void comm_allgather_u64_end(sgx_comm* cm, uint64_t n, uint64_t* out) {
+  SGX_CUDA(cudaEventSynchronize(cm->ag_done));
+  memcpy(out, cm->ag_host, (uint64_t)cm->world * n * sizeof(uint64_t));
 }
 
 static __global__ void add_u64_kernel(uint64_t* __restrict__ acc, const uint64_t* __restrict__ x, uint64_t n) {

@@ -20,6 +20,11 @@ struct sgx_comm {
   int rank;     // NCCL mode: this process's shard; local mode: 0
   bool local;   // true: all shards live in this process
   void* nccl;   // ncclComm_t
+  // small persistent staging of comm_allgather_u64 (device gather buffer, pinned host copy, completion event)
+  uint64_t* ag_dev;
+  uint64_t* ag_host;
+  uint64_t ag_cap;  // uint64 elements
+  cudaEvent_t ag_done;
   int n_local() const { return local ? world : 1; }
   int shard_of(int li) const { return local ? li : rank; }  // global shard index of local shard li
 };
@@ -34,8 +39,15 @@ sgx_comm* comm_create_local(sgx_ctx* ctx, int shards);
 void comm_destroy(sgx_comm* cm);
 
 // out[(s * n) + i] = value i of shard s, for all `world` shards, on the HOST of every process.  `dev_vals[li]` is a
-// device array of n uint64 values of local shard li.  Synchronises the stream.
-void comm_allgather_u64(sgx_comm* cm, const uint64_t* const* dev_vals, uint64_t n, uint64_t* out);
+// device array of n uint64 values of local shard li.  Waits for the gathered values only (an event), not for work
+// enqueued on the stream afterwards by comm_allgather_u64_begin's caller:
+//   comm_allgather_u64_begin(...); <enqueue more kernels>; comm_allgather_u64_end(cm, n, out);
+void comm_allgather_u64_begin(sgx_comm* cm, const uint64_t* const* dev_vals, uint64_t n);
+void comm_allgather_u64_end(sgx_comm* cm, uint64_t n, uint64_t* out);
+inline void comm_allgather_u64(sgx_comm* cm, const uint64_t* const* dev_vals, uint64_t n, uint64_t* out) {
+  comm_allgather_u64_begin(cm, dev_vals, n);
+  comm_allgather_u64_end(cm, n, out);
+}
 
 // Element-wise sum over shards of an n-element uint64 device array (in place, every local shard gets the sum).
 void comm_allreduce_sum_u64(sgx_comm* cm, uint64_t* const* dev_vals, uint64_t n);

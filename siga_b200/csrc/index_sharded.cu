@@ -138,6 +138,13 @@ __global__ void __launch_bounds__(256) shard_rank_kernel(ReadAcc acc, const uint
   tmpPos[k] = (PosT)(scanned[(uint64_t)c * nb + b] + inblk);
 }
 
+// One insert on the wire: the sender-local rank part and the read.
+template <class PosT>
+struct WireItem {
+  PosT pos;
+  uint32_t id;
+};
+
 struct DestDigit {
   const uint8_t* tmpDest;
   __device__ __forceinline__ int operator()(uint64_t k) const { return (int)tmpDest[k]; }  // 255 -> dropped
@@ -146,11 +153,12 @@ template <class PosT>
 struct SendMove {
   const uint32_t* ID;
   const PosT* tmpPos;
-  uint32_t* sendID;
-  PosT* sendPos;
+  WireItem<PosT>* send;
   __device__ __forceinline__ void operator()(uint64_t k, uint64_t dest) const {
-    sendID[dest] = ID[k];
-    sendPos[dest] = tmpPos[k];
+    WireItem<PosT> w;
+    w.pos = tmpPos[k];
+    w.id = ID[k];
+    send[dest] = w;
   }
 };
 
@@ -181,12 +189,13 @@ struct RecvFix {
   uint64_t roff[kMaxShards + 1];  // first item of each sender in the receive buffer
   int world;
 };
+template <class PosT>
 struct RecvDigit {
   ReadAcc acc;
-  const uint32_t* recvID;
+  const WireItem<PosT>* recv;
   uint32_t j;
   __device__ __forceinline__ int operator()(uint64_t k) const {
-    const uint32_t id = recvID[k];
+    const uint32_t id = recv[k].id;
     const uint32_t l = acc.rv.len[id];
     return (int)acc.code(id, l - j, l);
   }
@@ -194,22 +203,22 @@ struct RecvDigit {
 template <class PosT>
 struct RecvMove {
   ReadAcc acc;
-  const uint32_t* recvID;
-  const PosT* recvPos;
+  const WireItem<PosT>* recv;
   uint32_t j;
   RecvFix fix;
   uint32_t* ID2;
   PosT* NP2;
   uint8_t* SYM2;
   __device__ __forceinline__ void operator()(uint64_t k, uint64_t dest) const {
-    const uint32_t id = recvID[k];
+    const WireItem<PosT> w = recv[k];
+    const uint32_t id = w.id;
     const uint32_t l = acc.rv.len[id];
     const uint32_t c = acc.code(id, l - j, l);
     int s = 0;
 #pragma unroll
     for (int i = 1; i < kMaxShards; ++i) s += (i < fix.world && k >= fix.roff[i]) ? 1 : 0;
     ID2[dest] = id;
-    NP2[dest] = (PosT)((long long)recvPos[k] + fix.K[s][c]);
+    NP2[dest] = (PosT)((long long)w.pos + fix.K[s][c]);
     SYM2[dest] = (l == j) ? (uint8_t)0 : (uint8_t)(acc.code(id, l - j - 1, l) + 1);
   }
 };
@@ -219,8 +228,9 @@ struct Shard {
   int g = 0;
   uint64_t rows_final = 0;
   DevBuf<uint8_t> B0, B1, SYM, tmpDest;
-  DevBuf<uint32_t> ID0, ID1, sendID, recvID;
-  DevBuf<PosT> NP0, NP1, tmpPos, sendPos, recvPos;
+  DevBuf<uint32_t> ID0, ID1;
+  DevBuf<PosT> NP0, NP1, tmpPos;
+  DevBuf<WireItem<PosT> > send, recv;
   DevBuf<uint64_t> cnt, scan_ws, part_ws, tile_k0, meta, kept, sym_total;
   uint8_t* B = nullptr;
   uint8_t* Bn = nullptr;
@@ -243,13 +253,11 @@ struct Shard {
     tmpDest.alloc(N);
     ID0.alloc(N);
     ID1.alloc(N);
-    sendID.alloc(N);
-    recvID.alloc(N);
+    send.alloc(N);
+    recv.alloc(N);
     NP0.alloc(N);
     NP1.alloc(N);
     tmpPos.alloc(N);
-    sendPos.alloc(N);
-    recvPos.alloc(N);
     const uint64_t nb_max = rows_final / kBcrBlock + 2;
     cnt.alloc(4 * nb_max);
     scan_ws.alloc(scan_ws_elems(4 * nb_max));
@@ -303,7 +311,8 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
   std::vector<const void*> send_ptr(nl);
   std::vector<void*> recv_ptr(nl);
   for (uint32_t j = 1; j <= lmax; ++j) {
-    // ---- sender side
+    // ---- sender side: ranks + destinations, bucket sizes; the sizes travel (all-gather, copy to the host) while
+    //      the scatter into the send buffer runs
     for (int li = 0; li < nl; ++li) {
       Shard<PosT>& s = sh[li];
       uint32_t ntiles = 1;
@@ -312,16 +321,22 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
                    (const uint64_t*)s.cnt.p, s.nb, bounds, (const uint32_t*)s.ID, (const PosT*)s.NP, s.held, j, s.tmpDest.p,
                    s.tmpPos.p);
         DestDigit dg{s.tmpDest.p};
-        SendMove<PosT> mv{s.ID, s.tmpPos.p, s.sendID.p, s.sendPos.p};
-        partition_pass<kMaxShards>(ctx, dg, mv, s.held, s.part_ws.p, s.kept.p);
+        partition_count<kMaxShards, DestDigit>(ctx, dg, s.held, s.part_ws.p, s.kept.p);
         ntiles = part_tiles(s.held);
       }
       SGX_LAUNCH(ctx, shard_meta_kernel, 1, 32, 0, (const uint64_t*)s.part_ws.p, ntiles, s.held ? 1 : 0,
                  (const uint64_t*)s.kept.p, (const uint64_t*)s.cnt.p, s.nb, (const uint64_t*)s.sym_total.p, s.meta.p);
       meta_ptr[li] = s.meta.p;
     }
-    // ---- counts + symbol totals of every shard, then the inserts themselves
-    comm_allgather_u64(cm, meta_ptr.data(), kMetaN, M.data());
+    comm_allgather_u64_begin(cm, meta_ptr.data(), kMetaN);
+    for (int li = 0; li < nl; ++li) {
+      Shard<PosT>& s = sh[li];
+      if (!s.held) continue;
+      DestDigit dg{s.tmpDest.p};
+      SendMove<PosT> mv{s.ID, s.tmpPos.p, s.send.p};
+      partition_scatter<kMaxShards, DestDigit, SendMove<PosT> >(ctx, dg, mv, s.held, s.part_ws.p);
+    }
+    comm_allgather_u64_end(cm, kMetaN, M.data());
     uint64_t moved = 0;
     for (int s = 0; s < W; ++s) {
       uint64_t run = 0;
@@ -345,15 +360,10 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
       first_row[d + 1] = first_row[d] + n_new[d];
     }
     for (int li = 0; li < nl; ++li) {
-      send_ptr[li] = sh[li].sendID.p;
-      recv_ptr[li] = sh[li].recvID.p;
+      send_ptr[li] = sh[li].send.p;
+      recv_ptr[li] = sh[li].recv.p;
     }
-    comm_alltoallv(cm, send_ptr.data(), recv_ptr.data(), sizeof(uint32_t), cntm.data(), soff.data(), roff.data());
-    for (int li = 0; li < nl; ++li) {
-      send_ptr[li] = sh[li].sendPos.p;
-      recv_ptr[li] = sh[li].recvPos.p;
-    }
-    comm_alltoallv(cm, send_ptr.data(), recv_ptr.data(), sizeof(PosT), cntm.data(), soff.data(), roff.data());
+    comm_alltoallv(cm, send_ptr.data(), recv_ptr.data(), sizeof(WireItem<PosT>), cntm.data(), soff.data(), roff.data());
 
     // ---- receiver side
     uint64_t T[4] = {0, 0, 0, 0};
@@ -381,8 +391,8 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
           }
           less_global += (long long)T[c];
         }
-        RecvDigit dg{acc, s.recvID.p, j};
-        RecvMove<PosT> mv{acc, s.recvID.p, s.recvPos.p, j, fix, s.ID2, s.NP2, s.SYM.p};
+        RecvDigit<PosT> dg{acc, s.recv.p, j};
+        RecvMove<PosT> mv{acc, s.recv.p, j, fix, s.ID2, s.NP2, s.SYM.p};
         partition_pass<4>(ctx, dg, mv, held_new, s.part_ws.p, (uint64_t*)nullptr);
         const uint64_t rows_new = s.n_cur + held_new;
         const uint64_t ntiles = (rows_new + kMergeTile - 1) / kMergeTile;

@@ -202,20 +202,29 @@ inline uint64_t part_ws_elems(uint64_t n, int radix) {
 
 // Runs one stable partition pass.  bucket_starts_dev (optional, device, RADIX+... not provided): callers that need
 // the bucket sizes read tilecnt afterwards: after the call ws[d*ntiles] is the start offset of bucket d.
+// The two halves of a pass, for callers that want the bucket sizes (ws[d * ntiles] = start of bucket d after the
+// scan, *total_dev = items kept) on their way to the host while the scatter is still running.
+template <int RADIX, class DigitF>
+inline void partition_count(sgx_ctx* ctx, DigitF digit, uint64_t n, uint64_t* ws, uint64_t* total_dev) {
+  const uint32_t ntiles = part_tiles(n);
+  const uint64_t c = (uint64_t)RADIX * ntiles;
+  SGX_LAUNCH(ctx, (part_count_kernel<RADIX, DigitF>), ntiles, kPartThreads, 0, digit, n, ws, ntiles);
+  scan_exclusive(ctx, ws, c, ws + c, total_dev);
+}
+template <int RADIX, class DigitF, class MoveF>
+inline void partition_scatter(sgx_ctx* ctx, DigitF digit, MoveF move, uint64_t n, const uint64_t* ws) {
+  const uint32_t ntiles = part_tiles(n);
+  SGX_LAUNCH(ctx, (part_scatter_kernel<RADIX, DigitF, MoveF>), ntiles, kPartThreads, 0, digit, move, n, ws, ntiles);
+}
+
 template <int RADIX, class DigitF, class MoveF>
 inline void partition_pass(sgx_ctx* ctx, DigitF digit, MoveF move, uint64_t n, uint64_t* ws, uint64_t* total_dev) {
   if (n == 0) {
     if (total_dev) SGX_CUDA(cudaMemsetAsync(total_dev, 0, sizeof(uint64_t), ctx->stream));
     return;
   }
-  const uint32_t ntiles = part_tiles(n);
-  const uint64_t c = (uint64_t)RADIX * ntiles;
-  uint64_t* tilecnt = ws;
-  uint64_t* scan_ws = ws + c;
-  SGX_LAUNCH(ctx, (part_count_kernel<RADIX, DigitF>), ntiles, kPartThreads, 0, digit, n, tilecnt, ntiles);
-  scan_exclusive(ctx, tilecnt, c, scan_ws, total_dev);
-  SGX_LAUNCH(ctx, (part_scatter_kernel<RADIX, DigitF, MoveF>), ntiles, kPartThreads, 0, digit, move, n,
-             (const uint64_t*)tilecnt, ntiles);
+  partition_count<RADIX, DigitF>(ctx, digit, n, ws, total_dev);
+  partition_scatter<RADIX, DigitF, MoveF>(ctx, digit, move, n, ws);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
