@@ -91,20 +91,26 @@ void index_read_order(sgx_ctx* ctx, const sgx_reads* reads, const ReadAcc& acc, 
                       uint32_t* d_sord) {
   const uint64_t N = reads->n;
   const uint32_t lmax = reads->max_len;
-  // ---- 1. read ordering
+  // ---- 1. read ordering: LSD radix sort of the reads as strings of 32-base (64-bit) key chunks, last chunk first.
+  //      One gather per read and chunk builds the keys; the 8-bit passes inside a chunk stream (key, id) pairs.
+  //      Bases past the end of a read count as 'A' in the key, and the read length is the least significant key, so
+  //      that a read that is a proper prefix of another sorts first ('$' < 'A').
   DevBuf<uint32_t> idsA(N), idsB(N);
   DevBuf<uint64_t> part_ws(part_ws_elems(N, 256)), heads(N + 1), scan_ws(scan_ws_elems(N + 1)), d_total(1);
+  DevBuf<uint64_t> keys(N), keys2(N);
   SGX_LAUNCH(ctx, iota_kernel, grid_for(N, 256), 256, 0, idsA.p, N);
   uint32_t* ids = idsA.p;
-  uint32_t* ids2 = idsB.p;
-  for (uint32_t c = lmax; c > 0;) {
-    const int ncols = c >= 3 ? 3 : (int)c;
-    const uint32_t col0 = c - ncols;
-    ColDigit dg{acc, ids, col0, ncols};
-    IdMove mv{ids, ids2};
-    partition_pass<125>(ctx, dg, mv, N, part_ws.p, (uint64_t*)nullptr);
-    std::swap(ids, ids2);
-    c = col0;
+  if (reads->min_len != lmax) {
+    int lbits = 1;
+    while ((1u << lbits) <= lmax) ++lbits;
+    SGX_LAUNCH(ctx, len_keys_kernel, grid_for(N, 256), 256, 0, acc.rv, (const uint32_t*)ids, N, keys.p);
+    radix_sort_pairs(ctx, keys.p, ids, keys2.p, idsB.p, N, lbits, part_ws.p);
+  }
+  const uint32_t nchunks = (lmax + 31) / 32;
+  for (uint32_t ch = nchunks; ch-- > 0;) {
+    const uint32_t nbases = std::min<uint32_t>(32, lmax - 32 * ch);
+    SGX_LAUNCH(ctx, chunk_keys_kernel, grid_for(N, 256), 256, 0, acc, (const uint32_t*)ids, N, 32 * ch, nbases, keys.p);
+    radix_sort_pairs(ctx, keys.p, ids, keys2.p, idsB.p, N, 2 * (int)nbases, part_ws.p);
   }
   if (order == SGX_ORDER_SAIS) {
     // model A: equal suffixes tie by read index; the content sort is stable, so `ids` is the read-start order and
@@ -114,7 +120,6 @@ void index_read_order(sgx_ctx* ctx, const sgx_reads* reads, const ReadAcc& acc, 
   } else {
     // model B: rank reads by (content, rank of the following read, ...): prefix doubling over the read sequence.
     DevBuf<uint32_t> rank(N), vals(N), vals2(N);
-    DevBuf<uint64_t> keys(N), keys2(N);
     SGX_LAUNCH(ctx, read_heads_kernel, grid_for(N, 256), 256, 0, acc.rv, (const uint32_t*)ids, N, heads.p);
     scan_exclusive(ctx, heads.p, N, scan_ws.p, d_total.p);
     uint64_t distinct = 0;

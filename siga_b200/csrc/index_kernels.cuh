@@ -28,30 +28,36 @@ static __global__ void iota_kernel(uint32_t* a, uint64_t n) {
   if (i < n) a[i] = (uint32_t)i;
 }
 
-// Digit of a read for columns [col0, col0+ncols): base-5 number, leftmost column most significant, '$' (=0) past the
-// end of the read so that a read that is a proper prefix of another sorts first.
-struct ColDigit {
-  ReadAcc acc;
-  const uint32_t* ids;
-  uint32_t col0;
-  int ncols;
-  __device__ __forceinline__ int operator()(uint64_t k) const {
-    const uint32_t id = ids[k];
-    const uint32_t l = acc.rv.len[id];
-    int d = 0;
-    for (int q = 0; q < ncols; ++q) {
-      const uint32_t col = col0 + q;
-      const int s = col < l ? (int)acc.code(id, col, l) + 1 : 0;
-      d = d * 5 + s;
+// keys[k] = bases [col0, col0 + nbases) of read ids[k] in the indexed orientation, first base most significant,
+// 2 bits per base, bases past the end of the read = 0.
+static __global__ void __launch_bounds__(256) chunk_keys_kernel(ReadAcc acc, const uint32_t* __restrict__ ids, uint64_t n,
+                                                               uint32_t col0, uint32_t nbases, uint64_t* __restrict__ keys) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t id = ids[k];
+  const uint32_t l = acc.rv.len[id];
+  const uint32_t* w = acc.rv.words + acc.rv.woff[id];
+  uint64_t key = 0;
+  uint32_t cached = 0xffffffffu, word = 0;
+  for (uint32_t t = 0; t < nbases; ++t) {
+    const uint32_t col = col0 + t;
+    uint32_t code = 0;
+    if (col < l) {
+      const uint32_t j = acc.reversed ? l - 1 - col : col;
+      if ((j >> 4) != cached) {
+        cached = j >> 4;
+        word = w[cached];
+      }
+      code = (word >> (2 * (j & 15))) & 3u;
     }
-    return d;
+    key = (key << 2) | code;
   }
-};
-struct IdMove {
-  const uint32_t* in;
-  uint32_t* out;
-  __device__ __forceinline__ void operator()(uint64_t k, uint64_t dest) const { out[dest] = in[k]; }
-};
+  keys[k] = key;
+}
+static __global__ void len_keys_kernel(ReadsView rv, const uint32_t* __restrict__ ids, uint64_t n, uint64_t* __restrict__ keys) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) keys[k] = rv.len[ids[k]];
+}
 
 // heads[k] = 1 when the k-th read in content order differs from its predecessor.
 static __global__ void read_heads_kernel(ReadsView rv, const uint32_t* __restrict__ ids, uint64_t n, uint64_t* __restrict__ heads) {

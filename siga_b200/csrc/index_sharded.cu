@@ -306,6 +306,12 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
     scan_exclusive(ctx, s.cnt.p, 4 * s.nb, s.scan_ws.p, s.sym_total.p);
   }
 
+  // SGX_SHARD_TRACE=1: device time per phase of the column passes, printed to stderr (diagnostics only)
+  const char* tr = getenv("SGX_SHARD_TRACE");
+  const bool trace = tr && tr[0] == '1';
+  KernelClock k_send(ctx->stream), k_gather(ctx->stream), k_xchg(ctx->stream), k_recv(ctx->stream);
+#define SGX_TRACE_TICK(clock) \
+  if (trace) (clock).tick()
   std::vector<uint64_t> M((size_t)W * kMetaN), cntm((size_t)W * W), soff((size_t)W * W), roff((size_t)W * W);
   std::vector<const uint64_t*> meta_ptr(nl);
   std::vector<const void*> send_ptr(nl);
@@ -313,6 +319,7 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
   for (uint32_t j = 1; j <= lmax; ++j) {
     // ---- sender side: ranks + destinations, bucket sizes; the sizes travel (all-gather, copy to the host) while
     //      the scatter into the send buffer runs
+    SGX_TRACE_TICK(k_send);
     for (int li = 0; li < nl; ++li) {
       Shard<PosT>& s = sh[li];
       uint32_t ntiles = 1;
@@ -328,6 +335,8 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
                  (const uint64_t*)s.kept.p, (const uint64_t*)s.cnt.p, s.nb, (const uint64_t*)s.sym_total.p, s.meta.p);
       meta_ptr[li] = s.meta.p;
     }
+    SGX_TRACE_TICK(k_send);
+    SGX_TRACE_TICK(k_gather);
     comm_allgather_u64_begin(cm, meta_ptr.data(), kMetaN);
     for (int li = 0; li < nl; ++li) {
       Shard<PosT>& s = sh[li];
@@ -336,6 +345,7 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
       SendMove<PosT> mv{s.ID, s.tmpPos.p, s.send.p};
       partition_scatter<kMaxShards, DestDigit, SendMove<PosT> >(ctx, dg, mv, s.held, s.part_ws.p);
     }
+    SGX_TRACE_TICK(k_gather);
     comm_allgather_u64_end(cm, kMetaN, M.data());
     uint64_t moved = 0;
     for (int s = 0; s < W; ++s) {
@@ -363,7 +373,10 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
       send_ptr[li] = sh[li].send.p;
       recv_ptr[li] = sh[li].recv.p;
     }
+    SGX_TRACE_TICK(k_xchg);
     comm_alltoallv(cm, send_ptr.data(), recv_ptr.data(), sizeof(WireItem<PosT>), cntm.data(), soff.data(), roff.data());
+    SGX_TRACE_TICK(k_xchg);
+    SGX_TRACE_TICK(k_recv);
 
     // ---- receiver side
     uint64_t T[4] = {0, 0, 0, 0};
@@ -417,11 +430,19 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
       // without inserts the rows and their scanned counts stay as they are
       s.held = held_new;
     }
+    SGX_TRACE_TICK(k_recv);
     for (int d = 0; d < W; ++d) n_cur_all[d] = n_new[d];
   }
   for (int li = 0; li < nl; ++li)
     SGX_REQUIRE(sh[li].n_cur == sh[li].rows_final, SGX_ECUDA, "sharded index: column passes did not fill the shard's rows");
   t_bcr.stop();
+  if (trace) {
+    SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+    // an unmatched tick is left when the loop ended on `moved == 0`; total_ms() only sums complete pairs
+    fprintf(stderr, "[sgx shard %d/%d] passes: sender %.2f ms, counts gather+scatter %.2f ms, all-to-all %.2f ms, receiver %.2f ms (merge %.2f ms)\n",
+            cm->shard_of(0), W, k_send.total_ms(), k_gather.total_ms(), k_xchg.total_ms(), k_recv.total_ms(), k_merge.total_ms());
+  }
+#undef SGX_TRACE_TICK
 
   // ---- run-length encoding with seam handling, segments concatenated on shard 0
   t_emit.start();
