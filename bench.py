@@ -304,10 +304,10 @@ def main():
         dist.broadcast(uid, 0)
         comm = ctx.comm_init(uid.cpu().numpy(), rank, world)
 
-    def build_index(rd, rv):
+    def build_index(rd, rv, copy=True):
         if comm is None:
-            return ctx.index_build(rd, order=api.ORDER_SAIS2, reversed=rv)
-        return ctx.index_build_sharded(comm, rd, order=api.ORDER_SAIS2, reversed=rv)
+            return ctx.index_build(rd, order=api.ORDER_SAIS2, reversed=rv, copy=copy)
+        return ctx.index_build_sharded(comm, rd, order=api.ORDER_SAIS2, reversed=rv, copy=copy)
 
     for rv, ref_idx in ((False, fi), (True, ri)):  # warm-up + parity of the sharded build at full size
         o = build_index(r_dev, rv)
@@ -320,12 +320,13 @@ def main():
     idx_merge_bytes = idx_launches = idx_merge_launches = 0
     for _ in range(isteps):
         for rv in (False, True):
-            o = build_index(r_dev, rv)
+            o = build_index(r_dev, rv, copy=False)  # results stay in the library's pinned buffers (no numpy copy)
             idx_dev_ms += o.stats["ms_total"]
             idx_merge_ms += o.stats["ms_merge"]
             idx_merge_bytes += o.stats["merge_bytes"]
             idx_launches += o.stats["launches"]
             idx_merge_launches += o.stats["merge_launches"]
+            ctx.free_index(o)
     barrier()
     idx_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / isteps)
     barrier()
@@ -333,7 +334,8 @@ def main():
     for _ in range(isteps):
         rr = ctx.pack_reads(flat, off)
         for rv in (False, True):
-            o = build_index(rr, rv)
+            o = build_index(rr, rv, copy=False)
+            ctx.free_index(o)
         ctx.free_reads(rr)
     barrier()
     idx_e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / isteps)
@@ -370,7 +372,13 @@ def main():
                 "d2h_bytes_per_step": e2e_d2h,
                 "entry": "sgx_reads_pack + sgx_fm_attach_reads x2 + sgx_overlap_edges (pinned host reads / .sai / name ranks in, edges + SS flags out)"},
         "roofline": {"bound": "hbm", "kernel": "ov_search_kernel", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": ach_gbs / hbm_peak, "traffic": None, "peak_kind": peak_kind + " STREAM copy",
+                     "frac": ach_gbs / hbm_peak,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch (mode 0 of 4) at full cfg2 size,
+                     # ncu --set full capture profiles/r1c_prof_search.raw.csv; its algorithmic bytes are 89.5 GB
+                     "traffic": 42.14e9 if args.scale == 1.0 else None, "traffic_source": "profiles/r1c_summary.md",
+                     "launches_per_step": search_launches / args.steps,
+                     "algorithmic_bytes_per_launch": look_s * 128 / max(search_launches, 1),
+                     "peak_kind": peak_kind + " STREAM copy",
                      "lookups_per_read": look_s / args.steps / n_reads, "lookups_per_s": look_s / args.steps / search_s if search_s else 0,
                      "random_gather_128B_per_s": gather,
                      "frac_of_random_gather": (look_s / args.steps / search_s) / gather if gather and search_s else None,

@@ -129,11 +129,13 @@ def _ptr(a):
 class IndexResult:
     """Run bytes + read-start order of one index (what the .bwt / .sai files are written from)."""
 
-    def __init__(self, o):
+    def __init__(self, o, copy=True):
         self.n_strings = int(o.n_strings)
         self.n_suffixes = int(o.n_suffixes)
-        self.runs = np.ctypeslib.as_array(o.rle, shape=(max(int(o.n_runs), 1),))[:int(o.n_runs)].copy()
-        self.sai = np.ctypeslib.as_array(o.sai, shape=(self.n_strings,)).copy()
+        self.runs = np.ctypeslib.as_array(o.rle, shape=(max(int(o.n_runs), 1),))[:int(o.n_runs)]
+        self.sai = np.ctypeslib.as_array(o.sai, shape=(self.n_strings,))
+        if copy:  # otherwise views of the library's pinned output buffers, valid until free_index()
+            self.runs, self.sai = self.runs.copy(), self.sai.copy()
         self.stats = dict(ms_total=o.ms_total, ms_sort=o.ms_sort, ms_bcr=o.ms_bcr, ms_emit=o.ms_emit,
                           launches=int(o.launches), merge_launches=int(o.merge_launches), ms_merge=o.ms_merge,
                           merge_bytes=int(o.merge_bytes))
@@ -231,12 +233,24 @@ class Context:
         self.lib.sgx_reads_free(r)
 
     # ---- index
-    def index_build(self, reads, order=ORDER_SAIS2, reversed=False):
+    def index_build(self, reads, order=ORDER_SAIS2, reversed=False, copy=True):
         o = _IndexOut()
         self._check(self.lib.sgx_index_build(self.h, reads, int(order), 1 if reversed else 0, ctypes.byref(o)))
-        res = IndexResult(o)
-        self.lib.sgx_index_out_free(ctypes.byref(o))
+        return self._index_result(o, copy)
+
+    def _index_result(self, o, copy):
+        res = IndexResult(o, copy=copy)
+        if copy:
+            self.lib.sgx_index_out_free(ctypes.byref(o))
+        else:
+            res._raw = o  # caller releases with free_index
         return res
+
+    def free_index(self, res):
+        if getattr(res, "_raw", None) is not None:
+            self.lib.sgx_index_out_free(ctypes.byref(res._raw))
+            res._raw = None
+            res.runs = res.sai = None
 
     # ---- multi-GPU index
     def comm_unique_id(self):
@@ -263,7 +277,7 @@ class Context:
     def free_comm(self, c):
         self.lib.sgx_comm_free(c)
 
-    def index_build_sharded(self, comm, reads, order=ORDER_SAIS2, reversed=False):
+    def index_build_sharded(self, comm, reads, order=ORDER_SAIS2, reversed=False, copy=True):
         """Collective bucket-sharded build; `runs` is complete on rank 0 only, `sai` everywhere."""
         o = _IndexOut()
         self._check(self.lib.sgx_index_build_sharded(self.h, comm, reads, int(order), 1 if reversed else 0, ctypes.byref(o)))
@@ -271,9 +285,8 @@ class Context:
         n_runs = int(o.n_runs)
         if rank != 0:
             o.n_runs = 0
-        res = IndexResult(o)
+        res = self._index_result(o, copy)
         res.n_runs_total = n_runs
-        self.lib.sgx_index_out_free(ctypes.byref(o))
         return res
 
     # ---- FM-index

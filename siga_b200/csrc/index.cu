@@ -34,53 +34,55 @@ static void bcr_passes(sgx_ctx* ctx, const sgx_reads* reads, const ReadAcc& acc,
                        uint8_t** final_B, sgx_index_out* out, KernelClock& k_merge) {
   const uint64_t N = reads->n;
   const uint32_t lmax = reads->max_len;
-  const uint64_t nb_max = S / kBcrBlock + 2;
+  const uint32_t uniform_len = reads->min_len == lmax ? lmax : 0;
+  const uint64_t nt_max = S / kMergeTile + 2;
   DevBuf<uint32_t> ID0(N), ID1(N);
   DevBuf<PosT> NP0(N), NP1(N), tmpPos(N);
-  DevBuf<uint8_t> SYM(N), tmpC(N);
-  DevBuf<uint64_t> cnt(4 * nb_max), scan_ws(scan_ws_elems(4 * nb_max)), part_ws(part_ws_elems(N, 4)),
+  DevBuf<uint8_t> SYM0(N), SYM1(N);
+  DevBuf<uint2> blk(nt_max * 32);
+  DevBuf<uint64_t> tiletot(4 * nt_max), scan_ws(scan_ws_elems(4 * nt_max)), part_ws(part_ws_elems(N, 4)),
       tile_k0(S / kMergeTile + 4);
   uint32_t* ID = ID0.p;
   uint32_t* ID2 = ID1.p;
   PosT* NP = NP0.p;
   PosT* NP2 = NP1.p;
+  uint8_t* SYM = SYM0.p;
+  uint8_t* SYM2 = SYM1.p;
   uint8_t* B = B0;
   uint8_t* Bn = B1;
 
   uint64_t n_cur = N;
-  SGX_LAUNCH(ctx, (bcr_init_kernel<PosT>), grid_for((N + 1) / 2, 256), 256, 0, acc, d_sord, N, B, ID, NP);
-  uint64_t nb = n_cur / kBcrBlock + 1;
-  SGX_LAUNCH(ctx, sym_block_count_kernel, grid_for(nb * 32, 256), 256, 0, (const uint8_t*)B, n_cur, nb, cnt.p);
-  scan_exclusive(ctx, cnt.p, 4 * nb, scan_ws.p, (uint64_t*)nullptr);
+  SGX_LAUNCH(ctx, (bcr_init_kernel<PosT>), grid_for((N + 1) / 2, 256), 256, 0, acc, d_sord, N, B, ID, NP, SYM);
+  uint64_t nt = (n_cur + kMergeTile - 1) / kMergeTile;
+  SGX_LAUNCH(ctx, tile_count_kernel, (unsigned)nt, 256, 0, (const uint8_t*)B, n_cur, nt, blk.p, tiletot.p);
+  scan_exclusive(ctx, tiletot.p, 4 * nt, scan_ws.p, (uint64_t*)nullptr);
 
-  uint64_t nact_prev = N;  // items currently held in ID/NP (inserted by the previous pass)
+  uint64_t nact_prev = N;  // items currently held in ID/NP/SYM (inserted by the previous pass)
   for (uint32_t j = 1; j <= lmax; ++j) {
     const uint64_t nact = nact_by_pass[j];  // reads with length >= j
     if (nact == 0) break;
-    SGX_LAUNCH(ctx, (bcr_rank_kernel<PosT>), grid_for(nact_prev, 256), 256, 0, acc, (const uint8_t*)B,
-               (const uint64_t*)cnt.p, nb, N, (const uint32_t*)ID, (const PosT*)NP, nact_prev, j, tmpC.p, tmpPos.p);
-    BcrDigit dg{tmpC.p};
-    BcrMove<PosT> mv{acc, ID, tmpPos.p, j, ID2, NP2, SYM.p};
+    SGX_LAUNCH(ctx, (bcr_rank_kernel<PosT>), grid_for(nact_prev, 256), 256, 0, (const uint8_t*)B, (const uint2*)blk.p,
+               (const uint64_t*)tiletot.p, nt, N, (const uint8_t*)SYM, (const PosT*)NP, nact_prev, tmpPos.p);
+    SymDigit dg{SYM};
+    BcrMove<PosT> mv{acc, ID, tmpPos.p, j, uniform_len, ID2, NP2, SYM2};
     partition_pass<4>(ctx, dg, mv, nact_prev, part_ws.p, (uint64_t*)nullptr);
     const uint64_t n_new = n_cur + nact;
     const uint64_t ntiles = (n_new + kMergeTile - 1) / kMergeTile;
     SGX_LAUNCH(ctx, (bcr_tile_bounds_kernel<PosT>), grid_for(nact + 1, 256), 256, 0, (const PosT*)NP2, nact, ntiles,
                tile_k0.p);
-    const uint64_t nb_new = n_new / kBcrBlock + 1;
-    // the block past the last full one may not be touched by the merge when n_new is a multiple of 256
-    SGX_CUDA(cudaMemsetAsync(cnt.p, 0, 4 * nb_new * sizeof(uint64_t), ctx->stream));
     k_merge.tick();
     SGX_LAUNCH(ctx, (bcr_merge_kernel<PosT>), (unsigned)ntiles, kMergeThreads, 0, (const uint8_t*)B, n_cur,
-               (const PosT*)NP2, (const uint8_t*)SYM.p, nact, (const uint64_t*)tile_k0.p, Bn, n_new, nb_new, cnt.p);
+               (const PosT*)NP2, (const uint8_t*)SYM2, nact, (const uint64_t*)tile_k0.p, Bn, n_new, ntiles, blk.p, tiletot.p);
     k_merge.tick();
     out->merge_launches++;
     out->merge_bytes += (n_cur + n_new) / 2 + nact * (sizeof(PosT) + 1);
-    scan_exclusive(ctx, cnt.p, 4 * nb_new, scan_ws.p, (uint64_t*)nullptr);
+    scan_exclusive(ctx, tiletot.p, 4 * ntiles, scan_ws.p, (uint64_t*)nullptr);
     std::swap(B, Bn);
     std::swap(ID, ID2);
     std::swap(NP, NP2);
+    std::swap(SYM, SYM2);
     n_cur = n_new;
-    nb = nb_new;
+    nt = ntiles;
     nact_prev = nact;
   }
   SGX_REQUIRE(n_cur == S, SGX_ECUDA, "index: column passes did not produce n_suffixes rows");

@@ -134,7 +134,7 @@ __device__ __forceinline__ uint32_t nib_get(const uint8_t* __restrict__ B, uint6
 // sentinel row is the last base of its read.
 template <class PosT>
 __global__ void bcr_init_kernel(ReadAcc acc, const uint32_t* __restrict__ sord, uint64_t n, uint8_t* __restrict__ B,
-                                uint32_t* __restrict__ ID, PosT* __restrict__ NP) {
+                                uint32_t* __restrict__ ID, PosT* __restrict__ NP, uint8_t* __restrict__ SYM) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t k = 2 * i;
   if (k >= n) return;
@@ -143,9 +143,11 @@ __global__ void bcr_init_kernel(ReadAcc acc, const uint32_t* __restrict__ sord, 
     if (k + h < n) {
       const uint32_t id = sord[k + h];
       const uint32_t l = acc.rv.len[id];
-      byte |= (acc.code(id, l - 1, l) + 1) << (4 * h);
+      const uint32_t sym = acc.code(id, l - 1, l) + 1;
+      byte |= sym << (4 * h);
       ID[k + h] = id;
       NP[k + h] = (PosT)(k + h);
+      SYM[k + h] = (uint8_t)sym;  // the symbol of a row is also the first base of the suffix inserted from it
     }
   }
   B[i] = (uint8_t)byte;
@@ -166,32 +168,72 @@ __device__ __forceinline__ uint32_t nib_sum(uint32_t acc) {
   return (v * 0x01010101u) >> 24;
 }
 
-// Per-256-row counts of A,C,G,T of a nibble-packed symbol array: cnt[c*nb + b].  One warp per block, one word per lane.
-static __global__ void __launch_bounds__(256) sym_block_count_kernel(const uint8_t* __restrict__ B, uint64_t n, uint64_t nb,
-                                                              uint64_t* __restrict__ cnt) {
-  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= nb) return;
-  const uint64_t row0 = warp * kBcrBlock + (uint64_t)lane * 8;
-  uint32_t a = 0, c = 0, g = 0, t = 0;
-  if (row0 < n) {
-    const uint32_t w = *reinterpret_cast<const uint32_t*>(B + row0 / 2);  // the array is padded
-    const uint64_t left = n - row0;
-    const uint32_t keep = left >= 8 ? 0x11111111u : (0x11111111u & ((1u << (4 * (uint32_t)left)) - 1u));
-    nib_count_add(w, keep, a, c, g, t);
-  }
-  uint32_t w1 = nib_sum(a) | (nib_sum(c) << 16), w2 = nib_sum(g) | (nib_sum(t) << 16);
+// Rank checkpoints of a nibble-packed symbol array, two levels:
+//   blk[b]             per 256-row block: A | C<<16 , G | T<<16 counts of the rows of its 8192-row tile BEFORE the block
+//   tiletot[c*nt + t]  per tile: number of symbol c in tile t (A,C,G,T = c 0..3); the caller's exclusive scan of the
+//                      flattened [4][nt] array turns it into (#symbols < c) + (#c before tile t)
+// so that rank_c(row) = scanned[c*nt + row/8192] + field_c(blk[row/256]) + (#c in the block before the row), and only
+// nt = rows/8192 values per symbol are scanned per column pass.
+// Called by all 256 threads of a CTA that holds one tile, thread i owning rows [32 i, 32 i + 32) as four words whose
+// nibbles past the end of the array are zero.
+__device__ __forceinline__ void tile_checkpoints(const uint32_t out[4], uint64_t tile, uint64_t ntiles, uint32_t* sh_w /* 64 */,
+                                                 uint2* __restrict__ blk, uint64_t* __restrict__ tiletot) {
+  uint32_t accA = 0, accC = 0, accG = 0, accT = 0;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    w1 += __shfl_xor_sync(0xffffffffu, w1, o);
-    w2 += __shfl_xor_sync(0xffffffffu, w2, o);
+  for (int i = 0; i < 4; ++i) nib_count_add(out[i], 0x11111111u, accA, accC, accG, accT);
+  uint32_t w1 = nib_sum(accA) | (nib_sum(accC) << 16), w2 = nib_sum(accG) | (nib_sum(accT) << 16);
+#pragma unroll
+  for (int oo = 4; oo > 0; oo >>= 1) {  // 256-row block = 8 consecutive threads
+    w1 += __shfl_xor_sync(0xffffffffu, w1, oo);
+    w2 += __shfl_xor_sync(0xffffffffu, w2, oo);
   }
-  if (lane == 0) {
-    cnt[0 * nb + warp] = w1 & 0xffffu;
-    cnt[1 * nb + warp] = w1 >> 16;
-    cnt[2 * nb + warp] = w2 & 0xffffu;
-    cnt[3 * nb + warp] = w2 >> 16;
+  if ((threadIdx.x & 7) == 0) {
+    sh_w[threadIdx.x >> 3] = w1;
+    sh_w[32 + (threadIdx.x >> 3)] = w2;
   }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    const uint32_t v1 = sh_w[lane], v2 = sh_w[32 + lane];
+    uint32_t x1 = v1, x2 = v2;  // packed 16-bit fields: a tile holds at most 8192 of one symbol
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y1 = __shfl_up_sync(0xffffffffu, x1, o), y2 = __shfl_up_sync(0xffffffffu, x2, o);
+      if (lane >= o) {
+        x1 += y1;
+        x2 += y2;
+      }
+    }
+    blk[tile * 32 + lane] = make_uint2(x1 - v1, x2 - v2);
+    if (lane == 31) {
+      tiletot[0 * ntiles + tile] = x1 & 0xffffu;
+      tiletot[1 * ntiles + tile] = x1 >> 16;
+      tiletot[2 * ntiles + tile] = x2 & 0xffffu;
+      tiletot[3 * ntiles + tile] = x2 >> 16;
+    }
+  }
+}
+
+// Checkpoints of an existing array (the first BWT of the column passes): one CTA per 8192-row tile.
+static __global__ void __launch_bounds__(256) tile_count_kernel(const uint8_t* __restrict__ B, uint64_t n, uint64_t ntiles,
+                                                               uint2* __restrict__ blk, uint64_t* __restrict__ tiletot) {
+  __shared__ uint32_t sh_w[64];
+  const uint64_t row0 = (uint64_t)blockIdx.x * 8192 + (uint64_t)threadIdx.x * 32;
+  uint32_t out[4] = {0, 0, 0, 0};
+  if (row0 < n) {
+    const uint4 v = *reinterpret_cast<const uint4*>(B + row0 / 2);  // the array is padded
+    out[0] = v.x;
+    out[1] = v.y;
+    out[2] = v.z;
+    out[3] = v.w;
+    const uint32_t valid = (uint32_t)min((uint64_t)32, n - row0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t vw = valid >= 8u * (i + 1) ? 8u : (valid > 8u * i ? valid - 8u * i : 0u);
+      out[i] &= vw >= 8 ? 0xffffffffu : ((1u << (4 * vw)) - 1u);
+    }
+  }
+  tile_checkpoints(out, blockIdx.x, ntiles, sh_w, blk, tiletot);
 }
 
 // number of nibbles equal to the pattern's nibble among the first `nn` (<= 8) nibbles of w
@@ -204,46 +246,62 @@ __device__ __forceinline__ uint32_t nib_eq_count(uint32_t w, uint32_t pat, uint3
   return (uint32_t)__popc(eq & m);
 }
 
-// For every active read (in current row order): the symbol c that starts its next suffix and the row that suffix
-// takes in the next BWT:  N + (#symbols < c in B) + (#c in B[0..P)).
-//   scanned = exclusive scan of the flattened [4][nb] block counts, so scanned[c*nb + b] already equals
-//   (#symbols < c in B) + (#c before block b).
-template <class PosT>
-__global__ void __launch_bounds__(256) bcr_rank_kernel(ReadAcc acc, const uint8_t* __restrict__ B, const uint64_t* __restrict__ scanned,
-                                                       uint64_t nb, uint64_t n_reads, const uint32_t* __restrict__ ID,
-                                                       const PosT* __restrict__ NP, uint64_t nact, uint32_t j,
-                                                       uint8_t* __restrict__ tmpC, PosT* __restrict__ tmpPos) {
-  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= nact) return;
-  const uint32_t id = ID[k];
-  const uint32_t l = acc.rv.len[id];
-  if (l < j) {
-    tmpC[k] = 255;  // finished in the previous pass: dropped
-    return;
+// Number of nibbles equal to symbol `sym` (1..4) among the first r rows of 256-row block b.  One thread reads the
+// block's vectors it needs (those holding rows < r) with all loads issued before the first use: the kernels built on
+// this are latency-bound, what counts is independent loads in flight per thread times threads per SM.
+__device__ __forceinline__ uint32_t block_rank(const uint8_t* __restrict__ B, uint64_t b, uint32_t r, uint32_t sym) {
+  const uint4* v = reinterpret_cast<const uint4*>(B + b * (kBcrBlock / 2));
+  uint4 x[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) x[q] = (sym && r > 32u * q) ? __ldg(v + q) : make_uint4(0, 0, 0, 0);
+  const uint32_t pat = sym * 0x11111111u;
+  uint32_t cnt = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    if (r > 32u * q) {
+      const uint32_t left = r - 32u * q;
+      cnt += nib_eq_count(x[q].x, pat, left);
+      if (left > 8) cnt += nib_eq_count(x[q].y, pat, left - 8);
+      if (left > 16) cnt += nib_eq_count(x[q].z, pat, left - 16);
+      if (left > 24) cnt += nib_eq_count(x[q].w, pat, left - 24);
+    }
   }
-  const uint32_t c = acc.code(id, l - j, l);
-  const uint64_t P = (uint64_t)NP[k];
-  const uint64_t b = P / kBcrBlock;
-  const uint32_t r = (uint32_t)(P - b * kBcrBlock);  // rows of this block before P
-  const uint32_t pat = (c + 1) * 0x11111111u;
-  uint32_t inblk = 0;
-  const uint4* v = reinterpret_cast<const uint4*>(B + b * (kBcrBlock / 2));  // 128 bytes per block
-  const uint32_t nvec = (r + 31) / 32;
-  for (uint32_t q = 0; q < nvec; ++q) {
-    const uint4 x = v[q];
-    const uint32_t left = r - q * 32;  // nibbles of this vector that count (may exceed 32)
-    inblk += nib_eq_count(x.x, pat, left);
-    if (left > 8) inblk += nib_eq_count(x.y, pat, left - 8);
-    if (left > 16) inblk += nib_eq_count(x.z, pat, left - 16);
-    if (left > 24) inblk += nib_eq_count(x.w, pat, left - 24);
-  }
-  tmpC[k] = (uint8_t)c;
-  tmpPos[k] = (PosT)(n_reads + scanned[(uint64_t)c * nb + b] + inblk);
+  return sym ? cnt : 0;
+}
+__device__ __forceinline__ uint32_t blk_field(uint2 v, uint32_t c) {
+  const uint32_t w = c < 2 ? v.x : v.y;
+  return (c & 1) ? (w >> 16) : (w & 0xffffu);
 }
 
-struct BcrDigit {
-  const uint8_t* tmpC;
-  __device__ __forceinline__ int operator()(uint64_t k) const { return (int)tmpC[k]; }
+// For every active item (in current row order) the row its next suffix takes in the next BWT:
+//   base + (#symbols < c in B) + (#c in B[0..P))      with c = SYM[k] - 1 the base that precedes the item's suffix
+// (SYM, the symbol the item's row holds, was computed when the row was inserted; 0 = the read has ended: no insert).
+// No access to the read store; two dependent memory round trips per item: (SYM, NP) -> (block vectors, checkpoints).
+template <class PosT>
+__global__ void __launch_bounds__(256) bcr_rank_kernel(const uint8_t* __restrict__ B, const uint2* __restrict__ blk,
+                                                       const uint64_t* __restrict__ scanned, uint64_t ntiles, uint64_t base,
+                                                       const uint8_t* __restrict__ SYM, const PosT* __restrict__ NP,
+                                                       uint64_t nact, PosT* __restrict__ tmpPos) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nact) return;
+  const uint32_t sym = (uint32_t)SYM[k];
+  if (!sym) return;
+  const uint64_t P = (uint64_t)NP[k];
+  const uint64_t b = P / kBcrBlock;
+  const uint32_t c = sym - 1;
+  const uint2 bv = __ldg(blk + b);
+  const uint64_t sc = __ldg(scanned + (uint64_t)c * ntiles + (b >> 5));
+  const uint32_t inblk = block_rank(B, b, (uint32_t)(P - b * kBcrBlock), sym);
+  tmpPos[k] = (PosT)(base + sc + blk_field(bv, c) + inblk);
+}
+
+// partition digit of the column passes: the symbol the insert starts with; ended reads (SYM 0) are dropped
+struct SymDigit {
+  const uint8_t* SYM;
+  __device__ __forceinline__ int operator()(uint64_t k) const {
+    const int s = (int)SYM[k];
+    return s ? s - 1 : 255;
+  }
 };
 template <class PosT>
 struct BcrMove {
@@ -251,12 +309,13 @@ struct BcrMove {
   const uint32_t* ID;
   const PosT* tmpPos;
   uint32_t j;
+  uint32_t uniform_len;  // != 0: every read has this length (no gather of len[])
   uint32_t* ID2;
   PosT* NP2;
   uint8_t* SYM2;
   __device__ __forceinline__ void operator()(uint64_t k, uint64_t dest) const {
     const uint32_t id = ID[k];
-    const uint32_t l = acc.rv.len[id];
+    const uint32_t l = uniform_len ? uniform_len : acc.rv.len[id];
     ID2[dest] = id;
     NP2[dest] = tmpPos[k];
     SYM2[dest] = (l == j) ? (uint8_t)0 : (uint8_t)(acc.code(id, l - j - 1, l) + 1);
@@ -285,8 +344,8 @@ template <class PosT>
 __global__ void __launch_bounds__(kMergeThreads) bcr_merge_kernel(const uint8_t* __restrict__ Bo, uint64_t n_old,
                                                                   const PosT* __restrict__ NP, const uint8_t* __restrict__ SYM,
                                                                   uint64_t nact, const uint64_t* __restrict__ tile_k0,
-                                                                  uint8_t* __restrict__ Bn, uint64_t n_new, uint64_t nb,
-                                                                  uint64_t* __restrict__ cnt) {
+                                                                  uint8_t* __restrict__ Bn, uint64_t n_new, uint64_t ntiles,
+                                                                  uint2* __restrict__ blk, uint64_t* __restrict__ tiletot) {
   __shared__ __align__(16) uint32_t oldw[kMergeTile / 8 + 16];
   __shared__ uint32_t mask[kMergeTile / 32];
   __shared__ uint64_t sh[9];
@@ -345,31 +404,14 @@ __global__ void __launch_bounds__(kMergeThreads) bcr_merge_kernel(const uint8_t*
   // rows past the end of the array stay zero
   const uint64_t row0 = t0 + (uint64_t)threadIdx.x * 32;
   uint32_t valid = row0 >= t1 ? 0u : (uint32_t)min((uint64_t)32, t1 - row0);
-  uint32_t accA = 0, accC = 0, accG = 0, accT = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const uint32_t vw = valid >= 8u * (i + 1) ? 8u : (valid > 8u * i ? valid - 8u * i : 0u);
-    const uint32_t km = vw >= 8 ? 0xffffffffu : ((1u << (4 * vw)) - 1u);
-    out[i] &= km;
-    nib_count_add(out[i], 0x11111111u, accA, accC, accG, accT);
+    out[i] &= vw >= 8 ? 0xffffffffu : ((1u << (4 * vw)) - 1u);
   }
   if (valid) *reinterpret_cast<uint4*>(Bn + row0 / 2) = make_uint4(out[0], out[1], out[2], out[3]);
-  // 256-row block = 8 consecutive threads
-  uint32_t w1 = nib_sum(accA) | (nib_sum(accC) << 16), w2 = nib_sum(accG) | (nib_sum(accT) << 16);
-#pragma unroll
-  for (int oo = 4; oo > 0; oo >>= 1) {
-    w1 += __shfl_xor_sync(0xffffffffu, w1, oo);
-    w2 += __shfl_xor_sync(0xffffffffu, w2, oo);
-  }
-  if ((threadIdx.x & 7) == 0) {
-    const uint64_t b = row0 / kBcrBlock;
-    if (b < nb) {
-      cnt[0 * nb + b] = w1 & 0xffffu;
-      cnt[1 * nb + b] = w1 >> 16;
-      cnt[2 * nb + b] = w2 & 0xffffu;
-      cnt[3 * nb + b] = w2 >> 16;
-    }
-  }
+  __syncthreads();  // everyone is done with mask[] / oldw[]: reuse mask[] for the checkpoint scan
+  tile_checkpoints(out, blockIdx.x, ntiles, mask, blk, tiletot);
 }
 
 // ---- 3. run-length encoding ------------------------------------------------------------------------------------------

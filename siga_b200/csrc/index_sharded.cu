@@ -105,37 +105,29 @@ static __global__ void __launch_bounds__(256) shard_rows_kernel(ReadAcc acc, uin
 // Column pass, sender side: for every suffix inserted here by the previous pass, the destination shard of the suffix
 // one base longer and the sender-local part of its row: (#symbols < c in my rows) + (#c in my rows before mine).
 template <class PosT>
-__global__ void __launch_bounds__(256) shard_rank_kernel(ReadAcc acc, const uint8_t* __restrict__ B,
-                                                         const uint64_t* __restrict__ scanned, uint64_t nb, ShardBounds bounds,
-                                                         const uint32_t* __restrict__ ID, const PosT* __restrict__ NP,
+__global__ void __launch_bounds__(256) shard_rank_kernel(ReadAcc acc, const uint8_t* __restrict__ B, const uint2* __restrict__ blk,
+                                                         const uint64_t* __restrict__ scanned, uint64_t ntiles, ShardBounds bounds,
+                                                         uint32_t uniform_len, const uint32_t* __restrict__ ID,
+                                                         const PosT* __restrict__ NP, const uint8_t* __restrict__ SYM,
                                                          uint64_t held, uint32_t j, uint8_t* __restrict__ tmpDest,
                                                          PosT* __restrict__ tmpPos) {
   const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= held) return;
-  const uint32_t id = ID[k];
-  const uint32_t l = acc.rv.len[id];
-  if (l < j) {
-    tmpDest[k] = 255;  // the read ended in the previous pass
+  const uint32_t sym = (uint32_t)SYM[k];  // 0: the read ended in the previous pass
+  if (!sym) {
+    tmpDest[k] = 255;
     return;
   }
-  const uint32_t c = acc.code(id, l - j, l);
   const uint64_t P = (uint64_t)NP[k];
+  const uint32_t id = ID[k];
   const uint64_t b = P / kBcrBlock;
-  const uint32_t r = (uint32_t)(P - b * kBcrBlock);
-  const uint32_t pat = (c + 1) * 0x11111111u;
-  uint32_t inblk = 0;
-  const uint4* v = reinterpret_cast<const uint4*>(B + b * (kBcrBlock / 2));
-  const uint32_t nvec = (r + 31) / 32;
-  for (uint32_t q = 0; q < nvec; ++q) {
-    const uint4 x = v[q];
-    const uint32_t left = r - q * 32;
-    inblk += nib_eq_count(x.x, pat, left);
-    if (left > 8) inblk += nib_eq_count(x.y, pat, left - 8);
-    if (left > 16) inblk += nib_eq_count(x.z, pat, left - 16);
-    if (left > 24) inblk += nib_eq_count(x.w, pat, left - 24);
-  }
+  const uint32_t c = sym - 1;
+  const uint2 bv = __ldg(blk + b);
+  const uint64_t sc = __ldg(scanned + (uint64_t)c * ntiles + (b >> 5));
+  const uint32_t inblk = block_rank(B, b, (uint32_t)(P - b * kBcrBlock), sym);
+  const uint32_t l = uniform_len ? uniform_len : acc.rv.len[id];
   tmpDest[k] = (uint8_t)bounds.owner(suffix_key(acc, id, l - j, l));
-  tmpPos[k] = (PosT)(scanned[(uint64_t)c * nb + b] + inblk);
+  tmpPos[k] = (PosT)(sc + blk_field(bv, c) + inblk);
 }
 
 // One insert on the wire: the sender-local rank part and the read.
@@ -163,23 +155,23 @@ struct SendMove {
 };
 
 // meta[d] = items for shard d (d < kMaxShards), meta[kMaxShards + c] = number of symbol c in my rows.
-//   bucket_start: the partition workspace after its scan (bucket d starts at bucket_start[d * ntiles]); total = items kept.
-static __global__ void shard_meta_kernel(const uint64_t* __restrict__ bucket_start, uint32_t ntiles, int have_items,
-                                         const uint64_t* __restrict__ kept, const uint64_t* __restrict__ scanned, uint64_t nb,
+//   bucket_start: the partition workspace after its scan (bucket d starts at bucket_start[d * ptiles]); total = items kept.
+static __global__ void shard_meta_kernel(const uint64_t* __restrict__ bucket_start, uint32_t ptiles, int have_items,
+                                         const uint64_t* __restrict__ kept, const uint64_t* __restrict__ scanned, uint64_t ntiles,
                                          const uint64_t* __restrict__ sym_total, uint64_t* __restrict__ meta) {
   const int t = threadIdx.x;
   if (t < kMaxShards) {
     uint64_t c = 0;
     if (have_items) {
-      const uint64_t a = bucket_start[(uint64_t)t * ntiles];
-      const uint64_t e = t + 1 < kMaxShards ? bucket_start[(uint64_t)(t + 1) * ntiles] : *kept;
+      const uint64_t a = bucket_start[(uint64_t)t * ptiles];
+      const uint64_t e = t + 1 < kMaxShards ? bucket_start[(uint64_t)(t + 1) * ptiles] : *kept;
       c = e - a;
     }
     meta[t] = c;
   } else if (t < kMaxShards + 4) {
     const int c = t - kMaxShards;
-    const uint64_t e = c < 3 ? scanned[(uint64_t)(c + 1) * nb] : *sym_total;
-    meta[t] = e - scanned[(uint64_t)c * nb];
+    const uint64_t e = c < 3 ? scanned[(uint64_t)(c + 1) * ntiles] : *sym_total;
+    meta[t] = e - scanned[(uint64_t)c * ntiles];
   }
 }
 
@@ -205,6 +197,7 @@ struct RecvMove {
   ReadAcc acc;
   const WireItem<PosT>* recv;
   uint32_t j;
+  uint32_t uniform_len;
   RecvFix fix;
   uint32_t* ID2;
   PosT* NP2;
@@ -212,7 +205,7 @@ struct RecvMove {
   __device__ __forceinline__ void operator()(uint64_t k, uint64_t dest) const {
     const WireItem<PosT> w = recv[k];
     const uint32_t id = w.id;
-    const uint32_t l = acc.rv.len[id];
+    const uint32_t l = uniform_len ? uniform_len : acc.rv.len[id];
     const uint32_t c = acc.code(id, l - j, l);
     int s = 0;
 #pragma unroll
@@ -231,14 +224,15 @@ struct Shard {
   DevBuf<uint32_t> ID0, ID1;
   DevBuf<PosT> NP0, NP1, tmpPos;
   DevBuf<WireItem<PosT> > send, recv;
-  DevBuf<uint64_t> cnt, scan_ws, part_ws, tile_k0, meta, kept, sym_total;
+  DevBuf<uint2> blk;
+  DevBuf<uint64_t> tiletot, scan_ws, part_ws, tile_k0, meta, kept, sym_total;
   uint8_t* B = nullptr;
   uint8_t* Bn = nullptr;
   uint32_t* ID = nullptr;
   uint32_t* ID2 = nullptr;
   PosT* NP = nullptr;
   PosT* NP2 = nullptr;
-  uint64_t n_cur = 0, nb = 1, held = 0;
+  uint64_t n_cur = 0, nt = 1, held = 0;
   RleSegment seg;
   DevBuf<uint8_t> rle;
   uint64_t rle_bytes = 0;
@@ -258,9 +252,10 @@ struct Shard {
     NP0.alloc(N);
     NP1.alloc(N);
     tmpPos.alloc(N);
-    const uint64_t nb_max = rows_final / kBcrBlock + 2;
-    cnt.alloc(4 * nb_max);
-    scan_ws.alloc(scan_ws_elems(4 * nb_max));
+    const uint64_t nt_max = rows_final / kMergeTile + 2;
+    blk.alloc(nt_max * 32);
+    tiletot.alloc(4 * nt_max);
+    scan_ws.alloc(scan_ws_elems(4 * nt_max));
     part_ws.alloc(std::max(part_ws_elems(N, kMaxShards), part_ws_elems(N, 4)));
     tile_k0.alloc(rows_final / kMergeTile + 4);
     meta.alloc(kMetaN);
@@ -281,6 +276,7 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
                           KernelClock& k_merge, EventTimer& t_bcr, EventTimer& t_emit, uint8_t** rle_host, uint64_t* rle_total) {
   const uint64_t N = reads->n;
   const uint32_t lmax = reads->max_len;
+  const uint32_t uniform_len = reads->min_len == lmax ? lmax : 0;
   const int W = cm->world;
   const int nl = cm->n_local();
   std::vector<Shard<PosT> > sh(nl);
@@ -297,13 +293,13 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
   for (int li = 0; li < nl; ++li) {
     Shard<PosT>& s = sh[li];
     if (s.g == 0) {
-      SGX_LAUNCH(ctx, (bcr_init_kernel<PosT>), grid_for((N + 1) / 2, 256), 256, 0, acc, d_sord, N, s.B, s.ID, s.NP);
+      SGX_LAUNCH(ctx, (bcr_init_kernel<PosT>), grid_for((N + 1) / 2, 256), 256, 0, acc, d_sord, N, s.B, s.ID, s.NP, s.SYM.p);
       s.n_cur = N;
       s.held = N;
     }
-    s.nb = s.n_cur / kBcrBlock + 1;
-    SGX_LAUNCH(ctx, sym_block_count_kernel, grid_for(s.nb * 32, 256), 256, 0, (const uint8_t*)s.B, s.n_cur, s.nb, s.cnt.p);
-    scan_exclusive(ctx, s.cnt.p, 4 * s.nb, s.scan_ws.p, s.sym_total.p);
+    s.nt = std::max<uint64_t>(1, (s.n_cur + kMergeTile - 1) / kMergeTile);
+    SGX_LAUNCH(ctx, tile_count_kernel, (unsigned)s.nt, 256, 0, (const uint8_t*)s.B, s.n_cur, s.nt, s.blk.p, s.tiletot.p);
+    scan_exclusive(ctx, s.tiletot.p, 4 * s.nt, s.scan_ws.p, s.sym_total.p);
   }
 
   // SGX_SHARD_TRACE=1: device time per phase of the column passes, printed to stderr (diagnostics only)
@@ -325,14 +321,14 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
       uint32_t ntiles = 1;
       if (s.held) {
         SGX_LAUNCH(ctx, (shard_rank_kernel<PosT>), grid_for(s.held, 256), 256, 0, acc, (const uint8_t*)s.B,
-                   (const uint64_t*)s.cnt.p, s.nb, bounds, (const uint32_t*)s.ID, (const PosT*)s.NP, s.held, j, s.tmpDest.p,
-                   s.tmpPos.p);
+                   (const uint2*)s.blk.p, (const uint64_t*)s.tiletot.p, s.nt, bounds, uniform_len, (const uint32_t*)s.ID,
+                   (const PosT*)s.NP, (const uint8_t*)s.SYM.p, s.held, j, s.tmpDest.p, s.tmpPos.p);
         DestDigit dg{s.tmpDest.p};
         partition_count<kMaxShards, DestDigit>(ctx, dg, s.held, s.part_ws.p, s.kept.p);
         ntiles = part_tiles(s.held);
       }
       SGX_LAUNCH(ctx, shard_meta_kernel, 1, 32, 0, (const uint64_t*)s.part_ws.p, ntiles, s.held ? 1 : 0,
-                 (const uint64_t*)s.kept.p, (const uint64_t*)s.cnt.p, s.nb, (const uint64_t*)s.sym_total.p, s.meta.p);
+                 (const uint64_t*)s.kept.p, (const uint64_t*)s.tiletot.p, s.nt, (const uint64_t*)s.sym_total.p, s.meta.p);
       meta_ptr[li] = s.meta.p;
     }
     SGX_TRACE_TICK(k_send);
@@ -405,27 +401,25 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
           less_global += (long long)T[c];
         }
         RecvDigit<PosT> dg{acc, s.recv.p, j};
-        RecvMove<PosT> mv{acc, s.recv.p, j, fix, s.ID2, s.NP2, s.SYM.p};
+        RecvMove<PosT> mv{acc, s.recv.p, j, uniform_len, fix, s.ID2, s.NP2, s.SYM.p};
         partition_pass<4>(ctx, dg, mv, held_new, s.part_ws.p, (uint64_t*)nullptr);
         const uint64_t rows_new = s.n_cur + held_new;
         const uint64_t ntiles = (rows_new + kMergeTile - 1) / kMergeTile;
         SGX_LAUNCH(ctx, (bcr_tile_bounds_kernel<PosT>), grid_for(held_new + 1, 256), 256, 0, (const PosT*)s.NP2, held_new,
                    ntiles, s.tile_k0.p);
-        const uint64_t nb_new = rows_new / kBcrBlock + 1;
-        SGX_CUDA(cudaMemsetAsync(s.cnt.p, 0, 4 * nb_new * sizeof(uint64_t), ctx->stream));
         k_merge.tick();
         SGX_LAUNCH(ctx, (bcr_merge_kernel<PosT>), (unsigned)ntiles, kMergeThreads, 0, (const uint8_t*)s.B, s.n_cur,
-                   (const PosT*)s.NP2, (const uint8_t*)s.SYM.p, held_new, (const uint64_t*)s.tile_k0.p, s.Bn, rows_new, nb_new,
-                   s.cnt.p);
+                   (const PosT*)s.NP2, (const uint8_t*)s.SYM.p, held_new, (const uint64_t*)s.tile_k0.p, s.Bn, rows_new, ntiles,
+                   s.blk.p, s.tiletot.p);
         k_merge.tick();
         out->merge_launches++;
         out->merge_bytes += (s.n_cur + rows_new) / 2 + held_new * (sizeof(PosT) + 1);
-        scan_exclusive(ctx, s.cnt.p, 4 * nb_new, s.scan_ws.p, s.sym_total.p);
+        scan_exclusive(ctx, s.tiletot.p, 4 * ntiles, s.scan_ws.p, s.sym_total.p);
         std::swap(s.B, s.Bn);
         std::swap(s.ID, s.ID2);
         std::swap(s.NP, s.NP2);
         s.n_cur = rows_new;
-        s.nb = nb_new;
+        s.nt = ntiles;
       }
       // without inserts the rows and their scanned counts stay as they are
       s.held = held_new;
