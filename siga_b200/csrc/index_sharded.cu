@@ -12,12 +12,14 @@
 //   * Reads, the read-start order (.sai) and the sentinel order are replicated (N items; the heavy part is S rows).
 //   * Column pass j: every shard LF-maps the suffixes it inserted in pass j-1 through ITS rows (local rank of the
 //     preceding base c), finds the owner of the new suffix from its key, and partitions (id, local rank part) by
-//     destination shard.  One small all-gather carries the send counts and each shard's A/C/G/T totals; one
+//     (destination shard, c).  One small all-gather carries the send counts and each shard's A/C/G/T totals; one
 //     all-to-all carries the inserts.  The receiver turns the sender-local rank part into its own local row with a
 //     per-(sender, symbol) constant
 //         row = part + N + sum_{c'<c} T[c'] + sum_{s'<s} tot[s'][c] - sum_{c'<c} tot[s][c'] - first_row_of(receiver)
-//     and a stable 4-way partition by c of the sender-major receive buffer puts the inserts in row order (for one c
-//     the new row grows with the old global row, i.e. with (sender, sender row)).  Then the same streaming merge.
+//     The send partition is by (destination, c), so every sender's block arrives ordered by (c, sender row) and the
+//     receiver's row order -- for one c the new row grows with the old global row, i.e. with (sender, sender row) --
+//     is a permutation known from the gathered counts: one placement kernel, no counting pass.  Then the same
+//     streaming merge.
 //   * Run-length encoding per shard; a run crossing a seam belongs to the shard where it starts (run_length() in
 //     index_kernels.cuh), the segments are concatenated on shard 0.
 //
@@ -33,7 +35,8 @@ namespace sgx {
 static const int kKeySyms = 8;
 static const uint32_t kKeySpace = 390625;  // 5^8
 static const uint32_t kKeyTop = 78125;     // 5^7
-static const int kMetaN = kMaxShards + 4;  // per-shard values gathered every pass: send counts + A/C/G/T totals
+static const int kSendBuckets = kMaxShards * 4;  // (destination shard, first base of the new suffix)
+static const int kMetaN = kSendBuckets + 4;      // per-shard values gathered every pass: send counts + A/C/G/T totals
 
 struct ShardBounds {
   uint32_t b[kMaxShards + 1];
@@ -104,13 +107,15 @@ static __global__ void __launch_bounds__(256) shard_rows_kernel(ReadAcc acc, uin
 
 // Column pass, sender side: for every suffix inserted here by the previous pass, the destination shard of the suffix
 // one base longer and the sender-local part of its row: (#symbols < c in my rows) + (#c in my rows before mine).
+// The key of the new suffix is rolled from the key of the suffix it extends (c * 5^7 + key / 5), which travels with
+// the item, so the kernel does not touch the read store.
 template <class PosT>
-__global__ void __launch_bounds__(256) shard_rank_kernel(ReadAcc acc, const uint8_t* __restrict__ B, const uint2* __restrict__ blk,
+__global__ void __launch_bounds__(256) shard_rank_kernel(const uint8_t* __restrict__ B, const uint2* __restrict__ blk,
                                                          const uint64_t* __restrict__ scanned, uint64_t ntiles, ShardBounds bounds,
-                                                         uint32_t uniform_len, const uint32_t* __restrict__ ID,
                                                          const PosT* __restrict__ NP, const uint8_t* __restrict__ SYM,
-                                                         uint64_t held, uint32_t j, uint8_t* __restrict__ tmpDest,
-                                                         PosT* __restrict__ tmpPos) {
+                                                         const uint32_t* __restrict__ KEY, uint64_t held,
+                                                         uint8_t* __restrict__ tmpDest, PosT* __restrict__ tmpPos,
+                                                         uint32_t* __restrict__ tmpKey) {
   const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= held) return;
   const uint32_t sym = (uint32_t)SYM[k];  // 0: the read ended in the previous pass
@@ -119,22 +124,23 @@ __global__ void __launch_bounds__(256) shard_rank_kernel(ReadAcc acc, const uint
     return;
   }
   const uint64_t P = (uint64_t)NP[k];
-  const uint32_t id = ID[k];
+  const uint32_t key = sym * kKeyTop + KEY[k] / 5u;
   const uint64_t b = P / kBcrBlock;
   const uint32_t c = sym - 1;
   const uint2 bv = __ldg(blk + b);
   const uint64_t sc = __ldg(scanned + (uint64_t)c * ntiles + (b >> 5));
   const uint32_t inblk = block_rank(B, b, (uint32_t)(P - b * kBcrBlock), sym);
-  const uint32_t l = uniform_len ? uniform_len : acc.rv.len[id];
-  tmpDest[k] = (uint8_t)bounds.owner(suffix_key(acc, id, l - j, l));
+  tmpDest[k] = (uint8_t)(bounds.owner(key) * 4 + (int)c);  // send bucket: destination-major, then c
+  tmpKey[k] = key;
   tmpPos[k] = (PosT)(sc + blk_field(bv, c) + inblk);
 }
 
-// One insert on the wire: the sender-local rank part and the read.
+// One insert on the wire: the sender-local rank part, the read, the bucket key of the new suffix.
 template <class PosT>
 struct WireItem {
   PosT pos;
   uint32_t id;
+  uint32_t key;
 };
 
 struct DestDigit {
@@ -145,83 +151,80 @@ template <class PosT>
 struct SendMove {
   const uint32_t* ID;
   const PosT* tmpPos;
+  const uint32_t* tmpKey;
   WireItem<PosT>* send;
   __device__ __forceinline__ void operator()(uint64_t k, uint64_t dest) const {
     WireItem<PosT> w;
     w.pos = tmpPos[k];
     w.id = ID[k];
+    w.key = tmpKey[k];
     send[dest] = w;
   }
 };
 
-// meta[d] = items for shard d (d < kMaxShards), meta[kMaxShards + c] = number of symbol c in my rows.
-//   bucket_start: the partition workspace after its scan (bucket d starts at bucket_start[d * ptiles]); total = items kept.
+// meta[4 d + c] = items for shard d whose new suffix starts with c, meta[kSendBuckets + c] = symbol c in my rows.
+//   bucket_start: the partition workspace after its scan (bucket e starts at bucket_start[e * ptiles]); kept = items sent.
 static __global__ void shard_meta_kernel(const uint64_t* __restrict__ bucket_start, uint32_t ptiles, int have_items,
                                          const uint64_t* __restrict__ kept, const uint64_t* __restrict__ scanned, uint64_t ntiles,
                                          const uint64_t* __restrict__ sym_total, uint64_t* __restrict__ meta) {
   const int t = threadIdx.x;
-  if (t < kMaxShards) {
+  if (t < kSendBuckets) {
     uint64_t c = 0;
     if (have_items) {
       const uint64_t a = bucket_start[(uint64_t)t * ptiles];
-      const uint64_t e = t + 1 < kMaxShards ? bucket_start[(uint64_t)(t + 1) * ptiles] : *kept;
+      const uint64_t e = t + 1 < kSendBuckets ? bucket_start[(uint64_t)(t + 1) * ptiles] : *kept;
       c = e - a;
     }
     meta[t] = c;
-  } else if (t < kMaxShards + 4) {
-    const int c = t - kMaxShards;
+  } else if (t < kSendBuckets + 4) {
+    const int c = t - kSendBuckets;
     const uint64_t e = c < 3 ? scanned[(uint64_t)(c + 1) * ntiles] : *sym_total;
     meta[t] = e - scanned[(uint64_t)c * ntiles];
   }
 }
 
-// Receiver side: per-(sender, symbol) constants that turn the sender-local rank part into a local row.
-struct RecvFix {
-  long long K[kMaxShards][4];
-  uint64_t roff[kMaxShards + 1];  // first item of each sender in the receive buffer
+// Receiver side.  Every sender's block arrives ordered by (c, sender row), so the inserts of this shard in row order
+// are, for c = A..T, the (sender 0, c) run, the (sender 1, c) run, ...: a permutation known from the gathered counts.
+// Entry e = c * world + s of the plan: first output slot, first receive-buffer slot, and the constant that turns the
+// sender-local rank part into a local row.
+struct RecvPlan {
+  uint64_t out0[kSendBuckets + 1];  // non-decreasing; out0[entries] = number of inserts
+  uint64_t src0[kSendBuckets];
+  long long K[kSendBuckets];
+  int entries;
   int world;
 };
+
+// One thread per insert, in output (row) order: find its run, fetch the wire item, write id / local row / the symbol
+// its row holds (the base before the suffix, '$' when the read starts here).
 template <class PosT>
-struct RecvDigit {
-  ReadAcc acc;
-  const WireItem<PosT>* recv;
-  uint32_t j;
-  __device__ __forceinline__ int operator()(uint64_t k) const {
-    const uint32_t id = recv[k].id;
-    const uint32_t l = acc.rv.len[id];
-    return (int)acc.code(id, l - j, l);
+__global__ void __launch_bounds__(256) shard_place_kernel(ReadAcc acc, const WireItem<PosT>* __restrict__ recv, uint64_t n,
+                                                          uint32_t j, uint32_t uniform_len, RecvPlan plan,
+                                                          uint32_t* __restrict__ ID2, PosT* __restrict__ NP2,
+                                                          uint8_t* __restrict__ SYM2, uint32_t* __restrict__ KEY2) {
+  const uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= n) return;
+  int lo = 0, hi = plan.entries;  // last entry with out0 <= d
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (plan.out0[mid] <= d) lo = mid;
+    else hi = mid;
   }
-};
-template <class PosT>
-struct RecvMove {
-  ReadAcc acc;
-  const WireItem<PosT>* recv;
-  uint32_t j;
-  uint32_t uniform_len;
-  RecvFix fix;
-  uint32_t* ID2;
-  PosT* NP2;
-  uint8_t* SYM2;
-  __device__ __forceinline__ void operator()(uint64_t k, uint64_t dest) const {
-    const WireItem<PosT> w = recv[k];
-    const uint32_t id = w.id;
-    const uint32_t l = uniform_len ? uniform_len : acc.rv.len[id];
-    const uint32_t c = acc.code(id, l - j, l);
-    int s = 0;
-#pragma unroll
-    for (int i = 1; i < kMaxShards; ++i) s += (i < fix.world && k >= fix.roff[i]) ? 1 : 0;
-    ID2[dest] = id;
-    NP2[dest] = (PosT)((long long)w.pos + fix.K[s][c]);
-    SYM2[dest] = (l == j) ? (uint8_t)0 : (uint8_t)(acc.code(id, l - j - 1, l) + 1);
-  }
-};
+  const WireItem<PosT> w = recv[plan.src0[lo] + (d - plan.out0[lo])];
+  const uint32_t id = w.id;
+  const uint32_t l = uniform_len ? uniform_len : acc.rv.len[id];
+  ID2[d] = id;
+  NP2[d] = (PosT)((long long)w.pos + plan.K[lo]);
+  KEY2[d] = w.key;
+  SYM2[d] = (l == j) ? (uint8_t)0 : (uint8_t)(acc.code(id, l - j - 1, l) + 1);
+}
 
 template <class PosT>
 struct Shard {
   int g = 0;
   uint64_t rows_final = 0;
   DevBuf<uint8_t> B0, B1, SYM, tmpDest;
-  DevBuf<uint32_t> ID0, ID1;
+  DevBuf<uint32_t> ID0, ID1, KEY0, KEY1, tmpKey;
   DevBuf<PosT> NP0, NP1, tmpPos;
   DevBuf<WireItem<PosT> > send, recv;
   DevBuf<uint2> blk;
@@ -230,6 +233,8 @@ struct Shard {
   uint8_t* Bn = nullptr;
   uint32_t* ID = nullptr;
   uint32_t* ID2 = nullptr;
+  uint32_t* KEY = nullptr;
+  uint32_t* KEY2 = nullptr;
   PosT* NP = nullptr;
   PosT* NP2 = nullptr;
   uint64_t n_cur = 0, nt = 1, held = 0;
@@ -247,6 +252,10 @@ struct Shard {
     tmpDest.alloc(N);
     ID0.alloc(N);
     ID1.alloc(N);
+    KEY0.alloc(N);
+    KEY1.alloc(N);
+    tmpKey.alloc(N);
+    SGX_CUDA(cudaMemsetAsync(KEY0.p, 0, N * sizeof(uint32_t), ctx->stream));  // the sentinel rows: key of "$"
     send.alloc(N);
     recv.alloc(N);
     NP0.alloc(N);
@@ -256,7 +265,7 @@ struct Shard {
     blk.alloc(nt_max * 32);
     tiletot.alloc(4 * nt_max);
     scan_ws.alloc(scan_ws_elems(4 * nt_max));
-    part_ws.alloc(std::max(part_ws_elems(N, kMaxShards), part_ws_elems(N, 4)));
+    part_ws.alloc(part_ws_elems(N, kSendBuckets));
     tile_k0.alloc(rows_final / kMergeTile + 4);
     meta.alloc(kMetaN);
     kept.alloc(1);
@@ -265,6 +274,8 @@ struct Shard {
     Bn = B1.p;
     ID = ID0.p;
     ID2 = ID1.p;
+    KEY = KEY0.p;
+    KEY2 = KEY1.p;
     NP = NP0.p;
     NP2 = NP1.p;
   }
@@ -320,14 +331,14 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
       Shard<PosT>& s = sh[li];
       uint32_t ntiles = 1;
       if (s.held) {
-        SGX_LAUNCH(ctx, (shard_rank_kernel<PosT>), grid_for(s.held, 256), 256, 0, acc, (const uint8_t*)s.B,
-                   (const uint2*)s.blk.p, (const uint64_t*)s.tiletot.p, s.nt, bounds, uniform_len, (const uint32_t*)s.ID,
-                   (const PosT*)s.NP, (const uint8_t*)s.SYM.p, s.held, j, s.tmpDest.p, s.tmpPos.p);
+        SGX_LAUNCH(ctx, (shard_rank_kernel<PosT>), grid_for(s.held, 256), 256, 0, (const uint8_t*)s.B, (const uint2*)s.blk.p,
+                   (const uint64_t*)s.tiletot.p, s.nt, bounds, (const PosT*)s.NP, (const uint8_t*)s.SYM.p,
+                   (const uint32_t*)s.KEY, s.held, s.tmpDest.p, s.tmpPos.p, s.tmpKey.p);
         DestDigit dg{s.tmpDest.p};
-        partition_count<kMaxShards, DestDigit>(ctx, dg, s.held, s.part_ws.p, s.kept.p);
+        partition_count<kSendBuckets, DestDigit>(ctx, dg, s.held, s.part_ws.p, s.kept.p);
         ntiles = part_tiles(s.held);
       }
-      SGX_LAUNCH(ctx, shard_meta_kernel, 1, 32, 0, (const uint64_t*)s.part_ws.p, ntiles, s.held ? 1 : 0,
+      SGX_LAUNCH(ctx, shard_meta_kernel, 1, 96, 0, (const uint64_t*)s.part_ws.p, ntiles, s.held ? 1 : 0,
                  (const uint64_t*)s.kept.p, (const uint64_t*)s.tiletot.p, s.nt, (const uint64_t*)s.sym_total.p, s.meta.p);
       meta_ptr[li] = s.meta.p;
     }
@@ -338,8 +349,8 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
       Shard<PosT>& s = sh[li];
       if (!s.held) continue;
       DestDigit dg{s.tmpDest.p};
-      SendMove<PosT> mv{s.ID, s.tmpPos.p, s.send.p};
-      partition_scatter<kMaxShards, DestDigit, SendMove<PosT> >(ctx, dg, mv, s.held, s.part_ws.p);
+      SendMove<PosT> mv{s.ID, s.tmpPos.p, s.tmpKey.p, s.send.p};
+      partition_scatter<kSendBuckets, DestDigit, SendMove<PosT> >(ctx, dg, mv, s.held, s.part_ws.p);
     }
     SGX_TRACE_TICK(k_gather);
     comm_allgather_u64_end(cm, kMetaN, M.data());
@@ -347,7 +358,8 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
     for (int s = 0; s < W; ++s) {
       uint64_t run = 0;
       for (int d = 0; d < W; ++d) {
-        cntm[s * W + d] = M[(size_t)s * kMetaN + d];
+        cntm[s * W + d] = 0;
+        for (int c = 0; c < 4; ++c) cntm[s * W + d] += M[(size_t)s * kMetaN + d * 4 + c];
         soff[s * W + d] = run;
         run += cntm[s * W + d];
       }
@@ -377,32 +389,42 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
     // ---- receiver side
     uint64_t T[4] = {0, 0, 0, 0};
     for (int s = 0; s < W; ++s)
-      for (int c = 0; c < 4; ++c) T[c] += M[(size_t)s * kMetaN + kMaxShards + c];
+      for (int c = 0; c < 4; ++c) T[c] += M[(size_t)s * kMetaN + kSendBuckets + c];
     for (int li = 0; li < nl; ++li) {
       Shard<PosT>& s = sh[li];
       const int g = s.g;
       const uint64_t held_new = n_in[g];
       SGX_REQUIRE(n_new[g] <= s.rows_final, SGX_ECUDA, "sharded index: a shard received more rows than were counted for it");
       if (held_new) {
-        RecvFix fix;
-        memset(&fix, 0, sizeof(fix));
-        fix.world = W;
-        for (int q = 0; q < W; ++q) fix.roff[q] = roff[g * W + q];
-        fix.roff[W] = held_new;
+        RecvPlan plan;
+        memset(&plan, 0, sizeof(plan));
+        plan.world = W;
+        plan.entries = 4 * W;
         long long less_global = (long long)N;  // rows of suffixes starting with a symbol < c
+        uint64_t out_run = 0;
         for (int c = 0; c < 4; ++c) {
           long long before = 0;  // symbols c in the rows of shards before the sender
           for (int q = 0; q < W; ++q) {
+            const uint64_t* mq = &M[(size_t)q * kMetaN];
             long long less_local = 0;
-            for (int c2 = 0; c2 < c; ++c2) less_local += (long long)M[(size_t)q * kMetaN + kMaxShards + c2];
-            fix.K[q][c] = less_global + before - less_local - (long long)first_row[g];
-            before += (long long)M[(size_t)q * kMetaN + kMaxShards + c];
+            uint64_t src = roff[g * W + q];  // the sender's block, then its runs of smaller symbols
+            for (int c2 = 0; c2 < c; ++c2) {
+              less_local += (long long)mq[kSendBuckets + c2];
+              src += mq[g * 4 + c2];
+            }
+            const int e = c * W + q;
+            plan.out0[e] = out_run;
+            plan.src0[e] = src;
+            plan.K[e] = less_global + before - less_local - (long long)first_row[g];
+            out_run += mq[g * 4 + c];
+            before += (long long)mq[kSendBuckets + c];
           }
           less_global += (long long)T[c];
         }
-        RecvDigit<PosT> dg{acc, s.recv.p, j};
-        RecvMove<PosT> mv{acc, s.recv.p, j, uniform_len, fix, s.ID2, s.NP2, s.SYM.p};
-        partition_pass<4>(ctx, dg, mv, held_new, s.part_ws.p, (uint64_t*)nullptr);
+        plan.out0[4 * W] = out_run;
+        SGX_REQUIRE(out_run == held_new, SGX_ECUDA, "sharded index: receive plan does not cover the received inserts");
+        SGX_LAUNCH(ctx, (shard_place_kernel<PosT>), grid_for(held_new, 256), 256, 0, acc, (const WireItem<PosT>*)s.recv.p,
+                   held_new, j, uniform_len, plan, s.ID2, s.NP2, s.SYM.p, s.KEY2);
         const uint64_t rows_new = s.n_cur + held_new;
         const uint64_t ntiles = (rows_new + kMergeTile - 1) / kMergeTile;
         SGX_LAUNCH(ctx, (bcr_tile_bounds_kernel<PosT>), grid_for(held_new + 1, 256), 256, 0, (const PosT*)s.NP2, held_new,
@@ -418,6 +440,7 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
         std::swap(s.B, s.Bn);
         std::swap(s.ID, s.ID2);
         std::swap(s.NP, s.NP2);
+        std::swap(s.KEY, s.KEY2);
         s.n_cur = rows_new;
         s.nt = ntiles;
       }

@@ -358,3 +358,52 @@ def test_wide_position_paths_on_small_input(ctx, monkeypatch):
     for path in _GOLDEN:
         if any(k in path for k in ("random_fixed36_dups", "variable_length", "periodic30")):
             test_cuda_path_reproduces_golden_fixture(ctx, path)
+
+
+# ------------------------------------------------------------------------- the five BASELINE.json configs, scaled down
+
+@pytest.mark.skipif(not refrun.have_ref(), reason="compiled reference (oracle/_ref/siga) not present")
+@pytest.mark.parametrize("cfg,scale,m", [("cfg2", 0.004, 45), ("cfg3", 0.004, 31), ("cfg3", 0.004, 63), ("cfg3", 0.004, 101),
+                                         ("cfg4", 0.0002, 45), ("cfg5", 0.0003, 45)])
+def test_named_configs_scaled_down_match_reference(ctx, cfg, scale, m):
+    """Read shape, coverage, error rate and min-overlap of configs 2-5 (BASELINE.json) on a genome small enough for the
+    reference binary: .bwt/.rbwt/.sai/.rsai bytes and the canonically sorted ASQG must be identical, through the
+    single-device build, the bucket-sharded build (4 virtual shards) and sgx_overlap_edges."""
+    reads = synth.config_reads(cfg, scale)
+    n, L = reads.shape
+    flat, off = synth.reads_to_flat(reads)
+    with tempfile.TemporaryDirectory() as d:
+        fa = os.path.join(d, "x.fa")
+        synth.write_fasta(fa, reads)
+        refrun.ref_index(fa, d)
+        _, asqg = refrun.ref_overlap(fa, d, m, threads=os.cpu_count() or 1)
+        ref_asqg = formats.read_asqg(asqg)
+        want = {e: open(os.path.join(d, "x" + e), "rb").read() for e in (".bwt", ".rbwt", ".sai", ".rsai")}
+    r = ctx.pack_reads(flat, off)
+    comm = ctx.comm_init_local(4)
+    try:
+        fi = ctx.index_build(r)
+        ri = ctx.index_build(r, reversed=True)
+        assert formats.bwt_bytes(fi.n_strings, fi.n_suffixes, fi.runs) == want[".bwt"]
+        assert formats.bwt_bytes(ri.n_strings, ri.n_suffixes, ri.runs) == want[".rbwt"]
+        assert formats.sai_bytes(fi.sai) == want[".sai"] and formats.sai_bytes(ri.sai) == want[".rsai"]
+        for rv, one in ((False, fi), (True, ri)):
+            sh = ctx.index_build_sharded(comm, r, reversed=rv)
+            assert np.array_equal(sh.runs, one.runs) and np.array_equal(sh.sai, one.sai)
+        fwd = ctx.fm_create(fi.runs, fi.n_suffixes)
+        rev = ctx.fm_create(ri.runs, ri.n_suffixes)
+        try:
+            ctx.fm_attach_reads(fwd, fi.sai, r)
+            ctx.fm_attach_reads(rev, ri.sai, r)
+            names = ["r%d" % i for i in range(n)]
+            e = ctx.overlap_edges(fwd, rev, r, 0, n, m, api.name_ranks(names))
+        finally:
+            ctx.free_fm(fwd)
+            ctx.free_fm(rev)
+    finally:
+        ctx.free_comm(comm)
+        ctx.free_reads(r)
+    seqs = [x.tobytes().decode() for x in reads]
+    ed = formats.edges_to_ed(names, [L] * n, e.edges)
+    mine = formats.asqg_lines(names, seqs, e.substring, ed, m)
+    assert sorted(mine) == sorted(ref_asqg), (cfg, m, len(mine), len(ref_asqg))
