@@ -175,7 +175,11 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version banner must not share stdout with the JSON line
+        # NCCL's version banner must not share stdout with the JSON line; NCCL honours NCCL_DEBUG_FILE only above
+        # the VERSION level, so raise VERSION (the launcher's default) to WARN and send the log to stderr
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", ""):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -211,6 +215,11 @@ def main():
 
     ctx = api.Context(local)
     sampler = ClockSampler(local)
+    comm = None  # the library's own NCCL communicator: sharded index build + final gather of edge records
+    if world > 1:
+        uid = torch.from_numpy(ctx.comm_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)).cuda()
+        dist.broadcast(uid, 0)
+        comm = ctx.comm_init(uid.cpu().numpy(), rank, world)
 
     # ---- index (both strands) : build once for the overlap stage, then time it
     r_dev = ctx.pack_reads(flat, off)
@@ -277,6 +286,10 @@ def main():
         ctx.fm_attach_reads(rev, ri.sai, rr)
         ee = ctx.overlap_edges(fwd, rev, rr, 0, n_reads, MIN_OVERLAP, name_rank, copy=False)
         nb = int(ee.edges.nbytes + ee.substring.nbytes)
+        if comm is not None:  # N > 1: the edge records of every rank's shard end up in rank 0's host memory
+            ga = ctx.edges_gather(comm, ee, root=0, copy=False)
+            nb += int(ga.edges.nbytes + ga.substring.nbytes)
+            ctx.free_edges(ga)
         ctx.free_edges(ee)
         ctx.free_reads(rr)
         return nb
@@ -298,12 +311,6 @@ def main():
     #      inserts exchanged with NCCL all-to-all every column pass) -- strong scaling, checked against the
     #      single-GPU build of the setup phase byte for byte.
     isteps = args.index_steps or min(args.steps, 3)
-    comm = None
-    if world > 1:
-        uid = torch.from_numpy(ctx.comm_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)).cuda()
-        dist.broadcast(uid, 0)
-        comm = ctx.comm_init(uid.cpu().numpy(), rank, world)
-
     def build_index(rd, rv, copy=True):
         if comm is None:
             return ctx.index_build(rd, order=api.ORDER_SAIS2, reversed=rv, copy=copy)
@@ -370,7 +377,8 @@ def main():
         "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": "reads/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": e2e_h2d,
                 "d2h_bytes_per_step": e2e_d2h,
-                "entry": "sgx_reads_pack + sgx_fm_attach_reads x2 + sgx_overlap_edges (pinned host reads / .sai / name ranks in, edges + SS flags out)"},
+                "entry": "sgx_reads_pack + sgx_fm_attach_reads x2 + sgx_overlap_edges (pinned host reads / .sai / name ranks in, edges + SS flags out)"
+                         + ("; + sgx_edges_gather of all shards' edge records to rank 0 (NCCL)" if world > 1 else "")},
         "roofline": {"bound": "hbm", "kernel": "ov_search_kernel", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": ach_gbs / hbm_peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch (mode 0 of 4) at full cfg2 size,

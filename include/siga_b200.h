@@ -241,6 +241,15 @@ int sgx_overlap_edges(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const 
                       sgx_edges* out);
 void sgx_edges_free(sgx_edges* edges);
 
+/*
+ * Final gather of a read-sharded overlap run ("no collective beyond a final gather of ASQG
+ * records"): rank r searched the contiguous read range r of `world` ranges with sgx_overlap_edges; on `root` the
+ * result holds the SS flags of all reads in input order (rank order) and every rank's edge records; other ranks get
+ * an empty result.  Collective over an NCCL communicator (sgx_comm_init).  The ED order is free in the reference too
+ * (thread order, src/overlap_builder.cpp:447-480); VT order = input order is preserved by the rank-ordered flags.
+ */
+int sgx_edges_gather(sgx_ctx* ctx, sgx_comm* comm, const sgx_edges* local, int root, sgx_edges* out);
+
 /* ---- measurement helpers --------------------------------------------------------------------------------- */
 
 /*

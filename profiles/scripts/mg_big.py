@@ -119,24 +119,16 @@ def main():
         ed = e.edges
         if it == 2:
             assert np.all(name_rank[ed["query"]] > name_rank[ed["target"]]) and np.all((ed["length"] >= m) & (ed["length"] <= L))
-            # final gather of the edge records on rank 0
+            # final gather of the edge records on rank 0 (sgx_edges_gather: pinned buffers + NCCL)
             sync()
             t0 = time.perf_counter()
-            mine = torch.from_numpy(ed.view(np.uint8).reshape(-1).copy()).cuda()
-            sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
-            dist.all_gather(sizes, torch.tensor([mine.numel()], dtype=torch.int64, device="cuda"))
-            if rank == 0:
-                parts = [mine]
-                for s in range(1, world):
-                    b = torch.empty(int(sizes[s].item()), dtype=torch.uint8, device="cuda")
-                    dist.recv(b, s)
-                    parts.append(b)
-                allb = torch.cat(parts).cpu().numpy()
-                out["edges_total"] = int(allb.size // 16)
-            else:
-                dist.send(mine, 0)
+            allb = ctx.edges_gather(comm, e, root=0, copy=False)
             torch.cuda.synchronize()
             out["gather_ms"] = round(mx((time.perf_counter() - t0) * 1e3), 2)
+            if rank == 0:
+                out["edges_total"] = int(len(allb.edges))
+                assert allb.n_reads == n
+            ctx.free_edges(allb)
         ctx.free_edges(e)
     out["overlap"] = {"wall_ms": round(wall, 2), "reads_per_s": round(n / (wall * 1e-3)),
                       "ms_search": round(mx(st["ms_search"]), 2), "ms_extract": round(mx(st["ms_extract"]), 2),

@@ -22,7 +22,7 @@ ABI_SYMBOLS = [
     "sgx_reads_pack", "sgx_reads_free", "sgx_reads_count", "sgx_reads_bases",
     "sgx_index_build", "sgx_index_out_free",
     "sgx_comm_unique_id", "sgx_comm_init", "sgx_comm_init_local", "sgx_comm_free", "sgx_comm_world", "sgx_comm_rank",
-    "sgx_index_build_sharded",
+    "sgx_index_build_sharded", "sgx_edges_gather",
     "sgx_fm_create", "sgx_fm_free", "sgx_fm_attach_reads", "sgx_fm_length", "sgx_fm_pred", "sgx_fm_occ", "sgx_fm_count",
     "sgx_overlap_batch", "sgx_overlap_host", "sgx_hits_free", "sgx_overlap_edges", "sgx_edges_free",
     "sgx_bench_gather", "sgx_flush_l2",
@@ -114,6 +114,7 @@ def load_library():
     lib.sgx_hits_free.argtypes = [ctypes.POINTER(_Hits)]
     lib.sgx_hits_free.restype = None
     lib.sgx_overlap_edges.argtypes = [vp, vp, vp, vp, u64, u64, u32, i32, i32, vp, ctypes.POINTER(_Edges)]
+    lib.sgx_edges_gather.argtypes = [vp, vp, ctypes.POINTER(_Edges), i32, ctypes.POINTER(_Edges)]
     lib.sgx_edges_free.argtypes = [ctypes.POINTER(_Edges)]
     lib.sgx_edges_free.restype = None
     lib.sgx_bench_gather.argtypes = [vp, u64, u64, ctypes.POINTER(ctypes.c_double)]
@@ -170,9 +171,13 @@ class Edges:
 
     def __init__(self, e, copy=True):
         n, ne = int(e.n_reads), int(e.n_edges)
-        sub = np.ctypeslib.as_array(e.substring, shape=(max(n, 1),))[:n]
-        buf = (ctypes.c_uint8 * (max(ne, 1) * EDGE_DTYPE.itemsize)).from_address(e.edges)
-        edges = np.frombuffer(buf, dtype=EDGE_DTYPE)[:ne]
+        if not e.substring or not e.edges:  # empty result (e.g. a non-root rank of sgx_edges_gather)
+            n = ne = 0
+            sub, edges = np.zeros(0, dtype=np.uint8), np.zeros(0, dtype=EDGE_DTYPE)
+        else:
+            sub = np.ctypeslib.as_array(e.substring, shape=(max(n, 1),))[:n]
+            buf = (ctypes.c_uint8 * (max(ne, 1) * EDGE_DTYPE.itemsize)).from_address(e.edges)
+            edges = np.frombuffer(buf, dtype=EDGE_DTYPE)[:ne]
         if copy:
             sub, edges = sub.copy(), edges.copy()
         self.n_reads, self.substring, self.edges = n, sub, edges
@@ -358,6 +363,19 @@ class Context:
             self.lib.sgx_edges_free(ctypes.byref(e))
         else:
             res._raw = e
+        return res
+
+    def edges_gather(self, comm, edges, root=0, copy=True):
+        """Collective: every rank passes the Edges of its read range (obtained with copy=False); `root` gets the
+        concatenation (SS flags in input order), the other ranks an empty result."""
+        assert getattr(edges, "_raw", None) is not None, "edges_gather needs the raw result (overlap_edges(..., copy=False))"
+        out = _Edges()
+        self._check(self.lib.sgx_edges_gather(self.h, comm, ctypes.byref(edges._raw), int(root), ctypes.byref(out)))
+        res = Edges(out, copy=copy)
+        if copy:
+            self.lib.sgx_edges_free(ctypes.byref(out))
+        else:
+            res._raw = out
         return res
 
     def free_edges(self, edges):

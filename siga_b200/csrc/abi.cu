@@ -370,6 +370,58 @@ int sgx_overlap_edges(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const 
   SGX_ENTRY_END(ctx)
 }
 
+int sgx_edges_gather(sgx_ctx* ctx, sgx_comm* comm, const sgx_edges* local, int root, sgx_edges* out) {
+  if (!ctx || !comm || !local || !out || comm->ctx != ctx || root < 0 || root >= comm->world) return SGX_EINVAL;
+  SGX_ENTRY_BEGIN(ctx)
+  SGX_REQUIRE(!comm->local || comm->world == 1, SGX_EINVAL, "sgx_edges_gather: needs an NCCL communicator");
+  memset(out, 0, sizeof(*out));
+  const int W = comm->world;
+  EventTimer t(ctx->stream);
+  t.start();
+  // sizes of every rank
+  DevBuf<uint64_t> d_sz(2);
+  const uint64_t mine[2] = {local->n_reads, local->n_edges};
+  SGX_CUDA(cudaMemcpyAsync(d_sz.p, mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream));
+  SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<uint64_t> sz(2 * (size_t)W);
+  const uint64_t* szp = d_sz.p;
+  comm_allgather_u64(comm, &szp, 2, sz.data());
+  std::vector<uint64_t> fb(W), eb(W);
+  uint64_t n_reads = 0, n_edges = 0;
+  for (int r = 0; r < W; ++r) {
+    fb[r] = sz[2 * r];
+    eb[r] = sz[2 * r + 1] * sizeof(sgx_edge);
+    n_reads += sz[2 * r];
+    n_edges += sz[2 * r + 1];
+  }
+  const bool is_root = comm->rank == root || comm->local;
+  DevBuf<uint8_t> d_f(local->n_reads ? local->n_reads : 1), d_e(local->n_edges ? local->n_edges * sizeof(sgx_edge) : 1);
+  if (local->n_reads) SGX_CUDA(cudaMemcpyAsync(d_f.p, local->substring, local->n_reads, cudaMemcpyHostToDevice, ctx->stream));
+  if (local->n_edges)
+    SGX_CUDA(cudaMemcpyAsync(d_e.p, local->edges, local->n_edges * sizeof(sgx_edge), cudaMemcpyHostToDevice, ctx->stream));
+  DevBuf<uint8_t> a_f, a_e;
+  if (is_root) {
+    a_f.alloc(n_reads ? n_reads : 1);
+    a_e.alloc(n_edges ? n_edges * sizeof(sgx_edge) : 1);
+  }
+  const uint8_t* pf = d_f.p;
+  const uint8_t* pe = d_e.p;
+  comm_gatherv_bytes(comm, &pf, fb.data(), root, a_f.p);
+  comm_gatherv_bytes(comm, &pe, eb.data(), root, a_e.p);
+  if (is_root) {
+    out->n_reads = n_reads;
+    out->n_edges = n_edges;
+    out->substring = (uint8_t*)pinned_get(ctx, n_reads ? n_reads : 1);
+    out->edges = (sgx_edge*)pinned_get(ctx, n_edges ? n_edges * sizeof(sgx_edge) : 1);
+    SGX_CUDA(cudaMemcpyAsync(out->substring, a_f.p, n_reads, cudaMemcpyDeviceToHost, ctx->stream));
+    SGX_CUDA(cudaMemcpyAsync(out->edges, a_e.p, n_edges * sizeof(sgx_edge), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  t.stop();
+  SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+  out->ms_total = t.ms();
+  SGX_ENTRY_END(ctx)
+}
+
 void sgx_edges_free(sgx_edges* edges) {
   if (!edges) return;
   pinned_put(edges->substring);
