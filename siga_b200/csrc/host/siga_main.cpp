@@ -400,19 +400,154 @@ int cmd_overlap(int argc, char** argv) {
   return 0;
 }
 
+int usage_rmdup() {
+  printf("siga rmdup [OPTION] ... READSFILE\n"
+         "Remove duplicated reads from the data set\n"
+         "\n"
+         "      -h, --help                       display this help and exit\n"
+         "      -p, --prefix=PREFIX              use PREFIX instead of the prefix of the reads filename for the input/output files\n"
+         "      -t, --threads=N                  accepted for compatibility (the search runs on the GPU)\n"
+         "      -d, --sample-rate=N              accepted for compatibility (the rank layout is fixed: one 128-byte block per 256 symbols)\n"
+         "          --device=N                   CUDA device (default 0)\n"
+         "\n");
+  return 256;
+}
+
+// `siga rmdup` (src/rmdup.cpp:23-54, OverlapBuilder::rmdup / duplicate, src/overlap_builder.cpp:623-704, 1184-1195):
+// every read is searched at min-overlap = |read|, which leaves its containment blocks; the two searches duplicate()
+// runs are the seq / forward-index one (AlignFlags 0) and the complement / reverse-index one (TARGETREV|QUERYCOMP).
+// Output: PREFIX.rmdup.fa and PREFIX.rmdup.dups.fa, records as Hits2FastaConverter::convert writes them (563-616);
+// record order follows the input (the reference's follows its per-thread hits files).
+int cmd_rmdup(int argc, char** argv) {
+  enum { OPT_DEVICE = 1000 };
+  static const option longopts[] = {{"log4cxx", required_argument, nullptr, 'c'}, {"ini", required_argument, nullptr, 's'},
+                                    {"prefix", required_argument, nullptr, 'p'},  {"threads", required_argument, nullptr, 't'},
+                                    {"sample-rate", required_argument, nullptr, 'd'}, {"device", required_argument, nullptr, OPT_DEVICE},
+                                    {"help", no_argument, nullptr, 'h'},          {nullptr, 0, nullptr, 0}};
+  CommonOpts o;
+  int c;
+  while ((c = getopt_long(argc, argv, "c:s:t:p:d:h", longopts, nullptr)) != -1) {
+    switch (c) {
+      case 't': o.threads = atoi(optarg); break;
+      case 'p': o.prefix = optarg; break;
+      case OPT_DEVICE: o.device = atoi(optarg); break;
+      case 'h': o.help = true; break;
+      default: break;
+    }
+  }
+  if (o.help || argc - optind != 1) return usage_rmdup();
+  const std::string input = argv[optind];
+  const std::string output = o.prefix.empty() ? stem(input) : o.prefix;
+  info("input: %s", input.c_str());
+  info("output: %s", output.c_str());
+  const double t0 = now_s();
+  uint64_t ns = 0, nf = 0, rns = 0, rnf = 0;
+  std::vector<uint8_t> runs, rruns;
+  std::vector<uint32_t> sai, rsai;
+  if (!read_bwt(output + ".bwt", &ns, &nf, &runs) || !read_bwt(output + ".rbwt", &rns, &rnf, &rruns)) {
+    fprintf(stderr, "ERROR siga - Failed to load FMIndex from %s\n", input.c_str());
+    return -1;
+  }
+  if (!read_sai(output + ".sai", &sai) || !read_sai(output + ".rsai", &rsai)) {
+    fprintf(stderr, "ERROR siga - failed to load suffix array index %s\n", output.c_str());
+    return -1;
+  }
+  ReadSet rs;
+  std::string err;
+  if (!read_sequences(input, &rs, &err)) {
+    fprintf(stderr, "ERROR siga - %s\n", err.c_str());
+    return -1;
+  }
+  if (rs.size() != ns || rs.size() != sai.size() || rs.size() != rsai.size()) {
+    fprintf(stderr, "ERROR siga - %s holds %zu reads but the index was built from %llu\n", input.c_str(), rs.size(),
+            (unsigned long long)ns);
+    return -1;
+  }
+  sgx_ctx* ctx = nullptr;
+  int rc = sgx_init(o.device, &ctx);
+  if (rc != SGX_OK) return fail(nullptr, "sgx_init", rc);
+  sgx_reads* reads = nullptr;
+  sgx_fm *fwd = nullptr, *rev = nullptr;
+  if ((rc = sgx_reads_pack(ctx, rs.bases.data(), rs.off.data(), rs.size(), &reads)) != SGX_OK) return fail(ctx, "sgx_reads_pack", rc);
+  if ((rc = sgx_fm_create(ctx, runs.data(), runs.size(), nf, &fwd)) != SGX_OK) return fail(ctx, "sgx_fm_create", rc);
+  if ((rc = sgx_fm_create(ctx, rruns.data(), rruns.size(), rnf, &rev)) != SGX_OK) return fail(ctx, "sgx_fm_create", rc);
+  if ((rc = sgx_fm_attach_reads(ctx, fwd, sai.data(), sai.size(), reads)) != SGX_OK) return fail(ctx, "sgx_fm_attach_reads", rc);
+  if ((rc = sgx_fm_attach_reads(ctx, rev, rsai.data(), rsai.size(), reads)) != SGX_OK) return fail(ctx, "sgx_fm_attach_reads", rc);
+  uint32_t max_len = 0;
+  for (size_t i = 0; i < rs.size(); ++i) max_len = std::max<uint32_t>(max_len, (uint32_t)(rs.off[i + 1] - rs.off[i]));
+  // min-overlap = the longest read: no read has a proper overlap that long, only the full-length (containment) blocks remain
+  sgx_hits hits;
+  rc = sgx_overlap_batch(ctx, fwd, rev, reads, 0, rs.size(), max_len, /*irreducible=*/0, /*rc=*/1, &hits);
+  if (rc != SGX_OK) return fail(ctx, "sgx_overlap_batch", rc);
+  info("processed %zu sequences; device %.1f ms", rs.size(), hits.ms_total);
+
+  std::string keep, dups;
+  keep.reserve(rs.bases.size() + rs.size() * 48);
+  uint64_t n_dups = 0;
+  for (size_t q = 0; q < rs.size(); ++q) {
+    const std::string& qn = rs.names[q];
+    uint64_t copies = 0;
+    bool contained = hits.substring[q] != 0;
+    for (uint64_t b = hits.block_off[q]; b < hits.block_off[q + 1]; ++b) {
+      const sgx_block& blk = hits.blocks[b];
+      if (blk.af != 0 && blk.af != (SGX_AF_TARGETREV | SGX_AF_QUERYCOMP)) continue;
+      const std::vector<uint32_t>& sa = (blk.af & SGX_AF_TARGETREV) ? rsai : sai;
+      copies += blk.capped[1] - blk.capped[0] + 1;
+      for (uint64_t j = blk.capped[0]; j <= blk.capped[1] && !contained; ++j) {
+        const std::string& tn = rs.names[sa[j]];
+        if (tn != qn && !(qn < tn)) contained = true;  // an identical / reverse-complement read with a smaller name stays
+      }
+    }
+    std::string* dst = contained ? &dups : &keep;
+    *dst += '>';
+    *dst += qn;
+    if (contained) {
+      *dst += ",seqrank=";
+      append_uint(dst, q);
+      ++n_dups;
+    }
+    *dst += ' ';
+    *dst += qn;
+    *dst += " NumDuplicates=";
+    append_uint(dst, copies);
+    *dst += '\n';
+    dst->append(rs.bases, rs.off[q], rs.off[q + 1] - rs.off[q]);
+    *dst += '\n';
+  }
+  for (int k = 0; k < 2; ++k) {
+    const std::string path = output + (k == 0 ? ".rmdup.fa" : ".rmdup.dups.fa");
+    FILE* f = fopen(path.c_str(), "wb");
+    const std::string& text = k == 0 ? keep : dups;
+    if (!f || fwrite(text.data(), 1, text.size(), f) != text.size() || fclose(f) != 0) {
+      fprintf(stderr, "ERROR siga - Failed to create FASTA %s\n", path.c_str());
+      return -1;
+    }
+  }
+  info("%zu reads kept, %llu duplicates / substrings removed", rs.size() - (size_t)n_dups, (unsigned long long)n_dups);
+  sgx_hits_free(&hits);
+  sgx_fm_free(fwd);
+  sgx_fm_free(rev);
+  sgx_reads_free(reads);
+  sgx_shutdown(ctx);
+  info("wall: %.3f sec", now_s() - t0);
+  return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
   if (argc < 2 || !strcmp(argv[1], "-h") || !strcmp(argv[1], "--help")) {
     printf("siga (B200 build) -- Usage: siga <command> [<args>]\n\n"
            "   index       build the BWT and FM-index for a set of reads\n"
-           "   overlap     compute overlaps between reads\n\n"
+           "   overlap     compute overlaps between reads\n"
+           "   rmdup       remove duplicated reads from the data set\n\n"
            "See 'siga <command> -h' to read about a specific subcommand.\n");
     return 256;
   }
   const std::string cmd = argv[1];
   if (cmd == "index") return cmd_index(argc - 1, argv + 1);
   if (cmd == "overlap") return cmd_overlap(argc - 1, argv + 1);
-  fprintf(stderr, "siga: '%s' is not provided by this build (only the index/overlap hot path is)\n", cmd.c_str());
+  if (cmd == "rmdup") return cmd_rmdup(argc - 1, argv + 1);
+  fprintf(stderr, "siga: '%s' is not provided by this build (only the index / overlap / rmdup path is)\n", cmd.c_str());
   return 256;
 }

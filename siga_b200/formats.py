@@ -126,6 +126,36 @@ def hits_to_edges(names, lengths, substring, block_off, blocks, sai, rsai):
     return edges
 
 
+def rmdup_records(names, seqs, substring, block_off, blocks, sai, rsai):
+    """`siga rmdup` from hit blocks (OverlapBuilder::duplicate + Hits2FastaConverter::convert,
+    src/overlap_builder.cpp:1184-1195, 563-616): the blocks of a read searched with min-overlap = |read| are its
+    containment blocks; duplicate() keeps those of the seq / forward-index and complement / reverse-index searches
+    (AlignFlags 0 and TARGETREV|QUERYCOMP).  NumDuplicates = number of ranks in their capped[0] intervals (the read
+    itself included); the read is a duplicate when it is a substring of another read or an identical / reverse-
+    complement read has a smaller name.  -> (kept FASTA records, duplicate FASTA records), each ">header\nseq\n"."""
+    kept, dups = [], []
+    for q in range(len(names)):
+        qn = names[q]
+        copies, contained = 0, bool(substring[q])
+        for b in blocks[int(block_off[q]):int(block_off[q + 1])]:
+            af = int(b["af"])
+            if af not in (0, AF_TARGETREV | AF_QUERYCOMP):
+                continue
+            lo, hi = int(b["capped"][0]), int(b["capped"][1])
+            sa = rsai if af & AF_TARGETREV else sai
+            copies += hi - lo + 1
+            for j in range(lo, hi + 1):
+                tn = names[int(sa[j])]
+                if tn != qn and not qn < tn:  # kept overlap (id0 >= id1): mutually contained, containedIdx() == 0
+                    contained = True
+        meta = "%s NumDuplicates=%d" % (qn, copies)
+        if contained:
+            dups.append(">%s,seqrank=%d %s\n%s\n" % (qn, q, meta, seqs[q]))
+        else:
+            kept.append(">%s %s\n%s\n" % (qn, meta, seqs[q]))
+    return kept, dups
+
+
 def edges_to_ed(names, lengths, edges):
     """ED payload strings of compact edge records (sgx_edge): the coordinates of OverlapBlock::overlap
     (src/overlap_builder.cpp:158-175) printed like Overlap's writer (src/coord.cpp:66-80)."""

@@ -79,3 +79,40 @@ def test_cli_prefix_and_errors(tmp_path):
     assert r.returncode != 0  # the reference silently writes nothing here; we refuse
     r = subprocess.run([CLI, "overlap", "-p", "missing", str(fa)], cwd=str(tmp_path), capture_output=True, text=True)
     assert r.returncode != 0 and "Failed to load FMIndex" in r.stderr
+
+
+def _fasta_records(path):
+    txt = open(path).read()
+    return sorted(">" + r for r in txt.split(">") if r)
+
+
+@pytest.mark.skipif(not refrun.have_ref(), reason="compiled reference (oracle/_ref/siga) not present")
+@pytest.mark.skipif(not os.path.isfile(CLI), reason="siga_b200/bin/siga not built")
+@pytest.mark.parametrize("case", ["fixed", "varlen"])
+def test_cli_rmdup_matches_reference(case):
+    """`siga rmdup` (src/rmdup.cpp, OverlapBuilder::rmdup): the kept / duplicate FASTA record sets are identical
+    (the reference writes them in per-thread hits order, so the comparison is on sorted records)."""
+    rng = np.random.default_rng(23)
+    g = synth.random_genome(3000, rng)
+    if case == "fixed":
+        reads = [r.tobytes() for r in synth.sample_reads(g, 700, 40, rng, err=0.0)]
+    else:  # variable length: substrings of other reads are removed too
+        from test_gpu_parity import _rand_reads
+        reads = _rand_reads(rng, 700, 15, 50, 1500)
+    for _ in range(90):   # exact duplicates and reverse-complement duplicates
+        a, b = rng.integers(0, len(reads), 2)
+        reads[a] = reads[b] if rng.random() < 0.5 else synth.revcomp(np.frombuffer(reads[b], dtype=np.uint8)).tobytes()
+    with tempfile.TemporaryDirectory() as d:
+        ours, ref = os.path.join(d, "ours"), os.path.join(d, "ref")
+        os.mkdir(ours)
+        os.mkdir(ref)
+        src = os.path.join(d, "reads.fa")
+        synth.write_fasta(src, reads)
+        refrun.run_ref(["index", src], ref)
+        refrun.run_ref(["rmdup", "-t", "3", src], ref)
+        _run(["index", src], ours)
+        _run(["rmdup", src], ours)
+        for f in ("reads.rmdup.fa", "reads.rmdup.dups.fa"):
+            mine, want = _fasta_records(os.path.join(ours, f)), _fasta_records(os.path.join(ref, f))
+            assert mine == want, (case, f, len(mine), len(want))
+        assert len(_fasta_records(os.path.join(ours, "reads.rmdup.dups.fa"))) > 20

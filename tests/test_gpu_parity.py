@@ -407,3 +407,45 @@ def test_named_configs_scaled_down_match_reference(ctx, cfg, scale, m):
     ed = formats.edges_to_ed(names, [L] * n, e.edges)
     mine = formats.asqg_lines(names, seqs, e.substring, ed, m)
     assert sorted(mine) == sorted(ref_asqg), (cfg, m, len(mine), len(ref_asqg))
+
+
+# ------------------------------------------------------------------------------------------------------------ rmdup
+
+@pytest.mark.skipif(not refrun.have_ref(), reason="compiled reference (oracle/_ref/siga) not present")
+def test_rmdup_records_match_reference(ctx):
+    """`siga rmdup` (src/overlap_builder.cpp:623-704, 1184-1195) through the C ABI: a search at min-overlap = |read|
+    leaves the containment blocks; NumDuplicates and the kept / removed split must equal the reference's files."""
+    rng = np.random.default_rng(61)
+    g = synth.random_genome(2500, rng)
+    reads = [r.tobytes() for r in synth.sample_reads(g, 500, 36, rng, err=0.0)]
+    for _ in range(80):
+        a, b = rng.integers(0, len(reads), 2)
+        reads[a] = reads[b] if rng.random() < 0.5 else synth.revcomp(np.frombuffer(reads[b], dtype=np.uint8)).tobytes()
+    flat, off = synth.reads_to_flat(reads)
+    with tempfile.TemporaryDirectory() as d:
+        fa = os.path.join(d, "x.fa")
+        synth.write_fasta(fa, reads)
+        refrun.ref_index(fa, d)
+        refrun.run_ref(["rmdup", "-t", "2", fa], d)
+        want = [sorted(">" + r for r in open(os.path.join(d, f)).read().split(">") if r) for f in ("x.rmdup.fa", "x.rmdup.dups.fa")]
+    r = ctx.pack_reads(flat, off)
+    try:
+        fi = ctx.index_build(r)
+        ri = ctx.index_build(r, reversed=True)
+        fwd = ctx.fm_create(fi.runs, fi.n_suffixes)
+        rev = ctx.fm_create(ri.runs, ri.n_suffixes)
+        try:
+            for attach in (False, True):
+                if attach:
+                    ctx.fm_attach_reads(fwd, fi.sai, r)
+                    ctx.fm_attach_reads(rev, ri.sai, r)
+                h = ctx.overlap(fwd, rev, r, 0, len(reads), 36, irreducible=False)
+                names = ["r%d" % i for i in range(len(reads))]
+                kept, dups = formats.rmdup_records(names, [x.decode() for x in reads], h.substring, h.block_off, h.blocks,
+                                                   fi.sai, ri.sai)
+                assert sorted(kept) == want[0] and sorted(dups) == want[1], ("attach" if attach else "walk", len(kept), len(dups))
+        finally:
+            ctx.free_fm(fwd)
+            ctx.free_fm(rev)
+    finally:
+        ctx.free_reads(r)
