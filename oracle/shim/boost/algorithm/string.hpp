@@ -7,7 +7,20 @@
 namespace boost {
 struct shim_char_range { char lo, hi; bool operator()(char c) const { return c >= lo && c <= hi; } };
 inline shim_char_range is_from_range(char lo, char hi) { shim_char_range r = {lo, hi}; return r; }
+struct shim_any_of { std::string set; bool operator()(char c) const { return set.find(c) != std::string::npos; } };
+inline shim_any_of is_any_of(const std::string& set) { shim_any_of r = {set}; return r; }
 namespace algorithm {
+template <class Seq>
+inline std::string join(const Seq& parts, const std::string& sep) {
+  std::string out;
+  bool first = true;
+  for (typename Seq::const_iterator it = parts.begin(); it != parts.end(); ++it) {
+    if (!first) out += sep;
+    out += *it;
+    first = false;
+  }
+  return out;
+}
 inline bool equals(const std::string& a, const std::string& b) { return a == b; }
 inline bool iequals(const std::string& a, const std::string& b) {
   if (a.size() != b.size()) return false;

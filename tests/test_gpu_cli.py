@@ -116,3 +116,44 @@ def test_cli_rmdup_matches_reference(case):
             mine, want = _fasta_records(os.path.join(ours, f)), _fasta_records(os.path.join(ref, f))
             assert mine == want, (case, f, len(mine), len(want))
         assert len(_fasta_records(os.path.join(ours, "reads.rmdup.dups.fa"))) > 20
+
+
+def _contigs(path):
+    """Contig sequences in canonical orientation (the smaller of a sequence and its reverse complement), sorted."""
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    out = []
+    for rec in open(path, "rb").read().split(b">")[1:]:
+        seq = b"".join(rec.split(b"\n")[1:])
+        out.append(min(seq, seq.translate(comp)[::-1]))
+    return sorted(out)
+
+
+@pytest.mark.skipif(not refrun.have_ref(), reason="compiled reference (oracle/_ref/siga) not present")
+@pytest.mark.skipif(not os.path.isfile(CLI), reason="siga_b200/bin/siga not built")
+@pytest.mark.parametrize("err", [0.0, 0.005])
+def test_downstream_assemble_runs_unchanged(err):
+    """BASELINE.json north_star: "downstream `siga assemble` runs unchanged".  The reference's own assembler
+    (src/assembler.cpp, src/bigraph*.cpp, compiled into oracle/_ref/siga) is run on the .asqg.gz produced by this repo's
+    index -> rmdup -> index -> overlap chain and on the reference's; the contig sets must be identical."""
+    rng = np.random.default_rng(41)
+    g = synth.random_genome(30_000, rng)
+    g[20_000:20_400] = g[5_000:5_400]  # repeats longer than a read
+    g[25_000:25_800] = g[9_000:9_800]
+    reads = synth.sample_reads(g, 15_000, 100, rng, err=err)  # with errors: hundreds of contigs after trimming
+    with tempfile.TemporaryDirectory() as d:
+        out = {}
+        for who in ("ours", "ref"):
+            w = os.path.join(d, who)
+            os.mkdir(w)
+            src = os.path.join(w, "reads.fa")
+            synth.write_fasta(src, reads)
+            run = (lambda a: _run(a, w)) if who == "ours" else (lambda a: refrun.run_ref(a, w))
+            run(["index", src])
+            run(["rmdup"] + (["-t", "4"] if who == "ref" else []) + [src])
+            dedup = os.path.join(w, "reads.rmdup.fa")
+            run(["index", dedup])
+            run(["overlap", "-m", "45", "-t", "4", dedup])
+            refrun.run_ref(["assemble", "-m", "45", "-p", "asm", os.path.join(w, "reads.rmdup.asqg.gz")], w)
+            out[who] = _contigs(os.path.join(w, "asm-contigs.fa"))
+        assert sum(len(c) for c in out["ref"]) > 25_000 and (err == 0.0 or len(out["ref"]) > 100)
+        assert out["ours"] == out["ref"]
