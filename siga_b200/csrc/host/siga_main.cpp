@@ -55,7 +55,8 @@ int fail(sgx_ctx* ctx, const char* what, int rc) {
 // boost's readers, hence `siga assemble`, accept).
 class GzChunkWriter {
  public:
-  GzChunkWriter(const std::string& path, unsigned threads) : f_(fopen(path.c_str(), "wb")), threads_(threads ? threads : 1) {}
+  GzChunkWriter(const std::string& path, unsigned threads, int level)
+      : f_(fopen(path.c_str(), "wb")), threads_(threads ? threads : 1), level_(level) {}
   ~GzChunkWriter() {
     if (f_) fclose(f_);
   }
@@ -72,7 +73,7 @@ class GzChunkWriter {
         pool.emplace_back([&, t]() {
           std::string text;
           produce(base + t, &text);
-          gz[t] = deflate_member(text);
+          gz[t] = deflate_member(text, level_);
         });
       }
       for (auto& th : pool) th.join();
@@ -82,10 +83,10 @@ class GzChunkWriter {
   }
 
  private:
-  static std::string deflate_member(const std::string& text) {
+  static std::string deflate_member(const std::string& text, int level) {
     z_stream zs;
     memset(&zs, 0, sizeof(zs));
-    deflateInit2(&zs, Z_DEFAULT_COMPRESSION, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY);
+    deflateInit2(&zs, level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY);
     std::string out(deflateBound(&zs, text.size()) + 64, '\0');
     zs.next_in = (Bytef*)text.data();
     zs.avail_in = (uInt)text.size();
@@ -98,6 +99,7 @@ class GzChunkWriter {
   }
   FILE* f_;
   unsigned threads_;
+  int level_;
 };
 
 void append_uint(std::string* s, uint64_t v) {
@@ -148,10 +150,56 @@ void append_comment_tags(const std::string& comment, std::string* line) {
 
 struct CommonOpts {
   std::string prefix;
-  int threads = 1;
+  int threads = 0;     // host-side text / gzip work; 0 = all hardware threads (the search itself runs on the GPU)
   int device = 0;
+  int gzip_level = 1;  // .asqg.gz members are written at zlib level 1 unless --gzip-level says otherwise
   bool help = false;
 };
+
+// Index files and reads of `overlap` / `rmdup`, loaded concurrently with the CUDA context start-up.
+struct LoadedInput {
+  uint64_t ns = 0, nf = 0, rns = 0, rnf = 0;
+  std::vector<uint8_t> runs, rruns;
+  std::vector<uint32_t> sai, rsai;
+  ReadSet rs;
+  std::string err;
+  sgx_ctx* ctx = nullptr;
+  int ctx_rc = SGX_OK;
+  bool ok_bwt = false, ok_rbwt = false, ok_sai = false, ok_rsai = false, ok_reads = false;
+};
+
+bool load_input(const std::string& input, const std::string& output, int device, LoadedInput* in) {
+  std::vector<std::thread> pool;
+  pool.emplace_back([&]() { in->ctx_rc = sgx_init(device, &in->ctx); });
+  pool.emplace_back([&]() { in->ok_bwt = read_bwt(output + ".bwt", &in->ns, &in->nf, &in->runs); });
+  pool.emplace_back([&]() { in->ok_rbwt = read_bwt(output + ".rbwt", &in->rns, &in->rnf, &in->rruns); });
+  pool.emplace_back([&]() { in->ok_sai = read_sai(output + ".sai", &in->sai); });
+  pool.emplace_back([&]() { in->ok_rsai = read_sai(output + ".rsai", &in->rsai); });
+  pool.emplace_back([&]() { in->ok_reads = read_sequences(input, &in->rs, &in->err); });
+  for (auto& t : pool) t.join();
+  if (!in->ok_bwt || !in->ok_rbwt) {
+    fprintf(stderr, "ERROR siga - Failed to load FMIndex from %s\n", input.c_str());
+    return false;
+  }
+  if (!in->ok_sai || !in->ok_rsai) {
+    fprintf(stderr, "ERROR siga - failed to load suffix array index %s\n", output.c_str());
+    return false;
+  }
+  if (!in->ok_reads) {
+    fprintf(stderr, "ERROR siga - %s\n", in->err.c_str());
+    return false;
+  }
+  if (in->rs.size() != in->ns || in->rs.size() != in->sai.size() || in->rs.size() != in->rsai.size()) {
+    fprintf(stderr, "ERROR siga - %s holds %zu reads but the index was built from %llu\n", input.c_str(), in->rs.size(),
+            (unsigned long long)in->ns);
+    return false;
+  }
+  if (in->ctx_rc != SGX_OK) {
+    fail(nullptr, "sgx_init", in->ctx_rc);
+    return false;
+  }
+  return true;
+}
 
 int usage_index() {
   printf("siga index [OPTION] ... READSFILE\n"
@@ -172,7 +220,8 @@ int usage_overlap() {
   printf("siga overlap [OPTION] ... READSFILE\n"
          "Compute pairwise overlap between all the sequences in READS (searched on the GPU)\n\n"
          "      -h, --help                       display this help and exit\n\n"
-         "      -t, --threads=NUM                host threads for output formatting/compression (default: 1)\n"
+         "      -t, --threads=NUM                host threads for output formatting/compression (default: all)\n"
+         "          --gzip-level=N               zlib level of the .asqg.gz members, 1..9 (default: 1)\n"
          "          --batch-size=NUM             accepted for compatibility (batching is internal)\n"
          "      -m, --min-overlap=LEN            minimum overlap required between two reads (default: 10)\n"
          "      -p, --prefix=PREFIX              read the index from / write the graph to PREFIX instead of prefix of READSFILE\n"
@@ -223,31 +272,55 @@ int cmd_index(int argc, char** argv) {
   ReadSet rs;
   std::string err;
   info("loading reads: %s", input.c_str());
-  if (!read_sequences(input, &rs, &err)) {
+  sgx_ctx* ctx = nullptr;
+  int rc_init = SGX_OK;
+  std::thread init_thread([&]() { rc_init = sgx_init(o.device, &ctx); });  // CUDA start-up overlaps the parse
+  const bool parsed = read_sequences(input, &rs, &err);
+  init_thread.join();
+  if (!parsed) {
     fprintf(stderr, "ERROR siga - %s\n", err.c_str());
     return -1;
   }
-  sgx_ctx* ctx = nullptr;
-  int rc = sgx_init(o.device, &ctx);
-  if (rc != SGX_OK) return fail(nullptr, "sgx_init", rc);
+  if (rc_init != SGX_OK) return fail(nullptr, "sgx_init", rc_init);
+  int rc = SGX_OK;
   sgx_reads* reads = nullptr;
   rc = sgx_reads_pack(ctx, rs.bases.data(), rs.off.data(), rs.size(), &reads);
   if (rc != SGX_OK) return fail(ctx, "sgx_reads_pack", rc);
+  // the files of one strand are written on a host thread while the device builds the other strand
+  sgx_index_out outs[2];
+  std::thread writers[2];
+  bool wrote[2] = {true, true};
   for (int pass = 0; pass < 2; ++pass) {
     if ((pass == 0 && !fwd) || (pass == 1 && !rev)) continue;
     info("building %s index on device %d", pass == 0 ? "forward" : "reverse", o.device);
-    sgx_index_out out;
+    sgx_index_out& out = outs[pass];
     rc = sgx_index_build(ctx, reads, order, pass, &out);
-    if (rc != SGX_OK) return fail(ctx, "sgx_index_build", rc);
-    const std::string sa = output + (pass == 0 ? ".sai" : ".rsai"), bw = output + (pass == 0 ? ".bwt" : ".rbwt");
-    if (!write_sai(sa, out.sai, out.n_strings) || !write_bwt(bw, out.n_strings, out.n_suffixes, out.rle, out.n_runs)) {
-      fprintf(stderr, "ERROR siga - failed to write %s / %s\n", sa.c_str(), bw.c_str());
-      return -1;
+    if (rc != SGX_OK) {
+      for (auto& w : writers)
+        if (w.joinable()) w.join();
+      return fail(ctx, "sgx_index_build", rc);
     }
+    const std::string sa = output + (pass == 0 ? ".sai" : ".rsai"), bw = output + (pass == 0 ? ".bwt" : ".rbwt");
     info("%s: %llu strings, %llu suffixes, %llu runs; device %.1f ms (%llu kernel launches)", bw.c_str(),
          (unsigned long long)out.n_strings, (unsigned long long)out.n_suffixes, (unsigned long long)out.n_runs, out.ms_total,
          (unsigned long long)out.launches);
-    sgx_index_out_free(&out);
+    writers[pass] = std::thread([&outs, &wrote, pass, sa, bw]() {
+      const sgx_index_out& o2 = outs[pass];
+      bool a = false, b = false;
+      std::thread t([&]() { a = write_sai(sa, o2.sai, o2.n_strings); });
+      b = write_bwt(bw, o2.n_strings, o2.n_suffixes, o2.rle, o2.n_runs);
+      t.join();
+      wrote[pass] = a && b;
+    });
+  }
+  for (int pass = 0; pass < 2; ++pass) {
+    if (!writers[pass].joinable()) continue;
+    writers[pass].join();
+    sgx_index_out_free(&outs[pass]);
+    if (!wrote[pass]) {
+      fprintf(stderr, "ERROR siga - failed to write the %s index files of %s\n", pass == 0 ? "forward" : "reverse", output.c_str());
+      return -1;
+    }
   }
   sgx_reads_free(reads);
   sgx_shutdown(ctx);
@@ -256,14 +329,14 @@ int cmd_index(int argc, char** argv) {
 }
 
 int cmd_overlap(int argc, char** argv) {
-  enum { OPT_BATCH_SIZE = 1000, OPT_NO_RC, OPT_DEVICE };
+  enum { OPT_BATCH_SIZE = 1000, OPT_NO_RC, OPT_DEVICE, OPT_GZIP_LEVEL };
   static const option longopts[] = {{"log4cxx", required_argument, nullptr, 'c'},   {"ini", required_argument, nullptr, 's'},
                                     {"prefix", required_argument, nullptr, 'p'},    {"threads", required_argument, nullptr, 't'},
                                     {"batch-size", required_argument, nullptr, OPT_BATCH_SIZE},
                                     {"min-overlap", required_argument, nullptr, 'm'}, {"exhaustive", no_argument, nullptr, 'x'},
                                     {"no-opposite-strand", no_argument, nullptr, OPT_NO_RC},
                                     {"device", required_argument, nullptr, OPT_DEVICE}, {"help", no_argument, nullptr, 'h'},
-                                    {nullptr, 0, nullptr, 0}};
+                                    {"gzip-level", required_argument, nullptr, OPT_GZIP_LEVEL}, {nullptr, 0, nullptr, 0}};
   CommonOpts o;
   unsigned min_overlap = 10;
   bool exhaustive = false, rcomp = true;
@@ -275,6 +348,7 @@ int cmd_overlap(int argc, char** argv) {
       case 'm': min_overlap = (unsigned)atoi(optarg); break;
       case 'x': exhaustive = true; break;
       case OPT_NO_RC: rcomp = false; break;
+      case OPT_GZIP_LEVEL: o.gzip_level = std::max(1, std::min(9, atoi(optarg))); break;
       case OPT_DEVICE: o.device = atoi(optarg); break;
       case 'h': o.help = true; break;
       default: break;
@@ -288,33 +362,24 @@ int cmd_overlap(int argc, char** argv) {
   info("output: %s.asqg.gz", output.c_str());
   const double t0 = now_s();
 
-  uint64_t ns = 0, nf = 0, rns = 0, rnf = 0;
-  std::vector<uint8_t> runs, rruns;
-  std::vector<uint32_t> sai, rsai;
-  if (!read_bwt(output + ".bwt", &ns, &nf, &runs) || !read_bwt(output + ".rbwt", &rns, &rnf, &rruns)) {
-    fprintf(stderr, "ERROR siga - Failed to load FMIndex from %s\n", input.c_str());
-    return -1;
-  }
-  if (!read_sai(output + ".sai", &sai) || !read_sai(output + ".rsai", &rsai)) {
-    fprintf(stderr, "ERROR siga - failed to load suffix array index %s\n", output.c_str());
-    return -1;
-  }
-  ReadSet rs;
-  std::string err;
-  if (!read_sequences(input, &rs, &err)) {
-    fprintf(stderr, "ERROR siga - %s\n", err.c_str());
-    return -1;
-  }
-  if (rs.size() != ns || rs.size() != sai.size() || rs.size() != rsai.size()) {
-    fprintf(stderr, "ERROR siga - %s holds %zu reads but the index was built from %llu\n", input.c_str(), rs.size(),
-            (unsigned long long)ns);
-    return -1;
-  }
+  LoadedInput in;
+  if (!load_input(input, output, o.device, &in)) return -1;
+  ReadSet& rs = in.rs;
+  std::vector<uint8_t>&runs = in.runs, &rruns = in.rruns;
+  std::vector<uint32_t>&sai = in.sai, &rsai = in.rsai;
+  const uint64_t nf = in.nf, rnf = in.rnf;
+  sgx_ctx* ctx = in.ctx;
+  int rc = SGX_OK;
   const double t_load = now_s();
 
-  sgx_ctx* ctx = nullptr;
-  int rc = sgx_init(o.device, &ctx);
-  if (rc != SGX_OK) return fail(nullptr, "sgx_init", rc);
+  std::vector<uint32_t> rank;
+  std::thread rank_thread([&]() { rank = name_ranks(rs.names); });  // host sort of the names while the device loads the index
+  struct Joiner {
+    std::thread& t;
+    ~Joiner() {
+      if (t.joinable()) t.join();
+    }
+  } rank_joiner{rank_thread};
   sgx_reads* reads = nullptr;
   sgx_fm *fwd = nullptr, *rev = nullptr;
   if ((rc = sgx_reads_pack(ctx, rs.bases.data(), rs.off.data(), rs.size(), &reads)) != SGX_OK) return fail(ctx, "sgx_reads_pack", rc);
@@ -324,8 +389,8 @@ int cmd_overlap(int argc, char** argv) {
   if ((rc = sgx_fm_attach_reads(ctx, rev, rsai.data(), rsai.size(), reads)) != SGX_OK) return fail(ctx, "sgx_fm_attach_reads", rc);
   info("fm-index: %llu symbols in %zu runs (%.4f symbols per run)", (unsigned long long)nf, runs.size(),
        runs.empty() ? 0.0 : (double)nf / runs.size());
-  const std::vector<uint32_t> rank = name_ranks(rs.names);
   sgx_edges ed;
+  rank_thread.join();
   rc = sgx_overlap_edges(ctx, fwd, rev, reads, 0, rs.size(), min_overlap, exhaustive ? 0 : 1, rcomp ? 1 : 0, rank.data(), &ed);
   if (rc != SGX_OK) return fail(ctx, "sgx_overlap_edges", rc);
   const double t_search = now_s();
@@ -334,7 +399,7 @@ int cmd_overlap(int argc, char** argv) {
        (unsigned long long)(ed.lookups_search + ed.lookups_extract));
 
   // ---- ASQG: HT, all VT (input order), all ED (src/bigraph.cpp:532-616 requires this order)
-  GzChunkWriter gz(output + ".asqg.gz", (unsigned)o.threads);
+  GzChunkWriter gz(output + ".asqg.gz", (unsigned)o.threads, o.gzip_level);
   if (!gz.ok()) {
     fprintf(stderr, "ERROR siga - Failed to create ASQG %s.asqg.gz\n", output.c_str());
     return -1;
@@ -441,31 +506,14 @@ int cmd_rmdup(int argc, char** argv) {
   info("input: %s", input.c_str());
   info("output: %s", output.c_str());
   const double t0 = now_s();
-  uint64_t ns = 0, nf = 0, rns = 0, rnf = 0;
-  std::vector<uint8_t> runs, rruns;
-  std::vector<uint32_t> sai, rsai;
-  if (!read_bwt(output + ".bwt", &ns, &nf, &runs) || !read_bwt(output + ".rbwt", &rns, &rnf, &rruns)) {
-    fprintf(stderr, "ERROR siga - Failed to load FMIndex from %s\n", input.c_str());
-    return -1;
-  }
-  if (!read_sai(output + ".sai", &sai) || !read_sai(output + ".rsai", &rsai)) {
-    fprintf(stderr, "ERROR siga - failed to load suffix array index %s\n", output.c_str());
-    return -1;
-  }
-  ReadSet rs;
-  std::string err;
-  if (!read_sequences(input, &rs, &err)) {
-    fprintf(stderr, "ERROR siga - %s\n", err.c_str());
-    return -1;
-  }
-  if (rs.size() != ns || rs.size() != sai.size() || rs.size() != rsai.size()) {
-    fprintf(stderr, "ERROR siga - %s holds %zu reads but the index was built from %llu\n", input.c_str(), rs.size(),
-            (unsigned long long)ns);
-    return -1;
-  }
-  sgx_ctx* ctx = nullptr;
-  int rc = sgx_init(o.device, &ctx);
-  if (rc != SGX_OK) return fail(nullptr, "sgx_init", rc);
+  LoadedInput in;
+  if (!load_input(input, output, o.device, &in)) return -1;
+  ReadSet& rs = in.rs;
+  std::vector<uint8_t>&runs = in.runs, &rruns = in.rruns;
+  std::vector<uint32_t>&sai = in.sai, &rsai = in.rsai;
+  const uint64_t nf = in.nf, rnf = in.rnf;
+  sgx_ctx* ctx = in.ctx;
+  int rc = SGX_OK;
   sgx_reads* reads = nullptr;
   sgx_fm *fwd = nullptr, *rev = nullptr;
   if ((rc = sgx_reads_pack(ctx, rs.bases.data(), rs.off.data(), rs.size(), &reads)) != SGX_OK) return fail(ctx, "sgx_reads_pack", rc);
