@@ -29,14 +29,16 @@
 
 #include "comm.cuh"
 #include "index_kernels.cuh"
+#include "shard_plan.h"
 
 namespace sgx {
 
 static const int kKeySyms = 8;
-static const uint32_t kKeySpace = 390625;  // 5^8
-static const uint32_t kKeyTop = 78125;     // 5^7
-static const int kSendBuckets = kMaxShards * 4;  // (destination shard, first base of the new suffix)
-static const int kMetaN = kSendBuckets + 4;      // per-shard values gathered every pass: send counts + A/C/G/T totals
+static const uint32_t kKeySpace = kPlanKeySpace;  // 5^8
+static const uint32_t kKeyTop = kPlanKeyTop;      // 5^7
+static const int kSendBuckets = kPlanSendBuckets;  // (destination shard, first base of the new suffix)
+static const int kMetaN = kPlanMetaN;              // per-shard values gathered every pass: send counts + A/C/G/T totals
+static_assert(kPlanMaxShards == kMaxShards, "shard_plan.h and comm.cuh disagree on the shard limit");
 
 struct ShardBounds {
   uint32_t b[kMaxShards + 1];
@@ -187,13 +189,6 @@ static __global__ void shard_meta_kernel(const uint64_t* __restrict__ bucket_sta
 // are, for c = A..T, the (sender 0, c) run, the (sender 1, c) run, ...: a permutation known from the gathered counts.
 // Entry e = c * world + s of the plan: first output slot, first receive-buffer slot, and the constant that turns the
 // sender-local rank part into a local row.
-struct RecvPlan {
-  uint64_t out0[kSendBuckets + 1];  // non-decreasing; out0[entries] = number of inserts
-  uint64_t src0[kSendBuckets];
-  long long K[kSendBuckets];
-  int entries;
-  int world;
-};
 
 // One thread per insert, in output (row) order: find its run, fetch the wire item, write id / local row / the symbol
 // its row holds (the base before the suffix, '$' when the read starts here).
@@ -354,29 +349,10 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
     }
     SGX_TRACE_TICK(k_gather);
     comm_allgather_u64_end(cm, kMetaN, M.data());
-    uint64_t moved = 0;
-    for (int s = 0; s < W; ++s) {
-      uint64_t run = 0;
-      for (int d = 0; d < W; ++d) {
-        cntm[s * W + d] = 0;
-        for (int c = 0; c < 4; ++c) cntm[s * W + d] += M[(size_t)s * kMetaN + d * 4 + c];
-        soff[s * W + d] = run;
-        run += cntm[s * W + d];
-      }
-      moved += run;
-    }
-    if (moved == 0) break;  // every read has ended
     std::vector<uint64_t> n_in(W, 0), n_new(W, 0), first_row(W + 1, 0);
-    for (int d = 0; d < W; ++d) {
-      uint64_t run = 0;
-      for (int s = 0; s < W; ++s) {
-        roff[d * W + s] = run;
-        run += cntm[s * W + d];
-      }
-      n_in[d] = run;
-      n_new[d] = n_cur_all[d] + run;
-      first_row[d + 1] = first_row[d] + n_new[d];
-    }
+    const uint64_t moved = shard_pass_counts(M.data(), W, n_cur_all.data(), cntm.data(), soff.data(), roff.data(), n_in.data(),
+                                             n_new.data(), first_row.data());
+    if (moved == 0) break;  // every read has ended
     for (int li = 0; li < nl; ++li) {
       send_ptr[li] = sh[li].send.p;
       recv_ptr[li] = sh[li].recv.p;
@@ -387,9 +363,6 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
     SGX_TRACE_TICK(k_recv);
 
     // ---- receiver side
-    uint64_t T[4] = {0, 0, 0, 0};
-    for (int s = 0; s < W; ++s)
-      for (int c = 0; c < 4; ++c) T[c] += M[(size_t)s * kMetaN + kSendBuckets + c];
     for (int li = 0; li < nl; ++li) {
       Shard<PosT>& s = sh[li];
       const int g = s.g;
@@ -397,31 +370,7 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
       SGX_REQUIRE(n_new[g] <= s.rows_final, SGX_ECUDA, "sharded index: a shard received more rows than were counted for it");
       if (held_new) {
         RecvPlan plan;
-        memset(&plan, 0, sizeof(plan));
-        plan.world = W;
-        plan.entries = 4 * W;
-        long long less_global = (long long)N;  // rows of suffixes starting with a symbol < c
-        uint64_t out_run = 0;
-        for (int c = 0; c < 4; ++c) {
-          long long before = 0;  // symbols c in the rows of shards before the sender
-          for (int q = 0; q < W; ++q) {
-            const uint64_t* mq = &M[(size_t)q * kMetaN];
-            long long less_local = 0;
-            uint64_t src = roff[g * W + q];  // the sender's block, then its runs of smaller symbols
-            for (int c2 = 0; c2 < c; ++c2) {
-              less_local += (long long)mq[kSendBuckets + c2];
-              src += mq[g * 4 + c2];
-            }
-            const int e = c * W + q;
-            plan.out0[e] = out_run;
-            plan.src0[e] = src;
-            plan.K[e] = less_global + before - less_local - (long long)first_row[g];
-            out_run += mq[g * 4 + c];
-            before += (long long)mq[kSendBuckets + c];
-          }
-          less_global += (long long)T[c];
-        }
-        plan.out0[4 * W] = out_run;
+        const uint64_t out_run = shard_recv_plan(M.data(), W, g, N, roff.data(), first_row.data(), &plan);
         SGX_REQUIRE(out_run == held_new, SGX_ECUDA, "sharded index: receive plan does not cover the received inserts");
         SGX_LAUNCH(ctx, (shard_place_kernel<PosT>), grid_for(held_new, 256), 256, 0, acc, (const WireItem<PosT>*)s.recv.p,
                    held_new, j, uniform_len, plan, s.ID2, s.NP2, s.SYM.p, s.KEY2);
@@ -488,25 +437,7 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
       const int g = s.g;
       int skip_first = 0;
       uint64_t extend = 0;
-      if (s.seg.n_rows) {
-        // does my first run continue a run of an earlier shard?
-        for (int p = g - 1; p >= 0; --p) {
-          if (seam[(size_t)p * kSeamN + 0] == 0) continue;
-          skip_first = seam[(size_t)p * kSeamN + 3] == s.seg.first_sym ? 1 : 0;
-          break;
-        }
-        // rows of later shards that continue my last run (only counted by the shard where the run starts)
-        const bool whole = s.seg.n_runs == 1;
-        if (!(whole && skip_first)) {
-          for (int q = g + 1; q < W; ++q) {
-            const uint64_t* sq = &seam[(size_t)q * kSeamN];
-            if (sq[0] == 0) continue;
-            if (sq[1] != s.seg.last_sym) break;
-            extend += sq[2];
-            if (sq[2] != sq[0]) break;  // that shard has further runs
-          }
-        }
-      }
+      shard_seam_rule(seam.data(), W, g, s.seg.n_runs, &skip_first, &extend);
       rle_emit(ctx, s.B, s.seg, skip_first, extend, &s.rle, &s.rle_bytes);
       d_b[li].alloc(1);
       SGX_CUDA(cudaMemcpyAsync(d_b[li].p, &s.rle_bytes, sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -576,17 +507,7 @@ void index_build_sharded(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, int
     std::vector<uint64_t> h(kKeySpace);
     SGX_CUDA(cudaMemcpyAsync(h.data(), hist.p, kKeySpace * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     SGX_CUDA(cudaStreamSynchronize(ctx->stream));
-    uint64_t total = 0;
-    for (uint32_t k = 0; k < kKeySpace; ++k) total += h[k];
-    bounds.b[0] = 0;
-    uint64_t cum = 0;
-    uint32_t key = 0;
-    for (int g = 1; g < W; ++g) {
-      const uint64_t want = total / W * g + (total % W) * g / W;
-      while (key < kKeySpace && cum < want) cum += h[key++];
-      bounds.b[g] = std::max<uint32_t>(std::max<uint32_t>(key, 1u), bounds.b[g - 1]);  // key 0 (the '$' rows) stays on shard 0
-    }
-    for (int g = W; g <= kMaxShards; ++g) bounds.b[g] = kKeySpace;
+    shard_bounds_from_hist(h.data(), W, bounds.b);
 
     DevBuf<uint64_t> rows(kMaxShards);
     SGX_CUDA(cudaMemsetAsync(rows.p, 0, kMaxShards * sizeof(uint64_t), ctx->stream));

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../siga_b200/csrc/overlap_logic.h"
+#include "../../siga_b200/csrc/shard_plan.h"
 
 using namespace sgx;
 
@@ -167,6 +168,39 @@ void hemu_hits_free(sgx_hits* h) {
   free(h->block_off);
   free(h->blocks);
   memset(h, 0, sizeof(*h));
+}
+
+// ---- host-side planning of the bucket-sharded index build (siga_b200/csrc/shard_plan.h), for the CPU emulation in
+//      tests/test_cpu_sharded_index.py
+int hemu_plan_consts(int* max_shards, int* send_buckets, int* meta_n, uint32_t* key_space, uint32_t* key_top) {
+  *max_shards = kPlanMaxShards;
+  *send_buckets = kPlanSendBuckets;
+  *meta_n = kPlanMetaN;
+  *key_space = kPlanKeySpace;
+  *key_top = kPlanKeyTop;
+  return (int)sizeof(RecvPlan);
+}
+void hemu_shard_bounds(const uint64_t* hist, int world, uint32_t* b) { shard_bounds_from_hist(hist, world, b); }
+int hemu_shard_owner(const uint32_t* b, int world, uint32_t key) { return shard_owner(b, world, key); }
+uint64_t hemu_shard_pass_counts(const uint64_t* M, int W, const uint64_t* n_cur, uint64_t* cnt, uint64_t* soff, uint64_t* roff,
+                                uint64_t* n_in, uint64_t* n_new, uint64_t* first_row) {
+  return shard_pass_counts(M, W, n_cur, cnt, soff, roff, n_in, n_new, first_row);
+}
+// plan flattened for ctypes: out0[entries+1], src0[entries], K[entries]
+uint64_t hemu_shard_recv_plan(const uint64_t* M, int W, int g, uint64_t n_reads, const uint64_t* roff, const uint64_t* first_row,
+                              uint64_t* out0, uint64_t* src0, long long* K) {
+  RecvPlan plan;
+  const uint64_t n = shard_recv_plan(M, W, g, n_reads, roff, first_row, &plan);
+  for (int e = 0; e < plan.entries; ++e) {
+    out0[e] = plan.out0[e];
+    src0[e] = plan.src0[e];
+    K[e] = plan.K[e];
+  }
+  out0[plan.entries] = plan.out0[plan.entries];
+  return n;
+}
+void hemu_shard_seam_rule(const uint64_t* seam, int W, int g, uint64_t my_runs, int* skip_first, uint64_t* extend_last) {
+  shard_seam_rule(seam, W, g, my_runs, skip_first, extend_last);
 }
 
 }  // extern "C"
