@@ -71,7 +71,7 @@ static void bcr_passes(sgx_ctx* ctx, const sgx_reads* reads, const ReadAcc& acc,
     SGX_LAUNCH(ctx, (bcr_tile_bounds_kernel<PosT>), grid_for(nact + 1, 256), 256, 0, (const PosT*)NP2, nact, ntiles,
                tile_k0.p);
     k_merge.tick();
-    SGX_LAUNCH(ctx, (bcr_merge_kernel<PosT>), (unsigned)ntiles, kMergeThreads, 0, (const uint8_t*)B, n_cur,
+    SGX_LAUNCH(ctx, (bcr_merge_kernel<PosT>), merge_grid(ctx, ntiles), kMergeThreads, 0, (const uint8_t*)B, n_cur,
                (const PosT*)NP2, (const uint8_t*)SYM2, nact, (const uint64_t*)tile_k0.p, Bn, n_new, ntiles, blk.p, tiletot.p);
     k_merge.tick();
     out->merge_launches++;

@@ -335,83 +335,171 @@ __global__ void bcr_tile_bounds_kernel(const PosT* __restrict__ NP, uint64_t nac
 }
 
 // Streaming merge of the old BWT (n_old rows) with the sorted inserts (rows NP[0..nact) of the NEW array, symbols
-// SYM) into Bn (n_new rows), plus the per-256-row symbol counts of Bn.  HBM-bound by design: a CTA produces 8192 rows
-// (4 KB), a thread 32 rows (one 16-byte store).  The old rows of the tile are staged in shared memory; a thread
-// first takes the 32 old nibbles that would land on its rows if it had no inserts (five shared-memory words and
-// four funnel shifts), then opens a 4-bit gap for each of its inserts (the bits of its word of the tile's insert
-// mask), which pushes the surplus old nibbles out at the top -- exactly the ones the next thread starts with.
+// SYM) into Bn (n_new rows), plus both levels of rank checkpoints of Bn.  A tile = 8192 output rows (4 KB), a thread
+// 32 rows (one 16-byte store).  The old rows of a tile are staged in shared memory; a thread first takes the 32 old
+// nibbles that would land on its rows if it had no inserts (five shared-memory words and four funnel shifts), then
+// opens a 4-bit gap for each of its inserts (the bits of its word of the tile's insert mask), which pushes the
+// surplus old nibbles out at the top -- exactly the ones the next thread starts with.
+//
+// The kernel is persistent (a CTA walks tiles blockIdx.x, + gridDim.x, ...) and software-pipelined, because one tile
+// is a chain of dependent global accesses (tile bounds -> old rows / insert rows -> symbols) and the first version,
+// one CTA per tile, spent its time waiting on that chain (1.6 TB/s):
+//   * the insert bounds of the tile after next are loaded while the current tile is processed,
+//   * the old rows of the next tile are copied global -> shared with cp.async into the other half of a double buffer,
+//   * the first insert (row, symbol) of every thread for the next tile is loaded into registers.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+static const int kMergeOldWords = kMergeTile / 8 + 16;  // staged old rows of a tile, 32-bit words
+
+// cp.async of the old rows of the tile whose inserts are [k0, k1): 16-byte vectors from the 32-row-aligned position at
+// or below its first old row (the arrays are padded).
+__device__ __forceinline__ void merge_stage_old(const uint8_t* __restrict__ Bo, uint64_t tile, uint64_t n_new, uint64_t k0,
+                                                uint64_t k1, uint32_t* dst) {
+  const uint64_t t0 = tile * kMergeTile;
+  const uint64_t t1 = min(t0 + (uint64_t)kMergeTile, n_new);
+  const uint64_t a0 = t0 - k0;
+  const uint32_t nold = (uint32_t)((t1 - t0) - (k1 - k0));
+  const uint64_t a0al = a0 & ~(uint64_t)31;
+  const uint32_t nvec = (nold + (uint32_t)(a0 - a0al) + 31) / 32;  // <= kMergeTile / 32 + 1 = 257: two rounds of 256 threads
+  const uint8_t* src = Bo + a0al / 2;
+  if (threadIdx.x < nvec) cp_async16(dst + 4 * threadIdx.x, src + threadIdx.x * 16u);
+  if (threadIdx.x + kMergeThreads < nvec)
+    cp_async16(dst + 4 * (threadIdx.x + kMergeThreads), src + (threadIdx.x + kMergeThreads) * 16u);
+}
+
 template <class PosT>
 __global__ void __launch_bounds__(kMergeThreads) bcr_merge_kernel(const uint8_t* __restrict__ Bo, uint64_t n_old,
                                                                   const PosT* __restrict__ NP, const uint8_t* __restrict__ SYM,
                                                                   uint64_t nact, const uint64_t* __restrict__ tile_k0,
                                                                   uint8_t* __restrict__ Bn, uint64_t n_new, uint64_t ntiles,
                                                                   uint2* __restrict__ blk, uint64_t* __restrict__ tiletot) {
-  __shared__ __align__(16) uint32_t oldw[kMergeTile / 8 + 16];
+  __shared__ __align__(16) uint32_t oldw[2][kMergeOldWords];
   __shared__ uint32_t mask[kMergeTile / 32];
-  __shared__ uint64_t sh[9];
-  const uint64_t t0 = (uint64_t)blockIdx.x * kMergeTile;
-  const uint64_t t1 = min(t0 + (uint64_t)kMergeTile, n_new);
-  const uint64_t k0 = tile_k0[blockIdx.x], k1 = tile_k0[blockIdx.x + 1];
-  const uint64_t a0 = t0 - k0;  // first old row of this tile
-  const uint32_t nold = (uint32_t)((t1 - t0) - (k1 - k0));
-  mask[threadIdx.x] = 0;
-  // old rows -> shared, 16-byte vectors from the 32-row-aligned position at or below a0 (the arrays are padded)
-  const uint64_t a0al = a0 & ~(uint64_t)31;
-  const uint32_t shift = (uint32_t)(a0 - a0al);  // nibbles
-  const uint32_t nvec = (nold + shift + 31) / 32;
-  for (uint32_t q = threadIdx.x; q < nvec; q += kMergeThreads)
-    reinterpret_cast<uint4*>(oldw)[q] = *reinterpret_cast<const uint4*>(Bo + a0al / 2 + (uint64_t)q * 16);
-  __syncthreads();
-  for (uint64_t k = k0 + threadIdx.x; k < k1; k += kMergeThreads) {
-    const uint32_t r = (uint32_t)((uint64_t)NP[k] - t0);
-    atomicOr(&mask[r >> 5], 1u << (r & 31));
+  __shared__ uint8_t symsh[kMergeTile];  // symbols of the tile's inserts, by ordinal
+  __shared__ uint32_t ckpt[64];
+  __shared__ uint32_t sh[8];
+  const uint64_t G = gridDim.x;
+  uint64_t tile = blockIdx.x;
+  if (tile >= ntiles) return;
+  // prologue: bounds of my first two tiles, old rows + first insert of the first
+  uint64_t k0 = tile_k0[tile], k1 = tile_k0[tile + 1];
+  uint64_t kn0 = 0, kn1 = 0;
+  if (tile + G < ntiles) {
+    kn0 = tile_k0[tile + G];
+    kn1 = tile_k0[tile + G + 1];
   }
-  __syncthreads();
-  const uint32_t m = mask[threadIdx.x];
-  uint64_t total;
-  const uint32_t pre = (uint32_t)block_excl_scan((uint64_t)__popc(m), sh, total);  // inserts before my first row
-  // the 32 old nibbles starting at the one that lands on my first row
-  const uint32_t o = shift + threadIdx.x * 32 - pre;
-  const uint32_t wi = o >> 3, sft = 4 * (o & 7);
-  uint32_t out[4];
-  {
-    const uint32_t w0 = oldw[wi], w1 = oldw[wi + 1], w2 = oldw[wi + 2], w3 = oldw[wi + 3], w4 = oldw[wi + 4];
-    out[0] = __funnelshift_r(w0, w1, sft);
-    out[1] = __funnelshift_r(w1, w2, sft);
-    out[2] = __funnelshift_r(w2, w3, sft);
-    out[3] = __funnelshift_r(w3, w4, sft);
+  merge_stage_old(Bo, tile, n_new, k0, k1, oldw[0]);
+  cp_async_commit();
+  uint64_t pre_np = 0;
+  uint32_t pre_sym = 0;
+  if (k0 + threadIdx.x < k1) {
+    pre_np = (uint64_t)NP[k0 + threadIdx.x];
+    pre_sym = SYM[k0 + threadIdx.x];
   }
-  // open a gap for every insert, lowest row first
-  uint32_t mm = m;
-  uint64_t kk = k0 + pre;
-  while (mm) {
-    const uint32_t p = (uint32_t)__ffs(mm) - 1;
-    mm &= mm - 1;
-    const uint32_t s = SYM[kk++];
-    const uint32_t wq = p >> 3, bit = 4 * (p & 7);
+  int s = 0;
+  for (;; tile += G, s ^= 1) {
+    const uint64_t tn = tile + G;
+    const bool have_next = tn < ntiles;
+    // next tile: stage its old rows into the other buffer (free since the end of the previous iteration)
+    if (have_next) merge_stage_old(Bo, tn, n_new, kn0, kn1, oldw[s ^ 1]);
+    cp_async_commit();
+    // bounds of the tile after next; first insert of the next tile
+    uint64_t knn0 = 0, knn1 = 0;
+    if (tn + G < ntiles) {
+      knn0 = tile_k0[tn + G];
+      knn1 = tile_k0[tn + G + 1];
+    }
+    uint64_t nxt_np = 0;
+    uint32_t nxt_sym = 0;
+    if (have_next && kn0 + threadIdx.x < kn1) {
+      nxt_np = (uint64_t)NP[kn0 + threadIdx.x];
+      nxt_sym = SYM[kn0 + threadIdx.x];
+    }
+
+    const uint64_t t0 = tile * kMergeTile;
+    const uint64_t t1 = min(t0 + (uint64_t)kMergeTile, n_new);
+    const uint64_t a0 = t0 - k0;  // first old row of this tile
+    const uint32_t shift = (uint32_t)(a0 & 31);  // nibbles between the staged vector start and a0
+    mask[threadIdx.x] = 0;
+    __syncthreads();
+    // insert mask + symbols by ordinal (the first insert of every thread is already in registers)
+    if (k0 + threadIdx.x < k1) {
+      const uint32_t r = (uint32_t)(pre_np - t0);
+      atomicOr(&mask[r >> 5], 1u << (r & 31));
+      symsh[threadIdx.x] = (uint8_t)pre_sym;
+    }
+    for (uint64_t k = k0 + threadIdx.x + kMergeThreads; k < k1; k += kMergeThreads) {
+      const uint32_t r = (uint32_t)((uint64_t)NP[k] - t0);
+      atomicOr(&mask[r >> 5], 1u << (r & 31));
+      symsh[k - k0] = SYM[k];
+    }
+    cp_async_wait<1>();  // the current tile's old rows (the group committed one iteration ago) have landed
+    __syncthreads();
+    const uint32_t m = mask[threadIdx.x];
+    const uint32_t pre = block_excl_scan32((uint32_t)__popc(m), sh);  // inserts before my first row
+    // the 32 old nibbles starting at the one that lands on my first row
+    const uint32_t* ow = oldw[s];
+    const uint32_t o = shift + threadIdx.x * 32 - pre;
+    const uint32_t wi = o >> 3, sft = 4 * (o & 7);
+    uint32_t out[4];
+    {
+      const uint32_t w0 = ow[wi], w1 = ow[wi + 1], w2 = ow[wi + 2], w3 = ow[wi + 3], w4 = ow[wi + 4];
+      out[0] = __funnelshift_r(w0, w1, sft);
+      out[1] = __funnelshift_r(w1, w2, sft);
+      out[2] = __funnelshift_r(w2, w3, sft);
+      out[3] = __funnelshift_r(w3, w4, sft);
+    }
+    // open a gap for every insert, lowest row first
+    uint32_t mm = m;
+    uint32_t kk = pre;
+    while (mm) {
+      const uint32_t p = (uint32_t)__ffs(mm) - 1;
+      mm &= mm - 1;
+      const uint32_t sy = symsh[kk++];
+      const uint32_t wq = p >> 3, bit = 4 * (p & 7);
 #pragma unroll
-    for (int i = 3; i >= 1; --i)
-      if ((uint32_t)i > wq) out[i] = (out[i] << 4) | (out[i - 1] >> 28);
+      for (int i = 3; i >= 1; --i)
+        if ((uint32_t)i > wq) out[i] = (out[i] << 4) | (out[i - 1] >> 28);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if ((uint32_t)i == wq) {
-        const uint32_t lowm = (1u << bit) - 1u;
-        const uint32_t up = bit < 28 ? ((out[i] >> bit) << (bit + 4)) : 0u;
-        out[i] = (out[i] & lowm) | (s << bit) | up;
+      for (int i = 0; i < 4; ++i) {
+        if ((uint32_t)i == wq) {
+          const uint32_t lowm = (1u << bit) - 1u;
+          const uint32_t up = bit < 28 ? ((out[i] >> bit) << (bit + 4)) : 0u;
+          out[i] = (out[i] & lowm) | (sy << bit) | up;
+        }
       }
     }
-  }
-  // rows past the end of the array stay zero
-  const uint64_t row0 = t0 + (uint64_t)threadIdx.x * 32;
-  uint32_t valid = row0 >= t1 ? 0u : (uint32_t)min((uint64_t)32, t1 - row0);
+    // rows past the end of the array stay zero
+    const uint64_t row0 = t0 + (uint64_t)threadIdx.x * 32;
+    uint32_t valid = 32;
+    if (t1 - t0 != (uint64_t)kMergeTile) {  // only the last tile of the array is partial
+      valid = row0 >= t1 ? 0u : (uint32_t)min((uint64_t)32, t1 - row0);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint32_t vw = valid >= 8u * (i + 1) ? 8u : (valid > 8u * i ? valid - 8u * i : 0u);
-    out[i] &= vw >= 8 ? 0xffffffffu : ((1u << (4 * vw)) - 1u);
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t vw = valid >= 8u * (i + 1) ? 8u : (valid > 8u * i ? valid - 8u * i : 0u);
+        out[i] &= vw >= 8 ? 0xffffffffu : ((1u << (4 * vw)) - 1u);
+      }
+    }
+    if (valid) *reinterpret_cast<uint4*>(Bn + row0 / 2) = make_uint4(out[0], out[1], out[2], out[3]);
+    tile_checkpoints(out, tile, ntiles, ckpt, blk, tiletot);
+    __syncthreads();  // mask / symsh / oldw[s] / ckpt are free for the next iteration
+    if (!have_next) break;
+    k0 = kn0;
+    k1 = kn1;
+    kn0 = knn0;
+    kn1 = knn1;
+    pre_np = nxt_np;
+    pre_sym = nxt_sym;
   }
-  if (valid) *reinterpret_cast<uint4*>(Bn + row0 / 2) = make_uint4(out[0], out[1], out[2], out[3]);
-  __syncthreads();  // everyone is done with mask[] / oldw[]: reuse mask[] for the checkpoint scan
-  tile_checkpoints(out, blockIdx.x, ntiles, mask, blk, tiletot);
+  cp_async_wait<0>();
 }
 
 // ---- 3. run-length encoding ------------------------------------------------------------------------------------------
@@ -473,6 +561,12 @@ static __global__ void len_hist_kernel(const uint32_t* __restrict__ len, uint64_
   const uint32_t l = len[i];
   const unsigned m = __match_any_sync(act, l);
   if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&hist[l], (uint32_t)__popc(m));
+}
+
+// persistent grid of the merge kernel: enough CTAs to fill every SM (31 registers: 8 CTAs of 256 threads per SM), never more than tiles
+inline unsigned merge_grid(const sgx_ctx* ctx, uint64_t ntiles) {
+  const uint64_t cap = (uint64_t)ctx->sm_count * 8;
+  return (unsigned)(ntiles < cap ? (ntiles ? ntiles : 1) : cap);
 }
 
 // ---- host helpers defined in index.cu, shared with index_sharded.cu ------------------------------------------------

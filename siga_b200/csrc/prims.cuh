@@ -43,6 +43,24 @@ __device__ __forceinline__ uint64_t block_excl_scan(uint64_t v, uint64_t* sh /* 
   return off + x - v;
 }
 
+// 32-bit variant for per-thread counts whose block total fits 32 bits (two barriers, one shuffle per step).
+__device__ __forceinline__ uint32_t block_excl_scan32(uint32_t v, uint32_t* sh /* >= 8 entries */) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) sh[w] = x;
+  __syncthreads();
+  uint32_t off = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    if (q < w) off += sh[q];  // 8 warps: a short serial sum beats a second shuffle scan + barrier
+  return off + x - v;
+}
+
 static __global__ void scan_tile_reduce_kernel(const uint64_t* __restrict__ in, uint64_t n, uint64_t* __restrict__ tilesum) {
   __shared__ uint64_t sh[9];
   const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanIpt;
