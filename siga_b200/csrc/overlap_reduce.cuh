@@ -245,28 +245,33 @@ ov_reduce_kernel(ReadsView qreads, ReadsView treads, SaView sf, SaView sr, uint6
           R += tot;
         }
         if (slow) break;
-        // containment blocks belong to both lists of their index side: rows tagged 0xfff0 + 2*(0: list fa, 1: list fb)
-        // + (0/1: which of the side's two containment blocks)
-        const uint32_t Rc = R;  // candidate rows are [0, Rc)
-        for (int h = 0; h < 2 && !slow; ++h) {
+        // ---- SubMaximalBlockFilter precondition, on the entries: the capped[0] intervals of one list (its candidate
+        //      blocks plus the containment blocks of its index side, which belong to both lists of that side) must be
+        //      pairwise disjoint
+        bool inter = false;
+        for (int h = 0; h < 2; ++h) {
           const int f = h == 0 ? fa : fb;
           const int q0 = f < 2 ? 0 : 2;
-          for (int q = q0; q < q0 + 2 && !slow; ++q) {
-            if (!nk[q]) continue;
-            const RdEnt c = rd_contain<LEAN>(bt, r, q);
-            const uint64_t ww = (uint64_t)c.hi - c.lo + 1;
-            if (R + ww > rows_cap) {
-              slow = true;
-              break;
+          const uint32_t nE = nc[f];
+          for (uint32_t i = lane; i < nE + 2; i += 32) {
+            RdEnt a;
+            if (i < nE) a = rd_cand<LEAN>(bt, r, f, i);
+            else if (nk[q0 + (i - nE)]) a = rd_contain<LEAN>(bt, r, q0 + (int)(i - nE));
+            else continue;
+            for (uint32_t i2 = 0; i2 < i; ++i2) {
+              RdEnt c;
+              if (i2 < nE) c = rd_cand<LEAN>(bt, r, f, i2);
+              else if (nk[q0 + (i2 - nE)]) c = rd_contain<LEAN>(bt, r, q0 + (int)(i2 - nE));
+              else continue;
+              if (rd_intersect(a.lo, a.hi, c.lo, c.hi)) inter = true;
             }
-            for (uint32_t x = lane; x < (uint32_t)ww; x += 32) {
-              r_row[R + x] = c.lo + x;
-              r_ent[R + x] = (uint16_t)(0xfff0u + 2 * h + (q - q0));
-            }
-            R += (uint32_t)ww;
           }
         }
-        if (slow) break;
+        if (__any_sync(0xffffffffu, inter)) {
+          slow = true;  // intervals of one list intersect (periodic sequence): SubMaximalBlockFilter must run
+          break;
+        }
+        const uint32_t Rc = R;  // candidate rows
         __syncwarp();
         // ---- per candidate row: target read, extension string in query orientation (word level)
         //      (exhaustive mode, src/overlap_builder.cpp:1175-1178, only needs the rows and the intersection test)
@@ -311,23 +316,16 @@ ov_reduce_kernel(ReadsView qreads, ReadsView treads, SaView sf, SaView sr, uint6
           break;
         }
         __syncwarp();
-        // ---- one pass over the other rows: shared row inside a list (intersection), transitive rows, class heads
-        bool inter = false;
-        for (uint32_t s = lane; s < R; s += 32) {
+        // ---- transitive rows and class heads.  Rows with a longer overlap are scanned from the end of the table
+        //      (entries of a list come in increasing overlap length): the longest overlaps have the shortest
+        //      extensions and are the likeliest prefixes, so the scan usually stops after a few rows.
+        for (uint32_t s = lane; s < Rc && irreducible; s += 32) {
           const uint32_t es = r_ent[s];
-          const uint32_t ls = es >= 0xfff0u ? (es - 0xfff0u) >> 1 : (es < na ? 0u : 1u);  // 0 = list fa, 1 = list fb
-          const uint32_t rows = r_row[s];
-          const bool cand_row = s < Rc;
-          const uint32_t ka = (cand_row && irreducible) ? r_k[s] : 0;
+          const uint32_t ka = r_k[s];
           const uint64_t* ea = ext + (size_t)s * extw;
           bool red = false;
-          for (uint32_t b2 = 0; b2 < R; ++b2) {
-            if (b2 != s && r_row[b2] == rows) {
-              const uint32_t eb2 = r_ent[b2];
-              const uint32_t lb = eb2 >= 0xfff0u ? (eb2 - 0xfff0u) >> 1 : (eb2 < na ? 0u : 1u);
-              if (lb == ls && eb2 != es) inter = true;
-            }
-            if (!irreducible || !cand_row || red || b2 >= Rc || r_k[b2] <= ka) continue;
+          for (uint32_t b2 = Rc; b2-- > 0 && !red;) {
+            if (r_k[b2] <= ka) continue;
             const uint32_t nb = r_n[b2];
             const uint64_t* eb = ext + (size_t)b2 * extw;
             bool eq = true;
@@ -339,22 +337,17 @@ ov_reduce_kernel(ReadsView qreads, ReadsView treads, SaView sf, SaView sr, uint6
             }
             red = eq;
           }
-          if (cand_row) {
-            bool head = true;
-            if (!EDGES && irreducible && s > 0 && r_ent[s - 1] == es) {
-              const uint64_t* ep = ext + (size_t)(s - 1) * extw;
-              bool same = true;
-              for (uint32_t q = 0; q < extw && same; ++q) same = ea[q] == ep[q];
-              head = !same;
-            }
-            r_flag[s] = (uint16_t)((red ? 1u : 0u) | (head ? 2u : 0u));
+          bool head = true;
+          if (!EDGES && s > 0 && r_ent[s - 1] == es) {
+            const uint64_t* ep = ext + (size_t)(s - 1) * extw;
+            bool same = true;
+            for (uint32_t q = 0; q < extw && same; ++q) same = ea[q] == ep[q];
+            head = !same;
           }
+          r_flag[s] = (uint16_t)((red ? 1u : 0u) | (head ? 2u : 0u));
         }
-        if (__any_sync(0xffffffffu, inter)) {
-          slow = true;  // intervals of one list intersect (periodic sequence): SubMaximalBlockFilter must run
-          break;
-        }
-        R = Rc;  // the containment rows were only needed for the intersection test
+        if (!irreducible)
+          for (uint32_t s = lane; s < Rc; s += 32) r_flag[s] = 2u;
         __syncwarp();
         if (EDGES) {
           // ---- every surviving row is one candidate edge
