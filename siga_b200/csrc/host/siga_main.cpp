@@ -12,6 +12,8 @@
 // and ignored (there is no log4cxx here).  The per-thread .hits.gz files of the reference are an internal detail
 // nothing downstream reads and are not produced.
 #include <getopt.h>
+#include <sys/wait.h>
+#include <unistd.h>
 #include <strings.h>
 #include <zlib.h>
 
@@ -153,6 +155,7 @@ struct CommonOpts {
   int threads = 0;     // host-side text / gzip work; 0 = all hardware threads (the search itself runs on the GPU)
   int device = 0;
   int gzip_level = 1;  // .asqg.gz members are written at zlib level 1 unless --gzip-level says otherwise
+  int gpus = 1;        // --gpus N: one forked process per GPU (devices device .. device + N - 1)
   bool help = false;
 };
 
@@ -168,9 +171,9 @@ struct LoadedInput {
   bool ok_bwt = false, ok_rbwt = false, ok_sai = false, ok_rsai = false, ok_reads = false;
 };
 
-bool load_input(const std::string& input, const std::string& output, int device, LoadedInput* in) {
+bool load_input(const std::string& input, const std::string& output, int device, LoadedInput* in, bool with_ctx = true) {
   std::vector<std::thread> pool;
-  pool.emplace_back([&]() { in->ctx_rc = sgx_init(device, &in->ctx); });
+  if (with_ctx) pool.emplace_back([&]() { in->ctx_rc = sgx_init(device, &in->ctx); });
   pool.emplace_back([&]() { in->ok_bwt = read_bwt(output + ".bwt", &in->ns, &in->nf, &in->runs); });
   pool.emplace_back([&]() { in->ok_rbwt = read_bwt(output + ".rbwt", &in->rns, &in->rnf, &in->rruns); });
   pool.emplace_back([&]() { in->ok_sai = read_sai(output + ".sai", &in->sai); });
@@ -201,229 +204,35 @@ bool load_input(const std::string& input, const std::string& output, int device,
   return true;
 }
 
-int usage_index() {
-  printf("siga index [OPTION] ... READSFILE\n"
-         "Index the reads in READSFILE using a suffixarray/bwt (built on the GPU)\n\n"
-         "      -h, --help                       display this help and exit\n\n"
-         "      -a, --algorithm=STR              suffix ordering of the BWT. STR can be:\n"
-         "                                       sais  - equal suffixes ordered by read index\n"
-         "                                       sais2 - plain suffix order of the concatenated reads (default)\n"
-         "      -t, --threads=NUM                host threads for output formatting (default: 1)\n"
-         "      -p, --prefix=PREFIX              write index to file using PREFIX instead of prefix of READSFILE\n"
-         "          --no-forward                 suppress construction of the forward BWT.\n"
-         "          --no-reverse                 suppress construction of the reverse BWT.\n"
-         "          --device=NUM                 CUDA device (default: 0)\n\n");
-  return 256;
-}
-
-int usage_overlap() {
-  printf("siga overlap [OPTION] ... READSFILE\n"
-         "Compute pairwise overlap between all the sequences in READS (searched on the GPU)\n\n"
-         "      -h, --help                       display this help and exit\n\n"
-         "      -t, --threads=NUM                host threads for output formatting/compression (default: all)\n"
-         "          --gzip-level=N               zlib level of the .asqg.gz members, 1..9 (default: 1)\n"
-         "          --batch-size=NUM             accepted for compatibility (batching is internal)\n"
-         "      -m, --min-overlap=LEN            minimum overlap required between two reads (default: 10)\n"
-         "      -p, --prefix=PREFIX              read the index from / write the graph to PREFIX instead of prefix of READSFILE\n"
-         "      -x, --exhaustive                 output all overlaps, including transitive edges\n"
-         "          --no-opposite-strand         treat all reads as forward strand\n"
-         "          --device=NUM                 CUDA device (default: 0)\n\n");
-  return 256;
-}
-
-int cmd_index(int argc, char** argv) {
-  enum { OPT_NO_REVERSE = 1000, OPT_NO_FORWARD, OPT_DEVICE };
-  static const option longopts[] = {{"log4cxx", required_argument, nullptr, 'c'}, {"ini", required_argument, nullptr, 's'},
-                                    {"prefix", required_argument, nullptr, 'p'},  {"threads", required_argument, nullptr, 't'},
-                                    {"algorithm", required_argument, nullptr, 'a'}, {"no-reverse", no_argument, nullptr, OPT_NO_REVERSE},
-                                    {"no-forward", no_argument, nullptr, OPT_NO_FORWARD}, {"device", required_argument, nullptr, OPT_DEVICE},
-                                    {"help", no_argument, nullptr, 'h'},          {nullptr, 0, nullptr, 0}};
-  CommonOpts o;
-  std::string algorithm = "sais2";
-  bool fwd = true, rev = true;
-  int c;
-  while ((c = getopt_long(argc, argv, "c:s:a:t:p:g:h", longopts, nullptr)) != -1) {
-    switch (c) {
-      case 'a': algorithm = optarg; break;
-      case 't': o.threads = atoi(optarg); break;
-      case 'p': o.prefix = optarg; break;
-      case OPT_NO_REVERSE: rev = false; break;
-      case OPT_NO_FORWARD: fwd = false; break;
-      case OPT_DEVICE: o.device = atoi(optarg); break;
-      case 'h': o.help = true; break;
-      default: break;
-    }
-  }
-  if (o.help || argc - optind != 1) return usage_index();
-  const std::string input = argv[optind];
-  const std::string output = o.prefix.empty() ? stem(input) : o.prefix;
-  info("input: %s", input.c_str());
-  info("output: %s.(.sai|.bwt|.rsai|.rbwt)", output.c_str());
-  info("algorithm: %s", algorithm.c_str());
-  int order;
-  if (strcasecmp(algorithm.c_str(), "sais") == 0) order = SGX_ORDER_SAIS;
-  else if (strcasecmp(algorithm.c_str(), "sais2") == 0) order = SGX_ORDER_SAIS2;
-  else {
-    // the reference accepts "rope" and silently writes nothing (SURVEY.md Appendix D.2); refuse instead
-    fprintf(stderr, "ERROR siga - Failed to create suffix array builder algorithm %s\n", algorithm.c_str());
-    return -1;
-  }
-  const double t0 = now_s();
-  ReadSet rs;
-  std::string err;
-  info("loading reads: %s", input.c_str());
-  sgx_ctx* ctx = nullptr;
-  int rc_init = SGX_OK;
-  std::thread init_thread([&]() { rc_init = sgx_init(o.device, &ctx); });  // CUDA start-up overlaps the parse
-  const bool parsed = read_sequences(input, &rs, &err);
-  init_thread.join();
-  if (!parsed) {
-    fprintf(stderr, "ERROR siga - %s\n", err.c_str());
-    return -1;
-  }
-  if (rc_init != SGX_OK) return fail(nullptr, "sgx_init", rc_init);
-  int rc = SGX_OK;
-  sgx_reads* reads = nullptr;
-  rc = sgx_reads_pack(ctx, rs.bases.data(), rs.off.data(), rs.size(), &reads);
-  if (rc != SGX_OK) return fail(ctx, "sgx_reads_pack", rc);
-  // the files of one strand are written on a host thread while the device builds the other strand
-  sgx_index_out outs[2];
-  std::thread writers[2];
-  bool wrote[2] = {true, true};
-  for (int pass = 0; pass < 2; ++pass) {
-    if ((pass == 0 && !fwd) || (pass == 1 && !rev)) continue;
-    info("building %s index on device %d", pass == 0 ? "forward" : "reverse", o.device);
-    sgx_index_out& out = outs[pass];
-    rc = sgx_index_build(ctx, reads, order, pass, &out);
-    if (rc != SGX_OK) {
-      for (auto& w : writers)
-        if (w.joinable()) w.join();
-      return fail(ctx, "sgx_index_build", rc);
-    }
-    const std::string sa = output + (pass == 0 ? ".sai" : ".rsai"), bw = output + (pass == 0 ? ".bwt" : ".rbwt");
-    info("%s: %llu strings, %llu suffixes, %llu runs; device %.1f ms (%llu kernel launches)", bw.c_str(),
-         (unsigned long long)out.n_strings, (unsigned long long)out.n_suffixes, (unsigned long long)out.n_runs, out.ms_total,
-         (unsigned long long)out.launches);
-    writers[pass] = std::thread([&outs, &wrote, pass, sa, bw]() {
-      const sgx_index_out& o2 = outs[pass];
-      bool a = false, b = false;
-      std::thread t([&]() { a = write_sai(sa, o2.sai, o2.n_strings); });
-      b = write_bwt(bw, o2.n_strings, o2.n_suffixes, o2.rle, o2.n_runs);
-      t.join();
-      wrote[pass] = a && b;
-    });
-  }
-  for (int pass = 0; pass < 2; ++pass) {
-    if (!writers[pass].joinable()) continue;
-    writers[pass].join();
-    sgx_index_out_free(&outs[pass]);
-    if (!wrote[pass]) {
-      fprintf(stderr, "ERROR siga - failed to write the %s index files of %s\n", pass == 0 ? "forward" : "reverse", output.c_str());
-      return -1;
-    }
-  }
-  sgx_reads_free(reads);
-  sgx_shutdown(ctx);
-  info("wall: %.3f sec", now_s() - t0);
-  return 0;
-}
-
-int cmd_overlap(int argc, char** argv) {
-  enum { OPT_BATCH_SIZE = 1000, OPT_NO_RC, OPT_DEVICE, OPT_GZIP_LEVEL };
-  static const option longopts[] = {{"log4cxx", required_argument, nullptr, 'c'},   {"ini", required_argument, nullptr, 's'},
-                                    {"prefix", required_argument, nullptr, 'p'},    {"threads", required_argument, nullptr, 't'},
-                                    {"batch-size", required_argument, nullptr, OPT_BATCH_SIZE},
-                                    {"min-overlap", required_argument, nullptr, 'm'}, {"exhaustive", no_argument, nullptr, 'x'},
-                                    {"no-opposite-strand", no_argument, nullptr, OPT_NO_RC},
-                                    {"device", required_argument, nullptr, OPT_DEVICE}, {"help", no_argument, nullptr, 'h'},
-                                    {"gzip-level", required_argument, nullptr, OPT_GZIP_LEVEL}, {nullptr, 0, nullptr, 0}};
-  CommonOpts o;
-  unsigned min_overlap = 10;
-  bool exhaustive = false, rcomp = true;
-  int c;
-  while ((c = getopt_long(argc, argv, "c:s:t:p:m:xh", longopts, nullptr)) != -1) {
-    switch (c) {
-      case 't': o.threads = atoi(optarg); break;
-      case 'p': o.prefix = optarg; break;
-      case 'm': min_overlap = (unsigned)atoi(optarg); break;
-      case 'x': exhaustive = true; break;
-      case OPT_NO_RC: rcomp = false; break;
-      case OPT_GZIP_LEVEL: o.gzip_level = std::max(1, std::min(9, atoi(optarg))); break;
-      case OPT_DEVICE: o.device = atoi(optarg); break;
-      case 'h': o.help = true; break;
-      default: break;
-    }
-  }
-  if (o.help || argc - optind != 1) return usage_overlap();
-  if (o.threads <= 0) o.threads = (int)std::thread::hardware_concurrency();
-  const std::string input = argv[optind];
-  const std::string output = o.prefix.empty() ? stem(input) : o.prefix;
-  info("input: %s", input.c_str());
-  info("output: %s.asqg.gz", output.c_str());
-  const double t0 = now_s();
-
-  LoadedInput in;
-  if (!load_input(input, output, o.device, &in)) return -1;
-  ReadSet& rs = in.rs;
-  std::vector<uint8_t>&runs = in.runs, &rruns = in.rruns;
-  std::vector<uint32_t>&sai = in.sai, &rsai = in.rsai;
-  const uint64_t nf = in.nf, rnf = in.rnf;
-  sgx_ctx* ctx = in.ctx;
-  int rc = SGX_OK;
-  const double t_load = now_s();
-
-  std::vector<uint32_t> rank;
-  std::thread rank_thread([&]() { rank = name_ranks(rs.names); });  // host sort of the names while the device loads the index
-  struct Joiner {
-    std::thread& t;
-    ~Joiner() {
-      if (t.joinable()) t.join();
-    }
-  } rank_joiner{rank_thread};
-  sgx_reads* reads = nullptr;
-  sgx_fm *fwd = nullptr, *rev = nullptr;
-  if ((rc = sgx_reads_pack(ctx, rs.bases.data(), rs.off.data(), rs.size(), &reads)) != SGX_OK) return fail(ctx, "sgx_reads_pack", rc);
-  if ((rc = sgx_fm_create(ctx, runs.data(), runs.size(), nf, &fwd)) != SGX_OK) return fail(ctx, "sgx_fm_create", rc);
-  if ((rc = sgx_fm_create(ctx, rruns.data(), rruns.size(), rnf, &rev)) != SGX_OK) return fail(ctx, "sgx_fm_create", rc);
-  if ((rc = sgx_fm_attach_reads(ctx, fwd, sai.data(), sai.size(), reads)) != SGX_OK) return fail(ctx, "sgx_fm_attach_reads", rc);
-  if ((rc = sgx_fm_attach_reads(ctx, rev, rsai.data(), rsai.size(), reads)) != SGX_OK) return fail(ctx, "sgx_fm_attach_reads", rc);
-  info("fm-index: %llu symbols in %zu runs (%.4f symbols per run)", (unsigned long long)nf, runs.size(),
-       runs.empty() ? 0.0 : (double)nf / runs.size());
-  sgx_edges ed;
-  rank_thread.join();
-  rc = sgx_overlap_edges(ctx, fwd, rev, reads, 0, rs.size(), min_overlap, exhaustive ? 0 : 1, rcomp ? 1 : 0, rank.data(), &ed);
-  if (rc != SGX_OK) return fail(ctx, "sgx_overlap_edges", rc);
-  const double t_search = now_s();
-  info("processed %zu sequences: %llu blocks, %llu edges; device %.1f ms (search %.1f ms, post %.1f ms; %llu rank lookups)",
-       rs.size(), (unsigned long long)ed.n_blocks, (unsigned long long)ed.n_edges, ed.ms_total, ed.ms_search, ed.ms_extract,
-       (unsigned long long)(ed.lookups_search + ed.lookups_extract));
-
-  // ---- ASQG: HT, all VT (input order), all ED (src/bigraph.cpp:532-616 requires this order)
-  GzChunkWriter gz(output + ".asqg.gz", (unsigned)o.threads, o.gzip_level);
-  if (!gz.ok()) {
-    fprintf(stderr, "ERROR siga - Failed to create ASQG %s.asqg.gz\n", output.c_str());
-    return -1;
-  }
-  const size_t n = rs.size();
+// Writes the HT line / the VT lines of reads [first, first + ed.n_reads) / the ED lines of `ed` as gzip members.
+// One .asqg.gz = HT, all VT (input order), all ED (src/bigraph.cpp:532-616 requires this order); concatenated gzip
+// members are a valid gzip file, which is how the multi-GPU run assembles its output from per-rank parts.
+bool write_asqg(const std::string& path, const CommonOpts& o, const ReadSet& rs, const sgx_edges& ed, uint64_t first,
+                unsigned min_overlap, bool with_ht, bool with_vt, bool with_ed) {
+  GzChunkWriter gz(path, (unsigned)o.threads, o.gzip_level);
+  if (!gz.ok()) return false;
+  const size_t n = with_vt ? (size_t)ed.n_reads : 0;
   const size_t vt_chunk = 1 << 16, ed_chunk = 1 << 18;
-  const size_t n_vt = (n + vt_chunk - 1) / vt_chunk, n_ed = (ed.n_edges + ed_chunk - 1) / ed_chunk;
-  bool good = gz.write_chunks(1 + n_vt + n_ed, [&](size_t ci, std::string* text) {
-    if (ci == 0) {
+  const size_t n_ht = with_ht ? 1 : 0;
+  const size_t n_vt = (n + vt_chunk - 1) / vt_chunk, n_ed = with_ed ? (ed.n_edges + ed_chunk - 1) / ed_chunk : 0;
+  return gz.write_chunks(n_ht + n_vt + n_ed, [&](size_t ci, std::string* text) {
+    if (ci < n_ht) {
       *text = "HT\tVN:i:1\tOL:i:" + std::to_string(min_overlap) + "\tCN:i:1\n";  // IN/ER/TE are never set on this path
-    } else if (ci <= n_vt) {
-      const size_t b = (ci - 1) * vt_chunk, e = std::min(n, b + vt_chunk);
+    } else if (ci < n_ht + n_vt) {
+      const size_t b = (ci - n_ht) * vt_chunk, e = std::min(n, b + vt_chunk);
       text->reserve((e - b) * 200);
-      for (size_t i = b; i < e; ++i) {
+      for (size_t k = b; k < e; ++k) {
+        const size_t i = first + k;
         *text += "VT\t";
         *text += rs.names[i];
         *text += '\t';
         text->append(rs.bases, rs.off[i], rs.off[i + 1] - rs.off[i]);
-        *text += ed.substring[i] ? "\tSS:i:1" : "\tSS:i:0";
+        *text += ed.substring[k] ? "\tSS:i:1" : "\tSS:i:0";
         append_comment_tags(rs.comments[i], text);
         *text += '\n';
       }
     } else {
-      const size_t b = (ci - 1 - n_vt) * ed_chunk, e = std::min<size_t>(ed.n_edges, b + ed_chunk);
+      const size_t b = (ci - n_ht - n_vt) * ed_chunk, e = std::min<size_t>(ed.n_edges, b + ed_chunk);
       text->reserve((e - b) * 48);
       for (size_t k = b; k < e; ++k) {
         const sgx_edge& g = ed.edges[k];
@@ -451,6 +260,359 @@ int cmd_overlap(int argc, char** argv) {
       }
     }
   });
+}
+
+bool append_file(FILE* dst, const std::string& path) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  std::vector<char> buf(1 << 22);
+  bool ok = true;
+  size_t k;
+  while (ok && (k = fread(buf.data(), 1, buf.size(), f)) > 0) ok = fwrite(buf.data(), 1, k, dst) == k;
+  fclose(f);
+  return ok;
+}
+
+int usage_index() {
+  printf("siga index [OPTION] ... READSFILE\n"
+         "Index the reads in READSFILE using a suffixarray/bwt (built on the GPU)\n\n"
+         "      -h, --help                       display this help and exit\n\n"
+         "      -a, --algorithm=STR              suffix ordering of the BWT. STR can be:\n"
+         "                                       sais  - equal suffixes ordered by read index\n"
+         "                                       sais2 - plain suffix order of the concatenated reads (default)\n"
+         "      -t, --threads=NUM                host threads for output formatting (default: 1)\n"
+         "      -p, --prefix=PREFIX              write index to file using PREFIX instead of prefix of READSFILE\n"
+         "          --no-forward                 suppress construction of the forward BWT.\n"
+         "          --no-reverse                 suppress construction of the reverse BWT.\n"
+         "          --gpus=N                     build each index with N GPUs together (rows sharded by leading k-mer, NCCL)\n"
+         "          --device=NUM                 CUDA device (default: 0)\n\n");
+  return 256;
+}
+
+int usage_overlap() {
+  printf("siga overlap [OPTION] ... READSFILE\n"
+         "Compute pairwise overlap between all the sequences in READS (searched on the GPU)\n\n"
+         "      -h, --help                       display this help and exit\n\n"
+         "      -t, --threads=NUM                host threads for output formatting/compression (default: all)\n"
+         "          --gzip-level=N               zlib level of the .asqg.gz members, 1..9 (default: 1)\n"
+         "          --gpus=N                     shard the reads over N GPUs (devices --device .. --device + N - 1), one process each\n"
+         "          --batch-size=NUM             accepted for compatibility (batching is internal)\n"
+         "      -m, --min-overlap=LEN            minimum overlap required between two reads (default: 10)\n"
+         "      -p, --prefix=PREFIX              read the index from / write the graph to PREFIX instead of prefix of READSFILE\n"
+         "      -x, --exhaustive                 output all overlaps, including transitive edges\n"
+         "          --no-opposite-strand         treat all reads as forward strand\n"
+         "          --device=NUM                 CUDA device (default: 0)\n\n");
+  return 256;
+}
+
+int cmd_index(int argc, char** argv) {
+  enum { OPT_NO_REVERSE = 1000, OPT_NO_FORWARD, OPT_DEVICE, OPT_GPUS };
+  static const option longopts[] = {{"log4cxx", required_argument, nullptr, 'c'}, {"ini", required_argument, nullptr, 's'},
+                                    {"prefix", required_argument, nullptr, 'p'},  {"threads", required_argument, nullptr, 't'},
+                                    {"algorithm", required_argument, nullptr, 'a'}, {"no-reverse", no_argument, nullptr, OPT_NO_REVERSE},
+                                    {"no-forward", no_argument, nullptr, OPT_NO_FORWARD}, {"device", required_argument, nullptr, OPT_DEVICE},
+                                    {"gpus", required_argument, nullptr, OPT_GPUS},
+                                    {"help", no_argument, nullptr, 'h'},          {nullptr, 0, nullptr, 0}};
+  CommonOpts o;
+  std::string algorithm = "sais2";
+  bool fwd = true, rev = true;
+  int c;
+  while ((c = getopt_long(argc, argv, "c:s:a:t:p:g:h", longopts, nullptr)) != -1) {
+    switch (c) {
+      case 'a': algorithm = optarg; break;
+      case 't': o.threads = atoi(optarg); break;
+      case 'p': o.prefix = optarg; break;
+      case OPT_NO_REVERSE: rev = false; break;
+      case OPT_NO_FORWARD: fwd = false; break;
+      case OPT_GPUS: o.gpus = std::max(1, std::min(16, atoi(optarg))); break;
+      case OPT_DEVICE: o.device = atoi(optarg); break;
+      case 'h': o.help = true; break;
+      default: break;
+    }
+  }
+  if (o.help || argc - optind != 1) return usage_index();
+  const std::string input = argv[optind];
+  const std::string output = o.prefix.empty() ? stem(input) : o.prefix;
+  info("input: %s", input.c_str());
+  info("output: %s.(.sai|.bwt|.rsai|.rbwt)", output.c_str());
+  info("algorithm: %s", algorithm.c_str());
+  int order;
+  if (strcasecmp(algorithm.c_str(), "sais") == 0) order = SGX_ORDER_SAIS;
+  else if (strcasecmp(algorithm.c_str(), "sais2") == 0) order = SGX_ORDER_SAIS2;
+  else {
+    // the reference accepts "rope" and silently writes nothing (SURVEY.md Appendix D.2); refuse instead
+    fprintf(stderr, "ERROR siga - Failed to create suffix array builder algorithm %s\n", algorithm.c_str());
+    return -1;
+  }
+  const double t0 = now_s();
+  ReadSet rs;
+  std::string err;
+  info("loading reads: %s", input.c_str());
+  sgx_ctx* ctx = nullptr;
+  int rc_init = SGX_OK;
+  int rc = SGX_OK;
+  const int world = o.gpus;
+  int my = 0;
+  std::vector<pid_t> kids;
+  sgx_comm* comm = nullptr;
+  if (world == 1) {
+    std::thread init_thread([&]() { rc_init = sgx_init(o.device, &ctx); });  // CUDA start-up overlaps the parse
+    const bool parsed = read_sequences(input, &rs, &err);
+    init_thread.join();
+    if (!parsed) {
+      fprintf(stderr, "ERROR siga - %s\n", err.c_str());
+      return -1;
+    }
+    if (rc_init != SGX_OK) return fail(nullptr, "sgx_init", rc_init);
+  } else {
+    // --gpus N: parse once, fork one process per GPU before any CUDA call, carry rank 0's NCCL id through pipes; all
+    // ranks then build each index together (rows sharded by leading k-mer bucket) and rank 0 writes the files.
+    if (!read_sequences(input, &rs, &err)) {
+      fprintf(stderr, "ERROR siga - %s\n", err.c_str());
+      return -1;
+    }
+    std::vector<int> rd(world, -1), wr(world, -1);
+    for (int r = 1; r < world; ++r) {
+      int fds[2];
+      if (pipe(fds) != 0) {
+        fprintf(stderr, "ERROR siga - pipe failed\n");
+        return -1;
+      }
+      rd[r] = fds[0];
+      wr[r] = fds[1];
+    }
+    fflush(nullptr);
+    for (int r = 1; r < world && my == 0; ++r) {
+      const pid_t pid = fork();
+      if (pid < 0) {
+        fprintf(stderr, "ERROR siga - fork failed\n");
+        return -1;
+      }
+      if (pid == 0) my = r;
+      else kids.push_back(pid);
+    }
+    if ((rc_init = sgx_init(o.device + my, &ctx)) != SGX_OK) {
+      fail(nullptr, "sgx_init", rc_init);
+      if (my) _exit(1);
+      return -1;
+    }
+    uint8_t id[128];
+    bool ok_id = true;
+    if (my == 0) {
+      ok_id = sgx_comm_unique_id(id) == SGX_OK;
+      for (int r = 1; r < world; ++r) ok_id = write(wr[r], id, sizeof(id)) == (ssize_t)sizeof(id) && ok_id;
+    } else {
+      ok_id = read(rd[my], id, sizeof(id)) == (ssize_t)sizeof(id);
+    }
+    if (!ok_id || (rc = sgx_comm_init(ctx, id, my, world, &comm)) != SGX_OK) {
+      fail(ok_id ? ctx : nullptr, "sgx_comm_init", rc);
+      if (my) _exit(1);
+      return -1;
+    }
+  }
+  sgx_reads* reads = nullptr;
+  rc = sgx_reads_pack(ctx, rs.bases.data(), rs.off.data(), rs.size(), &reads);
+  if (rc != SGX_OK) {
+    fail(ctx, "sgx_reads_pack", rc);
+    if (my) _exit(1);
+    return -1;
+  }
+  // the files of one strand are written on a host thread while the device builds the other strand
+  sgx_index_out outs[2];
+  std::thread writers[2];
+  bool wrote[2] = {true, true};
+  for (int pass = 0; pass < 2; ++pass) {
+    if ((pass == 0 && !fwd) || (pass == 1 && !rev)) continue;
+    if (my == 0) info("building %s index on %d GPU(s) from device %d", pass == 0 ? "forward" : "reverse", world, o.device);
+    sgx_index_out& out = outs[pass];
+    rc = comm ? sgx_index_build_sharded(ctx, comm, reads, order, pass, &out) : sgx_index_build(ctx, reads, order, pass, &out);
+    if (rc != SGX_OK) {
+      for (auto& w : writers)
+        if (w.joinable()) w.join();
+      fail(ctx, comm ? "sgx_index_build_sharded" : "sgx_index_build", rc);
+      if (my) _exit(1);
+      return -1;
+    }
+    if (my) {  // only rank 0 holds the concatenated run bytes and writes the files
+      sgx_index_out_free(&out);
+      continue;
+    }
+    const std::string sa = output + (pass == 0 ? ".sai" : ".rsai"), bw = output + (pass == 0 ? ".bwt" : ".rbwt");
+    info("%s: %llu strings, %llu suffixes, %llu runs; device %.1f ms (%llu kernel launches)", bw.c_str(),
+         (unsigned long long)out.n_strings, (unsigned long long)out.n_suffixes, (unsigned long long)out.n_runs, out.ms_total,
+         (unsigned long long)out.launches);
+    writers[pass] = std::thread([&outs, &wrote, pass, sa, bw]() {
+      const sgx_index_out& o2 = outs[pass];
+      bool a = false, b = false;
+      std::thread t([&]() { a = write_sai(sa, o2.sai, o2.n_strings); });
+      b = write_bwt(bw, o2.n_strings, o2.n_suffixes, o2.rle, o2.n_runs);
+      t.join();
+      wrote[pass] = a && b;
+    });
+  }
+  for (int pass = 0; pass < 2; ++pass) {
+    if (!writers[pass].joinable()) continue;
+    writers[pass].join();
+    sgx_index_out_free(&outs[pass]);
+    if (!wrote[pass]) {
+      fprintf(stderr, "ERROR siga - failed to write the %s index files of %s\n", pass == 0 ? "forward" : "reverse", output.c_str());
+      return -1;
+    }
+  }
+  if (comm) sgx_comm_free(comm);
+  if (my) {
+    sgx_reads_free(reads);
+    sgx_shutdown(ctx);
+    _exit(0);
+  }
+  bool kids_ok = true;
+  for (pid_t pid : kids) {
+    int st = 0;
+    if (waitpid(pid, &st, 0) < 0 || !WIFEXITED(st) || WEXITSTATUS(st) != 0) kids_ok = false;
+  }
+  if (!kids_ok) {
+    fprintf(stderr, "ERROR siga - a GPU worker process failed\n");
+    return -1;
+  }
+  sgx_reads_free(reads);
+  sgx_shutdown(ctx);
+  info("wall: %.3f sec", now_s() - t0);
+  return 0;
+}
+
+int cmd_overlap(int argc, char** argv) {
+  enum { OPT_BATCH_SIZE = 1000, OPT_NO_RC, OPT_DEVICE, OPT_GZIP_LEVEL, OPT_GPUS };
+  static const option longopts[] = {{"log4cxx", required_argument, nullptr, 'c'},   {"ini", required_argument, nullptr, 's'},
+                                    {"prefix", required_argument, nullptr, 'p'},    {"threads", required_argument, nullptr, 't'},
+                                    {"batch-size", required_argument, nullptr, OPT_BATCH_SIZE},
+                                    {"min-overlap", required_argument, nullptr, 'm'}, {"exhaustive", no_argument, nullptr, 'x'},
+                                    {"no-opposite-strand", no_argument, nullptr, OPT_NO_RC},
+                                    {"device", required_argument, nullptr, OPT_DEVICE}, {"help", no_argument, nullptr, 'h'},
+                                    {"gzip-level", required_argument, nullptr, OPT_GZIP_LEVEL},
+                                    {"gpus", required_argument, nullptr, OPT_GPUS}, {nullptr, 0, nullptr, 0}};
+  CommonOpts o;
+  unsigned min_overlap = 10;
+  bool exhaustive = false, rcomp = true;
+  int c;
+  while ((c = getopt_long(argc, argv, "c:s:t:p:m:xh", longopts, nullptr)) != -1) {
+    switch (c) {
+      case 't': o.threads = atoi(optarg); break;
+      case 'p': o.prefix = optarg; break;
+      case 'm': min_overlap = (unsigned)atoi(optarg); break;
+      case 'x': exhaustive = true; break;
+      case OPT_NO_RC: rcomp = false; break;
+      case OPT_GZIP_LEVEL: o.gzip_level = std::max(1, std::min(9, atoi(optarg))); break;
+      case OPT_GPUS: o.gpus = std::max(1, std::min(16, atoi(optarg))); break;
+      case OPT_DEVICE: o.device = atoi(optarg); break;
+      case 'h': o.help = true; break;
+      default: break;
+    }
+  }
+  if (o.help || argc - optind != 1) return usage_overlap();
+  if (o.threads <= 0) o.threads = (int)std::thread::hardware_concurrency();
+  const std::string input = argv[optind];
+  const std::string output = o.prefix.empty() ? stem(input) : o.prefix;
+  info("input: %s", input.c_str());
+  info("output: %s.asqg.gz", output.c_str());
+  const double t0 = now_s();
+
+  // --gpus N: the index files and reads are loaded once, then one process per GPU is forked (before any CUDA call);
+  // rank r searches the contiguous read range r of N against its own copy of both FM-indices and writes the VT / ED
+  // members of its range into part files, which the parent concatenates (HT, all VT in input order, all ED).
+  const int world = o.gpus;
+  LoadedInput in;
+  if (!load_input(input, output, o.device, &in, /*with_ctx=*/world == 1)) return -1;
+  ReadSet& rs = in.rs;
+  std::vector<uint8_t>&runs = in.runs, &rruns = in.rruns;
+  std::vector<uint32_t>&sai = in.sai, &rsai = in.rsai;
+  const uint64_t nf = in.nf, rnf = in.rnf;
+  std::vector<uint32_t> rank;
+  int my = 0;
+  std::vector<pid_t> kids;
+  if (world > 1) {
+    rank = name_ranks(rs.names);  // before the fork: every rank needs it
+    fflush(nullptr);
+    for (int r = 1; r < world && my == 0; ++r) {
+      const pid_t pid = fork();
+      if (pid < 0) {
+        fprintf(stderr, "ERROR siga - fork failed\n");
+        return -1;
+      }
+      if (pid == 0) my = r;
+      else kids.push_back(pid);
+    }
+    if ((in.ctx_rc = sgx_init(o.device + my, &in.ctx)) != SGX_OK) {
+      fail(nullptr, "sgx_init", in.ctx_rc);
+      if (my) _exit(1);
+      return -1;
+    }
+    o.threads = std::max(1, o.threads / world);
+  }
+  sgx_ctx* ctx = in.ctx;
+  int rc = SGX_OK;
+  const double t_load = now_s();
+  const uint64_t first = rs.size() * (uint64_t)my / world, count = rs.size() * (uint64_t)(my + 1) / world - first;
+
+  std::thread rank_thread([&]() {
+    if (rank.empty()) rank = name_ranks(rs.names);  // host sort of the names while the device loads the index
+  });
+  struct Joiner {
+    std::thread& t;
+    ~Joiner() {
+      if (t.joinable()) t.join();
+    }
+  } rank_joiner{rank_thread};
+  sgx_reads* reads = nullptr;
+  sgx_fm *fwd = nullptr, *rev = nullptr;
+  if ((rc = sgx_reads_pack(ctx, rs.bases.data(), rs.off.data(), rs.size(), &reads)) != SGX_OK) return fail(ctx, "sgx_reads_pack", rc);
+  if ((rc = sgx_fm_create(ctx, runs.data(), runs.size(), nf, &fwd)) != SGX_OK) return fail(ctx, "sgx_fm_create", rc);
+  if ((rc = sgx_fm_create(ctx, rruns.data(), rruns.size(), rnf, &rev)) != SGX_OK) return fail(ctx, "sgx_fm_create", rc);
+  if ((rc = sgx_fm_attach_reads(ctx, fwd, sai.data(), sai.size(), reads)) != SGX_OK) return fail(ctx, "sgx_fm_attach_reads", rc);
+  if ((rc = sgx_fm_attach_reads(ctx, rev, rsai.data(), rsai.size(), reads)) != SGX_OK) return fail(ctx, "sgx_fm_attach_reads", rc);
+  info("fm-index: %llu symbols in %zu runs (%.4f symbols per run)", (unsigned long long)nf, runs.size(),
+       runs.empty() ? 0.0 : (double)nf / runs.size());
+  sgx_edges ed;
+  rank_thread.join();
+  rc = sgx_overlap_edges(ctx, fwd, rev, reads, first, count, min_overlap, exhaustive ? 0 : 1, rcomp ? 1 : 0, rank.data(), &ed);
+  if (rc != SGX_OK) {
+    fail(ctx, "sgx_overlap_edges", rc);
+    if (my) _exit(1);
+    return -1;
+  }
+  const double t_search = now_s();
+  info("processed %llu sequences: %llu blocks, %llu edges; device %.1f ms (search %.1f ms, post %.1f ms; %llu rank lookups)",
+       (unsigned long long)count, (unsigned long long)ed.n_blocks, (unsigned long long)ed.n_edges, ed.ms_total, ed.ms_search, ed.ms_extract,
+       (unsigned long long)(ed.lookups_search + ed.lookups_extract));
+
+  // ---- ASQG: HT, all VT (input order), all ED (src/bigraph.cpp:532-616 requires this order)
+  const std::string final_path = output + ".asqg.gz";
+  bool good;
+  if (world == 1) {
+    good = write_asqg(final_path, o, rs, ed, 0, min_overlap, true, true, true);
+  } else {
+    const std::string part = final_path + ".part" + std::to_string(my);
+    good = write_asqg(part + ".vt", o, rs, ed, first, min_overlap, my == 0, true, false) &&
+           write_asqg(part + ".ed", o, rs, ed, first, min_overlap, false, false, true);
+    if (my) {
+      sgx_edges_free(&ed);
+      sgx_shutdown(ctx);
+      _exit(good ? 0 : 1);
+    }
+    for (pid_t pid : kids) {
+      int st = 0;
+      if (waitpid(pid, &st, 0) < 0 || !WIFEXITED(st) || WEXITSTATUS(st) != 0) good = false;
+    }
+    if (good) {
+      FILE* f = fopen(final_path.c_str(), "wb");
+      good = f != nullptr;
+      for (int pass = 0; pass < 2 && good; ++pass)
+        for (int r = 0; r < world && good; ++r)
+          good = append_file(f, final_path + ".part" + std::to_string(r) + (pass == 0 ? ".vt" : ".ed"));
+      if (f && fclose(f) != 0) good = false;
+    }
+    for (int r = 0; r < world; ++r)
+      for (const char* ext : {".vt", ".ed"}) remove((final_path + ".part" + std::to_string(r) + ext).c_str());
+  }
   if (!good) {
     fprintf(stderr, "ERROR siga - write to %s.asqg.gz failed\n", output.c_str());
     return -1;

@@ -157,3 +157,38 @@ def test_downstream_assemble_runs_unchanged(err):
             out[who] = _contigs(os.path.join(w, "asm-contigs.fa"))
         assert sum(len(c) for c in out["ref"]) > 25_000 and (err == 0.0 or len(out["ref"]) > 100)
         assert out["ours"] == out["ref"]
+
+
+def _gpu_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(not os.path.isfile(CLI), reason="siga_b200/bin/siga not built")
+@pytest.mark.skipif(_gpu_count() < 2, reason="needs two GPUs (run under gpurun --gpus 2)")
+def test_cli_multi_gpu_outputs_equal_single_gpu():
+    """`siga index --gpus 2` (NCCL, rows sharded by k-mer bucket) and `siga overlap --gpus 2` (reads sharded, part files
+    concatenated) write the same index bytes, the same HT/VT lines and the same ED set as the one-GPU commands."""
+    rng = np.random.default_rng(5)
+    g = synth.random_genome(20_000, rng)
+    reads = synth.sample_reads(g, 9_001, 80, rng, err=0.01)
+    with tempfile.TemporaryDirectory() as d:
+        one, two = os.path.join(d, "one"), os.path.join(d, "two")
+        os.mkdir(one)
+        os.mkdir(two)
+        src = os.path.join(d, "reads.fa")
+        synth.write_fasta(src, reads)
+        _run(["index", src], one)
+        _run(["overlap", "-m", "30", src], one)
+        _run(["index", "--gpus", "2", src], two)
+        _run(["overlap", "-m", "30", "--gpus", "2", src], two)
+        for ext in (".bwt", ".rbwt", ".sai", ".rsai"):
+            assert open(os.path.join(one, "reads" + ext), "rb").read() == open(os.path.join(two, "reads" + ext), "rb").read(), ext
+        a, b = _asqg(os.path.join(one, "reads.asqg.gz")), _asqg(os.path.join(two, "reads.asqg.gz"))
+        n = len(reads)
+        assert a[:1 + n] == b[:1 + n]
+        assert sorted(a[1 + n:]) == sorted(b[1 + n:]) and len(a) > 1 + n
+        assert not [f for f in os.listdir(two) if ".part" in f]

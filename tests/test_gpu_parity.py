@@ -449,3 +449,33 @@ def test_rmdup_records_match_reference(ctx):
             ctx.free_fm(rev)
     finally:
         ctx.free_reads(r)
+
+
+# ------------------------------------------------------------------------------------------------------- edge cases
+
+@pytest.mark.skipif(not refrun.have_ref(), reason="compiled reference (oracle/_ref/siga) not present")
+@pytest.mark.parametrize("case", ["single_read", "two_identical", "min_overlap_above_length", "tiny_reads", "all_same_base",
+                                  "read_and_its_revcomp"])
+def test_edge_case_inputs_match_reference(ctx, case):
+    """Degenerate inputs through the whole chain (index bytes, hit blocks on both post paths, ASQG) against the
+    reference binary: one read, duplicates only, a min-overlap no read can reach, reads of 1-3 bases, homopolymers."""
+    m = 8
+    if case == "single_read":
+        reads = [b"ACGTTGCAAGGCTTAACCGG"]
+    elif case == "two_identical":
+        reads = [b"ACGTTGCAAGGCTTAACCGG"] * 2
+    elif case == "min_overlap_above_length":
+        reads, m = [b"ACGTTGCAAGGCTTAACCGG", b"TTGCAAGGCTTAACCGGATT", b"GCAAGGCTTAACCGGATTAC"], 64
+    elif case == "tiny_reads":
+        reads, m = [b"A", b"C", b"AC", b"CA", b"ACG", b"CGT", b"T", b"AC"], 1
+    elif case == "all_same_base":
+        reads, m = [b"A" * 40, b"A" * 40, b"A" * 35, b"T" * 40], 10
+    else:
+        reads = [b"ACGTTGCAAGGCTTAACCGGATTACA", b"TGTAATCCGGTTAAGCCTTGCAACGT"]
+    _check_index(ctx, reads, case)
+    _overlap_vs_ref(ctx, reads, m)
+
+
+def test_zero_reads_are_rejected(ctx):
+    with pytest.raises(api.SgxError):
+        ctx.pack_reads(np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.uint64))
