@@ -228,6 +228,31 @@ void comm_gatherv_bytes(sgx_comm* cm, const uint8_t* const* send, const uint64_t
   }
 }
 
+void comm_allgatherv(sgx_comm* cm, const void* const* send, const uint64_t* counts, size_t elem_bytes, void* recv) {
+  cudaStream_t st = cm->ctx->stream;
+  const int W = cm->world;
+  std::vector<uint64_t> off(W + 1, 0);
+  for (int s = 0; s < W; ++s) off[s + 1] = off[s] + counts[s];
+  uint8_t* dst = (uint8_t*)recv;
+  if (cm->local) {
+    for (int s = 0; s < W; ++s)
+      if (counts[s])
+        SGX_CUDA(cudaMemcpyAsync(dst + off[s] * elem_bytes, send[s], counts[s] * elem_bytes, cudaMemcpyDeviceToDevice, st));
+    return;
+  }
+  NcclApi& api = nccl_api();
+  const int me = cm->rank;
+  if (counts[me])
+    SGX_CUDA(cudaMemcpyAsync(dst + off[me] * elem_bytes, send[0], counts[me] * elem_bytes, cudaMemcpyDeviceToDevice, st));
+  SGX_NCCL(api.GroupStart());
+  for (int p = 0; p < W; ++p) {
+    if (p == me) continue;
+    if (counts[me]) SGX_NCCL(api.Send(send[0], counts[me] * elem_bytes, ncclUint8, p, (ncclComm_t)cm->nccl, st));
+    if (counts[p]) SGX_NCCL(api.Recv(dst + off[p] * elem_bytes, counts[p] * elem_bytes, ncclUint8, p, (ncclComm_t)cm->nccl, st));
+  }
+  SGX_NCCL(api.GroupEnd());
+}
+
 void comm_barrier(sgx_comm* cm) {
   if (cm->local) {
     SGX_CUDA(cudaStreamSynchronize(cm->ctx->stream));

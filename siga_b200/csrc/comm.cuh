@@ -62,6 +62,10 @@ void comm_alltoallv(sgx_comm* cm, const void* const* send, void* const* recv, si
 // `root_recv` (a device buffer of the local shard that is `root`; ignored elsewhere).
 void comm_gatherv_bytes(sgx_comm* cm, const uint8_t* const* send, const uint64_t* bytes, int root, uint8_t* root_recv);
 
+// Concatenation, on EVERY process, of one block per shard: shard s contributes counts[s] elements of elem_bytes from
+// send[local index of s]; `recv` (one buffer per process) receives them in shard order.
+void comm_allgatherv(sgx_comm* cm, const void* const* send, const uint64_t* counts, size_t elem_bytes, void* recv);
+
 void comm_barrier(sgx_comm* cm);
 
 }  // namespace sgx

@@ -89,31 +89,38 @@ static void bcr_passes(sgx_ctx* ctx, const sgx_reads* reads, const ReadAcc& acc,
   *final_B = B;
 }
 
+// Content sort of n read ids (stable): LSD radix sort of the reads as strings of 32-base (64-bit) key chunks, last chunk
+// first.  One gather per read and chunk builds the keys; the 8-bit passes inside a chunk stream (key, id) pairs.  Bases
+// past the end of a read count as 'A' in the key, and the read length is the least significant key, so that a read
+// that is a proper prefix of another sorts first ('$' < 'A').  The result is in `ids`.
+void index_content_sort(sgx_ctx* ctx, const sgx_reads* reads, const ReadAcc& acc, uint32_t* ids, uint32_t* ids_alt,
+                        uint64_t* keys, uint64_t* keys_alt, uint64_t n, uint64_t* part_ws) {
+  if (n == 0) return;
+  const uint32_t lmax = reads->max_len;
+  if (reads->min_len != lmax) {
+    int lbits = 1;
+    while ((1u << lbits) <= lmax) ++lbits;
+    SGX_LAUNCH(ctx, len_keys_kernel, grid_for(n, 256), 256, 0, acc.rv, (const uint32_t*)ids, n, keys);
+    radix_sort_pairs(ctx, keys, ids, keys_alt, ids_alt, n, lbits, part_ws);
+  }
+  const uint32_t nchunks = (lmax + 31) / 32;
+  for (uint32_t ch = nchunks; ch-- > 0;) {
+    const uint32_t nbases = std::min<uint32_t>(32, lmax - 32 * ch);
+    SGX_LAUNCH(ctx, chunk_keys_kernel, grid_for(n, 256), 256, 0, acc, (const uint32_t*)ids, n, 32 * ch, nbases, keys);
+    radix_sort_pairs(ctx, keys, ids, keys_alt, ids_alt, n, 2 * (int)nbases, part_ws);
+  }
+}
+
 void index_read_order(sgx_ctx* ctx, const sgx_reads* reads, const ReadAcc& acc, int order, uint32_t* d_sai,
                       uint32_t* d_sord) {
   const uint64_t N = reads->n;
-  const uint32_t lmax = reads->max_len;
-  // ---- 1. read ordering: LSD radix sort of the reads as strings of 32-base (64-bit) key chunks, last chunk first.
-  //      One gather per read and chunk builds the keys; the 8-bit passes inside a chunk stream (key, id) pairs.
-  //      Bases past the end of a read count as 'A' in the key, and the read length is the least significant key, so
-  //      that a read that is a proper prefix of another sorts first ('$' < 'A').
+  // ---- 1. read ordering
   DevBuf<uint32_t> idsA(N), idsB(N);
   DevBuf<uint64_t> part_ws(part_ws_elems(N, 256)), heads(N + 1), scan_ws(scan_ws_elems(N + 1)), d_total(1);
   DevBuf<uint64_t> keys(N), keys2(N);
   SGX_LAUNCH(ctx, iota_kernel, grid_for(N, 256), 256, 0, idsA.p, N);
   uint32_t* ids = idsA.p;
-  if (reads->min_len != lmax) {
-    int lbits = 1;
-    while ((1u << lbits) <= lmax) ++lbits;
-    SGX_LAUNCH(ctx, len_keys_kernel, grid_for(N, 256), 256, 0, acc.rv, (const uint32_t*)ids, N, keys.p);
-    radix_sort_pairs(ctx, keys.p, ids, keys2.p, idsB.p, N, lbits, part_ws.p);
-  }
-  const uint32_t nchunks = (lmax + 31) / 32;
-  for (uint32_t ch = nchunks; ch-- > 0;) {
-    const uint32_t nbases = std::min<uint32_t>(32, lmax - 32 * ch);
-    SGX_LAUNCH(ctx, chunk_keys_kernel, grid_for(N, 256), 256, 0, acc, (const uint32_t*)ids, N, 32 * ch, nbases, keys.p);
-    radix_sort_pairs(ctx, keys.p, ids, keys2.p, idsB.p, N, 2 * (int)nbases, part_ws.p);
-  }
+  index_content_sort(ctx, reads, acc, ids, idsB.p, keys.p, keys2.p, N, part_ws.p);
   if (order == SGX_ORDER_SAIS) {
     // model A: equal suffixes tie by read index; the content sort is stable, so `ids` is the read-start order and
     // the sentinel of read i is simply the i-th smallest.

@@ -574,6 +574,9 @@ inline unsigned merge_grid(const sgx_ctx* ctx, uint64_t ntiles) {
 // Order of the read-start suffixes (d_sai, the .sai file) and of the N sentinel rows (d_sord) under ordering model
 // `order`; both arrays hold N read ids.
 void index_read_order(sgx_ctx* ctx, const sgx_reads* reads, const ReadAcc& acc, int order, uint32_t* d_sai, uint32_t* d_sord);
+// Stable content sort of n read ids (result in `ids`); scratch arrays hold n elements, part_ws part_ws_elems(n, 256).
+void index_content_sort(sgx_ctx* ctx, const sgx_reads* reads, const ReadAcc& acc, uint32_t* ids, uint32_t* ids_alt,
+                        uint64_t* keys, uint64_t* keys_alt, uint64_t n, uint64_t* part_ws);
 // nact[j] = reads with length >= j (the inserts of column pass j), j in [1, max_len].
 std::vector<uint64_t> index_active_counts(sgx_ctx* ctx, const sgx_reads* reads);
 // bytes of a 4-bit symbol array of `rows` rows, padded so that whole-tile / whole-vector accesses stay in bounds

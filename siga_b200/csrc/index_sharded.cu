@@ -9,7 +9,8 @@
 //     partial BWT.  The bounds come from a k-mer histogram of a read sample (each shard counts its slice, NCCL
 //     all-reduce); they only balance the load -- any bounds give the same BWT.  Exact final rows per shard are
 //     counted the same way (slice + all-reduce) to size the arrays.
-//   * Reads, the read-start order (.sai) and the sentinel order are replicated (N items; the heavy part is S rows).
+//   * The packed reads are replicated.  The read-start order (.sai) and the sentinel order are computed sharded too
+//     (sharded_read_order below: every shard sorts the reads whose first 8-mer it owns) and then all-gathered.
 //   * Column pass j: every shard LF-maps the suffixes it inserted in pass j-1 through ITS rows (local rank of the
 //     preceding base c), finds the owner of the new suffix from its key, and partitions (id, local rank part) by
 //     (destination shard, c).  One small all-gather carries the send counts and each shard's A/C/G/T totals; one
@@ -466,6 +467,157 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
   t_emit.stop();
 }
 
+// ---- sharded read ordering -----------------------------------------------------------------------------------------
+// The order of the read-start suffixes (.sai) and of the sentinel rows, with the N reads split over the shards by the
+// same leading-k-mer bounds as the BWT rows: a shard sorts the reads whose first 8-mer it owns (identical reads share a
+// shard, shard order = lexicographic order), dense ranks get a per-shard offset from an all-gather of the distinct
+// counts, and the prefix-doubling rounds of ordering model B (ties decided by the following reads) sort only the
+// shard's own (rank, rank of the read h further) pairs; the full rank array is rebuilt on every process by an
+// all-gather of (read id, rank) after each round.
+
+struct OwnerDigit {
+  ReadAcc acc;
+  ShardBounds bounds;
+  int g;
+  __device__ __forceinline__ int operator()(uint64_t k) const {
+    const uint32_t id = (uint32_t)k;
+    return bounds.owner(suffix_key(acc, id, 0, acc.rv.len[id])) == g ? 0 : 255;
+  }
+};
+struct IotaMove {
+  uint32_t* out;
+  __device__ __forceinline__ void operator()(uint64_t k, uint64_t dest) const { out[dest] = (uint32_t)k; }
+};
+// out[k] = offset + (number of heads in [0, k]) given the exclusive scan of the head flags
+static __global__ void local_rank_kernel(const uint64_t* __restrict__ excl, uint64_t n, uint64_t total, uint64_t offset,
+                                         uint32_t* __restrict__ out) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  out[k] = (uint32_t)(offset + (k + 1 < n ? excl[k + 1] : total));
+}
+static __global__ void scatter_rank_kernel(const uint32_t* __restrict__ ids, const uint32_t* __restrict__ ranks, uint64_t n,
+                                           uint32_t* __restrict__ rank) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) rank[ids[k]] = ranks[k];
+}
+static __global__ void doubling_keys_owned_kernel(const uint32_t* __restrict__ rank, uint64_t n_all, const uint32_t* __restrict__ ids,
+                                                  uint64_t n, uint64_t h, int bits, uint64_t* __restrict__ keys,
+                                                  uint32_t* __restrict__ vals) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint64_t i = ids[k];
+  const uint64_t r2 = i + h < n_all ? rank[i + h] : 0;  // end of text is smallest
+  keys[k] = ((uint64_t)rank[i] << bits) | r2;
+  vals[k] = (uint32_t)i;
+}
+
+struct OrderShard {
+  int g = 0;
+  uint64_t n = 0;
+  DevBuf<uint32_t> ids, ids2, lrank;
+  DevBuf<uint64_t> keys, keys2, heads, scan_ws, part_ws, total;
+};
+
+static void sharded_read_order(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, const ReadAcc& acc, int order,
+                               const ShardBounds& bounds, uint32_t* d_sai, uint32_t* d_sord) {
+  const uint64_t N = reads->n;
+  const int W = cm->world, nl = cm->n_local();
+  std::vector<OrderShard> sh(nl);
+  std::vector<uint64_t> cnt(W, 0), distinct(W, 0);
+  std::vector<const uint64_t*> u64_ptr(nl);
+  std::vector<const void*> blk_ptr(nl);
+  DevBuf<uint64_t> sel_ws(part_ws_elems(N, 1));
+  // ---- the reads every shard owns (in read-index order: the sort below is stable, model A ties by read index)
+  for (int li = 0; li < nl; ++li) {
+    OrderShard& s = sh[li];
+    s.g = cm->shard_of(li);
+    s.total.alloc(1);
+    OwnerDigit dg{acc, bounds, s.g};
+    partition_count<1, OwnerDigit>(ctx, dg, N, sel_ws.p, s.total.p);
+    SGX_CUDA(cudaMemcpyAsync(&s.n, s.total.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+    const uint64_t cap = s.n ? s.n : 1;
+    s.ids.alloc(cap);
+    s.ids2.alloc(cap);
+    s.lrank.alloc(cap);
+    s.keys.alloc(cap);
+    s.keys2.alloc(cap);
+    s.heads.alloc(cap + 1);
+    s.scan_ws.alloc(scan_ws_elems(cap + 1));
+    s.part_ws.alloc(part_ws_elems(cap, 256));
+    IotaMove mv{s.ids.p};
+    partition_scatter<1, OwnerDigit, IotaMove>(ctx, dg, mv, N, sel_ws.p);
+    u64_ptr[li] = s.total.p;
+  }
+  comm_allgather_u64(cm, u64_ptr.data(), 1, cnt.data());
+  uint64_t sum = 0;
+  for (int g = 0; g < W; ++g) sum += cnt[g];
+  SGX_REQUIRE(sum == N, SGX_ECUDA, "sharded index: the shards' read sets do not add up to the read count");
+  // ---- content order + dense content ranks
+  for (int li = 0; li < nl; ++li) {
+    OrderShard& s = sh[li];
+    index_content_sort(ctx, reads, acc, s.ids.p, s.ids2.p, s.keys.p, s.keys2.p, s.n, s.part_ws.p);
+    if (s.n) SGX_LAUNCH(ctx, read_heads_kernel, grid_for(s.n, 256), 256, 0, acc.rv, (const uint32_t*)s.ids.p, s.n, s.heads.p);
+    scan_exclusive(ctx, s.heads.p, s.n, s.scan_ws.p, s.total.p);
+  }
+  DevBuf<uint32_t> rank, ranks_by_pos;
+  uint32_t* order_ids = d_sai;  // concatenation of the shards' sorted ids = the global order
+  auto publish = [&](bool need_ranks) {
+    // offsets of the dense ranks from the distinct counts, then (ids, ranks) of all shards to every process
+    comm_allgather_u64(cm, u64_ptr.data(), 1, distinct.data());
+    uint64_t off = 0, total = 0;
+    for (int g = 0; g < W; ++g) total += distinct[g];
+    for (int li = 0; li < nl; ++li) {
+      OrderShard& s = sh[li];
+      off = 0;
+      for (int g = 0; g < s.g; ++g) off += distinct[g];
+      if (s.n && need_ranks)
+        SGX_LAUNCH(ctx, local_rank_kernel, grid_for(s.n, 256), 256, 0, (const uint64_t*)s.heads.p, s.n, distinct[s.g], off,
+                   s.lrank.p);
+      blk_ptr[li] = s.ids.p;
+    }
+    comm_allgatherv(cm, blk_ptr.data(), cnt.data(), sizeof(uint32_t), order_ids);
+    if (need_ranks) {
+      for (int li = 0; li < nl; ++li) blk_ptr[li] = sh[li].lrank.p;
+      comm_allgatherv(cm, blk_ptr.data(), cnt.data(), sizeof(uint32_t), ranks_by_pos.p);
+      SGX_LAUNCH(ctx, scatter_rank_kernel, grid_for(N, 256), 256, 0, (const uint32_t*)order_ids, (const uint32_t*)ranks_by_pos.p, N,
+                 rank.p);
+    }
+    return total;
+  };
+  if (order == SGX_ORDER_SAIS) {
+    publish(false);
+    SGX_LAUNCH(ctx, iota_kernel, grid_for(N, 256), 256, 0, d_sord, N);
+    SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return;
+  }
+  rank.alloc(N);
+  ranks_by_pos.alloc(N);
+  uint64_t n_distinct = publish(true);
+  int bits = 1;
+  while (((uint64_t)1 << bits) <= N) ++bits;  // ranks are in [0, N]
+  for (uint64_t h = 1; n_distinct < N; h <<= 1) {
+    for (int li = 0; li < nl; ++li) {
+      OrderShard& s = sh[li];
+      if (s.n) {
+        SGX_LAUNCH(ctx, doubling_keys_owned_kernel, grid_for(s.n, 256), 256, 0, (const uint32_t*)rank.p, N,
+                   (const uint32_t*)s.ids.p, s.n, h, bits, s.keys.p, s.ids2.p);
+        radix_sort_pairs(ctx, s.keys.p, s.ids2.p, s.keys2.p, s.ids.p, s.n, 2 * bits, s.part_ws.p);
+        // sorted ids are in ids2 (keys in keys); make them the shard's current order
+        SGX_CUDA(cudaMemcpyAsync(s.ids.p, s.ids2.p, s.n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        SGX_LAUNCH(ctx, key_heads_kernel, grid_for(s.n, 256), 256, 0, (const uint64_t*)s.keys.p, s.n, s.heads.p);
+      }
+      scan_exclusive(ctx, s.heads.p, s.n, s.scan_ws.p, s.total.p);
+    }
+    n_distinct = publish(true);
+    SGX_REQUIRE(h < ((uint64_t)1 << 40), SGX_ECUDA, "index: read-rank doubling did not converge");
+  }
+  uint64_t* k0 = sh[0].total.p;  // scratch
+  SGX_LAUNCH(ctx, find_zero_kernel, grid_for(N, 256), 256, 0, (const uint32_t*)d_sai, N, k0);
+  SGX_LAUNCH(ctx, sentinel_order_kernel, grid_for(N, 256), 256, 0, (const uint32_t*)d_sai, N, (const uint64_t*)k0, d_sord);
+  SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
 void index_build_sharded(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, int order, bool reversed, sgx_index_out* out) {
   memset(out, 0, sizeof(*out));
   const uint64_t N = reads->n;
@@ -480,10 +632,7 @@ void index_build_sharded(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, int
 
   t_all.start();
   t_sort.start();
-  // ---- read order: replicated on every shard (N items)
   DevBuf<uint32_t> d_sai(N), d_sord(N);
-  index_read_order(ctx, reads, acc, order, d_sai.p, d_sord.p);
-
   // ---- bucket bounds from the k-mer histogram of a read sample; exact rows per shard
   const int nslices = cm->local ? 1 : W;
   const int slice = cm->local ? 0 : cm->rank;
@@ -529,12 +678,19 @@ void index_build_sharded(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, int
     }
     SGX_REQUIRE(sum == S, SGX_ECUDA, "sharded index: shard row counts do not add up to the number of suffixes");
   }
+  // ---- read order (.sai) and sentinel order, the reads sharded by the same bounds
+  sharded_read_order(ctx, cm, reads, acc, order, bounds, d_sai.p, d_sord.p);
   t_sort.stop();
 
   uint8_t* rle_host = nullptr;
   uint64_t rle_total = 0;
+  // Positions inside the sharded build are shard-local rows and sender-local rank parts (the global offsets live in
+  // the 64-bit constants of the receive plan), so 32 bits suffice whenever every SHARD has < 2^32 rows -- config 4
+  // (5.03 G symbols) runs the 32-bit kernels on 2+ GPUs.  SGX_FORCE_WIDE=1 (tests) takes the 64-bit path anyway.
+  uint64_t max_rows = 0;
+  for (int g = 0; g < W; ++g) max_rows = std::max(max_rows, rows_final[g]);
   const char* fw = getenv("SGX_FORCE_WIDE");
-  if (S < 0xffffffffull && !(fw && fw[0] == '1')) {
+  if (max_rows < 0xffffff00ull && !(fw && fw[0] == '1')) {
     sharded_build<uint32_t>(ctx, cm, reads, acc, d_sord.p, bounds, rows_final, out, k_merge, t_bcr, t_emit, &rle_host, &rle_total);
   } else {
     sharded_build<uint64_t>(ctx, cm, reads, acc, d_sord.p, bounds, rows_final, out, k_merge, t_bcr, t_emit, &rle_host, &rle_total);
