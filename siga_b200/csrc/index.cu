@@ -39,6 +39,7 @@ static void bcr_passes(sgx_ctx* ctx, const sgx_reads* reads, const ReadAcc& acc,
   DevBuf<uint32_t> ID0(N), ID1(N);
   DevBuf<PosT> NP0(N), NP1(N), tmpPos(N);
   DevBuf<uint8_t> SYM0(N), SYM1(N);
+  DevBuf<uint32_t> WIN0(N), WIN1(N);
   DevBuf<uint2> blk(nt_max * 32);
   DevBuf<uint64_t> tiletot(4 * nt_max), scan_ws(scan_ws_elems(4 * nt_max)), part_ws(part_ws_elems(N, 4)),
       tile_k0(S / kMergeTile + 4);
@@ -48,6 +49,8 @@ static void bcr_passes(sgx_ctx* ctx, const sgx_reads* reads, const ReadAcc& acc,
   PosT* NP2 = NP1.p;
   uint8_t* SYM = SYM0.p;
   uint8_t* SYM2 = SYM1.p;
+  uint32_t* WIN = WIN0.p;
+  uint32_t* WIN2 = WIN1.p;
   uint8_t* B = B0;
   uint8_t* Bn = B1;
 
@@ -64,7 +67,7 @@ static void bcr_passes(sgx_ctx* ctx, const sgx_reads* reads, const ReadAcc& acc,
     SGX_LAUNCH(ctx, (bcr_rank_kernel<PosT>), grid_for(nact_prev, 256), 256, 0, (const uint8_t*)B, (const uint2*)blk.p,
                (const uint64_t*)tiletot.p, nt, N, (const uint8_t*)SYM, (const PosT*)NP, nact_prev, tmpPos.p);
     SymDigit dg{SYM};
-    BcrMove<PosT> mv{acc, ID, tmpPos.p, j, uniform_len, ID2, NP2, SYM2};
+    BcrMove<PosT> mv{acc, ID, tmpPos.p, WIN, j, uniform_len, ID2, NP2, SYM2, WIN2};
     partition_pass<4>(ctx, dg, mv, nact_prev, part_ws.p, (uint64_t*)nullptr);
     const uint64_t n_new = n_cur + nact;
     const uint64_t ntiles = (n_new + kMergeTile - 1) / kMergeTile;
@@ -81,6 +84,7 @@ static void bcr_passes(sgx_ctx* ctx, const sgx_reads* reads, const ReadAcc& acc,
     std::swap(ID, ID2);
     std::swap(NP, NP2);
     std::swap(SYM, SYM2);
+    std::swap(WIN, WIN2);
     n_cur = n_new;
     nt = ntiles;
     nact_prev = nact;

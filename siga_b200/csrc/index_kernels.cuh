@@ -178,10 +178,14 @@ __device__ __forceinline__ uint32_t nib_sum(uint32_t acc) {
 // nibbles past the end of the array are zero.
 __device__ __forceinline__ void tile_checkpoints(const uint32_t out[4], uint64_t tile, uint64_t ntiles, uint32_t* sh_w /* 64 */,
                                                  uint2* __restrict__ blk, uint64_t* __restrict__ tiletot) {
-  uint32_t accA = 0, accC = 0, accG = 0, accT = 0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) nib_count_add(out[i], 0x11111111u, accA, accC, accG, accT);
-  uint32_t w1 = nib_sum(accA) | (nib_sum(accC) << 16), w2 = nib_sum(accG) | (nib_sum(accT) << 16);
+  // bit planes of the 32 nibbles packed into one word each (word i's plane shifted to bit i of every nibble): symbol
+  // ranks are A=1 C=2 G=3 T=4, so A = b0 & ~b1, C = b1 & ~b0, G = b0 & b1, T = b2 -- four popcounts per thread
+  const uint32_t M = 0x11111111u;
+  const uint32_t p0 = (out[0] & M) | ((out[1] << 1) & (M << 1)) | ((out[2] << 2) & (M << 2)) | ((out[3] << 3) & (M << 3));
+  const uint32_t p1 = ((out[0] >> 1) & M) | (out[1] & (M << 1)) | ((out[2] << 1) & (M << 2)) | ((out[3] << 2) & (M << 3));
+  const uint32_t p2 = ((out[0] >> 2) & M) | ((out[1] >> 1) & (M << 1)) | (out[2] & (M << 2)) | ((out[3] << 1) & (M << 3));
+  uint32_t w1 = (uint32_t)__popc(p0 & ~p1) | ((uint32_t)__popc(p1 & ~p0) << 16);
+  uint32_t w2 = (uint32_t)__popc(p0 & p1) | ((uint32_t)__popc(p2) << 16);
 #pragma unroll
   for (int oo = 4; oo > 0; oo >>= 1) {  // 256-row block = 8 consecutive threads
     w1 += __shfl_xor_sync(0xffffffffu, w1, oo);
@@ -303,22 +307,37 @@ struct SymDigit {
     return s ? s - 1 : 255;
   }
 };
+// Move functor of the column passes' partition: carries an item to its slot in new-row order and looks up the symbol
+// its new row holds (the base before the suffix; '$' when the read starts here).  That base comes from the read store
+// -- the one random gather of a pass -- so the 32-bit word it sits in travels with the item (WIN): consecutive passes
+// walk through the same word, and only every 16th pass (or every pass's first for a new item) touches the read store.
 template <class PosT>
 struct BcrMove {
   ReadAcc acc;
   const uint32_t* ID;
   const PosT* tmpPos;
+  const uint32_t* WIN;
   uint32_t j;
   uint32_t uniform_len;  // != 0: every read has this length (no gather of len[])
   uint32_t* ID2;
   PosT* NP2;
   uint8_t* SYM2;
+  uint32_t* WIN2;
   __device__ __forceinline__ void operator()(uint64_t k, uint64_t dest) const {
     const uint32_t id = ID[k];
     const uint32_t l = uniform_len ? uniform_len : acc.rv.len[id];
     ID2[dest] = id;
     NP2[dest] = tmpPos[k];
-    SYM2[dest] = (l == j) ? (uint8_t)0 : (uint8_t)(acc.code(id, l - j - 1, l) + 1);
+    if (l == j) {
+      SYM2[dest] = 0;
+      return;
+    }
+    // stored position of column l - j - 1: the walk goes down through a forward read, up through a reversed one
+    const uint32_t p = acc.reversed ? j : l - j - 1;
+    const bool fresh = j == 1 || (acc.reversed ? (p & 15u) == 0u : (p & 15u) == 15u);
+    const uint32_t w = fresh ? acc.rv.words[acc.rv.woff[id] + (p >> 4)] : WIN[k];
+    SYM2[dest] = (uint8_t)(((w >> (2 * (p & 15u))) & 3u) + 1u);
+    WIN2[dest] = w;
   }
 };
 
