@@ -293,12 +293,15 @@ def main():
         ctx.free_edges(ee)
         ctx.free_reads(rr)
         return nb
-    for _ in range(2):
+    for _ in range(3):
         e2e_step()
     barrier()
+    e2e_steps = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
+        ts = time.perf_counter()
         e2e_d2h = e2e_step()
+        e2e_steps.append((time.perf_counter() - ts) * 1e3)
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
     e2e_value = total_reads / (e2e_ms * 1e-3)
@@ -375,7 +378,8 @@ def main():
                          (fi.n_suffixes / 256 * 128 / 1e6)},
         "device_ms_per_step": dev_ms / args.steps,
         "gpu_launches": int(launches),
-        "e2e": {"value": e2e_value, "unit": "reads/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": e2e_h2d,
+        "e2e": {"value": e2e_value, "unit": "reads/s", "ms_per_step": e2e_ms, "step_ms": [round(x, 2) for x in e2e_steps],
+                "h2d_bytes_per_step": e2e_h2d,
                 "d2h_bytes_per_step": e2e_d2h,
                 "entry": "sgx_reads_pack + sgx_fm_attach_reads x2 + sgx_overlap_edges (pinned host reads / .sai / name ranks in, edges + SS flags out)"
                          + ("; + sgx_edges_gather of all shards' edge records to rank 0 (NCCL)" if world > 1 else "")},
