@@ -136,7 +136,7 @@ def reference_arm(args):
     line = {
         "impl": "reference", "metric": "overlap_reads_per_s", "value": value, "unit": "reads/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample},
         "cpu_baseline": {"value": value, "unit": "reads/s", "cores": threads, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -370,7 +370,7 @@ def main():
     line = {
         "metric": "overlap_reads_per_s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": WORKLOAD if args.scale == 1.0 else WORKLOAD + " [genome scale %g]" % args.scale,
                    "reads_per_gpu": n_reads, "read_len": read_len, "min_overlap": MIN_OVERLAP,
                    "sharding": "FM-indices replicated per GPU, every rank searches its own %d-read shard, no data-path collective" % n_reads,
