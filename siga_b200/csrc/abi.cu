@@ -160,7 +160,7 @@ int sgx_init(int device, sgx_ctx** out) {
     e = cudaFuncGetAttributes(&fa, probe_kernel);
     if (e != cudaSuccess) {
       cudaGetLastError();
-      char b[256];
+      char b[512];
       snprintf(b, sizeof(b), "device %d (%s, sm_%d%d) cannot run the sm_100a kernel image: %s (no fallback)", device,
                prop.name, prop.major, prop.minor, cudaGetErrorString(e));
       g_init_error = b;

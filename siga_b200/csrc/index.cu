@@ -5,8 +5,8 @@
 // CPU thread with SA-IS.  Here the BWT of the read collection is built directly, without a suffix array, by
 // column insertion (the BCR idea the reference vendors in 3rdparty/bcr.c but never calls):
 //
-//   1. Read ordering (N items): LSD stable partition passes over the read columns give the content order; dense
-//      content ranks + prefix doubling over the read sequence give the order of the read-start suffixes under
+//   1. Read ordering (N items): an LSD radix sort over 32-base key chunks (index_content_sort) gives the content order;
+//      dense content ranks + prefix doubling over the read sequence give the order of the read-start suffixes under
 //      ordering model B (`sais2`: all '$' equal, comparison runs on into the next read).  This order IS the .sai
 //      file, and it fixes the order of the N sentinel rows.  Model A (`sais`) orders ties by read index.
 //   2. Column passes j = 1..Lmax: the suffixes of length j are inserted into the BWT of all shorter suffixes.  The
@@ -14,7 +14,9 @@
 //      monotone in the previous row for a fixed c, ordering the inserts is ONE stable 4-way partition by c
 //      (count -> scan -> scatter), and the insertion itself is a streaming merge of the old BWT with the sorted
 //      inserts.  The merge is the dominant kernel: it reads and writes the partial BWT (4 bits per symbol) once
-//      per column (HBM-bound).
+//      per column and rewrites two levels of rank checkpoints (index_kernels.cuh).  An item carries the symbol of its
+//      row (= the first base of its next suffix) and the read word the next symbols come from, so the passes touch
+//      the read store once per 16 columns.
 //   3. Greedy run-length encoding (runs capped at 31) of the final symbol array into .bwt run bytes.
 //
 // Positions are 32-bit while the BWT has < 2^32 rows and 64-bit otherwise (PosT template parameter).
@@ -242,7 +244,6 @@ void index_build(sgx_ctx* ctx, const sgx_reads* reads, int order, bool reversed,
   memset(out, 0, sizeof(*out));
   const uint64_t N = reads->n;
   const uint64_t S = reads->bases + N;
-  const uint32_t lmax = reads->max_len;
   const uint64_t launches0 = ctx->launches;
   EventTimer t_all(ctx->stream), t_sort(ctx->stream), t_bcr(ctx->stream), t_emit(ctx->stream);
   KernelClock k_merge(ctx->stream);
