@@ -2,10 +2,15 @@
 
 #include <thread>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -92,7 +97,7 @@ void push(ReadSet* rs, const std::string& header, const std::string& seq) {
 
 }  // namespace
 
-bool read_sequences(const std::string& path, ReadSet* out, std::string* err) {
+bool read_sequences_serial(const std::string& path, ReadSet* out, std::string* err) {
   LineReader in(path);
   if (!in.ok()) {
     *err = "Failed to open input file " + path;
@@ -149,6 +154,177 @@ bool read_sequences(const std::string& path, ReadSet* out, std::string* err) {
   }
   *err = "failed to create dna reader (the file starts with neither '>' nor '@'): " + path;
   return false;
+}
+
+// ---- parallel parse of plain (uncompressed) files ------------------------------------------------------------------------
+// The file is mapped, cut into one range per thread at record starts, every range is parsed with the same line rules
+// as the serial reader (lines trimmed, empty lines skipped, multi-line FASTA joined) and the parts are concatenated.
+// Anything the serial reader would stop at (a header after an empty FASTA record, a malformed FASTQ record) makes the
+// whole call fall back to the serial reader, so the result is always the serial one.
+namespace {
+
+struct Line {
+  const char* b;
+  const char* e;
+};
+// next trimmed, non-empty line of [p, end); false at the end
+inline bool next_line(const char*& p, const char* end, Line* ln) {
+  while (p < end) {
+    const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+    const char* le = nl ? nl : end;
+    const char* b = p;
+    const char* e = le;
+    p = nl ? nl + 1 : end;
+    while (b < e && isspace((unsigned char)*b)) ++b;
+    while (e > b && isspace((unsigned char)e[-1])) --e;
+    if (b < e) {
+      ln->b = b;
+      ln->e = e;
+      return true;
+    }
+  }
+  return false;
+}
+
+void push_range(ReadSet* rs, const char* hb, const char* he, const std::string& seq) {
+  const char* sp = hb;
+  while (sp < he && *sp != ' ' && *sp != '\t') ++sp;
+  rs->names.emplace_back(hb, sp);
+  rs->comments.emplace_back(sp < he ? sp + 1 : he, he);
+  rs->bases += seq;
+  rs->off.push_back(rs->bases.size());
+}
+
+// false = something the serial reader treats specially: redo serially
+bool parse_fasta_range(const char* p, const char* end, ReadSet* out) {
+  out->off.assign(1, 0);
+  Line ln;
+  const char *hb = nullptr, *he = nullptr;
+  std::string seq;
+  bool have = false;
+  while (next_line(p, end, &ln)) {
+    if (*ln.b == '>') {
+      if (have && !seq.empty()) push_range(out, hb, he, seq);
+      else if (have) return false;
+      hb = ln.b + 1;
+      he = ln.e;
+      seq.clear();
+      have = true;
+    } else {
+      if (!have) return false;
+      seq.append(ln.b, ln.e);
+    }
+  }
+  if (have && !seq.empty()) push_range(out, hb, he, seq);
+  else if (have) return false;
+  return true;
+}
+
+bool parse_fastq_range(const char* p, const char* end, ReadSet* out) {
+  out->off.assign(1, 0);
+  Line h, sq, pl, ql;
+  std::string seq;
+  while (next_line(p, end, &h)) {
+    if (*h.b != '@') return false;
+    if (!next_line(p, end, &sq) || !next_line(p, end, &pl) || !next_line(p, end, &ql)) return false;
+    const size_t nlen = (size_t)(h.e - h.b - 1);
+    const bool plus_ok = *pl.b == '+' && (pl.e - pl.b == 1 || ((size_t)(pl.e - pl.b) >= nlen && memcmp(pl.e - nlen, h.b + 1, nlen) == 0));
+    if (!plus_ok || (ql.e - ql.b) != (sq.e - sq.b)) return false;
+    seq.assign(sq.b, sq.e);
+    push_range(out, h.b + 1, h.e, seq);
+  }
+  return true;
+}
+
+}  // namespace
+
+bool read_sequences(const std::string& path, ReadSet* out, std::string* err) {
+  size_t kMinParallel = (size_t)16 << 20;
+  if (const char* mp = getenv("SIGA_PARSE_MIN_PARALLEL")) kMinParallel = (size_t)strtoull(mp, nullptr, 10);  // tests
+  unsigned T = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+  if (ends_with(path, ".gz") || T < 2) return read_sequences_serial(path, out, err);
+  const int fd = open(path.c_str(), O_RDONLY);
+  if (fd < 0) return read_sequences_serial(path, out, err);  // the serial reader produces the error text
+  struct stat st;
+  if (fstat(fd, &st) != 0 || (size_t)st.st_size < kMinParallel) {
+    close(fd);
+    return read_sequences_serial(path, out, err);
+  }
+  const size_t size = (size_t)st.st_size;
+  const char* base = (const char*)mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+  close(fd);
+  if (base == MAP_FAILED) return read_sequences_serial(path, out, err);
+  const char* end = base + size;
+  const bool fasta = base[0] == '>', fastq = base[0] == '@';
+  bool ok = fasta || fastq;
+  std::vector<const char*> cut;
+  if (ok) {
+    cut.push_back(base);
+    for (unsigned t = 1; t < T; ++t) {
+      const char* p = base + size / T * t;
+      if (p <= cut.back()) continue;
+      const char* found = nullptr;
+      while (p < end) {
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+        if (!nl || nl + 1 >= end) break;
+        p = nl + 1;
+        if (fasta) {
+          if (*p == '>') {
+            found = p;
+            break;
+          }
+        } else if (*p == '@') {
+          // a header, not a quality line: the line after next starts with '+'
+          const char* l2 = (const char*)memchr(p, '\n', (size_t)(end - p));
+          const char* l3 = l2 ? (const char*)memchr(l2 + 1, '\n', (size_t)(end - l2 - 1)) : nullptr;
+          if (l3 && l3 + 1 < end && l3[1] == '+') {
+            found = p;
+            break;
+          }
+        }
+      }
+      if (found && found > cut.back()) cut.push_back(found);
+    }
+    cut.push_back(end);
+    const size_t parts = cut.size() - 1;
+    std::vector<ReadSet> sets(parts);
+    std::vector<char> good(parts, 0);
+    std::vector<std::thread> pool;
+    for (size_t i = 0; i < parts; ++i)
+      pool.emplace_back([&, i]() {
+        good[i] = (fasta ? parse_fasta_range(cut[i], cut[i + 1], &sets[i]) : parse_fastq_range(cut[i], cut[i + 1], &sets[i])) ? 1 : 0;
+      });
+    for (auto& th : pool) th.join();
+    for (size_t i = 0; i < parts; ++i) ok = ok && good[i];
+    if (ok) {
+      // concatenate in place, every part copied by its own thread
+      std::vector<size_t> n0(parts + 1, 0), b0(parts + 1, 0);
+      for (size_t i = 0; i < parts; ++i) {
+        n0[i + 1] = n0[i] + sets[i].names.size();
+        b0[i + 1] = b0[i] + sets[i].bases.size();
+      }
+      out->names.assign(n0[parts], std::string());
+      out->comments.assign(n0[parts], std::string());
+      out->bases.assign(b0[parts], '\0');
+      out->off.assign(n0[parts] + 1, 0);
+      std::vector<std::thread> movers;
+      for (size_t i = 0; i < parts; ++i)
+        movers.emplace_back([&, i]() {
+          ReadSet& s = sets[i];
+          if (!s.bases.empty()) memcpy(&out->bases[b0[i]], s.bases.data(), s.bases.size());
+          for (size_t k = 0; k < s.names.size(); ++k) {
+            out->names[n0[i] + k] = std::move(s.names[k]);
+            out->comments[n0[i] + k] = std::move(s.comments[k]);
+            out->off[n0[i] + k + 1] = b0[i] + s.off[k + 1];
+          }
+          std::string().swap(s.bases);
+        });
+      for (auto& th : movers) th.join();
+    }
+  }
+  munmap((void*)base, size);
+  if (!ok) return read_sequences_serial(path, out, err);
+  return true;
 }
 
 std::string stem(const std::string& path) {

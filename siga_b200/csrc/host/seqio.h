@@ -25,7 +25,10 @@ struct ReadSet {
 };
 
 // Returns false (with a message in *err) when the file cannot be read or is not FASTA/FASTQ.
+// Plain files of 16 MB and more are parsed on all cores (same result as the serial reader, which handles .gz input,
+// small files and anything irregular).
 bool read_sequences(const std::string& path, ReadSet* out, std::string* err);
+bool read_sequences_serial(const std::string& path, ReadSet* out, std::string* err);
 
 std::string stem(const std::string& path);
 

@@ -196,3 +196,39 @@ def test_library_exports_every_declared_symbol_and_refuses_to_run_without_a_gpu(
         assert b"no CUDA device" in lib.sgx_last_error(None) or b"cannot run" in lib.sgx_last_error(None)
         with pytest.raises(api.SgxError):
             api.Context(0)
+
+
+# ------------------------------------------------------------------------------------ host front-end: parallel parser
+
+def test_parallel_sequence_reader_equals_serial_reader(tmp_path):
+    """siga_b200/csrc/host/seqio.cpp: the multi-threaded FASTA/FASTQ reader (plain files) must return exactly what the
+    serial reader returns -- multi-line records, comments, CRLF, blank lines, '@' at the start of quality lines, and the
+    irregular inputs that make it fall back (empty record, truncated FASTQ)."""
+    import subprocess
+    exe = tmp_path / "seqio_check"
+    src = [os.path.join(REPO, "tests", "hostemu", "seqio_check.cpp"), os.path.join(REPO, "siga_b200", "csrc", "host", "seqio.cpp")]
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-o", str(exe)] + src + ["-lz", "-lpthread"], check=True)
+    rng = np.random.default_rng(12)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+    def seq(n):
+        return acgt[rng.integers(0, 4, n)].tobytes().decode()
+
+    files = {}
+    files["plain.fa"] = "".join(">r%d\n%s\n" % (i, seq(60)) for i in range(3000))
+    files["multiline_comments_crlf.fa"] = "".join(
+        ">q%d CR:i:%d  extra\r\n%s\r\n\r\n%s\r\n" % (i, i % 5, seq(35), seq(int(rng.integers(1, 40)))) for i in range(2500))
+    files["quality_at.fq"] = "".join("@s%d c%d\n%s\n+%s\n%s\n" % (i, i, s, "" if i % 2 else "s%d c%d" % (i, i), "@" + "I" * (len(s) - 1))
+                                     for i, s in ((i, seq(50)) for i in range(2500)))
+    files["empty_record.fa"] = files["plain.fa"][:40000] + ">empty\n>next\nACGT\n" + files["plain.fa"][40000:]
+    files["truncated.fq"] = files["quality_at.fq"][:-30]
+    paths = []
+    for name, text in files.items():
+        p = tmp_path / name
+        p.write_text(text, newline="")
+        paths.append(str(p))
+    env = dict(os.environ, SIGA_PARSE_MIN_PARALLEL="1000")
+    r = subprocess.run([str(exe)] + paths, capture_output=True, text=True, env=env)
+    lines = r.stdout.strip().splitlines()
+    assert r.returncode == 0 and len(lines) == len(paths) and all(" same " in l for l in lines), r.stdout + r.stderr
+    assert int(lines[0].split()[-1]) == 3000 and int(lines[2].split()[-1]) == 2500
