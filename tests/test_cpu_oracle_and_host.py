@@ -232,3 +232,52 @@ def test_parallel_sequence_reader_equals_serial_reader(tmp_path):
     lines = r.stdout.strip().splitlines()
     assert r.returncode == 0 and len(lines) == len(paths) and all(" same " in l for l in lines), r.stdout + r.stderr
     assert int(lines[0].split()[-1]) == 3000 and int(lines[2].split()[-1]) == 2500
+
+
+# ------------------------------------------------------------------------- the roofline numerator: executed rank lookups
+
+def _longest_occurring_suffix(s, corpus):
+    """Largest k such that every suffix of s of length <= k occurs in the corpus text (occurrence is monotone)."""
+    lo, hi = 0, len(s)
+    while lo < hi:
+        mid = (lo + hi + 1) // 2
+        if s[len(s) - mid:] in corpus:
+            lo = mid
+        else:
+            hi = mid - 1
+    return lo
+
+
+def expected_search_lookups(reads):
+    """SURVEY.md section 8d: executed 128-byte rank lookups of the four OverlapBlockFinder::find passes of every read --
+    two per step while the interval of the current suffix is non-empty, four more for the containment test when the
+    whole string occurs.  Counted from substring occurrence alone, independent of any FM-index."""
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    fwd = b"$".join(reads)
+    rev = b"$".join(r[::-1] for r in reads)
+    total = 0
+    for r in reads:
+        for s, corpus in ((r, fwd), (r.translate(comp)[::-1], fwd), (r[::-1], rev), (r.translate(comp), rev)):
+            k = _longest_occurring_suffix(s, corpus)
+            total += 2 * min(len(s) - 1, k) + (4 if k == len(s) else 0)
+    return total
+
+
+def test_executed_lookup_counter_matches_a_count_from_first_principles():
+    """The counter that feeds `roofline.achieved` (the same counting rule runs in the CUDA search kernel and in
+    overlap_logic.h) against a count derived from substring occurrence only."""
+    lib = _hostemu()
+    fx = _load([p for p in GOLDEN if "random_fixed36_dups" in p][0])
+    idx = fx["index_sais2"]
+    fr = np.frombuffer(bytes.fromhex(idx["bwt_hex"]), dtype=np.uint8)[30:].copy()
+    rr = np.frombuffer(bytes.fromhex(idx["rbwt_hex"]), dtype=np.uint8)[30:].copy()
+    fwd = lib.hemu_fm_from_rle(fr.ctypes.data, len(fr))
+    rev = lib.hemu_fm_from_rle(rr.ctypes.data, len(rr))
+    reads = [r.encode() for r in fx["reads"]]
+    flat, off = synth.reads_to_flat(reads)
+    h = api._Hits()
+    assert lib.hemu_overlap(fwd, rev, flat.ctypes.data, off.ctypes.data, len(off) - 1, fx["min_overlap"], 1, 1, ctypes.byref(h)) == 0
+    assert int(h.lookups_search) == expected_search_lookups(reads)
+    lib.hemu_hits_free(ctypes.byref(h))
+    lib.hemu_fm_free(fwd)
+    lib.hemu_fm_free(rev)
