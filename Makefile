@@ -7,7 +7,7 @@ HOSTCXX   ?= /usr/bin/g++
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := -std=c++17 -O3 -lineinfo $(ARCH) -ccbin $(HOSTCXX) -Xcompiler -fPIC,-Wall,-Wextra -Xptxas -v --expt-relaxed-constexpr
 CSRC      := siga_b200/csrc
-CU        := $(CSRC)/abi.cu $(CSRC)/reads.cu $(CSRC)/fm.cu $(CSRC)/overlap.cu $(CSRC)/index.cu $(CSRC)/index_sharded.cu $(CSRC)/comm.cu
+CU        := $(CSRC)/abi.cu $(CSRC)/reads.cu $(CSRC)/fm.cu $(CSRC)/overlap.cu $(CSRC)/correct.cu $(CSRC)/index.cu $(CSRC)/index_sharded.cu $(CSRC)/comm.cu
 OBJ       := $(patsubst $(CSRC)/%.cu,build/obj/%.o,$(CU))
 HDR       := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh include/*.h)
 LIB       := siga_b200/libsiga_b200.so

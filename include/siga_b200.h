@@ -250,6 +250,46 @@ void sgx_edges_free(sgx_edges* edges);
  */
 int sgx_edges_gather(sgx_ctx* ctx, sgx_comm* comm, const sgx_edges* local, int root, sgx_edges* out);
 
+/* ---- k-mer error correction (`siga correct`) -------------------------------------------------------------- */
+
+/* Options of KmerCorrector (src/correct_processor.cpp:74-79; defaults src/correct_processor.h:15-20). */
+typedef struct sgx_correct_params {
+  uint32_t kmer_size;         /* -k, default 31                                                                */
+  int32_t kmer_threshold;     /* -x, default 3: a k-mer seen fewer times is a correction candidate             */
+  uint32_t kmer_rounds;       /* -i, default 10                                                                */
+  uint64_t kmer_count_offset; /* -O, default 1                                                                 */
+} sgx_correct_params;
+
+/* One substituted base of a written read: position = pos_code >> 2, new base = "ACGT"[pos_code & 3]. */
+typedef struct sgx_fix {
+  uint32_t read;     /* index relative to `first` */
+  uint32_t pos_code;
+} sgx_fix;
+
+typedef struct sgx_corrected {
+  uint64_t n_reads;
+  uint8_t* valid;      /* n_reads flags: CorrectResult.validQC -- 1: every base ends covered by a solid k-mer and the
+                          read is written (with its fixes); 0: PostCorrector drops it (src/correct_processor.cpp:258-264) */
+  uint64_t n_fixes;
+  sgx_fix* fixes;      /* substitutions of the written reads, any order                                         */
+  double ms_total;     /* device time of the call incl. copies (CUDA events)                                    */
+  double ms_kernel;    /* the correction kernel                                                                 */
+  uint64_t lookups;    /* executed 128-byte rank lookups (two per backward-search step, as in the overlap search) */
+  uint64_t fixed_reads;
+  uint64_t launches;
+} sgx_corrected;
+
+/*
+ * KmerCorrector::process (src/correct_processor.cpp:72-232) for reads [first, first+count) of `reads` against the
+ * FORWARD index `fm` (the reference loads PREFIX.bwt only, src/correct.cpp:45-46); replaces the body of
+ * parallel::foreach in CorrectProcessor::process (src/correct_processor.cpp:282-287).  qual / qual_off: the FASTQ quality
+ * strings of exactly those reads in HOST memory, laid out like sgx_reads_pack's input (qual_off has count + 1
+ * entries); both NULL for FASTA input (DNASeq::score then returns 15, src/kseq.h:34-40).
+ */
+int sgx_correct_batch(sgx_ctx* ctx, const sgx_fm* fm, const sgx_reads* reads, uint64_t first, uint64_t count,
+                      const char* qual, const uint64_t* qual_off, const sgx_correct_params* params, sgx_corrected* out);
+void sgx_corrected_free(sgx_corrected* out);
+
 /* ---- measurement helpers --------------------------------------------------------------------------------- */
 
 /*

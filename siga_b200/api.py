@@ -25,6 +25,7 @@ ABI_SYMBOLS = [
     "sgx_index_build_sharded", "sgx_edges_gather",
     "sgx_fm_create", "sgx_fm_free", "sgx_fm_attach_reads", "sgx_fm_length", "sgx_fm_pred", "sgx_fm_occ", "sgx_fm_count",
     "sgx_overlap_batch", "sgx_overlap_host", "sgx_hits_free", "sgx_overlap_edges", "sgx_edges_free",
+    "sgx_correct_batch", "sgx_corrected_free",
     "sgx_bench_gather", "sgx_flush_l2",
 ]
 
@@ -61,6 +62,20 @@ class _Edges(ctypes.Structure):
 
 
 EDGE_DTYPE = np.dtype([("query", "<u4"), ("target", "<u4"), ("length", "<u4"), ("af", "<u4")])
+
+
+class _CorrectParams(ctypes.Structure):
+    _fields_ = [("kmer_size", ctypes.c_uint32), ("kmer_threshold", ctypes.c_int32), ("kmer_rounds", ctypes.c_uint32),
+                ("kmer_count_offset", ctypes.c_uint64)]
+
+
+class _Corrected(ctypes.Structure):
+    _fields_ = [("n_reads", ctypes.c_uint64), ("valid", ctypes.POINTER(ctypes.c_uint8)), ("n_fixes", ctypes.c_uint64),
+                ("fixes", ctypes.c_void_p), ("ms_total", ctypes.c_double), ("ms_kernel", ctypes.c_double),
+                ("lookups", ctypes.c_uint64), ("fixed_reads", ctypes.c_uint64), ("launches", ctypes.c_uint64)]
+
+
+FIX_DTYPE = np.dtype([("read", "<u4"), ("pos_code", "<u4")])
 
 _lib = None
 
@@ -117,6 +132,9 @@ def load_library():
     lib.sgx_edges_gather.argtypes = [vp, vp, ctypes.POINTER(_Edges), i32, ctypes.POINTER(_Edges)]
     lib.sgx_edges_free.argtypes = [ctypes.POINTER(_Edges)]
     lib.sgx_edges_free.restype = None
+    lib.sgx_correct_batch.argtypes = [vp, vp, vp, u64, u64, vp, vp, ctypes.POINTER(_CorrectParams), ctypes.POINTER(_Corrected)]
+    lib.sgx_corrected_free.argtypes = [ctypes.POINTER(_Corrected)]
+    lib.sgx_corrected_free.restype = None
     lib.sgx_bench_gather.argtypes = [vp, u64, u64, ctypes.POINTER(ctypes.c_double)]
     lib.sgx_flush_l2.argtypes = [vp]
     _lib = lib
@@ -185,6 +203,27 @@ class Edges:
                           lookups_search=int(e.lookups_search), lookups_extract=int(e.lookups_extract),
                           launches=int(e.launches), search_launches=int(e.search_launches),
                           slow_reads=int(e.slow_reads), n_blocks=int(e.n_blocks), n_edges=ne)
+
+
+class Corrected:
+    """Result of sgx_correct_batch: per-read `valid` flags (written / dropped) and the substituted bases."""
+
+    def __init__(self, c):
+        n, nf = int(c.n_reads), int(c.n_fixes)
+        self.n_reads = n
+        self.valid = np.ctypeslib.as_array(c.valid, shape=(max(n, 1),))[:n].copy()
+        buf = (ctypes.c_uint8 * (max(nf, 1) * FIX_DTYPE.itemsize)).from_address(c.fixes)
+        self.fixes = np.frombuffer(buf, dtype=FIX_DTYPE)[:nf].copy()
+        self.stats = dict(ms_total=c.ms_total, ms_kernel=c.ms_kernel, lookups=int(c.lookups), n_fixes=nf,
+                          fixed_reads=int(c.fixed_reads), launches=int(c.launches))
+
+    def apply(self, flat, off, first=0):
+        """Copy of the ASCII bases `flat` (layout of pack_reads) with the fixes of reads [first, first+n) applied."""
+        out = np.array(flat, dtype=np.uint8, copy=True)
+        if len(self.fixes):
+            at = off[first + self.fixes["read"].astype(np.int64)].astype(np.int64) + (self.fixes["pos_code"] >> 2).astype(np.int64)
+            out[at] = np.frombuffer(b"ACGT", dtype=np.uint8)[self.fixes["pos_code"] & 3]
+        return out
 
 
 def name_ranks(names):
@@ -376,6 +415,23 @@ class Context:
             self.lib.sgx_edges_free(ctypes.byref(out))
         else:
             res._raw = out
+        return res
+
+    # ---- k-mer error correction
+    def correct(self, fm, reads, first, count, qual=None, qual_off=None, kmer_size=31, kmer_threshold=3, kmer_rounds=10,
+                kmer_count_offset=1):
+        """KmerCorrector::process for reads [first, first+count); qual/qual_off = the quality strings of those reads."""
+        prm = _CorrectParams(int(kmer_size), int(kmer_threshold), int(kmer_rounds), int(kmer_count_offset))
+        c = _Corrected()
+        qp = qo = None
+        if qual is not None:
+            qual = np.ascontiguousarray(qual, dtype=np.uint8)
+            qual_off = np.ascontiguousarray(qual_off, dtype=np.uint64)
+            qp, qo = _ptr(qual), _ptr(qual_off)
+        self._check(self.lib.sgx_correct_batch(self.h, fm, reads, int(first), int(count), qp, qo, ctypes.byref(prm),
+                                               ctypes.byref(c)))
+        res = Corrected(c)
+        self.lib.sgx_corrected_free(ctypes.byref(c))
         return res
 
     def free_edges(self, edges):

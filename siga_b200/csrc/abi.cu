@@ -4,6 +4,7 @@
 #include <unordered_map>
 
 #include "index.cuh"
+#include "correct.cuh"
 #include "overlap.cuh"
 
 static std::string g_init_error;
@@ -340,6 +341,22 @@ int sgx_fm_count(sgx_ctx* ctx, const sgx_fm* fm, const char* ascii, const uint64
   SGX_ENTRY_BEGIN(ctx)
   fm_count_batch(ctx, fm, ascii, off, n, counts);
   SGX_ENTRY_END(ctx)
+}
+
+int sgx_correct_batch(sgx_ctx* ctx, const sgx_fm* fm, const sgx_reads* reads, uint64_t first, uint64_t count, const char* qual,
+                      const uint64_t* qual_off, const sgx_correct_params* params, sgx_corrected* out) {
+  if (!ctx || !out) return SGX_EINVAL;
+  SGX_ENTRY_BEGIN(ctx)
+  correct_run(ctx, fm, reads, first, count, qual, qual_off, params, out);
+  SGX_ENTRY_END(ctx)
+}
+
+void sgx_corrected_free(sgx_corrected* out) {
+  if (!out) return;
+  pinned_put(out->valid);
+  pinned_put(out->fixes);
+  out->valid = nullptr;
+  out->fixes = nullptr;
 }
 
 int sgx_overlap_batch(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const sgx_reads* reads, uint64_t first,

@@ -86,12 +86,13 @@ void split_name(const std::string& header, std::string* name, std::string* comme
   }
 }
 
-void push(ReadSet* rs, const std::string& header, const std::string& seq) {
+void push(ReadSet* rs, const std::string& header, const std::string& seq, const std::string* qual = nullptr) {
   std::string name, comment;
   split_name(header, &name, &comment);
   rs->names.push_back(name);
   rs->comments.push_back(comment);
   rs->bases += seq;
+  if (qual && rs->keep_quals) rs->quals += *qual;
   rs->off.push_back(rs->bases.size());
 }
 
@@ -106,6 +107,7 @@ bool read_sequences_serial(const std::string& path, ReadSet* out, std::string* e
   out->names.clear();
   out->comments.clear();
   out->bases.clear();
+  out->quals.clear();
   out->off.assign(1, 0);
   const int first = in.peek();
   std::string line;
@@ -146,7 +148,7 @@ bool read_sequences_serial(const std::string& path, ReadSet* out, std::string* e
         state = 3;
       } else {
         if (line.size() != seq.size()) break;
-        push(out, name, seq);
+        push(out, name, seq, &line);
         state = 0;
       }
     }
@@ -232,6 +234,7 @@ bool parse_fastq_range(const char* p, const char* end, ReadSet* out) {
     if (!plus_ok || (ql.e - ql.b) != (sq.e - sq.b)) return false;
     seq.assign(sq.b, sq.e);
     push_range(out, h.b + 1, h.e, seq);
+    if (out->keep_quals) out->quals.append(ql.b, ql.e);
   }
   return true;
 }
@@ -288,6 +291,7 @@ bool read_sequences(const std::string& path, ReadSet* out, std::string* err) {
     cut.push_back(end);
     const size_t parts = cut.size() - 1;
     std::vector<ReadSet> sets(parts);
+    for (auto& s : sets) s.keep_quals = out->keep_quals;
     std::vector<char> good(parts, 0);
     std::vector<std::thread> pool;
     for (size_t i = 0; i < parts; ++i)
@@ -306,12 +310,14 @@ bool read_sequences(const std::string& path, ReadSet* out, std::string* err) {
       out->names.assign(n0[parts], std::string());
       out->comments.assign(n0[parts], std::string());
       out->bases.assign(b0[parts], '\0');
+      out->quals.assign(fastq && out->keep_quals ? b0[parts] : 0, '\0');
       out->off.assign(n0[parts] + 1, 0);
       std::vector<std::thread> movers;
       for (size_t i = 0; i < parts; ++i)
         movers.emplace_back([&, i]() {
           ReadSet& s = sets[i];
           if (!s.bases.empty()) memcpy(&out->bases[b0[i]], s.bases.data(), s.bases.size());
+          if (!s.quals.empty()) memcpy(&out->quals[b0[i]], s.quals.data(), s.quals.size());
           for (size_t k = 0; k < s.names.size(); ++k) {
             out->names[n0[i] + k] = std::move(s.names[k]);
             out->comments[n0[i] + k] = std::move(s.comments[k]);

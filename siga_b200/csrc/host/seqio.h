@@ -21,6 +21,8 @@ struct ReadSet {
   std::vector<std::string> comments;
   std::string bases;            // all reads back to back
   std::vector<uint64_t> off;    // n + 1 offsets into bases
+  bool keep_quals = false;      // set before reading: keep the FASTQ quality strings (`correct` needs them)
+  std::string quals;            // with keep_quals and FASTQ input: qualities, same offsets as bases; else empty
   size_t size() const { return names.size(); }
 };
 

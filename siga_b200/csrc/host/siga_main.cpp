@@ -743,6 +743,182 @@ int cmd_rmdup(int argc, char** argv) {
   return 0;
 }
 
+int usage_correct() {
+  printf("siga correct [OPTION] ... READSFILE\n"
+         "Correct sequencing errors in all the reads in READSFILE\n"
+         "\n"
+         "      -h, --help                       display this help and exit\n"
+         "\n"
+         "      -p, --prefix=PREFIX              use PREFIX instead of prefix of READSFILE for the names of the index files\n"
+         "      -o, --outfile=FILE               write the corrected reads to FILE (default READFILE.ec.fa)\n"
+         "      -t, --threads=NUM                host threads for the output text (the correction runs on the GPU)\n"
+         "      -a, --algorithm=STR              specify the correction algorithm to use. STR must be kmer (default: kmer)\n"
+         "\n"
+         "      -k, --kmer-size=N                the length of the kmer to user (default: 31)\n"
+         "      -x, --kmer-threshold=N           attempt to correct kmers that are seen less than N times (default: 3)\n"
+         "      -i, --kmer-rounds=N              perform up to N rounds of kmer correction (default: 10)\n"
+         "      -O, --kmer-count-offset=N        when correcting a kmer, require the count of the new kmer is at least +N higher than the count of the old kmer. (default: 1)\n"
+         "          --device=N                   CUDA device (default 0)\n"
+         "\n");
+  return 256;
+}
+
+// `siga correct` (src/correct.cpp:22-59, CorrectProcessor::process src/correct_processor.cpp:269-316): loads PREFIX.bwt
+// only, corrects every read with sgx_correct_batch and writes, in input order, the reads that end all-solid
+// (PostCorrector, src/correct_processor.cpp:258-264) in the format of the input (operator<<, src/kseq.cpp:106-125).
+int cmd_correct(int argc, char** argv) {
+  enum { OPT_DEVICE = 1000 };
+  static const option longopts[] = {{"log4cxx", required_argument, nullptr, 'c'},     {"ini", required_argument, nullptr, 's'},
+                                    {"prefix", required_argument, nullptr, 'p'},      {"outfile", required_argument, nullptr, 'o'},
+                                    {"threads", required_argument, nullptr, 't'},     {"algorithm", required_argument, nullptr, 'a'},
+                                    {"kmer-size", required_argument, nullptr, 'k'},   {"kmer-threshold", required_argument, nullptr, 'x'},
+                                    {"kmer-rounds", required_argument, nullptr, 'i'}, {"kmer-count-offset", required_argument, nullptr, 'O'},
+                                    {"device", required_argument, nullptr, OPT_DEVICE}, {"help", no_argument, nullptr, 'h'},
+                                    {nullptr, 0, nullptr, 0}};
+  CommonOpts o;
+  std::string outfile, algorithm = "kmer";
+  sgx_correct_params prm;
+  prm.kmer_size = 31;
+  prm.kmer_threshold = 3;
+  prm.kmer_rounds = 10;
+  prm.kmer_count_offset = 1;
+  int c;
+  while ((c = getopt_long(argc, argv, "c:s:p:o:t:a:k:x:i:O:h", longopts, nullptr)) != -1) {
+    switch (c) {
+      case 't': o.threads = atoi(optarg); break;
+      case 'p': o.prefix = optarg; break;
+      case 'o': outfile = optarg; break;
+      case 'a': algorithm = optarg; break;
+      case 'k': prm.kmer_size = (uint32_t)std::min<unsigned long long>(strtoull(optarg, nullptr, 10), 0xffffffffull); break;
+      case 'x': prm.kmer_threshold = atoi(optarg); break;
+      case 'i': prm.kmer_rounds = (uint32_t)std::min<unsigned long long>(strtoull(optarg, nullptr, 10), 0xffffffffull); break;
+      case 'O': prm.kmer_count_offset = strtoull(optarg, nullptr, 10); break;
+      case OPT_DEVICE: o.device = atoi(optarg); break;
+      case 'h': o.help = true; break;
+      default: break;
+    }
+  }
+  if (o.help || argc - optind != 1) return usage_correct();
+  if (algorithm != "kmer") {
+    // the reference's "overlap" corrector is an empty stub (src/correct_processor.cpp:234-243) and any other name fails
+    fprintf(stderr, "ERROR siga - Failed to do error correction: algorithm '%s' is not available (kmer only)\n", algorithm.c_str());
+    return -1;
+  }
+  const std::string input = argv[optind];
+  const std::string st = stem(input);
+  if (outfile.empty()) outfile = st + ".ec.fa";
+  const std::string prefix = o.prefix.empty() ? st : o.prefix;
+  info("input: %s", input.c_str());
+  const double t0 = now_s();
+  if (o.threads <= 0) o.threads = (int)std::max(1u, std::thread::hardware_concurrency());
+
+  ReadSet rs;
+  rs.keep_quals = true;
+  std::string err;
+  uint64_t ns = 0, nf = 0;
+  std::vector<uint8_t> runs;
+  sgx_ctx* ctx = nullptr;
+  int ctx_rc = SGX_OK;
+  bool ok_bwt = false, ok_reads = false;
+  {
+    std::vector<std::thread> pool;
+    pool.emplace_back([&]() { ctx_rc = sgx_init(o.device, &ctx); });
+    pool.emplace_back([&]() { ok_bwt = read_bwt(prefix + ".bwt", &ns, &nf, &runs); });
+    pool.emplace_back([&]() { ok_reads = read_sequences(input, &rs, &err); });
+    for (auto& t : pool) t.join();
+  }
+  if (!ok_bwt) {
+    fprintf(stderr, "ERROR siga - Failed to load FMIndex from %s\n", prefix.c_str());
+    return -1;
+  }
+  if (!ok_reads) {
+    fprintf(stderr, "ERROR siga - %s\n", err.c_str());
+    return -1;
+  }
+  if (ctx_rc != SGX_OK) return fail(nullptr, "sgx_init", ctx_rc);
+  const bool fastq = !rs.quals.empty();
+  const double t_load = now_s();
+  sgx_corrected res;
+  memset(&res, 0, sizeof(res));
+  sgx_reads* reads = nullptr;
+  sgx_fm* fm = nullptr;
+  int rc = SGX_OK;
+  if (rs.size() > 0) {
+    if ((rc = sgx_reads_pack(ctx, rs.bases.data(), rs.off.data(), rs.size(), &reads)) != SGX_OK) return fail(ctx, "sgx_reads_pack", rc);
+    if ((rc = sgx_fm_create(ctx, runs.data(), runs.size(), nf, &fm)) != SGX_OK) return fail(ctx, "sgx_fm_create", rc);
+    rc = sgx_correct_batch(ctx, fm, reads, 0, rs.size(), fastq ? rs.quals.data() : nullptr, fastq ? rs.off.data() : nullptr, &prm, &res);
+    if (rc != SGX_OK) return fail(ctx, "sgx_correct_batch", rc);
+    info("processed %zu sequences; device %.1f ms (kernel %.1f ms, %.0f rank lookups per read), %llu bases fixed in %llu reads",
+         rs.size(), res.ms_total, res.ms_kernel, (double)res.lookups / (double)rs.size(), (unsigned long long)res.n_fixes,
+         (unsigned long long)res.fixed_reads);
+    for (uint64_t k = 0; k < res.n_fixes; ++k)
+      rs.bases[rs.off[res.fixes[k].read] + (res.fixes[k].pos_code >> 2)] = "ACGT"[res.fixes[k].pos_code & 3];
+  }
+  const double t_gpu = now_s();
+
+  // output: the written reads in input order, text produced on all threads
+  const size_t n = rs.size(), chunk = 1 << 16, n_chunks = (n + chunk - 1) / chunk;
+  auto produce = [&](size_t ci, std::string* text) {
+    const size_t b = ci * chunk, e = std::min(n, b + chunk);
+    text->reserve((e - b) * (fastq ? 400 : 200));
+    for (size_t i = b; i < e; ++i) {
+      if (!res.valid[i]) continue;
+      *text += fastq ? '@' : '>';
+      *text += rs.names[i];
+      if (!rs.comments[i].empty()) {
+        *text += ' ';
+        *text += rs.comments[i];
+      }
+      *text += '\n';
+      text->append(rs.bases, rs.off[i], rs.off[i + 1] - rs.off[i]);
+      *text += '\n';
+      if (fastq) {
+        *text += "+\n";
+        text->append(rs.quals, rs.off[i], rs.off[i + 1] - rs.off[i]);
+        *text += '\n';
+      }
+    }
+  };
+  bool good = true;
+  const bool gz = outfile.size() > 3 && outfile.compare(outfile.size() - 3, 3, ".gz") == 0;
+  if (outfile.size() > 4 && outfile.compare(outfile.size() - 4, 4, ".bz2") == 0) {
+    fprintf(stderr, "ERROR siga - Failed to create DNASeqWriter %s (bzip2 output is not supported by this build)\n", outfile.c_str());
+    return -1;
+  }
+  if (gz) {
+    GzChunkWriter w(outfile, (unsigned)o.threads, o.gzip_level);
+    good = w.ok() && w.write_chunks(std::max<size_t>(n_chunks, 1), [&](size_t ci, std::string* text) {
+      if (ci < n_chunks) produce(ci, text);
+    });
+  } else {
+    FILE* f = fopen(outfile.c_str(), "wb");
+    good = f != nullptr;
+    for (size_t base = 0; base < n_chunks && good; base += (size_t)o.threads) {
+      const size_t m = std::min<size_t>((size_t)o.threads, n_chunks - base);
+      std::vector<std::string> text(m);
+      std::vector<std::thread> pool;
+      for (size_t t = 0; t < m; ++t) pool.emplace_back([&, t]() { produce(base + t, &text[t]); });
+      for (auto& th : pool) th.join();
+      for (size_t t = 0; t < m && good; ++t) good = fwrite(text[t].data(), 1, text[t].size(), f) == text[t].size();
+    }
+    if (f && fclose(f) != 0) good = false;
+  }
+  if (!good) {
+    fprintf(stderr, "ERROR siga - Failed to create DNASeqWriter %s\n", outfile.c_str());
+    return -1;
+  }
+  uint64_t written = 0;
+  for (size_t i = 0; i < n; ++i) written += res.valid[i] ? 1 : 0;
+  info("%llu of %zu reads written to %s", (unsigned long long)written, n, outfile.c_str());
+  sgx_corrected_free(&res);
+  sgx_fm_free(fm);
+  sgx_reads_free(reads);
+  sgx_shutdown(ctx);
+  const double t1 = now_s();
+  info("wall: %.3f sec (load %.3f, gpu %.3f, write %.3f)", t1 - t0, t_load - t0, t_gpu - t_load, t1 - t_gpu);
+  return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -750,7 +926,8 @@ int main(int argc, char** argv) {
     printf("siga (B200 build) -- Usage: siga <command> [<args>]\n\n"
            "   index       build the BWT and FM-index for a set of reads\n"
            "   overlap     compute overlaps between reads\n"
-           "   rmdup       remove duplicated reads from the data set\n\n"
+           "   rmdup       remove duplicated reads from the data set\n"
+           "   correct     correct sequencing errors in a set of reads\n\n"
            "See 'siga <command> -h' to read about a specific subcommand.\n");
     return 256;
   }
@@ -758,6 +935,7 @@ int main(int argc, char** argv) {
   if (cmd == "index") return cmd_index(argc - 1, argv + 1);
   if (cmd == "overlap") return cmd_overlap(argc - 1, argv + 1);
   if (cmd == "rmdup") return cmd_rmdup(argc - 1, argv + 1);
-  fprintf(stderr, "siga: '%s' is not provided by this build (only the index / overlap / rmdup path is)\n", cmd.c_str());
+  if (cmd == "correct") return cmd_correct(argc - 1, argv + 1);
+  fprintf(stderr, "siga: '%s' is not provided by this build (only the index / overlap / rmdup / correct path is)\n", cmd.c_str());
   return 256;
 }

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <vector>
 
+#include "../../siga_b200/csrc/correct_logic.h"
 #include "../../siga_b200/csrc/overlap_logic.h"
 #include "../../siga_b200/csrc/shard_plan.h"
 
@@ -168,6 +169,55 @@ void hemu_hits_free(sgx_hits* h) {
   free(h->block_off);
   free(h->blocks);
   memset(h, 0, sizeof(*h));
+}
+
+// ---- k-mer error correction (siga_b200/csrc/correct_logic.h) on the host engine.  `out` receives the reads with the
+//      fixes applied (same offsets); valid[i] = the read ends all-solid, i.e. the reference would write it.
+int hemu_correct(void* fm_, const char* ascii, const char* qual, const uint64_t* off, uint64_t n, uint32_t k, int threshold,
+                 uint32_t rounds, uint64_t count_offset, char* out, uint8_t* valid, uint32_t* n_fixed, uint64_t* lookups) {
+  const FmView& fm = ((HemuFm*)fm_)->view;
+  if (k == 0) return SGX_EINVAL;
+  CorrectParams P;
+  P.k = k;
+  P.rounds = rounds;
+  P.low = (uint64_t)(int64_t)threshold;
+  P.high = (uint64_t)(int64_t)(threshold + 1);
+  P.count_offset = count_offset;
+  uint64_t look = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    const uint32_t l = (uint32_t)(off[i + 1] - off[i]);
+    if (l == 0) return SGX_EINVAL;
+    std::vector<uint32_t> seq((l + 15) / 16, 0), hq((l + 31) / 32, 0), ks((l + 31) / 32, 0), us((l + 31) / 32, 0);
+    for (uint32_t j = 0; j < l; ++j) {
+      int code;
+      switch (ascii[off[i] + j]) {
+        case 'A': code = 0; break;
+        case 'C': code = 1; break;
+        case 'G': code = 2; break;
+        case 'T': code = 3; break;
+        default: return SGX_EINVAL;
+      }
+      seq[j >> 4] |= (uint32_t)code << (2 * (j & 15));
+      if (qual && (int)(uint8_t)qual[off[i] + j] - kCorrPhredBase >= kCorrPhredCutoff) hq[j >> 5] |= 1u << (j & 31);
+    }
+    CorrectState st;
+    st.seq = seq.data();
+    st.hq = qual ? hq.data() : nullptr;
+    st.ksolid = ks.data();
+    st.unsolid = us.data();
+    HostCorrEng eng;
+    eng.fm = &fm;
+    eng.seq = seq.data();
+    eng.k = k;
+    eng.lookups = 0;
+    uint32_t nf = 0;
+    valid[i] = correct_read(eng, P, l, st, &nf) ? 1 : 0;
+    if (n_fixed) n_fixed[i] = nf;
+    look += eng.lookups;
+    for (uint32_t j = 0; j < l; ++j) out[off[i] + j] = valid[i] ? "ACGT"[read_rank(seq.data(), j) - 1] : ascii[off[i] + j];
+  }
+  if (lookups) *lookups = look;
+  return SGX_OK;
 }
 
 // ---- host-side planning of the bucket-sharded index build (siga_b200/csrc/shard_plan.h), for the CPU emulation in

@@ -1,0 +1,68 @@
+"""CPU tests of the k-mer correction row: correct_logic.h -- the per-read control logic the
+CUDA kernel runs -- instantiated with the single-lane host engine (tests/hostemu), against the committed outputs of the
+compiled reference (`siga correct`, tests/golden/make_golden_correct.py) and against the reference binary itself."""
+import os
+
+import numpy as np
+import pytest
+
+import correct_common as cc
+import refrun
+
+
+def _lib():
+    lib = cc.hostemu_lib()
+    if lib is None:
+        pytest.skip("build/libhostemu.so not built (make hostemu)")
+    return lib
+
+
+@pytest.mark.parametrize("path", cc.GOLDEN, ids=[os.path.basename(p)[:-5] for p in cc.GOLDEN])
+def test_correction_logic_reproduces_reference_output(path):
+    fx = cc.load(path)
+    runs = np.frombuffer(bytes.fromhex(fx["bwt_runs_hex"]), dtype=np.uint8)
+    reads, valid, nfix, lookups = cc.hostemu_correct(_lib(), runs, fx["reads"], fx["quals"], fx["options"])
+    assert cc.ec_text(reads, fx["quals"], valid) == fx["ec_text"]
+    assert int(nfix.sum()) > 0 and 0 < int(valid.sum()) < len(reads)  # the fixture exercises fixes and dropped reads
+    # dropped reads keep their input bases; reads shorter than k are always dropped (src/correct_processor.cpp:84-88)
+    for i, r in enumerate(fx["reads"]):
+        if not valid[i]:
+            assert reads[i] == r
+        if len(r) < fx["options"]["k"]:
+            assert not valid[i]
+
+
+@pytest.mark.skipif(not refrun.have_ref(), reason="compiled reference (oracle/_ref/siga) not present")
+@pytest.mark.parametrize("case", [
+    dict(seed=1, opt=dict(k=21, x=3, i=10, O=1)),
+    dict(seed=2, opt=dict(k=31, x=3, i=10, O=1), fastq=True),
+    dict(seed=3, opt=dict(k=17, x=4, i=3, O=0), fastq=True, variable=True),
+    dict(seed=4, opt=dict(k=1, x=3, i=10, O=1)),
+    dict(seed=5, opt=dict(k=60, x=1, i=10, O=1)),               # k = read length: one k-mer per read
+    dict(seed=6, opt=dict(k=19, x=2, i=0, O=1), both=True),     # no correction rounds at all
+    dict(seed=7, opt=dict(k=15, x=-1, i=10, O=1)),              # negative threshold wraps to a huge size_t in the reference
+], ids=lambda c: "seed%d_k%d" % (c["seed"], c["opt"]["k"]))
+def test_correction_logic_equals_reference_binary(case):
+    reads, quals = cc.random_case(case["seed"], fastq=case.get("fastq", False), variable=case.get("variable", False),
+                                  both=case.get("both", False))
+    runs, _, want = cc.reference_correct(reads, quals, case["opt"])
+    got_reads, valid, _, _ = cc.hostemu_correct(_lib(), runs, reads, quals, case["opt"])
+    assert cc.ec_text(got_reads, quals, valid) == want
+
+
+def test_lookup_count_of_clean_reads_is_the_nominal_figure():
+    """Error-free reads at high coverage: every k-mer is solid after one counting round, so the executed rank lookups
+    are exactly 2 (k-1) (n-k+1) per read -- the algorithmic-work figure DESIGN.md quotes for the correction kernel."""
+    rng = np.random.default_rng(9)
+    from siga_b200 import formats, synth
+    from oracle import pyoracle
+    g = synth.random_genome(300, rng)
+    reads = [x.tobytes().decode() for x in synth.sample_reads(g, 400, 40, rng, err=0.0, both_strands=False)]
+    bwt, _ = pyoracle.bwt_and_sai(reads, "B")
+    runs = formats.encode_runs(bwt)
+    k = 17
+    out, valid, nfix, lookups = cc.hostemu_correct(_lib(), runs, reads, None, dict(k=k, x=2, i=10, O=1))
+    solid = int(valid.sum())
+    assert int(nfix.sum()) == 0 and out == reads and solid > 0.9 * len(reads)
+    if solid == len(reads):
+        assert lookups == len(reads) * 2 * (k - 1) * (40 - k + 1)

@@ -231,7 +231,8 @@ def test_parallel_sequence_reader_equals_serial_reader(tmp_path):
     r = subprocess.run([str(exe)] + paths, capture_output=True, text=True, env=env)
     lines = r.stdout.strip().splitlines()
     assert r.returncode == 0 and len(lines) == len(paths) and all(" same " in l for l in lines), r.stdout + r.stderr
-    assert int(lines[0].split()[-1]) == 3000 and int(lines[2].split()[-1]) == 2500
+    assert int(lines[0].split()[2]) == 3000 and int(lines[2].split()[2]) == 2500
+    assert lines[2].endswith(" q") and not lines[0].endswith(" q")  # qualities kept for FASTQ only
 
 
 # ------------------------------------------------------------------------- the roofline numerator: executed rank lookups
