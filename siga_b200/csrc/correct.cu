@@ -26,51 +26,108 @@ struct DevCorrEng {
   IdxT pc1, pc2, pc3, pc4, pc5;  // C[] of the index by rank (pred[1..5]; pred[5] = n)
   const uint32_t* seq;           // working sequence of this warp's read (shared memory)
   uint32_t k;
+  uint64_t low, high;            // the two support thresholds of the certificate searches
+  bool two;                      // qualities present: k-mers of both threshold classes exist
   int lane, q, qbase, slot;
   unsigned long long nlook;
 
   __device__ __forceinline__ bool leader() const { return lane == 0; }
   __device__ __forceinline__ void sync() const { __syncwarp(); }
+  __device__ __forceinline__ uint32_t lane_id() const { return (uint32_t)lane; }
+  __device__ __forceinline__ uint32_t num_lanes() const { return 32u; }
+  __device__ __forceinline__ void atomic_or(uint32_t* p, uint32_t m) const { atomicOr(p, m); }
   __device__ __forceinline__ IdxT pcv(int c) const { return c == 1 ? pc1 : (c == 2 ? pc2 : (c == 3 ? pc3 : (c == 4 ? pc4 : pc5))); }
 
-  // All 32 lanes call this together; quad s answers query gen(s).  Finished / idle quads ride along with their loads
-  // pointed at block 0, so that every shuffle is a full-mask shuffle (see ov_search_quad_kernel).
+  // One backward-search step of every quad of the warp: interval [lo, hi] of the quad's string extended by symbol c.
+  // Idle quads ride along with their loads pointed at block 0, so that every shuffle is a full-mask shuffle (see
+  // ov_search_quad_kernel).
+  __device__ __forceinline__ void step(bool active, int c, IdxT& lo, IdxT& hi) {
+    const unsigned kFull = 0xffffffffu;
+    const QuadRank<IdxT> r = quad_rank<IdxT>(blocks, active ? lo : (IdxT)0, active ? (IdxT)(hi + 1) : (IdxT)0, q);
+    const IdxT Lc = __shfl_sync(kFull, r.Lq, qbase + c - 1);
+    const IdxT Uc = __shfl_sync(kFull, r.Uq, qbase + c - 1);
+    if (active) {
+      nlook += 2;
+      const IdxT pc = pcv(c);
+      lo = pc + Lc;
+      hi = pc + Uc - 1;
+    }
+  }
+  __device__ __forceinline__ uint64_t size_of(IdxT lo, IdxT hi) const {
+    return (hi != (IdxT)-1 && hi >= lo) ? (uint64_t)(IdxT)(hi - lo) + 1 : 0;
+  }
+
+  // try2Correct queries: all 32 lanes call this together; quad s answers query gen(s).
   template <class Gen>
   __device__ __forceinline__ uint32_t qualify(Gen gen) {
     const unsigned kFull = 0xffffffffu;
-    const IdxT kNone = (IdxT)-1;
     const KmerQuery kq = gen(slot);
     uint32_t j = kq.kidx + k - 1;  // read position of the last k-mer symbol: the search starts there
     int c = kq.have ? corr_query_sym(kq, seq, j) : 1;
     IdxT lo = pcv(c), hi = (IdxT)(pcv(c + 1) - 1);
     uint32_t steps = k - 1;
-    bool live = kq.have && steps > 0 && hi != kNone && hi >= lo;
+    uint64_t size = size_of(lo, hi);
+    // the interval only shrinks: the search can stop as soon as it is smaller than the count asked for
+    bool live = kq.have && steps > 0 && size > 0 && size >= kq.min_count;
 #pragma unroll 1
     while (__any_sync(kFull, live)) {
       if (live) {
         --j;
         c = corr_query_sym(kq, seq, j);
       }
-      const QuadRank<IdxT> r = quad_rank<IdxT>(blocks, live ? lo : (IdxT)0, live ? (IdxT)(hi + 1) : (IdxT)0, q);
-      const IdxT Lc = __shfl_sync(kFull, r.Lq, qbase + c - 1);
-      const IdxT Uc = __shfl_sync(kFull, r.Uq, qbase + c - 1);
+      step(live, c, lo, hi);
       if (live) {
-        nlook += 2;
-        const IdxT pc = pcv(c);
-        lo = pc + Lc;
-        hi = pc + Uc - 1;
         --steps;
-        live = steps > 0 && hi != kNone && hi >= lo;
+        size = size_of(lo, hi);
+        live = steps > 0 && size > 0 && size >= kq.min_count;
       }
     }
-    const bool valid = kq.have && hi != kNone && hi >= lo;
-    const uint64_t count = valid ? (uint64_t)(IdxT)(hi - lo) + 1 : 0;
-    const bool ok = kq.have && count >= kq.min_count;
+    const bool ok = kq.have && size >= kq.min_count;
     const unsigned b = __ballot_sync(kFull, ok && q == 0);
     uint32_t out = 0;
 #pragma unroll
     for (int s = 0; s < kCorrSlots; ++s) out |= ((b >> (4 * s)) & 1u) << s;
     return out;
+  }
+
+  // Certificate searches (correct_logic.h: WinQuery): quad s searches read[a..e] of query gen(s) from e towards a and
+  // stores {a, e, drop_low, drop_high} at out[4 s].  The caller synchronises before reading `out`.
+  template <class Gen>
+  __device__ __forceinline__ void windows(Gen gen, uint32_t* out) {
+    const unsigned kFull = 0xffffffffu;
+    const WinQuery wq = gen(slot);
+    uint32_t pos = wq.e, dl = kCorrNone, dh = kCorrNone;
+    bool fl = false, fh = !two;
+    int c = wq.have ? read_rank(seq, pos) : 1;
+    IdxT lo = pcv(c), hi = (IdxT)(pcv(c + 1) - 1);
+    bool alive = wq.have;
+#pragma unroll 1
+    for (;;) {
+      if (alive) {
+        const uint64_t size = size_of(lo, hi);
+        if (!fl && size < low) {
+          dl = pos;
+          fl = true;
+        }
+        if (!fh && size < high) {
+          dh = pos;
+          fh = true;
+        }
+        if (size == 0 || (fl && fh) || pos == wq.a) alive = false;
+      }
+      if (!__any_sync(kFull, alive)) break;
+      if (alive) {
+        --pos;
+        c = read_rank(seq, pos);
+      }
+      step(alive, c, lo, hi);
+    }
+    if (wq.have && q == 0) {
+      out[4 * slot] = wq.a;
+      out[4 * slot + 1] = wq.e;
+      out[4 * slot + 2] = dl;
+      out[4 * slot + 3] = dh;
+    }
   }
 };
 
@@ -102,6 +159,12 @@ __global__ void __launch_bounds__(256) corr_hq_kernel(const char* __restrict__ q
   }
 }
 
+// Shared-memory words of one warp: sequence | quality bits, khigh, known, ksolid, unsolid, tmp | certificate results |
+// remembered rare strings.
+__host__ __device__ inline size_t corr_smem_words(uint32_t w16, uint32_t w32) {
+  return (size_t)w16 + 6 * (size_t)w32 + kCorrWinWords + kCorrDeadCap;
+}
+
 struct CorrCounters {
   unsigned long long next_read, n_fixes, lookups, fixed_reads;
 };
@@ -113,13 +176,18 @@ corr_kernel(FmView fm, ReadsView reads, uint64_t first, uint64_t count, const ui
             CorrCounters* __restrict__ ctr) {
   extern __shared__ uint32_t corr_smem[];
   const int lane = threadIdx.x & 31;
-  uint32_t* mine = corr_smem + (size_t)(threadIdx.x >> 5) * (w16 + 3 * w32);
+  uint32_t* mine = corr_smem + (size_t)(threadIdx.x >> 5) * corr_smem_words(w16, w32);
   CorrectState st;
   st.seq = mine;
   uint32_t* hqs = mine + w16;
   st.hq = hq ? hqs : nullptr;
-  st.ksolid = hqs + w32;
+  st.khigh = hqs + w32;
+  st.known = st.khigh + w32;
+  st.ksolid = st.known + w32;
   st.unsolid = st.ksolid + w32;
+  st.tmp = st.unsolid + w32;
+  st.win = st.tmp + w32;
+  st.dead = st.win + kCorrWinWords;
   DevCorrEng<IdxT> eng;
   eng.blocks = fm.blocks;
   eng.pc1 = (IdxT)fm.pred[1];
@@ -129,6 +197,9 @@ corr_kernel(FmView fm, ReadsView reads, uint64_t first, uint64_t count, const ui
   eng.pc5 = (IdxT)fm.pred[5];
   eng.seq = st.seq;
   eng.k = P.k;
+  eng.low = P.low;
+  eng.high = P.high;
+  eng.two = hq != nullptr;
   eng.lane = lane;
   eng.q = lane & (kQuad - 1);
   eng.qbase = lane & ~(kQuad - 1);
@@ -248,7 +319,7 @@ void correct_run(sgx_ctx* ctx, const sgx_fm* fm, const sgx_reads* reads, uint64_
   DevBuf<uint8_t> d_valid(count);
   DevBuf<CorrCounters> d_ctr(1);
   SGX_CUDA(cudaMemsetAsync(d_ctr.p, 0, sizeof(CorrCounters), ctx->stream));
-  const size_t smem = (size_t)8 * (w16 + 3 * w32) * sizeof(uint32_t);
+  const size_t smem = 8 * corr_smem_words(w16, w32) * sizeof(uint32_t);
   const char* fw = getenv("SGX_FORCE_WIDE");  // tests: exercise the 64-bit position path on small inputs
   const bool wide = fm->n >= 0xffffffffull || (fw && fw[0] == '1');
   if (smem > 48 * 1024) {

@@ -173,6 +173,10 @@ void hemu_hits_free(sgx_hits* h) {
 
 // ---- k-mer error correction (siga_b200/csrc/correct_logic.h) on the host engine.  `out` receives the reads with the
 //      fixes applied (same offsets); valid[i] = the read ends all-solid, i.e. the reference would write it.
+static uint64_t g_corr_stats[4];
+// {certificate calls, their warp steps (longest query per call), try2Correct calls, their warp steps} of the last hemu_correct
+void hemu_correct_stats(uint64_t out[4]) { memcpy(out, g_corr_stats, sizeof(g_corr_stats)); }
+
 int hemu_correct(void* fm_, const char* ascii, const char* qual, const uint64_t* off, uint64_t n, uint32_t k, int threshold,
                  uint32_t rounds, uint64_t count_offset, char* out, uint8_t* valid, uint32_t* n_fixed, uint64_t* lookups) {
   const FmView& fm = ((HemuFm*)fm_)->view;
@@ -184,10 +188,12 @@ int hemu_correct(void* fm_, const char* ascii, const char* qual, const uint64_t*
   P.high = (uint64_t)(int64_t)(threshold + 1);
   P.count_offset = count_offset;
   uint64_t look = 0;
+  memset(g_corr_stats, 0, sizeof(g_corr_stats));
   for (uint64_t i = 0; i < n; ++i) {
     const uint32_t l = (uint32_t)(off[i + 1] - off[i]);
     if (l == 0) return SGX_EINVAL;
-    std::vector<uint32_t> seq((l + 15) / 16, 0), hq((l + 31) / 32, 0), ks((l + 31) / 32, 0), us((l + 31) / 32, 0);
+    std::vector<uint32_t> seq((l + 15) / 16, 0), hq((l + 31) / 32, 0), ks((l + 31) / 32, 0), us((l + 31) / 32, 0),
+        kh((l + 31) / 32, 0), kn((l + 31) / 32, 0), win(kCorrWinWords, 0), dead(kCorrDeadCap, 0), tmp((l + 31) / 32, 0);
     for (uint32_t j = 0; j < l; ++j) {
       int code;
       switch (ascii[off[i] + j]) {
@@ -203,17 +209,29 @@ int hemu_correct(void* fm_, const char* ascii, const char* qual, const uint64_t*
     CorrectState st;
     st.seq = seq.data();
     st.hq = qual ? hq.data() : nullptr;
+    st.khigh = kh.data();
+    st.known = kn.data();
     st.ksolid = ks.data();
     st.unsolid = us.data();
+    st.win = win.data();
+    st.dead = dead.data();
+    st.tmp = tmp.data();
     HostCorrEng eng;
     eng.fm = &fm;
     eng.seq = seq.data();
     eng.k = k;
+    eng.low = P.low;
+    eng.high = P.high;
     eng.lookups = 0;
+    eng.win_calls = eng.win_steps = eng.qual_calls = eng.qual_steps = 0;
     uint32_t nf = 0;
     valid[i] = correct_read(eng, P, l, st, &nf) ? 1 : 0;
     if (n_fixed) n_fixed[i] = nf;
     look += eng.lookups;
+    g_corr_stats[0] += eng.win_calls;
+    g_corr_stats[1] += eng.win_steps;
+    g_corr_stats[2] += eng.qual_calls;
+    g_corr_stats[3] += eng.qual_steps;
     for (uint32_t j = 0; j < l; ++j) out[off[i] + j] = valid[i] ? "ACGT"[read_rank(seq.data(), j) - 1] : ascii[off[i] + j];
   }
   if (lookups) *lookups = look;
