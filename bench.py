@@ -101,6 +101,9 @@ def run_reference_sample(scale, threads, workdir, want_index=True):
     subprocess.run([ref, "overlap", "-m", str(MIN_OVERLAP), "-t", str(threads), fa], cwd=workdir, env=env, check=True,
                    capture_output=True)
     out["overlap_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    subprocess.run([ref, "correct", "-t", str(threads), fa], cwd=workdir, env=env, check=True, capture_output=True)
+    out["correct_s"] = time.perf_counter() - t0
     return out
 
 
@@ -350,6 +353,36 @@ def main():
     barrier()
     idx_e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / isteps)
     idx_dev_ms = max_over_ranks(idx_dev_ms)
+
+    # ---- k-mer error correction (`siga correct`, defaults -k 31 -x 3 -i 10 -O 1) of the same reads against the forward
+    #      index: resident (reads + index in HBM) and end to end (pinned host reads in, flags + fixes out)
+    csteps = min(args.steps, 3)
+    ctx.correct(fwd, r_dev, 0, n_reads)
+    barrier()
+    t0 = time.perf_counter()
+    corr_kernel_ms = 0.0
+    corr_look = corr_launches = 0
+    for _ in range(csteps):
+        cr = ctx.correct(fwd, r_dev, 0, n_reads)
+        corr_kernel_ms += cr.stats["ms_kernel"]
+        corr_look += cr.stats["lookups"]
+        corr_launches += cr.stats["launches"]
+    barrier()
+    corr_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / csteps)
+    # size-independent properties at full size: a written read differs from its input exactly at its fixes, every fix
+    # changes the base, dropped reads carry no fixes
+    fx_pos = off[cr.fixes["read"].astype(np.int64)].astype(np.int64) + (cr.fixes["pos_code"] >> 2).astype(np.int64)
+    assert np.all(cr.valid[cr.fixes["read"]] == 1) and len(np.unique(fx_pos)) == len(fx_pos)
+    assert np.all(flat[fx_pos] != np.frombuffer(b"ACGT", dtype=np.uint8)[cr.fixes["pos_code"] & 3])
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(csteps):
+        rr = ctx.pack_reads(flat, off)
+        c2 = ctx.correct(fwd, rr, 0, n_reads)
+        ctx.free_reads(rr)
+    barrier()
+    corr_e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / csteps)
+    assert np.array_equal(c2.valid, cr.valid) and len(c2.fixes) == len(cr.fixes)
     if comm is not None:
         ctx.free_comm(comm)
     clocks = sampler.stop()
@@ -410,6 +443,19 @@ def main():
                                "merge_ms_per_build": idx_merge_ms / (2 * isteps),
                                "floor_bytes_per_suffix": idx_suffix_bytes,
                                "floor_frac": idx_suffix_bytes * 2 * fi.n_suffixes / (idx_dev_ms / isteps * 1e-3) / 1e9 / hbm_peak}},
+        "correct": {"metric": "correct_reads_per_s", "value": total_reads / (corr_ms * 1e-3), "unit": "reads/s",
+                    "ms_per_step": corr_ms, "steps": csteps, "kernel_ms_per_step": corr_kernel_ms / csteps,
+                    "scaling": "weak", "options": "-k 31 -x 3 -i 10 -O 1 (the reference's defaults), forward index only",
+                    "written_reads": int(cr.valid.sum()), "fixed_bases": int(len(cr.fixes)), "gpu_launches": int(corr_launches),
+                    "e2e": {"value": total_reads / (corr_e2e_ms * 1e-3), "unit": "reads/s", "ms_per_step": corr_e2e_ms,
+                            "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(cr.valid.nbytes + cr.fixes.nbytes),
+                            "entry": "sgx_reads_pack + sgx_correct_batch (pinned host reads in, written flags + fixes out)"},
+                    "roofline": {"bound": "hbm", "kernel": "corr_kernel", "unit": "GB/s", "peak": hbm_peak,
+                                 "achieved": corr_look * 128 / (corr_kernel_ms * 1e-3) / 1e9 if corr_kernel_ms else 0.0,
+                                 "frac": corr_look * 128 / (corr_kernel_ms * 1e-3) / 1e9 / hbm_peak if corr_kernel_ms else 0.0,
+                                 "traffic": None, "lookups_per_read": corr_look / csteps / n_reads,
+                                 "reference_lookups_per_read_nominal": 2 * 30 * (read_len - 30),
+                                 "lookups_per_s": corr_look / (corr_kernel_ms * 1e-3) if corr_kernel_ms else 0.0}},
         "clocks": clocks,
     }
 
@@ -422,7 +468,8 @@ def main():
             line["cpu_baseline"] = {"value": cpu["reads"] / cpu["overlap_s"], "unit": "reads/s", "cores": cpu["threads"],
                                     "kind": "reference", "sample": sample, "seconds": cpu["overlap_s"],
                                     "index_gbases_per_s": cpu["bases"] / cpu["index_s"] / 1e9, "index_seconds": cpu["index_s"],
-                                    "index_cores": 1}
+                                    "index_cores": 1, "correct_reads_per_s": cpu["reads"] / cpu["correct_s"],
+                                    "correct_seconds": cpu["correct_s"]}
     ctx.free_fm(fwd)
     ctx.free_fm(rev)
     ctx.free_reads(r_dev)

@@ -39,7 +39,7 @@ def main():
         n, L = reads.shape
         print("%s scale %g: %d reads x %d bp, FASTA %.1f MB" % (cfg, scale, n, L, os.path.getsize(fa) / 1e6))
         for rep in range(2):  # the first run pays the page-in of the binary / driver start-up
-            for args in (["index", fa], ["overlap", "-m", "45", fa], ["rmdup", fa]):
+            for args in (["index", fa], ["overlap", "-m", "45", fa], ["rmdup", fa], ["correct", fa]):
                 dt, lines = run(cli, args, d)
                 unit = n * L / dt / 1e9 if args[0] == "index" else n / dt / 1e6
                 print("run %d: siga %-8s %8.3f s  (%.3f %s)" % (rep, args[0], dt, unit, "Gbases/s" if args[0] == "index" else "M reads/s"))
@@ -56,7 +56,7 @@ def main():
             env = dict(os.environ, ORACLE_LOG_LEVEL="5")
             th = str(os.cpu_count() or 1)
             print("reference binary, %s scale %g: %d reads, %s host threads" % (cfg, ref_scale, n, th))
-            for args in (["index", fa], ["overlap", "-m", "45", "-t", th, fa], ["rmdup", "-t", th, fa]):
+            for args in (["index", fa], ["overlap", "-m", "45", "-t", th, fa], ["rmdup", "-t", th, fa], ["correct", "-t", th, fa]):
                 dt, _ = run(ref, args, d, env)
                 unit = n * L / dt / 1e9 if args[0] == "index" else n / dt / 1e6
                 print("      siga %-8s %8.3f s  (%.4f %s)" % (args[0], dt, unit, "Gbases/s" if args[0] == "index" else "M reads/s"))
