@@ -26,7 +26,7 @@ struct DevCorrEng {
   IdxT pc1, pc2, pc3, pc4, pc5;  // C[] of the index by rank (pred[1..5]; pred[5] = n)
   const uint32_t* seq;           // working sequence of this warp's read (shared memory)
   uint32_t k;
-  uint64_t low, high;            // the two support thresholds of the certificate searches
+  IdxT low, high;                // the two support thresholds of the certificate searches (clamp_count)
   bool two;                      // qualities present: k-mers of both threshold classes exist
   int lane, q, qbase, slot;
   unsigned long long nlook;
@@ -38,23 +38,23 @@ struct DevCorrEng {
   __device__ __forceinline__ void atomic_or(uint32_t* p, uint32_t m) const { atomicOr(p, m); }
   __device__ __forceinline__ IdxT pcv(int c) const { return c == 1 ? pc1 : (c == 2 ? pc2 : (c == 3 ? pc3 : (c == 4 ? pc4 : pc5))); }
 
-  // One backward-search step of every quad of the warp: interval [lo, hi] of the quad's string extended by symbol c.
-  // Idle quads ride along with their loads pointed at block 0, so that every shuffle is a full-mask shuffle (see
-  // ov_search_quad_kernel).
-  __device__ __forceinline__ void step(bool active, int c, IdxT& lo, IdxT& hi) {
-    const unsigned kFull = 0xffffffffu;
-    const QuadRank<IdxT> r = quad_rank<IdxT>(blocks, active ? lo : (IdxT)0, active ? (IdxT)(hi + 1) : (IdxT)0, q);
-    const IdxT Lc = __shfl_sync(kFull, r.Lq, qbase + c - 1);
-    const IdxT Uc = __shfl_sync(kFull, r.Uq, qbase + c - 1);
+  // One backward-search step of every quad of the warp: the interval [lo, lo + size) of the quad's string extended by
+  // symbol c (FMIndex::Interval::update, src/fmindex.h:96-100; an empty interval is size 0, which is what the
+  // reference's upper = lower - 1 amounts to).  Idle quads ride along with their loads pointed at block 0, so that every
+  // shuffle is a full-mask shuffle (see ov_search_quad_kernel).
+  __device__ __forceinline__ void step(bool active, int c, IdxT& lo, IdxT& size) {
+    IdxT Lc, Uc;
+    quad_rank_sym<IdxT>(blocks, active ? lo : (IdxT)0, active ? (IdxT)(lo + size) : (IdxT)0, q, qbase, c, Lc, Uc);
     if (active) {
       nlook += 2;
-      const IdxT pc = pcv(c);
-      lo = pc + Lc;
-      hi = pc + Uc - 1;
+      lo = pcv(c) + Lc;
+      size = Uc - Lc;
     }
   }
-  __device__ __forceinline__ uint64_t size_of(IdxT lo, IdxT hi) const {
-    return (hi != (IdxT)-1 && hi >= lo) ? (uint64_t)(IdxT)(hi - lo) + 1 : 0;
+  // Counts are compared in the position type: with 32-bit positions every count is below 2^32 - 1, so a larger
+  // threshold behaves like 2^32 - 1 (never reached).
+  __device__ __forceinline__ static IdxT clamp_count(uint64_t v) {
+    return (sizeof(IdxT) == 4 && v > 0xffffffffull) ? (IdxT)0xffffffffu : (IdxT)v;
   }
 
   // try2Correct queries: all 32 lanes call this together; quad s answers query gen(s).
@@ -62,28 +62,26 @@ struct DevCorrEng {
   __device__ __forceinline__ uint32_t qualify(Gen gen) {
     const unsigned kFull = 0xffffffffu;
     const KmerQuery kq = gen(slot);
+    const IdxT need = clamp_count(kq.min_count);
     uint32_t j = kq.kidx + k - 1;  // read position of the last k-mer symbol: the search starts there
     int c = kq.have ? corr_query_sym(kq, seq, j) : 1;
-    IdxT lo = pcv(c), hi = (IdxT)(pcv(c + 1) - 1);
+    IdxT lo = pcv(c), size = (IdxT)(pcv(c + 1) - lo);
     uint32_t steps = k - 1;
-    uint64_t size = size_of(lo, hi);
     // the interval only shrinks: the search can stop as soon as it is smaller than the count asked for
-    bool live = kq.have && steps > 0 && size > 0 && size >= kq.min_count;
+    bool live = kq.have && steps > 0 && size > 0 && size >= need;
 #pragma unroll 1
     while (__any_sync(kFull, live)) {
       if (live) {
         --j;
         c = corr_query_sym(kq, seq, j);
       }
-      step(live, c, lo, hi);
+      step(live, c, lo, size);
       if (live) {
         --steps;
-        size = size_of(lo, hi);
-        live = steps > 0 && size > 0 && size >= kq.min_count;
+        live = steps > 0 && size > 0 && size >= need;
       }
     }
-    const bool ok = kq.have && size >= kq.min_count;
-    const unsigned b = __ballot_sync(kFull, ok && q == 0);
+    const unsigned b = __ballot_sync(kFull, kq.have && size >= need && q == 0);
     uint32_t out = 0;
 #pragma unroll
     for (int s = 0; s < kCorrSlots; ++s) out |= ((b >> (4 * s)) & 1u) << s;
@@ -99,12 +97,11 @@ struct DevCorrEng {
     uint32_t pos = wq.e, dl = kCorrNone, dh = kCorrNone;
     bool fl = false, fh = !two;
     int c = wq.have ? read_rank(seq, pos) : 1;
-    IdxT lo = pcv(c), hi = (IdxT)(pcv(c + 1) - 1);
+    IdxT lo = pcv(c), size = (IdxT)(pcv(c + 1) - lo);
     bool alive = wq.have;
 #pragma unroll 1
     for (;;) {
       if (alive) {
-        const uint64_t size = size_of(lo, hi);
         if (!fl && size < low) {
           dl = pos;
           fl = true;
@@ -120,7 +117,7 @@ struct DevCorrEng {
         --pos;
         c = read_rank(seq, pos);
       }
-      step(alive, c, lo, hi);
+      step(alive, c, lo, size);
     }
     if (wq.have && q == 0) {
       out[4 * slot] = wq.a;
@@ -197,8 +194,8 @@ corr_kernel(FmView fm, ReadsView reads, uint64_t first, uint64_t count, const ui
   eng.pc5 = (IdxT)fm.pred[5];
   eng.seq = st.seq;
   eng.k = P.k;
-  eng.low = P.low;
-  eng.high = P.high;
+  eng.low = DevCorrEng<IdxT>::clamp_count(P.low);
+  eng.high = DevCorrEng<IdxT>::clamp_count(P.high);
   eng.two = hq != nullptr;
   eng.lane = lane;
   eng.q = lane & (kQuad - 1);

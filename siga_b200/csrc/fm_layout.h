@@ -55,6 +55,19 @@ SGX_HD void fm_lane_counts(uint32_t p0, uint32_t p1, uint32_t p2, int k, int r, 
   w2 = (uint32_t)popc32(hi & ~p0) | ((uint32_t)popc32(hi & p0) << 16);
 }
 
+// Single-symbol variant: how many of the first r symbols of a block that lane k holds are the symbol with code bits
+// (b0, b1), given x0 = b0 ? 0 : ~0 and x1 = b1 ? 0 : ~0 (so that p ^ x is 1 exactly where the plane bit equals the code bit).
+SGX_HD uint32_t fm_lane_sym_count(uint32_t p0, uint32_t p1, uint32_t p2, int k, int r, uint32_t x0, uint32_t x1) {
+  const int nb = r - 32 * k;
+  uint32_t hi_mask;
+#ifdef __CUDA_ARCH__
+  asm("shl.b32 %0, %1, %2;" : "=r"(hi_mask) : "r"(0xffffffffu), "r"((uint32_t)(nb > 0 ? nb : 0)));  // 0 for shifts >= 32
+#else
+  hi_mask = nb >= 32 ? 0u : (nb <= 0 ? 0xffffffffu : (0xffffffffu << nb));
+#endif
+  return (uint32_t)popc32(~(p2 | hi_mask) & (p0 ^ x0) & (p1 ^ x1));
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Group policies.  All control flow that uses a group is "group-uniform": every lane of the group executes the
 // same path with the same scalar state; only the rank query splits work across lanes.

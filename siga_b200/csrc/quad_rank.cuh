@@ -82,6 +82,42 @@ __device__ __forceinline__ QuadRank<IdxT> quad_rank(const FmBlockLane* __restric
   return out;
 }
 
+// Rank of ONE symbol c (1..4, the same on the four lanes of a quad) at prefix lengths plo <= phi: Lc = occurrences in
+// [0, plo), Uc = in [0, phi).  Same loads as quad_rank, a third of its arithmetic: one popcount per uint4, both ends
+// summed in one packed register (two xor-shuffles), the block headers of symbol c fetched from lane c-1 of the quad.
+// This is all a plain backward search (FMIndex::Interval::update, src/fmindex.h:96-100) needs.
+template <class IdxT>
+__device__ __forceinline__ void quad_rank_sym(const FmBlockLane* __restrict__ blocks, IdxT plo, IdxT phi, int q, int qbase,
+                                              int c, IdxT& Lc, IdxT& Uc) {
+  const unsigned kFull = 0xffffffffu;
+  const uint64_t b1 = (uint64_t)plo >> kBlockShift, b2 = (uint64_t)phi >> kBlockShift;
+  const int r1 = (int)(plo & (kBlockSyms - 1)), r2 = (int)(phi & (kBlockSyms - 1));
+  const uint4* pa = reinterpret_cast<const uint4*>(blocks + b1 * kGroup + q);
+  const uint4 a0 = __ldg(pa), a1 = __ldg(pa + 4);
+  uint4 c0 = a0, c1 = a1;
+  if (b2 != b1) {
+    const uint4* pb = reinterpret_cast<const uint4*>(blocks + b2 * kGroup + q);
+    c0 = __ldg(pb);
+    c1 = __ldg(pb + 4);
+  }
+  const uint32_t x0 = ((c - 1) & 1) ? 0u : 0xffffffffu, x1 = ((c - 1) & 2) ? 0u : 0xffffffffu;
+  uint32_t packed = fm_lane_sym_count(a0.x, a0.y, a0.z, q, r1, x0, x1) + fm_lane_sym_count(a1.x, a1.y, a1.z, q + 4, r1, x0, x1) +
+                    ((fm_lane_sym_count(c0.x, c0.y, c0.z, q, r2, x0, x1) + fm_lane_sym_count(c1.x, c1.y, c1.z, q + 4, r2, x0, x1)) << 16);
+  packed += __shfl_xor_sync(kFull, packed, 1);
+  packed += __shfl_xor_sync(kFull, packed, 2);
+  // header words of symbol c sit in lane c-1: .w of uint4 c-1 (low word) and of uint4 c+3 (high word)
+  const int src = qbase + c - 1;
+  const uint32_t hl1 = __shfl_sync(kFull, a0.w, src), hl2 = __shfl_sync(kFull, c0.w, src);
+  if (sizeof(IdxT) == 8) {
+    const uint32_t hh1 = __shfl_sync(kFull, a1.w, src), hh2 = __shfl_sync(kFull, c1.w, src);
+    Lc = (IdxT)(((uint64_t)hh1 << 32 | hl1) + (packed & 0xffffu));
+    Uc = (IdxT)(((uint64_t)hh2 << 32 | hl2) + (packed >> 16));
+  } else {
+    Lc = (IdxT)(hl1 + (packed & 0xffffu));
+    Uc = (IdxT)(hl2 + (packed >> 16));
+  }
+}
+
 }  // namespace sgx
 
 #endif  // SGX_QUAD_RANK_CUH_

@@ -70,6 +70,22 @@ void hemu_fm_free(void* p) { delete (HemuFm*)p; }
 
 uint64_t hemu_fm_length(void* p) { return ((HemuFm*)p)->view.n; }
 
+// getOcc(c, pos) for one symbol through fm_lane_sym_count (the per-lane arithmetic of quad_rank_sym): the eight lane
+// words of the block summed the way the four lanes of a quad sum them (lane q: words q and q + 4).
+uint64_t hemu_fm_occ_sym(void* p, uint64_t pos, int c) {
+  const FmView& fm = ((HemuFm*)p)->view;
+  const uint64_t pl = pos + 1;
+  if (pl == 0) return 0;
+  const FmBlockLane* blk = fm.blocks + (pl >> kBlockShift) * kGroup;
+  const int r = (int)(pl & (kBlockSyms - 1));
+  const uint32_t x0 = ((c - 1) & 1) ? 0u : 0xffffffffu, x1 = ((c - 1) & 2) ? 0u : 0xffffffffu;
+  uint32_t packed = 0;
+  for (int q = 0; q < 4; ++q)
+    packed += fm_lane_sym_count(blk[q].p0, blk[q].p1, blk[q].p2, q, r, x0, x1) +
+              fm_lane_sym_count(blk[q + 4].p0, blk[q + 4].p1, blk[q + 4].p2, q + 4, r, x0, x1);
+  return ((uint64_t)blk[c + 3].h << 32 | blk[c - 1].h) + packed;
+}
+
 void hemu_fm_occ(void* p, const uint64_t* pos, uint64_t n, uint64_t* counts) {
   HostGroup g;
   for (uint64_t i = 0; i < n; ++i) fm_occ(((HemuFm*)p)->view, pos[i], counts + 5 * i, g);
