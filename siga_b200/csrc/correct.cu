@@ -23,7 +23,9 @@ namespace sgx {
 template <class IdxT>
 struct DevCorrEng {
   const FmBlockLane* __restrict__ blocks;
-  IdxT pc1, pc2, pc3, pc4, pc5;  // C[] of the index by rank (pred[1..5]; pred[5] = n)
+  const uint64_t* pred;          // C[] of the index by rank (pred[5] = n): the kernel PARAMETER itself, so that pred[c] is
+                                 // one constant-bank load with a register index (selecting among five registers
+                                 // compiles to a branch tree)
   const uint32_t* seq;           // working sequence of this warp's read (shared memory)
   uint32_t k;
   IdxT low, high;                // the two support thresholds of the certificate searches (clamp_count)
@@ -36,7 +38,7 @@ struct DevCorrEng {
   __device__ __forceinline__ uint32_t lane_id() const { return (uint32_t)lane; }
   __device__ __forceinline__ uint32_t num_lanes() const { return 32u; }
   __device__ __forceinline__ void atomic_or(uint32_t* p, uint32_t m) const { atomicOr(p, m); }
-  __device__ __forceinline__ IdxT pcv(int c) const { return c == 1 ? pc1 : (c == 2 ? pc2 : (c == 3 ? pc3 : (c == 4 ? pc4 : pc5))); }
+  __device__ __forceinline__ IdxT pcv(int c) const { return (IdxT)pred[c]; }
 
   // One backward-search step of every quad of the warp: the interval [lo, lo + size) of the quad's string extended by
   // symbol c (FMIndex::Interval::update, src/fmindex.h:96-100; an empty interval is size 0, which is what the
@@ -45,11 +47,10 @@ struct DevCorrEng {
   __device__ __forceinline__ void step(bool active, int c, IdxT& lo, IdxT& size) {
     IdxT Lc, Uc;
     quad_rank_sym<IdxT>(blocks, active ? lo : (IdxT)0, active ? (IdxT)(lo + size) : (IdxT)0, q, qbase, c, Lc, Uc);
-    if (active) {
-      nlook += 2;
-      lo = pcv(c) + Lc;
-      size = Uc - Lc;
-    }
+    // branch-free: the kernel is bound by issue slots, and every divergent region costs a BSSY/BSYNC pair
+    nlook += active ? 2u : 0u;
+    lo = active ? (IdxT)(pcv(c) + Lc) : lo;
+    size = active ? (IdxT)(Uc - Lc) : size;
   }
   // Counts are compared in the position type: with 32-bit positions every count is below 2^32 - 1, so a larger
   // threshold behaves like 2^32 - 1 (never reached).
@@ -63,23 +64,19 @@ struct DevCorrEng {
     const unsigned kFull = 0xffffffffu;
     const KmerQuery kq = gen(slot);
     const IdxT need = clamp_count(kq.min_count);
-    uint32_t j = kq.kidx + k - 1;  // read position of the last k-mer symbol: the search starts there
-    int c = kq.have ? corr_query_sym(kq, seq, j) : 1;
+    uint32_t j = kq.have ? kq.kidx + k - 1 : 0u;  // read position of the last k-mer symbol: the search starts there
+    int c = corr_query_sym(kq, seq, j);
     IdxT lo = pcv(c), size = (IdxT)(pcv(c + 1) - lo);
     uint32_t steps = k - 1;
     // the interval only shrinks: the search can stop as soon as it is smaller than the count asked for
     bool live = kq.have && steps > 0 && size > 0 && size >= need;
 #pragma unroll 1
     while (__any_sync(kFull, live)) {
-      if (live) {
-        --j;
-        c = corr_query_sym(kq, seq, j);
-      }
+      j -= live ? 1u : 0u;  // a finished query keeps reading its last symbol (always a valid position)
+      c = corr_query_sym(kq, seq, j);
       step(live, c, lo, size);
-      if (live) {
-        --steps;
-        live = steps > 0 && size > 0 && size >= need;
-      }
+      steps -= live ? 1u : 0u;
+      live = live && steps > 0 && size > 0 && size >= need;
     }
     const unsigned b = __ballot_sync(kFull, kq.have && size >= need && q == 0);
     uint32_t out = 0;
@@ -94,29 +91,22 @@ struct DevCorrEng {
   __device__ __forceinline__ void windows(Gen gen, uint32_t* out) {
     const unsigned kFull = 0xffffffffu;
     const WinQuery wq = gen(slot);
-    uint32_t pos = wq.e, dl = kCorrNone, dh = kCorrNone;
+    uint32_t pos = wq.have ? wq.e : 0u, dl = kCorrNone, dh = kCorrNone;
     bool fl = false, fh = !two;
-    int c = wq.have ? read_rank(seq, pos) : 1;
+    int c = read_rank(seq, pos);
     IdxT lo = pcv(c), size = (IdxT)(pcv(c + 1) - lo);
     bool alive = wq.have;
 #pragma unroll 1
     for (;;) {
-      if (alive) {
-        if (!fl && size < low) {
-          dl = pos;
-          fl = true;
-        }
-        if (!fh && size < high) {
-          dh = pos;
-          fh = true;
-        }
-        if (size == 0 || (fl && fh) || pos == wq.a) alive = false;
-      }
+      const bool nl = alive && !fl && size < low, nh = alive && !fh && size < high;
+      dl = nl ? pos : dl;
+      dh = nh ? pos : dh;
+      fl = fl || nl;
+      fh = fh || nh;
+      alive = alive && size != 0 && !(fl && fh) && pos != wq.a;
       if (!__any_sync(kFull, alive)) break;
-      if (alive) {
-        --pos;
-        c = read_rank(seq, pos);
-      }
+      pos -= alive ? 1u : 0u;  // a finished search keeps reading its last symbol (always a valid position)
+      c = read_rank(seq, pos);
       step(alive, c, lo, size);
     }
     if (wq.have && q == 0) {
@@ -168,7 +158,7 @@ struct CorrCounters {
 
 template <class IdxT>
 __global__ void __launch_bounds__(256, 4)
-corr_kernel(FmView fm, ReadsView reads, uint64_t first, uint64_t count, const uint32_t* __restrict__ hq, uint64_t hbase,
+corr_kernel(const __grid_constant__ FmView fm, ReadsView reads, uint64_t first, uint64_t count, const uint32_t* __restrict__ hq, uint64_t hbase,
             CorrectParams P, uint32_t w16, uint32_t w32, uint8_t* __restrict__ valid, sgx_fix* __restrict__ fixes,
             CorrCounters* __restrict__ ctr) {
   extern __shared__ uint32_t corr_smem[];
@@ -187,11 +177,7 @@ corr_kernel(FmView fm, ReadsView reads, uint64_t first, uint64_t count, const ui
   st.dead = st.win + kCorrWinWords;
   DevCorrEng<IdxT> eng;
   eng.blocks = fm.blocks;
-  eng.pc1 = (IdxT)fm.pred[1];
-  eng.pc2 = (IdxT)fm.pred[2];
-  eng.pc3 = (IdxT)fm.pred[3];
-  eng.pc4 = (IdxT)fm.pred[4];
-  eng.pc5 = (IdxT)fm.pred[5];
+  eng.pred = fm.pred;
   eng.seq = st.seq;
   eng.k = P.k;
   eng.low = DevCorrEng<IdxT>::clamp_count(P.low);
