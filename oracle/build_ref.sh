@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # Oracle build recipe (test infrastructure only).
-# Compiles the reference's own `index` + `overlap` translation units IN PLACE from $SIGA_REF (default /root/reference)
+# Compiles the reference's own `index`, `overlap`, `rmdup`, `correct` and `assemble` translation units IN PLACE from $SIGA_REF (default /root/reference)
 # against the header shim in oracle/shim/ (Boost and log4cxx are not installed here) into oracle/_ref/siga.
 # No reference source is copied into this repo; only the binary lands in oracle/_ref/ (git-ignored, travels via gpurun).
 set -euo pipefail
