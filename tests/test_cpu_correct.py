@@ -41,10 +41,17 @@ def test_correction_logic_reproduces_reference_output(path):
     dict(seed=5, opt=dict(k=60, x=1, i=10, O=1)),               # k = read length: one k-mer per read
     dict(seed=6, opt=dict(k=19, x=2, i=0, O=1), both=True),     # no correction rounds at all
     dict(seed=7, opt=dict(k=15, x=-1, i=10, O=1)),              # negative threshold wraps to a huge size_t in the reference
+    # k > 64 and reads of more than 32 x 32 bases: multi-word shifts in the solid-base / quality dilation, word loops
+    dict(seed=31, opt=dict(k=100, x=3, i=10, O=1), fastq=True, n_reads=300, read_len=300, genome=2000, err=0.01),
+    dict(seed=33, opt=dict(k=70, x=2, i=5, O=1), fastq=True, variable=True, n_reads=250, read_len=400, genome=3000),
+    dict(seed=36, opt=dict(k=31, x=3, i=10, O=1), fastq=True, n_reads=150, read_len=1100, genome=4000, err=0.01),
+    # -x -1 with qualities: requiredSupport is 2^64 - 1 below the phred cut-off and 0 from it (every such k-mer "solid")
+    dict(seed=34, opt=dict(k=33, x=-1, i=10, O=1), fastq=True, n_reads=300, read_len=120, genome=1200, err=0.03),
+    dict(seed=35, opt=dict(k=32, x=0, i=10, O=0), fastq=True, n_reads=300, read_len=120, genome=1200, err=0.03),
 ], ids=lambda c: "seed%d_k%d" % (c["seed"], c["opt"]["k"]))
 def test_correction_logic_equals_reference_binary(case):
-    reads, quals = cc.random_case(case["seed"], fastq=case.get("fastq", False), variable=case.get("variable", False),
-                                  both=case.get("both", False))
+    kw = {k: v for k, v in case.items() if k not in ("seed", "opt")}
+    reads, quals = cc.random_case(case["seed"], **kw)
     runs, _, want = cc.reference_correct(reads, quals, case["opt"])
     got_reads, valid, _, _ = cc.hostemu_correct(_lib(), runs, reads, quals, case["opt"])
     assert cc.ec_text(got_reads, quals, valid) == want
