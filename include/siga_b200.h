@@ -285,6 +285,8 @@ typedef struct sgx_corrected {
  * parallel::foreach in CorrectProcessor::process (src/correct_processor.cpp:282-287).  qual / qual_off: the FASTQ quality
  * strings of exactly those reads in HOST memory, laid out like sgx_reads_pack's input (qual_off has count + 1
  * entries); both NULL for FASTA input (DNASeq::score then returns 15, src/kseq.h:34-40).
+ * SGX_EINVAL: kmer_size 0 (the reference asserts), a read longer than 32768 bases, a quality string whose length
+ * differs from its read's.  Reads shorter than kmer_size are dropped (valid = 0), as in the reference.
  */
 int sgx_correct_batch(sgx_ctx* ctx, const sgx_fm* fm, const sgx_reads* reads, uint64_t first, uint64_t count,
                       const char* qual, const uint64_t* qual_off, const sgx_correct_params* params, sgx_corrected* out);

@@ -302,20 +302,24 @@ void correct_run(sgx_ctx* ctx, const sgx_fm* fm, const sgx_reads* reads, uint64_
   DevBuf<uint8_t> d_valid(count);
   DevBuf<CorrCounters> d_ctr(1);
   SGX_CUDA(cudaMemsetAsync(d_ctr.p, 0, sizeof(CorrCounters), ctx->stream));
-  const size_t smem = 8 * corr_smem_words(w16, w32) * sizeof(uint32_t);
+  // one warp per read, up to 8 warps per block; long reads (33 KB of state per warp at 32768 bases) get fewer warps so
+  // that a block stays within the 227 KB of shared memory an SM can give one block
+  const size_t per_warp = corr_smem_words(w16, w32) * sizeof(uint32_t);
+  const unsigned warps = (unsigned)std::max<size_t>(1, std::min<size_t>(8, ((size_t)200 << 10) / per_warp));
+  const size_t smem = warps * per_warp;
   const char* fw = getenv("SGX_FORCE_WIDE");  // tests: exercise the 64-bit position path on small inputs
   const bool wide = fm->n >= 0xffffffffull || (fw && fw[0] == '1');
   if (smem > 48 * 1024) {
     if (wide) SGX_CUDA(cudaFuncSetAttribute(corr_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else SGX_CUDA(cudaFuncSetAttribute(corr_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  const unsigned grid = (unsigned)std::min<uint64_t>((count + 7) / 8, (uint64_t)ctx->sm_count * 4);
+  const unsigned grid = (unsigned)std::min<uint64_t>((count + warps - 1) / warps, (uint64_t)ctx->sm_count * 4 * (8 / warps));
   clk.tick();
   if (wide) {
-    SGX_LAUNCH(ctx, corr_kernel<uint64_t>, grid, 256, smem, fm->view(), reads->view(), first, count, (const uint32_t*)d_hq.p,
+    SGX_LAUNCH(ctx, corr_kernel<uint64_t>, grid, 32 * warps, smem, fm->view(), reads->view(), first, count, (const uint32_t*)d_hq.p,
                hbase, P, w16, w32, d_valid.p, d_fix.p, d_ctr.p);
   } else {
-    SGX_LAUNCH(ctx, corr_kernel<uint32_t>, grid, 256, smem, fm->view(), reads->view(), first, count, (const uint32_t*)d_hq.p,
+    SGX_LAUNCH(ctx, corr_kernel<uint32_t>, grid, 32 * warps, smem, fm->view(), reads->view(), first, count, (const uint32_t*)d_hq.p,
                hbase, P, w16, w32, d_valid.p, d_fix.p, d_ctr.p);
   }
   clk.tick();
