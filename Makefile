@@ -1,6 +1,7 @@
 # Build of the siga_b200 product library, the host CLI, the test-only host stand-in and the oracle.
 #   make            -> siga_b200/libsiga_b200.so + siga_b200/bin/siga
 #   make hostemu    -> build/libhostemu.so (tests only)
+#   make hostcli    -> build/siga_hostemu (tests only: the front-end sources linked against a host stand-in of the ABI)
 #   make oracle     -> oracle/liboracle.so (+ oracle/_ref/siga when /root/reference is present)
 NVCC      ?= /usr/local/cuda/bin/nvcc
 HOSTCXX   ?= /usr/bin/g++
@@ -34,10 +35,15 @@ build/libhostemu.so: tests/hostemu/hostemu.cpp $(HDR)
 	@mkdir -p build
 	$(HOSTCXX) -std=c++14 -O2 -Wall -Wextra -shared -fPIC $< -o $@
 
+hostcli: build/siga_hostemu
+build/siga_hostemu: tests/hostemu/sgx_stub.cpp tests/hostemu/hostemu.cpp $(wildcard $(CSRC)/host/*.cpp $(CSRC)/host/*.h) $(HDR)
+	@mkdir -p build
+	$(HOSTCXX) -std=c++17 -O2 -Wall -Wextra -Iinclude tests/hostemu/sgx_stub.cpp $(CSRC)/host/*.cpp -o $@ -lz -lpthread
+
 oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -rf build/obj $(LIB) siga_b200/bin build/libhostemu.so
+	rm -rf build/obj $(LIB) siga_b200/bin build/libhostemu.so build/siga_hostemu
 
-.PHONY: all cli hostemu oracle clean
+.PHONY: all cli hostemu hostcli oracle clean

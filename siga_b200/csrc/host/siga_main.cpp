@@ -759,21 +759,76 @@ int usage_correct() {
          "      -i, --kmer-rounds=N              perform up to N rounds of kmer correction (default: 10)\n"
          "      -O, --kmer-count-offset=N        when correcting a kmer, require the count of the new kmer is at least +N higher than the count of the old kmer. (default: 1)\n"
          "          --device=N                   CUDA device (default 0)\n"
+         "          --gpus=N                     correct on N GPUs (devices D .. D+N-1): reads sharded by contiguous range\n"
+         "          --gzip-level=N               zlib level of a .gz OUTFILE (default 1)\n"
          "\n");
   return 256;
+}
+
+// Text of the written reads of [first, first + count) in input order (PostCorrector, src/correct_processor.cpp:258-264;
+// record format: operator<<, src/kseq.cpp:106-125), produced on `threads` threads; plain file or gzip members.
+// valid[i - first] tells whether read i is written.
+bool write_corrected(const std::string& path, bool gz, int threads, int gzip_level, const ReadSet& rs, const uint8_t* valid,
+                     size_t first, size_t count) {
+  const bool fastq = !rs.quals.empty();
+  const size_t chunk = 1 << 16, n_chunks = (count + chunk - 1) / chunk;
+  auto produce = [&](size_t ci, std::string* text) {
+    const size_t b = first + ci * chunk, e = std::min(first + count, b + chunk);
+    text->reserve((e - b) * (fastq ? 400 : 200));
+    for (size_t i = b; i < e; ++i) {
+      if (!valid[i - first]) continue;
+      *text += fastq ? '@' : '>';
+      *text += rs.names[i];
+      if (!rs.comments[i].empty()) {
+        *text += ' ';
+        *text += rs.comments[i];
+      }
+      *text += '\n';
+      text->append(rs.bases, rs.off[i], rs.off[i + 1] - rs.off[i]);
+      *text += '\n';
+      if (fastq) {
+        *text += "+\n";
+        text->append(rs.quals, rs.off[i], rs.off[i + 1] - rs.off[i]);
+        *text += '\n';
+      }
+    }
+  };
+  if (threads < 1) threads = 1;
+  if (gz) {
+    GzChunkWriter w(path, (unsigned)threads, gzip_level);
+    return w.ok() && w.write_chunks(std::max<size_t>(n_chunks, 1), [&](size_t ci, std::string* text) {
+      if (ci < n_chunks) produce(ci, text);
+    });
+  }
+  FILE* f = fopen(path.c_str(), "wb");
+  bool good = f != nullptr;
+  for (size_t base = 0; base < n_chunks && good; base += (size_t)threads) {
+    const size_t m = std::min<size_t>((size_t)threads, n_chunks - base);
+    std::vector<std::string> text(m);
+    std::vector<std::thread> pool;
+    for (size_t t = 0; t < m; ++t) pool.emplace_back([&, t]() { produce(base + t, &text[t]); });
+    for (auto& th : pool) th.join();
+    for (size_t t = 0; t < m && good; ++t) good = fwrite(text[t].data(), 1, text[t].size(), f) == text[t].size();
+  }
+  if (f && fclose(f) != 0) good = false;
+  return good;
 }
 
 // `siga correct` (src/correct.cpp:22-59, CorrectProcessor::process src/correct_processor.cpp:269-316): loads PREFIX.bwt
 // only, corrects every read with sgx_correct_batch and writes, in input order, the reads that end all-solid
 // (PostCorrector, src/correct_processor.cpp:258-264) in the format of the input (operator<<, src/kseq.cpp:106-125).
+// --gpus N: reads are independent units; rank r corrects the contiguous read range r of N against its own copy of the
+// forward index (no collective) and writes the records of its range into a part file; the parent concatenates the
+// parts in rank order, which is input order.
 int cmd_correct(int argc, char** argv) {
-  enum { OPT_DEVICE = 1000 };
+  enum { OPT_DEVICE = 1000, OPT_GPUS, OPT_GZIP_LEVEL };
   static const option longopts[] = {{"log4cxx", required_argument, nullptr, 'c'},     {"ini", required_argument, nullptr, 's'},
                                     {"prefix", required_argument, nullptr, 'p'},      {"outfile", required_argument, nullptr, 'o'},
                                     {"threads", required_argument, nullptr, 't'},     {"algorithm", required_argument, nullptr, 'a'},
                                     {"kmer-size", required_argument, nullptr, 'k'},   {"kmer-threshold", required_argument, nullptr, 'x'},
                                     {"kmer-rounds", required_argument, nullptr, 'i'}, {"kmer-count-offset", required_argument, nullptr, 'O'},
-                                    {"device", required_argument, nullptr, OPT_DEVICE}, {"help", no_argument, nullptr, 'h'},
+                                    {"device", required_argument, nullptr, OPT_DEVICE}, {"gpus", required_argument, nullptr, OPT_GPUS},
+                                    {"gzip-level", required_argument, nullptr, OPT_GZIP_LEVEL}, {"help", no_argument, nullptr, 'h'},
                                     {nullptr, 0, nullptr, 0}};
   CommonOpts o;
   std::string outfile, algorithm = "kmer";
@@ -794,6 +849,8 @@ int cmd_correct(int argc, char** argv) {
       case 'i': prm.kmer_rounds = (uint32_t)std::min<unsigned long long>(strtoull(optarg, nullptr, 10), 0xffffffffull); break;
       case 'O': prm.kmer_count_offset = strtoull(optarg, nullptr, 10); break;
       case OPT_DEVICE: o.device = atoi(optarg); break;
+      case OPT_GPUS: o.gpus = std::max(1, std::min(16, atoi(optarg))); break;
+      case OPT_GZIP_LEVEL: o.gzip_level = std::max(1, std::min(9, atoi(optarg))); break;
       case 'h': o.help = true; break;
       default: break;
     }
@@ -809,8 +866,14 @@ int cmd_correct(int argc, char** argv) {
   if (outfile.empty()) outfile = st + ".ec.fa";
   const std::string prefix = o.prefix.empty() ? st : o.prefix;
   info("input: %s", input.c_str());
+  if (outfile.size() > 4 && outfile.compare(outfile.size() - 4, 4, ".bz2") == 0) {
+    fprintf(stderr, "ERROR siga - Failed to create DNASeqWriter %s (bzip2 output is not supported by this build)\n", outfile.c_str());
+    return -1;
+  }
+  const bool gz = outfile.size() > 3 && outfile.compare(outfile.size() - 3, 3, ".gz") == 0;
   const double t0 = now_s();
   if (o.threads <= 0) o.threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  const int world = o.gpus;
 
   ReadSet rs;
   rs.keep_quals = true;
@@ -822,7 +885,7 @@ int cmd_correct(int argc, char** argv) {
   bool ok_bwt = false, ok_reads = false;
   {
     std::vector<std::thread> pool;
-    pool.emplace_back([&]() { ctx_rc = sgx_init(o.device, &ctx); });
+    if (world == 1) pool.emplace_back([&]() { ctx_rc = sgx_init(o.device, &ctx); });  // no CUDA call before a fork
     pool.emplace_back([&]() { ok_bwt = read_bwt(prefix + ".bwt", &ns, &nf, &runs); });
     pool.emplace_back([&]() { ok_reads = read_sequences(input, &rs, &err); });
     for (auto& t : pool) t.join();
@@ -835,81 +898,81 @@ int cmd_correct(int argc, char** argv) {
     fprintf(stderr, "ERROR siga - %s\n", err.c_str());
     return -1;
   }
-  if (ctx_rc != SGX_OK) return fail(nullptr, "sgx_init", ctx_rc);
+  int my = 0;
+  std::vector<pid_t> kids;
+  if (world > 1) {
+    fflush(nullptr);
+    for (int r = 1; r < world && my == 0; ++r) {
+      const pid_t pid = fork();
+      if (pid < 0) {
+        fprintf(stderr, "ERROR siga - fork failed\n");
+        return -1;
+      }
+      if (pid == 0) my = r;
+      else kids.push_back(pid);
+    }
+    ctx_rc = sgx_init(o.device + my, &ctx);
+    o.threads = std::max(1, o.threads / world);
+  }
+  // a failing rank of a multi-GPU run leaves through _exit so that the parent sees a non-zero status
+  auto bail = [&](const char* what, int rc) {
+    fail(ctx_rc == SGX_OK ? ctx : nullptr, what, rc);
+    if (my) _exit(1);
+    return -1;
+  };
+  if (ctx_rc != SGX_OK) return bail("sgx_init", ctx_rc);
   const bool fastq = !rs.quals.empty();
   const double t_load = now_s();
+  const uint64_t first = rs.size() * (uint64_t)my / world, count = rs.size() * (uint64_t)(my + 1) / world - first;
   sgx_corrected res;
   memset(&res, 0, sizeof(res));
   sgx_reads* reads = nullptr;
   sgx_fm* fm = nullptr;
   int rc = SGX_OK;
-  if (rs.size() > 0) {
-    if ((rc = sgx_reads_pack(ctx, rs.bases.data(), rs.off.data(), rs.size(), &reads)) != SGX_OK) return fail(ctx, "sgx_reads_pack", rc);
-    if ((rc = sgx_fm_create(ctx, runs.data(), runs.size(), nf, &fm)) != SGX_OK) return fail(ctx, "sgx_fm_create", rc);
-    rc = sgx_correct_batch(ctx, fm, reads, 0, rs.size(), fastq ? rs.quals.data() : nullptr, fastq ? rs.off.data() : nullptr, &prm, &res);
-    if (rc != SGX_OK) return fail(ctx, "sgx_correct_batch", rc);
-    info("processed %zu sequences; device %.1f ms (kernel %.1f ms, %.0f rank lookups per read), %llu bases fixed in %llu reads",
-         rs.size(), res.ms_total, res.ms_kernel, (double)res.lookups / (double)rs.size(), (unsigned long long)res.n_fixes,
+  if (count > 0) {
+    // only this rank's range goes to the device (offsets need not start at zero)
+    if ((rc = sgx_reads_pack(ctx, rs.bases.data(), rs.off.data() + first, count, &reads)) != SGX_OK) return bail("sgx_reads_pack", rc);
+    if ((rc = sgx_fm_create(ctx, runs.data(), runs.size(), nf, &fm)) != SGX_OK) return bail("sgx_fm_create", rc);
+    rc = sgx_correct_batch(ctx, fm, reads, 0, count, fastq ? rs.quals.data() : nullptr, fastq ? rs.off.data() + first : nullptr, &prm, &res);
+    if (rc != SGX_OK) return bail("sgx_correct_batch", rc);
+    info("processed %llu sequences; device %.1f ms (kernel %.1f ms, %.0f rank lookups per read), %llu bases fixed in %llu reads",
+         (unsigned long long)count, res.ms_total, res.ms_kernel, (double)res.lookups / (double)count, (unsigned long long)res.n_fixes,
          (unsigned long long)res.fixed_reads);
     for (uint64_t k = 0; k < res.n_fixes; ++k)
-      rs.bases[rs.off[res.fixes[k].read] + (res.fixes[k].pos_code >> 2)] = "ACGT"[res.fixes[k].pos_code & 3];
+      rs.bases[rs.off[first + res.fixes[k].read] + (res.fixes[k].pos_code >> 2)] = "ACGT"[res.fixes[k].pos_code & 3];
   }
   const double t_gpu = now_s();
 
-  // output: the written reads in input order, text produced on all threads
-  const size_t n = rs.size(), chunk = 1 << 16, n_chunks = (n + chunk - 1) / chunk;
-  auto produce = [&](size_t ci, std::string* text) {
-    const size_t b = ci * chunk, e = std::min(n, b + chunk);
-    text->reserve((e - b) * (fastq ? 400 : 200));
-    for (size_t i = b; i < e; ++i) {
-      if (!res.valid[i]) continue;
-      *text += fastq ? '@' : '>';
-      *text += rs.names[i];
-      if (!rs.comments[i].empty()) {
-        *text += ' ';
-        *text += rs.comments[i];
-      }
-      *text += '\n';
-      text->append(rs.bases, rs.off[i], rs.off[i + 1] - rs.off[i]);
-      *text += '\n';
-      if (fastq) {
-        *text += "+\n";
-        text->append(rs.quals, rs.off[i], rs.off[i + 1] - rs.off[i]);
-        *text += '\n';
-      }
-    }
-  };
-  bool good = true;
-  const bool gz = outfile.size() > 3 && outfile.compare(outfile.size() - 3, 3, ".gz") == 0;
-  if (outfile.size() > 4 && outfile.compare(outfile.size() - 4, 4, ".bz2") == 0) {
-    fprintf(stderr, "ERROR siga - Failed to create DNASeqWriter %s (bzip2 output is not supported by this build)\n", outfile.c_str());
-    return -1;
-  }
-  if (gz) {
-    GzChunkWriter w(outfile, (unsigned)o.threads, o.gzip_level);
-    good = w.ok() && w.write_chunks(std::max<size_t>(n_chunks, 1), [&](size_t ci, std::string* text) {
-      if (ci < n_chunks) produce(ci, text);
-    });
+  bool good;
+  if (world == 1) {
+    good = write_corrected(outfile, gz, o.threads, o.gzip_level, rs, res.valid, 0, rs.size());
   } else {
-    FILE* f = fopen(outfile.c_str(), "wb");
-    good = f != nullptr;
-    for (size_t base = 0; base < n_chunks && good; base += (size_t)o.threads) {
-      const size_t m = std::min<size_t>((size_t)o.threads, n_chunks - base);
-      std::vector<std::string> text(m);
-      std::vector<std::thread> pool;
-      for (size_t t = 0; t < m; ++t) pool.emplace_back([&, t]() { produce(base + t, &text[t]); });
-      for (auto& th : pool) th.join();
-      for (size_t t = 0; t < m && good; ++t) good = fwrite(text[t].data(), 1, text[t].size(), f) == text[t].size();
+    good = write_corrected(outfile + ".part" + std::to_string(my), gz, o.threads, o.gzip_level, rs, res.valid, first, count);
+    if (my) {
+      sgx_corrected_free(&res);
+      sgx_shutdown(ctx);
+      _exit(good ? 0 : 1);
     }
-    if (f && fclose(f) != 0) good = false;
+    for (pid_t pid : kids) {
+      int stt = 0;
+      if (waitpid(pid, &stt, 0) < 0 || !WIFEXITED(stt) || WEXITSTATUS(stt) != 0) good = false;
+    }
+    if (good) {
+      FILE* f = fopen(outfile.c_str(), "wb");
+      good = f != nullptr;
+      for (int r = 0; r < world && good; ++r) good = append_file(f, outfile + ".part" + std::to_string(r));
+      if (f && fclose(f) != 0) good = false;
+    }
+    for (int r = 0; r < world; ++r) remove((outfile + ".part" + std::to_string(r)).c_str());
   }
   if (!good) {
     fprintf(stderr, "ERROR siga - Failed to create DNASeqWriter %s\n", outfile.c_str());
     return -1;
   }
   uint64_t written = 0;
-  for (size_t i = 0; i < n; ++i) written += res.valid[i] ? 1 : 0;
-  info("%llu of %zu reads written to %s", (unsigned long long)written, n, outfile.c_str());
+  for (size_t i = 0; i < count; ++i) written += res.valid[i] ? 1 : 0;
+  info("%llu of %llu reads%s written to %s", (unsigned long long)written, (unsigned long long)count,
+       world > 1 ? " of rank 0's range" : "", outfile.c_str());
   sgx_corrected_free(&res);
   sgx_fm_free(fm);
   sgx_reads_free(reads);

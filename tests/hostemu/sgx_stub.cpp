@@ -1,0 +1,161 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into, loaded by, or shipped with the product (siga_b200/libsiga_b200.so,
+// siga_b200/bin/siga have no CPU path and fail without a B200).
+//
+// A host stand-in for the part of the C ABI (include/siga_b200.h) that `siga correct` and `siga rmdup` call, built on the
+// single-lane instantiations in hostemu.cpp.  Linked with the UNMODIFIED front-end sources
+// (siga_b200/csrc/host/siga_main.cpp, seqio.cpp) into build/siga_hostemu, it lets the CPU test-suite run the
+// front-end's own host logic -- option parsing, FASTQ qualities, fix application, output formatting, the fork / part
+// file / concatenation path of --gpus N -- against the reference binary without a GPU.  Index construction and the
+// edge pipeline of `siga overlap` have no host stand-in: those entry points return SGX_ENODEV here.
+#include "hostemu.cpp"
+
+#include <string>
+
+struct sgx_ctx {
+  std::string err;
+};
+struct sgx_reads {
+  std::string ascii;
+  std::vector<uint64_t> off;  // rebased to 0
+};
+struct sgx_fm {
+  void* fm;
+};
+struct sgx_comm {
+  int unused;
+};
+
+namespace {
+int no_device(sgx_ctx* ctx, const char* what) {
+  if (ctx) ctx->err = std::string(what) + ": not available in the host stand-in (needs a B200)";
+  return SGX_ENODEV;
+}
+}  // namespace
+
+extern "C" {
+
+int sgx_init(int device, sgx_ctx** out) {
+  (void)device;
+  *out = new sgx_ctx();
+  return SGX_OK;
+}
+void sgx_shutdown(sgx_ctx* ctx) { delete ctx; }
+const char* sgx_last_error(const sgx_ctx* ctx) { return ctx ? ctx->err.c_str() : ""; }
+
+int sgx_reads_pack(sgx_ctx* ctx, const char* ascii, const uint64_t* off, uint64_t n, sgx_reads** out) {
+  if (!ctx || !ascii || !off || n == 0) return SGX_EINVAL;
+  sgx_reads* r = new sgx_reads();
+  r->ascii.assign(ascii + off[0], off[n] - off[0]);
+  r->off.resize(n + 1);
+  for (uint64_t i = 0; i <= n; ++i) r->off[i] = off[i] - off[0];
+  for (char ch : r->ascii)
+    if (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T') {
+      ctx->err = "sgx_reads_pack: base other than A/C/G/T";
+      delete r;
+      return SGX_EINVAL;
+    }
+  *out = r;
+  return SGX_OK;
+}
+void sgx_reads_free(sgx_reads* r) { delete r; }
+
+int sgx_fm_create(sgx_ctx* ctx, const uint8_t* rle, uint64_t n_runs, uint64_t n_suffixes, sgx_fm** out) {
+  (void)ctx;
+  sgx_fm* f = new sgx_fm();
+  f->fm = hemu_fm_from_rle(rle, n_runs);
+  if (hemu_fm_length(f->fm) != n_suffixes) {
+    hemu_fm_free(f->fm);
+    delete f;
+    return SGX_EINVAL;
+  }
+  *out = f;
+  return SGX_OK;
+}
+void sgx_fm_free(sgx_fm* f) {
+  if (!f) return;
+  hemu_fm_free(f->fm);
+  delete f;
+}
+int sgx_fm_attach_reads(sgx_ctx*, sgx_fm*, const uint32_t*, uint64_t, const sgx_reads*) { return SGX_OK; }
+
+int sgx_correct_batch(sgx_ctx* ctx, const sgx_fm* fm, const sgx_reads* reads, uint64_t first, uint64_t count, const char* qual,
+                      const uint64_t* qual_off, const sgx_correct_params* prm, sgx_corrected* out) {
+  if (!ctx || !fm || !reads || !prm || !out || first + count > reads->off.size() - 1) return SGX_EINVAL;
+  memset(out, 0, sizeof(*out));
+  out->n_reads = count;
+  out->valid = (uint8_t*)calloc(count ? count : 1, 1);
+  std::vector<uint64_t> off(count + 1);
+  for (uint64_t i = 0; i <= count; ++i) off[i] = reads->off[first + i] - reads->off[first];
+  const char* in = reads->ascii.data() + reads->off[first];
+  std::string q;
+  if (qual) {
+    for (uint64_t i = 0; i < count; ++i)
+      if (qual_off[i + 1] - qual_off[i] != off[i + 1] - off[i]) {
+        ctx->err = "sgx_correct_batch: a quality string differs in length from its read";
+        free(out->valid);
+        out->valid = nullptr;
+        return SGX_EINVAL;
+      }
+    q.assign(qual + qual_off[0], qual_off[count] - qual_off[0]);
+  }
+  std::string fixed(off[count], '\0');
+  std::vector<uint32_t> nfix(count ? count : 1);
+  uint64_t lookups = 0;
+  const int rc = count ? hemu_correct(fm->fm, in, qual ? q.data() : nullptr, off.data(), count, prm->kmer_size, prm->kmer_threshold,
+                                      prm->kmer_rounds, prm->kmer_count_offset, &fixed[0], out->valid, nfix.data(), &lookups)
+                       : SGX_OK;
+  if (rc != SGX_OK) {
+    free(out->valid);
+    out->valid = nullptr;
+    return rc;
+  }
+  std::vector<sgx_fix> fixes;
+  for (uint64_t i = 0; i < count; ++i) {
+    if (!out->valid[i]) continue;
+    bool any = false;
+    for (uint64_t j = off[i]; j < off[i + 1]; ++j)
+      if (fixed[j] != in[j]) {
+        uint32_t code = fixed[j] == 'A' ? 0 : (fixed[j] == 'C' ? 1 : (fixed[j] == 'G' ? 2 : 3));
+        fixes.push_back(sgx_fix{(uint32_t)i, (uint32_t)((j - off[i]) << 2) | code});
+        any = true;
+      }
+    out->fixed_reads += any ? 1 : 0;
+  }
+  out->n_fixes = fixes.size();
+  out->fixes = (sgx_fix*)malloc((fixes.size() ? fixes.size() : 1) * sizeof(sgx_fix));
+  if (!fixes.empty()) memcpy(out->fixes, fixes.data(), fixes.size() * sizeof(sgx_fix));
+  out->lookups = lookups;
+  return SGX_OK;
+}
+void sgx_corrected_free(sgx_corrected* out) {
+  if (!out) return;
+  free(out->valid);
+  free(out->fixes);
+  out->valid = nullptr;
+  out->fixes = nullptr;
+}
+
+// `siga rmdup`: hit blocks of a read range through overlap_logic.h on the host lane
+int sgx_overlap_batch(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const sgx_reads* reads, uint64_t first, uint64_t count,
+                      uint32_t min_overlap, int irreducible, int rc, sgx_hits* out) {
+  if (!ctx || !fwd || !rev || !reads || !out || first + count > reads->off.size() - 1) return SGX_EINVAL;
+  return hemu_overlap(fwd->fm, rev->fm, reads->ascii.data(), reads->off.data() + first, count, min_overlap, irreducible, rc, out);
+}
+void sgx_hits_free(sgx_hits* h) { hemu_hits_free(h); }
+
+// ---- no host stand-in
+int sgx_index_build(sgx_ctx* ctx, const sgx_reads*, int, int, sgx_index_out*) { return no_device(ctx, "sgx_index_build"); }
+void sgx_index_out_free(sgx_index_out*) {}
+int sgx_comm_unique_id(uint8_t*) { return SGX_ENODEV; }
+int sgx_comm_init(sgx_ctx* ctx, const uint8_t*, int, int, sgx_comm**) { return no_device(ctx, "sgx_comm_init"); }
+void sgx_comm_free(sgx_comm*) {}
+int sgx_index_build_sharded(sgx_ctx* ctx, sgx_comm*, const sgx_reads*, int, int, sgx_index_out*) {
+  return no_device(ctx, "sgx_index_build_sharded");
+}
+int sgx_overlap_edges(sgx_ctx* ctx, const sgx_fm*, const sgx_fm*, const sgx_reads*, uint64_t, uint64_t, uint32_t, int, int,
+                      const uint32_t*, sgx_edges*) {
+  return no_device(ctx, "sgx_overlap_edges");
+}
+void sgx_edges_free(sgx_edges*) {}
+
+}  // extern "C"

@@ -1,0 +1,89 @@
+"""CPU tests of the `siga` front-end's host logic: the UNMODIFIED front-end sources (siga_b200/csrc/host) linked against
+a host stand-in of the C ABI (tests/hostemu/sgx_stub.cpp -> build/siga_hostemu, test infrastructure only) and run against
+the compiled reference.  Covers what no kernel test sees: option parsing, FASTQ qualities and comments, fix application,
+output formatting and compression, and the N > 1 path of `siga correct --gpus N` (fork, per-rank read ranges, part
+files concatenated in rank order) on CPU processes."""
+import gzip
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import correct_common as cc
+import refrun
+from siga_b200 import synth
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(REPO, "build", "siga_hostemu")
+
+pytestmark = [pytest.mark.skipif(not os.path.isfile(CLI), reason="build/siga_hostemu not built (make hostcli)"),
+              pytest.mark.skipif(not refrun.have_ref(), reason="compiled reference (oracle/_ref/siga) not present")]
+
+
+def _cli(args, cwd, ok=True):
+    r = subprocess.run([CLI] + args, cwd=cwd, capture_output=True, text=True)
+    assert (r.returncode == 0) == ok, r.stderr[-2000:]
+    return r
+
+
+@pytest.mark.parametrize("fastq", [False, True], ids=["fasta", "fastq"])
+def test_correct_front_end_single_and_sharded_equal_reference_file(fastq):
+    reads, quals = cc.random_case(21 + int(fastq), n_reads=2001, read_len=75, genome=4000, err=0.015, fastq=fastq, both=True)
+    names = ["q%d%s" % (i, " CR:i:%d note" % (i % 5) if i % 3 == 0 else "") for i in range(len(reads))]
+    with tempfile.TemporaryDirectory() as d:
+        ours, ref = os.path.join(d, "ours"), os.path.join(d, "ref")
+        os.mkdir(ours)
+        os.mkdir(ref)
+        src = os.path.join(d, "reads.fq" if fastq else "reads.fa")
+        cc.write_reads(src, reads, quals, names)
+        refrun.run_ref(["index", "--no-reverse", src], ref)
+        refrun.run_ref(["correct", "-t", "3", "-k", "23", "-x", "2", "-i", "4", "-O", "2", src], ref)
+        want = open(os.path.join(ref, "reads.ec.fa"), "rb").read()
+        assert 0 < want.count(b"\n") // (4 if fastq else 2) < len(reads)
+        opts = ["-k", "23", "-x", "2", "-i", "4", "-O", "2", "-p", os.path.join(ref, "reads")]
+        for extra, out in (([], "reads.ec.fa"), (["--gpus", "2"], "reads.ec.fa"), (["--gpus", "3", "-o", "x.fa.gz"], "x.fa.gz"),
+                           (["--kmer-size=23", "--outfile", "y.fa"], "y.fa")):
+            _cli(["correct"] + opts + extra + [src], ours)
+            path = os.path.join(ours, out)
+            got = gzip.open(path, "rb").read() if out.endswith(".gz") else open(path, "rb").read()
+            assert got == want, extra
+            os.remove(path)
+            assert not [f for f in os.listdir(ours) if ".part" in f]
+        # errors: unknown algorithm, missing index, bzip2 output, a base other than A/C/G/T
+        _cli(["correct", "-a", "overlap"] + opts + [src], ours, ok=False)
+        _cli(["correct", "-p", "missing", src], ours, ok=False)
+        _cli(["correct", "-o", "z.fa.bz2"] + opts + [src], ours, ok=False)
+        bad = os.path.join(d, "bad.fa")
+        open(bad, "w").write(">a\nACGTNACGTACGTACGTACGTACGTACGT\n")
+        _cli(["correct"] + opts + [bad], ours, ok=False)
+
+
+def _fasta_records(path):
+    recs = open(path, "rb").read().split(b">")[1:]
+    return sorted(recs)
+
+
+def test_rmdup_front_end_equals_reference_records():
+    """`siga rmdup` host logic (NumDuplicates, the kept / removed split by name order) on hit blocks from the host lane."""
+    rng = np.random.default_rng(23)
+    g = synth.random_genome(1500, rng)
+    reads = [r.tobytes() for r in synth.sample_reads(g, 350, 40, rng, err=0.0)]
+    for _ in range(50):
+        a, b = rng.integers(0, len(reads), 2)
+        reads[a] = reads[b] if rng.random() < 0.5 else synth.revcomp(np.frombuffer(reads[b], dtype=np.uint8)).tobytes()
+    with tempfile.TemporaryDirectory() as d:
+        ours, ref = os.path.join(d, "ours"), os.path.join(d, "ref")
+        os.mkdir(ours)
+        os.mkdir(ref)
+        src = os.path.join(d, "reads.fa")
+        synth.write_fasta(src, reads)
+        refrun.run_ref(["index", src], ref)
+        refrun.run_ref(["rmdup", "-t", "3", src], ref)
+        for ext in (".bwt", ".rbwt", ".sai", ".rsai"):  # the front-end reads the reference's index files
+            os.symlink(os.path.join(ref, "reads" + ext), os.path.join(ours, "reads" + ext))
+        _cli(["rmdup", src], ours)
+        for f in ("reads.rmdup.fa", "reads.rmdup.dups.fa"):
+            assert _fasta_records(os.path.join(ours, f)) == _fasta_records(os.path.join(ref, f)), f
+        assert len(_fasta_records(os.path.join(ours, "reads.rmdup.dups.fa"))) > 10

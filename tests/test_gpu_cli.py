@@ -170,8 +170,9 @@ def _gpu_count():
 @pytest.mark.skipif(not os.path.isfile(CLI), reason="siga_b200/bin/siga not built")
 @pytest.mark.skipif(_gpu_count() < 2, reason="needs two GPUs (run under gpurun --gpus 2)")
 def test_cli_multi_gpu_outputs_equal_single_gpu():
-    """`siga index --gpus 2` (NCCL, rows sharded by k-mer bucket) and `siga overlap --gpus 2` (reads sharded, part files
-    concatenated) write the same index bytes, the same HT/VT lines and the same ED set as the one-GPU commands."""
+    """`siga index --gpus 2` (NCCL, rows sharded by k-mer bucket), `siga overlap --gpus 2` and `siga correct --gpus 2`
+    (reads sharded, part files concatenated) write the same index bytes, the same HT/VT lines, the same ED set and the
+    same corrected reads as the one-GPU commands."""
     rng = np.random.default_rng(5)
     g = synth.random_genome(20_000, rng)
     reads = synth.sample_reads(g, 9_001, 80, rng, err=0.01)
@@ -191,4 +192,9 @@ def test_cli_multi_gpu_outputs_equal_single_gpu():
         n = len(reads)
         assert a[:1 + n] == b[:1 + n]
         assert sorted(a[1 + n:]) == sorted(b[1 + n:]) and len(a) > 1 + n
+        # `siga correct --gpus 2`: reads sharded by contiguous range, part files concatenated in rank order
+        _run(["correct", "-k", "25", src], one)
+        _run(["correct", "-k", "25", "--gpus", "2", src], two)
+        ec = open(os.path.join(one, "reads.ec.fa"), "rb").read()
+        assert ec == open(os.path.join(two, "reads.ec.fa"), "rb").read() and ec.count(b">") > 1000
         assert not [f for f in os.listdir(two) if ".part" in f]
