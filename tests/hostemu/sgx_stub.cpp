@@ -1,12 +1,12 @@
 // TEST INFRASTRUCTURE ONLY -- never linked into, loaded by, or shipped with the product (siga_b200/libsiga_b200.so,
 // siga_b200/bin/siga have no CPU path and fail without a B200).
 //
-// A host stand-in for the part of the C ABI (include/siga_b200.h) that `siga correct` and `siga rmdup` call, built on the
+// A host stand-in for the part of the C ABI (include/siga_b200.h) that `siga overlap`, `siga rmdup` and `siga correct` call, built on the
 // single-lane instantiations in hostemu.cpp.  Linked with the UNMODIFIED front-end sources
 // (siga_b200/csrc/host/siga_main.cpp, seqio.cpp) into build/siga_hostemu, it lets the CPU test-suite run the
-// front-end's own host logic -- option parsing, FASTQ qualities, fix application, output formatting, the fork / part
-// file / concatenation path of --gpus N -- against the reference binary without a GPU.  Index construction and the
-// edge pipeline of `siga overlap` have no host stand-in: those entry points return SGX_ENODEV here.
+// front-end's own host logic -- option parsing, FASTQ qualities, fix application, ASQG / FASTA formatting, the fork /
+// part file / concatenation path of --gpus N -- against the reference binary without a GPU.  Index construction has no
+// host stand-in: those entry points return SGX_ENODEV here.
 #include "hostemu.cpp"
 
 #include <string>
@@ -20,6 +20,7 @@ struct sgx_reads {
 };
 struct sgx_fm {
   void* fm;
+  std::vector<uint32_t> sai;  // sgx_fm_attach_reads
 };
 struct sgx_comm {
   int unused;
@@ -76,7 +77,10 @@ void sgx_fm_free(sgx_fm* f) {
   hemu_fm_free(f->fm);
   delete f;
 }
-int sgx_fm_attach_reads(sgx_ctx*, sgx_fm*, const uint32_t*, uint64_t, const sgx_reads*) { return SGX_OK; }
+int sgx_fm_attach_reads(sgx_ctx*, sgx_fm* f, const uint32_t* sai, uint64_t n, const sgx_reads*) {
+  f->sai.assign(sai, sai + n);
+  return SGX_OK;
+}
 
 int sgx_correct_batch(sgx_ctx* ctx, const sgx_fm* fm, const sgx_reads* reads, uint64_t first, uint64_t count, const char* qual,
                       const uint64_t* qual_off, const sgx_correct_params* prm, sgx_corrected* out) {
@@ -143,6 +147,51 @@ int sgx_overlap_batch(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const 
 }
 void sgx_hits_free(sgx_hits* h) { hemu_hits_free(h); }
 
+// `siga overlap`: the same blocks turned into edge records by Hit2OverlapConverter::convert + OverlapBlock::overlap
+// (src/overlap_builder.cpp:158-175, 345-375), restated for the host (the product does this in ov_edges_kernel /
+// ov_reduce_kernel on the device)
+int sgx_overlap_edges(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const sgx_reads* reads, uint64_t first, uint64_t count,
+                      uint32_t min_overlap, int irreducible, int rc, const uint32_t* name_rank, sgx_edges* out) {
+  if (!ctx || !fwd || !rev || !reads || !name_rank || !out || first + count > reads->off.size() - 1) return SGX_EINVAL;
+  if (fwd->sai.size() != reads->off.size() - 1 || rev->sai.size() != reads->off.size() - 1) return SGX_EINVAL;
+  sgx_hits h;
+  const int st = hemu_overlap(fwd->fm, rev->fm, reads->ascii.data(), reads->off.data() + first, count, min_overlap, irreducible, rc, &h);
+  if (st != SGX_OK) return st;
+  std::vector<sgx_edge> edges;
+  for (uint64_t k = 0; k < count; ++k) {
+    const uint64_t q = first + k, lq = reads->off[q + 1] - reads->off[q];
+    for (uint64_t b = h.block_off[k]; b < h.block_off[k + 1]; ++b) {
+      const sgx_block& blk = h.blocks[b];
+      const std::vector<uint32_t>& sa = (blk.af & SGX_AF_TARGETREV) ? rev->sai : fwd->sai;
+      for (uint64_t j = blk.capped[0]; j <= blk.capped[1]; ++j) {
+        const uint32_t t = sa[j];
+        const uint64_t lt = reads->off[t + 1] - reads->off[t];
+        if (name_rank[q] == name_rank[t]) continue;  // same name: a self hit
+        const bool contained = blk.length == lq || blk.length == lt;
+        if (name_rank[q] < name_rank[t] || (contained && (blk.af & SGX_AF_QUERYREV))) continue;
+        edges.push_back(sgx_edge{(uint32_t)q, t, blk.length, blk.af});
+      }
+    }
+  }
+  memset(out, 0, sizeof(*out));
+  out->n_reads = count;
+  out->substring = (uint8_t*)malloc(count ? count : 1);
+  memcpy(out->substring, h.substring, count);
+  out->n_edges = edges.size();
+  out->edges = (sgx_edge*)malloc((edges.size() ? edges.size() : 1) * sizeof(sgx_edge));
+  if (!edges.empty()) memcpy(out->edges, edges.data(), edges.size() * sizeof(sgx_edge));
+  out->n_blocks = h.n_blocks;
+  hemu_hits_free(&h);
+  return SGX_OK;
+}
+void sgx_edges_free(sgx_edges* e) {
+  if (!e) return;
+  free(e->substring);
+  free(e->edges);
+  e->substring = nullptr;
+  e->edges = nullptr;
+}
+
 // ---- no host stand-in
 int sgx_index_build(sgx_ctx* ctx, const sgx_reads*, int, int, sgx_index_out*) { return no_device(ctx, "sgx_index_build"); }
 void sgx_index_out_free(sgx_index_out*) {}
@@ -152,10 +201,5 @@ void sgx_comm_free(sgx_comm*) {}
 int sgx_index_build_sharded(sgx_ctx* ctx, sgx_comm*, const sgx_reads*, int, int, sgx_index_out*) {
   return no_device(ctx, "sgx_index_build_sharded");
 }
-int sgx_overlap_edges(sgx_ctx* ctx, const sgx_fm*, const sgx_fm*, const sgx_reads*, uint64_t, uint64_t, uint32_t, int, int,
-                      const uint32_t*, sgx_edges*) {
-  return no_device(ctx, "sgx_overlap_edges");
-}
-void sgx_edges_free(sgx_edges*) {}
 
 }  // extern "C"

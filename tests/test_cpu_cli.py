@@ -87,3 +87,45 @@ def test_rmdup_front_end_equals_reference_records():
         for f in ("reads.rmdup.fa", "reads.rmdup.dups.fa"):
             assert _fasta_records(os.path.join(ours, f)) == _fasta_records(os.path.join(ref, f)), f
         assert len(_fasta_records(os.path.join(ours, "reads.rmdup.dups.fa"))) > 10
+
+
+def _asqg(path):
+    with gzip.open(path, "rt") as f:
+        return [l.rstrip("\n") for l in f]
+
+
+@pytest.mark.parametrize("case", ["fasta", "fastq_comments_exhaustive_norc"])
+def test_overlap_front_end_single_and_sharded_equal_reference_asqg(case):
+    """`siga overlap` host logic: index / read loading, name ranks, the ASQG writer (HT, VT in input order with SS / CR /
+    BX tags, ED) and the --gpus N path (fork, read ranges, .vt / .ed part files concatenated)."""
+    rng = np.random.default_rng(17)
+    g = synth.random_genome(2500, rng)
+    reads = synth.sample_reads(g, 901, 50, rng, err=0.01)
+    reads[rng.integers(0, 901, 30)] = reads[rng.integers(0, 901, 30)]
+    with tempfile.TemporaryDirectory() as d:
+        ours, ref = os.path.join(d, "ours"), os.path.join(d, "ref")
+        os.mkdir(ours)
+        os.mkdir(ref)
+        if case == "fasta":
+            src = os.path.join(d, "reads.fa")
+            synth.write_fasta(src, reads)
+            oargs = []
+        else:
+            src = os.path.join(d, "reads.fq")
+            with open(src, "w") as f:
+                for i, r in enumerate(reads):
+                    tag = " CR:i:%d BX:Z:bc%d junk" % (i % 7, i % 3) if i % 2 else ""
+                    f.write("@q%d%s\n%s\n+\n%s\n" % (i, tag, r.tobytes().decode(), "I" * 50))
+            oargs = ["-x", "--no-opposite-strand"]
+        refrun.run_ref(["index", src], ref)
+        refrun.run_ref(["overlap", "-m", "18", "-t", "3"] + oargs + [src], ref)
+        want = _asqg(os.path.join(ref, "reads.asqg.gz"))
+        n = len(reads)
+        assert len(want) > 1 + n + 100
+        for extra in ([], ["--gpus", "2"], ["--gpus", "3", "--gzip-level", "6"]):
+            os.remove(os.path.join(ref, "reads.asqg.gz"))  # -p PREFIX names the output too
+            _cli(["overlap", "-m", "18", "-p", os.path.join(ref, "reads")] + oargs + extra + [src], ours)
+            got = _asqg(os.path.join(ref, "reads.asqg.gz"))
+            assert got[:1 + n] == want[:1 + n], extra
+            assert sorted(got[1 + n:]) == sorted(want[1 + n:]), extra
+            assert not [f for f in os.listdir(ref) if ".part" in f]
