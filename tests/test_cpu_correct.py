@@ -73,3 +73,36 @@ def test_lookup_count_of_clean_reads_is_the_nominal_figure():
     assert int(nfix.sum()) == 0 and out == reads and solid > 0.9 * len(reads)
     if solid == len(reads):
         assert lookups == len(reads) * 2 * (k - 1) * (40 - k + 1)
+
+
+@pytest.mark.skipif(not refrun.have_ref(), reason="compiled reference (oracle/_ref/siga) not present")
+def test_correction_logic_fuzz_against_reference_binary():
+    """Random shapes and options (read length 20-260, k 1-90, thresholds 0-6, 0-30 rounds, offsets 0-5, error rates up to
+    10 %, FASTA / FASTQ, variable length, periodic genomes): the written file must always equal the reference's.  A longer
+    run of the same generator (3 568 cases) found no difference."""
+    from siga_b200 import synth
+    lib = _lib()
+    rng = np.random.default_rng(20261018)
+    for case in range(24):
+        seed = int(rng.integers(1 << 30))
+        L = int(rng.integers(20, 260))
+        G = int(rng.integers(L + 50, 3000))
+        N = int(rng.integers(100, 500))
+        err = float(rng.choice([0.0, 0.005, 0.02, 0.05, 0.1]))
+        fastq, var, both = bool(rng.integers(2)), bool(rng.integers(3) == 0), bool(rng.integers(2))
+        opt = dict(k=int(rng.integers(1, min(L, 90) + 1)), x=int(rng.choice([0, 1, 2, 3, 4, 6])), i=int(rng.choice([0, 1, 3, 10, 30])),
+                   O=int(rng.choice([0, 1, 2, 5])))
+        mode = int(rng.integers(4))
+        if mode == 0:
+            reads, quals = cc.random_case(seed, n_reads=N, read_len=L, genome=G, err=err, fastq=fastq, variable=var, both=both)
+        else:  # periodic / low-complexity genome with a few mutations
+            r2 = np.random.default_rng(seed)
+            unit = synth.random_genome(int(r2.integers(1, 40)), r2)
+            g = np.tile(unit, G // len(unit) + 2)[:G]
+            mut = r2.random(G) < 0.02 * mode
+            g[mut] = synth.random_genome(int(mut.sum()), r2)
+            reads = [a.tobytes().decode() for a in synth.sample_reads(g, N, L, r2, err=err, both_strands=both)]
+            quals = ["".join(chr(int(v)) for v in r2.integers(33, 33 + 42, size=L)) for _ in reads] if fastq else None
+        runs, _, want = cc.reference_correct(reads, quals, opt)
+        got, valid, _, _ = cc.hostemu_correct(lib, runs, reads, quals, opt)
+        assert cc.ec_text(got, quals, valid) == want, (case, seed, mode, L, G, N, err, fastq, var, both, opt)
