@@ -14,7 +14,7 @@ fi
 mkdir -p "$OUT/obj"
 CXX="${ORACLE_CXX:-/usr/bin/g++}"  # the image exports CXX=/opt/gcc/bin/g++, which lacks libgomp.spec
 FLAGS="-std=c++11 -O2 -fopenmp -w -DHAVE_CONFIG_H -include cstdint -include cassert -include functional -include algorithm -include numeric -I$HERE/shim -I$REF/src -I$REF/3rdparty"
-TUS="main indexer overlap rmdup correct correct_processor assembler bigraph bigraph_visitors bigraph_search suffix_array_builder suffix_array bwt fmindex overlap_builder asqg coord kseq reads"
+TUS="main indexer overlap rmdup correct correct_processor match assembler bigraph bigraph_visitors bigraph_search suffix_array_builder suffix_array bwt fmindex overlap_builder asqg coord kseq reads"
 pids=()
 for tu in $TUS; do
   if [ ! -f "$OUT/obj/$tu.o" ] || [ "$REF/src/$tu.cpp" -nt "$OUT/obj/$tu.o" ]; then

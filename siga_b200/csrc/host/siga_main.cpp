@@ -982,6 +982,128 @@ int cmd_correct(int argc, char** argv) {
   return 0;
 }
 
+int usage_match() {
+  printf("siga match [OPTION] ... READSFILE\n"
+         "Match reads in READSFILE with ref\n"
+         "\n"
+         "      -h, --help                       display this help and exit\n"
+         "\n"
+         "      -p, --prefix=PREFIX              use PREFIX instead of prefix of READSFILE for the names of the index files\n"
+         "      -l, --max-length=N               match only the first and the last N bases of longer reads\n"
+         "          --no-opposite-strand         treat all reads as forward strand\n"
+         "          --device=N                   CUDA device (default 0)\n"
+         "\n");
+  return 256;
+}
+
+// `siga match` (src/match.cpp:22-76): for every read of every READSFILE the number of occurrences of the read -- or of
+// its first and last max-length bases -- in the forward index PREFIX.bwt, plus those of the reverse complement unless
+// --no-opposite-strand; one "VT\t<0|1>\t<name>\t<seq>\t<count>" line per query on stdout, input order.  The counts are
+// FMIndex::Interval::occurrences (src/fmindex.h:67-86) = one sgx_fm_count call per file.
+int cmd_match(int argc, char** argv) {
+  enum { OPT_NO_RC = 1000, OPT_DEVICE };
+  static const option longopts[] = {{"log4cxx", required_argument, nullptr, 'c'},    {"ini", required_argument, nullptr, 's'},
+                                    {"prefix", required_argument, nullptr, 'p'},     {"threads", required_argument, nullptr, 't'},
+                                    {"max-length", required_argument, nullptr, 'l'}, {"no-opposite-strand", no_argument, nullptr, OPT_NO_RC},
+                                    {"device", required_argument, nullptr, OPT_DEVICE}, {"help", no_argument, nullptr, 'h'},
+                                    {nullptr, 0, nullptr, 0}};
+  CommonOpts o;
+  size_t max_len = (size_t)-1;
+  bool rcomp = true;
+  int c;
+  while ((c = getopt_long(argc, argv, "c:s:p:t:l:h", longopts, nullptr)) != -1) {
+    switch (c) {
+      case 'p': o.prefix = optarg; break;
+      case 'l': max_len = (size_t)strtoull(optarg, nullptr, 10); break;
+      case OPT_NO_RC: rcomp = false; break;
+      case OPT_DEVICE: o.device = atoi(optarg); break;
+      case 'h': o.help = true; break;
+      default: break;
+    }
+  }
+  if (o.help || argc - optind < 1) return usage_match();
+  const std::string prefix = o.prefix.empty() ? stem(argv[optind]) : o.prefix;
+  uint64_t ns = 0, nf = 0;
+  std::vector<uint8_t> runs;
+  if (!read_bwt(prefix + ".bwt", &ns, &nf, &runs)) {
+    fprintf(stderr, "ERROR siga - Failed to load FMIndex from %s\n", prefix.c_str());
+    return -1;
+  }
+  sgx_ctx* ctx = nullptr;
+  int rc = sgx_init(o.device, &ctx);
+  if (rc != SGX_OK) return fail(nullptr, "sgx_init", rc);
+  sgx_fm* fm = nullptr;
+  if ((rc = sgx_fm_create(ctx, runs.data(), runs.size(), nf, &fm)) != SGX_OK) return fail(ctx, "sgx_fm_create", rc);
+  int status = 0;
+  for (int a = optind; a < argc && status == 0; ++a) {
+    ReadSet rs;
+    std::string err;
+    if (!read_sequences(argv[a], &rs, &err)) {
+      fprintf(stderr, "ERROR siga - %s\n", err.c_str());
+      status = -1;
+      break;
+    }
+    // queries of read i: the read (or its first max-length bases) and, for longer reads, its last max-length bases;
+    // each followed by its reverse complement when both strands count
+    std::string q;
+    std::vector<uint64_t> qoff(1, 0);
+    auto add = [&](const char* p, size_t len) {
+      if (len) {  // an empty query occurs 0 times (Interval::get leaves the interval invalid)
+        q.append(p, len);
+        qoff.push_back(q.size());
+      }
+      if (len && rcomp) {
+        for (size_t k = 0; k < len; ++k) {
+          const char ch = p[len - 1 - k];
+          q += ch == 'A' ? 'T' : (ch == 'C' ? 'G' : (ch == 'G' ? 'C' : (ch == 'T' ? 'A' : ch)));
+        }
+        qoff.push_back(q.size());
+      }
+    };
+    for (size_t i = 0; i < rs.size(); ++i) {
+      const char* seq = rs.bases.data() + rs.off[i];
+      const size_t len = rs.off[i + 1] - rs.off[i];
+      if (len > max_len) {
+        add(seq, max_len);
+        add(seq + len - max_len, max_len);
+      } else {
+        add(seq, len);
+      }
+    }
+    std::vector<uint64_t> counts(qoff.size() - 1);
+    if (!counts.empty() && (rc = sgx_fm_count(ctx, fm, q.data(), qoff.data(), counts.size(), counts.data())) != SGX_OK) {
+      fail(ctx, "sgx_fm_count", rc);
+      status = -1;
+      break;
+    }
+    std::string text;
+    size_t k = 0;
+    const size_t per = rcomp ? 2 : 1;
+    for (size_t i = 0; i < rs.size(); ++i) {
+      const size_t len = rs.off[i + 1] - rs.off[i];
+      const int parts = len > max_len ? 2 : 1;
+      const size_t qlen = len > max_len ? max_len : len;
+      for (int part = 0; part < parts; ++part) {
+        uint64_t n = 0;
+        if (qlen)
+          for (size_t j = 0; j < per; ++j) n += counts[k++];
+        text += part == 0 ? "VT\t0\t" : "VT\t1\t";
+        text += rs.names[i];
+        text += '\t';
+        text.append(rs.bases, rs.off[i], len);
+        text += '\t';
+        append_uint(&text, n);
+        text += '\n';
+      }
+    }
+    if (fwrite(text.data(), 1, text.size(), stdout) != text.size()) status = -1;
+  }
+  fflush(stdout);
+  sgx_fm_free(fm);
+  sgx_shutdown(ctx);
+  return status;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -990,7 +1112,8 @@ int main(int argc, char** argv) {
            "   index       build the BWT and FM-index for a set of reads\n"
            "   overlap     compute overlaps between reads\n"
            "   rmdup       remove duplicated reads from the data set\n"
-           "   correct     correct sequencing errors in a set of reads\n\n"
+           "   correct     correct sequencing errors in a set of reads\n"
+           "   match       count the occurrences of reads in an indexed read set\n\n"
            "See 'siga <command> -h' to read about a specific subcommand.\n");
     return 256;
   }
@@ -999,6 +1122,7 @@ int main(int argc, char** argv) {
   if (cmd == "overlap") return cmd_overlap(argc - 1, argv + 1);
   if (cmd == "rmdup") return cmd_rmdup(argc - 1, argv + 1);
   if (cmd == "correct") return cmd_correct(argc - 1, argv + 1);
-  fprintf(stderr, "siga: '%s' is not provided by this build (only the index / overlap / rmdup / correct path is)\n", cmd.c_str());
+  if (cmd == "match") return cmd_match(argc - 1, argv + 1);
+  fprintf(stderr, "siga: '%s' is not provided by this build (only index / overlap / rmdup / correct / match are)\n", cmd.c_str());
   return 256;
 }

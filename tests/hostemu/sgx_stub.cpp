@@ -192,6 +192,41 @@ void sgx_edges_free(sgx_edges* e) {
   e->edges = nullptr;
 }
 
+// FMIndex::Interval::occurrences (src/fmindex.h:67-86) per query on the scalar rank query
+int sgx_fm_count(sgx_ctx* ctx, const sgx_fm* fm, const char* ascii, const uint64_t* off, uint64_t n, uint64_t* counts) {
+  if (!ctx || !fm || !ascii || !off || (!counts && n)) return SGX_EINVAL;
+  const FmView& v = ((HemuFm*)fm->fm)->view;
+  HostGroup g;
+  for (uint64_t i = 0; i < n; ++i) {
+    uint64_t j = off[i + 1] - off[i];
+    if (j == 0) return SGX_EINVAL;
+    int rk[256];
+    memset(rk, 0, sizeof(rk));
+    rk[(int)'A'] = 1;
+    rk[(int)'C'] = 2;
+    rk[(int)'G'] = 3;
+    rk[(int)'T'] = 4;
+    const char* w = ascii + off[i];
+    for (uint64_t t = 0; t < j; ++t)
+      if (!rk[(unsigned char)w[t]]) {
+        ctx->err = "sgx_reads_pack: base other than A/C/G/T";
+        return SGX_EINVAL;
+      }
+    int c = rk[(unsigned char)w[j - 1]];
+    pos_t lo = v.pred[c], hi = v.pred[c + 1] - 1;
+    uint64_t L[5], U[5];
+    while (--j > 0 && ival_valid(lo, hi)) {
+      c = rk[(unsigned char)w[j - 1]];
+      fm_occ(v, lo - 1, L, g);
+      fm_occ(v, hi, U, g);
+      lo = v.pred[c] + L[c];
+      hi = v.pred[c] + U[c] - 1;
+    }
+    counts[i] = ival_valid(lo, hi) ? hi - lo + 1 : 0;
+  }
+  return SGX_OK;
+}
+
 // ---- no host stand-in
 int sgx_index_build(sgx_ctx* ctx, const sgx_reads*, int, int, sgx_index_out*) { return no_device(ctx, "sgx_index_build"); }
 void sgx_index_out_free(sgx_index_out*) {}

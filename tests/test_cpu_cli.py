@@ -129,3 +129,28 @@ def test_overlap_front_end_single_and_sharded_equal_reference_asqg(case):
             assert got[:1 + n] == want[:1 + n], extra
             assert sorted(got[1 + n:]) == sorted(want[1 + n:]), extra
             assert not [f for f in os.listdir(ref) if ".part" in f]
+
+
+def test_match_front_end_equals_reference_stdout():
+    """`siga match` (src/match.cpp:22-76): occurrence counts of whole reads or of their first / last -l bases, both
+    strands or forward only, several input files, FASTA and FASTQ -- stdout byte for byte."""
+    rng = np.random.default_rng(77)
+    g = synth.random_genome(3000, rng)
+    idx_reads = synth.sample_reads(g, 1200, 60, rng, err=0.005)
+    q1 = [r.tobytes().decode() for r in synth.sample_reads(g, 300, 60, rng, err=0.01)]
+    q2 = [r.tobytes().decode()[:int(l)] for r, l in zip(synth.sample_reads(g, 200, 60, rng, err=0.0), rng.integers(5, 61, 200))]
+    with tempfile.TemporaryDirectory() as d:
+        ref_fa = os.path.join(d, "ref.fa")
+        synth.write_fasta(ref_fa, idx_reads)
+        refrun.run_ref(["index", "--no-reverse", ref_fa], d)
+        a, b = os.path.join(d, "a.fa"), os.path.join(d, "b.fq")
+        cc.write_reads(a, q1, None, ["a%d extra" % i for i in range(len(q1))])
+        cc.write_reads(b, q2, ["I" * len(s) for s in q2])
+        for args in (["-p", "ref", a], ["-p", "ref", "--no-opposite-strand", a, b], ["-p", "ref", "-l", "20", a, b],
+                     ["--prefix=ref", "--max-length", "7", "--no-opposite-strand", b]):
+            want = subprocess.run([refrun.REF_BIN, "match"] + args, cwd=d, capture_output=True, text=True,
+                                  env=dict(os.environ, ORACLE_LOG_LEVEL="5"))
+            assert want.returncode == 0 and want.stdout.count("\n") >= len(q2)
+            got = _cli(["match"] + args, d)
+            assert got.stdout == want.stdout, args
+        _cli(["match", "-p", "missing", a], d, ok=False)
