@@ -453,7 +453,11 @@ def main():
                     "roofline": {"bound": "hbm", "kernel": "corr_kernel", "unit": "GB/s", "peak": hbm_peak,
                                  "achieved": corr_look * 128 / (corr_kernel_ms * 1e-3) / 1e9 if corr_kernel_ms else 0.0,
                                  "frac": corr_look * 128 / (corr_kernel_ms * 1e-3) / 1e9 / hbm_peak if corr_kernel_ms else 0.0,
-                                 "traffic": None, "lookups_per_read": corr_look / csteps / n_reads,
+                                 # dram__bytes_read.sum + dram__bytes_write.sum of the one launch at full cfg2 size, ncu --set
+                                 # full capture profiles/r1h_prof_correct.raw.csv (the r1h kernel: same rank-block loads in
+                                 # the same order as the current one, which only spends fewer instructions per step)
+                                 "traffic": 75.20e9 if args.scale == 1.0 else None, "traffic_source": "profiles/r1h_summary.md",
+                                 "lookups_per_read": corr_look / csteps / n_reads,
                                  "reference_lookups_per_read_nominal": 2 * 30 * (read_len - 30),
                                  "lookups_per_s": corr_look / (corr_kernel_ms * 1e-3) if corr_kernel_ms else 0.0}},
         "clocks": clocks,
