@@ -282,3 +282,27 @@ def test_executed_lookup_counter_matches_a_count_from_first_principles():
     lib.hemu_hits_free(ctypes.byref(h))
     lib.hemu_fm_free(fwd)
     lib.hemu_fm_free(rev)
+
+
+def test_single_symbol_lane_arithmetic_equals_full_rank_query():
+    """fm_lane_sym_count (fm_layout.h) is the per-lane arithmetic of quad_rank_sym, the rank query of the correction
+    kernel; summed the way a quad sums it, it must give getOcc(c, i) of the all-symbol query for every symbol and
+    position (block boundaries, the last block, position -1)."""
+    lib = _hostemu()
+    lib.hemu_fm_occ_sym.restype = ctypes.c_uint64
+    lib.hemu_fm_occ_sym.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int]
+    lib.hemu_fm_length.restype = ctypes.c_uint64
+    lib.hemu_fm_length.argtypes = [ctypes.c_void_p]
+    fx = _load([p for p in GOLDEN if "random_fixed36_dups" in p][0])
+    runs = np.frombuffer(bytes.fromhex(fx["index_sais2"]["bwt_hex"]), dtype=np.uint8)[30:].copy()
+    fm = lib.hemu_fm_from_rle(runs.ctypes.data, len(runs))
+    n = int(lib.hemu_fm_length(fm))
+    rng = np.random.default_rng(3)
+    pos = np.concatenate([np.arange(0, min(n, 600)), rng.integers(0, n, 1500), [n - 1]]).astype(np.uint64)
+    pos = np.concatenate([pos, np.array([2 ** 64 - 1], dtype=np.uint64)])
+    want = np.zeros((len(pos), 5), dtype=np.uint64)
+    lib.hemu_fm_occ(fm, pos.ctypes.data, len(pos), want.ctypes.data)
+    for i, p in enumerate(pos.tolist()):
+        for c in range(1, 5):
+            assert lib.hemu_fm_occ_sym(fm, p, c) == int(want[i, c]), (p, c)
+    lib.hemu_fm_free(fm)
