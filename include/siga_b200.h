@@ -256,7 +256,7 @@ int sgx_edges_gather(sgx_ctx* ctx, sgx_comm* comm, const sgx_edges* local, int r
 typedef struct sgx_correct_params {
   uint32_t kmer_size;         /* -k, default 31                                                                */
   int32_t kmer_threshold;     /* -x, default 3: a k-mer seen fewer times is a correction candidate             */
-  uint32_t kmer_rounds;       /* -i, default 10                                                                */
+  uint32_t kmer_rounds;       /* -i, default 10 (values above 2^20 are treated as 2^20)                        */
   uint64_t kmer_count_offset; /* -O, default 1                                                                 */
 } sgx_correct_params;
 

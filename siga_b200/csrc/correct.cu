@@ -265,7 +265,9 @@ void correct_run(sgx_ctx* ctx, const sgx_fm* fm, const sgx_reads* reads, uint64_
   t_all.start();
   CorrectParams P;
   P.k = prm->kmer_size;
-  P.rounds = prm->kmer_rounds;
+  // every round fixes one base or ends the read, and a fix makes its k-mer solid, so real reads stop after a handful of
+  // rounds; the cap only bounds the kernel's run time should fixes ever chase each other in a cycle
+  P.rounds = std::min<uint32_t>(prm->kmer_rounds, 1u << 20);
   P.low = (uint64_t)(int64_t)prm->kmer_threshold;  // int -> size_t like CorrectThreshold::requiredSupport
   P.high = (uint64_t)((int64_t)prm->kmer_threshold + 1);
   P.count_offset = prm->kmer_count_offset;
