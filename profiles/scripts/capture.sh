@@ -16,3 +16,7 @@ ncu --set full --clock-control none --import-source on -k regex:ov_reduce -c 1 -
     python profiles/scripts/prof_overlap.py 1.0 1 > $out/${tag}_ncu_reduce.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:bcr_merge --launch-skip 100 -c 1 -o $out/${tag}_merge -f \
     python profiles/scripts/prof_overlap.py 0.2 1 > $out/${tag}_ncu_merge.log 2>&1
+# k-mer correction kernel (siga correct): plain run first, then one --set full capture of the single launch
+python profiles/scripts/prof_correct.py 1.0 2 > $out/${tag}_correct.jsonl 2> $out/${tag}_correct.err || exit 1
+ncu --set full --clock-control none --import-source on -k regex:corr_kernel -c 1 -o $out/${tag}_correct -f \
+    python profiles/scripts/prof_correct.py 1.0 1 > $out/${tag}_ncu_correct.log 2>&1
