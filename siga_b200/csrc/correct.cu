@@ -1,13 +1,16 @@
 // `siga correct` on the device: KmerCorrector::process (src/correct_processor.cpp:72-232) for a batch of reads.
 //
-// One warp per read (reads are handed out dynamically: a read that needs ten correction rounds costs ~20 x a clean
+// One warp per read (reads are handed out dynamically: a read that needs ten correction rounds costs many times a clean
 // one).  The control logic is correct_logic.h, executed uniformly by the 32 lanes on per-warp state in shared memory
-// (working sequence, quality bits, solid bits); its one parallel primitive -- "does this k-mer reach this count?" for
-// up to eight k-mers at a time -- maps to the eight 4-lane quads of the warp, each running
-// FMIndex::Interval::get (src/fmindex.h:67-86) as a backward search on the 128-byte rank blocks with quad_rank
-// (overlap_search.cuh): lower and upper end of the interval share one call, so a step is one or two 128-byte lines.
-// Bound: random 128-byte access, like the overlap search; algorithmic work = executed rank lookups x 128 B, about
-// 2 (k-1) (n-k+1) per clean read (7200 at n = 150, k = 31: eight times the four overlap searches of the same read).
+// (working sequence, quality bits, solid / decided bits, remembered rare strings).  Its two parallel primitives --
+// certificate searches over runs of undecided k-mers (windows) and "does this k-mer with one base substituted reach
+// this count?" (qualify) -- each give up to eight queries to the eight 4-lane quads of the warp.  A quad runs a plain
+// backward search (FMIndex::Interval::update, src/fmindex.h:96-100) on the 128-byte rank blocks with quad_rank_sym
+// (quad_rank.cuh): the rank of the ONE stepped symbol at both interval ends from one or two 128-byte lines.
+// Bound: random 128-byte access, like the overlap search; algorithmic work = executed rank lookups x 128 B.  The
+// reference's way of counting costs 2 (k-1) (n-k+1) lookups per counting round (7200 at n = 150, k = 31, eight times
+// the four overlap searches of the same read); the certificates settle the same solid bits with about a third
+// (correct_logic.h).  Measured: profiles/r1h_summary.md -- the kernel is issue-bound, hence the branch-free loops.
 //
 // Output is compact: one flag per read (written or dropped by PostCorrector, src/correct_processor.cpp:258-264) and
 // the list of substituted bases of the written reads.
