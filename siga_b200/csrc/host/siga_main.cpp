@@ -19,15 +19,18 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
 
 #include "../../../include/siga_b200.h"
+#include "fastgz.h"
 #include "seqio.h"
 
 using namespace sgxhost;
@@ -63,24 +66,68 @@ class GzChunkWriter {
     if (f_) fclose(f_);
   }
   bool ok() const { return f_ != NULL; }
-  // produce(i, &text) fills the text of chunk i in [0, n); chunks are emitted in index order.
+  // produce(i, &text) fills the text of chunk i in [0, n); chunks are emitted in index order.  literal(i) says whether
+  // chunk i is sequence-like text, which goes through the literal-only encoder (fastgz.h) instead of zlib.
   template <class F>
   bool write_chunks(size_t n, F produce) {
+    return write_chunks(n, produce, [](size_t) { return false; });
+  }
+  template <class F, class L>
+  bool write_chunks(size_t n, F produce, L literal) {
+    // a pool of workers takes chunk indices in order; the calling thread writes finished members in index order while
+    // later chunks are still being produced (at most 2 x threads chunks are in flight, which bounds the memory)
+    const size_t window = 2 * (size_t)threads_;
+    std::vector<std::string> slot(window);
+    std::vector<char> ready(window, 0);
+    std::mutex mu;
+    std::condition_variable cv;
+    size_t next = 0, written = 0;
     bool good = true;
-    for (size_t base = 0; base < n && good; base += threads_) {
-      const size_t m = std::min<size_t>(threads_, n - base);
-      std::vector<std::string> gz(m);
-      std::vector<std::thread> pool;
-      for (size_t t = 0; t < m; ++t) {
-        pool.emplace_back([&, t]() {
-          std::string text;
-          produce(base + t, &text);
-          gz[t] = deflate_member(text, level_);
-        });
+    auto worker = [&]() {
+      for (;;) {
+        size_t i;
+        {
+          std::unique_lock<std::mutex> lk(mu);
+          cv.wait(lk, [&]() { return !good || next >= n || next < written + window; });
+          if (!good || next >= n) return;
+          i = next++;
+        }
+        std::string text;
+        produce(i, &text);
+        std::string gz = literal(i) ? gzip_member_huffman(text.data(), text.size()) : deflate_member(text, level_);
+        {
+          std::lock_guard<std::mutex> lk(mu);
+          slot[i % window].swap(gz);
+          ready[i % window] = 1;
+        }
+        cv.notify_all();
       }
-      for (auto& th : pool) th.join();
-      for (size_t t = 0; t < m && good; ++t) good = fwrite(gz[t].data(), 1, gz[t].size(), f_) == gz[t].size();
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < threads_ && t < n; ++t) pool.emplace_back(worker);
+    while (written < n) {
+      std::string gz;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&]() { return ready[written % window] != 0; });
+        gz.swap(slot[written % window]);
+        ready[written % window] = 0;
+      }
+      const bool ok_write = fwrite(gz.data(), 1, gz.size(), f_) == gz.size();
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!ok_write) good = false;
+        ++written;
+      }
+      cv.notify_all();
+      if (!ok_write) break;
     }
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      if (written < n) good = false;  // stop the workers after a failed write
+    }
+    cv.notify_all();
+    for (auto& th : pool) th.join();
     return good;
   }
 
@@ -154,7 +201,9 @@ struct CommonOpts {
   std::string prefix;
   int threads = 0;     // host-side text / gzip work; 0 = all hardware threads (the search itself runs on the GPU)
   int device = 0;
-  int gzip_level = 1;  // .asqg.gz members are written at zlib level 1 unless --gzip-level says otherwise
+  int gzip_level = 1;  // zlib level of the .gz members that go through zlib
+  bool gzip_fast = true;  // sequence records (VT lines, corrected reads) use the literal-only encoder; --gzip-level N
+                          // turns that off and sends everything through zlib at level N
   int gpus = 1;        // --gpus N: one forked process per GPU (devices device .. device + N - 1)
   bool help = false;
 };
@@ -259,7 +308,7 @@ bool write_asqg(const std::string& path, const CommonOpts& o, const ReadSet& rs,
         *text += (g.af & SGX_AF_QUERYCOMP) ? " 1 0\n" : " 0 0\n";
       }
     }
-  });
+  }, [&](size_t ci) { return o.gzip_fast && ci >= n_ht && ci < n_ht + n_vt; });  // VT records are mostly read sequence
 }
 
 bool append_file(FILE* dst, const std::string& path) {
@@ -501,7 +550,10 @@ int cmd_overlap(int argc, char** argv) {
       case 'm': min_overlap = (unsigned)atoi(optarg); break;
       case 'x': exhaustive = true; break;
       case OPT_NO_RC: rcomp = false; break;
-      case OPT_GZIP_LEVEL: o.gzip_level = std::max(1, std::min(9, atoi(optarg))); break;
+      case OPT_GZIP_LEVEL:
+        o.gzip_level = std::max(1, std::min(9, atoi(optarg)));
+        o.gzip_fast = false;
+        break;
       case OPT_GPUS: o.gpus = std::max(1, std::min(16, atoi(optarg))); break;
       case OPT_DEVICE: o.device = atoi(optarg); break;
       case 'h': o.help = true; break;
@@ -768,8 +820,8 @@ int usage_correct() {
 // Text of the written reads of [first, first + count) in input order (PostCorrector, src/correct_processor.cpp:258-264;
 // record format: operator<<, src/kseq.cpp:106-125), produced on `threads` threads; plain file or gzip members.
 // valid[i - first] tells whether read i is written.
-bool write_corrected(const std::string& path, bool gz, int threads, int gzip_level, const ReadSet& rs, const uint8_t* valid,
-                     size_t first, size_t count) {
+bool write_corrected(const std::string& path, bool gz, int threads, int gzip_level, bool gzip_fast, const ReadSet& rs,
+                     const uint8_t* valid, size_t first, size_t count) {
   const bool fastq = !rs.quals.empty();
   const size_t chunk = 1 << 16, n_chunks = (count + chunk - 1) / chunk;
   auto produce = [&](size_t ci, std::string* text) {
@@ -798,7 +850,7 @@ bool write_corrected(const std::string& path, bool gz, int threads, int gzip_lev
     GzChunkWriter w(path, (unsigned)threads, gzip_level);
     return w.ok() && w.write_chunks(std::max<size_t>(n_chunks, 1), [&](size_t ci, std::string* text) {
       if (ci < n_chunks) produce(ci, text);
-    });
+    }, [&](size_t) { return gzip_fast; });
   }
   FILE* f = fopen(path.c_str(), "wb");
   bool good = f != nullptr;
@@ -850,7 +902,10 @@ int cmd_correct(int argc, char** argv) {
       case 'O': prm.kmer_count_offset = strtoull(optarg, nullptr, 10); break;
       case OPT_DEVICE: o.device = atoi(optarg); break;
       case OPT_GPUS: o.gpus = std::max(1, std::min(16, atoi(optarg))); break;
-      case OPT_GZIP_LEVEL: o.gzip_level = std::max(1, std::min(9, atoi(optarg))); break;
+      case OPT_GZIP_LEVEL:
+        o.gzip_level = std::max(1, std::min(9, atoi(optarg)));
+        o.gzip_fast = false;
+        break;
       case 'h': o.help = true; break;
       default: break;
     }
@@ -945,9 +1000,9 @@ int cmd_correct(int argc, char** argv) {
 
   bool good;
   if (world == 1) {
-    good = write_corrected(outfile, gz, o.threads, o.gzip_level, rs, res.valid, 0, rs.size());
+    good = write_corrected(outfile, gz, o.threads, o.gzip_level, o.gzip_fast, rs, res.valid, 0, rs.size());
   } else {
-    good = write_corrected(outfile + ".part" + std::to_string(my), gz, o.threads, o.gzip_level, rs, res.valid, first, count);
+    good = write_corrected(outfile + ".part" + std::to_string(my), gz, o.threads, o.gzip_level, o.gzip_fast, rs, res.valid, first, count);
     if (my) {
       sgx_corrected_free(&res);
       sgx_shutdown(ctx);

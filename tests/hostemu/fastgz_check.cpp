@@ -1,0 +1,23 @@
+// TEST INFRASTRUCTURE ONLY: writes gzip_member_huffman(file) for every file given on the command line to <file>.gz and
+// prints "<file> <input bytes> <output bytes> <MB/s>"; the Python test decompresses the results with zlib.
+#include <chrono>
+#include <cstdio>
+#include <fstream>
+#include <iterator>
+#include <string>
+
+#include "../../siga_b200/csrc/host/fastgz.h"
+
+int main(int argc, char** argv) {
+  for (int i = 1; i < argc; ++i) {
+    std::ifstream f(argv[i], std::ios::binary);
+    const std::string data((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    const auto t0 = std::chrono::steady_clock::now();
+    const std::string gz = sgxhost::gzip_member_huffman(data.data(), data.size());
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    std::ofstream o(std::string(argv[i]) + ".gz", std::ios::binary);
+    o.write(gz.data(), (std::streamsize)gz.size());
+    printf("%s %zu %zu %.0f\n", argv[i], data.size(), gz.size(), data.size() / 1e6 / (dt > 0 ? dt : 1e-9));
+  }
+  return 0;
+}

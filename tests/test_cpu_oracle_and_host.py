@@ -306,3 +306,42 @@ def test_single_symbol_lane_arithmetic_equals_full_rank_query():
         for c in range(1, 5):
             assert lib.hemu_fm_occ_sym(fm, p, c) == int(want[i, c]), (p, c)
     lib.hemu_fm_free(fm)
+
+
+def test_literal_only_gzip_writer_round_trips(tmp_path):
+    """siga_b200/csrc/host/fastgz.cpp (the encoder of the VT members of .asqg.gz and of `siga correct -o x.gz`): every
+    member must be a valid gzip stream that decodes to its input -- empty and one-byte inputs, one and two symbols, all
+    256 byte values, a frequency profile that forces the 15-bit length limit, block boundaries, ASQG-like text."""
+    import gzip
+    import subprocess
+    import zlib
+    exe = tmp_path / "fastgz_check"
+    src = [os.path.join(REPO, "tests", "hostemu", "fastgz_check.cpp"), os.path.join(REPO, "siga_b200", "csrc", "host", "fastgz.cpp")]
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-o", str(exe)] + src + ["-lz"], check=True)
+    rng = np.random.default_rng(3)
+    skew = np.concatenate([np.full(2 ** i, i, dtype=np.uint8) for i in range(20)] + [np.arange(20, 256, dtype=np.uint8)])
+    rng.shuffle(skew)
+    g = synth.random_genome(20000, rng)
+    reads = synth.sample_reads(g, 6000, 150, rng, err=0.01)
+    files = {
+        "empty": b"", "one": b"A", "same": b"A" * 100000, "two": b"AB" * 70000,
+        "random256": rng.integers(0, 256, 700000, dtype=np.uint8).tobytes(),
+        "length_limit": skew.tobytes(),
+        "block_edge": b"ACGT" * 65536, "block_edge_plus_one": b"ACGT" * 65536 + b"N",
+        "vt": b"".join(b"VT\tr%d\t%s\tSS:i:0\n" % (i, r.tobytes()) for i, r in enumerate(reads)),
+    }
+    for k in range(12):  # random lengths around the block size, random alphabets
+        n = int(rng.integers(1, 3 * 262144))
+        files["fuzz%d" % k] = rng.integers(0, int(rng.integers(1, 257)), n, dtype=np.uint8).tobytes()
+    for name, data in files.items():
+        (tmp_path / name).write_bytes(data)
+    r = subprocess.run([str(exe)] + [str(tmp_path / n) for n in files], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for name, data in files.items():
+        blob = (tmp_path / (name + ".gz")).read_bytes()
+        assert gzip.decompress(blob) == data, name
+        d = zlib.decompressobj(31)
+        assert d.decompress(blob) == data and d.eof and d.unused_data == b"", name
+    # within a few percent of zlib level 1 on sequence records
+    z = zlib.compressobj(1, zlib.DEFLATED, 31)
+    assert len((tmp_path / "vt.gz").read_bytes()) < 1.05 * len(z.compress(files["vt"]) + z.flush())
