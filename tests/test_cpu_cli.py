@@ -154,3 +154,39 @@ def test_match_front_end_equals_reference_stdout():
             got = _cli(["match"] + args, d)
             assert got.stdout == want.stdout, args
         _cli(["match", "-p", "missing", a], d, ok=False)
+
+
+def test_reference_assembler_reads_our_asqg_and_builds_the_same_contigs():
+    """BASELINE.json: "downstream `siga assemble` runs unchanged" -- the reference's assembler (compiled into the oracle
+    binary) on the .asqg.gz this front-end writes (multi-member gzip, literal-only members for the VT records) and on the
+    reference's own file: identical contig sets."""
+    rng = np.random.default_rng(41)
+    g = synth.random_genome(6000, rng)
+    reads = synth.sample_reads(g, 2500, 80, rng, err=0.0)
+
+    def contigs(path):
+        comp = bytes.maketrans(b"ACGT", b"TGCA")
+        out = []
+        for rec in open(path, "rb").read().split(b">")[1:]:
+            s = b"".join(rec.split(b"\n")[1:])
+            out.append(min(s, s.translate(comp)[::-1]))
+        return sorted(out)
+
+    with tempfile.TemporaryDirectory() as d:
+        ref, ours = os.path.join(d, "ref"), os.path.join(d, "ours")
+        os.mkdir(ref)
+        os.mkdir(ours)
+        src = os.path.join(ref, "reads.fa")
+        synth.write_fasta(src, reads)
+        refrun.run_ref(["index", src], ref)
+        refrun.run_ref(["rmdup", "-t", "3", src], ref)
+        dedup = os.path.join(ref, "reads.rmdup.fa")
+        refrun.run_ref(["index", dedup], ref)
+        refrun.run_ref(["overlap", "-m", "40", "-t", "3", dedup], ref)
+        refrun.run_ref(["assemble", "-m", "40", "-p", "asm", os.path.join(ref, "reads.rmdup.asqg.gz")], ref)
+        for ext in (".fa", ".bwt", ".rbwt", ".sai", ".rsai"):
+            os.symlink(os.path.join(ref, "reads.rmdup" + ext), os.path.join(ours, "reads.rmdup" + ext))
+        _cli(["overlap", "-m", "40", os.path.join(ours, "reads.rmdup.fa")], ours)
+        refrun.run_ref(["assemble", "-m", "40", "-p", "asm", os.path.join(ours, "reads.rmdup.asqg.gz")], ours)
+        a, b = contigs(os.path.join(ours, "asm-contigs.fa")), contigs(os.path.join(ref, "asm-contigs.fa"))
+        assert a == b and sum(len(c) for c in a) > 4000
