@@ -91,8 +91,8 @@ void push(ReadSet* rs, const std::string& header, const std::string& seq, const 
   split_name(header, &name, &comment);
   rs->names.push_back(name);
   rs->comments.push_back(comment);
-  rs->bases += seq;
-  if (qual && rs->keep_quals) rs->quals += *qual;
+  rs->bases.append(seq.data(), seq.size());
+  if (qual && rs->keep_quals) rs->quals.append(qual->data(), qual->size());
   rs->off.push_back(rs->bases.size());
 }
 
@@ -107,7 +107,7 @@ bool read_sequences_serial(const std::string& path, ReadSet* out, std::string* e
   out->names.clear();
   out->comments.clear();
   out->bases.clear();
-  out->quals.clear();
+  out->quals.release();
   out->off.assign(1, 0);
   const int first = in.peek();
   std::string line;
@@ -188,56 +188,77 @@ inline bool next_line(const char*& p, const char* end, Line* ln) {
   return false;
 }
 
-void push_range(ReadSet* rs, const char* hb, const char* he, const std::string& seq) {
-  const char* sp = hb;
-  while (sp < he && *sp != ' ' && *sp != '\t') ++sp;
-  rs->names.emplace_back(hb, sp);
-  rs->comments.emplace_back(sp < he ? sp + 1 : he, he);
-  rs->bases += seq;
-  rs->off.push_back(rs->bases.size());
-}
-
-// false = something the serial reader treats specially: redo serially
-bool parse_fasta_range(const char* p, const char* end, ReadSet* out) {
-  out->off.assign(1, 0);
+// One pass over the records of [p, end) with the line rules of the serial reader; the sink sees every record as
+// header(hb, he), then seq(b, e) per sequence line (and qual(b, e) for FASTQ), then done().  false = something the
+// serial reader treats specially (a header after an empty FASTA record, a malformed FASTQ record): redo serially.
+template <class Sink>
+bool scan_fasta_range(const char* p, const char* end, Sink& sink) {
   Line ln;
-  const char *hb = nullptr, *he = nullptr;
-  std::string seq;
-  bool have = false;
+  bool have = false, any_seq = false;
   while (next_line(p, end, &ln)) {
     if (*ln.b == '>') {
-      if (have && !seq.empty()) push_range(out, hb, he, seq);
+      if (have && any_seq) sink.done();
       else if (have) return false;
-      hb = ln.b + 1;
-      he = ln.e;
-      seq.clear();
+      sink.header(ln.b + 1, ln.e);
       have = true;
+      any_seq = false;
     } else {
       if (!have) return false;
-      seq.append(ln.b, ln.e);
+      sink.seq(ln.b, ln.e);
+      any_seq = true;
     }
   }
-  if (have && !seq.empty()) push_range(out, hb, he, seq);
+  if (have && any_seq) sink.done();
   else if (have) return false;
   return true;
 }
 
-bool parse_fastq_range(const char* p, const char* end, ReadSet* out) {
-  out->off.assign(1, 0);
+template <class Sink>
+bool scan_fastq_range(const char* p, const char* end, Sink& sink) {
   Line h, sq, pl, ql;
-  std::string seq;
   while (next_line(p, end, &h)) {
     if (*h.b != '@') return false;
     if (!next_line(p, end, &sq) || !next_line(p, end, &pl) || !next_line(p, end, &ql)) return false;
     const size_t nlen = (size_t)(h.e - h.b - 1);
     const bool plus_ok = *pl.b == '+' && (pl.e - pl.b == 1 || ((size_t)(pl.e - pl.b) >= nlen && memcmp(pl.e - nlen, h.b + 1, nlen) == 0));
     if (!plus_ok || (ql.e - ql.b) != (sq.e - sq.b)) return false;
-    seq.assign(sq.b, sq.e);
-    push_range(out, h.b + 1, h.e, seq);
-    if (out->keep_quals) out->quals.append(ql.b, ql.e);
+    sink.header(h.b + 1, h.e);
+    sink.seq(sq.b, sq.e);
+    sink.qual(ql.b, ql.e);
+    sink.done();
   }
   return true;
 }
+
+// first pass: how many records and bases a range holds
+struct CountSink {
+  size_t records = 0, bases = 0;
+  void header(const char*, const char*) {}
+  void seq(const char* b, const char* e) { bases += (size_t)(e - b); }
+  void qual(const char*, const char*) {}
+  void done() { ++records; }
+};
+
+// second pass: every range writes its records straight into their final places
+struct FillSink {
+  ReadSet* out;
+  size_t rec, pos;  // next record index, next byte of bases / quals
+  bool quals;
+  void header(const char* hb, const char* he) {
+    const char* sp = hb;
+    while (sp < he && *sp != ' ' && *sp != '\t') ++sp;
+    out->names[rec].assign(hb, sp);
+    out->comments[rec].assign(sp < he ? sp + 1 : he, he);
+  }
+  void seq(const char* b, const char* e) {
+    memcpy(out->bases.data() + pos, b, (size_t)(e - b));
+    pos += (size_t)(e - b);
+  }
+  void qual(const char* b, const char* e) {
+    if (quals) memcpy(out->quals.data() + pos - (size_t)(e - b), b, (size_t)(e - b));  // same offsets as the bases
+  }
+  void done() { out->off[++rec] = pos; }
+};
 
 }  // namespace
 
@@ -290,42 +311,42 @@ bool read_sequences(const std::string& path, ReadSet* out, std::string* err) {
     }
     cut.push_back(end);
     const size_t parts = cut.size() - 1;
-    std::vector<ReadSet> sets(parts);
-    for (auto& s : sets) s.keep_quals = out->keep_quals;
+    // pass 1: sizes of every range
+    std::vector<CountSink> cnt(parts);
     std::vector<char> good(parts, 0);
-    std::vector<std::thread> pool;
-    for (size_t i = 0; i < parts; ++i)
-      pool.emplace_back([&, i]() {
-        good[i] = (fasta ? parse_fasta_range(cut[i], cut[i + 1], &sets[i]) : parse_fastq_range(cut[i], cut[i + 1], &sets[i])) ? 1 : 0;
-      });
-    for (auto& th : pool) th.join();
+    {
+      std::vector<std::thread> pool;
+      for (size_t i = 0; i < parts; ++i)
+        pool.emplace_back([&, i]() {
+          good[i] = (fasta ? scan_fasta_range(cut[i], cut[i + 1], cnt[i]) : scan_fastq_range(cut[i], cut[i + 1], cnt[i])) ? 1 : 0;
+        });
+      for (auto& th : pool) th.join();
+    }
     for (size_t i = 0; i < parts; ++i) ok = ok && good[i];
     if (ok) {
-      // concatenate in place, every part copied by its own thread
       std::vector<size_t> n0(parts + 1, 0), b0(parts + 1, 0);
       for (size_t i = 0; i < parts; ++i) {
-        n0[i + 1] = n0[i] + sets[i].names.size();
-        b0[i + 1] = b0[i] + sets[i].bases.size();
+        n0[i + 1] = n0[i] + cnt[i].records;
+        b0[i + 1] = b0[i] + cnt[i].bases;
       }
+      const bool quals = fastq && out->keep_quals;
       out->names.assign(n0[parts], std::string());
       out->comments.assign(n0[parts], std::string());
-      out->bases.assign(b0[parts], '\0');
-      out->quals.assign(fastq && out->keep_quals ? b0[parts] : 0, '\0');
       out->off.assign(n0[parts] + 1, 0);
-      std::vector<std::thread> movers;
-      for (size_t i = 0; i < parts; ++i)
-        movers.emplace_back([&, i]() {
-          ReadSet& s = sets[i];
-          if (!s.bases.empty()) memcpy(&out->bases[b0[i]], s.bases.data(), s.bases.size());
-          if (!s.quals.empty()) memcpy(&out->quals[b0[i]], s.quals.data(), s.quals.size());
-          for (size_t k = 0; k < s.names.size(); ++k) {
-            out->names[n0[i] + k] = std::move(s.names[k]);
-            out->comments[n0[i] + k] = std::move(s.comments[k]);
-            out->off[n0[i] + k + 1] = b0[i] + s.off[k + 1];
-          }
-          std::string().swap(s.bases);
-        });
-      for (auto& th : movers) th.join();
+      out->quals.release();
+      ok = out->bases.resize_uninit(b0[parts]) && (!quals || out->quals.resize_uninit(b0[parts]));
+      if (ok) {
+        // pass 2: every range fills its own slice (and faults in its own pages)
+        std::vector<std::thread> pool;
+        for (size_t i = 0; i < parts; ++i)
+          pool.emplace_back([&, i]() {
+            FillSink fs{out, n0[i], b0[i], quals};
+            out->off[n0[i]] = b0[i];
+            if (fasta) scan_fasta_range(cut[i], cut[i + 1], fs);
+            else scan_fastq_range(cut[i], cut[i + 1], fs);
+          });
+        for (auto& th : pool) th.join();
+      }
     }
   }
   munmap((void*)base, size);

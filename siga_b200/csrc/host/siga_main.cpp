@@ -275,7 +275,7 @@ bool write_asqg(const std::string& path, const CommonOpts& o, const ReadSet& rs,
         *text += "VT\t";
         *text += rs.names[i];
         *text += '\t';
-        text->append(rs.bases, rs.off[i], rs.off[i + 1] - rs.off[i]);
+        text->append(rs.bases.data() + rs.off[i], rs.off[i + 1] - rs.off[i]);
         *text += ed.substring[k] ? "\tSS:i:1" : "\tSS:i:0";
         append_comment_tags(rs.comments[i], text);
         *text += '\n';
@@ -773,7 +773,7 @@ int cmd_rmdup(int argc, char** argv) {
     *dst += " NumDuplicates=";
     append_uint(dst, copies);
     *dst += '\n';
-    dst->append(rs.bases, rs.off[q], rs.off[q + 1] - rs.off[q]);
+    dst->append(rs.bases.data() + rs.off[q], rs.off[q + 1] - rs.off[q]);
     *dst += '\n';
   }
   for (int k = 0; k < 2; ++k) {
@@ -836,11 +836,11 @@ bool write_corrected(const std::string& path, bool gz, int threads, int gzip_lev
         *text += rs.comments[i];
       }
       *text += '\n';
-      text->append(rs.bases, rs.off[i], rs.off[i + 1] - rs.off[i]);
+      text->append(rs.bases.data() + rs.off[i], rs.off[i + 1] - rs.off[i]);
       *text += '\n';
       if (fastq) {
         *text += "+\n";
-        text->append(rs.quals, rs.off[i], rs.off[i + 1] - rs.off[i]);
+        text->append(rs.quals.data() + rs.off[i], rs.off[i + 1] - rs.off[i]);
         *text += '\n';
       }
     }
@@ -1145,7 +1145,7 @@ int cmd_match(int argc, char** argv) {
         text += part == 0 ? "VT\t0\t" : "VT\t1\t";
         text += rs.names[i];
         text += '\t';
-        text.append(rs.bases, rs.off[i], len);
+        text.append(rs.bases.data() + rs.off[i], len);
         text += '\t';
         append_uint(&text, n);
         text += '\n';
