@@ -211,6 +211,132 @@ void write_block(BitWriter& bw, const unsigned char* p, size_t n, bool last, con
   bw.put(bp.code[256], bp.len[256]);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Greedy single-probe LZ77 for record text with repeated fields (the ED lines of an ASQG file): one hash-table probe
+// per position, matches of 4..258 bytes within the 32 KB window, no lazy evaluation, no chains.
+// ---------------------------------------------------------------------------------------------------------
+const int kHashBits = 15;
+const uint32_t kNoPosition = 0xffffffffu;
+
+inline uint32_t load32(const unsigned char* p) {
+  uint32_t v;
+  memcpy(&v, p, 4);
+  return v;
+}
+
+// token: literal byte, or 0x80000000 | (length - 3) << 15 | (distance - 1)
+inline void length_symbol_slow(uint32_t l3, int* sym, int* nbits, uint32_t* extra) {  // l3 = length - 3 in [0, 255]
+  if (l3 < 8) {
+    *sym = 257 + (int)l3;
+    *nbits = 0;
+    *extra = 0;
+  } else if (l3 == 255) {
+    *sym = 285;
+    *nbits = 0;
+    *extra = 0;
+  } else {
+    const int nb = 31 - __builtin_clz(l3);
+    *sym = 257 + 4 * (nb - 1) + (int)((l3 >> (nb - 2)) & 3u);
+    *nbits = nb - 2;
+    *extra = l3 & ((1u << (nb - 2)) - 1u);
+  }
+}
+struct LengthTable {
+  uint16_t sym[256];
+  uint8_t nbits[256];
+  uint8_t extra[256];
+  LengthTable() {
+    for (uint32_t l3 = 0; l3 < 256; ++l3) {
+      int s, nb;
+      uint32_t ex;
+      length_symbol_slow(l3, &s, &nb, &ex);
+      sym[l3] = (uint16_t)s;
+      nbits[l3] = (uint8_t)nb;
+      extra[l3] = (uint8_t)ex;
+    }
+  }
+};
+const LengthTable kLength;
+inline void length_symbol(uint32_t l3, int* sym, int* nbits, uint32_t* extra) {
+  *sym = kLength.sym[l3];
+  *nbits = kLength.nbits[l3];
+  *extra = kLength.extra[l3];
+}
+inline void distance_symbol(uint32_t d1, int* sym, int* nbits, uint32_t* extra) {  // d1 = distance - 1 in [0, 32767]
+  if (d1 < 4) {
+    *sym = (int)d1;
+    *nbits = 0;
+    *extra = 0;
+  } else {
+    const int nb = 31 - __builtin_clz(d1);
+    *sym = 2 * nb + (int)((d1 >> (nb - 1)) & 1u);
+    *nbits = nb - 1;
+    *extra = d1 & ((1u << (nb - 1)) - 1u);
+  }
+}
+
+struct LzBlock {
+  std::vector<uint32_t> tokens;  // kBlock + 1 slots, n_tokens used
+  size_t n_tokens;
+  uint32_t lfreq[286], dfreq[30];
+  uint64_t extra_bits;
+};
+
+// Parses data[from, to) into tokens; matches may reach back into data[0, from) (one deflate stream per member).
+void lz_parse(const unsigned char* data, size_t from, size_t to, size_t n, uint32_t* table, LzBlock* blk) {
+  if (blk->tokens.size() < kBlock + 1) blk->tokens.resize(kBlock + 1);
+  uint32_t* tok = blk->tokens.data();
+  size_t nt = 0;
+  memset(blk->lfreq, 0, sizeof(blk->lfreq));
+  memset(blk->dfreq, 0, sizeof(blk->dfreq));
+  blk->extra_bits = 0;
+  size_t i = from;
+  while (i < to) {
+    if (i + 4 <= n) {
+      const uint32_t v = load32(data + i);
+      const uint32_t h = (v * 2654435761u) >> (32 - kHashBits);
+      const uint32_t cand = table[h];
+      table[h] = (uint32_t)i;
+      if (cand != kNoPosition && i - cand <= 32768 && load32(data + cand) == v) {
+        const size_t limit = std::min<size_t>(258, to - i);  // a match does not cross the block end
+        size_t len = 4;
+        while (len + 8 <= limit) {  // eight bytes per comparison
+          uint64_t x, y;
+          memcpy(&x, data + cand + len, 8);
+          memcpy(&y, data + i + len, 8);
+          if (x != y) {
+            len += (size_t)(__builtin_ctzll(x ^ y) >> 3);
+            goto extended;
+          }
+          len += 8;
+        }
+        while (len < limit && data[cand + len] == data[i + len]) ++len;
+      extended:
+        if (len <= limit) {
+          int sym, nb;
+          uint32_t ex;
+          length_symbol((uint32_t)len - 3, &sym, &nb, &ex);
+          blk->lfreq[sym]++;
+          blk->extra_bits += (uint64_t)nb;
+          distance_symbol((uint32_t)(i - cand) - 1, &sym, &nb, &ex);
+          blk->dfreq[sym]++;
+          blk->extra_bits += (uint64_t)nb;
+          tok[nt++] = 0x80000000u | (((uint32_t)len - 3) << 15) | ((uint32_t)(i - cand) - 1);
+          // index a second position inside the match (cheap, and it is what later records tend to repeat from)
+          if (i + len / 2 + 4 <= n) table[(load32(data + i + len / 2) * 2654435761u) >> (32 - kHashBits)] = (uint32_t)(i + len / 2);
+          i += len;
+          continue;
+        }
+      }
+    }
+    blk->lfreq[data[i]]++;
+    tok[nt++] = data[i];
+    ++i;
+  }
+  blk->lfreq[256]++;
+  blk->n_tokens = nt;
+}
+
 }  // namespace
 
 std::string gzip_member_huffman(const char* data, size_t n) {
@@ -243,6 +369,89 @@ std::string gzip_member_huffman(const char* data, size_t n) {
   const uint32_t tail[2] = {(uint32_t)crc, (uint32_t)(n & 0xffffffffu)};
   memcpy(end, tail, 8);
   out.resize(10 + body + 8);
+  return out;
+}
+
+}  // namespace sgxhost
+
+namespace sgxhost {
+
+std::string gzip_member_lz(const char* data, size_t n) {
+  const unsigned char* p = (const unsigned char*)data;
+  std::string out(10 + n / 3 + 65536, '\0');
+  static const unsigned char header[10] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 4 /* fastest */, 3 /* unix */};
+  memcpy(&out[0], header, 10);
+  size_t pos = 10;  // bytes of `out` that are final
+  uint64_t pend_acc = 0;
+  int pend_n = 0;   // bits of the last, partial byte carried from block to block
+  std::vector<uint32_t> table((size_t)1 << kHashBits, kNoPosition);
+  LzBlock blk;
+  static const int order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+  const size_t n_blocks = n ? (n + kBlock - 1) / kBlock : 1;
+  for (size_t b = 0; b < n_blocks; ++b) {
+    const size_t from = b * kBlock, to = std::min(n, from + kBlock);
+    lz_parse(p, from, to, n, table.data(), &blk);
+    uint8_t llen[286], dlen[30], cllen[19];
+    uint16_t lcode[286], dcode[30], clcode[19];
+    code_lengths(blk.lfreq, 286, 15, llen);
+    canonical_codes(llen, 286, lcode);
+    code_lengths(blk.dfreq, 30, 15, dlen);
+    canonical_codes(dlen, 30, dcode);
+    uint32_t clfreq[19];
+    memset(clfreq, 0, sizeof(clfreq));
+    for (int i = 0; i < 286; ++i) clfreq[llen[i]]++;
+    for (int i = 0; i < 30; ++i) clfreq[dlen[i]]++;
+    code_lengths(clfreq, 19, 7, cllen);
+    canonical_codes(cllen, 19, clcode);
+    uint64_t bits = 3 + 5 + 5 + 4 + 19 * 3 + blk.extra_bits;
+    for (int i = 0; i < 286; ++i) bits += cllen[llen[i]] + (uint64_t)blk.lfreq[i] * llen[i];
+    for (int i = 0; i < 30; ++i) bits += cllen[dlen[i]] + (uint64_t)blk.dfreq[i] * dlen[i];
+    const size_t need = pos + (size_t)((bits + pend_n + 7) / 8) + 16;
+    if (out.size() < need) out.resize(std::max(need, out.size() + out.size() / 2));
+    BitWriter bw((unsigned char*)&out[pos]);
+    bw.acc = pend_acc;
+    bw.n = pend_n;
+    bw.put(b + 1 == n_blocks ? 1u : 0u, 1);
+    bw.put(2u, 2);
+    bw.put(286 - 257, 5);
+    bw.put(30 - 1, 5);
+    bw.put(19 - 4, 4);
+    for (int i = 0; i < 19; ++i) bw.put(cllen[order[i]], 3);
+    for (int i = 0; i < 286; ++i) bw.put(clcode[llen[i]], cllen[llen[i]]);
+    for (int i = 0; i < 30; ++i) bw.put(clcode[dlen[i]], cllen[dlen[i]]);
+    for (size_t ti = 0; ti < blk.n_tokens; ++ti) {
+      const uint32_t t = blk.tokens[ti];
+      if (!(t & 0x80000000u)) {
+        bw.put(lcode[t], llen[t]);
+      } else {
+        int sym, nb, dsym, dnb;
+        uint32_t ex, dex;
+        length_symbol((t >> 15) & 0xffu, &sym, &nb, &ex);
+        distance_symbol(t & 0x7fffu, &dsym, &dnb, &dex);
+        // length code + extra (<= 20 bits), distance code + extra (<= 28 bits): 48 bits at most in one append
+        uint64_t v = lcode[sym];
+        int k = llen[sym];
+        v |= (uint64_t)ex << k;
+        k += nb;
+        v |= (uint64_t)dcode[dsym] << k;
+        k += dlen[dsym];
+        v |= (uint64_t)dex << k;
+        k += dnb;
+        bw.put(v, k);
+      }
+    }
+    bw.put(lcode[256], llen[256]);
+    pos = (size_t)(bw.p - (unsigned char*)&out[0]);
+    pend_acc = bw.acc;
+    pend_n = bw.n;
+  }
+  if (pend_n > 0) out[pos++] = (char)(pend_acc & 0xff);
+  uLong crc = crc32(0L, Z_NULL, 0);
+  for (size_t b = 0; b < n; b += (size_t)1 << 30) crc = crc32(crc, p + b, (uInt)std::min<size_t>((size_t)1 << 30, n - b));
+  const uint32_t tail[2] = {(uint32_t)crc, (uint32_t)(n & 0xffffffffu)};
+  if (out.size() < pos + 8) out.resize(pos + 8);
+  memcpy(&out[pos], tail, 8);
+  out.resize(pos + 8);
   return out;
 }
 

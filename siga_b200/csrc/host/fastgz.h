@@ -14,6 +14,10 @@ namespace sgxhost {
 // One complete gzip member (header, deflate stream, CRC-32, size) that decodes to data[0, n).
 std::string gzip_member_huffman(const char* data, size_t n);
 
+// The same with a greedy single-probe LZ77 match finder in front (4..258-byte matches within 32 KB): for record text
+// with repeated fields (the ED lines), where literal-only coding would give away a third of the ratio.
+std::string gzip_member_lz(const char* data, size_t n);
+
 }  // namespace sgxhost
 
 #endif  // SGX_HOST_FASTGZ_H_

@@ -66,14 +66,16 @@ class GzChunkWriter {
     if (f_) fclose(f_);
   }
   bool ok() const { return f_ != NULL; }
-  // produce(i, &text) fills the text of chunk i in [0, n); chunks are emitted in index order.  literal(i) says whether
-  // chunk i is sequence-like text, which goes through the literal-only encoder (fastgz.h) instead of zlib.
+  // produce(i, &text) fills the text of chunk i in [0, n); chunks are emitted in index order.  encoder(i) picks the
+  // member encoder of chunk i: zlib at the configured level, or one of the two writers of fastgz.h (literal-only for
+  // sequence records, greedy LZ77 for records with repeated fields).
+  enum Encoder { kZlib = 0, kLiteral = 1, kFastLz = 2 };
   template <class F>
   bool write_chunks(size_t n, F produce) {
-    return write_chunks(n, produce, [](size_t) { return false; });
+    return write_chunks(n, produce, [](size_t) { return kZlib; });
   }
   template <class F, class L>
-  bool write_chunks(size_t n, F produce, L literal) {
+  bool write_chunks(size_t n, F produce, L encoder) {
     // a pool of workers takes chunk indices in order; the calling thread writes finished members in index order while
     // later chunks are still being produced (at most 2 x threads chunks are in flight, which bounds the memory)
     const size_t window = 2 * (size_t)threads_;
@@ -94,7 +96,9 @@ class GzChunkWriter {
         }
         std::string text;
         produce(i, &text);
-        std::string gz = literal(i) ? gzip_member_huffman(text.data(), text.size()) : deflate_member(text, level_);
+        const int enc = encoder(i);
+        std::string gz = enc == kLiteral ? gzip_member_huffman(text.data(), text.size())
+                         : enc == kFastLz ? gzip_member_lz(text.data(), text.size()) : deflate_member(text, level_);
         {
           std::lock_guard<std::mutex> lk(mu);
           slot[i % window].swap(gz);
@@ -202,8 +206,8 @@ struct CommonOpts {
   int threads = 0;     // host-side text / gzip work; 0 = all hardware threads (the search itself runs on the GPU)
   int device = 0;
   int gzip_level = 1;  // zlib level of the .gz members that go through zlib
-  bool gzip_fast = true;  // sequence records (VT lines, corrected reads) use the literal-only encoder; --gzip-level N
-                          // turns that off and sends everything through zlib at level N
+  bool gzip_fast = true;  // sequence records (VT lines, corrected reads) use the literal-only encoder and ED records the
+                          // greedy-LZ77 one (fastgz.h); --gzip-level N sends everything through zlib at level N
   int gpus = 1;        // --gpus N: one forked process per GPU (devices device .. device + N - 1)
   bool help = false;
 };
@@ -308,7 +312,10 @@ bool write_asqg(const std::string& path, const CommonOpts& o, const ReadSet& rs,
         *text += (g.af & SGX_AF_QUERYCOMP) ? " 1 0\n" : " 0 0\n";
       }
     }
-  }, [&](size_t ci) { return o.gzip_fast && ci >= n_ht && ci < n_ht + n_vt; });  // VT records are mostly read sequence
+  }, [&](size_t ci) {  // VT records are mostly read sequence; HT / ED records repeat their fields
+    if (!o.gzip_fast) return GzChunkWriter::kZlib;
+    return ci >= n_ht && ci < n_ht + n_vt ? GzChunkWriter::kLiteral : GzChunkWriter::kFastLz;
+  });
 }
 
 bool append_file(FILE* dst, const std::string& path) {
@@ -850,7 +857,7 @@ bool write_corrected(const std::string& path, bool gz, int threads, int gzip_lev
     GzChunkWriter w(path, (unsigned)threads, gzip_level);
     return w.ok() && w.write_chunks(std::max<size_t>(n_chunks, 1), [&](size_t ci, std::string* text) {
       if (ci < n_chunks) produce(ci, text);
-    }, [&](size_t) { return gzip_fast; });
+    }, [&](size_t) { return gzip_fast ? GzChunkWriter::kLiteral : GzChunkWriter::kZlib; });
   }
   FILE* f = fopen(path.c_str(), "wb");
   bool good = f != nullptr;

@@ -333,15 +333,30 @@ def test_literal_only_gzip_writer_round_trips(tmp_path):
     for k in range(12):  # random lengths around the block size, random alphabets
         n = int(rng.integers(1, 3 * 262144))
         files["fuzz%d" % k] = rng.integers(0, int(rng.integers(1, 257)), n, dtype=np.uint8).tobytes()
+    # inputs for the LZ77 variant: repeated phrases, repeats beyond the 32 KB window, maximal matches, ED-like records
+    phrases = [rng.integers(65, 91, int(rng.integers(1, 400)), dtype=np.uint8).tobytes() for _ in range(40)]
+    files["phrases"] = b"".join(phrases[int(i)] for i in rng.integers(0, 40, 6000))
+    far = rng.integers(0, 4, 50000, dtype=np.uint8).tobytes()
+    files["far_repeats"] = far + b"x" * 40000 + far + b"A" * 3000 + far
+    files["ed"] = b"".join(b"ED\tr%d r%d %d 149 150 0 %d 150 %d 0\n" % (rng.integers(3e6), rng.integers(3e6), a, 149 - a, rng.integers(2))
+                           for a in rng.integers(0, 105, 60000))
+    files["three"] = b"ACG"
     for name, data in files.items():
         (tmp_path / name).write_bytes(data)
-    r = subprocess.run([str(exe)] + [str(tmp_path / n) for n in files], capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr
-    for name, data in files.items():
-        blob = (tmp_path / (name + ".gz")).read_bytes()
-        assert gzip.decompress(blob) == data, name
-        d = zlib.decompressobj(31)
-        assert d.decompress(blob) == data and d.eof and d.unused_data == b"", name
-    # within a few percent of zlib level 1 on sequence records
-    z = zlib.compressobj(1, zlib.DEFLATED, 31)
-    assert len((tmp_path / "vt.gz").read_bytes()) < 1.05 * len(z.compress(files["vt"]) + z.flush())
+    sizes = {}
+    for mode in ([], ["lz"]):  # literal-only encoder, then the greedy-LZ77 one
+        r = subprocess.run([str(exe)] + mode + [str(tmp_path / n) for n in files], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        for name, data in files.items():
+            blob = (tmp_path / (name + ".gz")).read_bytes()
+            assert gzip.decompress(blob) == data, (mode, name)
+            d = zlib.decompressobj(31)
+            assert d.decompress(blob) == data and d.eof and d.unused_data == b"", (mode, name)
+            sizes[(bool(mode), name)] = len(blob)
+
+    def zlib1(data):
+        z = zlib.compressobj(1, zlib.DEFLATED, 31)
+        return len(z.compress(data) + z.flush())
+    # within a few percent of zlib level 1: literal-only on sequence records, LZ77 on ED records
+    assert sizes[(False, "vt")] < 1.05 * zlib1(files["vt"])
+    assert sizes[(True, "ed")] < 1.05 * zlib1(files["ed"])
