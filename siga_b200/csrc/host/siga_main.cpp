@@ -11,6 +11,7 @@
 // -t/--threads only sizes the host-side output formatting/compression pool; -c/--log4cxx and -s/--ini are accepted
 // and ignored (there is no log4cxx here).  The per-thread .hits.gz files of the reference are an internal detail
 // nothing downstream reads and are not produced.
+#include <fcntl.h>
 #include <getopt.h>
 #include <sys/wait.h>
 #include <unistd.h>
@@ -326,6 +327,37 @@ bool append_file(FILE* dst, const std::string& path) {
   size_t k;
   while (ok && (k = fread(buf.data(), 1, buf.size(), f)) > 0) ok = fwrite(buf.data(), 1, k, dst) == k;
   fclose(f);
+  return ok;
+}
+
+// Writes the strings back to back into `path`, every string by its own thread at its own offset (the copy into the page
+// cache is what a single writer spends its time on at hundreds of MB).
+bool write_parts_parallel(const std::string& path, const std::vector<std::string>& parts) {
+  const int fd = open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+  if (fd < 0) return false;
+  std::vector<uint64_t> at(parts.size() + 1, 0);
+  for (size_t i = 0; i < parts.size(); ++i) at[i + 1] = at[i] + parts[i].size();
+  std::vector<char> good(parts.size(), 1);
+  std::vector<std::thread> pool;
+  for (size_t i = 0; i < parts.size(); ++i)
+    pool.emplace_back([&, i]() {
+      const char* p = parts[i].data();
+      size_t left = parts[i].size();
+      uint64_t off = at[i];
+      while (left > 0) {
+        const ssize_t k = pwrite(fd, p, left, (off_t)off);
+        if (k <= 0) {
+          good[i] = 0;
+          return;
+        }
+        p += k;
+        left -= (size_t)k;
+        off += (uint64_t)k;
+      }
+    });
+  for (auto& th : pool) th.join();
+  bool ok = close(fd) == 0;
+  for (char g : good) ok = ok && g;
   return ok;
 }
 
@@ -729,6 +761,7 @@ int cmd_rmdup(int argc, char** argv) {
   const double t0 = now_s();
   LoadedInput in;
   if (!load_input(input, output, o.device, &in)) return -1;
+  const double t_load = now_s();
   ReadSet& rs = in.rs;
   std::vector<uint8_t>&runs = in.runs, &rruns = in.rruns;
   std::vector<uint32_t>&sai = in.sai, &rsai = in.rsai;
@@ -749,45 +782,58 @@ int cmd_rmdup(int argc, char** argv) {
   rc = sgx_overlap_batch(ctx, fwd, rev, reads, 0, rs.size(), max_len, /*irreducible=*/0, /*rc=*/1, &hits);
   if (rc != SGX_OK) return fail(ctx, "sgx_overlap_batch", rc);
   info("processed %zu sequences; device %.1f ms", rs.size(), hits.ms_total);
+  const double t_gpu = now_s();
 
-  std::string keep, dups;
-  keep.reserve(rs.bases.size() + rs.size() * 48);
-  uint64_t n_dups = 0;
-  for (size_t q = 0; q < rs.size(); ++q) {
-    const std::string& qn = rs.names[q];
-    uint64_t copies = 0;
-    bool contained = hits.substring[q] != 0;
-    for (uint64_t b = hits.block_off[q]; b < hits.block_off[q + 1]; ++b) {
-      const sgx_block& blk = hits.blocks[b];
-      if (blk.af != 0 && blk.af != (SGX_AF_TARGETREV | SGX_AF_QUERYCOMP)) continue;
-      const std::vector<uint32_t>& sa = (blk.af & SGX_AF_TARGETREV) ? rsai : sai;
-      copies += blk.capped[1] - blk.capped[0] + 1;
-      for (uint64_t j = blk.capped[0]; j <= blk.capped[1] && !contained; ++j) {
-        const std::string& tn = rs.names[sa[j]];
-        if (tn != qn && !(qn < tn)) contained = true;  // an identical / reverse-complement read with a smaller name stays
-      }
-    }
-    std::string* dst = contained ? &dups : &keep;
-    *dst += '>';
-    *dst += qn;
-    if (contained) {
-      *dst += ",seqrank=";
-      append_uint(dst, q);
-      ++n_dups;
-    }
-    *dst += ' ';
-    *dst += qn;
-    *dst += " NumDuplicates=";
-    append_uint(dst, copies);
-    *dst += '\n';
-    dst->append(rs.bases.data() + rs.off[q], rs.off[q + 1] - rs.off[q]);
-    *dst += '\n';
+  // records are formatted per range of reads on all threads; both files keep the input order
+  if (o.threads <= 0) o.threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  const size_t n_parts = std::max<size_t>(1, std::min<size_t>((size_t)o.threads, (rs.size() + 65535) / 65536));
+  std::vector<std::string> keep(n_parts), dups(n_parts);
+  std::vector<uint64_t> part_dups(n_parts, 0);
+  {
+    std::vector<std::thread> pool;
+    for (size_t part = 0; part < n_parts; ++part)
+      pool.emplace_back([&, part]() {
+        const size_t q0 = rs.size() * part / n_parts, q1 = rs.size() * (part + 1) / n_parts;
+        keep[part].reserve((size_t)(rs.off[q1] - rs.off[q0]) + (q1 - q0) * 48);
+        for (size_t q = q0; q < q1; ++q) {
+          const std::string& qn = rs.names[q];
+          uint64_t copies = 0;
+          bool contained = hits.substring[q] != 0;
+          for (uint64_t b = hits.block_off[q]; b < hits.block_off[q + 1]; ++b) {
+            const sgx_block& blk = hits.blocks[b];
+            if (blk.af != 0 && blk.af != (SGX_AF_TARGETREV | SGX_AF_QUERYCOMP)) continue;
+            const std::vector<uint32_t>& sa = (blk.af & SGX_AF_TARGETREV) ? rsai : sai;
+            copies += blk.capped[1] - blk.capped[0] + 1;
+            for (uint64_t j = blk.capped[0]; j <= blk.capped[1] && !contained; ++j) {
+              const std::string& tn = rs.names[sa[j]];
+              if (tn != qn && !(qn < tn)) contained = true;  // an identical / reverse-complement read with a smaller name stays
+            }
+          }
+          std::string* dst = contained ? &dups[part] : &keep[part];
+          *dst += '>';
+          *dst += qn;
+          if (contained) {
+            *dst += ",seqrank=";
+            append_uint(dst, q);
+            ++part_dups[part];
+          }
+          *dst += ' ';
+          *dst += qn;
+          *dst += " NumDuplicates=";
+          append_uint(dst, copies);
+          *dst += '\n';
+          dst->append(rs.bases.data() + rs.off[q], rs.off[q + 1] - rs.off[q]);
+          *dst += '\n';
+        }
+      });
+    for (auto& th : pool) th.join();
   }
+  uint64_t n_dups = 0;
+  for (uint64_t d : part_dups) n_dups += d;
   for (int k = 0; k < 2; ++k) {
     const std::string path = output + (k == 0 ? ".rmdup.fa" : ".rmdup.dups.fa");
-    FILE* f = fopen(path.c_str(), "wb");
-    const std::string& text = k == 0 ? keep : dups;
-    if (!f || fwrite(text.data(), 1, text.size(), f) != text.size() || fclose(f) != 0) {
+    const bool good = write_parts_parallel(path, k == 0 ? keep : dups);
+    if (!good) {
       fprintf(stderr, "ERROR siga - Failed to create FASTA %s\n", path.c_str());
       return -1;
     }
@@ -798,7 +844,8 @@ int cmd_rmdup(int argc, char** argv) {
   sgx_fm_free(rev);
   sgx_reads_free(reads);
   sgx_shutdown(ctx);
-  info("wall: %.3f sec", now_s() - t0);
+  const double t1 = now_s();
+  info("wall: %.3f sec (load %.3f, gpu %.3f, write %.3f)", t1 - t0, t_load - t0, t_gpu - t_load, t1 - t_gpu);
   return 0;
 }
 
@@ -833,7 +880,7 @@ bool write_corrected(const std::string& path, bool gz, int threads, int gzip_lev
   const size_t chunk = 1 << 16, n_chunks = (count + chunk - 1) / chunk;
   auto produce = [&](size_t ci, std::string* text) {
     const size_t b = first + ci * chunk, e = std::min(first + count, b + chunk);
-    text->reserve((e - b) * (fastq ? 400 : 200));
+    text->reserve(text->size() + (size_t)(rs.off[e] - rs.off[b]) * (fastq ? 2 : 1) + (e - b) * 64);
     for (size_t i = b; i < e; ++i) {
       if (!valid[i - first]) continue;
       *text += fastq ? '@' : '>';
@@ -859,18 +906,21 @@ bool write_corrected(const std::string& path, bool gz, int threads, int gzip_lev
       if (ci < n_chunks) produce(ci, text);
     }, [&](size_t) { return gzip_fast ? GzChunkWriter::kLiteral : GzChunkWriter::kZlib; });
   }
-  FILE* f = fopen(path.c_str(), "wb");
-  bool good = f != nullptr;
-  for (size_t base = 0; base < n_chunks && good; base += (size_t)threads) {
-    const size_t m = std::min<size_t>((size_t)threads, n_chunks - base);
-    std::vector<std::string> text(m);
+  // plain file: one range of reads per thread, formatted and then written at its own offset
+  const size_t n_parts = std::max<size_t>(1, std::min<size_t>((size_t)threads, n_chunks));
+  std::vector<std::string> text(n_parts);
+  {
     std::vector<std::thread> pool;
-    for (size_t t = 0; t < m; ++t) pool.emplace_back([&, t]() { produce(base + t, &text[t]); });
+    for (size_t t = 0; t < n_parts; ++t)
+      pool.emplace_back([&, t]() {
+        const size_t c0 = n_chunks * t / n_parts, c1 = n_chunks * (t + 1) / n_parts;
+        const size_t r0 = first + c0 * chunk, r1 = std::min(first + count, first + c1 * chunk);
+        if (r1 > r0) text[t].reserve((size_t)(rs.off[r1] - rs.off[r0]) * (fastq ? 2 : 1) + (r1 - r0) * 64);
+        for (size_t ci = c0; ci < c1; ++ci) produce(ci, &text[t]);
+      });
     for (auto& th : pool) th.join();
-    for (size_t t = 0; t < m && good; ++t) good = fwrite(text[t].data(), 1, text[t].size(), f) == text[t].size();
   }
-  if (f && fclose(f) != 0) good = false;
-  return good;
+  return write_parts_parallel(path, text);
 }
 
 // `siga correct` (src/correct.cpp:22-59, CorrectProcessor::process src/correct_processor.cpp:269-316): loads PREFIX.bwt
