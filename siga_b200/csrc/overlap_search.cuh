@@ -121,7 +121,12 @@ ov_search_quad_kernel(FmPair fm, ReadsView reads, uint64_t first, uint64_t count
         below += dd;
         lo1 = lo1 + below;
         hi1 = lo1 + (Uc - Lc) - 1;
-        const IdxT pc = c == 1 ? pc1 : (c == 2 ? pc2 : (c == 3 ? pc3 : pc4));
+        // a chain of selects on registers: the nested form compiles to a branch tree, which diverges whenever the quads of
+        // a warp step different symbols (a register-indexed constant load instead was slower, profiles/r1h_summary.md)
+        IdxT pc = pc1;
+        pc = c == 2 ? pc2 : pc;
+        pc = c == 3 ? pc3 : pc;
+        pc = c == 4 ? pc4 : pc;
         lo0 = pc + Lc;
         hi0 = pc + Uc - 1;
         --i;
