@@ -22,8 +22,8 @@ pytestmark = [pytest.mark.skipif(not os.path.isfile(CLI), reason="build/siga_hos
               pytest.mark.skipif(not refrun.have_ref(), reason="compiled reference (oracle/_ref/siga) not present")]
 
 
-def _cli(args, cwd, ok=True):
-    r = subprocess.run([CLI] + args, cwd=cwd, capture_output=True, text=True)
+def _cli(args, cwd, ok=True, env=None):
+    r = subprocess.run([CLI] + args, cwd=cwd, capture_output=True, text=True, env=env)
     assert (r.returncode == 0) == ok, r.stderr[-2000:]
     return r
 
@@ -43,9 +43,11 @@ def test_correct_front_end_single_and_sharded_equal_reference_file(fastq):
         want = open(os.path.join(ref, "reads.ec.fa"), "rb").read()
         assert 0 < want.count(b"\n") // (4 if fastq else 2) < len(reads)
         opts = ["-k", "23", "-x", "2", "-i", "4", "-O", "2", "-p", os.path.join(ref, "reads")]
-        for extra, out in (([], "reads.ec.fa"), (["--gpus", "2"], "reads.ec.fa"), (["--gpus", "3", "-o", "x.fa.gz"], "x.fa.gz"),
-                           (["--kmer-size=23", "--outfile", "y.fa"], "y.fa")):
-            _cli(["correct"] + opts + extra + [src], ours)
+        par = dict(os.environ, SIGA_PARSE_MIN_PARALLEL="1000")  # the multi-threaded in-place reader instead of the serial one
+        for extra, out, env in (([], "reads.ec.fa", None), (["--gpus", "2"], "reads.ec.fa", par),
+                                (["--gpus", "3", "-o", "x.fa.gz"], "x.fa.gz", None),
+                                (["--kmer-size=23", "--outfile", "y.fa"], "y.fa", par)):
+            _cli(["correct"] + opts + extra + [src], ours, env=env)
             path = os.path.join(ours, out)
             got = gzip.open(path, "rb").read() if out.endswith(".gz") else open(path, "rb").read()
             assert got == want, extra
