@@ -1,14 +1,15 @@
 // TEST INFRASTRUCTURE ONLY -- never linked into, loaded by, or shipped with the product (siga_b200/libsiga_b200.so,
 // siga_b200/bin/siga have no CPU path and fail without a B200).
 //
-// A host stand-in for the part of the C ABI (include/siga_b200.h) that `siga overlap`, `siga rmdup` and `siga correct` call, built on the
+// A host stand-in for the part of the C ABI (include/siga_b200.h) that `siga index | overlap | rmdup | correct | match` call, built on the
 // single-lane instantiations in hostemu.cpp.  Linked with the UNMODIFIED front-end sources
 // (siga_b200/csrc/host/siga_main.cpp, seqio.cpp) into build/siga_hostemu, it lets the CPU test-suite run the
 // front-end's own host logic -- option parsing, FASTQ qualities, fix application, ASQG / FASTA formatting, the fork /
-// part file / concatenation path of --gpus N -- against the reference binary without a GPU.  Index construction has no
-// host stand-in: those entry points return SGX_ENODEV here.
+// part file / concatenation path of --gpus N -- against the reference binary without a GPU.  The index build is a
+// brute-force suffix sort (small inputs); the NCCL-sharded build has no host stand-in and returns SGX_ENODEV.
 #include "hostemu.cpp"
 
+#include <algorithm>
 #include <string>
 
 struct sgx_ctx {
@@ -269,8 +270,82 @@ int sgx_fm_count(sgx_ctx* ctx, const sgx_fm* fm, const char* ascii, const uint64
 }
 
 // ---- no host stand-in
-int sgx_index_build(sgx_ctx* ctx, const sgx_reads*, int, int, sgx_index_out*) { return no_device(ctx, "sgx_index_build"); }
-void sgx_index_out_free(sgx_index_out*) {}
+// `siga index`: brute-force suffix sorting of the two ordering models (the statement
+// oracle/pyoracle.py checks against the reference's golden vectors), small inputs only.
+//   model B (sais2): plain suffix array of T = R0 $ R1 $ ... with every '$' the smallest symbol and end-of-text smaller still;
+//   model A (sais):  suffixes ordered by (R_i[j:] $, i).
+// BWT symbol of a row = the symbol before the suffix, '$' at a read start; runs are cut at 31 (src/bwt.cpp:16-27).
+int sgx_index_build(sgx_ctx* ctx, const sgx_reads* reads, int order, int reversed, sgx_index_out* out) {
+  if (!ctx || !reads || !out || (order != SGX_ORDER_SAIS && order != SGX_ORDER_SAIS2)) return SGX_EINVAL;
+  const uint64_t n = reads->off.size() - 1;
+  std::vector<uint8_t> text;  // ranks, 0 = '$'
+  std::vector<uint64_t> start(n + 1);
+  std::vector<uint32_t> owner;
+  for (uint64_t i = 0; i < n; ++i) {
+    start[i] = text.size();
+    const uint64_t a = reads->off[i], l = reads->off[i + 1] - a;
+    for (uint64_t j = 0; j < l; ++j) {
+      const char ch = reads->ascii[reversed ? a + l - 1 - j : a + j];
+      text.push_back((uint8_t)(ch == 'A' ? 1 : ch == 'C' ? 2 : ch == 'G' ? 3 : 4));
+      owner.push_back((uint32_t)i);
+    }
+    text.push_back(0);
+    owner.push_back((uint32_t)i);
+  }
+  start[n] = text.size();
+  const uint64_t S = text.size();
+  std::vector<uint64_t> sa(S);
+  for (uint64_t q = 0; q < S; ++q) sa[q] = q;
+  if (order == SGX_ORDER_SAIS2) {
+    std::sort(sa.begin(), sa.end(), [&](uint64_t x, uint64_t y) {
+      const uint64_t m = std::min(S - x, S - y);
+      const int c = memcmp(&text[x], &text[y], m);
+      return c != 0 ? c < 0 : x > y;  // the shorter suffix (end of text) first
+    });
+  } else {
+    std::sort(sa.begin(), sa.end(), [&](uint64_t x, uint64_t y) {
+      const uint64_t ex = start[owner[x] + 1], ey = start[owner[y] + 1];  // one past the read's own '$'
+      const uint64_t m = std::min(ex - x, ey - y);
+      const int c = memcmp(&text[x], &text[y], m);  // both strings end with their '$', so equal prefixes mean equal strings
+      if (c != 0) return c < 0;
+      if (ex - x != ey - y) return ex - x < ey - y;
+      return owner[x] < owner[y];
+    });
+  }
+  std::vector<uint8_t> rle;
+  std::vector<uint32_t> sai;
+  int run_sym = -1, run_len = 0;
+  for (uint64_t k = 0; k < S; ++k) {
+    const uint64_t q = sa[k];
+    const bool at_start = q == start[owner[q]];
+    const int sym = at_start ? 0 : text[q - 1];
+    if (at_start) sai.push_back(owner[q]);
+    if (sym == run_sym && run_len < 31) {
+      ++run_len;
+    } else {
+      if (run_len) rle.push_back((uint8_t)((run_sym << 5) | run_len));
+      run_sym = sym;
+      run_len = 1;
+    }
+  }
+  if (run_len) rle.push_back((uint8_t)((run_sym << 5) | run_len));
+  memset(out, 0, sizeof(*out));
+  out->n_strings = n;
+  out->n_suffixes = S;
+  out->n_runs = rle.size();
+  out->rle = (uint8_t*)malloc(rle.size() ? rle.size() : 1);
+  memcpy(out->rle, rle.data(), rle.size());
+  out->sai = (uint32_t*)malloc((n ? n : 1) * sizeof(uint32_t));
+  memcpy(out->sai, sai.data(), n * sizeof(uint32_t));
+  return SGX_OK;
+}
+void sgx_index_out_free(sgx_index_out* o) {
+  if (!o) return;
+  free(o->rle);
+  free(o->sai);
+  o->rle = nullptr;
+  o->sai = nullptr;
+}
 int sgx_comm_unique_id(uint8_t*) { return SGX_ENODEV; }
 int sgx_comm_init(sgx_ctx* ctx, const uint8_t*, int, int, sgx_comm**) { return no_device(ctx, "sgx_comm_init"); }
 void sgx_comm_free(sgx_comm*) {}

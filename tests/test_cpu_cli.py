@@ -192,3 +192,67 @@ def test_reference_assembler_reads_our_asqg_and_builds_the_same_contigs():
         refrun.run_ref(["assemble", "-m", "40", "-p", "asm", os.path.join(ours, "reads.rmdup.asqg.gz")], ours)
         a, b = contigs(os.path.join(ours, "asm-contigs.fa")), contigs(os.path.join(ref, "asm-contigs.fa"))
         assert a == b and sum(len(c) for c in a) > 4000
+
+
+@pytest.mark.parametrize("algo", ["sais2", "sais"])
+def test_index_front_end_equals_reference_files(algo):
+    """`siga index` host logic (reads in, .bwt/.sai/.rbwt/.rsai writers, -a / -p / --no-forward / --no-reverse) with the
+    brute-force suffix sort of the host stand-in: both ordering models, variable lengths, duplicates, multi-line FASTA."""
+    rng = np.random.default_rng(5)
+    g = synth.random_genome(1200, rng)
+    reads = [r.tobytes().decode()[:int(l)] for r, l in zip(synth.sample_reads(g, 400, 50, rng, err=0.01), rng.integers(8, 51, 400))]
+    for _ in range(40):
+        a, b = rng.integers(0, len(reads), 2)
+        reads[a] = reads[b]
+    with tempfile.TemporaryDirectory() as d:
+        ours, ref = os.path.join(d, "ours"), os.path.join(d, "ref")
+        os.mkdir(ours)
+        os.mkdir(ref)
+        src = os.path.join(d, "reads.fa")
+        with open(src, "w") as f:
+            for i, s in enumerate(reads):
+                f.write(">r%d some comment\n%s\n%s\n" % (i, s[:20], s[20:]) if len(s) > 20 else ">r%d\n%s\n" % (i, s))
+        refrun.run_ref(["index", "-a", algo, src], ref)
+        _cli(["index", "-a", algo, src], ours)
+        for ext in (".bwt", ".rbwt", ".sai", ".rsai"):
+            assert open(os.path.join(ours, "reads" + ext), "rb").read() == open(os.path.join(ref, "reads" + ext), "rb").read(), ext
+        _cli(["index", "-a", algo, "-p", "fwd", "--no-reverse", src], ours)
+        assert sorted(f for f in os.listdir(ours) if f.startswith("fwd")) == ["fwd.bwt", "fwd.sai"]
+        assert open(os.path.join(ours, "fwd.bwt"), "rb").read() == open(os.path.join(ref, "reads.bwt"), "rb").read()
+        _cli(["index", "-a", algo, "-p", "rev", "--no-forward", src], ours)
+        assert sorted(f for f in os.listdir(ours) if f.startswith("rev")) == ["rev.rbwt", "rev.rsai"]
+        assert open(os.path.join(ours, "rev.rsai"), "rb").read() == open(os.path.join(ref, "reads.rsai"), "rb").read()
+        _cli(["index", "-a", "rope", src], ours, ok=False)
+
+
+def test_whole_pipeline_through_the_front_end_gives_the_reference_contigs():
+    """index -> rmdup -> index -> overlap with this repo's front-end (host stand-in of the device), then the reference's
+    assembler: the same contigs as the all-reference pipeline."""
+    rng = np.random.default_rng(43)
+    g = synth.random_genome(5000, rng)
+    reads = synth.sample_reads(g, 2000, 70, rng, err=0.0)
+
+    def contigs(path):
+        comp = bytes.maketrans(b"ACGT", b"TGCA")
+        out = []
+        for rec in open(path, "rb").read().split(b">")[1:]:
+            s = b"".join(rec.split(b"\n")[1:])
+            out.append(min(s, s.translate(comp)[::-1]))
+        return sorted(out)
+
+    with tempfile.TemporaryDirectory() as d:
+        res = {}
+        for who in ("ours", "ref"):
+            w = os.path.join(d, who)
+            os.mkdir(w)
+            src = os.path.join(w, "reads.fa")
+            synth.write_fasta(src, reads)
+            run = (lambda a: _cli(a, w)) if who == "ours" else (lambda a: refrun.run_ref(a, w))
+            run(["index", src])
+            run(["rmdup", src])
+            dedup = os.path.join(w, "reads.rmdup.fa")
+            run(["index", dedup])
+            run(["overlap", "-m", "35", dedup])
+            refrun.run_ref(["assemble", "-m", "35", "-p", "asm", os.path.join(w, "reads.rmdup.asqg.gz")], w)
+            res[who] = contigs(os.path.join(w, "asm-contigs.fa"))
+        assert res["ours"] == res["ref"] and sum(len(c) for c in res["ref"]) > 3000
