@@ -20,6 +20,15 @@ namespace sgx {
 
 static const int kOvThreads = 256;
 
+// Test hooks (tests/test_gpu_parity.py): the named environment variable overrides a sizing decision so that the
+// multi-batch loops, the regrow-and-redo branches and the edge-buffer overflow round run on small inputs.
+static inline uint64_t env_u64(const char* name, uint64_t dflt) {
+  const char* v = getenv(name);
+  if (!v || !*v) return dflt;
+  const unsigned long long x = strtoull(v, nullptr, 10);
+  return x ? (uint64_t)x : dflt;
+}
+
 // Candidate block reduced to what the edge pipeline needs: capped[0] (rows of the '$' block, always < 2^32 because
 // there are < 2^32 reads), overlap length (low 16 bits) and AlignFlags (bits 16..18).
 struct LeanCand {
@@ -174,7 +183,7 @@ struct OvPlan {
     narrow = f->n < 0xffffffffull && r->n < 0xffffffffull && !(fw && fw[0] == '1');  // 32-bit positions suffice
     const uint32_t lmax = rd->max_len;
     find_cap = lmax > m ? lmax - m : 1;
-    out_cap = 4 * find_cap + 4;
+    out_cap = (uint32_t)env_u64("SGX_OUT_CAP", 4 * find_cap + 4);  // hook: small regions force the redo branch
     grid_search = (unsigned)c->sm_count * 8;
     grid_post = (unsigned)c->sm_count * 4;
     ac.list_cap = find_cap + 4 + 28;
@@ -281,6 +290,7 @@ static void overlap_core(OvPlan& pl, OvCore& core, KernelClock& k_search, Kernel
   // batch size: keep candidate + output regions within ~6 GB
   const size_t per_read = ((size_t)4 * pl.find_cap + 4 + pl.out_cap) * sizeof(sgx_block);
   uint64_t batch = std::max<uint64_t>(1024, std::min<uint64_t>((6ull << 30) / per_read, 1u << 20));
+  batch = env_u64("SGX_MAX_BATCH", batch);  // hook: many small batches
   batch = std::min<uint64_t>(batch, std::max<uint64_t>(count, 1));
 
   DevBuf<sgx_block> d_cand(batch * 4 * pl.find_cap), d_contain(batch * 4), d_out(batch * pl.out_cap);
@@ -470,7 +480,7 @@ void overlap_edges_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const
   DevBuf<uint32_t> d_slow(std::max<uint64_t>(count, 1)), d_flags(2);  // [0] n_slow, [1] overflow
   DevBuf<unsigned long long> d_counter(2);
   DevBuf<sgx_edge> d_edges;
-  uint64_t edge_cap = std::max<uint64_t>(count * 8, 1u << 16);
+  uint64_t edge_cap = env_u64("SGX_EDGE_CAP", std::max<uint64_t>(count * 8, 1u << 16));  // hook: overflow round
   uint64_t n_edges = 0, n_slow = 0, search_launches = 0;
 
   for (int round = 0;; ++round) {
@@ -492,6 +502,7 @@ void overlap_edges_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const
       // ---- lean pass over all reads, batch after batch, nothing comes back to the host in between
       const size_t per_read = ((size_t)4 * pl.find_cap + 4) * sizeof(LeanCand) + 32;
       uint64_t batch = std::max<uint64_t>(1024, std::min<uint64_t>((4ull << 30) / per_read, 1u << 21));
+      batch = env_u64("SGX_MAX_BATCH", batch);
       batch = std::min<uint64_t>(batch, std::max<uint64_t>(count, 1));
       DevBuf<LeanCand> d_lean(batch * 4 * pl.find_cap), d_lcontain(batch * 4);
       DevBuf<uint32_t> d_ncand(batch * 4), d_ncontain(batch * 4);
@@ -534,6 +545,7 @@ void overlap_edges_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const
     if (n_slow) {
       const size_t per_item = ((size_t)4 * pl.find_cap + 4 + pl.out_cap) * sizeof(sgx_block);
       uint64_t chunk = std::max<uint64_t>(1024, std::min<uint64_t>((4ull << 30) / per_item, 1u << 20));
+      chunk = env_u64("SGX_MAX_BATCH", chunk);
       chunk = std::min<uint64_t>(chunk, n_slow);
       DevBuf<sgx_block> d_cand(chunk * 4 * pl.find_cap), d_contain(chunk * 4), d_out(chunk * (size_t)pl.out_cap);
       DevBuf<uint32_t> d_ncand(chunk * 4), d_ncontain(chunk * 4), d_nout(chunk);

@@ -40,6 +40,10 @@ def main():
     dist.broadcast(uid, 0)
     comm = ctx.comm_init(uid.cpu().numpy(), rank, world)
     r = ctx.pack_reads(flat, off)
+    # reference hashes of this (config, scale), when tests/golden/make_fullsize.py pinned them
+    import hashlib
+    gp = os.path.join(REPO, "tests", "golden", "fullsize", "%s_%g.json" % (cfg, scale))
+    golden = json.load(open(gp))["index"] if os.path.isfile(gp) else None
     ok = True
     out = {"cfg": cfg, "scale": scale, "reads": int(reads.shape[0]), "read_len": int(reads.shape[1]), "world": world}
     for rev in (False, True):
@@ -61,6 +65,11 @@ def main():
         if rank == 0:
             same = np.array_equal(res.runs, one.runs) and np.array_equal(res.sai, one.sai)
             ok = ok and same
+            if golden is not None:
+                ref_same = (hashlib.sha256(res.runs.tobytes()).hexdigest() == golden["rbwt_runs_sha256" if rev else "bwt_runs_sha256"] and
+                            hashlib.sha256(res.sai.astype("<u4").tobytes()).hexdigest() == golden["rsai_u32_sha256" if rev else "sai_u32_sha256"])
+                out["reference_identical_rev%d" % rev] = bool(ref_same)
+                ok = ok and ref_same
             out["sharded_rev%d" % rev] = dict(zip(["wall_ms", "ms_total", "ms_sort", "ms_bcr", "ms_emit", "ms_merge"],
                                                   [round(float(x), 2) for x in t.tolist()]), identical=bool(same),
                                               run_bytes=int(len(res.runs)), launches=res.stats["launches"])

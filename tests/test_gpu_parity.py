@@ -285,6 +285,9 @@ def test_config1_full_pipeline_bit_exact(ctx):
             ctx.fm_attach_reads(rev, ri.sai, r)
             h = ctx.overlap(fwd, rev, r, 0, 20_000, 45)
             assert h.stats["slow_reads"] == 0  # fixed-length, non-periodic reads all take the read-based path
+            e = ctx.overlap_edges(fwd, rev, r, 0, 20_000, 45, synth.default_name_ranks(20_000))
+            if os.environ.get("SGX_MAX_BATCH"):
+                assert h.stats["search_launches"] > 1 and e.stats["search_launches"] > 1
         finally:
             ctx.free_fm(fwd)
             ctx.free_fm(rev)
@@ -294,6 +297,8 @@ def test_config1_full_pipeline_bit_exact(ctx):
     seqs = [x.tobytes().decode() for x in reads]
     edges = formats.hits_to_edges(names, [100] * 20_000, h.substring, h.block_off, h.blocks, fi.sai, ri.sai)
     assert sorted(formats.asqg_lines(names, seqs, h.substring, edges, 45)) == sorted(ref_asqg)
+    assert sorted(formats.edges_to_ed(names, [100] * 20_000, e.edges)) == sorted(edges)
+    assert np.array_equal(e.substring, h.substring)
 
 
 def test_rejects_bad_input(ctx):
@@ -407,6 +412,64 @@ def test_named_configs_scaled_down_match_reference(ctx, cfg, scale, m):
     ed = formats.edges_to_ed(names, [L] * n, e.edges)
     mine = formats.asqg_lines(names, seqs, e.substring, ed, m)
     assert sorted(mine) == sorted(ref_asqg), (cfg, m, len(mine), len(ref_asqg))
+
+
+# ------------------------------------------------------------ multi-batch loops, regrow-and-redo, edge-buffer overflow
+# parallel::foreach hands the reference's workers `threads * batch` reads at a time (src/parallel_framework.h:35-45,
+# src/overlap_builder.cpp:453-480); here a batch is a kernel launch over a slice of the read range.  The production
+# batch (~0.8 M reads) never splits a test-sized input, so the hooks of overlap.cu (SGX_MAX_BATCH, SGX_OUT_CAP,
+# SGX_EDGE_CAP) force many batches / undersized output regions / an undersized edge buffer onto the same
+# reference-checked cases as above.
+
+@pytest.mark.skipif(not refrun.have_ref(), reason="compiled reference (oracle/_ref/siga) not present")
+@pytest.mark.parametrize("hook", ["batch1024", "batch1000_outcap4", "edgecap64"])
+def test_config1_full_pipeline_multibatch(ctx, monkeypatch, hook):
+    if hook.startswith("batch1024"):
+        monkeypatch.setenv("SGX_MAX_BATCH", "1024")
+    if hook == "batch1000_outcap4":
+        monkeypatch.setenv("SGX_MAX_BATCH", "1000")
+        monkeypatch.setenv("SGX_OUT_CAP", "4")
+    if hook == "edgecap64":
+        monkeypatch.setenv("SGX_MAX_BATCH", "3000")
+        monkeypatch.setenv("SGX_EDGE_CAP", "64")
+    test_config1_full_pipeline_bit_exact(ctx)
+
+
+@pytest.mark.parametrize("batch", ["1", "7"])
+def test_golden_fixtures_multibatch(ctx, monkeypatch, batch):
+    monkeypatch.setenv("SGX_MAX_BATCH", batch)
+    for path in _GOLDEN:
+        test_cuda_path_reproduces_golden_fixture(ctx, path)
+
+
+def test_golden_fixtures_regrow_and_edge_overflow(ctx, monkeypatch):
+    monkeypatch.setenv("SGX_MAX_BATCH", "16")
+    monkeypatch.setenv("SGX_OUT_CAP", "4")
+    monkeypatch.setenv("SGX_EDGE_CAP", "8")
+    for path in _GOLDEN:
+        test_cuda_path_reproduces_golden_fixture(ctx, path)
+
+
+@pytest.mark.skipif(not refrun.have_ref(), reason="compiled reference (oracle/_ref/siga) not present")
+@pytest.mark.parametrize("seed,batch", [(0, "64"), (1, "100"), (4, "33"), (5, "50")])
+def test_overlap_blocks_match_reference_hits_multibatch(ctx, monkeypatch, seed, batch):
+    monkeypatch.setenv("SGX_MAX_BATCH", batch)
+    monkeypatch.setenv("SGX_EDGE_CAP", "1000")
+    test_overlap_blocks_match_reference_hits(ctx, seed)
+
+
+@pytest.mark.skipif(not refrun.have_ref(), reason="compiled reference (oracle/_ref/siga) not present")
+def test_overlap_periodic_and_variable_length_multibatch(ctx, monkeypatch):
+    monkeypatch.setenv("SGX_MAX_BATCH", "16")   # the general-path chunks of sgx_overlap_edges split too
+    monkeypatch.setenv("SGX_OUT_CAP", "8")
+    test_overlap_periodic_and_variable_length(ctx)
+
+
+@pytest.mark.skipif(not refrun.have_ref(), reason="compiled reference (oracle/_ref/siga) not present")
+@pytest.mark.parametrize("cfg,scale,m", [("cfg2", 0.004, 45), ("cfg3", 0.004, 31), ("cfg4", 0.0002, 45), ("cfg5", 0.0003, 45)])
+def test_named_configs_scaled_down_multibatch(ctx, monkeypatch, cfg, scale, m):
+    monkeypatch.setenv("SGX_MAX_BATCH", "1024")
+    test_named_configs_scaled_down_match_reference(ctx, cfg, scale, m)
 
 
 # ------------------------------------------------------------------------------------------------------------ rmdup

@@ -5,6 +5,11 @@ shards on one context: the exchange steps are device copies instead of NCCL send
 bounds, per-shard ranks, destination partition, receiver-side row fix-up, seam-aware run-length encoding -- is the code
 the NCCL path runs).  The NCCL transport itself is exercised by `bench.py --gpus N` / tests/multigpu_index_check.py.
 """
+import json
+import os
+import subprocess
+import sys
+
 import numpy as np
 import pytest
 
@@ -74,3 +79,29 @@ def test_sharded_index_wide_positions(ctx, monkeypatch):
     monkeypatch.setenv("SGX_FORCE_WIDE", "1")
     rng = np.random.default_rng(31)
     _check_sharded(ctx, _rand_reads(rng, 120, 10, 50, 500, err=0.01, dup=0.05), 4, "wide")
+
+
+def _gpu_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_gpu_count() < 2, reason="needs two GPUs (run under gpurun --gpus 2)")
+@pytest.mark.parametrize("cfg,scale", [("cfg4", 0.01), ("cfg5", 0.01)])
+def test_sharded_index_over_nccl_matches_reference(cfg, scale):
+    """The NCCL transport (one process per GPU, ncclSend/ncclRecv all-to-all per column pass): run bytes and .sai of the
+    sharded build equal the single-GPU build AND the reference's hashes (tests/golden/fullsize)."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    n = min(_gpu_count(), 8)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(here, "multigpu_index_check.py"), cfg, str(scale), "1"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stderr[-3000:]
+    line = [l for l in p.stdout.splitlines() if l.startswith("{")][-1]
+    out = json.loads(line)
+    assert out["ok"] and out["world"] == n
+    assert out["sharded_rev0"]["identical"] and out["sharded_rev1"]["identical"]
+    assert out["reference_identical_rev0"] and out["reference_identical_rev1"]
