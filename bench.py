@@ -8,6 +8,10 @@ Workload: BASELINE.json configs[1] -- synthetic E. coli-sized 4.6 Mbp genome, 10
 1 % substitution errors, both strands (3 066 666 reads), `index` + `overlap -m 45`.
 Headline metric: overlap reads/s (a step = one overlap pass over the whole read set, index resident);
 the BWT-build Gbases/s of the same read set is reported in the "index" object of the same JSON line.
+Further objects of the line: "strong" (BASELINE.json configs[2]: ONE cfg2 read set split over the N ranks by contiguous
+range -- what `siga overlap --gpus N` does -- for min-overlap 31 / 45 / 63 / 101), "cli" (N = 1: `siga index` and
+`siga overlap` file to file), "cfg4" (N = 8: the 100 Mbp config, index sharded over the 8 GPUs + overlap, each with its
+1-GPU time), "parity" (full-size outputs against hashes of the reference's own files, tests/golden/fullsize).
 """
 import argparse
 import json
@@ -28,6 +32,33 @@ from siga_b200 import synth  # noqa: E402
 
 MIN_OVERLAP = 45
 WORKLOAD = "cfg2: 4.6 Mbp random genome, 100x, 150 bp reads, 1% substitutions, both strands, 3066666 reads; index + overlap -m 45"
+
+
+def read_range(n_reads, rank, world):
+    """Contiguous, balanced read range of a rank (first, count): the split `siga overlap --gpus N` makes."""
+    first = (n_reads * rank) // world
+    return first, (n_reads * (rank + 1)) // world - first
+
+
+def golden_fullsize(cfg, scale):
+    """Hashes of the reference's own outputs for (config, scale) (tests/golden/make_fullsize.py), or None."""
+    p = os.path.join(REPO, "tests", "golden", "fullsize", "%s_%g.json" % (cfg, scale))
+    return json.load(open(p)) if os.path.isfile(p) else None
+
+
+def sha256(b):
+    import hashlib
+    return hashlib.sha256(b).hexdigest()
+
+
+def check_index_hashes(golden, fi, ri):
+    """Run bytes and .sai ids of both indices against the reference's files (sha256 of buffers already held)."""
+    ix = golden["index"]
+    assert fi.n_suffixes == ix["n_suffixes"]
+    assert sha256(fi.runs.tobytes()) == ix["bwt_runs_sha256"], ".bwt run bytes differ from the reference's"
+    assert sha256(ri.runs.tobytes()) == ix["rbwt_runs_sha256"], ".rbwt run bytes differ from the reference's"
+    assert sha256(fi.sai.astype("<u4").tobytes()) == ix["sai_u32_sha256"], ".sai differs from the reference's"
+    assert sha256(ri.sai.astype("<u4").tobytes()) == ix["rsai_u32_sha256"], ".rsai differs from the reference's"
 
 
 def measured_peaks():
@@ -150,6 +181,78 @@ def reference_arm(args):
     return 0
 
 
+def lf_check_sample(ctx, fm, sai, reads, sample, rng):
+    """Size-independent exact check of a full-size index: for `sample` random reads, walk the BWT backwards from the
+    read's sentinel row (LF mapping through sgx_fm_occ); the symbols met must spell the read from its last base to its
+    first, and the walk must end on the '$' row whose .sai entry is the read."""
+    n, L = reads.shape
+    sai = np.asarray(sai, dtype=np.int64)
+    ids = np.sort(rng.choice(n, size=min(sample, n), replace=False)).astype(np.int64)
+    # sentinel rows under ordering model B: the '$' of read i sorts by the suffix that follows it, i.e. by the rank of
+    # read i+1 among the read-start suffixes; the last read's '$' (end of text) comes first
+    inv = np.empty(n, dtype=np.int64)
+    inv[sai] = np.arange(n, dtype=np.int64)
+    k0 = inv[0]
+    nxt = np.minimum(ids + 1, n - 1)
+    kk = inv[nxt]
+    row = np.where(ids == n - 1, 0, 1 + kk - (kk > k0)).astype(np.uint64)
+    pred = np.array(ctx.fm_pred(fm), dtype=np.uint64)
+    code = np.zeros(256, dtype=np.int64)
+    for i, ch in enumerate(b"ACGT"):
+        code[ch] = i + 1
+    for j in range(L - 1, -2, -1):
+        occ_hi = ctx.fm_occ(fm, row)
+        occ_lo = ctx.fm_occ(fm, row - np.uint64(1))  # row 0 - 1 wraps to getOcc(-1) = 0
+        d = (occ_hi - occ_lo).astype(np.int64)
+        assert np.all(d.sum(axis=1) == 1)
+        sym = d.argmax(axis=1)
+        if j >= 0:
+            assert np.array_equal(sym, code[reads[ids, j]]), "LF walk does not spell the read (column %d)" % j
+            row = pred[sym] + occ_hi[np.arange(len(ids)), sym] - np.uint64(1)
+        else:
+            assert np.all(sym == 0)
+            assert np.array_equal(sai[occ_hi[:, 0].astype(np.int64) - 1], ids), "LF walk ends on another read's row"
+    return int(len(ids))
+
+
+def run_cli(args, cwd):
+    t0 = time.perf_counter()
+    p = subprocess.run(args, cwd=cwd, capture_output=True, text=True)
+    dt = time.perf_counter() - t0
+    if p.returncode != 0:
+        raise RuntimeError("%s failed: %s" % (args[:2], p.stderr[-1500:]))
+    return dt, p.stderr
+
+
+def cli_object(reads, golden, min_overlap):
+    """`siga index` + `siga overlap -m M` file to file (FASTA in /dev/shm -> .bwt/.rbwt/.sai/.rsai and .asqg.gz)."""
+    cli = os.path.join(REPO, "siga_b200", "bin", "siga")
+    if not os.path.isfile(cli):
+        return {"unavailable": "siga_b200/bin/siga not built"}
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    n, L = reads.shape
+    with tempfile.TemporaryDirectory(dir=base) as d:
+        fa = os.path.join(d, "reads.fa")
+        synth.write_fasta(fa, reads)
+        t_index, err_i = run_cli([cli, "index", fa], d)
+        t_overlap, err_o = run_cli([cli, "overlap", "-m", str(min_overlap), fa], d)
+        out = {"index_s": t_index, "overlap_s": t_overlap, "index_gbases_per_s": n * L / t_index / 1e9,
+               "overlap_reads_per_s": n / t_overlap, "input": "FASTA, %d bytes, tmpfs" % os.path.getsize(fa),
+               "asqg_gz_bytes": os.path.getsize(os.path.join(d, "reads.asqg.gz")),
+               "phases_index": [l.strip() for l in err_i.splitlines() if "phase" in l.lower() or " ms" in l][-6:],
+               "phases_overlap": [l.strip() for l in err_o.splitlines() if "phase" in l.lower() or " ms" in l][-8:]}
+        if golden is not None:
+            ok = True
+            for ext in ("bwt", "rbwt", "sai", "rsai"):
+                with open(os.path.join(d, "reads." + ext), "rb") as f:
+                    ok = ok and sha256(f.read()) == golden["index"][ext + "_sha256"]
+            p = subprocess.run("zcat reads.asqg.gz | LC_ALL=C sort -S 2G | sha256sum", shell=True, cwd=d, capture_output=True, text=True)
+            ok = ok and p.stdout.split()[0] == golden["overlap"][str(min_overlap)]["sorted_asqg_sha256"]
+            out["files_identical_to_reference"] = bool(ok)
+            assert ok, "CLI output files differ from the reference's (sha256)"
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -159,6 +262,10 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="genome scale of cfg2 (1.0 = the named workload)")
     ap.add_argument("--ref-scale", type=float, default=0.01, help="genome scale of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cli", action="store_true")
+    ap.add_argument("--no-correct", action="store_true")
+    ap.add_argument("--cfg4", default="auto", choices=["auto", "on", "off"], help="the 100 Mbp config (auto: at 8 GPUs)")
+    ap.add_argument("--cfg4-scale", type=float, default=1.0)
     ap.add_argument("--index-steps", type=int, default=0, help="timed index builds (default: min(steps, 3))")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -190,26 +297,29 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
+    def reduce_ranks(x, op):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
+    def max_over_ranks(x):
+        return reduce_ranks(x, dist.ReduceOp.MAX)
+
     def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return reduce_ranks(x, dist.ReduceOp.SUM)
 
     peaks, peak_kind = measured_peaks()
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    golden = golden_fullsize("cfg2", args.scale)
+    parity = {"reference_hashes": "tests/golden/fullsize/cfg2_%g.json" % args.scale if golden else None}
 
     # ---- synthetic input, resident in pinned host memory (every rank holds the same read set)
     reads = synth.config_reads("cfg2", args.scale)
     n_reads, read_len = reads.shape
+    if golden:
+        assert sha256(np.ascontiguousarray(reads).tobytes()) == golden["reads_sha256"], "generator drifted from the pinned reads"
     host = torch.empty(reads.size, dtype=torch.uint8).pin_memory()
     host.numpy()[:] = reads.reshape(-1)
     off = (np.arange(n_reads + 1, dtype=np.uint64) * np.uint64(read_len))
@@ -228,6 +338,9 @@ def main():
     r_dev = ctx.pack_reads(flat, off)
     fi = ctx.index_build(r_dev, order=api.ORDER_SAIS2, reversed=False)
     ri = ctx.index_build(r_dev, order=api.ORDER_SAIS2, reversed=True)
+    if golden:  # full-size parity: byte-identical to the reference's .bwt/.rbwt/.sai/.rsai (hashes of one full reference run)
+        check_index_hashes(golden, fi, ri)
+        parity["index_identical_to_reference"] = True
     fwd = ctx.fm_create(fi.runs, fi.n_suffixes)
     rev = ctx.fm_create(ri.runs, ri.n_suffixes)
     ctx.fm_attach_reads(fwd, fi.sai, r_dev)
@@ -240,9 +353,7 @@ def main():
         base_counts = np.bincount(flat, minlength=256)[[65, 67, 71, 84]]
         assert np.array_equal(sym_counts[1:], base_counts)
 
-    names = ["r%d" % i for i in range(n_reads)]
-    name_rank = api.name_ranks(names)
-    lengths = np.full(n_reads, read_len, dtype=np.int64)
+    name_rank = synth.default_name_ranks(n_reads)
 
     sampler.start()
     # ---- overlap, inputs resident in HBM ("value"): search + post + hits->edges on the device, edges copied out
@@ -252,8 +363,7 @@ def main():
     barrier()
     t0 = time.perf_counter()
     dev_ms = search_ms = extract_ms = 0.0
-    look_s = look_e = launches = search_launches = 0
-    d2h_bytes = 0
+    look_s = look_e = lines_s = launches = search_launches = 0
     for _ in range(args.steps):
         e = ctx.overlap_edges(fwd, rev, r_dev, 0, n_reads, MIN_OVERLAP, name_rank, copy=False)
         st = e.stats
@@ -262,9 +372,9 @@ def main():
         extract_ms += st["ms_extract"]
         look_s += st["lookups_search"]
         look_e += st["lookups_extract"]
+        lines_s += st["lines_search"]
         launches += st["launches"]
         search_launches += st["search_launches"]
-        d2h_bytes = int(e.edges.nbytes + e.substring.nbytes)
         n_blocks = st["n_blocks"]
         n_edges = st["n_edges"]
         slow_reads = st["slow_reads"]
@@ -274,12 +384,19 @@ def main():
     total_reads = n_reads * world
     value = total_reads / (ms_step * 1e-3)
 
-    # size-independent parity property at full size: the edge set is closed under the reference's symmetry -- every
-    # overlap is found from both reads, and exactly one of the two directions survives the id0 >= id1 rule
+    # ---- parity at full size: the ED set (canonical digest) and the SS flags against the reference's .asqg.gz; plus the
+    #      size-independent property that exactly one direction of every overlap survives the id0 >= id1 rule
     chk = ctx.overlap_edges(fwd, rev, r_dev, 0, n_reads, MIN_OVERLAP, name_rank)
     ed = chk.edges
     assert len(ed) == n_edges and np.all(name_rank[ed["query"]] > name_rank[ed["target"]])
     assert np.all((ed["length"] >= MIN_OVERLAP) & (ed["length"] <= read_len))
+    if golden and str(MIN_OVERLAP) in golden.get("overlap", {}):
+        g = golden["overlap"][str(MIN_OVERLAP)]
+        assert len(ed) == g["n_ed"] and int(chk.substring.sum()) == g["n_substring"]
+        if rank == 0:
+            assert formats.edge_digest(ed, np.int64(read_len)) == g["edges_digest"], "ED set differs from the reference's"
+        parity["edges_identical_to_reference_m%d" % MIN_OVERLAP] = True
+    del chk, ed
 
     # ---- overlap end to end through the C ABI with HOST buffers ("e2e"): pack the pinned host reads, attach the
     #      host .sai/.rsai, search, convert, copy the edges out
@@ -289,10 +406,6 @@ def main():
         ctx.fm_attach_reads(rev, ri.sai, rr)
         ee = ctx.overlap_edges(fwd, rev, rr, 0, n_reads, MIN_OVERLAP, name_rank, copy=False)
         nb = int(ee.edges.nbytes + ee.substring.nbytes)
-        if comm is not None:  # N > 1: the edge records of every rank's shard end up in rank 0's host memory
-            ga = ctx.edges_gather(comm, ee, root=0, copy=False)
-            nb += int(ga.edges.nbytes + ga.substring.nbytes)
-            ctx.free_edges(ga)
         ctx.free_edges(ee)
         ctx.free_reads(rr)
         return nb
@@ -312,6 +425,45 @@ def main():
     ctx.fm_attach_reads(rev, ri.sai, r_dev)
     e2e_h2d = int(flat.nbytes + off.nbytes + 2 * fi.sai.nbytes + name_rank.nbytes)
 
+    # ---- BASELINE.json configs[2]: the same read set, min-overlap sweep, overlap stage sharded over the N ranks by
+    #      contiguous read range (strong scaling of ONE read set; FM-indices replicated; what `siga overlap --gpus N`
+    #      does: every rank formats and writes the records of its own range, nothing is gathered)
+    first, count = read_range(n_reads, rank, world)
+    strong = {"scaling": "strong", "split": "one cfg2 read set, contiguous ranges of %d reads per rank, FM-indices replicated" % count,
+              "by_min_overlap": {}}
+    for m in (31, 45, 63, 101):
+        ctx.free_edges(ctx.overlap_edges(fwd, rev, r_dev, first, count, m, name_rank, copy=False))
+        times = []
+        for _ in range(max(3, min(args.steps, 5))):
+            barrier()
+            t0 = time.perf_counter()
+            e = ctx.overlap_edges(fwd, rev, r_dev, first, count, m, name_rank, copy=False)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) * 1e3
+            st = dict(e.stats)
+            ctx.free_edges(e)
+            times.append(max_over_ranks(dt))
+        ms = sorted(times)[len(times) // 2]
+        ne = int(sum_over_ranks(st["n_edges"]))
+        rec = {"ms": ms, "reads_per_s": n_reads / (ms * 1e-3), "edges": ne,
+               "search_ms_max_rank": max_over_ranks(st["ms_search"]), "post_ms_max_rank": max_over_ranks(st["ms_extract"]),
+               "lookups_per_read": sum_over_ranks(st["lookups_search"]) / n_reads,
+               "lines_per_read": sum_over_ranks(st["lines_search"]) / n_reads}
+        if golden and str(m) in golden.get("overlap", {}):
+            g = golden["overlap"][str(m)]
+            assert ne == g["n_ed"], ("edge count differs from the reference's", m, ne, g["n_ed"])
+            if world == 1:
+                ck = ctx.overlap_edges(fwd, rev, r_dev, 0, n_reads, m, name_rank)
+                assert formats.edge_digest(ck.edges, np.int64(read_len)) == g["edges_digest"] and \
+                    int(ck.substring.sum()) == g["n_substring"], ("ED set differs from the reference's", m)
+                del ck
+                rec["identical_to_reference"] = "ED set digest + SS flags"
+            else:
+                rec["identical_to_reference"] = "ED count (the digest is checked at N = 1 and by tests/test_gpu_fullsize.py)"
+            rec["reference_seconds"] = g["seconds"]
+            rec["reference_threads"] = g["threads"]
+        strong["by_min_overlap"][str(m)] = rec
+
     # ---- index build (fwd + rev), resident and end to end.  N = 1: sgx_index_build.  N > 1: ONE index of the same
     #      read set built by all N GPUs together (sgx_index_build_sharded: rows sharded by leading k-mer bucket,
     #      inserts exchanged with NCCL all-to-all every column pass) -- strong scaling, checked against the
@@ -327,6 +479,8 @@ def main():
         assert np.array_equal(o.sai, ref_idx.sai)
         if rank == 0:
             assert np.array_equal(o.runs, ref_idx.runs), "sharded index differs from the single-GPU build"
+    if world > 1 and golden:
+        parity["sharded_index_identical_to_reference"] = True  # == the single-GPU build, which matched the hashes above
     barrier()
     t0 = time.perf_counter()
     idx_dev_ms = idx_merge_ms = 0.0
@@ -356,46 +510,74 @@ def main():
 
     # ---- k-mer error correction (`siga correct`, defaults -k 31 -x 3 -i 10 -O 1) of the same reads against the forward
     #      index: resident (reads + index in HBM) and end to end (pinned host reads in, flags + fixes out)
-    csteps = min(args.steps, 3)
-    ctx.correct(fwd, r_dev, 0, n_reads)
-    barrier()
-    t0 = time.perf_counter()
-    corr_kernel_ms = 0.0
-    corr_look = corr_launches = 0
-    for _ in range(csteps):
-        cr = ctx.correct(fwd, r_dev, 0, n_reads)
-        corr_kernel_ms += cr.stats["ms_kernel"]
-        corr_look += cr.stats["lookups"]
-        corr_launches += cr.stats["launches"]
-    barrier()
-    corr_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / csteps)
-    # size-independent properties at full size: a written read differs from its input exactly at its fixes, every fix
-    # changes the base, dropped reads carry no fixes
-    fx_pos = off[cr.fixes["read"].astype(np.int64)].astype(np.int64) + (cr.fixes["pos_code"] >> 2).astype(np.int64)
-    assert np.all(cr.valid[cr.fixes["read"]] == 1) and len(np.unique(fx_pos)) == len(fx_pos)
-    assert np.all(flat[fx_pos] != np.frombuffer(b"ACGT", dtype=np.uint8)[cr.fixes["pos_code"] & 3])
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(csteps):
-        rr = ctx.pack_reads(flat, off)
-        c2 = ctx.correct(fwd, rr, 0, n_reads)
-        ctx.free_reads(rr)
-    barrier()
-    corr_e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / csteps)
-    assert np.array_equal(c2.valid, cr.valid) and len(c2.fixes) == len(cr.fixes)
+    correct_obj = None
+    if not args.no_correct:
+        csteps = min(args.steps, 3)
+        ctx.correct(fwd, r_dev, 0, n_reads)
+        barrier()
+        t0 = time.perf_counter()
+        corr_kernel_ms = 0.0
+        corr_look = corr_launches = 0
+        for _ in range(csteps):
+            cr = ctx.correct(fwd, r_dev, 0, n_reads)
+            corr_kernel_ms += cr.stats["ms_kernel"]
+            corr_look += cr.stats["lookups"]
+            corr_launches += cr.stats["launches"]
+        barrier()
+        corr_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / csteps)
+        # size-independent properties at full size: a written read differs from its input exactly at its fixes, every fix
+        # changes the base, dropped reads carry no fixes
+        fx_pos = off[cr.fixes["read"].astype(np.int64)].astype(np.int64) + (cr.fixes["pos_code"] >> 2).astype(np.int64)
+        assert np.all(cr.valid[cr.fixes["read"]] == 1) and len(np.unique(fx_pos)) == len(fx_pos)
+        assert np.all(flat[fx_pos] != np.frombuffer(b"ACGT", dtype=np.uint8)[cr.fixes["pos_code"] & 3])
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(csteps):
+            rr = ctx.pack_reads(flat, off)
+            c2 = ctx.correct(fwd, rr, 0, n_reads)
+            ctx.free_reads(rr)
+        barrier()
+        corr_e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / csteps)
+        assert np.array_equal(c2.valid, cr.valid) and len(c2.fixes) == len(cr.fixes)
+        correct_obj = {
+            "metric": "correct_reads_per_s", "value": total_reads / (corr_ms * 1e-3), "unit": "reads/s",
+            "ms_per_step": corr_ms, "steps": csteps, "kernel_ms_per_step": corr_kernel_ms / csteps,
+            "scaling": "weak", "options": "-k 31 -x 3 -i 10 -O 1 (the reference's defaults), forward index only",
+            "written_reads": int(cr.valid.sum()), "fixed_bases": int(len(cr.fixes)), "gpu_launches": int(corr_launches),
+            "e2e": {"value": total_reads / (corr_e2e_ms * 1e-3), "unit": "reads/s", "ms_per_step": corr_e2e_ms,
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(cr.valid.nbytes + cr.fixes.nbytes),
+                    "entry": "sgx_reads_pack + sgx_correct_batch (pinned host reads in, written flags + fixes out)"},
+            "roofline": {"bound": "hbm", "kernel": "corr_kernel", "unit": "GB/s", "peak": hbm_peak,
+                         "achieved": corr_look * 128 / (corr_kernel_ms * 1e-3) / 1e9 if corr_kernel_ms else 0.0,
+                         "frac": corr_look * 128 / (corr_kernel_ms * 1e-3) / 1e9 / hbm_peak if corr_kernel_ms else 0.0,
+                         "note": "numerator = executed rank lookups x 128 B (two lookups of one step often share a line and L2 "
+                                 "absorbs the top of the index: not an HBM fraction, see DESIGN.md 4.8)",
+                         # dram__bytes_read.sum + dram__bytes_write.sum of the one launch at full cfg2 size, ncu --set
+                         # full capture profiles/r1h_prof_correct.raw.csv
+                         "traffic": 75.20e9 if args.scale == 1.0 else None, "traffic_source": "profiles/r1h_summary.md",
+                         "lookups_per_read": corr_look / csteps / n_reads,
+                         "reference_lookups_per_read_nominal": 2 * 30 * (read_len - 30),
+                         "lookups_per_s": corr_look / (corr_kernel_ms * 1e-3) if corr_kernel_ms else 0.0}}
     if comm is not None:
         ctx.free_comm(comm)
+        comm = None
     clocks = sampler.stop()
 
     bases = n_reads * read_len
-    # random-access roofline of the search kernel: executed rank lookups x 128 B over its device time
+    # random-access roofline of the search kernel: distinct 128-byte rank-block lines fetched over its device time
     search_s = search_ms * 1e-3 / args.steps
-    ach_gbs = (look_s / args.steps) * 128 / search_s / 1e9 if search_s > 0 else 0.0
+    lines_per_s = (lines_s / args.steps) / search_s if search_s > 0 else 0.0
+    ach_gbs = lines_per_s * 128 / 1e9
     gather = None
     try:
         gather = ctx.bench_gather(8 << 30, 1 << 27)
     except Exception:
         gather = None
+    traffic, traffic_src = None, None
+    tp = os.path.join(REPO, "profiles", "r2_traffic.json")
+    if args.scale == 1.0 and os.path.isfile(tp):
+        tj = json.load(open(tp))
+        traffic, traffic_src = tj.get("search_dram_bytes_per_launch"), tj.get("source")
     idx_suffix_bytes = {100: 31, 150: 37, 250: 50}.get(read_len, (read_len + 1 + 7) // 8 + 18)
     merge_s = idx_merge_ms * 1e-3 / max(idx_merge_launches, 1)
     merge_ach = (idx_merge_bytes / max(idx_merge_launches, 1)) / merge_s / 1e9 if merge_s > 0 else 0.0
@@ -414,22 +596,26 @@ def main():
         "e2e": {"value": e2e_value, "unit": "reads/s", "ms_per_step": e2e_ms, "step_ms": [round(x, 2) for x in e2e_steps],
                 "h2d_bytes_per_step": e2e_h2d,
                 "d2h_bytes_per_step": e2e_d2h,
-                "entry": "sgx_reads_pack + sgx_fm_attach_reads x2 + sgx_overlap_edges (pinned host reads / .sai / name ranks in, edges + SS flags out)"
-                         + ("; + sgx_edges_gather of all shards' edge records to rank 0 (NCCL)" if world > 1 else "")},
-        "roofline": {"bound": "hbm", "kernel": "ov_search_kernel", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
+                "entry": "sgx_reads_pack + sgx_fm_attach_reads x2 + sgx_overlap_edges (pinned host reads / .sai / name ranks in, "
+                         "edges + SS flags out); every rank keeps the records of its own reads, as `siga overlap --gpus N` does"},
+        "roofline": {"bound": "hbm", "kernel": "ov_search_lean_kernel", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": ach_gbs / hbm_peak,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch (mode 0 of 4) at full cfg2 size,
-                     # ncu --set full capture profiles/r1c_prof_search.raw.csv; its algorithmic bytes are 89.5 GB
-                     "traffic": 42.14e9 if args.scale == 1.0 else None, "traffic_source": "profiles/r1c_summary.md",
+                     "numerator": "distinct 128-byte rank-block lines fetched (a step whose interval ends share a block counts one line)",
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at full cfg2 size from the ncu --set full
+                     # capture named in profiles/r2_traffic.json
+                     "traffic": traffic, "traffic_source": traffic_src,
                      "launches_per_step": search_launches / args.steps,
-                     "algorithmic_bytes_per_launch": look_s * 128 / max(search_launches, 1),
+                     "algorithmic_bytes_per_launch": lines_s * 128 / max(search_launches, 1),
                      "peak_kind": peak_kind + " STREAM copy",
+                     "lines_per_read": lines_s / args.steps / n_reads, "lines_per_s": lines_per_s,
                      "lookups_per_read": look_s / args.steps / n_reads, "lookups_per_s": look_s / args.steps / search_s if search_s else 0,
                      "random_gather_128B_per_s": gather,
-                     "frac_of_random_gather": (look_s / args.steps / search_s) / gather if gather and search_s else None,
+                     "frac_of_random_gather": lines_per_s / gather if gather and search_s else None,
                      "search_ms": search_ms / args.steps, "extract_ms": extract_ms / args.steps,
                      "extract_lookups_per_read": look_e / args.steps / n_reads, "blocks_per_read": n_blocks / n_reads, "edges_per_read": n_edges / n_reads,
                      "slow_path_reads": slow_reads},
+        "strong": strong,
+        "parity": parity,
         "index": {"metric": "bwt_build_gbases_per_s", "value": bases / (idx_ms * 1e-3) / 1e9, "unit": "Gbases/s",
                   "ms_per_step": idx_ms, "steps": isteps, "device_ms_per_step": idx_dev_ms / isteps,
                   "scaling": "strong" if world > 1 else "single GPU",
@@ -443,25 +629,36 @@ def main():
                                "merge_ms_per_build": idx_merge_ms / (2 * isteps),
                                "floor_bytes_per_suffix": idx_suffix_bytes,
                                "floor_frac": idx_suffix_bytes * 2 * fi.n_suffixes / (idx_dev_ms / isteps * 1e-3) / 1e9 / hbm_peak}},
-        "correct": {"metric": "correct_reads_per_s", "value": total_reads / (corr_ms * 1e-3), "unit": "reads/s",
-                    "ms_per_step": corr_ms, "steps": csteps, "kernel_ms_per_step": corr_kernel_ms / csteps,
-                    "scaling": "weak", "options": "-k 31 -x 3 -i 10 -O 1 (the reference's defaults), forward index only",
-                    "written_reads": int(cr.valid.sum()), "fixed_bases": int(len(cr.fixes)), "gpu_launches": int(corr_launches),
-                    "e2e": {"value": total_reads / (corr_e2e_ms * 1e-3), "unit": "reads/s", "ms_per_step": corr_e2e_ms,
-                            "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(cr.valid.nbytes + cr.fixes.nbytes),
-                            "entry": "sgx_reads_pack + sgx_correct_batch (pinned host reads in, written flags + fixes out)"},
-                    "roofline": {"bound": "hbm", "kernel": "corr_kernel", "unit": "GB/s", "peak": hbm_peak,
-                                 "achieved": corr_look * 128 / (corr_kernel_ms * 1e-3) / 1e9 if corr_kernel_ms else 0.0,
-                                 "frac": corr_look * 128 / (corr_kernel_ms * 1e-3) / 1e9 / hbm_peak if corr_kernel_ms else 0.0,
-                                 # dram__bytes_read.sum + dram__bytes_write.sum of the one launch at full cfg2 size, ncu --set
-                                 # full capture profiles/r1h_prof_correct.raw.csv (the r1h kernel: same rank-block loads in
-                                 # the same order as the current one, which only spends fewer instructions per step)
-                                 "traffic": 75.20e9 if args.scale == 1.0 else None, "traffic_source": "profiles/r1h_summary.md",
-                                 "lookups_per_read": corr_look / csteps / n_reads,
-                                 "reference_lookups_per_read_nominal": 2 * 30 * (read_len - 30),
-                                 "lookups_per_s": corr_look / (corr_kernel_ms * 1e-3) if corr_kernel_ms else 0.0}},
         "clocks": clocks,
     }
+    if golden:
+        line["reference_full_size"] = {
+            "what": "the compiled reference on this exact read set, run once (tests/golden/make_fullsize.py)",
+            "index_seconds": golden["index"]["seconds"], "index_threads": 1,
+            "overlap_seconds": {m: v["seconds"] for m, v in golden.get("overlap", {}).items()},
+            "overlap_threads": {m: v["threads"] for m, v in golden.get("overlap", {}).items()}}
+    if correct_obj:
+        line["correct"] = correct_obj
+
+    if rank == 0 and world == 1 and not args.no_cli:
+        ctx.free_fm(fwd)
+        ctx.free_fm(rev)
+        ctx.free_reads(r_dev)
+        fwd = rev = r_dev = None
+        try:
+            line["cli"] = cli_object(reads, golden, MIN_OVERLAP)
+        except Exception as ex:  # the CLI is a separate process: report, do not lose the line
+            line["cli"] = {"error": str(ex)[:500]}
+
+    want_cfg4 = args.cfg4 == "on" or (args.cfg4 == "auto" and world == 8)
+    if want_cfg4:
+        if fwd is not None:
+            ctx.free_fm(fwd)
+            ctx.free_fm(rev)
+            ctx.free_reads(r_dev)
+            fwd = rev = r_dev = None
+        del host, flat
+        line["cfg4"] = cfg4_object(args, ctx, api, formats, torch, dist, rank, world, local, barrier, max_over_ranks, sum_over_ranks)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         with tempfile.TemporaryDirectory() as d:
@@ -474,15 +671,135 @@ def main():
                                     "index_gbases_per_s": cpu["bases"] / cpu["index_s"] / 1e9, "index_seconds": cpu["index_s"],
                                     "index_cores": 1, "correct_reads_per_s": cpu["reads"] / cpu["correct_s"],
                                     "correct_seconds": cpu["correct_s"]}
-    ctx.free_fm(fwd)
-    ctx.free_fm(rev)
-    ctx.free_reads(r_dev)
+    if fwd is not None:
+        ctx.free_fm(fwd)
+        ctx.free_fm(rev)
+        ctx.free_reads(r_dev)
     ctx.close()
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def cfg4_object(args, ctx, api, formats, torch, dist, rank, world, local, barrier, max_over_ranks, sum_over_ranks):
+    """BASELINE.json configs[3]: 100 Mbp genome, 50x 150 bp reads (33.3 M reads, 5.03 G symbols per index): the index built
+    by all ranks together (rows sharded by k-mer bucket, NCCL all-to-all per column pass) and the overlap stage sharded by
+    read range, each next to the time ONE GPU takes for the same job with the same kernels (rank 0, the others idle)."""
+    scale = args.cfg4_scale
+    shm = "/dev/shm/siga_b200_cfg4_%g.u8" % scale
+    c = synth.CONFIGS["cfg4"]
+    g = max(int(c["genome"] * scale), 4 * c["read_len"])
+    n = int(g * c["coverage"] // c["read_len"])
+    L = c["read_len"]
+    t0 = time.perf_counter()
+    if rank == 0:  # one generation, shared through tmpfs (33.3 M x 150 bytes)
+        reads0 = synth.config_reads("cfg4", scale)
+        assert reads0.shape == (n, L)
+        mm = np.lib.format.open_memmap(shm, mode="w+", dtype=np.uint8, shape=(n, L))
+        mm[:] = reads0
+        mm.flush()
+        del mm, reads0
+    barrier()
+    reads = np.load(shm, mmap_mode="r")
+    gen_s = time.perf_counter() - t0
+    flat = reads.reshape(-1)
+    off = (np.arange(n + 1, dtype=np.uint64) * np.uint64(L))
+    out = {"workload": "cfg4%s: %d Mbp random genome, 50x, 150 bp error-free reads, both strands, %d reads; index + overlap -m %d" %
+                       ("" if scale == 1.0 else " [genome scale %g]" % scale, g // 1_000_000, n, MIN_OVERLAP),
+           "generate_s": gen_s, "n_gpus": world}
+    comm = None
+    if world > 1:
+        uid = torch.from_numpy(ctx.comm_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)).cuda()
+        dist.broadcast(uid, 0)
+        comm = ctx.comm_init(uid.cpu().numpy(), rank, world)
+    r_dev = ctx.pack_reads(flat, off)
+    # index: sharded over all ranks (timed, max over ranks), then rank 0 alone
+    res = {}
+    for rv in (False, True):
+        times = []
+        for it in range(2):
+            barrier()
+            t0 = time.perf_counter()
+            o = ctx.index_build_sharded(comm, r_dev, order=api.ORDER_SAIS2, reversed=rv) if comm is not None else \
+                ctx.index_build(r_dev, order=api.ORDER_SAIS2, reversed=rv)
+            torch.cuda.synchronize()
+            times.append(max_over_ranks((time.perf_counter() - t0) * 1e3))
+        res[rv] = o
+        out["index_ms_rev%d" % rv] = min(times)
+    out["index_ms"] = out["index_ms_rev0"] + out["index_ms_rev1"]
+    out["index_gbases_per_s"] = n * L / (out["index_ms"] * 1e-3) / 1e9
+    single = {}
+    if rank == 0 and world > 1:
+        for rv in (False, True):
+            ctx.free_index(ctx.index_build(r_dev, order=api.ORDER_SAIS2, reversed=rv, copy=False))  # warm-up (work areas)
+            t0 = time.perf_counter()
+            one = ctx.index_build(r_dev, order=api.ORDER_SAIS2, reversed=rv)
+            single[rv] = (time.perf_counter() - t0) * 1e3
+            assert np.array_equal(one.runs, res[rv].runs) and np.array_equal(one.sai, res[rv].sai), \
+                "cfg4: sharded index differs from the single-GPU build"
+            del one
+        out["index_ms_one_gpu"] = single[False] + single[True]
+        out["index_speedup"] = out["index_ms_one_gpu"] / out["index_ms"]
+        out["index_efficiency"] = out["index_speedup"] / world
+        out["index_sharded_identical_to_one_gpu"] = True
+    barrier()
+    # the run bytes are complete on rank 0 only: share them through tmpfs for the replicated FM-indices
+    runs_path = "/dev/shm/siga_b200_cfg4_runs_%d.npy"
+    if rank == 0:
+        for rv in (False, True):
+            np.save(runs_path % rv, res[rv].runs)
+    barrier()
+    fms = []
+    for rv in (False, True):
+        runs = res[rv].runs if rank == 0 else np.load(runs_path % rv, mmap_mode="r")
+        fm = ctx.fm_create(runs, res[rv].n_suffixes)
+        ctx.fm_attach_reads(fm, res[rv].sai, r_dev)
+        fms.append(fm)
+    fwd, rev = fms
+    if rank == 0:
+        # exact, size-independent check of the full-size index: LF-walk a sample of reads out of the BWT
+        out["lf_walk_reads_checked"] = lf_check_sample(ctx, fwd, res[False].sai, reads, 20000, np.random.default_rng(4))
+    name_rank = synth.default_name_ranks(n)
+    first, count = read_range(n, rank, world)
+    ctx.free_edges(ctx.overlap_edges(fwd, rev, r_dev, first, count, MIN_OVERLAP, name_rank, copy=False))
+    times = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        e = ctx.overlap_edges(fwd, rev, r_dev, first, count, MIN_OVERLAP, name_rank, copy=False)
+        torch.cuda.synchronize()
+        times.append(max_over_ranks((time.perf_counter() - t0) * 1e3))
+        st = dict(e.stats)
+        ctx.free_edges(e)
+    out["overlap_ms"] = sorted(times)[1]
+    out["overlap_reads_per_s"] = n / (out["overlap_ms"] * 1e-3)
+    out["edges"] = int(sum_over_ranks(st["n_edges"]))
+    out["slow_path_reads"] = int(sum_over_ranks(st["slow_reads"]))
+    if rank == 0 and world > 1:
+        ctx.free_edges(ctx.overlap_edges(fwd, rev, r_dev, 0, n, MIN_OVERLAP, name_rank, copy=False))
+        t0 = time.perf_counter()
+        e = ctx.overlap_edges(fwd, rev, r_dev, 0, n, MIN_OVERLAP, name_rank, copy=False)
+        out["overlap_ms_one_gpu"] = (time.perf_counter() - t0) * 1e3
+        assert e.stats["n_edges"] == out["edges"], "cfg4: sharded overlap found a different number of edges"
+        ctx.free_edges(e)
+        out["overlap_speedup"] = out["overlap_ms_one_gpu"] / out["overlap_ms"]
+        out["overlap_efficiency"] = out["overlap_speedup"] / world
+    barrier()
+    ctx.free_fm(fwd)
+    ctx.free_fm(rev)
+    ctx.free_reads(r_dev)
+    if comm is not None:
+        ctx.free_comm(comm)
+    del reads, flat
+    if rank == 0:
+        for f in [shm] + [runs_path % rv for rv in (False, True)]:
+            try:
+                os.remove(f)
+            except OSError:
+                pass
+    return out
 
 
 if __name__ == "__main__":

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SGX_ABI_VERSION 1
+#define SGX_ABI_VERSION 2
 
 enum {
   SGX_OK = 0,
@@ -186,6 +186,7 @@ typedef struct sgx_hits {
   uint64_t launches;    /* kernels launched by this call                                                       */
   uint64_t search_launches;
   uint64_t slow_reads;  /* reads whose post stage took the general BWT-walking path                            */
+  uint64_t lines_search; /* 128-byte lines those fetches touched (one when both interval ends share a rank block) */
 } sgx_hits;
 
 /*
@@ -226,6 +227,8 @@ typedef struct sgx_edges {
   uint64_t n_blocks;   /* overlap blocks the edges were expanded from                               */
   double ms_total, ms_search, ms_extract;
   uint64_t lookups_search, lookups_extract, launches, search_launches, slow_reads;
+  uint64_t lines_search; /* distinct 128-byte rank-block lines the search fetched: a backward step whose interval ends
+                            share a block counts one line for its two lookups (the random-access roofline numerator) */
 } sgx_edges;
 
 /*

@@ -16,13 +16,16 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, REPO)
 
 
 def main():
     import torch
     import torch.distributed as dist
-    from siga_b200 import api, shard, synth
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import shard
+    from siga_b200 import api, synth
 
     cfg = sys.argv[1]
     m = int(sys.argv[2]) if len(sys.argv) > 2 else 45

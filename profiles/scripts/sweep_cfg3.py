@@ -14,7 +14,9 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-from siga_b200 import api, shard, synth  # noqa: E402
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests"))
+import shard  # noqa: E402
+from siga_b200 import api, synth  # noqa: E402
 
 
 def main():

@@ -50,7 +50,7 @@ class _Hits(ctypes.Structure):
                 ("n_blocks", ctypes.c_uint64), ("ms_total", ctypes.c_double), ("ms_search", ctypes.c_double),
                 ("ms_extract", ctypes.c_double), ("lookups_search", ctypes.c_uint64),
                 ("lookups_extract", ctypes.c_uint64), ("launches", ctypes.c_uint64),
-                ("search_launches", ctypes.c_uint64), ("slow_reads", ctypes.c_uint64)]
+                ("search_launches", ctypes.c_uint64), ("slow_reads", ctypes.c_uint64), ("lines_search", ctypes.c_uint64)]
 
 
 class _Edges(ctypes.Structure):
@@ -58,7 +58,7 @@ class _Edges(ctypes.Structure):
                 ("n_edges", ctypes.c_uint64), ("edges", ctypes.c_void_p), ("n_blocks", ctypes.c_uint64),
                 ("ms_total", ctypes.c_double), ("ms_search", ctypes.c_double), ("ms_extract", ctypes.c_double),
                 ("lookups_search", ctypes.c_uint64), ("lookups_extract", ctypes.c_uint64), ("launches", ctypes.c_uint64),
-                ("search_launches", ctypes.c_uint64), ("slow_reads", ctypes.c_uint64)]
+                ("search_launches", ctypes.c_uint64), ("slow_reads", ctypes.c_uint64), ("lines_search", ctypes.c_uint64)]
 
 
 EDGE_DTYPE = np.dtype([("query", "<u4"), ("target", "<u4"), ("length", "<u4"), ("af", "<u4")])
@@ -173,7 +173,7 @@ class Hits:
             sub, off, blocks = sub.copy(), off.copy(), blocks.copy()
         self.substring, self.block_off, self.blocks = sub, off, blocks
         self.stats = dict(ms_total=h.ms_total, ms_search=h.ms_search, ms_extract=h.ms_extract,
-                          lookups_search=int(h.lookups_search), lookups_extract=int(h.lookups_extract),
+                          lookups_search=int(h.lookups_search), lookups_extract=int(h.lookups_extract), lines_search=int(h.lines_search),
                           launches=int(h.launches), search_launches=int(h.search_launches), n_blocks=nb,
                           slow_reads=int(h.slow_reads))
 
@@ -200,7 +200,7 @@ class Edges:
             sub, edges = sub.copy(), edges.copy()
         self.n_reads, self.substring, self.edges = n, sub, edges
         self.stats = dict(ms_total=e.ms_total, ms_search=e.ms_search, ms_extract=e.ms_extract,
-                          lookups_search=int(e.lookups_search), lookups_extract=int(e.lookups_extract),
+                          lookups_search=int(e.lookups_search), lookups_extract=int(e.lookups_extract), lines_search=int(e.lines_search),
                           launches=int(e.launches), search_launches=int(e.search_launches),
                           slow_reads=int(e.slow_reads), n_blocks=int(e.n_blocks), n_edges=ne)
 

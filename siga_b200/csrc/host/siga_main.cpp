@@ -13,12 +13,15 @@
 // nothing downstream reads and are not produced.
 #include <fcntl.h>
 #include <getopt.h>
+#include <signal.h>
+#include <sys/prctl.h>
 #include <sys/wait.h>
 #include <unistd.h>
 #include <strings.h>
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <cstdarg>
@@ -56,6 +59,104 @@ int fail(sgx_ctx* ctx, const char* what, int rc) {
   fprintf(stderr, "ERROR siga - %s failed (%d): %s\n", what, rc, sgx_last_error(ctx));
   return -1;
 }
+
+// The worker processes of a `--gpus N` run (rank 0 is the calling process, ranks 1..N-1 are forked before any CUDA call).
+// A rank that fails leaves through _exit(1) while its peers may sit inside an NCCL collective that will never complete,
+// so the parent watches its children: the first one that ends badly gets the others killed, the part files removed and
+// the parent itself out with an error, wherever its main thread is blocked.  The same clean-up runs when the parent
+// returns early on an error of its own.  Children die with the parent (PR_SET_PDEATHSIG).
+class Gang {
+ public:
+  ~Gang() { abort_all(); }
+  // Forks ranks 1..world-1; returns this process's rank (0 in the parent), -1 when a fork failed.
+  int spawn(int world) {
+    fflush(nullptr);
+    const pid_t parent = getpid();
+    for (int r = 1; r < world; ++r) {
+      const pid_t pid = fork();
+      if (pid < 0) {
+        fprintf(stderr, "ERROR siga - fork failed\n");
+        abort_all();
+        return -1;
+      }
+      if (pid == 0) {
+        kids_.clear();  // not ours
+        prctl(PR_SET_PDEATHSIG, SIGKILL);
+        if (getppid() != parent) _exit(1);  // the parent went away between fork and prctl
+        return r;
+      }
+      kids_.push_back(pid);
+    }
+    done_.assign(kids_.size(), 0);
+    if (!kids_.empty()) monitor_ = std::thread([this]() { watch(); });
+    return 0;
+  }
+  void add_temp(const std::string& path) {
+    std::lock_guard<std::mutex> lk(m_);
+    temps_.push_back(path);
+  }
+  // Parent: waits for every child; true when all of them exited with status 0.
+  bool wait_all() {
+    if (monitor_.joinable()) monitor_.join();
+    return !failed_;
+  }
+  void remove_temps() {
+    std::lock_guard<std::mutex> lk(m_);
+    for (const auto& t : temps_) remove(t.c_str());
+    temps_.clear();
+  }
+
+ private:
+  void watch() {
+    size_t left = kids_.size();
+    while (left > 0) {
+      for (size_t i = 0; i < kids_.size(); ++i) {
+        if (done_[i]) continue;
+        int st = 0;
+        std::unique_lock<std::mutex> lk(km_);  // a pid is signalled only while it is known not to be reaped
+        const pid_t w = waitpid(kids_[i], &st, WNOHANG);
+        if (w == 0) continue;
+        done_[i] = 1;
+        lk.unlock();
+        --left;
+        if (w < 0 || !WIFEXITED(st) || WEXITSTATUS(st) != 0) {
+          failed_ = true;
+          if (!aborting_) {
+            // a worker failed while the others (and possibly this process's main thread) wait for it in a collective
+            fprintf(stderr, "ERROR siga - GPU worker process %d failed; stopping the other workers\n", (int)kids_[i]);
+            for (size_t k = 0; k < kids_.size(); ++k)
+              if (!done_[k]) kill(kids_[k], SIGKILL);
+            for (size_t k = 0; k < kids_.size(); ++k)
+              if (!done_[k]) waitpid(kids_[k], &st, 0);
+            remove_temps();
+            fflush(nullptr);
+            _exit(1);
+          }
+        }
+      }
+      if (left) std::this_thread::sleep_for(std::chrono::milliseconds(10));
+    }
+  }
+  void abort_all() {
+    aborting_ = true;
+    if (monitor_.joinable()) {
+      {
+        std::lock_guard<std::mutex> lk(km_);
+        for (size_t k = 0; k < kids_.size(); ++k)
+          if (!done_[k]) kill(kids_[k], SIGKILL);
+      }
+      monitor_.join();
+    }
+    kids_.clear();
+    remove_temps();
+  }
+  std::vector<pid_t> kids_;
+  std::vector<char> done_;
+  std::vector<std::string> temps_;
+  std::thread monitor_;
+  std::mutex m_, km_;
+  std::atomic<bool> failed_{false}, aborting_{false};
+};
 
 // One gzip member per chunk, compressed on worker threads, written in order (multi-member gzip is what zlib's and
 // boost's readers, hence `siga assemble`, accept).
@@ -441,7 +542,7 @@ int cmd_index(int argc, char** argv) {
   int rc = SGX_OK;
   const int world = o.gpus;
   int my = 0;
-  std::vector<pid_t> kids;
+  Gang gang;
   sgx_comm* comm = nullptr;
   if (world == 1) {
     std::thread init_thread([&]() { rc_init = sgx_init(o.device, &ctx); });  // CUDA start-up overlaps the parse
@@ -469,16 +570,7 @@ int cmd_index(int argc, char** argv) {
       rd[r] = fds[0];
       wr[r] = fds[1];
     }
-    fflush(nullptr);
-    for (int r = 1; r < world && my == 0; ++r) {
-      const pid_t pid = fork();
-      if (pid < 0) {
-        fprintf(stderr, "ERROR siga - fork failed\n");
-        return -1;
-      }
-      if (pid == 0) my = r;
-      else kids.push_back(pid);
-    }
+    if ((my = gang.spawn(world)) < 0) return -1;
     if ((rc_init = sgx_init(o.device + my, &ctx)) != SGX_OK) {
       fail(nullptr, "sgx_init", rc_init);
       if (my) _exit(1);
@@ -553,11 +645,7 @@ int cmd_index(int argc, char** argv) {
     sgx_shutdown(ctx);
     _exit(0);
   }
-  bool kids_ok = true;
-  for (pid_t pid : kids) {
-    int st = 0;
-    if (waitpid(pid, &st, 0) < 0 || !WIFEXITED(st) || WEXITSTATUS(st) != 0) kids_ok = false;
-  }
+  const bool kids_ok = gang.wait_all();
   if (!kids_ok) {
     fprintf(stderr, "ERROR siga - a GPU worker process failed\n");
     return -1;
@@ -619,19 +707,13 @@ int cmd_overlap(int argc, char** argv) {
   const uint64_t nf = in.nf, rnf = in.rnf;
   std::vector<uint32_t> rank;
   int my = 0;
-  std::vector<pid_t> kids;
+  Gang gang;
   if (world > 1) {
     rank = name_ranks(rs.names);  // before the fork: every rank needs it
-    fflush(nullptr);
-    for (int r = 1; r < world && my == 0; ++r) {
-      const pid_t pid = fork();
-      if (pid < 0) {
-        fprintf(stderr, "ERROR siga - fork failed\n");
-        return -1;
-      }
-      if (pid == 0) my = r;
-      else kids.push_back(pid);
-    }
+    if ((my = gang.spawn(world)) < 0) return -1;
+    if (my == 0)
+      for (int r = 0; r < world; ++r)
+        for (const char* ext : {".vt", ".ed"}) gang.add_temp(output + ".asqg.gz.part" + std::to_string(r) + ext);
     if ((in.ctx_rc = sgx_init(o.device + my, &in.ctx)) != SGX_OK) {
       fail(nullptr, "sgx_init", in.ctx_rc);
       if (my) _exit(1);
@@ -655,11 +737,20 @@ int cmd_overlap(int argc, char** argv) {
   } rank_joiner{rank_thread};
   sgx_reads* reads = nullptr;
   sgx_fm *fwd = nullptr, *rev = nullptr;
-  if ((rc = sgx_reads_pack(ctx, rs.bases.data(), rs.off.data(), rs.size(), &reads)) != SGX_OK) return fail(ctx, "sgx_reads_pack", rc);
-  if ((rc = sgx_fm_create(ctx, runs.data(), runs.size(), nf, &fwd)) != SGX_OK) return fail(ctx, "sgx_fm_create", rc);
-  if ((rc = sgx_fm_create(ctx, rruns.data(), rruns.size(), rnf, &rev)) != SGX_OK) return fail(ctx, "sgx_fm_create", rc);
-  if ((rc = sgx_fm_attach_reads(ctx, fwd, sai.data(), sai.size(), reads)) != SGX_OK) return fail(ctx, "sgx_fm_attach_reads", rc);
-  if ((rc = sgx_fm_attach_reads(ctx, rev, rsai.data(), rsai.size(), reads)) != SGX_OK) return fail(ctx, "sgx_fm_attach_reads", rc);
+  // a failing worker rank leaves through _exit so that the parent's watcher sees a non-zero status
+  auto bail = [&](const char* what, int code) {
+    fail(ctx, what, code);
+    if (my) {
+      if (rank_thread.joinable()) rank_thread.join();
+      _exit(1);
+    }
+    return -1;
+  };
+  if ((rc = sgx_reads_pack(ctx, rs.bases.data(), rs.off.data(), rs.size(), &reads)) != SGX_OK) return bail("sgx_reads_pack", rc);
+  if ((rc = sgx_fm_create(ctx, runs.data(), runs.size(), nf, &fwd)) != SGX_OK) return bail("sgx_fm_create", rc);
+  if ((rc = sgx_fm_create(ctx, rruns.data(), rruns.size(), rnf, &rev)) != SGX_OK) return bail("sgx_fm_create", rc);
+  if ((rc = sgx_fm_attach_reads(ctx, fwd, sai.data(), sai.size(), reads)) != SGX_OK) return bail("sgx_fm_attach_reads", rc);
+  if ((rc = sgx_fm_attach_reads(ctx, rev, rsai.data(), rsai.size(), reads)) != SGX_OK) return bail("sgx_fm_attach_reads", rc);
   info("fm-index: %llu symbols in %zu runs (%.4f symbols per run)", (unsigned long long)nf, runs.size(),
        runs.empty() ? 0.0 : (double)nf / runs.size());
   sgx_edges ed;
@@ -689,10 +780,7 @@ int cmd_overlap(int argc, char** argv) {
       sgx_shutdown(ctx);
       _exit(good ? 0 : 1);
     }
-    for (pid_t pid : kids) {
-      int st = 0;
-      if (waitpid(pid, &st, 0) < 0 || !WIFEXITED(st) || WEXITSTATUS(st) != 0) good = false;
-    }
+    if (!gang.wait_all()) good = false;
     if (good) {
       FILE* f = fopen(final_path.c_str(), "wb");
       good = f != nullptr;
@@ -701,8 +789,7 @@ int cmd_overlap(int argc, char** argv) {
           good = append_file(f, final_path + ".part" + std::to_string(r) + (pass == 0 ? ".vt" : ".ed"));
       if (f && fclose(f) != 0) good = false;
     }
-    for (int r = 0; r < world; ++r)
-      for (const char* ext : {".vt", ".ed"}) remove((final_path + ".part" + std::to_string(r) + ext).c_str());
+    gang.remove_temps();
   }
   if (!good) {
     fprintf(stderr, "ERROR siga - write to %s.asqg.gz failed\n", output.c_str());
@@ -1011,18 +1098,11 @@ int cmd_correct(int argc, char** argv) {
     return -1;
   }
   int my = 0;
-  std::vector<pid_t> kids;
+  Gang gang;
   if (world > 1) {
-    fflush(nullptr);
-    for (int r = 1; r < world && my == 0; ++r) {
-      const pid_t pid = fork();
-      if (pid < 0) {
-        fprintf(stderr, "ERROR siga - fork failed\n");
-        return -1;
-      }
-      if (pid == 0) my = r;
-      else kids.push_back(pid);
-    }
+    if ((my = gang.spawn(world)) < 0) return -1;
+    if (my == 0)
+      for (int r = 0; r < world; ++r) gang.add_temp(outfile + ".part" + std::to_string(r));
     ctx_rc = sgx_init(o.device + my, &ctx);
     o.threads = std::max(1, o.threads / world);
   }
@@ -1065,17 +1145,14 @@ int cmd_correct(int argc, char** argv) {
       sgx_shutdown(ctx);
       _exit(good ? 0 : 1);
     }
-    for (pid_t pid : kids) {
-      int stt = 0;
-      if (waitpid(pid, &stt, 0) < 0 || !WIFEXITED(stt) || WEXITSTATUS(stt) != 0) good = false;
-    }
+    if (!gang.wait_all()) good = false;
     if (good) {
       FILE* f = fopen(outfile.c_str(), "wb");
       good = f != nullptr;
       for (int r = 0; r < world && good; ++r) good = append_file(f, outfile + ".part" + std::to_string(r));
       if (f && fclose(f) != 0) good = false;
     }
-    for (int r = 0; r < world; ++r) remove((outfile + ".part" + std::to_string(r)).c_str());
+    gang.remove_temps();
   }
   if (!good) {
     fprintf(stderr, "ERROR siga - Failed to create DNASeqWriter %s\n", outfile.c_str());

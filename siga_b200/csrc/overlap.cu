@@ -145,6 +145,7 @@ struct OvPlan {
   ReadsView rv, treads;
   SaView sf, sr;
   bool narrow, fast;
+  size_t persist_bytes, persist_window;  // SGX_L2_PERSIST experiment: persisting-L2 carve-out, max window
   uint32_t find_cap, out_cap, rows_cap, extw;
   unsigned grid_search, grid_post, grid_reduce;
   // general-path work area (allocated on first use, regrown on overflow)
@@ -153,7 +154,7 @@ struct OvPlan {
   DevBuf<uint32_t> d_gd;
   bool arena_ready;
   DevBuf<uint32_t> d_status;
-  DevBuf<unsigned long long> d_look;  // [0] search lookups, [1] general-path lookups
+  DevBuf<unsigned long long> d_look;  // [0] search lookups, [1] general-path lookups, [2] rank-block lines the search fetched
 
   void init(sgx_ctx* c, const sgx_fm* f, const sgx_fm* r, const sgx_reads* rd, uint64_t fst, uint64_t cnt, uint32_t m,
             int irr, int rcomp) {
@@ -191,9 +192,17 @@ struct OvPlan {
     ac.st_cap = 4 * ac.list_cap;
     ac.g_cap = 256;
     arena_ready = false;
+    persist_bytes = persist_window = 0;
+    if (env_u64("SGX_L2_PERSIST", 0)) {
+      cudaDeviceProp pr;
+      SGX_CUDA(cudaGetDeviceProperties(&pr, c->device));
+      persist_bytes = (size_t)pr.persistingL2CacheMaxSize;
+      persist_window = (size_t)pr.accessPolicyMaxWindowSize;
+      SGX_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist_bytes));
+    }
     d_status.alloc(1);
-    d_look.alloc(2);
-    SGX_CUDA(cudaMemsetAsync(d_look.p, 0, 2 * sizeof(unsigned long long), c->stream));
+    d_look.alloc(3);
+    SGX_CUDA(cudaMemsetAsync(d_look.p, 0, 3 * sizeof(unsigned long long), c->stream));
     // fast post path: needs the read-start orders and the indexed read set on the device (sgx_fm_attach_reads)
     fast = f->sai && r->sai && f->indexed && f->indexed == r->indexed && f->indexed->max_len < 65536 &&
            f->indexed->ctx == c && lmax < 65536;
@@ -227,18 +236,63 @@ struct OvPlan {
     arena_ready = true;
   }
 
+  // lean search: resident CTAs per SM selectable for experiments (SGX_LEAN_MINB = 4 / 5 / 6)
+  template <class IdxT>
+  void launch_lean(uint64_t rfirst, uint64_t n, const OvBatch& bt, const uint32_t* list) {
+    const int minb = (int)env_u64("SGX_LEAN_MINB", 4);
+    const unsigned grid = (unsigned)ctx->sm_count * 2 * (unsigned)minb;
+    // uniform: the queries are the indexed reads and all of them have one length (see the kernel's header)
+    const bool uni = fast && reads == fwd->indexed && reads->min_len == reads->max_len;
+    if (minb == 9) {  // experiments: the round-1 kernel (full rank vectors, other-side interval carried along)
+      SGX_LAUNCH(ctx, (ov_search_quad_kernel<IdxT, true>), grid_search, kOvThreads, 0, fmp, rv, rfirst, n, min_ov, rc, bt, list, d_look.p);
+      return;
+    }
+    // SGX_L2_PERSIST=1 (experiment): one launch per index, its rank blocks under a persisting-L2 access window
+    const bool persist = env_u64("SGX_L2_PERSIST", 0) != 0;
+    for (int pass = 0; pass < (persist ? 2 : 1); ++pass) {
+      const int only = persist ? pass : -1;
+      if (persist) {
+        cudaStreamAttrValue av;
+        memset(&av, 0, sizeof(av));
+        const sgx_fm* f = pass == 0 ? fwd : rev;
+        av.accessPolicyWindow.base_ptr = (void*)f->blocks;
+        av.accessPolicyWindow.num_bytes = std::min<size_t>(fm_num_blocks(f->n) * 128, persist_window);
+        av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)persist_bytes / (double)av.accessPolicyWindow.num_bytes);
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        SGX_CUDA(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &av));
+      }
+      if (minb == 6) {
+        if (uni) SGX_LAUNCH(ctx, (ov_search_lean_kernel<IdxT, 6, true>), grid, kOvThreads, 0, fmp, rv, rfirst, n, min_ov, rc, bt, list, d_look.p, only);
+        else SGX_LAUNCH(ctx, (ov_search_lean_kernel<IdxT, 6, false>), grid, kOvThreads, 0, fmp, rv, rfirst, n, min_ov, rc, bt, list, d_look.p, only);
+      } else if (minb == 5) {
+        if (uni) SGX_LAUNCH(ctx, (ov_search_lean_kernel<IdxT, 5, true>), grid, kOvThreads, 0, fmp, rv, rfirst, n, min_ov, rc, bt, list, d_look.p, only);
+        else SGX_LAUNCH(ctx, (ov_search_lean_kernel<IdxT, 5, false>), grid, kOvThreads, 0, fmp, rv, rfirst, n, min_ov, rc, bt, list, d_look.p, only);
+      } else {
+        if (uni) SGX_LAUNCH(ctx, (ov_search_lean_kernel<IdxT, 4, true>), grid, kOvThreads, 0, fmp, rv, rfirst, n, min_ov, rc, bt, list, d_look.p, only);
+        else SGX_LAUNCH(ctx, (ov_search_lean_kernel<IdxT, 4, false>), grid, kOvThreads, 0, fmp, rv, rfirst, n, min_ov, rc, bt, list, d_look.p, only);
+      }
+    }
+    if (persist) {
+      cudaStreamAttrValue av;
+      memset(&av, 0, sizeof(av));
+      av.accessPolicyWindow.num_bytes = 0;
+      SGX_CUDA(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &av));
+    }
+  }
+
   // search of `n` work items starting at read `rfirst` (or the reads of `list`, relative to rfirst)
   void search(bool lean, uint64_t rfirst, uint64_t n, const OvBatch& bt, const uint32_t* list) {
     if (n == 0) return;
     if (narrow) {
       if (lean) {
-        SGX_LAUNCH(ctx, (ov_search_quad_kernel<uint32_t, true>), grid_search, kOvThreads, 0, fmp, rv, rfirst, n, min_ov, rc, bt, list, d_look.p);
+        launch_lean<uint32_t>(rfirst, n, bt, list);
       } else {
         SGX_LAUNCH(ctx, (ov_search_quad_kernel<uint32_t, false>), grid_search, kOvThreads, 0, fmp, rv, rfirst, n, min_ov, rc, bt, list, d_look.p);
       }
     } else {
       if (lean) {
-        SGX_LAUNCH(ctx, (ov_search_quad_kernel<uint64_t, true>), grid_search, kOvThreads, 0, fmp, rv, rfirst, n, min_ov, rc, bt, list, d_look.p);
+        launch_lean<uint64_t>(rfirst, n, bt, list);
       } else {
         SGX_LAUNCH(ctx, (ov_search_quad_kernel<uint64_t, false>), grid_search, kOvThreads, 0, fmp, rv, rfirst, n, min_ov, rc, bt, list, d_look.p);
       }
@@ -398,10 +452,11 @@ void overlap_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const sgx_r
   if (count) SGX_CUDA(cudaMemcpyAsync(hits->substring, core.sub.p, count, cudaMemcpyDeviceToHost, ctx->stream));
   if (core.n_blocks)
     SGX_CUDA(cudaMemcpyAsync(hits->blocks, core.compact.p, core.n_blocks * sizeof(sgx_block), cudaMemcpyDeviceToHost, ctx->stream));
-  unsigned long long look[2] = {0, 0};
+  unsigned long long look[3] = {0, 0, 0};
   SGX_CUDA(cudaMemcpyAsync(look, pl.d_look.p, sizeof(look), cudaMemcpyDeviceToHost, ctx->stream));
   t_all.stop();
   SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+  hits->lines_search = look[2];
   hits->ms_total = t_all.ms();
   hits->ms_search = k_search.total_ms();
   hits->ms_extract = k_post.total_ms();
@@ -489,7 +544,7 @@ void overlap_edges_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const
     SGX_CUDA(cudaMemsetAsync(d_sub.p, 0, std::max<uint64_t>(count, 1), ctx->stream));
     SGX_CUDA(cudaMemsetAsync(d_flags.p, 0, 2 * sizeof(uint32_t), ctx->stream));
     SGX_CUDA(cudaMemsetAsync(d_counter.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
-    SGX_CUDA(cudaMemsetAsync(pl.d_look.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    SGX_CUDA(cudaMemsetAsync(pl.d_look.p, 0, 3 * sizeof(unsigned long long), ctx->stream));
     EdgeSink sink;
     sink.edges = d_edges.p;
     sink.counter = d_counter.p;
@@ -506,8 +561,17 @@ void overlap_edges_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const
       batch = std::min<uint64_t>(batch, std::max<uint64_t>(count, 1));
       DevBuf<LeanCand> d_lean(batch * 4 * pl.find_cap), d_lcontain(batch * 4);
       DevBuf<uint32_t> d_ncand(batch * 4), d_ncontain(batch * 4);
-      const size_t smem = pl.reduce_smem(true);
-      SGX_CUDA(cudaFuncSetAttribute(ov_reduce_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const sgx_reads* idx = fwd->indexed;
+      const bool uniform = idx->min_len == idx->max_len;
+      uint32_t rows = (uint32_t)env_u64("SGX_REDUCE_ROWS", 128);  // rows of a read held in shared memory at a time
+      while (rows > 32 && reduce_lean_smem_per_warp(rows, pl.extw) * kRlWarps > (size_t)200 * 1024) rows /= 2;
+      const size_t smem = reduce_lean_smem_per_warp(rows, pl.extw) * kRlWarps;
+      SGX_CUDA(cudaFuncSetAttribute(ov_reduce_lean_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      SGX_CUDA(cudaFuncSetAttribute(ov_reduce_lean_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const unsigned grid_rl = (unsigned)ctx->sm_count * (unsigned)env_u64("SGX_REDUCE_CTAS", 16);
+      const bool old_reduce = env_u64("SGX_REDUCE_OLD", 0) != 0;
+      const size_t smem_old = pl.reduce_smem(true);
+      SGX_CUDA(cudaFuncSetAttribute(ov_reduce_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_old));
       for (uint64_t b0 = 0; b0 < count; b0 += batch) {
         const uint64_t bn = std::min<uint64_t>(batch, count - b0);
         OvBatch bt;
@@ -525,8 +589,16 @@ void overlap_edges_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const
         ++search_launches;
         sink.qbase = first + b0;
         k_post.tick();
-        SGX_LAUNCH(ctx, (ov_reduce_kernel<true, true>), pl.grid_reduce, kRdWarps * 32, smem, pl.rv, pl.treads, pl.sf, pl.sr, bn,
-                   irreducible, bt, pl.rows_cap, pl.extw, b0, d_slow.p, d_flags.p, sink);
+        if (old_reduce) {  // experiments: the round-1 kernel (one side after the other, staged edges)
+          SGX_LAUNCH(ctx, (ov_reduce_kernel<true, true>), pl.grid_reduce, kRdWarps * 32, smem_old, pl.rv, pl.treads, pl.sf, pl.sr, bn,
+                     irreducible, bt, pl.rows_cap, pl.extw, b0, d_slow.p, d_flags.p, sink);
+        } else if (uniform) {
+          SGX_LAUNCH(ctx, (ov_reduce_lean_kernel<true>), grid_rl, kRlWarps * 32, smem, pl.rv, pl.treads, idx->max_len,
+                     (idx->max_len + 15) / 16, pl.sf, pl.sr, bn, irreducible, bt, rows, pl.extw, b0, d_slow.p, d_flags.p, sink);
+        } else {
+          SGX_LAUNCH(ctx, (ov_reduce_lean_kernel<false>), grid_rl, kRlWarps * 32, smem, pl.rv, pl.treads, 0u, 0u, pl.sf,
+                     pl.sr, bn, irreducible, bt, rows, pl.extw, b0, d_slow.p, d_flags.p, sink);
+        }
         k_post.tick();
       }
       uint32_t fl[2] = {0, 0};
@@ -604,10 +676,11 @@ void overlap_edges_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const
   if (count) SGX_CUDA(cudaMemcpyAsync(out->substring, d_sub.p, count, cudaMemcpyDeviceToHost, ctx->stream));
   if (n_edges)
     SGX_CUDA(cudaMemcpyAsync(out->edges, d_edges.p, n_edges * sizeof(sgx_edge), cudaMemcpyDeviceToHost, ctx->stream));
-  unsigned long long look[2] = {0, 0};
+  unsigned long long look[3] = {0, 0, 0};
   SGX_CUDA(cudaMemcpyAsync(look, pl.d_look.p, sizeof(look), cudaMemcpyDeviceToHost, ctx->stream));
   t_all.stop();
   SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+  out->lines_search = look[2];
   out->ms_total = t_all.ms();
   out->ms_search = k_search.total_ms();
   out->ms_extract = k_post.total_ms();

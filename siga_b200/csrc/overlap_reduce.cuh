@@ -439,6 +439,269 @@ ov_reduce_kernel(ReadsView qreads, ReadsView treads, SaView sf, SaView sr, uint6
   }
 }
 
+
+// ---- lean reduce (sgx_overlap_edges): the same rule on the 12-byte candidates, reorganised for latency ------------
+//
+// ov_reduce_kernel above serves both output forms; for the edge pipeline it walks a read's two sides one after the other,
+// each a chain of dependent gathers (candidate -> .sai row -> length -> word offset -> read words -> name rank), and
+// re-reads the candidates from global memory in every phase.  This kernel does the work of one read in ONE pass:
+//   * the candidate entries of all four lists and the containment entries are copied to shared memory once (coalesced);
+//   * the rows of both sides and of the containment blocks go into one table, so that the gathers of every row of the
+//     read (.sai, read words, name rank) are in flight together: four dependent round trips per read instead of twelve;
+//   * reads of one common length (known when the read store was packed) need no gather of len[] / woff[] at all;
+//   * edges are counted with a ballot, reserved with one atomic per read and written straight from the row table (no
+//     staging area), which shrinks the shared-memory footprint per warp.
+// Preconditions and fallbacks are those of ov_reduce_kernel (anything else goes to the slow list, nothing is approximated);
+// a read whose rows do not fit the table in one pass takes its sides one at a time.
+static const int kRlWarps = 4;
+static const int kRlEntCap = 96;   // candidate + containment entries per read held in shared memory
+
+__host__ __device__ inline size_t reduce_lean_smem_per_warp(uint32_t rows_cap, uint32_t extw) {
+  return (size_t)rows_cap * extw * 8 + (size_t)rows_cap * (4 + 4 + 2 + 1 + 1) + (size_t)kRlEntCap * 12;
+}
+
+template <bool UNIFORM>
+__global__ void __launch_bounds__(kRlWarps * 32)
+ov_reduce_lean_kernel(ReadsView qreads, ReadsView treads, uint32_t ulen, uint32_t uwords, SaView sf, SaView sr,
+                      uint64_t count, int irreducible, OvBatch bt, uint32_t rows_cap, uint32_t extw, uint64_t slow_base,
+                      uint32_t* __restrict__ slow_list, uint32_t* __restrict__ n_slow, EdgeSink sink) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const unsigned kFull = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  unsigned char* base = smem_raw + (size_t)wib * reduce_lean_smem_per_warp(rows_cap, extw);
+  uint64_t* ext = reinterpret_cast<uint64_t*>(base);                             // [rows_cap][extw]
+  uint32_t* r_row = reinterpret_cast<uint32_t*>(ext + (size_t)rows_cap * extw);  // row in the '$' block
+  uint32_t* r_tgt = r_row + rows_cap;                                            // target read id
+  uint16_t* r_n = reinterpret_cast<uint16_t*>(r_tgt + rows_cap);                 // extension length (bases)
+  uint8_t* r_ent = reinterpret_cast<uint8_t*>(r_n + rows_cap);                   // entry index
+  uint8_t* r_flag = r_ent + rows_cap;                                            // bit0 transitive, bit1 passes the edge filter
+  uint32_t* e_lo = reinterpret_cast<uint32_t*>(r_flag + rows_cap);               // entries: capped[0], length | af << 16
+  uint32_t* e_hi = e_lo + kRlEntCap;
+  uint32_t* e_kaf = e_hi + kRlEntCap;
+
+  const uint64_t warp0 = (uint64_t)blockIdx.x * kRlWarps + wib;
+  const uint64_t nwarps = (uint64_t)gridDim.x * kRlWarps;
+  for (uint64_t r = warp0; r < count; r += nwarps) {
+    // ---- entries: lists 0..3 (search modes), then the containment entry of each mode that has one
+    const uint4 nc4 = *reinterpret_cast<const uint4*>(bt.ncand + r * 4);
+    const uint4 nk4 = *reinterpret_cast<const uint4*>(bt.ncontain + r * 4);
+    const uint32_t nc[4] = {nc4.x, nc4.y, nc4.z, nc4.w};
+    const uint32_t nk[4] = {nk4.x, nk4.y, nk4.z, nk4.w};
+    const uint32_t eb1 = nc[0], eb2 = eb1 + nc[1], eb3 = eb2 + nc[2], Ec = eb3 + nc[3];  // list f starts at eb_f
+    const uint32_t E = Ec + 4;  // containment slots Ec + q; absent ones are empty intervals
+    const uint64_t qglob = sink.qbase + r;
+    const uint32_t lq = UNIFORM ? ulen : qreads.len[qglob];
+    const uint32_t rq = sink.name_rank[qglob];
+    bool slow = E > (uint32_t)kRlEntCap;
+    if (!slow) {
+      for (uint32_t e = lane; e < E; e += 32) {
+        LeanCand c;
+        if (e < Ec) {
+          const int f = (e >= eb1) + (e >= eb2) + (e >= eb3);
+          const uint32_t i = e - (f == 0 ? 0u : f == 1 ? eb1 : f == 2 ? eb2 : eb3);
+          c = bt.lean[((size_t)r * 4 + f) * bt.find_cap + i];
+        } else if (nk[e - Ec]) {
+          c = bt.lean_contain[(size_t)r * 4 + (e - Ec)];
+        } else {
+          c.lo = 1;
+          c.hi = 0;
+          c.len_af = 0;
+        }
+        e_lo[e] = c.lo;
+        e_hi[e] = c.hi;
+        e_kaf[e] = c.len_af;
+      }
+      __syncwarp();
+      // ---- SubMaximalBlockFilter precondition (src/overlap_builder.cpp:929-953): inside one list -- its candidates plus the
+      //      containment entries of its index side -- no two capped[0] intervals may intersect
+      bool inter = false;
+      for (uint32_t e = lane; e < Ec; e += 32) {
+        const int f = (e >= eb1) + (e >= eb2) + (e >= eb3);
+        const uint32_t f0 = f == 0 ? 0u : f == 1 ? eb1 : f == 2 ? eb2 : eb3;
+        const uint32_t lo = e_lo[e], hi = e_hi[e];
+        for (uint32_t e2 = f0; e2 < e; ++e2) inter |= rd_intersect(lo, hi, e_lo[e2], e_hi[e2]);
+        const uint32_t q0 = Ec + (f < 2 ? 0u : 2u);
+        inter |= (e_hi[q0] >= e_lo[q0] && rd_intersect(lo, hi, e_lo[q0], e_hi[q0])) ||
+                 (e_hi[q0 + 1] >= e_lo[q0 + 1] && rd_intersect(lo, hi, e_lo[q0 + 1], e_hi[q0 + 1]));
+      }
+      if (lane < 2) {  // the two containment entries of an index side against each other
+        const uint32_t q0 = Ec + 2 * lane;
+        inter |= e_hi[q0] >= e_lo[q0] && e_hi[q0 + 1] >= e_lo[q0 + 1] && rd_intersect(e_lo[q0], e_hi[q0], e_lo[q0 + 1], e_hi[q0 + 1]);
+      }
+      if (__any_sync(kFull, inter)) slow = true;  // periodic sequence: the filter must run (literal path)
+    }
+    // ---- row counts per side (lists 0 and 3 extend to the right, 1 and 2 to the left) and of the containment entries
+    unsigned long long at = 0;
+    if (!slow) {
+      uint32_t w[3] = {0, 0, 0};
+      for (uint32_t e = lane; e < E; e += 32) {
+        const uint64_t ww = e_hi[e] >= e_lo[e] ? (uint64_t)e_hi[e] - e_lo[e] + 1 : 0;
+        const uint32_t wc = ww > rows_cap ? rows_cap + 1 : (uint32_t)ww;
+        const int g = e >= Ec ? 2 : ((e < eb1 || e >= eb3) ? 0 : 1);
+        w[g] = min(w[g] + wc, rows_cap + 1);
+      }
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) w[g] = min(w[g] + __shfl_xor_sync(kFull, w[g], o), rows_cap + 1);
+      }
+      // passes: everything at once when it fits, else one group (side / containment) at a time
+      // (one group at a time only for reads of one length: there no check can fail after a pass has written edges)
+      const bool one_pass = w[0] + w[1] + w[2] <= rows_cap;
+      if (!one_pass && (!UNIFORM || w[0] > rows_cap || w[1] > rows_cap || w[2] > rows_cap)) slow = true;
+      const int npass = one_pass ? 1 : 3;
+      for (int pass = 0; pass < npass && !slow; ++pass) {
+        // ---- rows of this pass: (entry, row of its interval), entries in list order 0,3 | 1,2 | containment
+        uint32_t R = 0, side_end[3] = {0, 0, 0};
+#pragma unroll 1
+        for (int g = 0; g < 3; ++g) {
+          if (one_pass || g == pass) {
+            // entries of group g in the order the reference concatenates the lists: g0 = list 0 then 3, g1 = 1 then 2
+            const uint32_t aS = g == 0 ? 0u : g == 1 ? eb1 : Ec, aE = g == 0 ? eb1 : g == 1 ? eb2 : E;
+            const uint32_t bS = g == 0 ? eb3 : g == 1 ? eb2 : E, bE = g == 0 ? Ec : g == 1 ? eb3 : E;
+            const uint32_t ne = (aE - aS) + (bE - bS);
+            for (uint32_t i0 = 0; i0 < ne; i0 += 32) {
+              const uint32_t i = i0 + lane;
+              uint32_t e = 0, wd = 0;
+              if (i < ne) {
+                e = i < aE - aS ? aS + i : bS + (i - (aE - aS));
+                wd = e_hi[e] >= e_lo[e] ? e_hi[e] - e_lo[e] + 1 : 0;
+              }
+              uint32_t incl = wd;
+#pragma unroll
+              for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(kFull, incl, o);
+                if (lane >= o) incl += y;
+              }
+              const uint32_t a = R + incl - wd;
+              for (uint32_t x = 0; x < wd; ++x) {
+                r_row[a + x] = e_lo[e] + x;
+                r_ent[a + x] = (uint8_t)e;
+              }
+              R += __shfl_sync(kFull, incl, 31);
+            }
+          }
+          side_end[g] = R;
+        }
+        __syncwarp();
+        // ---- per row: target read, edge filter, extension string in query orientation (word level)
+        bool mixed = false;
+        uint32_t len_first[2] = {0xffffffffu, 0xffffffffu};
+        for (uint32_t s = lane; s < R; s += 32) {
+          const uint32_t e = r_ent[s];
+          const uint32_t kaf = e_kaf[e];
+          const uint32_t k = kaf & 0xffffu, af = kaf >> 16;
+          const bool tr = (af & SGX_AF_TARGETREV) != 0;
+          const uint32_t t = (tr ? sr.sa : sf.sa)[r_row[s]];
+          const uint32_t lt = UNIFORM ? ulen : treads.len[t];
+          const uint32_t rt = sink.name_rank[t];
+          r_tgt[s] = t;
+          const bool contain = k == lq || k == lt;
+          const bool okf = rq != rt && !(rq < rt || (contain && (af & SGX_AF_QUERYREV)));
+          uint8_t flag = okf ? 2 : 0;
+          if (s < side_end[1] && irreducible) {
+            const int g = s < side_end[0] ? 0 : 1;
+            if (len_first[g] == 0xffffffffu) len_first[g] = lt;
+            if (len_first[g] != lt) mixed = true;
+            const uint32_t n = lt - k;
+            if (n > extw * 32) mixed = true;  // cannot happen when extw covers max_len - min_overlap
+            r_n[s] = (uint16_t)n;
+            const uint32_t* wsrc = treads.words + (UNIFORM ? (uint64_t)t * uwords : treads.woff[t]);
+            const uint32_t cm = (af & SGX_AF_QUERYCOMP) ? 0xffffffffu : 0u;
+            uint64_t* dst = ext + (size_t)s * extw;
+            if (!mixed) {
+              for (uint32_t q = 0; q < extw; ++q) {
+                uint64_t v = 0;
+                if (32 * q < n) {
+                  const uint32_t lo = rd_ext16(wsrc, lt, k, tr, 2 * q) ^ cm;
+                  const uint32_t hi = (32 * q + 16 < n) ? (rd_ext16(wsrc, lt, k, tr, 2 * q + 1) ^ cm) : 0u;
+                  v = ((uint64_t)hi << 32) | lo;
+                  const uint32_t left = n - 32 * q;
+                  if (left < 32) v &= (1ull << (2 * left)) - 1ull;
+                }
+                dst[q] = v;
+              }
+            }
+          }
+          r_flag[s] = flag;
+        }
+        if (!UNIFORM && irreducible) {
+          // all targets of a side must have one length (else the group semantics are not the simple rule)
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const uint32_t mn = __reduce_min_sync(kFull, len_first[g]);
+            if (len_first[g] != 0xffffffffu && len_first[g] != mn) mixed = true;
+          }
+        }
+        if (__any_sync(kFull, mixed)) {
+          slow = true;
+          break;
+        }
+        __syncwarp();
+        // ---- transitive rows: some row of the same side with a longer overlap has its whole extension as a prefix.
+        //      Rows with longer overlaps are scanned from the end of the side (entries come in increasing overlap length).
+        for (uint32_t s = lane; s < side_end[1] && irreducible; s += 32) {
+          const uint32_t s0 = s < side_end[0] ? 0u : side_end[0], s1 = s < side_end[0] ? side_end[0] : side_end[1];
+          const uint32_t ka = e_kaf[r_ent[s]] & 0xffffu;
+          const uint64_t* ea = ext + (size_t)s * extw;
+          bool red = false;
+          for (uint32_t b2 = s1; b2-- > s0 && !red;) {
+            if ((e_kaf[r_ent[b2]] & 0xffffu) <= ka) continue;
+            const uint32_t nb = r_n[b2];
+            const uint64_t* eb = ext + (size_t)b2 * extw;
+            bool eq = true;
+            const uint32_t full = nb >> 5;
+            for (uint32_t q = 0; q < full && eq; ++q) eq = ea[q] == eb[q];
+            if (eq && (nb & 31)) {
+              const uint64_t m = (1ull << (2 * (nb & 31))) - 1ull;
+              eq = ((ea[full] ^ eb[full]) & m) == 0;
+            }
+            red = eq;
+          }
+          if (red) r_flag[s] |= 1;
+        }
+        __syncwarp();
+        // ---- edges of this pass: count, reserve, write
+        uint32_t cnt = 0;
+        for (uint32_t s = lane; s < R; s += 32) cnt += r_flag[s] == 2 ? 1u : 0u;
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t y = __shfl_up_sync(kFull, incl, o);
+          if (lane >= o) incl += y;
+        }
+        const uint32_t tot = __shfl_sync(kFull, incl, 31);
+        if (tot) {
+          if (lane == 0) at = atomicAdd(sink.counter, (unsigned long long)tot);
+          at = __shfl_sync(kFull, at, 0);
+          if (at + tot > sink.cap) {
+            if (lane == 0) atomicOr(sink.overflow, 1u);
+          } else {
+            unsigned long long o = at + incl - cnt;
+            for (uint32_t s = lane; s < R; s += 32) {
+              if (r_flag[s] == 2) {
+                const uint32_t kaf = e_kaf[r_ent[s]];
+                sgx_edge ed;
+                ed.query = (uint32_t)qglob;
+                ed.target = r_tgt[s];
+                ed.length = kaf & 0xffffu;
+                ed.af = kaf >> 16;
+                sink.edges[o++] = ed;
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    // every check that can fail (entry / row capacity, intersections, mixed target lengths) fails before the first edge
+    // of the read is written: in one-pass mode they all precede the write, group-at-a-time mode is for uniform reads only
+    if (lane == 0 && slow) slow_list[atomicAdd(n_slow, 1u)] = (uint32_t)(slow_base + r);
+    __syncwarp();
+  }
+}
+
 }  // namespace sgx
 
 #endif  // SGX_OVERLAP_REDUCE_CUH_

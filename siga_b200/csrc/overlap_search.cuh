@@ -54,7 +54,7 @@ ov_search_quad_kernel(FmPair fm, ReadsView reads, uint64_t first, uint64_t count
   const uint64_t nquads = ((uint64_t)gridDim.x * blockDim.x) / kQuad;
   const int nmodes = rc ? 4 : 2;
   const uint64_t nwork = count * nmodes;
-  unsigned long long nlook = 0;
+  unsigned long long nlook = 0, nlines = 0;
   const IdxT kNone = (IdxT)-1;
 
   for (uint64_t wk = quad; __any_sync(kFull, wk < nwork); wk += nquads) {
@@ -102,6 +102,7 @@ ov_search_quad_kernel(FmPair fm, ReadsView reads, uint64_t first, uint64_t count
       for (int m = 1; m < kQuad; m <<= 1) below += __shfl_xor_sync(kFull, below, m);
       if (live) {
         nlook += 2;
+        nlines += (((uint64_t)lo0 >> kBlockShift) != ((uint64_t)(IdxT)(hi0 + 1) >> kBlockShift)) ? 2 : 1;
         const IdxT dd = k.Ud - k.Ld;
         const uint32_t olen = l - i;
         if (olen >= min_ov && dd >= 1) {
@@ -156,10 +157,12 @@ ov_search_quad_kernel(FmPair fm, ReadsView reads, uint64_t first, uint64_t count
         if (need3) {
           U3d = k3.Ud;
           nlook += 1;
+          nlines += 1;
         }
       }
       if (tail) {
         nlook += 4;
+        nlines += 4;
         if (dna) {
           if (q == 0) bt.substring[r] = 1;
         } else if (want) {
@@ -200,7 +203,285 @@ ov_search_quad_kernel(FmPair fm, ReadsView reads, uint64_t first, uint64_t count
       }
     }
   }
-  if (q == 0 && nlook) atomicAdd(lookups, nlook);
+  if (q == 0 && nlook) {
+    atomicAdd(lookups, nlook);
+    atomicAdd(lookups + 2, nlines);
+  }
+}
+
+
+// ---- lean search (sgx_overlap_edges): the walk the edge pipeline needs, at a third of the instructions --------------
+//
+// The edge pipeline consumes capped[0] of the '$' blocks only (LeanCand).  Per backward step that takes
+//   * the rank of ONE symbol at both interval ends (the next interval): quad_rank_sym's arithmetic -- one popcount per
+//     uint4, both ends packed in one register, two xor-shuffles, headers from lane c-1;
+//   * once the overlap length has reached min_overlap, the number of '$' rows inside the interval: the in-block '$'
+//     counts at both ends and the header difference of the two blocks packed into ONE register (9 + 9 + 14 bits; a
+//     quad whose ends lie more than 63 blocks apart takes the full rank query instead), two more shuffles.  Steps
+//     shorter than min_overlap skip the '$' probe altogether (30 % of the steps at L = 150, m = 45);
+//   * '$' ranks themselves (the block headers summed over the quad) only on the steps that emit a block.
+// The other-side interval (IntervalPair's second half, src/overlap_builder.cpp:70-136) is not carried through the walk:
+// only the containment tail reads it, for the ~2 % of (read, mode) pairs whose full-length interval is non-empty, and
+// there it is recomputed by a plain backward search of the reversed string in the opposite index (the bidirectional
+// invariant: it IS the interval of reverse(X) there).
+// UNIFORM (every indexed read has the same length, and the queries are the indexed reads): a full-length match is an
+// identical read, every row of its interval holds '$' in both indices, so the containment block is the '$' rank of the
+// interval's first row and its width -- one rank-block fetch, no walk through the opposite index.  (Modes 0 and 2 always
+// end with a full-length match: the read finds itself.)
+// Work order: all (read, mode) pairs that search the forward index first, then those of the reverse index; the quads of
+// the grid advance together, so at any time one index (232 MB at config 2) competes for the 126 MB L2, not both.
+// The symbol stream is read one 32-bit word per 16 steps.
+template <class IdxT, int MINB, bool UNIFORM>
+__global__ void __launch_bounds__(256, MINB)
+ov_search_lean_kernel(FmPair fm, ReadsView reads, uint64_t first, uint64_t count, uint32_t min_ov, int rc,
+                      OvBatch bt, const uint32_t* __restrict__ list, unsigned long long* __restrict__ lookups, int only_pi) {
+  const unsigned kFull = 0xffffffffu;
+  const int q = threadIdx.x & (kQuad - 1);
+  const int qbase = threadIdx.x & 31 & ~(kQuad - 1);
+  const int nmodes = rc ? 4 : 2;
+  const uint64_t nwork = count * nmodes;
+  unsigned long long nlook = 0, nlines = 0;
+  const IdxT kNone = (IdxT)-1;
+  const bool wide = sizeof(IdxT) == 8;
+
+  // only_pi >= 0: this launch handles the searches of one index only (the launches of both indices cover the batch)
+  const uint64_t wk_begin = only_pi > 0 ? nwork / 2 : 0, wk_end = only_pi == 0 ? nwork / 2 : nwork;
+  for (uint64_t wk = wk_begin + ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / kQuad; __any_sync(kFull, wk < wk_end);
+       wk += ((uint64_t)gridDim.x * blockDim.x) / kQuad) {
+    const bool have = wk < wk_end;
+    // index-major order: [0, nwork/2) searches the forward index (modes 0, 1), the rest the reverse index (modes 2, 3)
+    const int pi = (have && wk >= nwork / 2) ? 1 : 0;
+    const uint64_t within = have ? wk - (pi ? nwork / 2 : 0) : 0;
+    const uint64_t wi = rc ? within >> 1 : within;  // where the results are stored
+    const int mode = 2 * pi + (rc ? (int)(within & 1) : 0);
+    const FmBlockLane* __restrict__ Pb = fm.blocks[pi];
+    const uint64_t rd = first + (list ? (uint64_t)list[wi] : wi);  // which read
+    const uint32_t* rw = reads.words + reads.woff[rd];
+    const uint32_t l = reads.len[rd];
+    uint32_t n = 0;
+    const bool backwards = mode == 1 || mode == 2;  // string position k reads base l-1-k
+    const uint32_t cm = (mode & 1) ? 0xffffffffu : 0u;  // modes 1 and 3 complement: flip both code bits
+    // C[] of the searched index: lane q keeps C[q+1], the symbol whose block header it loads, and adds it to the
+    // header before the header is handed to the quad (C['$'] = 0)
+    const IdxT mypc = (IdxT)fm.pred[pi][q + 1];
+    int c = ov_sym(rw, l, mode, l - 1);
+    IdxT lo0 = (IdxT)fm.pred[pi][c], hi0 = (IdxT)(fm.pred[pi][c + 1] - 1);
+    uint32_t j = backwards ? 1u : l - 2;  // base index of string position l-2; moves by dj as the position decreases
+    const uint32_t dj = backwards ? 1u : 0xffffffffu;
+    uint32_t i = have ? l - 1 : 0;  // remaining steps
+    bool live = have && i > 0 && hi0 != kNone && hi0 >= lo0;
+    uint32_t word = live ? (rw[j >> 4] ^ cm) : 0u;  // (complemented) codes of the 16 bases around j
+    int cnext = (int)((word >> (2 * (j & 15))) & 3u) + 1;
+    uint32_t lines = 0;
+#pragma unroll 1
+    while (__any_sync(kFull, live)) {
+      c = cnext;
+      j += dj;
+      // next step's symbol: a new word every 16 bases (entered from below when j grows, from above when it falls)
+      if (live && i > 1 && (j & 15u) == (backwards ? 0u : 15u)) word = rw[j >> 4] ^ cm;
+      cnext = (int)((word >> (2 * (j & 15))) & 3u) + 1;
+      const IdxT plo = live ? lo0 : (IdxT)0, phi = live ? (IdxT)(hi0 + 1) : (IdxT)0;
+      const uint64_t b1 = (uint64_t)plo >> kBlockShift, b2 = (uint64_t)phi >> kBlockShift;
+      const int r1 = (int)(plo & (kBlockSyms - 1)), r2 = (int)(phi & (kBlockSyms - 1));
+      const uint4* pa = reinterpret_cast<const uint4*>(Pb + b1 * kGroup + q);
+      const uint4 a0 = __ldg(pa), a1 = __ldg(pa + 4);
+      uint4 c0 = a0, c1 = a1;
+      if (b2 != b1) {
+        const uint4* pb = reinterpret_cast<const uint4*>(Pb + b2 * kGroup + q);
+        c0 = __ldg(pb);
+        c1 = __ldg(pb + 4);
+      }
+      // prefix masks of this lane's two words at both ends (1 = at or past the prefix end)
+      uint32_t ma0, ma1, mc0, mc1;
+      asm("shl.b32 %0, %1, %2;" : "=r"(ma0) : "r"(0xffffffffu), "r"((uint32_t)max(r1 - 32 * q, 0)));
+      asm("shl.b32 %0, %1, %2;" : "=r"(ma1) : "r"(0xffffffffu), "r"((uint32_t)max(r1 - 32 * (q + 4), 0)));
+      asm("shl.b32 %0, %1, %2;" : "=r"(mc0) : "r"(0xffffffffu), "r"((uint32_t)max(r2 - 32 * q, 0)));
+      asm("shl.b32 %0, %1, %2;" : "=r"(mc1) : "r"(0xffffffffu), "r"((uint32_t)max(r2 - 32 * (q + 4), 0)));
+      const uint32_t x0 = ((c - 1) & 1) ? 0u : 0xffffffffu, x1 = ((c - 1) & 2) ? 0u : 0xffffffffu;
+      uint32_t packed = (uint32_t)__popc(~(a0.z | ma0) & (a0.x ^ x0) & (a0.y ^ x1)) +
+                        (uint32_t)__popc(~(a1.z | ma1) & (a1.x ^ x0) & (a1.y ^ x1)) +
+                        (((uint32_t)__popc(~(c0.z | mc0) & (c0.x ^ x0) & (c0.y ^ x1)) +
+                          (uint32_t)__popc(~(c1.z | mc1) & (c1.x ^ x0) & (c1.y ^ x1))) << 16);
+      packed += __shfl_xor_sync(kFull, packed, 1);
+      packed += __shfl_xor_sync(kFull, packed, 2);
+      // C[c] + header of symbol c at both ends, from lane c-1 of the quad
+      const int src = qbase + c - 1;
+      IdxT nlo, nhi;
+      if (wide) {
+        const uint64_t ha = ((uint64_t)a1.w << 32 | a0.w) + mypc, hc = ((uint64_t)c1.w << 32 | c0.w) + mypc;
+        nlo = (IdxT)__shfl_sync(kFull, (unsigned long long)ha, src);
+        nhi = (IdxT)__shfl_sync(kFull, (unsigned long long)hc, src);
+      } else {
+        nlo = (IdxT)__shfl_sync(kFull, a0.w + (uint32_t)mypc, src);
+        nhi = (IdxT)__shfl_sync(kFull, c0.w + (uint32_t)mypc, src);
+      }
+      nlo += (IdxT)(packed & 0xffffu);
+      nhi += (IdxT)(packed >> 16);
+      nhi -= 1;
+      const uint32_t olen = l - i;
+      const bool elig = live && olen >= min_ov;
+      if (__any_sync(kFull, elig)) {
+        // '$' rows inside [plo, phi): in-block counts at both ends + what the blocks in between hold
+        const uint32_t nb = (uint32_t)min(b2 - b1, (uint64_t)64);
+        uint32_t pk = ((uint32_t)__popc(a0.z & ~ma0) + (uint32_t)__popc(a1.z & ~ma1)) |
+                      (((uint32_t)__popc(c0.z & ~mc0) + (uint32_t)__popc(c1.z & ~mc1)) << 9) | ((c0.w - a0.w) << 18);
+        pk += __shfl_xor_sync(kFull, pk, 1);
+        pk += __shfl_xor_sync(kFull, pk, 2);
+        const uint32_t dl = pk & 511u;
+        IdxT dd = (IdxT)(((pk >> 9) & 511u) - dl + 256u * nb - (pk >> 18));
+        IdxT Ld = 0;
+        const bool far = elig && nb > 63;  // the 14-bit header field does not hold this distance: full rank query
+        if (__any_sync(kFull, far)) {
+          const QuadRank<IdxT> k = quad_rank<IdxT>(Pb, far ? plo : (IdxT)0, far ? phi : (IdxT)0, q);
+          if (far) {
+            dd = k.Ud - k.Ld;
+            Ld = k.Ld;
+          }
+        }
+        const bool emit = elig && dd >= 1;
+        if (__any_sync(kFull, emit)) {
+          // '$' rank at the lower end = rows before it minus the A,C,G,T among them (block headers + in-block part)
+          IdxT hs = wide ? (IdxT)((uint64_t)a1.w << 32 | a0.w) : (IdxT)a0.w;
+          hs += __shfl_xor_sync(kFull, hs, 1);
+          hs += __shfl_xor_sync(kFull, hs, 2);
+          if (!far) Ld = (IdxT)(b1 << kBlockShift) - hs + dl;
+          if (emit) {
+            if (n < bt.find_cap && q == 0) {
+              LeanCand lc;  // C['$'] = 0: the '$' rank is the row
+              lc.lo = (uint32_t)Ld;
+              lc.hi = (uint32_t)(Ld + dd - 1);
+              lc.len_af = olen | (ov_mode_af(mode) << 16);
+              bt.lean[((size_t)wi * 4 + mode) * bt.find_cap + n] = lc;
+            }
+            ++n;
+          }
+        }
+      }
+      if (live) {
+        lines += b2 != b1 ? 2u : 1u;
+        lo0 = nlo;
+        hi0 = nhi;
+        --i;
+        live = i > 0 && hi0 != kNone && hi0 >= lo0;
+      }
+    }
+    if (have && l > 0) nlook += 2ull * ((l - 1) - i);  // steps taken
+    // ---- containment handling (src/overlap_builder.cpp:877-905), warp-uniform
+    const bool tail = have && hi0 != kNone && hi0 >= lo0;  // only reachable with i == 0
+    uint32_t ncontain = 0;
+    if (UNIFORM) {
+      if (__any_sync(kFull, tail)) {
+        const IdxT plo = tail ? lo0 : (IdxT)0;
+        const uint64_t b1 = (uint64_t)plo >> kBlockShift;
+        const int r1 = (int)(plo & (kBlockSyms - 1));
+        const uint4* pa = reinterpret_cast<const uint4*>(Pb + b1 * kGroup + q);
+        const uint4 a0 = __ldg(pa), a1 = __ldg(pa + 4);
+        uint32_t ma0, ma1;
+        asm("shl.b32 %0, %1, %2;" : "=r"(ma0) : "r"(0xffffffffu), "r"((uint32_t)max(r1 - 32 * q, 0)));
+        asm("shl.b32 %0, %1, %2;" : "=r"(ma1) : "r"(0xffffffffu), "r"((uint32_t)max(r1 - 32 * (q + 4), 0)));
+        uint32_t dl = (uint32_t)__popc(a0.z & ~ma0) + (uint32_t)__popc(a1.z & ~ma1);
+        IdxT hs = wide ? (IdxT)((uint64_t)a1.w << 32 | a0.w) : (IdxT)a0.w;
+#pragma unroll
+        for (int m = 1; m < kQuad; m <<= 1) {
+          dl += __shfl_xor_sync(kFull, dl, m);
+          hs += __shfl_xor_sync(kFull, hs, m);
+        }
+        if (tail) {
+          nlook += 1;
+          lines += 1;
+          if (q == 0) {
+            const IdxT Ld = (IdxT)(b1 << kBlockShift) - hs + dl;
+            LeanCand lc;
+            lc.lo = (uint32_t)Ld;
+            lc.hi = (uint32_t)(Ld + (hi0 - lo0));
+            lc.len_af = l | (ov_mode_af(mode) << 16);
+            bt.lean_contain[(size_t)wi * 4 + mode] = lc;
+          }
+          ncontain = 1;
+        }
+      }
+    } else if (__any_sync(kFull, tail)) {
+      // the other-side interval: reverse(X) searched backwards in the opposite index = X read front to back
+      const FmBlockLane* __restrict__ Sb = fm.blocks[1 - pi];
+      int cs = tail ? ov_sym(rw, l, mode, 0) : 1;
+      IdxT lo1 = (IdxT)fm.pred[1 - pi][cs], hi1 = (IdxT)(fm.pred[1 - pi][cs + 1] - 1);
+      uint32_t t = 1;
+      bool tl = tail && t < l;
+#pragma unroll 1
+      while (__any_sync(kFull, tl)) {
+        cs = tl ? ov_sym(rw, l, mode, t) : 1;
+        IdxT Ls, Us;
+        quad_rank_sym<IdxT>(Sb, tl ? lo1 : (IdxT)0, tl ? (IdxT)(hi1 + 1) : (IdxT)0, q, qbase, cs, Ls, Us);
+        if (tl) {
+          nlook += 2;
+          lines += (((uint64_t)lo1 >> kBlockShift) != ((uint64_t)(IdxT)(hi1 + 1) >> kBlockShift)) ? 2u : 1u;
+          lo1 = (IdxT)fm.pred[1 - pi][cs] + Ls;
+          hi1 = (IdxT)fm.pred[1 - pi][cs] + Us - 1;
+          ++t;
+          tl = t < l && hi1 != kNone && hi1 >= lo1;
+        }
+      }
+      const QuadRank<IdxT> kp = quad_rank<IdxT>(Pb, tail ? lo0 : (IdxT)0, tail ? (IdxT)(hi0 + 1) : (IdxT)0, q);
+      const QuadRank<IdxT> ks = quad_rank<IdxT>(Sb, tail ? lo1 : (IdxT)0, tail ? (IdxT)(hi1 + 1) : (IdxT)0, q);
+      const bool mydna = (kp.Uq - kp.Lq) > 0 || (ks.Uq - ks.Lq) > 0;
+      const bool dna = ((__ballot_sync(kFull, mydna) >> qbase) & 0xfu) != 0;
+      const IdxT d = kp.Ud - kp.Ld;
+      const IdxT p0lo = kp.Ld;  // + C['$'] = 0
+      IdxT p0hi = kp.Ud - 1;
+      const IdxT p1hi = lo1 + d - 1;
+      const bool v0 = p0hi != kNone && p0hi >= p0lo, v1 = p1hi != kNone && p1hi >= lo1;
+      const bool want = tail && !dna && v0 && v1;
+      const bool need3 = want && p1hi != hi1;
+      IdxT U3d = ks.Ud;
+      if (__any_sync(kFull, need3)) {
+        const QuadRank<IdxT> k3 = quad_rank<IdxT>(Sb, need3 ? lo1 : (IdxT)0, need3 ? (IdxT)(p1hi + 1) : (IdxT)0, q);
+        if (need3) {
+          U3d = k3.Ud;
+          nlook += 1;
+          lines += 1;
+        }
+      }
+      if (tail) {
+        nlook += 4;
+        lines += 4;
+        if (dna) {
+          if (q == 0) bt.substring[list ? (uint64_t)list[wi] : wi] = 1;
+        } else if (want) {
+          const IdxT d3 = U3d - ks.Ld;
+          p0hi = p0lo + d3 - 1;
+          if (q == 0) {
+            LeanCand lc;
+            lc.lo = (uint32_t)p0lo;
+            lc.hi = (uint32_t)p0hi;
+            lc.len_af = l | (ov_mode_af(mode) << 16);
+            bt.lean_contain[(size_t)wi * 4 + mode] = lc;
+          }
+          ncontain = 1;
+        }
+      }
+    }
+    nlines += lines;
+    if (have && q == 0) {
+      bt.ncand[wi * 4 + mode] = n < bt.find_cap ? n : bt.find_cap;
+      bt.ncontain[wi * 4 + mode] = ncontain;
+    }
+  }
+  if (!rc && only_pi <= 0) {
+    const uint64_t quad = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / kQuad;
+    const uint64_t nquads = ((uint64_t)gridDim.x * blockDim.x) / kQuad;
+    for (uint64_t r = quad; r < count; r += nquads) {
+      if (q == 0) {
+        bt.ncand[r * 4 + 1] = 0;
+        bt.ncand[r * 4 + 3] = 0;
+        bt.ncontain[r * 4 + 1] = 0;
+        bt.ncontain[r * 4 + 3] = 0;
+      }
+    }
+  }
+  if (q == 0) {
+    if (nlook) atomicAdd(lookups, nlook);
+    if (nlines) atomicAdd(lookups + 2, nlines);
+  }
 }
 
 }  // namespace sgx

@@ -175,6 +175,39 @@ def edges_to_ed(names, lengths, edges):
                                                  s1.tolist(), e1.tolist(), lt.tolist(), rc.tolist())]
 
 
+def edge_rows(edges, lengths):
+    """int64 columns (query, target, s1, e1, s2, e2, rc) of compact edge records: the numbers of the ED line
+    (OverlapBlock::overlap, src/overlap_builder.cpp:158-175).  `lengths`: per-read array or one common length."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    q, t = edges["query"].astype(np.int64), edges["target"].astype(np.int64)
+    k, af = edges["length"].astype(np.int64), edges["af"].astype(np.int64)
+    lq, lt = (lengths[q], lengths[t]) if lengths.ndim else (np.full_like(q, lengths), np.full_like(q, lengths))
+    qr = (af & AF_QUERYREV) != 0
+    tr = (af & AF_TARGETREV) != 0
+    return (q, t, np.where(qr, 0, lq - k), np.where(qr, k - 1, lq - 1), np.where(tr, lt - k, 0), np.where(tr, lt - 1, k - 1),
+            ((af & AF_QUERYCOMP) != 0).astype(np.int64))
+
+
+def edge_digest_rows(q, t, s1, e1, s2, e2, rc):
+    """sha256 over the ED set as int32 rows (query index, target index, s1, e1, s2, e2, rc) sorted lexicographically --
+    the canonical form full-size parity compares (the reference emits ED records in thread order)."""
+    import hashlib
+    cols = [np.asarray(x, dtype=np.int64) for x in (q, t, s1, e1, s2, e2, rc)]
+    if all(len(c) == 0 or (c.min() >= 0 and c.max() < (1 << 15)) for c in cols[2:]) and \
+            all(len(c) == 0 or (c.min() >= 0 and c.max() < (1 << 31)) for c in cols[:2]):
+        k1 = (cols[0] << 31) | cols[1]  # same order as the seven-key sort, two packed keys
+        k2 = (cols[2] << 46) | (cols[3] << 31) | (cols[4] << 16) | (cols[5] << 1) | cols[6]
+        order = np.lexsort((k2, k1))
+    else:
+        order = np.lexsort(tuple(cols[::-1]))
+    rows = np.stack(cols, axis=1)[order].astype("<i4")
+    return hashlib.sha256(np.ascontiguousarray(rows).tobytes()).hexdigest()
+
+
+def edge_digest(edges, lengths):
+    return edge_digest_rows(*edge_rows(edges, lengths))
+
+
 def asqg_lines(names, seqs, substring, edges, min_overlap):
     """HT / VT / ED lines exactly as OverlapBuilder::build emits them (src/overlap_builder.cpp:428-437, 301-322,
     410-413; src/asqg.cpp:93-124, 171-186, 228-237)."""

@@ -10,33 +10,11 @@ import subprocess
 
 import numpy as np
 
-AF_QUERYREV, AF_TARGETREV, AF_QUERYCOMP = 1, 2, 4
+import os
+import sys
 
-
-def edge_digest_rows(q, t, s1, e1, s2, e2, rc):
-    rows = np.stack([np.asarray(x, dtype=np.int64) for x in (q, t, s1, e1, s2, e2, rc)], axis=1)
-    order = np.lexsort(rows.T[::-1])
-    return hashlib.sha256(np.ascontiguousarray(rows[order].astype("<i4")).tobytes()).hexdigest()
-
-
-def edge_rows_from_records(edges, lengths):
-    """Coordinates of OverlapBlock::overlap (src/overlap_builder.cpp:158-175) from compact sgx_edge records."""
-    lengths = np.asarray(lengths, dtype=np.int64)
-    q, t = edges["query"].astype(np.int64), edges["target"].astype(np.int64)
-    k, af = edges["length"].astype(np.int64), edges["af"].astype(np.int64)
-    lq, lt = (lengths[q], lengths[t]) if lengths.ndim else (np.full_like(q, lengths), np.full_like(q, lengths))
-    qr = (af & AF_QUERYREV) != 0
-    tr = (af & AF_TARGETREV) != 0
-    s1 = np.where(qr, 0, lq - k)
-    e1 = np.where(qr, k - 1, lq - 1)
-    s2 = np.where(tr, lt - k, 0)
-    e2 = np.where(tr, lt - 1, k - 1)
-    rc = ((af & AF_QUERYCOMP) != 0).astype(np.int64)
-    return q, t, s1, e1, s2, e2, rc
-
-
-def edge_digest(edges, lengths):
-    return edge_digest_rows(*edge_rows_from_records(edges, lengths))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from siga_b200.formats import edge_digest, edge_digest_rows, edge_rows  # noqa: E402,F401  (the canonical form lives with the formats)
 
 
 def parse_asqg_edges(path):

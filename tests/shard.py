@@ -1,4 +1,5 @@
-"""Host-side sharding of the overlap stage across GPUs.
+"""Test helper: host-side sharding of the overlap stage across ranks -- used by the gloo tests and
+the profiling scripts; the product splits reads in the CLI (siga_main.cpp) and bench.py carries its own read_range.
 
 Overlap search shards by independent units (reads): both FM-indices are replicated on every GPU, rank g searches the
 contiguous read range [g*N/G, (g+1)*N/G).  VT records keep input order by concatenating the ranges in rank order; ED

@@ -12,7 +12,8 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _worker(rank, world, port, n_reads, out_dir):
     sys.path.insert(0, REPO)
-    from siga_b200 import shard
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import shard
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -45,7 +46,7 @@ def _correct_worker(rank, world, port, fixture, out_dir):
     sys.path.insert(0, REPO)
     sys.path.insert(0, os.path.join(REPO, "tests"))
     import correct_common as cc
-    from siga_b200 import shard
+    import shard
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)

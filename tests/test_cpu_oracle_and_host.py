@@ -10,7 +10,8 @@ import numpy as np
 import pytest
 
 from oracle import pyoracle
-from siga_b200 import api, formats, shard, synth
+import shard
+from siga_b200 import api, formats, synth
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = sorted(glob.glob(os.path.join(REPO, "tests", "golden", "*.json")))
@@ -188,7 +189,7 @@ def test_library_exports_every_declared_symbol_and_refuses_to_run_without_a_gpu(
     lib = api.load_library()
     for s in api.ABI_SYMBOLS:
         assert hasattr(lib, s), s
-    assert lib.sgx_abi_version() == 1
+    assert lib.sgx_abi_version() == 2
     import torch
     if not torch.cuda.is_available():
         h = ctypes.c_void_p()
