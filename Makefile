@@ -27,7 +27,7 @@ cli: siga_b200/bin/siga
 siga_b200/bin/siga: $(wildcard $(CSRC)/host/*.cpp $(CSRC)/host/*.h) include/siga_b200.h $(LIB)
 	@mkdir -p siga_b200/bin
 	@if ls $(CSRC)/host/*.cpp >/dev/null 2>&1; then \
-	  $(HOSTCXX) -std=c++17 -O2 -Wall -Wextra -Iinclude $(CSRC)/host/*.cpp -o $@ -Lsiga_b200 -lsiga_b200 -lz -lpthread -Wl,-rpath,'$$ORIGIN/..'; \
+	  $(HOSTCXX) -std=c++17 -O2 -Wall -Wextra -Iinclude $(CSRC)/host/*.cpp -o $@ -Lsiga_b200 -lsiga_b200 -lz -lpthread -ldl -Wl,-rpath,'$$ORIGIN/..'; \
 	else echo "no host CLI sources yet"; fi
 
 hostemu: build/libhostemu.so
@@ -38,7 +38,7 @@ build/libhostemu.so: tests/hostemu/hostemu.cpp $(HDR)
 hostcli: build/siga_hostemu
 build/siga_hostemu: tests/hostemu/sgx_stub.cpp tests/hostemu/hostemu.cpp $(wildcard $(CSRC)/host/*.cpp $(CSRC)/host/*.h) $(HDR)
 	@mkdir -p build
-	$(HOSTCXX) -std=c++17 -O2 -Wall -Wextra -Iinclude tests/hostemu/sgx_stub.cpp $(CSRC)/host/*.cpp -o $@ -lz -lpthread
+	$(HOSTCXX) -std=c++17 -O2 -Wall -Wextra -Iinclude tests/hostemu/sgx_stub.cpp $(CSRC)/host/*.cpp -o $@ -lz -lpthread -ldl
 
 oracle:
 	$(MAKE) -C oracle

@@ -328,11 +328,6 @@ def main():
 
     ctx = api.Context(local)
     sampler = ClockSampler(local)
-    comm = None  # the library's own NCCL communicator: sharded index build + final gather of edge records
-    if world > 1:
-        uid = torch.from_numpy(ctx.comm_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)).cuda()
-        dist.broadcast(uid, 0)
-        comm = ctx.comm_init(uid.cpu().numpy(), rank, world)
 
     # ---- index (both strands) : build once for the overlap stage, then time it
     r_dev = ctx.pack_reads(flat, off)
@@ -464,49 +459,69 @@ def main():
             rec["reference_threads"] = g["threads"]
         strong["by_min_overlap"][str(m)] = rec
 
-    # ---- index build (fwd + rev), resident and end to end.  N = 1: sgx_index_build.  N > 1: ONE index of the same
-    #      read set built by all N GPUs together (sgx_index_build_sharded: rows sharded by leading k-mer bucket,
-    #      inserts exchanged with NCCL all-to-all every column pass) -- strong scaling, checked against the
-    #      single-GPU build of the setup phase byte for byte.
+    # ---- index build (fwd + rev), resident and end to end.  N = 1: sgx_index_build_pair (both strands side by side on two
+    #      streams).  N > 1: ONE index pair of the same read set built by all N GPUs together (strong scaling): the ranks
+    #      split into two groups, one per strand -- the two indices are independent jobs, so the first factor of two costs
+    #      no communication -- and inside a group of N/2 > 1 GPUs the rows are sharded by leading k-mer bucket with an NCCL
+    #      all-to-all of the inserts every column pass (sgx_index_build_sharded).  Checked byte for byte against the
+    #      single-GPU build of the setup phase (itself checked against the reference's hashes above).
     isteps = args.index_steps or min(args.steps, 3)
-    def build_index(rd, rv, copy=True):
-        if comm is None:
-            return ctx.index_build(rd, order=api.ORDER_SAIS2, reversed=rv, copy=copy)
-        return ctx.index_build_sharded(comm, rd, order=api.ORDER_SAIS2, reversed=rv, copy=copy)
+    group = 0 if world == 1 else rank // (world // 2)   # which strand this rank works on
+    sub_world = 1 if world == 1 else world // 2
+    sub_rank = rank % sub_world
+    sub_comm = None  # the library's own NCCL communicator of this rank's strand group
+    if sub_world > 1:
+        ids = []
+        for leader in (0, world // 2):  # each group's leader creates its NCCL id
+            uid = torch.from_numpy(ctx.comm_unique_id() if rank == leader else np.zeros(128, dtype=np.uint8)).cuda()
+            dist.broadcast(uid, leader)
+            ids.append(uid.cpu().numpy())
+        sub_comm = ctx.comm_init(ids[group], sub_rank, sub_world)
 
-    for rv, ref_idx in ((False, fi), (True, ri)):  # warm-up + parity of the sharded build at full size
-        o = build_index(r_dev, rv)
+    def build_index(rd, copy=True):
+        """-> list of results this rank produced (both strands at N = 1, its group's strand otherwise)"""
+        if world == 1:
+            return list(ctx.index_build_pair(rd, order=api.ORDER_SAIS2, copy=copy))
+        if sub_comm is None:
+            return [ctx.index_build(rd, order=api.ORDER_SAIS2, reversed=bool(group), copy=copy)]
+        return [ctx.index_build_sharded(sub_comm, rd, order=api.ORDER_SAIS2, reversed=bool(group), copy=copy)]
+
+    res = build_index(r_dev)  # warm-up + parity at full size
+    refs = [fi, ri] if world == 1 else [ri if group else fi]
+    for o, ref_idx in zip(res, refs):
         assert np.array_equal(o.sai, ref_idx.sai)
-        if rank == 0:
-            assert np.array_equal(o.runs, ref_idx.runs), "sharded index differs from the single-GPU build"
-    if world > 1 and golden:
-        parity["sharded_index_identical_to_reference"] = True  # == the single-GPU build, which matched the hashes above
+        if sub_rank == 0:
+            assert np.array_equal(o.runs, ref_idx.runs), "index differs from the single-GPU build"
+    if golden:
+        parity["timed_index_build_identical_to_reference"] = True  # == the setup build, which matched the hashes above
     barrier()
     t0 = time.perf_counter()
     idx_dev_ms = idx_merge_ms = 0.0
     idx_merge_bytes = idx_launches = idx_merge_launches = 0
     for _ in range(isteps):
-        for rv in (False, True):
-            o = build_index(r_dev, rv, copy=False)  # results stay in the library's pinned buffers (no numpy copy)
-            idx_dev_ms += o.stats["ms_total"]
+        step_dev = 0.0
+        for o in build_index(r_dev, copy=False):  # results stay in the library's pinned buffers (no numpy copy)
+            step_dev = max(step_dev, o.stats["ms_total"])
             idx_merge_ms += o.stats["ms_merge"]
             idx_merge_bytes += o.stats["merge_bytes"]
             idx_launches += o.stats["launches"]
             idx_merge_launches += o.stats["merge_launches"]
             ctx.free_index(o)
+        idx_dev_ms += step_dev
     barrier()
     idx_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / isteps)
     barrier()
     t0 = time.perf_counter()
     for _ in range(isteps):
         rr = ctx.pack_reads(flat, off)
-        for rv in (False, True):
-            o = build_index(rr, rv, copy=False)
+        for o in build_index(rr, copy=False):
             ctx.free_index(o)
         ctx.free_reads(rr)
     barrier()
     idx_e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / isteps)
     idx_dev_ms = max_over_ranks(idx_dev_ms)
+    if sub_comm is not None:
+        ctx.free_comm(sub_comm)
 
     # ---- k-mer error correction (`siga correct`, defaults -k 31 -x 3 -i 10 -O 1) of the same reads against the forward
     #      index: resident (reads + index in HBM) and end to end (pinned host reads in, flags + fixes out)
@@ -558,9 +573,6 @@ def main():
                          "lookups_per_read": corr_look / csteps / n_reads,
                          "reference_lookups_per_read_nominal": 2 * 30 * (read_len - 30),
                          "lookups_per_s": corr_look / (corr_kernel_ms * 1e-3) if corr_kernel_ms else 0.0}}
-    if comm is not None:
-        ctx.free_comm(comm)
-        comm = None
     clocks = sampler.stop()
 
     bases = n_reads * read_len
@@ -619,14 +631,16 @@ def main():
         "index": {"metric": "bwt_build_gbases_per_s", "value": bases / (idx_ms * 1e-3) / 1e9, "unit": "Gbases/s",
                   "ms_per_step": idx_ms, "steps": isteps, "device_ms_per_step": idx_dev_ms / isteps,
                   "scaling": "strong" if world > 1 else "single GPU",
-                  "path": ("sgx_index_build_sharded over NCCL: one cfg2 index (fwd + rev) built by %d GPUs, byte-identical "
-                           "to the single-GPU build" % world) if world > 1 else "sgx_index_build",
+                  "path": ("one cfg2 index pair built by %d GPUs: one group of %d per strand%s; byte-identical to the single-GPU build"
+                           % (world, sub_world, ", rows sharded by k-mer bucket inside a group (sgx_index_build_sharded over NCCL)"
+                              if sub_world > 1 else " (sgx_index_build, no collective)")) if world > 1
+                          else "sgx_index_build_pair (both strands side by side on two streams)",
                   "e2e": {"value": bases / (idx_e2e_ms * 1e-3) / 1e9, "unit": "Gbases/s", "ms_per_step": idx_e2e_ms,
                           "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(len(fi.runs) + len(ri.runs) + 8 * n_reads)},
                   "gpu_launches": int(idx_launches),
                   "roofline": {"bound": "hbm", "kernel": "bcr_merge_kernel", "achieved": merge_ach, "peak": hbm_peak, "unit": "GB/s",
                                "frac": merge_ach / hbm_peak, "traffic": None,
-                               "merge_ms_per_build": idx_merge_ms / (2 * isteps),
+                               "merge_ms_per_build": idx_merge_ms / ((2 if world == 1 else 1) * isteps),
                                "floor_bytes_per_suffix": idx_suffix_bytes,
                                "floor_frac": idx_suffix_bytes * 2 * fi.n_suffixes / (idx_dev_ms / isteps * 1e-3) / 1e9 / hbm_peak}},
         "clocks": clocks,
@@ -709,55 +723,71 @@ def cfg4_object(args, ctx, api, formats, torch, dist, rank, world, local, barrie
     out = {"workload": "cfg4%s: %d Mbp random genome, 50x, 150 bp error-free reads, both strands, %d reads; index + overlap -m %d" %
                        ("" if scale == 1.0 else " [genome scale %g]" % scale, g // 1_000_000, n, MIN_OVERLAP),
            "generate_s": gen_s, "n_gpus": world}
+    # strand groups, as in the cfg2 index object: ranks [0, N/2) build the forward index, ranks [N/2, N) the reverse one
+    group = 0 if world == 1 else rank // (world // 2)
+    sub_world = 1 if world == 1 else world // 2
+    sub_rank = rank % sub_world
     comm = None
-    if world > 1:
-        uid = torch.from_numpy(ctx.comm_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)).cuda()
-        dist.broadcast(uid, 0)
-        comm = ctx.comm_init(uid.cpu().numpy(), rank, world)
+    if sub_world > 1:
+        ids = []
+        for leader in (0, world // 2):
+            uid = torch.from_numpy(ctx.comm_unique_id() if rank == leader else np.zeros(128, dtype=np.uint8)).cuda()
+            dist.broadcast(uid, leader)
+            ids.append(uid.cpu().numpy())
+        comm = ctx.comm_init(ids[group], sub_rank, sub_world)
     r_dev = ctx.pack_reads(flat, off)
-    # index: sharded over all ranks (timed, max over ranks), then rank 0 alone
-    res = {}
-    for rv in (False, True):
-        times = []
-        for it in range(2):
-            barrier()
-            t0 = time.perf_counter()
-            o = ctx.index_build_sharded(comm, r_dev, order=api.ORDER_SAIS2, reversed=rv) if comm is not None else \
-                ctx.index_build(r_dev, order=api.ORDER_SAIS2, reversed=rv)
-            torch.cuda.synchronize()
-            times.append(max_over_ranks((time.perf_counter() - t0) * 1e3))
-        res[rv] = o
-        out["index_ms_rev%d" % rv] = min(times)
-    out["index_ms"] = out["index_ms_rev0"] + out["index_ms_rev1"]
+
+    def build_mine():
+        if world == 1:
+            return list(ctx.index_build_pair(r_dev, order=api.ORDER_SAIS2))
+        if comm is None:
+            return [ctx.index_build(r_dev, order=api.ORDER_SAIS2, reversed=bool(group))]
+        return [ctx.index_build_sharded(comm, r_dev, order=api.ORDER_SAIS2, reversed=bool(group))]
+
+    times = []
+    for it in range(2):
+        barrier()
+        t0 = time.perf_counter()
+        mine = build_mine()
+        torch.cuda.synchronize()
+        times.append(max_over_ranks((time.perf_counter() - t0) * 1e3))
+    out["index_ms"] = min(times)
+    out["index_ms_runs"] = times
     out["index_gbases_per_s"] = n * L / (out["index_ms"] * 1e-3) / 1e9
-    single = {}
-    if rank == 0 and world > 1:
-        for rv in (False, True):
-            ctx.free_index(ctx.index_build(r_dev, order=api.ORDER_SAIS2, reversed=rv, copy=False))  # warm-up (work areas)
-            t0 = time.perf_counter()
-            one = ctx.index_build(r_dev, order=api.ORDER_SAIS2, reversed=rv)
-            single[rv] = (time.perf_counter() - t0) * 1e3
-            assert np.array_equal(one.runs, res[rv].runs) and np.array_equal(one.sai, res[rv].sai), \
-                "cfg4: sharded index differs from the single-GPU build"
-            del one
-        out["index_ms_one_gpu"] = single[False] + single[True]
+    out["index_path"] = "one group of %d GPU(s) per strand%s" % (sub_world, ", rows sharded by k-mer bucket over NCCL" if sub_world > 1 else "")
+    # the finished indices travel through tmpfs: run bytes are complete on each group's leader, .sai everywhere in the group
+    runs_path, sai_path = "/dev/shm/siga_b200_cfg4_runs_%d.npy", "/dev/shm/siga_b200_cfg4_sai_%d.npy"
+    if sub_rank == 0:
+        for k, o in enumerate(mine):
+            rv = k if world == 1 else group
+            np.save(runs_path % rv, o.runs)
+            np.save(sai_path % rv, o.sai)
+    n_suffixes = mine[0].n_suffixes
+    del mine
+    barrier()
+    if rank == 0 and world > 1:  # the same job on ONE GPU with the same kernels (both strands side by side)
+        a1, b1 = ctx.index_build_pair(r_dev, order=api.ORDER_SAIS2)
+        del a1, b1
+        t0 = time.perf_counter()
+        a1, b1 = ctx.index_build_pair(r_dev, order=api.ORDER_SAIS2)
+        out["index_ms_one_gpu"] = (time.perf_counter() - t0) * 1e3
+        for rv, one in ((0, a1), (1, b1)):
+            assert np.array_equal(one.runs, np.load(runs_path % rv, mmap_mode="r")) and \
+                np.array_equal(one.sai, np.load(sai_path % rv, mmap_mode="r")), "cfg4: multi-GPU index differs from the single-GPU build"
+        del a1, b1
         out["index_speedup"] = out["index_ms_one_gpu"] / out["index_ms"]
         out["index_efficiency"] = out["index_speedup"] / world
-        out["index_sharded_identical_to_one_gpu"] = True
+        out["index_identical_to_one_gpu"] = True
     barrier()
-    # the run bytes are complete on rank 0 only: share them through tmpfs for the replicated FM-indices
-    runs_path = "/dev/shm/siga_b200_cfg4_runs_%d.npy"
-    if rank == 0:
-        for rv in (False, True):
-            np.save(runs_path % rv, res[rv].runs)
-    barrier()
-    fms = []
-    for rv in (False, True):
-        runs = res[rv].runs if rank == 0 else np.load(runs_path % rv, mmap_mode="r")
-        fm = ctx.fm_create(runs, res[rv].n_suffixes)
-        ctx.fm_attach_reads(fm, res[rv].sai, r_dev)
+    fms, sais = [], []
+    for rv in (0, 1):
+        sai = np.load(sai_path % rv)
+        fm = ctx.fm_create(np.load(runs_path % rv, mmap_mode="r"), n_suffixes)
+        ctx.fm_attach_reads(fm, sai, r_dev)
         fms.append(fm)
+        sais.append(sai)
     fwd, rev = fms
+    res = {False: type("R", (), {"sai": sais[0]})(), True: type("R", (), {"sai": sais[1]})()}
     if rank == 0:
         # exact, size-independent check of the full-size index: LF-walk a sample of reads out of the BWT
         out["lf_walk_reads_checked"] = lf_check_sample(ctx, fwd, res[False].sai, reads, 20000, np.random.default_rng(4))
@@ -794,7 +824,7 @@ def cfg4_object(args, ctx, api, formats, torch, dist, rank, world, local, barrie
         ctx.free_comm(comm)
     del reads, flat
     if rank == 0:
-        for f in [shm] + [runs_path % rv for rv in (False, True)]:
+        for f in [shm] + [runs_path % rv for rv in (0, 1)] + [sai_path % rv for rv in (0, 1)]:
             try:
                 os.remove(f)
             except OSError:

@@ -102,6 +102,14 @@ typedef struct sgx_index_out {
 int sgx_index_build(sgx_ctx* ctx, const sgx_reads* reads, int order, int reversed, sgx_index_out* out);
 void sgx_index_out_free(sgx_index_out* out);
 
+/*
+ * Both indices of a read set in one call -- what one `siga index` run produces (Indexer::run builds the index of the reads
+ * and then of the reversed reads, src/indexer.cpp:25-77) -- built concurrently on two streams of the device.  The results
+ * are those of sgx_index_build(.., reversed = 0, ..) and sgx_index_build(.., reversed = 1, ..); release both with
+ * sgx_index_out_free.  The time fields of each result cover that build alone; the two overlap in time.
+ */
+int sgx_index_build_pair(sgx_ctx* ctx, const sgx_reads* reads, int order, sgx_index_out* out_fwd, sgx_index_out* out_rev);
+
 /* ---- multi-GPU index construction ------------------------------------------------------------------------ */
 
 /*

@@ -20,7 +20,7 @@ assert BLOCK_DTYPE.itemsize == 72
 ABI_SYMBOLS = [
     "sgx_abi_version", "sgx_init", "sgx_shutdown", "sgx_last_error", "sgx_sm_count",
     "sgx_reads_pack", "sgx_reads_free", "sgx_reads_count", "sgx_reads_bases",
-    "sgx_index_build", "sgx_index_out_free",
+    "sgx_index_build", "sgx_index_build_pair", "sgx_index_out_free",
     "sgx_comm_unique_id", "sgx_comm_init", "sgx_comm_init_local", "sgx_comm_free", "sgx_comm_world", "sgx_comm_rank",
     "sgx_index_build_sharded", "sgx_edges_gather",
     "sgx_fm_create", "sgx_fm_free", "sgx_fm_attach_reads", "sgx_fm_length", "sgx_fm_pred", "sgx_fm_occ", "sgx_fm_count",
@@ -105,6 +105,7 @@ def load_library():
     lib.sgx_reads_bases.argtypes = [vp]
     lib.sgx_reads_bases.restype = u64
     lib.sgx_index_build.argtypes = [vp, vp, i32, i32, ctypes.POINTER(_IndexOut)]
+    lib.sgx_index_build_pair.argtypes = [vp, vp, i32, ctypes.POINTER(_IndexOut), ctypes.POINTER(_IndexOut)]
     lib.sgx_index_out_free.argtypes = [ctypes.POINTER(_IndexOut)]
     lib.sgx_index_out_free.restype = None
     lib.sgx_comm_unique_id.argtypes = [vp]
@@ -281,6 +282,12 @@ class Context:
         o = _IndexOut()
         self._check(self.lib.sgx_index_build(self.h, reads, int(order), 1 if reversed else 0, ctypes.byref(o)))
         return self._index_result(o, copy)
+
+    def index_build_pair(self, reads, order=ORDER_SAIS2, copy=True):
+        """Forward and reversed index built concurrently (sgx_index_build_pair) -> (forward, reversed) results."""
+        a, b = _IndexOut(), _IndexOut()
+        self._check(self.lib.sgx_index_build_pair(self.h, reads, int(order), ctypes.byref(a), ctypes.byref(b)))
+        return self._index_result(a, copy), self._index_result(b, copy)
 
     def _index_result(self, o, copy):
         res = IndexResult(o, copy=copy)

@@ -1,6 +1,7 @@
 // extern "C" entry points of libsiga_b200.so (include/siga_b200.h).  Thin: argument checks, error mapping, timing.
 #include <mutex>
 #include <new>
+#include <thread>
 #include <unordered_map>
 
 #include "index.cuh"
@@ -197,6 +198,10 @@ int sgx_init(int device, sgx_ctx** out) {
 
 void sgx_shutdown(sgx_ctx* ctx) {
   if (!ctx) return;
+  if (ctx->aux) {
+    sgx_shutdown(ctx->aux);
+    ctx->aux = nullptr;
+  }
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   {
@@ -243,6 +248,73 @@ int sgx_index_build(sgx_ctx* ctx, const sgx_reads* reads, int order, int reverse
   SGX_ENTRY_BEGIN(ctx)
   SGX_REQUIRE(order == SGX_ORDER_SAIS || order == SGX_ORDER_SAIS2, SGX_EINVAL, "sgx_index_build: unknown order");
   index_build(ctx, reads, order, reversed != 0, out);
+  SGX_ENTRY_END(ctx)
+}
+
+// Both indices of a read set (what one `siga index` run builds, src/indexer.cpp:25-77) at the same time: the forward
+// build on the context's stream, the build of the reversed reads on a second stream of the same device, driven by a
+// second host thread.  The column passes of one build are chains of small dependent kernels; two independent chains
+// fill each other's gaps.
+int sgx_index_build_pair(sgx_ctx* ctx, const sgx_reads* reads, int order, sgx_index_out* out_fwd, sgx_index_out* out_rev) {
+  if (!ctx || !reads || !out_fwd || !out_rev) return SGX_EINVAL;
+  SGX_ENTRY_BEGIN(ctx)
+  SGX_REQUIRE(order == SGX_ORDER_SAIS || order == SGX_ORDER_SAIS2, SGX_EINVAL, "sgx_index_build_pair: unknown order");
+  if (!ctx->aux) {
+    sgx_ctx* a = new sgx_ctx();
+    a->device = ctx->device;
+    a->sm_count = ctx->sm_count;
+    a->l2_bytes = ctx->l2_bytes;
+    a->launches = 0;
+    a->flush_buf = nullptr;
+    a->flush_bytes = 0;
+    cudaError_t e = cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      delete a;
+      SGX_CUDA(e);
+    }
+    ctx->aux = a;
+  }
+  sgx_ctx* aux = ctx->aux;
+  // the second stream starts after everything queued on the first (the read store may still be in flight there)
+  cudaEvent_t ready;
+  SGX_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+  SGX_CUDA(cudaEventRecord(ready, ctx->stream));
+  SGX_CUDA(cudaStreamWaitEvent(aux->stream, ready, 0));
+  cudaEventDestroy(ready);
+  const uint64_t aux_launches0 = aux->launches;
+  int rc_rev = SGX_OK;
+  std::string err_rev;
+  std::thread second([&]() {
+    try {
+      SGX_CUDA(cudaSetDevice(aux->device));
+      sgx::g_stream = aux->stream;
+      sgx::g_ctx = aux;
+      index_build(aux, reads, order, true, out_rev);
+    } catch (const sgx::Error& e) {
+      rc_rev = e.code;
+      err_rev = e.msg;
+      cudaGetLastError();
+    } catch (const std::bad_alloc&) {
+      rc_rev = SGX_ENOMEM;
+      err_rev = "host allocation failed";
+    }
+  });
+  int rc_fwd = SGX_OK;
+  std::string err_fwd;
+  try {
+    index_build(ctx, reads, order, false, out_fwd);
+  } catch (const sgx::Error& e) {
+    rc_fwd = e.code;
+    err_fwd = e.msg;
+    cudaGetLastError();
+  }
+  second.join();
+  ctx->launches += aux->launches - aux_launches0;
+  if (rc_fwd != SGX_OK || rc_rev != SGX_OK) {
+    if (rc_fwd == SGX_OK) sgx_index_out_free(out_fwd);
+    if (rc_rev == SGX_OK) sgx_index_out_free(out_rev);
+    throw sgx::Error{rc_fwd != SGX_OK ? rc_fwd : rc_rev, rc_fwd != SGX_OK ? err_fwd : err_rev};
+  }
   SGX_ENTRY_END(ctx)
 }
 

@@ -36,7 +36,10 @@ static NcclApi& nccl_api() {
   void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
   if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
   if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-  if (!h) throw Error{SGX_ENODEV, std::string("NCCL is not available: ") + (dlerror() ? dlerror() : "dlopen failed")};
+  if (!h) {
+    const char* why = dlerror();  // one call: dlerror() clears the message it returns
+    throw Error{SGX_ENODEV, std::string("NCCL is not available: ") + (why ? why : "dlopen failed")};
+  }
 #define SGX_NCCL_SYM(field, name)                                                         \
   *(void**)(&g_nccl.field) = dlsym(h, name);                                              \
   if (!g_nccl.field) throw Error{SGX_ENODEV, std::string("NCCL symbol missing: ") + name};
@@ -65,6 +68,24 @@ static NcclApi& nccl_api() {
       throw sgx::Error{SGX_ECUDA, _b};                                                                      \
     }                                                                                                       \
   } while (0)
+
+// ncclGroupStart ... ncclGroupEnd with the group closed on every path: a throw between the two calls must not leave the
+// NCCL group of this thread open (the next collective would silently queue into it).
+struct NcclGroup {
+  NcclApi& api;
+  bool open;
+  explicit NcclGroup(NcclApi& a) : api(a), open(false) {
+    SGX_NCCL(api.GroupStart());
+    open = true;
+  }
+  void end() {
+    open = false;
+    SGX_NCCL(api.GroupEnd());
+  }
+  ~NcclGroup() {
+    if (open) api.GroupEnd();
+  }
+};
 
 void comm_unique_id(uint8_t id[128]) {
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
@@ -191,7 +212,7 @@ void comm_alltoallv(sgx_comm* cm, const void* const* send, void* const* recv, si
     SGX_CUDA(cudaMemcpyAsync((uint8_t*)recv[0] + recv_off[me * W + me] * elem_bytes,
                              (const uint8_t*)send[0] + send_off[me * W + me] * elem_bytes, cnt[me * W + me] * elem_bytes,
                              cudaMemcpyDeviceToDevice, st));
-  SGX_NCCL(api.GroupStart());
+  NcclGroup grp(api);
   for (int p = 0; p < W; ++p) {
     if (p == me) continue;
     const uint64_t cs = cnt[me * W + p], cr = cnt[p * W + me];
@@ -202,7 +223,7 @@ void comm_alltoallv(sgx_comm* cm, const void* const* send, void* const* recv, si
       SGX_NCCL(api.Recv((uint8_t*)recv[0] + recv_off[me * W + p] * elem_bytes, cr * elem_bytes, ncclUint8, p,
                         (ncclComm_t)cm->nccl, st));
   }
-  SGX_NCCL(api.GroupEnd());
+  grp.end();
 }
 
 void comm_gatherv_bytes(sgx_comm* cm, const uint8_t* const* send, const uint64_t* bytes, int root, uint8_t* root_recv) {
@@ -219,10 +240,10 @@ void comm_gatherv_bytes(sgx_comm* cm, const uint8_t* const* send, const uint64_t
   const int me = cm->rank;
   if (me == root) {
     if (bytes[me]) SGX_CUDA(cudaMemcpyAsync(root_recv + off[me], send[0], bytes[me], cudaMemcpyDeviceToDevice, st));
-    SGX_NCCL(api.GroupStart());
+    NcclGroup grp(api);
     for (int s = 0; s < W; ++s)
       if (s != me && bytes[s]) SGX_NCCL(api.Recv(root_recv + off[s], bytes[s], ncclUint8, s, (ncclComm_t)cm->nccl, st));
-    SGX_NCCL(api.GroupEnd());
+    grp.end();
   } else if (bytes[me]) {
     SGX_NCCL(api.Send(send[0], bytes[me], ncclUint8, root, (ncclComm_t)cm->nccl, st));
   }
@@ -244,13 +265,13 @@ void comm_allgatherv(sgx_comm* cm, const void* const* send, const uint64_t* coun
   const int me = cm->rank;
   if (counts[me])
     SGX_CUDA(cudaMemcpyAsync(dst + off[me] * elem_bytes, send[0], counts[me] * elem_bytes, cudaMemcpyDeviceToDevice, st));
-  SGX_NCCL(api.GroupStart());
+  NcclGroup grp(api);
   for (int p = 0; p < W; ++p) {
     if (p == me) continue;
     if (counts[me]) SGX_NCCL(api.Send(send[0], counts[me] * elem_bytes, ncclUint8, p, (ncclComm_t)cm->nccl, st));
     if (counts[p]) SGX_NCCL(api.Recv(dst + off[p] * elem_bytes, counts[p] * elem_bytes, ncclUint8, p, (ncclComm_t)cm->nccl, st));
   }
-  SGX_NCCL(api.GroupEnd());
+  grp.end();
 }
 
 void comm_barrier(sgx_comm* cm) {

@@ -2,6 +2,7 @@
 
 #include <thread>
 
+#include <dlfcn.h>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -262,7 +263,107 @@ struct FillSink {
 
 }  // namespace
 
+namespace {
+// bzip2 input (the reference reads .bz2 through boost::iostreams, src/utils.cpp:92-95).  There are no bzlib headers in
+// the build image, only the runtime library, so libbz2.so.1 is resolved with dlopen and the stream interface declared
+// here (stable since bzip2 1.0).  The file is decompressed into a temporary plain file, which the normal readers parse.
+struct BzStream {
+  char* next_in;
+  unsigned int avail_in, total_in_lo32, total_in_hi32;
+  char* next_out;
+  unsigned int avail_out, total_out_lo32, total_out_hi32;
+  void* state;
+  void* (*bzalloc)(void*, int, int);
+  void (*bzfree)(void*, void*);
+  void* opaque;
+};
+
+bool bunzip2_to_temp(const std::string& path, std::string* tmp_path, std::string* err) {
+  void* h = dlopen("libbz2.so.1.0", RTLD_NOW);
+  if (!h) h = dlopen("libbz2.so.1", RTLD_NOW);
+  if (!h) {
+    *err = "cannot read " + path + ": bzip2 input needs libbz2.so.1, which is not installed (decompress the file first)";
+    return false;
+  }
+  typedef int (*InitF)(BzStream*, int, int);
+  typedef int (*StepF)(BzStream*);
+  InitF init = (InitF)dlsym(h, "BZ2_bzDecompressInit");
+  StepF step = (StepF)dlsym(h, "BZ2_bzDecompress"), end = (StepF)dlsym(h, "BZ2_bzDecompressEnd");
+  if (!init || !step || !end) {
+    *err = "cannot read " + path + ": libbz2 lacks the decompression interface";
+    return false;
+  }
+  FILE* in = fopen(path.c_str(), "rb");
+  if (!in) {
+    *err = "cannot open " + path;
+    return false;
+  }
+  const char* tdir = getenv("TMPDIR");
+  std::string tmpl = std::string(tdir && *tdir ? tdir : "/tmp") + "/siga_bz2_XXXXXX";
+  std::vector<char> name(tmpl.begin(), tmpl.end());
+  name.push_back('\0');
+  const int fd = mkstemp(name.data());
+  FILE* outf = fd >= 0 ? fdopen(fd, "wb") : nullptr;
+  if (!outf) {
+    fclose(in);
+    *err = "cannot create a temporary file for " + path;
+    return false;
+  }
+  *tmp_path = name.data();
+  std::vector<char> ibuf(1 << 20), obuf(1 << 22);
+  BzStream bz;
+  memset(&bz, 0, sizeof(bz));
+  bool ok = init(&bz, 0, 0) == 0, open_stream = ok;
+  while (ok) {
+    if (bz.avail_in == 0) {
+      bz.avail_in = (unsigned int)fread(ibuf.data(), 1, ibuf.size(), in);
+      bz.next_in = ibuf.data();
+      if (bz.avail_in == 0) break;  // end of file (between streams when open_stream is false)
+    }
+    if (!open_stream) {  // concatenated streams
+      ok = init(&bz, 0, 0) == 0;
+      open_stream = ok;
+      if (!ok) break;
+    }
+    bz.next_out = obuf.data();
+    bz.avail_out = (unsigned int)obuf.size();
+    const int rc = step(&bz);
+    const size_t got = obuf.size() - bz.avail_out;
+    if (got && fwrite(obuf.data(), 1, got, outf) != got) ok = false;
+    if (rc == 4) {  // BZ_STREAM_END
+      char* ni = bz.next_in;
+      const unsigned int ai = bz.avail_in;
+      end(&bz);
+      memset(&bz, 0, sizeof(bz));
+      bz.next_in = ni;
+      bz.avail_in = ai;
+      open_stream = false;
+    } else if (rc != 0) {
+      ok = false;
+    }
+  }
+  if (open_stream) {
+    end(&bz);
+    ok = false;  // the file ended inside a stream
+  }
+  fclose(in);
+  if (fclose(outf) != 0) ok = false;
+  if (!ok) {
+    remove(tmp_path->c_str());
+    *err = "cannot read " + path + ": not a valid bzip2 file";
+  }
+  return ok;
+}
+}  // namespace
+
 bool read_sequences(const std::string& path, ReadSet* out, std::string* err) {
+  if (ends_with(path, ".bz2")) {
+    std::string tmp;
+    if (!bunzip2_to_temp(path, &tmp, err)) return false;
+    const bool ok = read_sequences(tmp, out, err);
+    remove(tmp.c_str());
+    return ok;
+  }
   size_t kMinParallel = (size_t)16 << 20;
   if (const char* mp = getenv("SIGA_PARSE_MIN_PARALLEL")) kMinParallel = (size_t)strtoull(mp, nullptr, 10);  // tests
   unsigned T = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));

@@ -8,8 +8,8 @@
 //       loads PREFIX.bwt/.rbwt/.sai/.rsai, writes PREFIX.asqg.gz (HT, VT in input order, then ED)
 //
 // Option defaults are the reference's CODE defaults (min-overlap 10, algorithm sais2).
-// -t/--threads only sizes the host-side output formatting/compression pool; -c/--log4cxx and -s/--ini are accepted
-// and ignored (there is no log4cxx here).  The per-thread .hits.gz files of the reference are an internal detail
+// -t/--threads only sizes the host-side output formatting/compression pool; -c/--log4cxx is accepted and ignored (there
+// is no log4cxx here); -s/--ini FILE supplies options as `key=value` lines which the command line overrides.  The per-thread .hits.gz files of the reference are an internal detail
 // nothing downstream reads and are not produced.
 #include <fcntl.h>
 #include <getopt.h>
@@ -58,6 +58,20 @@ void info(const char* fmt, ...) {
 int fail(sgx_ctx* ctx, const char* what, int rc) {
   fprintf(stderr, "ERROR siga - %s failed (%d): %s\n", what, rc, sgx_last_error(ctx));
   return -1;
+}
+
+// After sgx_reads_pack has refused the input: name the first read with a byte other than A/C/G/T.
+void explain_bad_bases(const ReadSet& rs, uint64_t first = 0, uint64_t count = (uint64_t)-1) {
+  const uint64_t end = count == (uint64_t)-1 ? rs.size() : first + count;
+  for (uint64_t i = first; i < end; ++i)
+    for (uint64_t k = rs.off[i]; k < rs.off[i + 1]; ++k) {
+      const char ch = rs.bases[k];
+      if (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T') {
+        fprintf(stderr, "ERROR siga - read %llu (%s) has '%c' at base %llu: reads must hold A/C/G/T only (run them through "
+                        "`siga preprocess` first)\n", (unsigned long long)i, rs.names[i].c_str(), ch, (unsigned long long)(k - rs.off[i]));
+        return;
+      }
+    }
 }
 
 // The worker processes of a `--gpus N` run (rank 0 is the calling process, ranks 1..N-1 are forked before any CUDA call).
@@ -168,6 +182,15 @@ class GzChunkWriter {
     if (f_) fclose(f_);
   }
   bool ok() const { return f_ != NULL; }
+  // Flushes and closes the file; false when the last buffered bytes could not be written (ENOSPC, EIO).  Callers fold
+  // this into their result: a destructor cannot report it.
+  bool close() {
+    if (!f_) return false;
+    const bool good = fflush(f_) == 0 && !ferror(f_);
+    const bool closed = fclose(f_) == 0;
+    f_ = NULL;
+    return good && closed;
+  }
   // produce(i, &text) fills the text of chunk i in [0, n); chunks are emitted in index order.  encoder(i) picks the
   // member encoder of chunk i: zlib at the configured level, or one of the two writers of fastgz.h (literal-only for
   // sequence records, greedy LZ77 for records with repeated fields).
@@ -201,8 +224,10 @@ class GzChunkWriter {
         const int enc = encoder(i);
         std::string gz = enc == kLiteral ? gzip_member_huffman(text.data(), text.size())
                          : enc == kFastLz ? gzip_member_lz(text.data(), text.size()) : deflate_member(text, level_);
+        if (gz.empty() && enc != kZlib) gz = deflate_member(text, level_);  // the fast encoders return "" on an internal mismatch
         {
           std::lock_guard<std::mutex> lk(mu);
+          if (gz.empty()) good = false;  // a gzip member is never empty (18 bytes of header + trailer at least)
           slot[i % window].swap(gz);
           ready[i % window] = 1;
         }
@@ -239,16 +264,23 @@ class GzChunkWriter {
 
  private:
   static std::string deflate_member(const std::string& text, int level) {
+    // "" = failure (the caller treats an empty member as an error)
     z_stream zs;
     memset(&zs, 0, sizeof(zs));
-    deflateInit2(&zs, level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY);
-    std::string out(deflateBound(&zs, text.size()) + 64, '\0');
+    if (text.size() > 0x7fffffffu) return std::string();  // chunks are a few MB; avail_in is 32 bits
+    if (deflateInit2(&zs, level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) return std::string();
+    const uLong bound = deflateBound(&zs, (uLong)text.size()) + 64;
+    if (bound > 0xffffffffu) {
+      deflateEnd(&zs);
+      return std::string();
+    }
+    std::string out(bound, '\0');
     zs.next_in = (Bytef*)text.data();
     zs.avail_in = (uInt)text.size();
     zs.next_out = (Bytef*)&out[0];
     zs.avail_out = (uInt)out.size();
-    deflate(&zs, Z_FINISH);
-    out.resize(zs.total_out);
+    const int rc = deflate(&zs, Z_FINISH);
+    out.resize(rc == Z_STREAM_END ? zs.total_out : 0);
     deflateEnd(&zs);
     return out;
   }
@@ -370,7 +402,7 @@ bool write_asqg(const std::string& path, const CommonOpts& o, const ReadSet& rs,
   const size_t vt_chunk = 1 << 16, ed_chunk = 1 << 18;
   const size_t n_ht = with_ht ? 1 : 0;
   const size_t n_vt = (n + vt_chunk - 1) / vt_chunk, n_ed = with_ed ? (ed.n_edges + ed_chunk - 1) / ed_chunk : 0;
-  return gz.write_chunks(n_ht + n_vt + n_ed, [&](size_t ci, std::string* text) {
+  const bool wrote = gz.write_chunks(n_ht + n_vt + n_ed, [&](size_t ci, std::string* text) {
     if (ci < n_ht) {
       *text = "HT\tVN:i:1\tOL:i:" + std::to_string(min_overlap) + "\tCN:i:1\n";  // IN/ER/TE are never set on this path
     } else if (ci < n_ht + n_vt) {
@@ -418,6 +450,7 @@ bool write_asqg(const std::string& path, const CommonOpts& o, const ReadSet& rs,
     if (!o.gzip_fast) return GzChunkWriter::kZlib;
     return ci >= n_ht && ci < n_ht + n_vt ? GzChunkWriter::kLiteral : GzChunkWriter::kFastLz;
   });
+  return gz.close() && wrote;
 }
 
 bool append_file(FILE* dst, const std::string& path) {
@@ -542,6 +575,7 @@ int cmd_index(int argc, char** argv) {
   int rc = SGX_OK;
   const int world = o.gpus;
   int my = 0;
+  int group = -1, sub_world = 1, sub_rank = 0;  // --gpus N: strand group of this rank (see below)
   Gang gang;
   sgx_comm* comm = nullptr;
   if (world == 1) {
@@ -576,47 +610,52 @@ int cmd_index(int argc, char** argv) {
       if (my) _exit(1);
       return -1;
     }
-    uint8_t id[128];
-    bool ok_id = true;
-    if (my == 0) {
-      ok_id = sgx_comm_unique_id(id) == SGX_OK;
-      for (int r = 1; r < world; ++r) ok_id = write(wr[r], id, sizeof(id)) == (ssize_t)sizeof(id) && ok_id;
+    // Strand groups: the two indices are independent jobs, so with both wanted and an even number of GPUs the ranks split
+    // into one group per strand (ranks [0, N/2) forward, [N/2, N) reverse) -- the first factor of two costs no
+    // communication -- and only inside a group of more than one GPU are the rows sharded over NCCL.  Each group's first
+    // rank holds the finished index and writes its two files.
+    if (fwd && rev && world % 2 == 0) {
+      sub_world = world / 2;
+      group = my / sub_world;
+      sub_rank = my % sub_world;
     } else {
-      ok_id = read(rd[my], id, sizeof(id)) == (ssize_t)sizeof(id);
+      sub_world = world;
+      group = -1;  // one group builds the wanted strands one after the other
+      sub_rank = my;
     }
-    if (!ok_id || (rc = sgx_comm_init(ctx, id, my, world, &comm)) != SGX_OK) {
-      fail(ok_id ? ctx : nullptr, "sgx_comm_init", rc);
-      if (my) _exit(1);
-      return -1;
+    if (sub_world > 1) {
+      const int leader = group > 0 ? sub_world : 0;
+      uint8_t id[128];
+      bool ok_id = true;
+      if (my == leader) {
+        ok_id = sgx_comm_unique_id(id) == SGX_OK;
+        for (int r = leader + 1; r < leader + sub_world; ++r) ok_id = write(wr[r], id, sizeof(id)) == (ssize_t)sizeof(id) && ok_id;
+      } else {
+        ok_id = read(rd[my], id, sizeof(id)) == (ssize_t)sizeof(id);
+      }
+      if (!ok_id || (rc = sgx_comm_init(ctx, id, sub_rank, sub_world, &comm)) != SGX_OK) {
+        fail(ok_id ? ctx : nullptr, "sgx_comm_init", rc);
+        if (my) _exit(1);
+        return -1;
+      }
     }
   }
   sgx_reads* reads = nullptr;
   rc = sgx_reads_pack(ctx, rs.bases.data(), rs.off.data(), rs.size(), &reads);
   if (rc != SGX_OK) {
     fail(ctx, "sgx_reads_pack", rc);
+    if (rc == SGX_EINVAL && my == 0) explain_bad_bases(rs);
     if (my) _exit(1);
     return -1;
   }
-  // the files of one strand are written on a host thread while the device builds the other strand
+  // the files of one strand are written on a host thread while the device builds the other strand; on one GPU with both
+  // strands wanted, the two builds run side by side on the device (sgx_index_build_pair) and all four files are written
+  // at once
   sgx_index_out outs[2];
   std::thread writers[2];
   bool wrote[2] = {true, true};
-  for (int pass = 0; pass < 2; ++pass) {
-    if ((pass == 0 && !fwd) || (pass == 1 && !rev)) continue;
-    if (my == 0) info("building %s index on %d GPU(s) from device %d", pass == 0 ? "forward" : "reverse", world, o.device);
+  auto start_writer = [&](int pass) {
     sgx_index_out& out = outs[pass];
-    rc = comm ? sgx_index_build_sharded(ctx, comm, reads, order, pass, &out) : sgx_index_build(ctx, reads, order, pass, &out);
-    if (rc != SGX_OK) {
-      for (auto& w : writers)
-        if (w.joinable()) w.join();
-      fail(ctx, comm ? "sgx_index_build_sharded" : "sgx_index_build", rc);
-      if (my) _exit(1);
-      return -1;
-    }
-    if (my) {  // only rank 0 holds the concatenated run bytes and writes the files
-      sgx_index_out_free(&out);
-      continue;
-    }
     const std::string sa = output + (pass == 0 ? ".sai" : ".rsai"), bw = output + (pass == 0 ? ".bwt" : ".rbwt");
     info("%s: %llu strings, %llu suffixes, %llu runs; device %.1f ms (%llu kernel launches)", bw.c_str(),
          (unsigned long long)out.n_strings, (unsigned long long)out.n_suffixes, (unsigned long long)out.n_runs, out.ms_total,
@@ -629,6 +668,34 @@ int cmd_index(int argc, char** argv) {
       t.join();
       wrote[pass] = a && b;
     });
+  };
+  if (world == 1 && fwd && rev) {
+    info("building forward and reverse index side by side on device %d", o.device);
+    rc = sgx_index_build_pair(ctx, reads, order, &outs[0], &outs[1]);
+    if (rc != SGX_OK) return fail(ctx, "sgx_index_build_pair", rc);
+    start_writer(0);
+    start_writer(1);
+  } else {
+    for (int pass = 0; pass < 2; ++pass) {
+      if ((pass == 0 && !fwd) || (pass == 1 && !rev)) continue;
+      if (group >= 0 && pass != group) continue;  // the other strand group builds this one
+      if (sub_rank == 0)
+        info("building %s index on %d GPU(s) from device %d", pass == 0 ? "forward" : "reverse", sub_world, o.device + my);
+      sgx_index_out& out = outs[pass];
+      rc = comm ? sgx_index_build_sharded(ctx, comm, reads, order, pass, &out) : sgx_index_build(ctx, reads, order, pass, &out);
+      if (rc != SGX_OK) {
+        for (auto& w : writers)
+          if (w.joinable()) w.join();
+        fail(ctx, comm ? "sgx_index_build_sharded" : "sgx_index_build", rc);
+        if (my) _exit(1);
+        return -1;
+      }
+      if (sub_rank) {  // only a group's first rank holds the concatenated run bytes and writes the files
+        sgx_index_out_free(&out);
+        continue;
+      }
+      start_writer(pass);
+    }
   }
   for (int pass = 0; pass < 2; ++pass) {
     if (!writers[pass].joinable()) continue;
@@ -636,6 +703,7 @@ int cmd_index(int argc, char** argv) {
     sgx_index_out_free(&outs[pass]);
     if (!wrote[pass]) {
       fprintf(stderr, "ERROR siga - failed to write the %s index files of %s\n", pass == 0 ? "forward" : "reverse", output.c_str());
+      if (my) _exit(1);
       return -1;
     }
   }
@@ -746,7 +814,10 @@ int cmd_overlap(int argc, char** argv) {
     }
     return -1;
   };
-  if ((rc = sgx_reads_pack(ctx, rs.bases.data(), rs.off.data(), rs.size(), &reads)) != SGX_OK) return bail("sgx_reads_pack", rc);
+  if ((rc = sgx_reads_pack(ctx, rs.bases.data(), rs.off.data(), rs.size(), &reads)) != SGX_OK) {
+    if (rc == SGX_EINVAL && my == 0) explain_bad_bases(rs);
+    return bail("sgx_reads_pack", rc);
+  }
   if ((rc = sgx_fm_create(ctx, runs.data(), runs.size(), nf, &fwd)) != SGX_OK) return bail("sgx_fm_create", rc);
   if ((rc = sgx_fm_create(ctx, rruns.data(), rruns.size(), rnf, &rev)) != SGX_OK) return bail("sgx_fm_create", rc);
   if ((rc = sgx_fm_attach_reads(ctx, fwd, sai.data(), sai.size(), reads)) != SGX_OK) return bail("sgx_fm_attach_reads", rc);
@@ -857,7 +928,10 @@ int cmd_rmdup(int argc, char** argv) {
   int rc = SGX_OK;
   sgx_reads* reads = nullptr;
   sgx_fm *fwd = nullptr, *rev = nullptr;
-  if ((rc = sgx_reads_pack(ctx, rs.bases.data(), rs.off.data(), rs.size(), &reads)) != SGX_OK) return fail(ctx, "sgx_reads_pack", rc);
+  if ((rc = sgx_reads_pack(ctx, rs.bases.data(), rs.off.data(), rs.size(), &reads)) != SGX_OK) {
+    if (rc == SGX_EINVAL) explain_bad_bases(rs);
+    return fail(ctx, "sgx_reads_pack", rc);
+  }
   if ((rc = sgx_fm_create(ctx, runs.data(), runs.size(), nf, &fwd)) != SGX_OK) return fail(ctx, "sgx_fm_create", rc);
   if ((rc = sgx_fm_create(ctx, rruns.data(), rruns.size(), rnf, &rev)) != SGX_OK) return fail(ctx, "sgx_fm_create", rc);
   if ((rc = sgx_fm_attach_reads(ctx, fwd, sai.data(), sai.size(), reads)) != SGX_OK) return fail(ctx, "sgx_fm_attach_reads", rc);
@@ -989,9 +1063,11 @@ bool write_corrected(const std::string& path, bool gz, int threads, int gzip_lev
   if (threads < 1) threads = 1;
   if (gz) {
     GzChunkWriter w(path, (unsigned)threads, gzip_level);
-    return w.ok() && w.write_chunks(std::max<size_t>(n_chunks, 1), [&](size_t ci, std::string* text) {
+    if (!w.ok()) return false;
+    const bool wrote = w.write_chunks(std::max<size_t>(n_chunks, 1), [&](size_t ci, std::string* text) {
       if (ci < n_chunks) produce(ci, text);
     }, [&](size_t) { return gzip_fast ? GzChunkWriter::kLiteral : GzChunkWriter::kZlib; });
+    return w.close() && wrote;
   }
   // plain file: one range of reads per thread, formatted and then written at its own offset
   const size_t n_parts = std::max<size_t>(1, std::min<size_t>((size_t)threads, n_chunks));
@@ -1123,7 +1199,10 @@ int cmd_correct(int argc, char** argv) {
   int rc = SGX_OK;
   if (count > 0) {
     // only this rank's range goes to the device (offsets need not start at zero)
-    if ((rc = sgx_reads_pack(ctx, rs.bases.data(), rs.off.data() + first, count, &reads)) != SGX_OK) return bail("sgx_reads_pack", rc);
+    if ((rc = sgx_reads_pack(ctx, rs.bases.data(), rs.off.data() + first, count, &reads)) != SGX_OK) {
+      if (rc == SGX_EINVAL) explain_bad_bases(rs, first, count);
+      return bail("sgx_reads_pack", rc);
+    }
     if ((rc = sgx_fm_create(ctx, runs.data(), runs.size(), nf, &fm)) != SGX_OK) return bail("sgx_fm_create", rc);
     rc = sgx_correct_batch(ctx, fm, reads, 0, count, fastq ? rs.quals.data() : nullptr, fastq ? rs.off.data() + first : nullptr, &prm, &res);
     if (rc != SGX_OK) return bail("sgx_correct_batch", rc);
@@ -1259,12 +1338,56 @@ int cmd_match(int argc, char** argv) {
         add(seq, len);
       }
     }
+    // Queries with a byte other than A/C/G/T: the reference searches them with that byte mapped to rank 0, the
+    // sentinel (DNAAlphabet::torank, src/alphabet.h:19-39; Interval::get, src/fmindex.h:67-78).  They are rare
+    // (un-preprocessed input), so they are stepped here on the host through sgx_fm_occ with exactly that mapping and
+    // only the clean queries go to the batched device search (sgx_reads_pack rejects other bytes).
     std::vector<uint64_t> counts(qoff.size() - 1);
-    if (!counts.empty() && (rc = sgx_fm_count(ctx, fm, q.data(), qoff.data(), counts.size(), counts.data())) != SGX_OK) {
-      fail(ctx, "sgx_fm_count", rc);
+    std::string qc;
+    std::vector<uint64_t> qcoff(1, 0);
+    std::vector<size_t> clean_ix;
+    uint64_t pred[5] = {0, 0, 0, 0, 0};
+    sgx_fm_pred(fm, pred);
+    bool occ_fail = false;
+    for (size_t k = 0; k + 1 < qoff.size() && !occ_fail; ++k) {
+      const char* w = q.data() + qoff[k];
+      const size_t len = qoff[k + 1] - qoff[k];
+      bool clean = true;
+      for (size_t j = 0; j < len && clean; ++j) clean = w[j] == 'A' || w[j] == 'C' || w[j] == 'G' || w[j] == 'T';
+      if (clean) {
+        qc.append(w, len);
+        qcoff.push_back(qc.size());
+        clean_ix.push_back(k);
+        continue;
+      }
+      auto rank_of = [](char ch) { return ch == 'A' ? 1 : ch == 'C' ? 2 : ch == 'G' ? 3 : ch == 'T' ? 4 : 0; };
+      uint64_t lower = 0, upper = (uint64_t)-1;
+      for (size_t j = len; j-- > 0;) {
+        const int r = rank_of(w[j]);
+        uint64_t pos[2], occ[10];
+        if (j + 1 == len) {  // Interval::init
+          pos[0] = pos[1] = nf - 1;
+          if (sgx_fm_occ(ctx, fm, pos, 1, occ) != SGX_OK) occ_fail = true;
+          lower = pred[r];
+          upper = lower + occ[r] - 1;
+        } else {             // Interval::update
+          pos[0] = lower - 1;
+          pos[1] = upper;
+          if (sgx_fm_occ(ctx, fm, pos, 2, occ) != SGX_OK) occ_fail = true;
+          lower = pred[r] + occ[r];
+          upper = pred[r] + occ[5 + r] - 1;
+        }
+        if (occ_fail || !(upper != (uint64_t)-1 && upper >= lower)) break;
+      }
+      counts[k] = (upper != (uint64_t)-1 && upper >= lower) ? upper - lower + 1 : 0;
+    }
+    std::vector<uint64_t> ccounts(clean_ix.size());
+    if (occ_fail || (!ccounts.empty() && (rc = sgx_fm_count(ctx, fm, qc.data(), qcoff.data(), ccounts.size(), ccounts.data())) != SGX_OK)) {
+      fail(ctx, occ_fail ? "sgx_fm_occ" : "sgx_fm_count", rc);
       status = -1;
       break;
     }
+    for (size_t k = 0; k < clean_ix.size(); ++k) counts[clean_ix[k]] = ccounts[k];
     std::string text;
     size_t k = 0;
     const size_t per = rcomp ? 2 : 1;
@@ -1295,7 +1418,61 @@ int cmd_match(int argc, char** argv) {
 
 }  // namespace
 
-int main(int argc, char** argv) {
+// -s / --ini FILE (src/main.cpp:63-77): `key=value` lines of an INI file are options, command-line options override
+// them.  The file's entries become `--key=value` arguments placed before the command line's own, and every option loop
+// here lets the last occurrence win.  A file that cannot be read is an error, as in the reference.
+bool expand_ini(int argc, char** argv, std::vector<std::string>* store, std::vector<char*>* out) {
+  std::string file;
+  for (int a = 2; a < argc; ++a) {
+    const std::string s = argv[a];
+    if ((s == "-s" || s == "--ini") && a + 1 < argc) file = argv[a + 1];
+    else if (s.compare(0, 6, "--ini=") == 0) file = s.substr(6);
+    else if (s.size() > 2 && s[0] == '-' && s[1] == 's') file = s.substr(2);
+  }
+  out->assign(argv, argv + argc);
+  if (file.empty()) return true;
+  FILE* f = fopen(file.c_str(), "r");
+  if (!f) {
+    fprintf(stderr, "ERROR siga - load %s failed(cannot open file).\n", file.c_str());
+    return false;
+  }
+  char line[4096];
+  store->reserve(256);  // the pointers handed out below must stay valid
+  while (fgets(line, sizeof(line), f) && store->size() < 256) {
+    std::string s = line;
+    const size_t cpos = s.find_first_of(";#");
+    if (cpos == 0) continue;
+    while (!s.empty() && isspace((unsigned char)s.back())) s.pop_back();
+    size_t b = 0;
+    while (b < s.size() && isspace((unsigned char)s[b])) ++b;
+    s = s.substr(b);
+    if (s.empty() || s[0] == '[') continue;  // sections only group keys; the option names are flat
+    const size_t eq = s.find('=');
+    std::string key = eq == std::string::npos ? s : s.substr(0, eq), val = eq == std::string::npos ? "" : s.substr(eq + 1);
+    while (!key.empty() && isspace((unsigned char)key.back())) key.pop_back();
+    size_t vb = 0;
+    while (vb < val.size() && isspace((unsigned char)val[vb])) ++vb;
+    val = val.substr(vb);
+    if (key.empty() || key == "ini") continue;
+    store->push_back(val.empty() ? "--" + key : "--" + key + "=" + val);
+  }
+  fclose(f);
+  out->clear();
+  out->push_back(argv[0]);
+  out->push_back(argv[1]);
+  for (auto& s : *store) out->push_back(&s[0]);
+  for (int a = 2; a < argc; ++a) out->push_back(argv[a]);
+  return true;
+}
+
+int main(int argc0, char** argv0) {
+  std::vector<std::string> ini_store;
+  std::vector<char*> args;
+  if (argc0 >= 2 && !expand_ini(argc0, argv0, &ini_store, &args)) return 1;
+  if (argc0 < 2) args.assign(argv0, argv0 + argc0);
+  args.push_back(nullptr);
+  const int argc = (int)args.size() - 1;
+  char** argv = args.data();
   if (argc < 2 || !strcmp(argv[1], "-h") || !strcmp(argv[1], "--help")) {
     printf("siga (B200 build) -- Usage: siga <command> [<args>]\n\n"
            "   index       build the BWT and FM-index for a set of reads\n"

@@ -39,7 +39,7 @@ static void bcr_passes(sgx_ctx* ctx, const sgx_reads* reads, const ReadAcc& acc,
   const uint32_t uniform_len = reads->min_len == lmax ? lmax : 0;
   const uint64_t nt_max = S / kMergeTile + 2;
   DevBuf<uint32_t> ID0(N), ID1(N);
-  DevBuf<PosT> NP0(N), NP1(N), tmpPos(N);
+  DevBuf<PosT> NP0(N), NP1(N);
   DevBuf<uint8_t> SYM0(N), SYM1(N);
   DevBuf<uint32_t> WIN0(N), WIN1(N);
   DevBuf<uint2> blk(nt_max * 32);
@@ -66,10 +66,8 @@ static void bcr_passes(sgx_ctx* ctx, const sgx_reads* reads, const ReadAcc& acc,
   for (uint32_t j = 1; j <= lmax; ++j) {
     const uint64_t nact = nact_by_pass[j];  // reads with length >= j
     if (nact == 0) break;
-    SGX_LAUNCH(ctx, (bcr_rank_kernel<PosT>), grid_for(nact_prev, 256), 256, 0, (const uint8_t*)B, (const uint2*)blk.p,
-               (const uint64_t*)tiletot.p, nt, N, (const uint8_t*)SYM, (const PosT*)NP, nact_prev, tmpPos.p);
     SymDigit dg{SYM};
-    BcrMove<PosT> mv{acc, ID, tmpPos.p, WIN, j, uniform_len, ID2, NP2, SYM2, WIN2};
+    BcrMove<PosT> mv{acc, ID, WIN, j, uniform_len, ID2, NP2, SYM2, WIN2, B, blk.p, tiletot.p, nt, N, SYM, NP};
     partition_pass<4>(ctx, dg, mv, nact_prev, part_ws.p, (uint64_t*)nullptr);
     const uint64_t n_new = n_cur + nact;
     const uint64_t ntiles = (n_new + kMergeTile - 1) / kMergeTile;

@@ -311,11 +311,13 @@ struct SymDigit {
 // its new row holds (the base before the suffix; '$' when the read starts here).  That base comes from the read store
 // -- the one random gather of a pass -- so the 32-bit word it sits in travels with the item (WIN): consecutive passes
 // walk through the same word, and only every 16th pass (or every pass's first for a new item) touches the read store.
+// The row of the item's next suffix is computed right here (the arithmetic of bcr_rank_kernel, which the single-device
+// build no longer launches): the scatter already visits every active item once, so the rank lookup rides on it and the
+// array of new positions never goes through memory on its own.
 template <class PosT>
 struct BcrMove {
   ReadAcc acc;
   const uint32_t* ID;
-  const PosT* tmpPos;
   const uint32_t* WIN;
   uint32_t j;
   uint32_t uniform_len;  // != 0: every read has this length (no gather of len[])
@@ -323,11 +325,25 @@ struct BcrMove {
   PosT* NP2;
   uint8_t* SYM2;
   uint32_t* WIN2;
+  // rank lookup: partial BWT of the previous pass, its two checkpoint levels, the items' current rows and symbols
+  const uint8_t* B;
+  const uint2* blk;
+  const uint64_t* scanned;
+  uint64_t ntiles, base;
+  const uint8_t* SYM;
+  const PosT* NP;
   __device__ __forceinline__ void operator()(uint64_t k, uint64_t dest) const {
     const uint32_t id = ID[k];
+    const uint32_t sym = (uint32_t)SYM[k];  // 1..4 here: ended reads are dropped by the partition digit
+    const uint64_t P = (uint64_t)NP[k];
+    const uint64_t b = P / kBcrBlock;
+    const uint32_t c = sym - 1;
+    const uint2 bv = __ldg(blk + b);
+    const uint64_t sc = __ldg(scanned + (uint64_t)c * ntiles + (b >> 5));
+    const uint32_t inblk = block_rank(B, b, (uint32_t)(P - b * kBcrBlock), sym);
     const uint32_t l = uniform_len ? uniform_len : acc.rv.len[id];
     ID2[dest] = id;
-    NP2[dest] = tmpPos[k];
+    NP2[dest] = (PosT)(base + sc + blk_field(bv, c) + inblk);
     if (l == j) {
       SYM2[dest] = 0;
       return;

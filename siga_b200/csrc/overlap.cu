@@ -176,6 +176,8 @@ struct OvPlan {
     rv = rd->view();
     fmp.blocks[0] = vf.blocks;
     fmp.blocks[1] = vr.blocks;
+    fmp.inv[0] = f->inv;
+    fmp.inv[1] = r->inv;
     for (int i = 0; i < 6; ++i) {
       fmp.pred[0][i] = vf.pred[i];
       fmp.pred[1][i] = vr.pred[i];
@@ -240,7 +242,7 @@ struct OvPlan {
   template <class IdxT>
   void launch_lean(uint64_t rfirst, uint64_t n, const OvBatch& bt, const uint32_t* list) {
     const int minb = (int)env_u64("SGX_LEAN_MINB", 4);
-    const unsigned grid = (unsigned)ctx->sm_count * 2 * (unsigned)minb;
+    const unsigned grid = (unsigned)ctx->sm_count * (unsigned)env_u64("SGX_LEAN_WAVES", 1) * (unsigned)(minb == 9 ? 4 : minb);
     // uniform: the queries are the indexed reads and all of them have one length (see the kernel's header)
     const bool uni = fast && reads == fwd->indexed && reads->min_len == reads->max_len;
     if (minb == 9) {  // experiments: the round-1 kernel (full rank vectors, other-side interval carried along)
@@ -262,7 +264,12 @@ struct OvPlan {
         av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
         SGX_CUDA(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &av));
       }
-      if (minb == 6) {
+      if (uni && !env_u64("SGX_LEAN_LOCKSTEP", 0)) {  // reads of one length: persistent quads
+        const uint32_t ul = reads->max_len, uw = (reads->max_len + 15) / 16;
+        if (minb == 6) SGX_LAUNCH(ctx, (ov_search_pq_kernel<IdxT, 6>), grid, kOvThreads, 0, fmp, rv, ul, uw, rfirst, n, min_ov, rc, bt, list, d_look.p, only);
+        else if (minb == 5) SGX_LAUNCH(ctx, (ov_search_pq_kernel<IdxT, 5>), grid, kOvThreads, 0, fmp, rv, ul, uw, rfirst, n, min_ov, rc, bt, list, d_look.p, only);
+        else SGX_LAUNCH(ctx, (ov_search_pq_kernel<IdxT, 4>), grid, kOvThreads, 0, fmp, rv, ul, uw, rfirst, n, min_ov, rc, bt, list, d_look.p, only);
+      } else if (minb == 6) {
         if (uni) SGX_LAUNCH(ctx, (ov_search_lean_kernel<IdxT, 6, true>), grid, kOvThreads, 0, fmp, rv, rfirst, n, min_ov, rc, bt, list, d_look.p, only);
         else SGX_LAUNCH(ctx, (ov_search_lean_kernel<IdxT, 6, false>), grid, kOvThreads, 0, fmp, rv, rfirst, n, min_ov, rc, bt, list, d_look.p, only);
       } else if (minb == 5) {
@@ -471,6 +478,25 @@ void overlap_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const sgx_r
 // straight to the output; no blocks, no compaction, no host round trip per batch.  Reads outside the fast path's
 // preconditions are collected and redone at the end through the full-block kernels + ov_edges_items_kernel.
 
+// Deterministic edge order: reads reserve their slice of the edge array with an atomic, so the order of the slices
+// depends on warp scheduling; a stable sort by query read (LSD radix over the query index, the edges of one read keep
+// the order their warp wrote them in) makes the array -- and the ED section the CLI writes from it -- identical from
+// run to run.
+__global__ void ov_edge_keys_kernel(const sgx_edge* __restrict__ edges, uint64_t n, uint64_t first, uint64_t* __restrict__ keys,
+                                    uint32_t* __restrict__ vals) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  keys[i] = (uint64_t)edges[i].query - first;
+  vals[i] = (uint32_t)i;
+}
+__global__ void ov_edge_permute_kernel(const sgx_edge* __restrict__ edges, const uint32_t* __restrict__ order, uint64_t n,
+                                       sgx_edge* __restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint4 e = *reinterpret_cast<const uint4*>(edges + order[i]);
+  *reinterpret_cast<uint4*>(out + i) = e;
+}
+
 // One thread per general-path work item: expands the blocks it produced into edges.
 __global__ void ov_edges_items_kernel(const sgx_block* __restrict__ out, const uint32_t* __restrict__ nout, uint32_t out_cap,
                                       const uint32_t* __restrict__ list, uint64_t n_items, uint64_t first,
@@ -665,6 +691,19 @@ void overlap_edges_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const
     SGX_CUDA(cudaStreamSynchronize(ctx->stream));
     n_edges = ne;
     break;
+  }
+  if (n_edges > 1 && n_edges < 0xffffffffull && !env_u64("SGX_EDGES_UNSORTED", 0)) {
+    static_assert(sizeof(sgx_edge) == 16, "sgx_edge is moved as one 16-byte vector");
+    DevBuf<uint64_t> keys(n_edges), keys2(n_edges), ws(part_ws_elems(n_edges, 256));
+    DevBuf<uint32_t> vals(n_edges), vals2(n_edges);
+    DevBuf<sgx_edge> sorted(n_edges);
+    SGX_LAUNCH(ctx, ov_edge_keys_kernel, grid_for(n_edges, 256), 256, 0, (const sgx_edge*)d_edges.p, n_edges, first, keys.p, vals.p);
+    int bits = 1;
+    while (bits < 32 && ((uint64_t)1 << bits) < std::max<uint64_t>(count, 2)) ++bits;
+    radix_sort_pairs(ctx, keys.p, vals.p, keys2.p, vals2.p, n_edges, bits, ws.p);
+    SGX_LAUNCH(ctx, ov_edge_permute_kernel, grid_for(n_edges, 256), 256, 0, (const sgx_edge*)d_edges.p, (const uint32_t*)vals.p,
+               n_edges, sorted.p);
+    d_edges.swap(sorted);
   }
   out->n_reads = count;
   out->n_edges = n_edges;

@@ -33,6 +33,7 @@ __device__ __forceinline__ void quad_store_block(sgx_block* dst, IdxT c0lo, IdxT
 struct FmPair {
   const FmBlockLane* blocks[2];  // 0 = forward index, 1 = reverse index
   uint64_t pred[2][6];
+  const uint32_t* inv[2];        // read id -> row of its '$' block entry (inverse .sai / .rsai), when reads are attached
 };
 
 // LEAN: write 12-byte LeanCand records (capped[0], length, flags) instead of full 72-byte blocks.
@@ -228,6 +229,11 @@ ov_search_quad_kernel(FmPair fm, ReadsView reads, uint64_t first, uint64_t count
 // identical read, every row of its interval holds '$' in both indices, so the containment block is the '$' rank of the
 // interval's first row and its width -- one rank-block fetch, no walk through the opposite index.  (Modes 0 and 2 always
 // end with a full-length match: the read finds itself.)
+// Modes 0 and 2 search a read in the index that holds it, so their interval never empties: once it has narrowed to ONE row
+// that row is the read's own suffix, no other read shares it, every further '$' probe finds nothing and the full-length
+// interval is the read's own row of the '$' block, i.e. its position in the .sai order.  The walk stops there (a read with a
+// sequencing error walks on average half its length instead of all of it) and the containment block comes from the inverse
+// .sai without a fetch.
 // Work order: all (read, mode) pairs that search the forward index first, then those of the reverse index; the quads of
 // the grid advance together, so at any time one index (232 MB at config 2) competes for the 126 MB L2, not both.
 // The symbol stream is read one 32-bit word per 16 steps.
@@ -272,7 +278,9 @@ ov_search_lean_kernel(FmPair fm, ReadsView reads, uint64_t first, uint64_t count
     bool live = have && i > 0 && hi0 != kNone && hi0 >= lo0;
     uint32_t word = live ? (rw[j >> 4] ^ cm) : 0u;  // (complemented) codes of the 16 bases around j
     int cnext = (int)((word >> (2 * (j & 15))) & 3u) + 1;
-    uint32_t lines = 0;
+    uint32_t lines = 0, steps = 0;
+    const bool selfmode = (mode & 1) == 0;  // modes 0 and 2: the read is in the searched index
+    bool selfonly = false;
 #pragma unroll 1
     while (__any_sync(kFull, live)) {
       c = cnext;
@@ -362,14 +370,28 @@ ov_search_lean_kernel(FmPair fm, ReadsView reads, uint64_t first, uint64_t count
         lo0 = nlo;
         hi0 = nhi;
         --i;
+        ++steps;
         live = i > 0 && hi0 != kNone && hi0 >= lo0;
+        if (UNIFORM && selfmode && live && hi0 == lo0) {  // only the read itself is left
+          live = false;
+          selfonly = true;
+        }
       }
     }
-    if (have && l > 0) nlook += 2ull * ((l - 1) - i);  // steps taken
+    nlook += 2ull * steps;
     // ---- containment handling (src/overlap_builder.cpp:877-905), warp-uniform
-    const bool tail = have && hi0 != kNone && hi0 >= lo0;  // only reachable with i == 0
+    const bool tail = have && !selfonly && hi0 != kNone && hi0 >= lo0;  // only reachable with i == 0
     uint32_t ncontain = 0;
     if (UNIFORM) {
+      if (selfonly) {
+        if (q == 0) {
+          LeanCand lc;
+          lc.lo = lc.hi = fm.inv[pi][rd];
+          lc.len_af = l | (ov_mode_af(mode) << 16);
+          bt.lean_contain[(size_t)wi * 4 + mode] = lc;
+        }
+        ncontain = 1;
+      }
       if (__any_sync(kFull, tail)) {
         const IdxT plo = tail ? lo0 : (IdxT)0;
         const uint64_t b1 = (uint64_t)plo >> kBlockShift;
@@ -470,6 +492,233 @@ ov_search_lean_kernel(FmPair fm, ReadsView reads, uint64_t first, uint64_t count
     const uint64_t quad = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / kQuad;
     const uint64_t nquads = ((uint64_t)gridDim.x * blockDim.x) / kQuad;
     for (uint64_t r = quad; r < count; r += nquads) {
+      if (q == 0) {
+        bt.ncand[r * 4 + 1] = 0;
+        bt.ncand[r * 4 + 3] = 0;
+        bt.ncontain[r * 4 + 1] = 0;
+        bt.ncontain[r * 4 + 3] = 0;
+      }
+    }
+  }
+  if (q == 0) {
+    if (nlook) atomicAdd(lookups, nlook);
+    if (nlines) atomicAdd(lookups + 2, nlines);
+  }
+}
+
+
+// ---- lean search, persistent quads (reads of one length) -------------------------------------------------------------
+//
+// ov_search_lean_kernel walks the eight chains of a warp in lock-step until the LAST of them has finished; with the early
+// exits above a chain takes anything between a few and L-1 steps (77 on average at config 2), so half of the lanes of a
+// warp step were idle riders.  Here a quad that has finished its (read, mode) pair writes its result and takes its next
+// pair at once, inside the same loop: the warp executes the finalize-and-fetch block when any of its quads needs it
+// (~150 instructions per pair, against ~100 per step), and every step it executes carries eight live chains.
+// Same arithmetic and outputs as ov_search_lean_kernel<.., UNIFORM = true>; pairs are handed out in index-major order
+// (quad g takes pairs g, g + #quads, ...).
+template <class IdxT, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+ov_search_pq_kernel(FmPair fm, ReadsView reads, uint32_t ulen, uint32_t uwords, uint64_t first, uint64_t count, uint32_t min_ov,
+                    int rc, OvBatch bt, const uint32_t* __restrict__ list, unsigned long long* __restrict__ lookups, int only_pi) {
+  const unsigned kFull = 0xffffffffu;
+  const int q = threadIdx.x & (kQuad - 1);
+  const int qbase = threadIdx.x & 31 & ~(kQuad - 1);
+  const int nmodes = rc ? 4 : 2;
+  const uint64_t nwork = count * nmodes;
+  const uint64_t wk_begin = only_pi > 0 ? nwork / 2 : 0, wk_end = only_pi == 0 ? nwork / 2 : nwork;
+  const uint64_t stride = ((uint64_t)gridDim.x * blockDim.x) / kQuad;
+  uint64_t wk = wk_begin + ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / kQuad;  // next pair of this quad
+  unsigned long long nlook = 0, nlines = 0;
+  const IdxT kNone = (IdxT)-1;
+  const bool wide = sizeof(IdxT) == 8;
+  const uint32_t l = ulen;
+
+  // state of the pair in flight
+  bool active = false, live = false, selfonly = false, selfmode = false, backwards = false;
+  const FmBlockLane* __restrict__ Pb = fm.blocks[0];
+  const uint32_t* rw = reads.words;
+  IdxT mypc = 0, lo0 = 0, hi0 = 0;
+  uint64_t slot = 0;  // wi * 4 + mode: where the results go
+  uint32_t rd32 = 0, i = 0, j = 0, word = 0, cm = 0, n = 0, steps = 0, lines = 0;
+  int cnext = 1, pi = 0;
+
+  for (;;) {
+    const bool need = !live;
+    if (__any_sync(kFull, need)) {
+      // ---- finish the pair that has just ended: containment block, counters
+      const bool tail = need && active && !selfonly && hi0 != kNone && hi0 >= lo0;  // full-length match other than the read itself
+      if (__any_sync(kFull, tail)) {
+        const IdxT plo = tail ? lo0 : (IdxT)0;
+        const uint64_t b1 = (uint64_t)plo >> kBlockShift;
+        const int r1 = (int)(plo & (kBlockSyms - 1));
+        const uint4* pa = reinterpret_cast<const uint4*>(Pb + b1 * kGroup + q);
+        const uint4 a0 = __ldg(pa), a1 = __ldg(pa + 4);
+        uint32_t ma0, ma1;
+        asm("shl.b32 %0, %1, %2;" : "=r"(ma0) : "r"(0xffffffffu), "r"((uint32_t)max(r1 - 32 * q, 0)));
+        asm("shl.b32 %0, %1, %2;" : "=r"(ma1) : "r"(0xffffffffu), "r"((uint32_t)max(r1 - 32 * (q + 4), 0)));
+        uint32_t dl = (uint32_t)__popc(a0.z & ~ma0) + (uint32_t)__popc(a1.z & ~ma1);
+        IdxT hs = wide ? (IdxT)((uint64_t)a1.w << 32 | a0.w) : (IdxT)a0.w;
+#pragma unroll
+        for (int m = 1; m < kQuad; m <<= 1) {
+          dl += __shfl_xor_sync(kFull, dl, m);
+          hs += __shfl_xor_sync(kFull, hs, m);
+        }
+        if (tail) {
+          nlook += 1;
+          nlines += 1;
+          if (q == 0) {
+            const IdxT Ld = (IdxT)(b1 << kBlockShift) - hs + dl;
+            LeanCand lc;
+            lc.lo = (uint32_t)Ld;
+            lc.hi = (uint32_t)(Ld + (hi0 - lo0));
+            lc.len_af = l | (ov_mode_af((int)(slot & 3)) << 16);
+            bt.lean_contain[slot] = lc;
+          }
+        }
+      }
+      if (need && active) {
+        if (selfonly && q == 0) {
+          LeanCand lc;
+          lc.lo = lc.hi = fm.inv[pi][rd32];
+          lc.len_af = l | (ov_mode_af((int)(slot & 3)) << 16);
+          bt.lean_contain[slot] = lc;
+        }
+        if (q == 0) {
+          bt.ncand[slot] = n < bt.find_cap ? n : bt.find_cap;
+          bt.ncontain[slot] = (selfonly || tail) ? 1u : 0u;
+        }
+        nlook += 2ull * steps;
+        nlines += lines;
+        active = false;
+      }
+      // ---- take the next pair
+      if (need && wk < wk_end) {
+        active = true;
+        pi = wk >= nwork / 2 ? 1 : 0;  // index-major order (see ov_search_lean_kernel)
+        const uint64_t within = wk - (pi ? nwork / 2 : 0);
+        const uint64_t wi = rc ? within >> 1 : within;
+        const int mode = 2 * pi + (rc ? (int)(within & 1) : 0);
+        wk += stride;
+        slot = wi * 4 + mode;
+        Pb = fm.blocks[pi];
+        mypc = (IdxT)fm.pred[pi][q + 1];
+        const uint64_t rd = first + (list ? (uint64_t)list[wi] : wi);
+        rd32 = (uint32_t)rd;
+        rw = reads.words + rd * uwords;
+        backwards = mode == 1 || mode == 2;
+        cm = (mode & 1) ? 0xffffffffu : 0u;
+        selfmode = (mode & 1) == 0;
+        selfonly = false;
+        n = 0;
+        steps = 0;
+        lines = 0;
+        const int c = ov_sym(rw, l, mode, l - 1);
+        lo0 = (IdxT)fm.pred[pi][c];
+        hi0 = (IdxT)(fm.pred[pi][c + 1] - 1);
+        j = backwards ? 1u : l - 2;
+        i = l - 1;
+        live = i > 0 && hi0 != kNone && hi0 >= lo0;
+        word = live ? (rw[j >> 4] ^ cm) : 0u;
+        cnext = (int)((word >> (2 * (j & 15))) & 3u) + 1;
+      }
+      if (!__any_sync(kFull, active)) break;
+      if (!__any_sync(kFull, live)) continue;  // pairs that ended before their first step are finished next round
+    }
+    // ---- one backward step of every live quad (the body of ov_search_lean_kernel)
+    const int c = cnext;
+    const uint32_t dj = backwards ? 1u : 0xffffffffu;
+    j += dj;
+    if (live && i > 1 && (j & 15u) == (backwards ? 0u : 15u)) word = rw[j >> 4] ^ cm;
+    cnext = (int)((word >> (2 * (j & 15))) & 3u) + 1;
+    const IdxT plo = live ? lo0 : (IdxT)0, phi = live ? (IdxT)(hi0 + 1) : (IdxT)0;
+    const uint64_t b1 = (uint64_t)plo >> kBlockShift, b2 = (uint64_t)phi >> kBlockShift;
+    const int r1 = (int)(plo & (kBlockSyms - 1)), r2 = (int)(phi & (kBlockSyms - 1));
+    const uint4* pa = reinterpret_cast<const uint4*>(Pb + b1 * kGroup + q);
+    const uint4 a0 = __ldg(pa), a1 = __ldg(pa + 4);
+    uint4 c0 = a0, c1 = a1;
+    if (b2 != b1) {
+      const uint4* pb = reinterpret_cast<const uint4*>(Pb + b2 * kGroup + q);
+      c0 = __ldg(pb);
+      c1 = __ldg(pb + 4);
+    }
+    uint32_t ma0, ma1, mc0, mc1;
+    asm("shl.b32 %0, %1, %2;" : "=r"(ma0) : "r"(0xffffffffu), "r"((uint32_t)max(r1 - 32 * q, 0)));
+    asm("shl.b32 %0, %1, %2;" : "=r"(ma1) : "r"(0xffffffffu), "r"((uint32_t)max(r1 - 32 * (q + 4), 0)));
+    asm("shl.b32 %0, %1, %2;" : "=r"(mc0) : "r"(0xffffffffu), "r"((uint32_t)max(r2 - 32 * q, 0)));
+    asm("shl.b32 %0, %1, %2;" : "=r"(mc1) : "r"(0xffffffffu), "r"((uint32_t)max(r2 - 32 * (q + 4), 0)));
+    const uint32_t x0 = ((c - 1) & 1) ? 0u : 0xffffffffu, x1 = ((c - 1) & 2) ? 0u : 0xffffffffu;
+    uint32_t packed = (uint32_t)__popc(~(a0.z | ma0) & (a0.x ^ x0) & (a0.y ^ x1)) +
+                      (uint32_t)__popc(~(a1.z | ma1) & (a1.x ^ x0) & (a1.y ^ x1)) +
+                      (((uint32_t)__popc(~(c0.z | mc0) & (c0.x ^ x0) & (c0.y ^ x1)) +
+                        (uint32_t)__popc(~(c1.z | mc1) & (c1.x ^ x0) & (c1.y ^ x1))) << 16);
+    packed += __shfl_xor_sync(kFull, packed, 1);
+    packed += __shfl_xor_sync(kFull, packed, 2);
+    const int src = qbase + c - 1;
+    IdxT nlo, nhi;
+    if (wide) {
+      const uint64_t ha = ((uint64_t)a1.w << 32 | a0.w) + mypc, hc = ((uint64_t)c1.w << 32 | c0.w) + mypc;
+      nlo = (IdxT)__shfl_sync(kFull, (unsigned long long)ha, src);
+      nhi = (IdxT)__shfl_sync(kFull, (unsigned long long)hc, src);
+    } else {
+      nlo = (IdxT)__shfl_sync(kFull, a0.w + (uint32_t)mypc, src);
+      nhi = (IdxT)__shfl_sync(kFull, c0.w + (uint32_t)mypc, src);
+    }
+    nlo += (IdxT)(packed & 0xffffu);
+    nhi += (IdxT)(packed >> 16);
+    nhi -= 1;
+    const uint32_t olen = l - i;
+    const bool elig = live && olen >= min_ov;
+    if (__any_sync(kFull, elig)) {
+      const uint32_t nb = (uint32_t)min(b2 - b1, (uint64_t)64);
+      uint32_t pk = ((uint32_t)__popc(a0.z & ~ma0) + (uint32_t)__popc(a1.z & ~ma1)) |
+                    (((uint32_t)__popc(c0.z & ~mc0) + (uint32_t)__popc(c1.z & ~mc1)) << 9) | ((c0.w - a0.w) << 18);
+      pk += __shfl_xor_sync(kFull, pk, 1);
+      pk += __shfl_xor_sync(kFull, pk, 2);
+      const uint32_t dl = pk & 511u;
+      IdxT dd = (IdxT)(((pk >> 9) & 511u) - dl + 256u * nb - (pk >> 18));
+      IdxT Ld = 0;
+      const bool far = elig && nb > 63;
+      if (__any_sync(kFull, far)) {
+        const QuadRank<IdxT> k = quad_rank<IdxT>(Pb, far ? plo : (IdxT)0, far ? phi : (IdxT)0, q);
+        if (far) {
+          dd = k.Ud - k.Ld;
+          Ld = k.Ld;
+        }
+      }
+      const bool emit = elig && dd >= 1;
+      if (__any_sync(kFull, emit)) {
+        IdxT hs = wide ? (IdxT)((uint64_t)a1.w << 32 | a0.w) : (IdxT)a0.w;
+        hs += __shfl_xor_sync(kFull, hs, 1);
+        hs += __shfl_xor_sync(kFull, hs, 2);
+        if (!far) Ld = (IdxT)(b1 << kBlockShift) - hs + dl;
+        if (emit) {
+          if (n < bt.find_cap && q == 0) {
+            LeanCand lc;
+            lc.lo = (uint32_t)Ld;
+            lc.hi = (uint32_t)(Ld + dd - 1);
+            lc.len_af = olen | (ov_mode_af((int)(slot & 3)) << 16);
+            bt.lean[slot * bt.find_cap + n] = lc;
+          }
+          ++n;
+        }
+      }
+    }
+    if (live) {
+      lines += b2 != b1 ? 2u : 1u;
+      lo0 = nlo;
+      hi0 = nhi;
+      --i;
+      ++steps;
+      live = i > 0 && hi0 != kNone && hi0 >= lo0;
+      if (selfmode && live && hi0 == lo0) {  // only the read itself is left
+        live = false;
+        selfonly = true;
+      }
+    }
+  }
+  if (!rc && only_pi <= 0) {
+    const uint64_t quad = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / kQuad;
+    for (uint64_t r = quad; r < count; r += stride) {
       if (q == 0) {
         bt.ncand[r * 4 + 1] = 0;
         bt.ncand[r * 4 + 3] = 0;

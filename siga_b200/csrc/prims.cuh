@@ -95,6 +95,34 @@ static __global__ void scan_tile_apply_kernel(uint64_t* __restrict__ data, uint6
   if (total_out && blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) *total_out = run;
 }
 
+// Same, with the tile offset summed by the CTA itself from the tile sums (no scan of the tile sums in between): two
+// launches instead of three for arrays of up to kScanDirectTiles tiles, which is every scan of a column pass.
+static const uint64_t kScanDirectTiles = 4096;
+static __global__ void scan_tile_apply_direct_kernel(uint64_t* __restrict__ data, uint64_t n, const uint64_t* __restrict__ tilesum,
+                                                     uint64_t* __restrict__ total_out) {
+  __shared__ uint64_t sh[9];
+  uint64_t before = 0;
+  for (uint32_t t = threadIdx.x; t < blockIdx.x; t += kScanThreads) before += tilesum[t];
+  uint64_t off_total;
+  block_excl_scan(before, sh, off_total);  // off_total = sum of the sums of all earlier tiles
+  const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanIpt;
+  uint64_t v[kScanIpt];
+  uint64_t s = 0;
+#pragma unroll
+  for (int i = 0; i < kScanIpt; ++i) {
+    v[i] = base + i < n ? data[base + i] : 0;
+    s += v[i];
+  }
+  uint64_t total;
+  uint64_t run = block_excl_scan(s, sh, total) + off_total;
+#pragma unroll
+  for (int i = 0; i < kScanIpt; ++i) {
+    if (base + i < n) data[base + i] = run;
+    run += v[i];
+  }
+  if (total_out && blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) *total_out = run;
+}
+
 // Number of uint64 workspace elements scan_exclusive needs for an n-element array.
 inline uint64_t scan_ws_elems(uint64_t n) {
   uint64_t ws = 0;
@@ -117,6 +145,10 @@ inline void scan_exclusive(sgx_ctx* ctx, uint64_t* data, uint64_t n, uint64_t* w
     return;
   }
   SGX_LAUNCH(ctx, scan_tile_reduce_kernel, (unsigned)ntiles, kScanThreads, 0, data, n, ws);
+  if (ntiles <= kScanDirectTiles) {
+    SGX_LAUNCH(ctx, scan_tile_apply_direct_kernel, (unsigned)ntiles, kScanThreads, 0, data, n, (const uint64_t*)ws, total_dev);
+    return;
+  }
   scan_exclusive(ctx, ws, ntiles, ws + ntiles, total_dev);
   SGX_LAUNCH(ctx, scan_tile_apply_kernel, (unsigned)ntiles, kScanThreads, 0, data, n, (const uint64_t*)ws,
              (uint64_t*)nullptr);

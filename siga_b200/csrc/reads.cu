@@ -68,7 +68,10 @@ __global__ void __launch_bounds__(256) reads_pack_kernel(const char* __restrict_
     }
     dst[w] = v;
   }
-  if (!ok) atomicOr(bad, 2u);
+  if (!ok) {
+    atomicOr(bad, 2u);
+    atomicMin(bad + 1, (uint32_t)warp);  // first offending read, for the error message
+  }
 }
 
 sgx_reads* reads_pack(sgx_ctx* ctx, const char* ascii, const uint64_t* off, uint64_t n) {
@@ -78,12 +81,12 @@ sgx_reads* reads_pack(sgx_ctx* ctx, const char* ascii, const uint64_t* off, uint
   SGX_REQUIRE(off[n] >= off[0] && total > 0, SGX_EINVAL, "sgx_reads_pack: bad offsets");
   DevBuf<char> d_ascii(total);
   DevBuf<uint64_t> d_off(n + 1), d_woff, ws(scan_ws_elems(n + 1));
-  DevBuf<uint32_t> d_len, d_flags(3);
+  DevBuf<uint32_t> d_len, d_flags(4);
   d_woff.alloc_owned(n + 1);  // woff / len / words become the read store
   d_len.alloc_owned(n);
   SGX_CUDA(cudaMemcpyAsync(d_ascii.p, ascii + off[0], total, cudaMemcpyHostToDevice, ctx->stream));
   SGX_CUDA(cudaMemcpyAsync(d_off.p, off, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-  const uint32_t init[3] = {0xffffffffu, 0u, 0u};  // min, max, bad
+  const uint32_t init[4] = {0xffffffffu, 0u, 0u, 0xffffffffu};  // min, max, bad, first read with a bad base
   SGX_CUDA(cudaMemcpyAsync(d_flags.p, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
   SGX_CUDA(cudaMemsetAsync(d_woff.p, 0, (n + 1) * sizeof(uint64_t), ctx->stream));
   SGX_LAUNCH(ctx, reads_len_kernel, grid_for(n, 256), 256, 0, (const uint64_t*)d_off.p, n, d_len.p, d_woff.p,
@@ -91,7 +94,7 @@ sgx_reads* reads_pack(sgx_ctx* ctx, const char* ascii, const uint64_t* off, uint
   // woff[i] = words before read i ; woff[n] = total words (the scan of n+1 elements with a trailing 0)
   scan_exclusive(ctx, d_woff.p, n + 1, ws.p, (uint64_t*)nullptr);
   uint64_t n_words = 0;
-  uint32_t flags[3];
+  uint32_t flags[4];
   SGX_CUDA(cudaMemcpyAsync(&n_words, d_woff.p + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
   SGX_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
   SGX_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -112,7 +115,12 @@ sgx_reads* reads_pack(sgx_ctx* ctx, const char* ascii, const uint64_t* off, uint
              (const uint64_t*)d_woff.p, n, d_words.p, d_flags.p + 2);
   SGX_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
   SGX_CUDA(cudaStreamSynchronize(ctx->stream));
-  SGX_REQUIRE((flags[2] & 2u) == 0, SGX_EINVAL, "sgx_reads_pack: base other than A/C/G/T");
+  if (flags[2] & 2u) {
+    char msg[200];
+    snprintf(msg, sizeof(msg), "sgx_reads_pack: base other than A/C/G/T (first in read %u of this call; the hot path takes "
+                               "preprocessed reads, as `siga preprocess` writes them)", flags[3]);
+    throw Error{SGX_EINVAL, msg};
+  }
   sgx_reads* r = new sgx_reads();
   r->ctx = ctx;
   r->n = n;

@@ -30,6 +30,9 @@ struct sgx_ctx {
     bool in_use;
   };
   std::vector<WsEntry> ws_cache;
+  // second stream of the same device with its own work-area cache, for entry points that run two independent jobs
+  // side by side (sgx_index_build_pair); created on first use, owned by this context
+  sgx_ctx* aux = nullptr;
 };
 
 namespace sgx {

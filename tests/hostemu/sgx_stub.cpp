@@ -10,6 +10,8 @@
 #include "hostemu.cpp"
 
 #include <algorithm>
+#include <unistd.h>
+
 #include <string>
 
 struct sgx_ctx {
@@ -43,8 +45,12 @@ int no_device(sgx_ctx* ctx, const char* what) {
 
 extern "C" {
 
+// Failure injection for the tests of the front-end's worker coordination (`--gpus N`): the rank whose device index equals
+// SGX_STUB_FAIL_DEVICE fails in sgx_reads_pack; the rank on SGX_STUB_HANG_DEVICE never returns from it (a peer stuck in
+// a collective).
+static int g_device = 0;
 int sgx_init(int device, sgx_ctx** out) {
-  (void)device;
+  g_device = device;
   *out = new sgx_ctx();
   return SGX_OK;
 }
@@ -53,6 +59,12 @@ const char* sgx_last_error(const sgx_ctx* ctx) { return ctx ? ctx->err.c_str() :
 
 int sgx_reads_pack(sgx_ctx* ctx, const char* ascii, const uint64_t* off, uint64_t n, sgx_reads** out) {
   if (!ctx || !ascii || !off || n == 0) return SGX_EINVAL;
+  if (getenv("SGX_STUB_HANG_DEVICE") && atoi(getenv("SGX_STUB_HANG_DEVICE")) == g_device)
+    for (;;) pause();
+  if (getenv("SGX_STUB_FAIL_DEVICE") && atoi(getenv("SGX_STUB_FAIL_DEVICE")) == g_device) {
+    ctx->err = "sgx_reads_pack: injected failure";
+    return SGX_ENOMEM;
+  }
   sgx_reads* r = new sgx_reads();
   r->ascii.assign(ascii + off[0], off[n] - off[0]);
   r->off.resize(n + 1);
@@ -269,6 +281,19 @@ int sgx_fm_count(sgx_ctx* ctx, const sgx_fm* fm, const char* ascii, const uint64
   return SGX_OK;
 }
 
+int sgx_fm_pred(const sgx_fm* fm, uint64_t pred[5]) {
+  if (!fm || !pred) return SGX_EINVAL;
+  const FmView& v = ((HemuFm*)fm->fm)->view;
+  for (int c = 0; c < 5; ++c) pred[c] = v.pred[c];
+  return SGX_OK;
+}
+
+int sgx_fm_occ(sgx_ctx* ctx, const sgx_fm* fm, const uint64_t* pos, uint64_t n, uint64_t* counts) {
+  if (!ctx || !fm || !pos || !counts) return SGX_EINVAL;
+  hemu_fm_occ(fm->fm, pos, n, counts);
+  return SGX_OK;
+}
+
 // ---- no host stand-in
 // `siga index`: brute-force suffix sorting of the two ordering models (the statement
 // oracle/pyoracle.py checks against the reference's golden vectors), small inputs only.
@@ -350,6 +375,13 @@ int sgx_index_build(sgx_ctx* ctx, const sgx_reads* reads, int order, int reverse
   memcpy(out->sai, sai.data(), n * sizeof(uint32_t));
   return SGX_OK;
 }
+void sgx_index_out_free(sgx_index_out* o);
+int sgx_index_build_pair(sgx_ctx* ctx, const sgx_reads* reads, int order, sgx_index_out* out_fwd, sgx_index_out* out_rev) {
+  int rc = sgx_index_build(ctx, reads, order, 0, out_fwd);
+  if (rc == SGX_OK && (rc = sgx_index_build(ctx, reads, order, 1, out_rev)) != SGX_OK) sgx_index_out_free(out_fwd);
+  return rc;
+}
+
 void sgx_index_out_free(sgx_index_out* o) {
   if (!o) return;
   free(o->rle);

@@ -133,6 +133,31 @@ def test_overlap_front_end_single_and_sharded_equal_reference_asqg(case):
             assert not [f for f in os.listdir(ref) if ".part" in f]
 
 
+@pytest.mark.parametrize("fail,hang", [(1, 0), (0, 1), (2, 1)])
+def test_multi_gpu_worker_failure_ends_the_run_cleanly(fail, hang):
+    """`--gpus 3`: one rank fails while another never returns (a peer blocked in a collective).  The command must exit
+    with an error within seconds, leave no part files and no worker process behind -- whichever rank fails, the calling
+    process (rank 0) included."""
+    import time
+    rng = np.random.default_rng(3)
+    g = synth.random_genome(1500, rng)
+    reads = synth.sample_reads(g, 300, 40, rng)
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "reads.fa")
+        synth.write_fasta(src, reads)
+        _cli(["index", src], d)
+        env = dict(os.environ, SGX_STUB_FAIL_DEVICE=str(fail), SGX_STUB_HANG_DEVICE=str(hang))
+        for cmd in (["overlap", "-m", "15", "--gpus", "3", src], ["correct", "-k", "11", "--gpus", "3", src]):
+            t0 = time.time()
+            p = subprocess.run([CLI] + cmd, cwd=d, env=env, capture_output=True, text=True, timeout=60)
+            assert p.returncode != 0 and time.time() - t0 < 20, (cmd, p.returncode, p.stderr[-500:])
+            assert "ERROR" in p.stderr
+            assert not [f for f in os.listdir(d) if ".part" in f], os.listdir(d)
+            time.sleep(0.3)
+            left = subprocess.run(["pgrep", "-f", src], capture_output=True, text=True).stdout.split()
+            assert not left, "worker processes left behind: %s" % left
+
+
 def test_match_front_end_equals_reference_stdout():
     """`siga match` (src/match.cpp:22-76): occurrence counts of whole reads or of their first / last -l bases, both
     strands or forward only, several input files, FASTA and FASTQ -- stdout byte for byte."""
@@ -141,6 +166,12 @@ def test_match_front_end_equals_reference_stdout():
     idx_reads = synth.sample_reads(g, 1200, 60, rng, err=0.005)
     q1 = [r.tobytes().decode() for r in synth.sample_reads(g, 300, 60, rng, err=0.01)]
     q2 = [r.tobytes().decode()[:int(l)] for r, l in zip(synth.sample_reads(g, 200, 60, rng, err=0.0), rng.integers(5, 61, 200))]
+    # un-preprocessed queries: the reference maps any other byte to the sentinel rank and reports a count for every read
+    for i, ch in ((3, "N"), (10, "n"), (11, "R"), (50, "N")):
+        k = int(rng.integers(0, len(q1[i])))
+        q1[i] = q1[i][:k] + ch + q1[i][k + 1:]
+    q1[20] = q1[20][:-1] + "N"
+    q1[21] = "N" + q1[21][1:]
     with tempfile.TemporaryDirectory() as d:
         ref_fa = os.path.join(d, "ref.fa")
         synth.write_fasta(ref_fa, idx_reads)
@@ -223,6 +254,11 @@ def test_index_front_end_equals_reference_files(algo):
         assert sorted(f for f in os.listdir(ours) if f.startswith("rev")) == ["rev.rbwt", "rev.rsai"]
         assert open(os.path.join(ours, "rev.rsai"), "rb").read() == open(os.path.join(ref, "reads.rsai"), "rb").read()
         _cli(["index", "-a", "rope", src], ours, ok=False)
+        # --gpus 2: one strand per worker process (strand groups of one GPU, no collective); each group's first rank
+        # writes its two files
+        _cli(["index", "-a", algo, "-p", "two", "--gpus", "2", src], ours)
+        for ext in (".bwt", ".rbwt", ".sai", ".rsai"):
+            assert open(os.path.join(ours, "two" + ext), "rb").read() == open(os.path.join(ref, "reads" + ext), "rb").read(), ext
 
 
 def test_whole_pipeline_through_the_front_end_gives_the_reference_contigs():
@@ -256,3 +292,37 @@ def test_whole_pipeline_through_the_front_end_gives_the_reference_contigs():
             refrun.run_ref(["assemble", "-m", "35", "-p", "asm", os.path.join(w, "reads.rmdup.asqg.gz")], w)
             res[who] = contigs(os.path.join(w, "asm-contigs.fa"))
         assert res["ours"] == res["ref"] and sum(len(c) for c in res["ref"]) > 3000
+
+
+def test_ini_file_and_bzip2_input():
+    """-s/--ini FILE: options as key=value lines, overridden by the command line (src/main.cpp:63-77); .bz2 input
+    (src/utils.cpp:92-95) gives the same files as the plain input."""
+    rng = np.random.default_rng(8)
+    g = synth.random_genome(1200, rng)
+    reads = synth.sample_reads(g, 200, 40, rng)
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "reads.fa")
+        synth.write_fasta(src, reads)
+        refrun.run_ref(["index", src], d)
+        want = {e: open(os.path.join(d, "reads" + e), "rb").read() for e in (".bwt", ".rbwt", ".sai", ".rsai")}
+        refrun.run_ref(["overlap", "-m", "17", src], d)
+        want_asqg = _asqg(os.path.join(d, "reads.asqg.gz"))
+        # bzip2 input
+        subprocess.run(["bzip2", "-k", src], check=True)
+        sub = os.path.join(d, "bz")
+        os.mkdir(sub)
+        _cli(["index", "-p", os.path.join(sub, "reads"), src + ".bz2"], d)
+        for e, b in want.items():
+            assert open(os.path.join(sub, "reads" + e), "rb").read() == b, e
+        # ini file: min-overlap from the file; a second run overrides it on the command line
+        ini = os.path.join(d, "opts.ini")
+        with open(ini, "w") as f:
+            f.write("; options\n[overlap]\nmin-overlap = 17\n")
+        os.remove(os.path.join(d, "reads.asqg.gz"))
+        _cli(["overlap", "-s", ini, src], d)
+        got = _asqg(os.path.join(d, "reads.asqg.gz"))
+        assert got[0] == want_asqg[0] and sorted(got) == sorted(want_asqg)
+        _cli(["overlap", "--ini", ini, "-m", "25", src], d)
+        assert _asqg(os.path.join(d, "reads.asqg.gz"))[0].split("\t")[2] == "OL:i:25"
+        r = _cli(["overlap", "-s", os.path.join(d, "missing.ini"), src], d, ok=False)
+        assert "load" in r.stderr and "failed" in r.stderr

@@ -198,3 +198,51 @@ def test_cli_multi_gpu_outputs_equal_single_gpu():
         ec = open(os.path.join(one, "reads.ec.fa"), "rb").read()
         assert ec == open(os.path.join(two, "reads.ec.fa"), "rb").read() and ec.count(b">") > 1000
         assert not [f for f in os.listdir(two) if ".part" in f]
+
+
+@pytest.mark.skipif(not refrun.have_ref(), reason="compiled reference (oracle/_ref/siga) not present")
+@pytest.mark.skipif(not os.path.isfile(CLI), reason="siga_b200/bin/siga not built")
+def test_cli_match_stdout_equals_reference():
+    """`siga match` on the device (sgx_fm_count, and sgx_fm_occ for queries with bytes other than A/C/G/T): stdout byte
+    for byte the reference's (src/match.cpp:22-76), whole reads and -l windows, both strands and forward only."""
+    rng = np.random.default_rng(77)
+    g = synth.random_genome(3000, rng)
+    idx_reads = synth.sample_reads(g, 1200, 60, rng, err=0.005)
+    q = [r.tobytes().decode() for r in synth.sample_reads(g, 300, 60, rng, err=0.01)]
+    q += [r.tobytes().decode()[:int(l)] for r, l in zip(synth.sample_reads(g, 100, 60, rng), rng.integers(5, 61, 100))]
+    for i, ch in ((3, "N"), (10, "n"), (11, "R")):
+        k = int(rng.integers(0, len(q[i])))
+        q[i] = q[i][:k] + ch + q[i][k + 1:]
+    q[20] = q[20][:-1] + "N"
+    q[21] = "N" + q[21][1:]
+    with tempfile.TemporaryDirectory() as d:
+        ref_fa = os.path.join(d, "ref.fa")
+        synth.write_fasta(ref_fa, idx_reads)
+        refrun.run_ref(["index", "--no-reverse", ref_fa], d)
+        a = os.path.join(d, "a.fa")
+        synth.write_fasta(a, q, names=["a%d" % i for i in range(len(q))])
+        for args in (["-p", "ref", a], ["-p", "ref", "--no-opposite-strand", a], ["-p", "ref", "-l", "20", a]):
+            want = subprocess.run([refrun.REF_BIN, "match"] + args, cwd=d, capture_output=True, text=True,
+                                  env=dict(os.environ, ORACLE_LOG_LEVEL="5"))
+            assert want.returncode == 0 and want.stdout.count("\n") >= len(q)
+            assert _run(["match"] + args, d).stdout == want.stdout, args
+
+
+@pytest.mark.skipif(not os.path.isfile(CLI), reason="siga_b200/bin/siga not built")
+def test_cli_edge_order_is_reproducible():
+    """The ED section is ordered by query read (stable device sort of the edge records): two runs write the same bytes."""
+    rng = np.random.default_rng(12)
+    g = synth.random_genome(30_000, rng)
+    reads = synth.sample_reads(g, 20_000, 100, rng, err=0.01)
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "reads.fa")
+        synth.write_fasta(src, reads)
+        _run(["index", src], d)
+        outs = []
+        for k in range(2):
+            _run(["overlap", "-m", "40", "-p", os.path.join(d, "reads"), src], d)
+            with gzip.open(os.path.join(d, "reads.asqg.gz"), "rb") as f:
+                outs.append(f.read())
+        assert outs[0] == outs[1] and outs[0].count(b"\nED\t") > 10_000
+        ed = [int(l.split(b"\t")[1].split(b" ")[0][1:]) for l in outs[0].split(b"\n") if l.startswith(b"ED")]
+        assert ed == sorted(ed)
