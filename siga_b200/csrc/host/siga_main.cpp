@@ -640,6 +640,7 @@ int cmd_index(int argc, char** argv) {
       }
     }
   }
+  const double t_load = now_s();
   sgx_reads* reads = nullptr;
   rc = sgx_reads_pack(ctx, rs.bases.data(), rs.off.data(), rs.size(), &reads);
   if (rc != SGX_OK) {
@@ -657,9 +658,9 @@ int cmd_index(int argc, char** argv) {
   auto start_writer = [&](int pass) {
     sgx_index_out& out = outs[pass];
     const std::string sa = output + (pass == 0 ? ".sai" : ".rsai"), bw = output + (pass == 0 ? ".bwt" : ".rbwt");
-    info("%s: %llu strings, %llu suffixes, %llu runs; device %.1f ms (%llu kernel launches)", bw.c_str(),
-         (unsigned long long)out.n_strings, (unsigned long long)out.n_suffixes, (unsigned long long)out.n_runs, out.ms_total,
-         (unsigned long long)out.launches);
+    info("%s: %llu strings, %llu suffixes, %llu runs; device %.1f ms (read order %.1f, column passes %.1f, run-length coding + copy "
+         "out %.1f; %llu kernel launches)", bw.c_str(), (unsigned long long)out.n_strings, (unsigned long long)out.n_suffixes,
+         (unsigned long long)out.n_runs, out.ms_total, out.ms_sort, out.ms_bcr, out.ms_emit, (unsigned long long)out.launches);
     writers[pass] = std::thread([&outs, &wrote, pass, sa, bw]() {
       const sgx_index_out& o2 = outs[pass];
       bool a = false, b = false;
@@ -697,6 +698,7 @@ int cmd_index(int argc, char** argv) {
       start_writer(pass);
     }
   }
+  const double t_built = now_s();
   for (int pass = 0; pass < 2; ++pass) {
     if (!writers[pass].joinable()) continue;
     writers[pass].join();
@@ -719,8 +721,11 @@ int cmd_index(int argc, char** argv) {
     return -1;
   }
   sgx_reads_free(reads);
+  const double t_written = now_s();
   sgx_shutdown(ctx);
-  info("wall: %.3f sec", now_s() - t0);
+  const double t1 = now_s();
+  info("wall: %.3f sec (load + CUDA start %.3f, pack + build %.3f, rest of the writes %.3f, shutdown %.3f)", t1 - t0, t_load - t0,
+       t_built - t_load, t_written - t_built, t1 - t_written);
   return 0;
 }
 

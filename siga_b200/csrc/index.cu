@@ -42,7 +42,7 @@ static void bcr_passes(sgx_ctx* ctx, const sgx_reads* reads, const ReadAcc& acc,
   DevBuf<PosT> NP0(N), NP1(N);
   DevBuf<uint8_t> SYM0(N), SYM1(N);
   DevBuf<uint32_t> WIN0(N), WIN1(N);
-  DevBuf<uint2> blk(nt_max * 32);
+  DevBuf<uint16_t> RL0(N), RL1(N);  // tile-local rank of every item's row (see tile_checkpoints)
   DevBuf<uint64_t> tiletot(4 * nt_max), scan_ws(scan_ws_elems(4 * nt_max)), part_ws(part_ws_elems(N, 4)),
       tile_k0(S / kMergeTile + 4);
   uint32_t* ID = ID0.p;
@@ -53,13 +53,15 @@ static void bcr_passes(sgx_ctx* ctx, const sgx_reads* reads, const ReadAcc& acc,
   uint8_t* SYM2 = SYM1.p;
   uint32_t* WIN = WIN0.p;
   uint32_t* WIN2 = WIN1.p;
+  uint16_t* RL = RL0.p;
+  uint16_t* RL2 = RL1.p;
   uint8_t* B = B0;
   uint8_t* Bn = B1;
 
   uint64_t n_cur = N;
   SGX_LAUNCH(ctx, (bcr_init_kernel<PosT>), grid_for((N + 1) / 2, 256), 256, 0, acc, d_sord, N, B, ID, NP, SYM);
   uint64_t nt = (n_cur + kMergeTile - 1) / kMergeTile;
-  SGX_LAUNCH(ctx, tile_count_kernel, (unsigned)nt, 256, 0, (const uint8_t*)B, n_cur, nt, blk.p, tiletot.p);
+  SGX_LAUNCH(ctx, tile_count_kernel, (unsigned)nt, 256, 0, (const uint8_t*)B, n_cur, nt, (uint2*)nullptr, tiletot.p, RL);
   scan_exclusive(ctx, tiletot.p, 4 * nt, scan_ws.p, (uint64_t*)nullptr);
 
   uint64_t nact_prev = N;  // items currently held in ID/NP/SYM (inserted by the previous pass)
@@ -67,15 +69,16 @@ static void bcr_passes(sgx_ctx* ctx, const sgx_reads* reads, const ReadAcc& acc,
     const uint64_t nact = nact_by_pass[j];  // reads with length >= j
     if (nact == 0) break;
     SymDigit dg{SYM};
-    BcrMove<PosT> mv{acc, ID, WIN, j, uniform_len, ID2, NP2, SYM2, WIN2, B, blk.p, tiletot.p, nt, N, SYM, NP};
+    BcrMove<PosT> mv{acc, ID, WIN, j, uniform_len, ID2, NP2, SYM2, WIN2, tiletot.p, nt, N, SYM, NP, RL};
     partition_pass<4>(ctx, dg, mv, nact_prev, part_ws.p, (uint64_t*)nullptr);
     const uint64_t n_new = n_cur + nact;
     const uint64_t ntiles = (n_new + kMergeTile - 1) / kMergeTile;
     SGX_LAUNCH(ctx, (bcr_tile_bounds_kernel<PosT>), grid_for(nact + 1, 256), 256, 0, (const PosT*)NP2, nact, ntiles,
                tile_k0.p);
     k_merge.tick();
-    SGX_LAUNCH(ctx, (bcr_merge_kernel<PosT>), merge_grid(ctx, ntiles), kMergeThreads, 0, (const uint8_t*)B, n_cur,
-               (const PosT*)NP2, (const uint8_t*)SYM2, nact, (const uint64_t*)tile_k0.p, Bn, n_new, ntiles, blk.p, tiletot.p);
+    SGX_LAUNCH(ctx, (bcr_merge_kernel<PosT>), merge_grid<PosT>(ctx, ntiles), kMergeThreads, 0, (const uint8_t*)B, n_cur,
+               (const PosT*)NP2, (const uint8_t*)SYM2, nact, (const uint64_t*)tile_k0.p, Bn, n_new, ntiles, (uint2*)nullptr,
+               tiletot.p, RL2);
     k_merge.tick();
     out->merge_launches++;
     out->merge_bytes += (n_cur + n_new) / 2 + nact * (sizeof(PosT) + 1);
@@ -85,6 +88,7 @@ static void bcr_passes(sgx_ctx* ctx, const sgx_reads* reads, const ReadAcc& acc,
     std::swap(NP, NP2);
     std::swap(SYM, SYM2);
     std::swap(WIN, WIN2);
+    std::swap(RL, RL2);
     n_cur = n_new;
     nt = ntiles;
     nact_prev = nact;

@@ -174,26 +174,36 @@ __device__ __forceinline__ uint32_t nib_sum(uint32_t acc) {
 //                      flattened [4][nt] array turns it into (#symbols < c) + (#c before tile t)
 // so that rank_c(row) = scanned[c*nt + row/8192] + field_c(blk[row/256]) + (#c in the block before the row), and only
 // nt = rows/8192 values per symbol are scanned per column pass.
+// The single-device build does not even need blk: the kernel that writes a tile (the merge, or tile_count_kernel for the
+// first array) has all of its rows at hand and stores, for every item the tile holds, the item's TILE-LOCAL rank
+//   rloc[k] = number of rows of the tile before the item's row that hold the item's symbol
+// so that the next pass computes rank_c(row) = scanned[c*nt + row/8192] + rloc[k] without touching the BWT at all.
 // Called by all 256 threads of a CTA that holds one tile, thread i owning rows [32 i, 32 i + 32) as four words whose
 // nibbles past the end of the array are zero.
 __device__ __forceinline__ void tile_checkpoints(const uint32_t out[4], uint64_t tile, uint64_t ntiles, uint32_t* sh_w /* 64 */,
-                                                 uint2* __restrict__ blk, uint64_t* __restrict__ tiletot) {
+                                                 uint2* __restrict__ blk, uint64_t* __restrict__ tiletot, uint32_t& pre1,
+                                                 uint32_t& pre2) {
   // bit planes of the 32 nibbles packed into one word each (word i's plane shifted to bit i of every nibble): symbol
   // ranks are A=1 C=2 G=3 T=4, so A = b0 & ~b1, C = b1 & ~b0, G = b0 & b1, T = b2 -- four popcounts per thread
   const uint32_t M = 0x11111111u;
   const uint32_t p0 = (out[0] & M) | ((out[1] << 1) & (M << 1)) | ((out[2] << 2) & (M << 2)) | ((out[3] << 3) & (M << 3));
   const uint32_t p1 = ((out[0] >> 1) & M) | (out[1] & (M << 1)) | ((out[2] << 1) & (M << 2)) | ((out[3] << 2) & (M << 3));
   const uint32_t p2 = ((out[0] >> 2) & M) | ((out[1] >> 1) & (M << 1)) | (out[2] & (M << 2)) | ((out[3] << 1) & (M << 3));
-  uint32_t w1 = (uint32_t)__popc(p0 & ~p1) | ((uint32_t)__popc(p1 & ~p0) << 16);
-  uint32_t w2 = (uint32_t)__popc(p0 & p1) | ((uint32_t)__popc(p2) << 16);
+  const uint32_t w1 = (uint32_t)__popc(p0 & ~p1) | ((uint32_t)__popc(p1 & ~p0) << 16);
+  const uint32_t w2 = (uint32_t)__popc(p0 & p1) | ((uint32_t)__popc(p2) << 16);
+  // inclusive prefix inside the 8 consecutive threads of a 256-row block
+  uint32_t i1 = w1, i2 = w2;
 #pragma unroll
-  for (int oo = 4; oo > 0; oo >>= 1) {  // 256-row block = 8 consecutive threads
-    w1 += __shfl_xor_sync(0xffffffffu, w1, oo);
-    w2 += __shfl_xor_sync(0xffffffffu, w2, oo);
+  for (int o = 1; o < 8; o <<= 1) {
+    const uint32_t y1 = __shfl_up_sync(0xffffffffu, i1, o, 8), y2 = __shfl_up_sync(0xffffffffu, i2, o, 8);
+    if ((int)(threadIdx.x & 7) >= o) {
+      i1 += y1;
+      i2 += y2;
+    }
   }
-  if ((threadIdx.x & 7) == 0) {
-    sh_w[threadIdx.x >> 3] = w1;
-    sh_w[32 + (threadIdx.x >> 3)] = w2;
+  if ((threadIdx.x & 7) == 7) {
+    sh_w[threadIdx.x >> 3] = i1;
+    sh_w[32 + (threadIdx.x >> 3)] = i2;
   }
   __syncthreads();
   if (threadIdx.x < 32) {
@@ -208,7 +218,9 @@ __device__ __forceinline__ void tile_checkpoints(const uint32_t out[4], uint64_t
         x2 += y2;
       }
     }
-    blk[tile * 32 + lane] = make_uint2(x1 - v1, x2 - v2);
+    if (blk) blk[tile * 32 + lane] = make_uint2(x1 - v1, x2 - v2);
+    sh_w[lane] = x1 - v1;  // counts of the tile's rows before this block
+    sh_w[32 + lane] = x2 - v2;
     if (lane == 31) {
       tiletot[0 * ntiles + tile] = x1 & 0xffffu;
       tiletot[1 * ntiles + tile] = x1 >> 16;
@@ -216,11 +228,19 @@ __device__ __forceinline__ void tile_checkpoints(const uint32_t out[4], uint64_t
       tiletot[3 * ntiles + tile] = x2 >> 16;
     }
   }
+  __syncthreads();
+  // counts of the tile's rows before this thread's 32 rows
+  pre1 = sh_w[threadIdx.x >> 3] + i1 - w1;
+  pre2 = sh_w[32 + (threadIdx.x >> 3)] + i2 - w2;
 }
+
+// Number of nibbles equal to `sym` among the first p (< 32) of a thread's 32 rows.
+__device__ __forceinline__ uint32_t rows_eq_before(const uint32_t out[4], uint32_t sym, uint32_t p);
 
 // Checkpoints of an existing array (the first BWT of the column passes): one CTA per 8192-row tile.
 static __global__ void __launch_bounds__(256) tile_count_kernel(const uint8_t* __restrict__ B, uint64_t n, uint64_t ntiles,
-                                                               uint2* __restrict__ blk, uint64_t* __restrict__ tiletot) {
+                                                               uint2* __restrict__ blk, uint64_t* __restrict__ tiletot,
+                                                               uint16_t* __restrict__ rloc /* optional: per row */) {
   __shared__ uint32_t sh_w[64];
   const uint64_t row0 = (uint64_t)blockIdx.x * 8192 + (uint64_t)threadIdx.x * 32;
   uint32_t out[4] = {0, 0, 0, 0};
@@ -237,7 +257,20 @@ static __global__ void __launch_bounds__(256) tile_count_kernel(const uint8_t* _
       out[i] &= vw >= 8 ? 0xffffffffu : ((1u << (4 * vw)) - 1u);
     }
   }
-  tile_checkpoints(out, blockIdx.x, ntiles, sh_w, blk, tiletot);
+  uint32_t pre1, pre2;
+  tile_checkpoints(out, blockIdx.x, ntiles, sh_w, blk, tiletot, pre1, pre2);
+  if (rloc && row0 < n) {
+    const uint32_t valid = (uint32_t)min((uint64_t)32, n - row0);
+    for (uint32_t p = 0; p < valid; ++p) {
+      const uint32_t sym = (out[p >> 3] >> (4 * (p & 7))) & 15u;
+      uint32_t r = 0;
+      if (sym) {
+        const uint32_t c = sym - 1, f = c < 2 ? pre1 : pre2;
+        r = ((c & 1) ? (f >> 16) : (f & 0xffffu)) + rows_eq_before(out, sym, p);
+      }
+      rloc[row0 + p] = (uint16_t)r;
+    }
+  }
 }
 
 // number of nibbles equal to the pattern's nibble among the first `nn` (<= 8) nibbles of w
@@ -248,6 +281,17 @@ __device__ __forceinline__ uint32_t nib_eq_count(uint32_t w, uint32_t pat, uint3
   const uint32_t eq = ~x & 0x11111111u;
   const uint32_t m = nn >= 8 ? 0xffffffffu : ((1u << (4 * nn)) - 1u);
   return (uint32_t)__popc(eq & m);
+}
+
+__device__ __forceinline__ uint32_t rows_eq_before(const uint32_t out[4], uint32_t sym, uint32_t p) {
+  const uint32_t pat = sym * 0x11111111u, wq = p >> 3;
+  uint32_t cnt = 0;
+#pragma unroll
+  for (uint32_t i = 0; i < 4; ++i) {
+    if (i < wq) cnt += nib_eq_count(out[i], pat, 8);
+    else if (i == wq) cnt += nib_eq_count(out[i], pat, p & 7);
+  }
+  return cnt;
 }
 
 // Number of nibbles equal to symbol `sym` (1..4) among the first r rows of 256-row block b.  One thread reads the
@@ -311,9 +355,9 @@ struct SymDigit {
 // its new row holds (the base before the suffix; '$' when the read starts here).  That base comes from the read store
 // -- the one random gather of a pass -- so the 32-bit word it sits in travels with the item (WIN): consecutive passes
 // walk through the same word, and only every 16th pass (or every pass's first for a new item) touches the read store.
-// The row of the item's next suffix is computed right here (the arithmetic of bcr_rank_kernel, which the single-device
-// build no longer launches): the scatter already visits every active item once, so the rank lookup rides on it and the
-// array of new positions never goes through memory on its own.
+// The row of the item's next suffix is computed right here (what bcr_rank_kernel did in a launch of its own): the scatter
+// already visits every active item once.  The rank needs no access to the BWT: the kernel that wrote the item's row left
+// its tile-local rank in rloc (see tile_checkpoints), and the scanned tile totals supply the rest.
 template <class PosT>
 struct BcrMove {
   ReadAcc acc;
@@ -325,25 +369,20 @@ struct BcrMove {
   PosT* NP2;
   uint8_t* SYM2;
   uint32_t* WIN2;
-  // rank lookup: partial BWT of the previous pass, its two checkpoint levels, the items' current rows and symbols
-  const uint8_t* B;
-  const uint2* blk;
+  // rank lookup: scanned tile totals of the previous pass's BWT, the items' rows, symbols and tile-local ranks
   const uint64_t* scanned;
   uint64_t ntiles, base;
   const uint8_t* SYM;
   const PosT* NP;
+  const uint16_t* rloc;
   __device__ __forceinline__ void operator()(uint64_t k, uint64_t dest) const {
     const uint32_t id = ID[k];
-    const uint32_t sym = (uint32_t)SYM[k];  // 1..4 here: ended reads are dropped by the partition digit
-    const uint64_t P = (uint64_t)NP[k];
-    const uint64_t b = P / kBcrBlock;
-    const uint32_t c = sym - 1;
-    const uint2 bv = __ldg(blk + b);
-    const uint64_t sc = __ldg(scanned + (uint64_t)c * ntiles + (b >> 5));
-    const uint32_t inblk = block_rank(B, b, (uint32_t)(P - b * kBcrBlock), sym);
+    const uint32_t c = (uint32_t)SYM[k] - 1;  // SYM is 1..4 here: ended reads are dropped by the partition digit
+    const uint64_t tile = (uint64_t)NP[k] / kMergeTile;
+    const uint64_t sc = __ldg(scanned + (uint64_t)c * ntiles + tile);
     const uint32_t l = uniform_len ? uniform_len : acc.rv.len[id];
     ID2[dest] = id;
-    NP2[dest] = (PosT)(base + sc + blk_field(bv, c) + inblk);
+    NP2[dest] = (PosT)(base + sc + rloc[k]);
     if (l == j) {
       SYM2[dest] = 0;
       return;
@@ -411,16 +450,19 @@ __device__ __forceinline__ void merge_stage_old(const uint8_t* __restrict__ Bo, 
 }
 
 template <class PosT>
-__global__ void __launch_bounds__(kMergeThreads) bcr_merge_kernel(const uint8_t* __restrict__ Bo, uint64_t n_old,
+__global__ void __launch_bounds__(kMergeThreads, 8) bcr_merge_kernel(const uint8_t* __restrict__ Bo, uint64_t n_old,
                                                                   const PosT* __restrict__ NP, const uint8_t* __restrict__ SYM,
                                                                   uint64_t nact, const uint64_t* __restrict__ tile_k0,
                                                                   uint8_t* __restrict__ Bn, uint64_t n_new, uint64_t ntiles,
-                                                                  uint2* __restrict__ blk, uint64_t* __restrict__ tiletot) {
+                                                                  uint2* __restrict__ blk, uint64_t* __restrict__ tiletot,
+                                                                  uint16_t* __restrict__ rloc /* optional: per insert */) {
   __shared__ __align__(16) uint32_t oldw[2][kMergeOldWords];
   __shared__ uint32_t mask[kMergeTile / 32];
   __shared__ uint8_t symsh[kMergeTile];  // symbols of the tile's inserts, by ordinal
   __shared__ uint32_t ckpt[64];
   __shared__ uint32_t sh[8];
+  __shared__ uint32_t outsm[kMergeTile / 8];  // the finished tile (for the tile-local ranks)
+  __shared__ uint2 presm[kMergeThreads];      // symbol counts of the tile before each thread's rows
   const uint64_t G = gridDim.x;
   uint64_t tile = blockIdx.x;
   if (tile >= ntiles) return;
@@ -524,7 +566,35 @@ __global__ void __launch_bounds__(kMergeThreads) bcr_merge_kernel(const uint8_t*
       }
     }
     if (valid) *reinterpret_cast<uint4*>(Bn + row0 / 2) = make_uint4(out[0], out[1], out[2], out[3]);
-    tile_checkpoints(out, tile, ntiles, ckpt, blk, tiletot);
+    uint32_t cp1, cp2;
+    tile_checkpoints(out, tile, ntiles, ckpt, blk, tiletot, cp1, cp2);
+    if (rloc) {
+      // Tile-local rank of every insert of the tile: rows of the tile before it that hold the same symbol = the count
+      // before its thread's 32 rows (cp1 / cp2) + the matches among the rows of that thread below it.  The inserts are
+      // taken by ordinal, one per thread and round, from the finished tile in shared memory: a thread looping over its
+      // OWN inserts would leave most lanes idle (a tile holds 8192 / (pass + 1) inserts, under one per thread after
+      // pass 31, but the busiest lane of a warp still has two or three).
+#pragma unroll
+      for (int i = 0; i < 4; ++i) outsm[4 * threadIdx.x + i] = out[i];
+      presm[threadIdx.x] = make_uint2(cp1, cp2);
+      __syncthreads();
+      for (uint64_t o = threadIdx.x; o < k1 - k0; o += kMergeThreads) {
+        const uint32_t r = (uint32_t)((uint64_t)NP[k0 + o] - t0);
+        const uint32_t sy = symsh[o];
+        uint32_t v = 0;
+        if (sy) {
+          const uint32_t owner = r >> 5, p = r & 31u, c = sy - 1;
+          const uint2 pf = presm[owner];
+          const uint32_t f = c < 2 ? pf.x : pf.y;
+          const uint32_t* ow4 = outsm + 4 * owner;
+          const uint32_t pat = sy * 0x11111111u, wq = p >> 3;
+          uint32_t cnt = nib_eq_count(ow4[wq], pat, p & 7);
+          for (uint32_t i = 0; i < wq; ++i) cnt += nib_eq_count(ow4[i], pat, 8);
+          v = ((c & 1) ? (f >> 16) : (f & 0xffffu)) + cnt;
+        }
+        rloc[k0 + o] = (uint16_t)v;
+      }
+    }
     __syncthreads();  // mask / symsh / oldw[s] / ckpt are free for the next iteration
     if (!have_next) break;
     k0 = kn0;
@@ -598,9 +668,17 @@ static __global__ void len_hist_kernel(const uint32_t* __restrict__ len, uint64_
   if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&hist[l], (uint32_t)__popc(m));
 }
 
-// persistent grid of the merge kernel: enough CTAs to fill every SM (31 registers: 8 CTAs of 256 threads per SM), never more than tiles
+// persistent grid of the merge kernel: as many CTAs as are resident at once (asked of the runtime: the register count
+// decides it), never more than tiles
+template <class PosT>
 inline unsigned merge_grid(const sgx_ctx* ctx, uint64_t ntiles) {
-  const uint64_t cap = (uint64_t)ctx->sm_count * 8;
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bcr_merge_kernel<PosT>, kMergeThreads, 0) != cudaSuccess || n < 1) n = 4;
+    per_sm = n;
+  }
+  const uint64_t cap = (uint64_t)ctx->sm_count * (uint64_t)per_sm;
   return (unsigned)(ntiles < cap ? (ntiles ? ntiles : 1) : cap);
 }
 

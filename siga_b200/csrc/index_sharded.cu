@@ -113,7 +113,7 @@ static __global__ void __launch_bounds__(256) shard_rows_kernel(ReadAcc acc, uin
 // The key of the new suffix is rolled from the key of the suffix it extends (c * 5^7 + key / 5), which travels with
 // the item, so the kernel does not touch the read store.
 template <class PosT>
-__global__ void __launch_bounds__(256) shard_rank_kernel(const uint8_t* __restrict__ B, const uint2* __restrict__ blk,
+__global__ void __launch_bounds__(256) shard_rank_kernel(const uint16_t* __restrict__ rloc,
                                                          const uint64_t* __restrict__ scanned, uint64_t ntiles, ShardBounds bounds,
                                                          const PosT* __restrict__ NP, const uint8_t* __restrict__ SYM,
                                                          const uint32_t* __restrict__ KEY, uint64_t held,
@@ -128,14 +128,13 @@ __global__ void __launch_bounds__(256) shard_rank_kernel(const uint8_t* __restri
   }
   const uint64_t P = (uint64_t)NP[k];
   const uint32_t key = sym * kKeyTop + KEY[k] / 5u;
-  const uint64_t b = P / kBcrBlock;
   const uint32_t c = sym - 1;
-  const uint2 bv = __ldg(blk + b);
-  const uint64_t sc = __ldg(scanned + (uint64_t)c * ntiles + (b >> 5));
-  const uint32_t inblk = block_rank(B, b, (uint32_t)(P - b * kBcrBlock), sym);
+  // rank of c before the item's row in this shard's rows: scanned tile totals + the tile-local rank the kernel that
+  // wrote the row left behind (tile_checkpoints, index_kernels.cuh) -- no access to the BWT
+  const uint64_t sc = __ldg(scanned + (uint64_t)c * ntiles + P / kMergeTile);
   tmpDest[k] = (uint8_t)(bounds.owner(key) * 4 + (int)c);  // send bucket: destination-major, then c
   tmpKey[k] = key;
-  tmpPos[k] = (PosT)(sc + blk_field(bv, c) + inblk);
+  tmpPos[k] = (PosT)(sc + rloc[k]);
 }
 
 // One insert on the wire: the sender-local rank part, the read, the bucket key of the new suffix.
@@ -223,7 +222,7 @@ struct Shard {
   DevBuf<uint32_t> ID0, ID1, KEY0, KEY1, tmpKey;
   DevBuf<PosT> NP0, NP1, tmpPos;
   DevBuf<WireItem<PosT> > send, recv;
-  DevBuf<uint2> blk;
+  DevBuf<uint16_t> RL;  // tile-local rank of every held item's row
   DevBuf<uint64_t> tiletot, scan_ws, part_ws, tile_k0, meta, kept, sym_total;
   uint8_t* B = nullptr;
   uint8_t* Bn = nullptr;
@@ -258,7 +257,7 @@ struct Shard {
     NP1.alloc(N);
     tmpPos.alloc(N);
     const uint64_t nt_max = rows_final / kMergeTile + 2;
-    blk.alloc(nt_max * 32);
+    RL.alloc(N);
     tiletot.alloc(4 * nt_max);
     scan_ws.alloc(scan_ws_elems(4 * nt_max));
     part_ws.alloc(part_ws_elems(N, kSendBuckets));
@@ -305,7 +304,7 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
       s.held = N;
     }
     s.nt = std::max<uint64_t>(1, (s.n_cur + kMergeTile - 1) / kMergeTile);
-    SGX_LAUNCH(ctx, tile_count_kernel, (unsigned)s.nt, 256, 0, (const uint8_t*)s.B, s.n_cur, s.nt, s.blk.p, s.tiletot.p);
+    SGX_LAUNCH(ctx, tile_count_kernel, (unsigned)s.nt, 256, 0, (const uint8_t*)s.B, s.n_cur, s.nt, (uint2*)nullptr, s.tiletot.p, s.RL.p);
     scan_exclusive(ctx, s.tiletot.p, 4 * s.nt, s.scan_ws.p, s.sym_total.p);
   }
 
@@ -327,7 +326,7 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
       Shard<PosT>& s = sh[li];
       uint32_t ntiles = 1;
       if (s.held) {
-        SGX_LAUNCH(ctx, (shard_rank_kernel<PosT>), grid_for(s.held, 256), 256, 0, (const uint8_t*)s.B, (const uint2*)s.blk.p,
+        SGX_LAUNCH(ctx, (shard_rank_kernel<PosT>), grid_for(s.held, 256), 256, 0, (const uint16_t*)s.RL.p,
                    (const uint64_t*)s.tiletot.p, s.nt, bounds, (const PosT*)s.NP, (const uint8_t*)s.SYM.p,
                    (const uint32_t*)s.KEY, s.held, s.tmpDest.p, s.tmpPos.p, s.tmpKey.p);
         DestDigit dg{s.tmpDest.p};
@@ -380,9 +379,9 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
         SGX_LAUNCH(ctx, (bcr_tile_bounds_kernel<PosT>), grid_for(held_new + 1, 256), 256, 0, (const PosT*)s.NP2, held_new,
                    ntiles, s.tile_k0.p);
         k_merge.tick();
-        SGX_LAUNCH(ctx, (bcr_merge_kernel<PosT>), merge_grid(ctx, ntiles), kMergeThreads, 0, (const uint8_t*)s.B, s.n_cur,
+        SGX_LAUNCH(ctx, (bcr_merge_kernel<PosT>), merge_grid<PosT>(ctx, ntiles), kMergeThreads, 0, (const uint8_t*)s.B, s.n_cur,
                    (const PosT*)s.NP2, (const uint8_t*)s.SYM.p, held_new, (const uint64_t*)s.tile_k0.p, s.Bn, rows_new, ntiles,
-                   s.blk.p, s.tiletot.p);
+                   (uint2*)nullptr, s.tiletot.p, s.RL.p);
         k_merge.tick();
         out->merge_launches++;
         out->merge_bytes += (s.n_cur + rows_new) / 2 + held_new * (sizeof(PosT) + 1);

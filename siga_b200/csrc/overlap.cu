@@ -241,7 +241,7 @@ struct OvPlan {
   // lean search: resident CTAs per SM selectable for experiments (SGX_LEAN_MINB = 4 / 5 / 6)
   template <class IdxT>
   void launch_lean(uint64_t rfirst, uint64_t n, const OvBatch& bt, const uint32_t* list) {
-    const int minb = (int)env_u64("SGX_LEAN_MINB", 4);
+    const int minb = (int)env_u64("SGX_LEAN_MINB", 5);
     const unsigned grid = (unsigned)ctx->sm_count * (unsigned)env_u64("SGX_LEAN_WAVES", 1) * (unsigned)(minb == 9 ? 4 : minb);
     // uniform: the queries are the indexed reads and all of them have one length (see the kernel's header)
     const bool uni = fast && reads == fwd->indexed && reads->min_len == reads->max_len;
@@ -266,7 +266,11 @@ struct OvPlan {
       }
       if (uni && !env_u64("SGX_LEAN_LOCKSTEP", 0)) {  // reads of one length: persistent quads
         const uint32_t ul = reads->max_len, uw = (reads->max_len + 15) / 16;
-        if (minb == 6) SGX_LAUNCH(ctx, (ov_search_pq_kernel<IdxT, 6>), grid, kOvThreads, 0, fmp, rv, ul, uw, rfirst, n, min_ov, rc, bt, list, d_look.p, only);
+        if (env_u64("SGX_LEAN_PQ2", 1)) {  // cold state in shared memory (default; 0 = the register-heavy variant)
+          if (minb == 6) SGX_LAUNCH(ctx, (ov_search_pq2_kernel<IdxT, 6>), grid, kOvThreads, 0, fmp, rv, ul, uw, rfirst, n, min_ov, rc, bt, list, d_look.p, only);
+          else if (minb == 5) SGX_LAUNCH(ctx, (ov_search_pq2_kernel<IdxT, 5>), grid, kOvThreads, 0, fmp, rv, ul, uw, rfirst, n, min_ov, rc, bt, list, d_look.p, only);
+          else SGX_LAUNCH(ctx, (ov_search_pq2_kernel<IdxT, 4>), grid, kOvThreads, 0, fmp, rv, ul, uw, rfirst, n, min_ov, rc, bt, list, d_look.p, only);
+        } else if (minb == 6) SGX_LAUNCH(ctx, (ov_search_pq_kernel<IdxT, 6>), grid, kOvThreads, 0, fmp, rv, ul, uw, rfirst, n, min_ov, rc, bt, list, d_look.p, only);
         else if (minb == 5) SGX_LAUNCH(ctx, (ov_search_pq_kernel<IdxT, 5>), grid, kOvThreads, 0, fmp, rv, ul, uw, rfirst, n, min_ov, rc, bt, list, d_look.p, only);
         else SGX_LAUNCH(ctx, (ov_search_pq_kernel<IdxT, 4>), grid, kOvThreads, 0, fmp, rv, ul, uw, rfirst, n, min_ov, rc, bt, list, d_look.p, only);
       } else if (minb == 6) {

@@ -733,6 +733,250 @@ ov_search_pq_kernel(FmPair fm, ReadsView reads, uint32_t ulen, uint32_t uwords, 
   }
 }
 
+
+// ---- persistent quads, lean registers ---------------------------------------------------------------------------------
+//
+// ov_search_pq_kernel is bound by the latency of its dependent rank-block fetches: one fetch per chain in flight, and the
+// number of chains in flight is the number of resident warps, which its 64 registers per thread cap at 32 per SM.  Most of
+// those registers hold state that changes once per (read, mode) pair, replicated over the four lanes of the quad.  Here
+// that state (result slot, read id, candidate count, counters, the hand-out position) lives in shared memory, one record
+// per quad, and what a step can derive is derived (symbol position from the step count, symbol from the cached word):
+// the loop keeps the interval, the step count, the cached read word, the index base and C[] of the lane's symbol.
+// Same outputs as ov_search_pq_kernel.
+struct PqCold {
+  unsigned long long wk;      // next pair of this quad
+  unsigned long long slot;    // wi * 4 + mode of the pair in flight
+  unsigned long long nlook;   // executed rank lookups (two per step)
+  unsigned long long nlines;  // rank-block lines those lookups touched
+  uint32_t rd;                // read of the pair in flight
+  uint32_t n;                 // candidates emitted so far
+  uint32_t extra;             // steps whose interval ends lay in different blocks
+  uint32_t pad;
+};
+
+template <class IdxT, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+ov_search_pq2_kernel(FmPair fm, ReadsView reads, uint32_t ulen, uint32_t uwords, uint64_t first, uint64_t count, uint32_t min_ov,
+                     int rc, OvBatch bt, const uint32_t* __restrict__ list, unsigned long long* __restrict__ lookups, int only_pi) {
+  __shared__ PqCold cold[256 / kQuad];
+  const unsigned kFull = 0xffffffffu;
+  const int q = threadIdx.x & (kQuad - 1);
+  const int qbase = threadIdx.x & 31 & ~(kQuad - 1);
+  PqCold& cs = cold[threadIdx.x / kQuad];
+  const uint64_t nwork = count * (rc ? 4 : 2);
+  const uint64_t wk_end = only_pi == 0 ? nwork / 2 : nwork;
+  const IdxT kNone = (IdxT)-1;
+  const bool wide = sizeof(IdxT) == 8;
+  const uint32_t l = ulen;
+  if (q == 0) {
+    cs.wk = (only_pi > 0 ? nwork / 2 : 0) + ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / kQuad;
+    cs.nlook = 0;
+    cs.nlines = 0;
+  }
+  __syncwarp();
+
+  // flags: bit 0 live, 1 active, 2 selfonly, 3 backwards (modes 1, 2), 4 complement (modes 1, 3), 5 index (modes 2, 3)
+  uint32_t fl = 0, i = 0, word = 0;
+  IdxT lo0 = 0, hi0 = 0, mypc = 0;
+  const FmBlockLane* __restrict__ Pb = fm.blocks[0];
+
+  for (;;) {
+    if (__any_sync(kFull, !(fl & 1u))) {
+      const bool need = !(fl & 1u);
+      // ---- finish the pair that has just ended
+      const bool tail = need && (fl & 2u) && !(fl & 4u) && hi0 != kNone && hi0 >= lo0;  // full-length match, not just the read itself
+      if (__any_sync(kFull, tail)) {
+        const IdxT plo = tail ? lo0 : (IdxT)0;
+        const uint64_t b1 = (uint64_t)plo >> kBlockShift;
+        const int r1 = (int)(plo & (kBlockSyms - 1));
+        const uint4* pa = reinterpret_cast<const uint4*>(Pb + b1 * kGroup + q);
+        const uint4 a0 = __ldg(pa), a1 = __ldg(pa + 4);
+        uint32_t ma0, ma1;
+        asm("shl.b32 %0, %1, %2;" : "=r"(ma0) : "r"(0xffffffffu), "r"((uint32_t)max(r1 - 32 * q, 0)));
+        asm("shl.b32 %0, %1, %2;" : "=r"(ma1) : "r"(0xffffffffu), "r"((uint32_t)max(r1 - 32 * (q + 4), 0)));
+        uint32_t dl = (uint32_t)__popc(a0.z & ~ma0) + (uint32_t)__popc(a1.z & ~ma1);
+        IdxT hs = wide ? (IdxT)((uint64_t)a1.w << 32 | a0.w) : (IdxT)a0.w;
+#pragma unroll
+        for (int m = 1; m < kQuad; m <<= 1) {
+          dl += __shfl_xor_sync(kFull, dl, m);
+          hs += __shfl_xor_sync(kFull, hs, m);
+        }
+        if (tail && q == 0) {
+          const IdxT Ld = (IdxT)(b1 << kBlockShift) - hs + dl;
+          LeanCand lc;
+          lc.lo = (uint32_t)Ld;
+          lc.hi = (uint32_t)(Ld + (hi0 - lo0));
+          lc.len_af = l | (ov_mode_af((int)(cs.slot & 3)) << 16);
+          bt.lean_contain[cs.slot] = lc;
+          cs.nlook += 1;
+          cs.nlines += 1;
+        }
+      }
+      if (need && (fl & 2u) && q == 0) {
+        const uint64_t slot = cs.slot;
+        if (fl & 4u) {
+          LeanCand lc;
+          lc.lo = lc.hi = fm.inv[(fl >> 5) & 1u][cs.rd];
+          lc.len_af = l | (ov_mode_af((int)(slot & 3)) << 16);
+          bt.lean_contain[slot] = lc;
+        }
+        bt.ncand[slot] = cs.n < bt.find_cap ? cs.n : bt.find_cap;
+        bt.ncontain[slot] = ((fl & 4u) || tail) ? 1u : 0u;
+        const uint32_t steps = (l - 1) - i;
+        cs.nlook += 2ull * steps;
+        cs.nlines += (unsigned long long)steps + cs.extra;
+      }
+      if (need) fl &= ~2u;
+      __syncwarp();
+      // ---- take the next pair
+      const uint64_t wk = cs.wk;
+      __syncwarp();
+      if (need && wk < wk_end) {
+        const uint32_t pi = wk >= nwork / 2 ? 1u : 0u;  // index-major order (see ov_search_lean_kernel)
+        const uint64_t within = wk - (pi ? nwork / 2 : 0);
+        const uint64_t wi = rc ? within >> 1 : within;
+        const int mode = 2 * (int)pi + (rc ? (int)(within & 1) : 0);
+        const uint64_t rd = first + (list ? (uint64_t)list[wi] : wi);
+        if (q == 0) {
+          cs.wk = wk + ((uint64_t)gridDim.x * blockDim.x) / kQuad;
+          cs.slot = wi * 4 + mode;
+          cs.rd = (uint32_t)rd;
+          cs.n = 0;
+          cs.extra = 0;
+        }
+        Pb = fm.blocks[pi];
+        mypc = (IdxT)fm.pred[pi][q + 1];
+        const uint32_t* rw = reads.words + rd * uwords;
+        fl = 2u | ((mode == 1 || mode == 2) ? 8u : 0u) | ((mode & 1) ? 16u : 0u) | (pi << 5);
+        const int c = ov_sym(rw, l, mode, l - 1);
+        lo0 = (IdxT)fm.pred[pi][c];
+        hi0 = (IdxT)(fm.pred[pi][c + 1] - 1);
+        i = l - 1;
+        if (i > 0 && hi0 != kNone && hi0 >= lo0) {
+          fl |= 1u;
+          const uint32_t j = (fl & 8u) ? l - i : i - 1;  // base index of string position i - 1
+          word = rw[j >> 4] ^ ((fl & 16u) ? 0xffffffffu : 0u);
+        }
+      }
+      __syncwarp();
+      if (!__any_sync(kFull, fl & 2u)) break;
+      if (!__any_sync(kFull, fl & 1u)) continue;  // pairs that ended before their first step are finished next round
+    }
+    // ---- one backward step of every live quad
+    const bool live = (fl & 1u) != 0;
+    const uint32_t j = (fl & 8u) ? l - i : i - 1;  // base index of string position i - 1, the symbol of this step
+    const int c = (int)((word >> (2 * (j & 15))) & 3u) + 1;
+    // the symbol of the next step sits in the neighbouring word when this one is at the word's edge
+    if (live && i > 1 && (j & 15u) == ((fl & 8u) ? 15u : 0u)) {
+      const uint32_t jn = (fl & 8u) ? j + 1 : j - 1;
+      word = reads.words[(uint64_t)cs.rd * uwords + (jn >> 4)] ^ ((fl & 16u) ? 0xffffffffu : 0u);
+    }
+    const IdxT plo = live ? lo0 : (IdxT)0, phi = live ? (IdxT)(hi0 + 1) : (IdxT)0;
+    const uint64_t b1 = (uint64_t)plo >> kBlockShift, b2 = (uint64_t)phi >> kBlockShift;
+    const int r1 = (int)(plo & (kBlockSyms - 1)), r2 = (int)(phi & (kBlockSyms - 1));
+    const uint4* pa = reinterpret_cast<const uint4*>(Pb + b1 * kGroup + q);
+    const uint4 a0 = __ldg(pa), a1 = __ldg(pa + 4);
+    uint4 c0 = a0, c1 = a1;
+    if (b2 != b1) {
+      const uint4* pb = reinterpret_cast<const uint4*>(Pb + b2 * kGroup + q);
+      c0 = __ldg(pb);
+      c1 = __ldg(pb + 4);
+    }
+    uint32_t ma0, ma1, mc0, mc1;
+    asm("shl.b32 %0, %1, %2;" : "=r"(ma0) : "r"(0xffffffffu), "r"((uint32_t)max(r1 - 32 * q, 0)));
+    asm("shl.b32 %0, %1, %2;" : "=r"(ma1) : "r"(0xffffffffu), "r"((uint32_t)max(r1 - 32 * (q + 4), 0)));
+    asm("shl.b32 %0, %1, %2;" : "=r"(mc0) : "r"(0xffffffffu), "r"((uint32_t)max(r2 - 32 * q, 0)));
+    asm("shl.b32 %0, %1, %2;" : "=r"(mc1) : "r"(0xffffffffu), "r"((uint32_t)max(r2 - 32 * (q + 4), 0)));
+    const uint32_t x0 = ((c - 1) & 1) ? 0u : 0xffffffffu, x1 = ((c - 1) & 2) ? 0u : 0xffffffffu;
+    uint32_t packed = (uint32_t)__popc(~(a0.z | ma0) & (a0.x ^ x0) & (a0.y ^ x1)) +
+                      (uint32_t)__popc(~(a1.z | ma1) & (a1.x ^ x0) & (a1.y ^ x1)) +
+                      (((uint32_t)__popc(~(c0.z | mc0) & (c0.x ^ x0) & (c0.y ^ x1)) +
+                        (uint32_t)__popc(~(c1.z | mc1) & (c1.x ^ x0) & (c1.y ^ x1))) << 16);
+    packed += __shfl_xor_sync(kFull, packed, 1);
+    packed += __shfl_xor_sync(kFull, packed, 2);
+    const int src = qbase + c - 1;
+    IdxT nlo, nhi;
+    if (wide) {
+      const uint64_t ha = ((uint64_t)a1.w << 32 | a0.w) + mypc, hc = ((uint64_t)c1.w << 32 | c0.w) + mypc;
+      nlo = (IdxT)__shfl_sync(kFull, (unsigned long long)ha, src);
+      nhi = (IdxT)__shfl_sync(kFull, (unsigned long long)hc, src);
+    } else {
+      nlo = (IdxT)__shfl_sync(kFull, a0.w + (uint32_t)mypc, src);
+      nhi = (IdxT)__shfl_sync(kFull, c0.w + (uint32_t)mypc, src);
+    }
+    nlo += (IdxT)(packed & 0xffffu);
+    nhi += (IdxT)(packed >> 16);
+    nhi -= 1;
+    const uint32_t olen = l - i;
+    const bool elig = live && olen >= min_ov;
+    if (__any_sync(kFull, elig)) {
+      const uint32_t nb = (uint32_t)min(b2 - b1, (uint64_t)64);
+      uint32_t pk = ((uint32_t)__popc(a0.z & ~ma0) + (uint32_t)__popc(a1.z & ~ma1)) |
+                    (((uint32_t)__popc(c0.z & ~mc0) + (uint32_t)__popc(c1.z & ~mc1)) << 9) | ((c0.w - a0.w) << 18);
+      pk += __shfl_xor_sync(kFull, pk, 1);
+      pk += __shfl_xor_sync(kFull, pk, 2);
+      const uint32_t dl = pk & 511u;
+      IdxT dd = (IdxT)(((pk >> 9) & 511u) - dl + 256u * nb - (pk >> 18));
+      IdxT Ld = 0;
+      const bool far = elig && nb > 63;
+      if (__any_sync(kFull, far)) {
+        const QuadRank<IdxT> k = quad_rank<IdxT>(Pb, far ? plo : (IdxT)0, far ? phi : (IdxT)0, q);
+        if (far) {
+          dd = k.Ud - k.Ld;
+          Ld = k.Ld;
+        }
+      }
+      const bool emit = elig && dd >= 1;
+      if (__any_sync(kFull, emit)) {
+        IdxT hs = wide ? (IdxT)((uint64_t)a1.w << 32 | a0.w) : (IdxT)a0.w;
+        hs += __shfl_xor_sync(kFull, hs, 1);
+        hs += __shfl_xor_sync(kFull, hs, 2);
+        if (!far) Ld = (IdxT)(b1 << kBlockShift) - hs + dl;
+        if (emit && q == 0) {
+          const uint32_t n = cs.n;
+          const uint64_t slot = cs.slot;
+          if (n < bt.find_cap) {
+            LeanCand lc;
+            lc.lo = (uint32_t)Ld;
+            lc.hi = (uint32_t)(Ld + dd - 1);
+            lc.len_af = olen | (ov_mode_af((int)(slot & 3)) << 16);
+            bt.lean[slot * bt.find_cap + n] = lc;
+          }
+          cs.n = n + 1;
+        }
+      }
+    }
+    if (live) {
+      if (b2 != b1 && q == 0) cs.extra += 1;
+      lo0 = nlo;
+      hi0 = nhi;
+      --i;
+      if (!(i > 0 && hi0 != kNone && hi0 >= lo0)) {
+        fl &= ~1u;
+      } else if (!(fl & 16u) && hi0 == lo0) {  // modes 0 and 2 (no complement): only the read itself is left
+        fl = (fl & ~1u) | 4u;
+      }
+    }
+  }
+  __syncwarp();
+  if (!rc && only_pi <= 0) {
+    const uint64_t quad = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / kQuad;
+    const uint64_t stride = ((uint64_t)gridDim.x * blockDim.x) / kQuad;
+    for (uint64_t r = quad; r < count; r += stride) {
+      if (q == 0) {
+        bt.ncand[r * 4 + 1] = 0;
+        bt.ncand[r * 4 + 3] = 0;
+        bt.ncontain[r * 4 + 1] = 0;
+        bt.ncontain[r * 4 + 3] = 0;
+      }
+    }
+  }
+  if (q == 0) {
+    if (cs.nlook) atomicAdd(lookups, cs.nlook);
+    if (cs.nlines) atomicAdd(lookups + 2, cs.nlines);
+  }
+}
+
 }  // namespace sgx
 
 #endif  // SGX_OVERLAP_SEARCH_CUH_
