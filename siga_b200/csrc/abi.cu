@@ -96,6 +96,25 @@ void pinned_put(void* p) {
   it->second.first->pinned_free.push_back(std::make_pair(p, it->second.second));
 }
 
+sgx_ctx* ctx_aux(sgx_ctx* ctx) {
+  if (!ctx->aux) {
+    sgx_ctx* a = new sgx_ctx();
+    a->device = ctx->device;
+    a->sm_count = ctx->sm_count;
+    a->l2_bytes = ctx->l2_bytes;
+    a->launches = 0;
+    a->flush_buf = nullptr;
+    a->flush_bytes = 0;
+    cudaError_t e = cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      delete a;
+      SGX_CUDA(e);
+    }
+    ctx->aux = a;
+  }
+  return ctx->aux;
+}
+
 __global__ void probe_kernel(int* out) {
   if (out) *out = 1;
 }
@@ -259,22 +278,7 @@ int sgx_index_build_pair(sgx_ctx* ctx, const sgx_reads* reads, int order, sgx_in
   if (!ctx || !reads || !out_fwd || !out_rev) return SGX_EINVAL;
   SGX_ENTRY_BEGIN(ctx)
   SGX_REQUIRE(order == SGX_ORDER_SAIS || order == SGX_ORDER_SAIS2, SGX_EINVAL, "sgx_index_build_pair: unknown order");
-  if (!ctx->aux) {
-    sgx_ctx* a = new sgx_ctx();
-    a->device = ctx->device;
-    a->sm_count = ctx->sm_count;
-    a->l2_bytes = ctx->l2_bytes;
-    a->launches = 0;
-    a->flush_buf = nullptr;
-    a->flush_bytes = 0;
-    cudaError_t e = cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking);
-    if (e != cudaSuccess) {
-      delete a;
-      SGX_CUDA(e);
-    }
-    ctx->aux = a;
-  }
-  sgx_ctx* aux = ctx->aux;
+  sgx_ctx* aux = ctx_aux(ctx);
   // the second stream starts after everything queued on the first (the read store may still be in flight there)
   cudaEvent_t ready;
   SGX_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));

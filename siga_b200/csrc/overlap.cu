@@ -242,7 +242,8 @@ struct OvPlan {
   template <class IdxT>
   void launch_lean(uint64_t rfirst, uint64_t n, const OvBatch& bt, const uint32_t* list) {
     const int minb = (int)env_u64("SGX_LEAN_MINB", 5);
-    const unsigned grid = (unsigned)ctx->sm_count * (unsigned)env_u64("SGX_LEAN_WAVES", 1) * (unsigned)(minb == 9 ? 4 : minb);
+    const unsigned grid = (unsigned)ctx->sm_count * (unsigned)env_u64("SGX_LEAN_WAVES", 1) *
+                          (unsigned)env_u64("SGX_LEAN_CTAS", minb == 9 ? 4 : minb);  // CTAs per SM; fewer than resident leaves room for the reduce kernel
     // uniform: the queries are the indexed reads and all of them have one length (see the kernel's header)
     const bool uni = fast && reads == fwd->indexed && reads->min_len == reads->max_len;
     if (minb == 9) {  // experiments: the round-1 kernel (full rank vectors, other-side interval carried along)
@@ -567,6 +568,7 @@ void overlap_edges_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const
   DevBuf<sgx_edge> d_edges;
   uint64_t edge_cap = env_u64("SGX_EDGE_CAP", std::max<uint64_t>(count * 8, 1u << 16));  // hook: overflow round
   uint64_t n_edges = 0, n_slow = 0, search_launches = 0;
+  double post2_ms = 0;  // reduce kernels that ran on the second stream
 
   for (int round = 0;; ++round) {
     SGX_REQUIRE(round < 8, SGX_EOVERFLOW, "sgx_overlap_edges: edge buffer overflow persists");
@@ -602,34 +604,81 @@ void overlap_edges_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const
       const bool old_reduce = env_u64("SGX_REDUCE_OLD", 0) != 0;
       const size_t smem_old = pl.reduce_smem(true);
       SGX_CUDA(cudaFuncSetAttribute(ov_reduce_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_old));
-      for (uint64_t b0 = 0; b0 < count; b0 += batch) {
+      // SGX_OVERLAP_STREAMS=2 (experiment, off by default): the search of batch b + 1 runs while batch b is reduced, on
+      // two streams with two sets of candidate buffers (events order search(b) -> reduce(b) -> search(b + 2)).  Measured
+      // at cfg2: the kernels do overlap, each stretches, the pass takes the same 63.5 ms -- both live off the same
+      // random-access rate of the memory system (profiles/r2_summary.md).
+      const bool two = env_u64("SGX_OVERLAP_STREAMS", 1) >= 2 && count > batch && !old_reduce;
+      sgx_ctx* aux = two ? ctx_aux(ctx) : nullptr;
+      DevBuf<LeanCand> d_lean2, d_lcontain2;
+      DevBuf<uint32_t> d_ncand2, d_ncontain2;
+      cudaEvent_t ev_s[2] = {nullptr, nullptr}, ev_r[2] = {nullptr, nullptr};
+      if (two) {
+        d_lean2.alloc(batch * 4 * pl.find_cap);
+        d_lcontain2.alloc(batch * 4);
+        d_ncand2.alloc(batch * 4);
+        d_ncontain2.alloc(batch * 4);
+        for (int k = 0; k < 2; ++k) {
+          SGX_CUDA(cudaEventCreateWithFlags(&ev_s[k], cudaEventDisableTiming));
+          SGX_CUDA(cudaEventCreateWithFlags(&ev_r[k], cudaEventDisableTiming));
+        }
+      }
+      struct EvGuard {
+        cudaEvent_t* a;
+        cudaEvent_t* b;
+        ~EvGuard() {
+          for (int k = 0; k < 2; ++k) {
+            if (a[k]) cudaEventDestroy(a[k]);
+            if (b[k]) cudaEventDestroy(b[k]);
+          }
+        }
+      } ev_guard{ev_s, ev_r};
+      KernelClock k_post2(two ? aux->stream : ctx->stream);
+      sgx_ctx* rctx = two ? aux : ctx;  // where the reduce kernels are launched
+      const uint64_t aux_launches0 = two ? aux->launches : 0;
+      uint64_t bi = 0;
+      for (uint64_t b0 = 0; b0 < count; b0 += batch, ++bi) {
         const uint64_t bn = std::min<uint64_t>(batch, count - b0);
+        const int set = two ? (int)(bi & 1) : 0;
         OvBatch bt;
         memset(&bt, 0, sizeof(bt));
-        bt.lean = d_lean.p;
-        bt.lean_contain = d_lcontain.p;
-        bt.ncand = d_ncand.p;
-        bt.ncontain = d_ncontain.p;
+        bt.lean = set ? d_lean2.p : d_lean.p;
+        bt.lean_contain = set ? d_lcontain2.p : d_lcontain.p;
+        bt.ncand = set ? d_ncand2.p : d_ncand.p;
+        bt.ncontain = set ? d_ncontain2.p : d_ncontain.p;
         bt.substring = d_sub.p + b0;
         bt.find_cap = pl.find_cap;
         bt.out_cap = pl.out_cap;
+        if (two && bi >= 2) SGX_CUDA(cudaStreamWaitEvent(ctx->stream, ev_r[set], 0));  // the reduce of batch b - 2 is done with this set
         k_search.tick();
         pl.search(true, first + b0, bn, bt, nullptr);
         k_search.tick();
         ++search_launches;
         sink.qbase = first + b0;
-        k_post.tick();
+        if (two) {
+          SGX_CUDA(cudaEventRecord(ev_s[set], ctx->stream));
+          SGX_CUDA(cudaStreamWaitEvent(aux->stream, ev_s[set], 0));
+        }
+        KernelClock& kp = two ? k_post2 : k_post;
+        kp.tick();
         if (old_reduce) {  // experiments: the round-1 kernel (one side after the other, staged edges)
           SGX_LAUNCH(ctx, (ov_reduce_kernel<true, true>), pl.grid_reduce, kRdWarps * 32, smem_old, pl.rv, pl.treads, pl.sf, pl.sr, bn,
                      irreducible, bt, pl.rows_cap, pl.extw, b0, d_slow.p, d_flags.p, sink);
         } else if (uniform) {
-          SGX_LAUNCH(ctx, (ov_reduce_lean_kernel<true>), grid_rl, kRlWarps * 32, smem, pl.rv, pl.treads, idx->max_len,
+          SGX_LAUNCH(rctx, (ov_reduce_lean_kernel<true>), grid_rl, kRlWarps * 32, smem, pl.rv, pl.treads, idx->max_len,
                      (idx->max_len + 15) / 16, pl.sf, pl.sr, bn, irreducible, bt, rows, pl.extw, b0, d_slow.p, d_flags.p, sink);
         } else {
-          SGX_LAUNCH(ctx, (ov_reduce_lean_kernel<false>), grid_rl, kRlWarps * 32, smem, pl.rv, pl.treads, 0u, 0u, pl.sf,
+          SGX_LAUNCH(rctx, (ov_reduce_lean_kernel<false>), grid_rl, kRlWarps * 32, smem, pl.rv, pl.treads, 0u, 0u, pl.sf,
                      pl.sr, bn, irreducible, bt, rows, pl.extw, b0, d_slow.p, d_flags.p, sink);
         }
-        k_post.tick();
+        kp.tick();
+        if (two) SGX_CUDA(cudaEventRecord(ev_r[set], aux->stream));
+      }
+      if (two) {
+        for (int k = 0; k < 2 && (uint64_t)k < bi; ++k) SGX_CUDA(cudaStreamWaitEvent(ctx->stream, ev_r[k], 0));
+        SGX_CUDA(cudaStreamSynchronize(ctx->stream));  // k_post2's events are read below; the buffers go back to the cache
+        post2_ms += k_post2.total_ms();
+        ctx->launches += aux->launches - aux_launches0;
       }
       uint32_t fl[2] = {0, 0};
       SGX_CUDA(cudaMemcpyAsync(fl, d_flags.p, sizeof(fl), cudaMemcpyDeviceToHost, ctx->stream));
@@ -726,7 +775,7 @@ void overlap_edges_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const
   out->lines_search = look[2];
   out->ms_total = t_all.ms();
   out->ms_search = k_search.total_ms();
-  out->ms_extract = k_post.total_ms();
+  out->ms_extract = k_post.total_ms() + post2_ms;
   out->lookups_search = look[0];
   out->lookups_extract = look[1];
   out->launches = ctx->launches - launches0;

@@ -244,6 +244,8 @@ inline unsigned grid_for(uint64_t n, unsigned per_block) {
 void sgx_set_error(sgx_ctx* ctx, const char* msg);
 
 namespace sgx {
+// The context's second stream (ctx->aux), created on first use.
+sgx_ctx* ctx_aux(sgx_ctx* ctx);
 // Pinned host memory pool of a context (outputs of the ABI live here).
 void* pinned_get(sgx_ctx* ctx, size_t bytes);
 void pinned_put(void* p);  // returns the buffer to the pool of the context it came from
