@@ -61,6 +61,12 @@ def check_index_hashes(golden, fi, ri):
     assert sha256(ri.sai.astype("<u4").tobytes()) == ix["rsai_u32_sha256"], ".rsai differs from the reference's"
 
 
+# A strand group shards its strand over its GPUs only when the strand is big: a column pass of a config-2-sized build
+# (463 M rows) takes 0.3 ms on one GPU, less than the collectives of a sharded pass cost, so one GPU per strand is fastest
+# there (measured: 51.7 ms on 2 GPUs, 60.3 ms on 4 with groups of 2); config 4 (5.03 G rows) and 5 (2.57 G) shard.
+SHARD_MIN_ROWS = int(os.environ.get("SIGA_SHARD_MIN_ROWS", str(1 << 31)))
+
+
 def measured_peaks():
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -467,8 +473,10 @@ def main():
     #      single-GPU build of the setup phase (itself checked against the reference's hashes above).
     isteps = args.index_steps or min(args.steps, 3)
     group = 0 if world == 1 else rank // (world // 2)   # which strand this rank works on
-    sub_world = 1 if world == 1 else world // 2
-    sub_rank = rank % sub_world
+    group_size = 1 if world == 1 else world // 2
+    sub_world = group_size if fi.n_suffixes >= SHARD_MIN_ROWS else 1  # GPUs of the group that take part (SHARD_MIN_ROWS)
+    sub_rank = rank % group_size
+    idle = sub_rank >= sub_world  # a small build leaves the group's other GPUs out
     sub_comm = None  # the library's own NCCL communicator of this rank's strand group
     if sub_world > 1:
         ids = []
@@ -476,10 +484,13 @@ def main():
             uid = torch.from_numpy(ctx.comm_unique_id() if rank == leader else np.zeros(128, dtype=np.uint8)).cuda()
             dist.broadcast(uid, leader)
             ids.append(uid.cpu().numpy())
-        sub_comm = ctx.comm_init(ids[group], sub_rank, sub_world)
+        if not idle:
+            sub_comm = ctx.comm_init(ids[group], sub_rank, sub_world)
 
     def build_index(rd, copy=True):
         """-> list of results this rank produced (both strands at N = 1, its group's strand otherwise)"""
+        if idle:
+            return []
         if world == 1:
             return list(ctx.index_build_pair(rd, order=api.ORDER_SAIS2, copy=copy))
         if sub_comm is None:
@@ -631,9 +642,10 @@ def main():
         "index": {"metric": "bwt_build_gbases_per_s", "value": bases / (idx_ms * 1e-3) / 1e9, "unit": "Gbases/s",
                   "ms_per_step": idx_ms, "steps": isteps, "device_ms_per_step": idx_dev_ms / isteps,
                   "scaling": "strong" if world > 1 else "single GPU",
-                  "path": ("one cfg2 index pair built by %d GPUs: one group of %d per strand%s; byte-identical to the single-GPU build"
-                           % (world, sub_world, ", rows sharded by k-mer bucket inside a group (sgx_index_build_sharded over NCCL)"
-                              if sub_world > 1 else " (sgx_index_build, no collective)")) if world > 1
+                  "path": ("one cfg2 index pair built by %d GPUs: one group of %d per strand, %d of them building%s; byte-identical to "
+                           "the single-GPU build" % (world, group_size, sub_world, " (rows sharded by k-mer bucket, sgx_index_build_sharded "
+                           "over NCCL)" if sub_world > 1 else " (sgx_index_build, no collective: a strand of %d rows is below the sharding "
+                           "threshold of %d)" % (fi.n_suffixes, SHARD_MIN_ROWS))) if world > 1
                           else "sgx_index_build_pair (both strands side by side on two streams)",
                   "e2e": {"value": bases / (idx_e2e_ms * 1e-3) / 1e9, "unit": "Gbases/s", "ms_per_step": idx_e2e_ms,
                           "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(len(fi.runs) + len(ri.runs) + 8 * n_reads)},
@@ -725,8 +737,10 @@ def cfg4_object(args, ctx, api, formats, torch, dist, rank, world, local, barrie
            "generate_s": gen_s, "n_gpus": world}
     # strand groups, as in the cfg2 index object: ranks [0, N/2) build the forward index, ranks [N/2, N) the reverse one
     group = 0 if world == 1 else rank // (world // 2)
-    sub_world = 1 if world == 1 else world // 2
-    sub_rank = rank % sub_world
+    group_size = 1 if world == 1 else world // 2
+    sub_world = group_size if n * (L + 1) >= SHARD_MIN_ROWS else 1  # see SHARD_MIN_ROWS
+    sub_rank = rank % group_size
+    idle = sub_rank >= sub_world
     comm = None
     if sub_world > 1:
         ids = []
@@ -734,10 +748,13 @@ def cfg4_object(args, ctx, api, formats, torch, dist, rank, world, local, barrie
             uid = torch.from_numpy(ctx.comm_unique_id() if rank == leader else np.zeros(128, dtype=np.uint8)).cuda()
             dist.broadcast(uid, leader)
             ids.append(uid.cpu().numpy())
-        comm = ctx.comm_init(ids[group], sub_rank, sub_world)
+        if not idle:
+            comm = ctx.comm_init(ids[group], sub_rank, sub_world)
     r_dev = ctx.pack_reads(flat, off)
 
     def build_mine():
+        if idle:
+            return []
         if world == 1:
             return list(ctx.index_build_pair(r_dev, order=api.ORDER_SAIS2))
         if comm is None:
@@ -754,7 +771,8 @@ def cfg4_object(args, ctx, api, formats, torch, dist, rank, world, local, barrie
     out["index_ms"] = min(times)
     out["index_ms_runs"] = times
     out["index_gbases_per_s"] = n * L / (out["index_ms"] * 1e-3) / 1e9
-    out["index_path"] = "one group of %d GPU(s) per strand%s" % (sub_world, ", rows sharded by k-mer bucket over NCCL" if sub_world > 1 else "")
+    out["index_path"] = "one group of %d GPU(s) per strand, %d of them building%s" % (
+        group_size, sub_world, " (rows sharded by k-mer bucket over NCCL)" if sub_world > 1 else " (strand below the sharding threshold)")
     # the finished indices travel through tmpfs: run bytes are complete on each group's leader, .sai everywhere in the group
     runs_path, sai_path = "/dev/shm/siga_b200_cfg4_runs_%d.npy", "/dev/shm/siga_b200_cfg4_sai_%d.npy"
     if sub_rank == 0:
@@ -762,7 +780,7 @@ def cfg4_object(args, ctx, api, formats, torch, dist, rank, world, local, barrie
             rv = k if world == 1 else group
             np.save(runs_path % rv, o.runs)
             np.save(sai_path % rv, o.sai)
-    n_suffixes = mine[0].n_suffixes
+    n_suffixes = n * (L + 1)
     del mine
     barrier()
     if rank == 0 and world > 1:  # the same job on ONE GPU with the same kernels (both strands side by side)

@@ -573,7 +573,7 @@ int cmd_index(int argc, char** argv) {
   sgx_ctx* ctx = nullptr;
   int rc_init = SGX_OK;
   int rc = SGX_OK;
-  const int world = o.gpus;
+  int world = o.gpus;
   int my = 0;
   int group = -1, sub_world = 1, sub_rank = 0;  // --gpus N: strand group of this rank (see below)
   Gang gang;
@@ -593,6 +593,20 @@ int cmd_index(int argc, char** argv) {
     if (!read_sequences(input, &rs, &err)) {
       fprintf(stderr, "ERROR siga - %s\n", err.c_str());
       return -1;
+    }
+    // A strand is sharded over several GPUs only when it is big: a column pass of a config-2-sized build (463 M rows)
+    // takes 0.3 ms on one GPU, less than the collectives of a sharded pass cost.  Below the
+    // threshold one GPU per wanted strand does the work and the other devices are not used.
+    {
+      uint64_t min_rows = (uint64_t)1 << 31;
+      if (const char* e = getenv("SIGA_SHARD_MIN_ROWS")) min_rows = strtoull(e, nullptr, 10);
+      const uint64_t rows = rs.bases.size() + rs.size();
+      const int strands = (fwd ? 1 : 0) + (rev ? 1 : 0);
+      if (rows < min_rows && world > strands) {
+        info("%llu rows per index: one GPU per strand (sharding starts at %llu rows), using %d of the %d GPUs",
+             (unsigned long long)rows, (unsigned long long)min_rows, strands, world);
+        world = strands;
+      }
     }
     std::vector<int> rd(world, -1), wr(world, -1);
     for (int r = 1; r < world; ++r) {

@@ -117,10 +117,22 @@ def write_fasta(path, reads, names=None, prefix="r"):
 
 
 def default_name_ranks(n, prefix="r"):
-    """Rank of the default names r0..r(n-1) in std::string order (vectorised; equal to api.name_ranks of the list)."""
-    width = len(prefix) + len(str(max(n - 1, 0)))
-    names = np.char.add(prefix, np.arange(n).astype(str)).astype("S%d" % width)
-    order = np.argsort(names, kind="stable")
+    """Rank of the default names r0..r(n-1) in std::string order (equal to api.name_ranks of the list).
+
+    Byte-wise order of decimal strings = order of the numbers left-aligned to the longest width, a shorter string
+    before the longer ones it is a prefix of ("r1" < "r10" < "r2"): one integer key per name, no string sort."""
+    if n <= 0:
+        return np.zeros(0, dtype=np.uint32)
+    x = np.arange(n, dtype=np.uint64)
+    width = len(str(n - 1))
+    digits = np.ones(n, dtype=np.uint64)
+    p = np.uint64(10)
+    for d in range(2, width + 1):
+        digits[x >= p] = d
+        p = p * np.uint64(10)
+    pow10 = np.array([10 ** k for k in range(width + 1)], dtype=np.uint64)
+    key = x * pow10[(np.uint64(width) - digits).astype(np.int64)] * np.uint64(width + 1) + digits
+    order = np.argsort(key, kind="stable")
     rank = np.empty(n, dtype=np.uint32)
     rank[order] = np.arange(n, dtype=np.uint32)
     return rank

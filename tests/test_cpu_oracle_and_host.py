@@ -361,3 +361,9 @@ def test_literal_only_gzip_writer_round_trips(tmp_path):
     # within a few percent of zlib level 1: literal-only on sequence records, LZ77 on ED records
     assert sizes[(False, "vt")] < 1.05 * zlib1(files["vt"])
     assert sizes[(True, "ed")] < 1.05 * zlib1(files["ed"])
+
+
+def test_default_name_ranks_equal_string_sort():
+    """synth.default_name_ranks (one integer key per name) == ranks from sorting the names as strings."""
+    for n in (1, 2, 9, 10, 11, 99, 100, 101, 1234, 20000, 100001):
+        assert np.array_equal(synth.default_name_ranks(n), api.name_ranks(["r%d" % i for i in range(n)])), n

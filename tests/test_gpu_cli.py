@@ -188,6 +188,13 @@ def test_cli_multi_gpu_outputs_equal_single_gpu():
         _run(["overlap", "-m", "30", "--gpus", "2", src], two)
         for ext in (".bwt", ".rbwt", ".sai", ".rsai"):
             assert open(os.path.join(one, "reads" + ext), "rb").read() == open(os.path.join(two, "reads" + ext), "rb").read(), ext
+        # one strand sharded over both GPUs (rows by k-mer bucket, NCCL): forced below the size threshold
+        for flag, exts in (("--no-reverse", (".bwt", ".sai")), ("--no-forward", (".rbwt", ".rsai"))):
+            r = subprocess.run([CLI, "index", "--gpus", "2", flag, "-p", "sharded", src], cwd=two, capture_output=True, text=True,
+                               env=dict(os.environ, SIGA_SHARD_MIN_ROWS="0"))
+            assert r.returncode == 0, r.stderr[-2000:]
+            for ext in exts:
+                assert open(os.path.join(one, "reads" + ext), "rb").read() == open(os.path.join(two, "sharded" + ext), "rb").read(), ext
         a, b = _asqg(os.path.join(one, "reads.asqg.gz")), _asqg(os.path.join(two, "reads.asqg.gz"))
         n = len(reads)
         assert a[:1 + n] == b[:1 + n]
