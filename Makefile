@@ -21,7 +21,7 @@ build/obj/%.o: $(CSRC)/%.cu $(HDR)
 	@grep -E "error|warning" build/obj/$*.ptxas.log | grep -v "ptxas info" || true
 
 $(LIB): $(OBJ)
-	$(NVCC) -shared $(ARCH) -ccbin $(HOSTCXX) -o $@ $(OBJ) -lcudart_static -lpthread -ldl -lrt
+	$(NVCC) -shared $(ARCH) -ccbin $(HOSTCXX) -o $@.tmp $(OBJ) -lcudart_static -lpthread -ldl -lrt && mv -f $@.tmp $@
 
 cli: siga_b200/bin/siga
 siga_b200/bin/siga: $(wildcard $(CSRC)/host/*.cpp $(CSRC)/host/*.h) include/siga_b200.h $(LIB)

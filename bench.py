@@ -90,7 +90,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "250"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -402,18 +402,21 @@ def main():
     # ---- overlap end to end through the C ABI with HOST buffers ("e2e"): pack the pinned host reads, attach the
     #      host .sai/.rsai, search, convert, copy the edges out
     def e2e_step():
-        rr = ctx.pack_reads(flat, off)
+        rr = ctx.pack_reads_async(flat, off)  # the bases stream in while the index attaches and the first batches search
         ctx.fm_attach_reads(fwd, fi.sai, rr)
         ctx.fm_attach_reads(rev, ri.sai, rr)
         ee = ctx.overlap_edges(fwd, rev, rr, 0, n_reads, MIN_OVERLAP, name_rank, copy=False)
         nb = int(ee.edges.nbytes + ee.substring.nbytes)
+        e2e_dev.append(ee.stats["ms_total"])
         ctx.free_edges(ee)
         ctx.free_reads(rr)
         return nb
+    e2e_dev = []  # device time of the overlap call inside every e2e step (a slow step with a normal device time is the host's)
     for _ in range(3):
         e2e_step()
     barrier()
     e2e_steps = []
+    del e2e_dev[:]
     t0 = time.perf_counter()
     for _ in range(args.steps):
         ts = time.perf_counter()
@@ -617,9 +620,10 @@ def main():
         "device_ms_per_step": dev_ms / args.steps,
         "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": "reads/s", "ms_per_step": e2e_ms, "step_ms": [round(x, 2) for x in e2e_steps],
+                "step_overlap_device_ms": [round(x, 2) for x in e2e_dev],
                 "h2d_bytes_per_step": e2e_h2d,
                 "d2h_bytes_per_step": e2e_d2h,
-                "entry": "sgx_reads_pack + sgx_fm_attach_reads x2 + sgx_overlap_edges (pinned host reads / .sai / name ranks in, "
+                "entry": "sgx_reads_pack_async + sgx_fm_attach_reads x2 + sgx_overlap_edges (pinned host reads / .sai / name ranks in, "
                          "edges + SS flags out); every rank keeps the records of its own reads, as `siga overlap --gpus N` does"},
         "roofline": {"bound": "hbm", "kernel": "ov_search_lean_kernel", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": ach_gbs / hbm_peak,
@@ -752,17 +756,20 @@ def cfg4_object(args, ctx, api, formats, torch, dist, rank, world, local, barrie
             comm = ctx.comm_init(ids[group], sub_rank, sub_world)
     r_dev = ctx.pack_reads(flat, off)
 
-    def build_mine():
+    def build_mine():  # results stay in the library's pinned buffers (views, no numpy copy of ~0.6 GB of run bytes)
         if idle:
             return []
         if world == 1:
-            return list(ctx.index_build_pair(r_dev, order=api.ORDER_SAIS2))
+            return list(ctx.index_build_pair(r_dev, order=api.ORDER_SAIS2, copy=False))
         if comm is None:
-            return [ctx.index_build(r_dev, order=api.ORDER_SAIS2, reversed=bool(group))]
-        return [ctx.index_build_sharded(comm, r_dev, order=api.ORDER_SAIS2, reversed=bool(group))]
+            return [ctx.index_build(r_dev, order=api.ORDER_SAIS2, reversed=bool(group), copy=False)]
+        return [ctx.index_build_sharded(comm, r_dev, order=api.ORDER_SAIS2, reversed=bool(group), copy=False)]
 
     times = []
+    mine = []
     for it in range(2):
+        for o in mine:
+            ctx.free_index(o)
         barrier()
         t0 = time.perf_counter()
         mine = build_mine()
@@ -781,18 +788,21 @@ def cfg4_object(args, ctx, api, formats, torch, dist, rank, world, local, barrie
             np.save(runs_path % rv, o.runs)
             np.save(sai_path % rv, o.sai)
     n_suffixes = n * (L + 1)
+    for o in mine:
+        ctx.free_index(o)
     del mine
     barrier()
     if rank == 0 and world > 1:  # the same job on ONE GPU with the same kernels (both strands side by side)
-        a1, b1 = ctx.index_build_pair(r_dev, order=api.ORDER_SAIS2)
-        del a1, b1
+        for o in ctx.index_build_pair(r_dev, order=api.ORDER_SAIS2, copy=False):
+            ctx.free_index(o)
         t0 = time.perf_counter()
-        a1, b1 = ctx.index_build_pair(r_dev, order=api.ORDER_SAIS2)
+        a1, b1 = ctx.index_build_pair(r_dev, order=api.ORDER_SAIS2, copy=False)
         out["index_ms_one_gpu"] = (time.perf_counter() - t0) * 1e3
         for rv, one in ((0, a1), (1, b1)):
             assert np.array_equal(one.runs, np.load(runs_path % rv, mmap_mode="r")) and \
                 np.array_equal(one.sai, np.load(sai_path % rv, mmap_mode="r")), "cfg4: multi-GPU index differs from the single-GPU build"
-        del a1, b1
+        ctx.free_index(a1)
+        ctx.free_index(b1)
         out["index_speedup"] = out["index_ms_one_gpu"] / out["index_ms"]
         out["index_efficiency"] = out["index_speedup"] / world
         out["index_identical_to_one_gpu"] = True

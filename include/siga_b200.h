@@ -70,6 +70,16 @@ int sgx_sm_count(const sgx_ctx* ctx);
  * SGX_EINVAL instead of being mapped to rank 0.
  */
 int sgx_reads_pack(sgx_ctx* ctx, const char* ascii, const uint64_t* off, uint64_t n, sgx_reads** out);
+/*
+ * sgx_reads_pack without the wait: returns once the read lengths are known (one small upload); the bases cross PCIe in
+ * chunks of ~32 MB on a second stream of the context and are packed as they land, while the caller goes on (host ->
+ * device streaming).  sgx_overlap_edges starts each of its search batches as soon as the
+ * chunks holding that batch's query reads have arrived; every other consumer waits for the whole store first.
+ * `ascii` must stay valid, and a byte other than A/C/G/T is reported (SGX_EINVAL), by the first call that consumes the
+ * store or by sgx_reads_wait.
+ */
+int sgx_reads_pack_async(sgx_ctx* ctx, const char* ascii, const uint64_t* off, uint64_t n, sgx_reads** out);
+int sgx_reads_wait(sgx_ctx* ctx, const sgx_reads* reads);
 void sgx_reads_free(sgx_reads* reads);
 uint64_t sgx_reads_count(const sgx_reads* reads);
 uint64_t sgx_reads_bases(const sgx_reads* reads);

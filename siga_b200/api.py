@@ -19,7 +19,7 @@ assert BLOCK_DTYPE.itemsize == 72
 # Every symbol include/siga_b200.h declares (checked by the CPU tests against the built library).
 ABI_SYMBOLS = [
     "sgx_abi_version", "sgx_init", "sgx_shutdown", "sgx_last_error", "sgx_sm_count",
-    "sgx_reads_pack", "sgx_reads_free", "sgx_reads_count", "sgx_reads_bases",
+    "sgx_reads_pack", "sgx_reads_pack_async", "sgx_reads_wait", "sgx_reads_free", "sgx_reads_count", "sgx_reads_bases",
     "sgx_index_build", "sgx_index_build_pair", "sgx_index_out_free",
     "sgx_comm_unique_id", "sgx_comm_init", "sgx_comm_init_local", "sgx_comm_free", "sgx_comm_world", "sgx_comm_rank",
     "sgx_index_build_sharded", "sgx_edges_gather",
@@ -98,6 +98,8 @@ def load_library():
     lib.sgx_last_error.restype = ctypes.c_char_p
     lib.sgx_sm_count.argtypes = [vp]
     lib.sgx_reads_pack.argtypes = [vp, vp, vp, u64, ctypes.POINTER(vp)]
+    lib.sgx_reads_pack_async.argtypes = [vp, vp, vp, u64, ctypes.POINTER(vp)]
+    lib.sgx_reads_wait.argtypes = [vp, vp]
     lib.sgx_reads_free.argtypes = [vp]
     lib.sgx_reads_free.restype = None
     lib.sgx_reads_count.argtypes = [vp]
@@ -273,6 +275,18 @@ class Context:
         r = ctypes.c_void_p()
         self._check(self.lib.sgx_reads_pack(self.h, _ptr(flat), _ptr(off), len(off) - 1, ctypes.byref(r)))
         return r
+
+    def pack_reads_async(self, flat, off):
+        """sgx_reads_pack_async: returns at once, the bases stream to the device in chunks on a second stream.  `flat` must
+        stay alive (and should be pinned) until a consumer of the store has returned."""
+        flat = np.ascontiguousarray(flat, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        r = ctypes.c_void_p()
+        self._check(self.lib.sgx_reads_pack_async(self.h, _ptr(flat), _ptr(off), len(off) - 1, ctypes.byref(r)))
+        return r
+
+    def reads_wait(self, r):
+        self._check(self.lib.sgx_reads_wait(self.h, r))
 
     def free_reads(self, r):
         self.lib.sgx_reads_free(r)

@@ -3,6 +3,7 @@
 #include <new>
 #include <thread>
 #include <unordered_map>
+#include <unordered_set>
 
 #include "index.cuh"
 #include "correct.cuh"
@@ -11,6 +12,7 @@
 static std::string g_init_error;
 static std::mutex g_pin_mutex;
 static std::unordered_map<void*, std::pair<sgx_ctx*, size_t> > g_pin_owner;
+static std::unordered_set<void*> g_pageable;  // output buffers of one-shot contexts (plain memory, see pinned_get)
 
 void sgx_set_error(sgx_ctx* ctx, const char* msg) {
   if (ctx) {
@@ -82,6 +84,14 @@ void* pinned_get(sgx_ctx* ctx, size_t bytes) {
     }
   }
   void* p = nullptr;
+  if (ctx->oneshot && bytes >= ((size_t)4 << 20)) {
+    // a process that makes one call and exits (the CLI): pinning 100 MB costs ~50 ms, five times the price of copying
+    // the same bytes into pageable memory once; the buffer is handed out as is and never cached
+    if (posix_memalign(&p, 4096, bytes) != 0) throw sgx::Error{SGX_ENOMEM, "host allocation failed"};
+    std::lock_guard<std::mutex> lk(g_pin_mutex);
+    g_pageable.insert(p);
+    return p;
+  }
   SGX_CUDA(cudaMallocHost(&p, bytes));
   std::lock_guard<std::mutex> lk(g_pin_mutex);
   g_pin_owner[p] = std::make_pair(ctx, bytes);
@@ -91,6 +101,10 @@ void* pinned_get(sgx_ctx* ctx, size_t bytes) {
 void pinned_put(void* p) {
   if (!p) return;
   std::lock_guard<std::mutex> lk(g_pin_mutex);
+  if (g_pageable.erase(p)) {
+    free(p);
+    return;
+  }
   auto it = g_pin_owner.find(p);
   if (it == g_pin_owner.end()) return;
   it->second.first->pinned_free.push_back(std::make_pair(p, it->second.second));
@@ -105,6 +119,7 @@ sgx_ctx* ctx_aux(sgx_ctx* ctx) {
     a->launches = 0;
     a->flush_buf = nullptr;
     a->flush_bytes = 0;
+    a->oneshot = ctx->oneshot;
     cudaError_t e = cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
       delete a;
@@ -194,6 +209,10 @@ int sgx_init(int device, sgx_ctx** out) {
     ctx->launches = 0;
     ctx->flush_buf = nullptr;
     ctx->flush_bytes = 0;
+    {
+      const char* os = getenv("SGX_ONESHOT");  // set by the CLI: one call per process, see pinned_get
+      ctx->oneshot = os && os[0] == '1';
+    }
     SGX_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     {
       // keep freed device memory in the pool (see DevBuf)
@@ -254,6 +273,20 @@ int sgx_reads_pack(sgx_ctx* ctx, const char* ascii, const uint64_t* off, uint64_
   SGX_ENTRY_END(ctx)
 }
 
+int sgx_reads_pack_async(sgx_ctx* ctx, const char* ascii, const uint64_t* off, uint64_t n, sgx_reads** out) {
+  if (!ctx || !out) return SGX_EINVAL;
+  SGX_ENTRY_BEGIN(ctx)
+  *out = reads_pack_async(ctx, ascii, off, n);
+  SGX_ENTRY_END(ctx)
+}
+
+int sgx_reads_wait(sgx_ctx* ctx, const sgx_reads* reads) {
+  if (!ctx || !reads) return SGX_EINVAL;
+  SGX_ENTRY_BEGIN(ctx)
+  reads_settle(reads);
+  SGX_ENTRY_END(ctx)
+}
+
 void sgx_reads_free(sgx_reads* reads) {
   if (reads) cudaSetDevice(reads->ctx->device);
   reads_destroy(reads);
@@ -266,6 +299,7 @@ int sgx_index_build(sgx_ctx* ctx, const sgx_reads* reads, int order, int reverse
   if (!ctx || !reads || !out) return SGX_EINVAL;
   SGX_ENTRY_BEGIN(ctx)
   SGX_REQUIRE(order == SGX_ORDER_SAIS || order == SGX_ORDER_SAIS2, SGX_EINVAL, "sgx_index_build: unknown order");
+  reads_settle(reads);
   index_build(ctx, reads, order, reversed != 0, out);
   SGX_ENTRY_END(ctx)
 }
@@ -278,6 +312,7 @@ int sgx_index_build_pair(sgx_ctx* ctx, const sgx_reads* reads, int order, sgx_in
   if (!ctx || !reads || !out_fwd || !out_rev) return SGX_EINVAL;
   SGX_ENTRY_BEGIN(ctx)
   SGX_REQUIRE(order == SGX_ORDER_SAIS || order == SGX_ORDER_SAIS2, SGX_EINVAL, "sgx_index_build_pair: unknown order");
+  reads_settle(reads);
   sgx_ctx* aux = ctx_aux(ctx);
   // the second stream starts after everything queued on the first (the read store may still be in flight there)
   cudaEvent_t ready;
@@ -358,6 +393,7 @@ int sgx_index_build_sharded(sgx_ctx* ctx, sgx_comm* comm, const sgx_reads* reads
   if (!ctx || !comm || !reads || !out || comm->ctx != ctx) return SGX_EINVAL;
   SGX_ENTRY_BEGIN(ctx)
   SGX_REQUIRE(order == SGX_ORDER_SAIS || order == SGX_ORDER_SAIS2, SGX_EINVAL, "sgx_index_build_sharded: unknown order");
+  reads_settle(reads);
   index_build_sharded(ctx, comm, reads, order, reversed != 0, out);
   SGX_ENTRY_END(ctx)
 }
@@ -423,6 +459,7 @@ int sgx_correct_batch(sgx_ctx* ctx, const sgx_fm* fm, const sgx_reads* reads, ui
                       const uint64_t* qual_off, const sgx_correct_params* params, sgx_corrected* out) {
   if (!ctx || !out) return SGX_EINVAL;
   SGX_ENTRY_BEGIN(ctx)
+  reads_settle(reads);
   correct_run(ctx, fm, reads, first, count, qual, qual_off, params, out);
   SGX_ENTRY_END(ctx)
 }
@@ -439,6 +476,7 @@ int sgx_overlap_batch(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const 
                       uint64_t count, uint32_t min_overlap, int irreducible, int rc, sgx_hits* out) {
   if (!ctx || !out) return SGX_EINVAL;
   SGX_ENTRY_BEGIN(ctx)
+  reads_settle(reads);
   overlap_run(ctx, fwd, rev, reads, first, count, min_overlap, irreducible, rc, out);
   SGX_ENTRY_END(ctx)
 }

@@ -28,6 +28,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -356,17 +357,25 @@ struct LoadedInput {
   sgx_ctx* ctx = nullptr;
   int ctx_rc = SGX_OK;
   bool ok_bwt = false, ok_rbwt = false, ok_sai = false, ok_rsai = false, ok_reads = false;
+  double t_part[4] = {0, 0, 0, 0};  // seconds of the concurrent loaders: CUDA start, .bwt, .sai, reads
 };
 
 bool load_input(const std::string& input, const std::string& output, int device, LoadedInput* in, bool with_ctx = true) {
   std::vector<std::thread> pool;
-  if (with_ctx) pool.emplace_back([&]() { in->ctx_rc = sgx_init(device, &in->ctx); });
-  pool.emplace_back([&]() { in->ok_bwt = read_bwt(output + ".bwt", &in->ns, &in->nf, &in->runs); });
+  auto timed = [in](int slot, const std::function<void()>& f) {
+    const double t = now_s();
+    f();
+    in->t_part[slot] = now_s() - t;
+  };
+  if (with_ctx) pool.emplace_back([&]() { timed(0, [&]() { in->ctx_rc = sgx_init(device, &in->ctx); }); });
+  pool.emplace_back([&]() { timed(1, [&]() { in->ok_bwt = read_bwt(output + ".bwt", &in->ns, &in->nf, &in->runs); }); });
   pool.emplace_back([&]() { in->ok_rbwt = read_bwt(output + ".rbwt", &in->rns, &in->rnf, &in->rruns); });
-  pool.emplace_back([&]() { in->ok_sai = read_sai(output + ".sai", &in->sai); });
+  pool.emplace_back([&]() { timed(2, [&]() { in->ok_sai = read_sai(output + ".sai", &in->sai); }); });
   pool.emplace_back([&]() { in->ok_rsai = read_sai(output + ".rsai", &in->rsai); });
-  pool.emplace_back([&]() { in->ok_reads = read_sequences(input, &in->rs, &in->err); });
+  pool.emplace_back([&]() { timed(3, [&]() { in->ok_reads = read_sequences(input, &in->rs, &in->err); }); });
   for (auto& t : pool) t.join();
+  info("load (concurrent): CUDA start %.3f s, .bwt %.3f s, .sai %.3f s, reads %.3f s", in->t_part[0], in->t_part[1], in->t_part[2],
+       in->t_part[3]);
   if (!in->ok_bwt || !in->ok_rbwt) {
     fprintf(stderr, "ERROR siga - Failed to load FMIndex from %s\n", input.c_str());
     return false;
@@ -576,10 +585,15 @@ int cmd_index(int argc, char** argv) {
   int world = o.gpus;
   int my = 0;
   int group = -1, sub_world = 1, sub_rank = 0;  // --gpus N: strand group of this rank (see below)
+  double t_cuda = 0;  // seconds inside sgx_init (driver + context start-up)
   Gang gang;
   sgx_comm* comm = nullptr;
   if (world == 1) {
-    std::thread init_thread([&]() { rc_init = sgx_init(o.device, &ctx); });  // CUDA start-up overlaps the parse
+    std::thread init_thread([&]() {  // CUDA start-up overlaps the parse
+      const double tc = now_s();
+      rc_init = sgx_init(o.device, &ctx);
+      t_cuda = now_s() - tc;
+    });
     const bool parsed = read_sequences(input, &rs, &err);
     init_thread.join();
     if (!parsed) {
@@ -726,7 +740,7 @@ int cmd_index(int argc, char** argv) {
   if (comm) sgx_comm_free(comm);
   if (my) {
     sgx_reads_free(reads);
-    sgx_shutdown(ctx);
+    // (the context goes with the process: see main)
     _exit(0);
   }
   const bool kids_ok = gang.wait_all();
@@ -735,11 +749,9 @@ int cmd_index(int argc, char** argv) {
     return -1;
   }
   sgx_reads_free(reads);
-  const double t_written = now_s();
-  sgx_shutdown(ctx);
   const double t1 = now_s();
-  info("wall: %.3f sec (load + CUDA start %.3f, pack + build %.3f, rest of the writes %.3f, shutdown %.3f)", t1 - t0, t_load - t0,
-       t_built - t_load, t_written - t_built, t1 - t_written);
+  info("wall: %.3f sec (load + CUDA start %.3f [CUDA start alone %.3f], pack + build %.3f, rest of the writes %.3f)", t1 - t0,
+       t_load - t0, t_cuda, t_built - t_load, t1 - t_built);
   return 0;
 }
 
@@ -833,14 +845,19 @@ int cmd_overlap(int argc, char** argv) {
     }
     return -1;
   };
+  const double tp0 = now_s();
   if ((rc = sgx_reads_pack(ctx, rs.bases.data(), rs.off.data(), rs.size(), &reads)) != SGX_OK) {
     if (rc == SGX_EINVAL && my == 0) explain_bad_bases(rs);
     return bail("sgx_reads_pack", rc);
   }
+  const double tp1 = now_s();
   if ((rc = sgx_fm_create(ctx, runs.data(), runs.size(), nf, &fwd)) != SGX_OK) return bail("sgx_fm_create", rc);
   if ((rc = sgx_fm_create(ctx, rruns.data(), rruns.size(), rnf, &rev)) != SGX_OK) return bail("sgx_fm_create", rc);
+  const double tp2 = now_s();
   if ((rc = sgx_fm_attach_reads(ctx, fwd, sai.data(), sai.size(), reads)) != SGX_OK) return bail("sgx_fm_attach_reads", rc);
   if ((rc = sgx_fm_attach_reads(ctx, rev, rsai.data(), rsai.size(), reads)) != SGX_OK) return bail("sgx_fm_attach_reads", rc);
+  const double tp3 = now_s();
+  info("device set-up: reads %.3f s, rank blocks of both indices %.3f s, .sai attach %.3f s", tp1 - tp0, tp2 - tp1, tp3 - tp2);
   info("fm-index: %llu symbols in %zu runs (%.4f symbols per run)", (unsigned long long)nf, runs.size(),
        runs.empty() ? 0.0 : (double)nf / runs.size());
   sgx_edges ed;
@@ -867,7 +884,7 @@ int cmd_overlap(int argc, char** argv) {
            write_asqg(part + ".ed", o, rs, ed, first, min_overlap, false, false, true);
     if (my) {
       sgx_edges_free(&ed);
-      sgx_shutdown(ctx);
+      // (the context goes with the process: see main)
       _exit(good ? 0 : 1);
     }
     if (!gang.wait_all()) good = false;
@@ -889,7 +906,7 @@ int cmd_overlap(int argc, char** argv) {
   sgx_fm_free(fwd);
   sgx_fm_free(rev);
   sgx_reads_free(reads);
-  sgx_shutdown(ctx);
+  // (the context goes with the process: see main)
   const double t1 = now_s();
   info("wall: %.3f sec (load %.3f, gpu %.3f, write %.3f)", t1 - t0, t_load - t0, t_search - t_load, t1 - t_search);
   return 0;
@@ -1023,7 +1040,7 @@ int cmd_rmdup(int argc, char** argv) {
   sgx_fm_free(fwd);
   sgx_fm_free(rev);
   sgx_reads_free(reads);
-  sgx_shutdown(ctx);
+  // (the context goes with the process: see main)
   const double t1 = now_s();
   info("wall: %.3f sec (load %.3f, gpu %.3f, write %.3f)", t1 - t0, t_load - t0, t_gpu - t_load, t1 - t_gpu);
   return 0;
@@ -1240,7 +1257,7 @@ int cmd_correct(int argc, char** argv) {
     good = write_corrected(outfile + ".part" + std::to_string(my), gz, o.threads, o.gzip_level, o.gzip_fast, rs, res.valid, first, count);
     if (my) {
       sgx_corrected_free(&res);
-      sgx_shutdown(ctx);
+      // (the context goes with the process: see main)
       _exit(good ? 0 : 1);
     }
     if (!gang.wait_all()) good = false;
@@ -1263,7 +1280,7 @@ int cmd_correct(int argc, char** argv) {
   sgx_corrected_free(&res);
   sgx_fm_free(fm);
   sgx_reads_free(reads);
-  sgx_shutdown(ctx);
+  // (the context goes with the process: see main)
   const double t1 = now_s();
   info("wall: %.3f sec (load %.3f, gpu %.3f, write %.3f)", t1 - t0, t_load - t0, t_gpu - t_load, t1 - t_gpu);
   return 0;
@@ -1431,7 +1448,7 @@ int cmd_match(int argc, char** argv) {
   }
   fflush(stdout);
   sgx_fm_free(fm);
-  sgx_shutdown(ctx);
+  // (the context goes with the process: see main)
   return status;
 }
 
@@ -1503,11 +1520,19 @@ int main(int argc0, char** argv0) {
     return 256;
   }
   const std::string cmd = argv[1];
-  if (cmd == "index") return cmd_index(argc - 1, argv + 1);
-  if (cmd == "overlap") return cmd_overlap(argc - 1, argv + 1);
-  if (cmd == "rmdup") return cmd_rmdup(argc - 1, argv + 1);
-  if (cmd == "correct") return cmd_correct(argc - 1, argv + 1);
-  if (cmd == "match") return cmd_match(argc - 1, argv + 1);
+  // Every output file is closed (and its close checked) inside the command.  Leaving through _exit skips the tear-down
+  // of the CUDA context and of gigabytes of cached device work areas by the runtime's exit handlers, which costs up to
+  // a second and a half and frees nothing the process exit does not free anyway.
+  auto leave = [](int rc) {
+    fflush(nullptr);
+    _exit(rc & 0xff);
+    return rc;
+  };
+  if (cmd == "index") return leave(cmd_index(argc - 1, argv + 1));
+  if (cmd == "overlap") return leave(cmd_overlap(argc - 1, argv + 1));
+  if (cmd == "rmdup") return leave(cmd_rmdup(argc - 1, argv + 1));
+  if (cmd == "correct") return leave(cmd_correct(argc - 1, argv + 1));
+  if (cmd == "match") return leave(cmd_match(argc - 1, argv + 1));
   fprintf(stderr, "siga: '%s' is not provided by this build (only index / overlap / rmdup / correct / match are)\n", cmd.c_str());
   return 256;
 }

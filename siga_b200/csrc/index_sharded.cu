@@ -117,8 +117,7 @@ __global__ void __launch_bounds__(256) shard_rank_kernel(const uint16_t* __restr
                                                          const uint64_t* __restrict__ scanned, uint64_t ntiles, ShardBounds bounds,
                                                          const PosT* __restrict__ NP, const uint8_t* __restrict__ SYM,
                                                          const uint32_t* __restrict__ KEY, uint64_t held,
-                                                         uint8_t* __restrict__ tmpDest, PosT* __restrict__ tmpPos,
-                                                         uint32_t* __restrict__ tmpKey) {
+                                                         uint8_t* __restrict__ tmpDest, PosT* __restrict__ tmpPos) {
   const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= held) return;
   const uint32_t sym = (uint32_t)SYM[k];  // 0: the read ended in the previous pass
@@ -133,16 +132,15 @@ __global__ void __launch_bounds__(256) shard_rank_kernel(const uint16_t* __restr
   // wrote the row left behind (tile_checkpoints, index_kernels.cuh) -- no access to the BWT
   const uint64_t sc = __ldg(scanned + (uint64_t)c * ntiles + P / kMergeTile);
   tmpDest[k] = (uint8_t)(bounds.owner(key) * 4 + (int)c);  // send bucket: destination-major, then c
-  tmpKey[k] = key;
   tmpPos[k] = (PosT)(sc + rloc[k]);
 }
 
-// One insert on the wire: the sender-local rank part, the read, the bucket key of the new suffix.
+// One insert on the wire: the sender-local rank part and the read.  (The bucket key of the new suffix is not sent: the
+// receiver reads it off the read store next to the symbol it fetches there anyway -- a third less all-to-all traffic.)
 template <class PosT>
 struct WireItem {
   PosT pos;
   uint32_t id;
-  uint32_t key;
 };
 
 struct DestDigit {
@@ -153,13 +151,11 @@ template <class PosT>
 struct SendMove {
   const uint32_t* ID;
   const PosT* tmpPos;
-  const uint32_t* tmpKey;
   WireItem<PosT>* send;
   __device__ __forceinline__ void operator()(uint64_t k, uint64_t dest) const {
     WireItem<PosT> w;
     w.pos = tmpPos[k];
     w.id = ID[k];
-    w.key = tmpKey[k];
     send[dest] = w;
   }
 };
@@ -197,20 +193,32 @@ __global__ void __launch_bounds__(256) shard_place_kernel(ReadAcc acc, const Wir
                                                           uint32_t j, uint32_t uniform_len, RecvPlan plan,
                                                           uint32_t* __restrict__ ID2, PosT* __restrict__ NP2,
                                                           uint8_t* __restrict__ SYM2, uint32_t* __restrict__ KEY2) {
+  // the plan (at most 64 runs) in shared memory: a search with thread-dependent indices into kernel parameters would go
+  // through a local-memory copy of the whole structure in every thread
+  __shared__ uint64_t s_out0[kSendBuckets + 1], s_src0[kSendBuckets];
+  __shared__ long long s_K[kSendBuckets];
+  for (int e = threadIdx.x; e <= plan.entries; e += blockDim.x) {
+    s_out0[e] = plan.out0[e];
+    if (e < plan.entries) {
+      s_src0[e] = plan.src0[e];
+      s_K[e] = plan.K[e];
+    }
+  }
+  __syncthreads();
   const uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= n) return;
   int lo = 0, hi = plan.entries;  // last entry with out0 <= d
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
-    if (plan.out0[mid] <= d) lo = mid;
+    if (s_out0[mid] <= d) lo = mid;
     else hi = mid;
   }
-  const WireItem<PosT> w = recv[plan.src0[lo] + (d - plan.out0[lo])];
+  const WireItem<PosT> w = recv[s_src0[lo] + (d - s_out0[lo])];
   const uint32_t id = w.id;
   const uint32_t l = uniform_len ? uniform_len : acc.rv.len[id];
   ID2[d] = id;
-  NP2[d] = (PosT)((long long)w.pos + plan.K[lo]);
-  KEY2[d] = w.key;
+  NP2[d] = (PosT)((long long)w.pos + s_K[lo]);
+  KEY2[d] = suffix_key(acc, id, l - j, l);  // the suffix inserted in pass j starts at column l - j
   SYM2[d] = (l == j) ? (uint8_t)0 : (uint8_t)(acc.code(id, l - j - 1, l) + 1);
 }
 
@@ -219,7 +227,7 @@ struct Shard {
   int g = 0;
   uint64_t rows_final = 0;
   DevBuf<uint8_t> B0, B1, SYM, tmpDest;
-  DevBuf<uint32_t> ID0, ID1, KEY0, KEY1, tmpKey;
+  DevBuf<uint32_t> ID0, ID1, KEY0, KEY1;
   DevBuf<PosT> NP0, NP1, tmpPos;
   DevBuf<WireItem<PosT> > send, recv;
   DevBuf<uint16_t> RL;  // tile-local rank of every held item's row
@@ -249,7 +257,6 @@ struct Shard {
     ID1.alloc(N);
     KEY0.alloc(N);
     KEY1.alloc(N);
-    tmpKey.alloc(N);
     SGX_CUDA(cudaMemsetAsync(KEY0.p, 0, N * sizeof(uint32_t), ctx->stream));  // the sentinel rows: key of "$"
     send.alloc(N);
     recv.alloc(N);
@@ -328,7 +335,7 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
       if (s.held) {
         SGX_LAUNCH(ctx, (shard_rank_kernel<PosT>), grid_for(s.held, 256), 256, 0, (const uint16_t*)s.RL.p,
                    (const uint64_t*)s.tiletot.p, s.nt, bounds, (const PosT*)s.NP, (const uint8_t*)s.SYM.p,
-                   (const uint32_t*)s.KEY, s.held, s.tmpDest.p, s.tmpPos.p, s.tmpKey.p);
+                   (const uint32_t*)s.KEY, s.held, s.tmpDest.p, s.tmpPos.p);
         DestDigit dg{s.tmpDest.p};
         partition_count<kSendBuckets, DestDigit>(ctx, dg, s.held, s.part_ws.p, s.kept.p);
         ntiles = part_tiles(s.held);
@@ -344,7 +351,7 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
       Shard<PosT>& s = sh[li];
       if (!s.held) continue;
       DestDigit dg{s.tmpDest.p};
-      SendMove<PosT> mv{s.ID, s.tmpPos.p, s.tmpKey.p, s.send.p};
+      SendMove<PosT> mv{s.ID, s.tmpPos.p, s.send.p};
       partition_scatter<kSendBuckets, DestDigit, SendMove<PosT> >(ctx, dg, mv, s.held, s.part_ws.p);
     }
     SGX_TRACE_TICK(k_gather);

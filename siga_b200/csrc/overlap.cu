@@ -559,6 +559,7 @@ void overlap_edges_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const
   t_all.start();
   OvPlan pl;
   pl.init(ctx, fwd, rev, reads, first, count, min_ov, irreducible, rc);
+  if (!pl.fast) reads_settle(reads);
   const uint64_t n_all = fwd->indexed->n;
   DevBuf<uint32_t> d_rank(n_all);
   SGX_CUDA(cudaMemcpyAsync(d_rank.p, name_rank, n_all * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -566,7 +567,9 @@ void overlap_edges_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const
   DevBuf<uint32_t> d_slow(std::max<uint64_t>(count, 1)), d_flags(2);  // [0] n_slow, [1] overflow
   DevBuf<unsigned long long> d_counter(2);
   DevBuf<sgx_edge> d_edges;
-  uint64_t edge_cap = env_u64("SGX_EDGE_CAP", std::max<uint64_t>(count * 8, 1u << 16));  // hook: overflow round
+  // edges kept per read: ~3-5 on average at 100x coverage, but the id0 >= id1 rule keeps up to twice the average for a
+  // range of reads whose names sort high (a rank of a multi-GPU run); an overflow costs a whole second round
+  uint64_t edge_cap = env_u64("SGX_EDGE_CAP", std::max<uint64_t>(count * 12, 1u << 16));  // hook: overflow round
   uint64_t n_edges = 0, n_slow = 0, search_launches = 0;
   double post2_ms = 0;  // reduce kernels that ran on the second stream
 
@@ -650,6 +653,8 @@ void overlap_edges_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const
         bt.find_cap = pl.find_cap;
         bt.out_cap = pl.out_cap;
         if (two && bi >= 2) SGX_CUDA(cudaStreamWaitEvent(ctx->stream, ev_r[set], 0));  // the reduce of batch b - 2 is done with this set
+        // a read store that is still arriving (sgx_reads_pack_async): the search needs the query reads of its batch only
+        reads_wait_range(ctx->stream, reads, first + b0, first + b0 + bn);
         k_search.tick();
         pl.search(true, first + b0, bn, bt, nullptr);
         k_search.tick();
@@ -659,6 +664,7 @@ void overlap_edges_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const
           SGX_CUDA(cudaEventRecord(ev_s[set], ctx->stream));
           SGX_CUDA(cudaStreamWaitEvent(aux->stream, ev_s[set], 0));
         }
+        if (bi == 0) reads_wait_range(ctx->stream, reads, 0, reads->n);  // the reduce reads targets anywhere in the store
         KernelClock& kp = two ? k_post2 : k_post;
         kp.tick();
         if (old_reduce) {  // experiments: the round-1 kernel (one side after the other, staged edges)
@@ -683,6 +689,7 @@ void overlap_edges_run(sgx_ctx* ctx, const sgx_fm* fwd, const sgx_fm* rev, const
       uint32_t fl[2] = {0, 0};
       SGX_CUDA(cudaMemcpyAsync(fl, d_flags.p, sizeof(fl), cudaMemcpyDeviceToHost, ctx->stream));
       SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+      reads_settle(reads);  // all chunks have arrived by now; a store with a bad base is refused here
       n_slow = fl[0];
       if (fl[1]) {
         edge_cap *= 4;

@@ -542,3 +542,62 @@ def test_edge_case_inputs_match_reference(ctx, case):
 def test_zero_reads_are_rejected(ctx):
     with pytest.raises(api.SgxError):
         ctx.pack_reads(np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.uint64))
+
+
+# ------------------------------------------------------------------------------------------- streaming read store
+
+def test_async_read_store_gives_identical_results(ctx, monkeypatch):
+    """sgx_reads_pack_async (bases streamed to the device in chunks on a second stream): index, overlap edges (several
+    search batches, each waiting only for its own chunks) and correction equal those of the synchronous store."""
+    monkeypatch.setenv("SGX_MAX_BATCH", "3000")
+    rng = np.random.default_rng(88)
+    g = synth.random_genome(40_000, rng)
+    reads = synth.sample_reads(g, 30_000, 100, rng, err=0.01)
+    flat, off = synth.reads_to_flat(reads)
+    n = len(off) - 1
+    ranks = synth.default_name_ranks(n)
+    r = ctx.pack_reads(flat, off)
+    fi, ri = ctx.index_build(r), ctx.index_build(r, reversed=True)
+    fwd, rev = ctx.fm_create(fi.runs, fi.n_suffixes), ctx.fm_create(ri.runs, ri.n_suffixes)
+    try:
+        ctx.fm_attach_reads(fwd, fi.sai, r)
+        ctx.fm_attach_reads(rev, ri.sai, r)
+        want = ctx.overlap_edges(fwd, rev, r, 0, n, 40, ranks)
+        for _ in range(3):
+            ra = ctx.pack_reads_async(flat, off)
+            ctx.fm_attach_reads(fwd, fi.sai, ra)
+            ctx.fm_attach_reads(rev, ri.sai, ra)
+            got = ctx.overlap_edges(fwd, rev, ra, 0, n, 40, ranks)
+            assert got.stats["search_launches"] > 1
+            assert np.array_equal(got.edges, want.edges) and np.array_equal(got.substring, want.substring)
+            ctx.free_reads(ra)
+        # any other consumer waits for the whole store first
+        ra = ctx.pack_reads_async(flat, off)
+        fa = ctx.index_build(ra)
+        assert np.array_equal(fa.runs, fi.runs) and np.array_equal(fa.sai, fi.sai)
+        ctx.free_reads(ra)
+        ra = ctx.pack_reads_async(flat, off)
+        ctx.free_reads(ra)  # released while chunks may still be in flight
+    finally:
+        ctx.fm_attach_reads(fwd, fi.sai, r)
+        ctx.fm_attach_reads(rev, ri.sai, r)
+        ctx.free_fm(fwd)
+        ctx.free_fm(rev)
+        ctx.free_reads(r)
+
+
+def test_async_read_store_reports_bad_bases_at_the_consumer(ctx):
+    bad = synth.sample_reads(synth.random_genome(5000, np.random.default_rng(1)), 4000, 50, np.random.default_rng(2))
+    bad[3210, 7] = ord("N")
+    flat, off = synth.reads_to_flat(bad)
+    ra = ctx.pack_reads_async(flat, off)
+    with pytest.raises(api.SgxError) as e:
+        ctx.reads_wait(ra)
+    assert e.value.code == -1 and "3210" in str(e.value)
+    with pytest.raises(api.SgxError):
+        ctx.index_build(ra)  # stays refused
+    ctx.free_reads(ra)
+    ra = ctx.pack_reads_async(flat, off)
+    with pytest.raises(api.SgxError):
+        ctx.index_build(ra)
+    ctx.free_reads(ra)
