@@ -270,7 +270,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cli", action="store_true")
     ap.add_argument("--no-correct", action="store_true")
-    ap.add_argument("--cfg4", default="auto", choices=["auto", "on", "off"], help="the 100 Mbp config (auto: at 8 GPUs)")
+    ap.add_argument("--cfg4", default="auto", choices=["auto", "on", "off"], help="the 100 Mbp and 64 Mbp configs 4 and 5 (auto: at 8 GPUs)")
     ap.add_argument("--cfg4-scale", type=float, default=1.0)
     ap.add_argument("--index-steps", type=int, default=0, help="timed index builds (default: min(steps, 3))")
     args = ap.parse_args()
@@ -688,7 +688,9 @@ def main():
             ctx.free_reads(r_dev)
             fwd = rev = r_dev = None
         del host, flat
-        line["cfg4"] = cfg4_object(args, ctx, api, formats, torch, dist, rank, world, local, barrier, max_over_ranks, sum_over_ranks)
+        for big in ("cfg4", "cfg5"):  # BASELINE.json configs[3] and configs[4]
+            line[big] = cfg4_object(args, ctx, api, formats, torch, dist, rank, world, local, barrier, max_over_ranks,
+                                    sum_over_ranks, cfg=big)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         with tempfile.TemporaryDirectory() as d:
@@ -713,19 +715,20 @@ def main():
     return 0
 
 
-def cfg4_object(args, ctx, api, formats, torch, dist, rank, world, local, barrier, max_over_ranks, sum_over_ranks):
-    """BASELINE.json configs[3]: 100 Mbp genome, 50x 150 bp reads (33.3 M reads, 5.03 G symbols per index): the index built
-    by all ranks together (rows sharded by k-mer bucket, NCCL all-to-all per column pass) and the overlap stage sharded by
-    read range, each next to the time ONE GPU takes for the same job with the same kernels (rank 0, the others idle)."""
+def cfg4_object(args, ctx, api, formats, torch, dist, rank, world, local, barrier, max_over_ranks, sum_over_ranks, cfg="cfg4"):
+    """BASELINE.json configs[3] (cfg4: 100 Mbp genome, 50x 150 bp reads, 33.3 M reads, 5.03 G symbols per index) or
+    configs[4] (cfg5: 64 Mbp, 40x 250 bp, 10.2 M reads, 2.57 G symbols): the index built by all ranks together (strand
+    groups, rows sharded by k-mer bucket with an NCCL all-to-all per column pass) and the overlap stage sharded by read
+    range, each next to the time ONE GPU takes for the same job with the same kernels (rank 0, the others idle)."""
     scale = args.cfg4_scale
-    shm = "/dev/shm/siga_b200_cfg4_%g.u8" % scale
-    c = synth.CONFIGS["cfg4"]
+    shm = "/dev/shm/siga_b200_%s_%g.u8" % (cfg, scale)
+    c = synth.CONFIGS[cfg]
     g = max(int(c["genome"] * scale), 4 * c["read_len"])
     n = int(g * c["coverage"] // c["read_len"])
     L = c["read_len"]
     t0 = time.perf_counter()
     if rank == 0:  # one generation, shared through tmpfs (33.3 M x 150 bytes)
-        reads0 = synth.config_reads("cfg4", scale)
+        reads0 = synth.config_reads(cfg, scale)
         assert reads0.shape == (n, L)
         mm = np.lib.format.open_memmap(shm, mode="w+", dtype=np.uint8, shape=(n, L))
         mm[:] = reads0
@@ -736,8 +739,8 @@ def cfg4_object(args, ctx, api, formats, torch, dist, rank, world, local, barrie
     gen_s = time.perf_counter() - t0
     flat = reads.reshape(-1)
     off = (np.arange(n + 1, dtype=np.uint64) * np.uint64(L))
-    out = {"workload": "cfg4%s: %d Mbp random genome, 50x, 150 bp error-free reads, both strands, %d reads; index + overlap -m %d" %
-                       ("" if scale == 1.0 else " [genome scale %g]" % scale, g // 1_000_000, n, MIN_OVERLAP),
+    out = {"workload": "%s%s: %d Mbp random genome, %dx, %d bp error-free reads, both strands, %d reads; index + overlap -m %d" %
+                       (cfg, "" if scale == 1.0 else " [genome scale %g]" % scale, g // 1_000_000, c["coverage"], L, n, MIN_OVERLAP),
            "generate_s": gen_s, "n_gpus": world}
     # strand groups, as in the cfg2 index object: ranks [0, N/2) build the forward index, ranks [N/2, N) the reverse one
     group = 0 if world == 1 else rank // (world // 2)
@@ -781,7 +784,7 @@ def cfg4_object(args, ctx, api, formats, torch, dist, rank, world, local, barrie
     out["index_path"] = "one group of %d GPU(s) per strand, %d of them building%s" % (
         group_size, sub_world, " (rows sharded by k-mer bucket over NCCL)" if sub_world > 1 else " (strand below the sharding threshold)")
     # the finished indices travel through tmpfs: run bytes are complete on each group's leader, .sai everywhere in the group
-    runs_path, sai_path = "/dev/shm/siga_b200_cfg4_runs_%d.npy", "/dev/shm/siga_b200_cfg4_sai_%d.npy"
+    runs_path, sai_path = "/dev/shm/siga_b200_" + cfg + "_runs_%d.npy", "/dev/shm/siga_b200_" + cfg + "_sai_%d.npy"
     if sub_rank == 0:
         for k, o in enumerate(mine):
             rv = k if world == 1 else group
@@ -800,7 +803,7 @@ def cfg4_object(args, ctx, api, formats, torch, dist, rank, world, local, barrie
         out["index_ms_one_gpu"] = (time.perf_counter() - t0) * 1e3
         for rv, one in ((0, a1), (1, b1)):
             assert np.array_equal(one.runs, np.load(runs_path % rv, mmap_mode="r")) and \
-                np.array_equal(one.sai, np.load(sai_path % rv, mmap_mode="r")), "cfg4: multi-GPU index differs from the single-GPU build"
+                np.array_equal(one.sai, np.load(sai_path % rv, mmap_mode="r")), "%s: multi-GPU index differs from the single-GPU build" % cfg
         ctx.free_index(a1)
         ctx.free_index(b1)
         out["index_speedup"] = out["index_ms_one_gpu"] / out["index_ms"]
@@ -840,7 +843,7 @@ def cfg4_object(args, ctx, api, formats, torch, dist, rank, world, local, barrie
         t0 = time.perf_counter()
         e = ctx.overlap_edges(fwd, rev, r_dev, 0, n, MIN_OVERLAP, name_rank, copy=False)
         out["overlap_ms_one_gpu"] = (time.perf_counter() - t0) * 1e3
-        assert e.stats["n_edges"] == out["edges"], "cfg4: sharded overlap found a different number of edges"
+        assert e.stats["n_edges"] == out["edges"], "%s: sharded overlap found a different number of edges" % cfg
         ctx.free_edges(e)
         out["overlap_speedup"] = out["overlap_ms_one_gpu"] / out["overlap_ms"]
         out["overlap_efficiency"] = out["overlap_speedup"] / world

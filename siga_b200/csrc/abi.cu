@@ -3,7 +3,6 @@
 #include <new>
 #include <thread>
 #include <unordered_map>
-#include <unordered_set>
 
 #include "index.cuh"
 #include "correct.cuh"
@@ -12,7 +11,6 @@
 static std::string g_init_error;
 static std::mutex g_pin_mutex;
 static std::unordered_map<void*, std::pair<sgx_ctx*, size_t> > g_pin_owner;
-static std::unordered_set<void*> g_pageable;  // output buffers of one-shot contexts (plain memory, see pinned_get)
 
 void sgx_set_error(sgx_ctx* ctx, const char* msg) {
   if (ctx) {
@@ -84,14 +82,6 @@ void* pinned_get(sgx_ctx* ctx, size_t bytes) {
     }
   }
   void* p = nullptr;
-  if (ctx->oneshot && bytes >= ((size_t)4 << 20)) {
-    // a process that makes one call and exits (the CLI): pinning 100 MB costs ~50 ms, five times the price of copying
-    // the same bytes into pageable memory once; the buffer is handed out as is and never cached
-    if (posix_memalign(&p, 4096, bytes) != 0) throw sgx::Error{SGX_ENOMEM, "host allocation failed"};
-    std::lock_guard<std::mutex> lk(g_pin_mutex);
-    g_pageable.insert(p);
-    return p;
-  }
   SGX_CUDA(cudaMallocHost(&p, bytes));
   std::lock_guard<std::mutex> lk(g_pin_mutex);
   g_pin_owner[p] = std::make_pair(ctx, bytes);
@@ -101,10 +91,6 @@ void* pinned_get(sgx_ctx* ctx, size_t bytes) {
 void pinned_put(void* p) {
   if (!p) return;
   std::lock_guard<std::mutex> lk(g_pin_mutex);
-  if (g_pageable.erase(p)) {
-    free(p);
-    return;
-  }
   auto it = g_pin_owner.find(p);
   if (it == g_pin_owner.end()) return;
   it->second.first->pinned_free.push_back(std::make_pair(p, it->second.second));
@@ -119,7 +105,6 @@ sgx_ctx* ctx_aux(sgx_ctx* ctx) {
     a->launches = 0;
     a->flush_buf = nullptr;
     a->flush_bytes = 0;
-    a->oneshot = ctx->oneshot;
     cudaError_t e = cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
       delete a;
@@ -209,10 +194,6 @@ int sgx_init(int device, sgx_ctx** out) {
     ctx->launches = 0;
     ctx->flush_buf = nullptr;
     ctx->flush_bytes = 0;
-    {
-      const char* os = getenv("SGX_ONESHOT");  // set by the CLI: one call per process, see pinned_get
-      ctx->oneshot = os && os[0] == '1';
-    }
     SGX_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     {
       // keep freed device memory in the pool (see DevBuf)

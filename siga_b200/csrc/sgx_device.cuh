@@ -33,7 +33,6 @@ struct sgx_ctx {
   // second stream of the same device with its own work-area cache, for entry points that run two independent jobs
   // side by side (sgx_index_build_pair); created on first use, owned by this context
   sgx_ctx* aux = nullptr;
-  bool oneshot = false;  // SGX_ONESHOT=1 at sgx_init: large outputs in pageable memory (pinning costs more than one copy)
 };
 
 namespace sgx {
