@@ -245,8 +245,8 @@ def cli_object(reads, golden, min_overlap):
         out = {"index_s": t_index, "overlap_s": t_overlap, "index_gbases_per_s": n * L / t_index / 1e9,
                "overlap_reads_per_s": n / t_overlap, "input": "FASTA, %d bytes, tmpfs" % os.path.getsize(fa),
                "asqg_gz_bytes": os.path.getsize(os.path.join(d, "reads.asqg.gz")),
-               "phases_index": [l.strip() for l in err_i.splitlines() if "wall" in l or " ms" in l][-6:],
-               "phases_overlap": [l.strip() for l in err_o.splitlines() if "wall" in l or " ms" in l][-8:]}
+               "phases_index": [l.strip() for l in err_i.splitlines() if "wall" in l or " ms" in l or "load (" in l][-6:],
+               "phases_overlap": [l.strip() for l in err_o.splitlines() if "wall" in l or " ms" in l or " s," in l][-8:]}
         if golden is not None:
             ok = True
             for ext in ("bwt", "rbwt", "sai", "rsai"):
@@ -401,11 +401,19 @@ def main():
 
     # ---- overlap end to end through the C ABI with HOST buffers ("e2e"): pack the pinned host reads, attach the
     #      host .sai/.rsai, search, convert, copy the edges out
+    def pinned(a):  # every e2e input lives in pinned host memory (the reads already do)
+        t = torch.empty(a.shape, dtype=getattr(torch, str(a.dtype))).pin_memory()
+        t.numpy()[...] = a
+        return t  # keep the tensor: its numpy view does not own the memory
+    pin_keep = [pinned(off.view(np.int64)), pinned(fi.sai.view(np.int32)), pinned(ri.sai.view(np.int32)), pinned(name_rank.view(np.int32))]
+    off_p = pin_keep[0].numpy().view(np.uint64)
+    sai_p, rsai_p, rank_p = (t.numpy().view(np.uint32) for t in pin_keep[1:])
+
     def e2e_step():
-        rr = ctx.pack_reads_async(flat, off)  # the bases stream in while the index attaches and the first batches search
-        ctx.fm_attach_reads(fwd, fi.sai, rr)
-        ctx.fm_attach_reads(rev, ri.sai, rr)
-        ee = ctx.overlap_edges(fwd, rev, rr, 0, n_reads, MIN_OVERLAP, name_rank, copy=False)
+        rr = ctx.pack_reads_async(flat, off_p)  # the bases stream in while the index attaches and the first batches search
+        ctx.fm_attach_reads(fwd, sai_p, rr)
+        ctx.fm_attach_reads(rev, rsai_p, rr)
+        ee = ctx.overlap_edges(fwd, rev, rr, 0, n_reads, MIN_OVERLAP, rank_p, copy=False)
         nb = int(ee.edges.nbytes + ee.substring.nbytes)
         e2e_dev.append(ee.stats["ms_total"])
         ctx.free_edges(ee)
@@ -599,11 +607,12 @@ def main():
         gather = ctx.bench_gather(8 << 30, 1 << 27)
     except Exception:
         gather = None
-    traffic, traffic_src = None, None
+    traffic, traffic_src, merge_traffic, merge_traffic_src = None, None, None, None
     tp = os.path.join(REPO, "profiles", "r2_traffic.json")
     if args.scale == 1.0 and os.path.isfile(tp):
         tj = json.load(open(tp))
         traffic, traffic_src = tj.get("search_dram_bytes_per_launch"), tj.get("source")
+        merge_traffic, merge_traffic_src = tj.get("merge_dram_bytes_of_captured_launch"), tj.get("merge_source")
     idx_suffix_bytes = {100: 31, 150: 37, 250: 50}.get(read_len, (read_len + 1 + 7) // 8 + 18)
     merge_s = idx_merge_ms * 1e-3 / max(idx_merge_launches, 1)
     merge_ach = (idx_merge_bytes / max(idx_merge_launches, 1)) / merge_s / 1e9 if merge_s > 0 else 0.0
@@ -655,7 +664,11 @@ def main():
                           "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(len(fi.runs) + len(ri.runs) + 8 * n_reads)},
                   "gpu_launches": int(idx_launches),
                   "roofline": {"bound": "hbm", "kernel": "bcr_merge_kernel", "achieved": merge_ach, "peak": hbm_peak, "unit": "GB/s",
-                               "frac": merge_ach / hbm_peak, "traffic": None,
+                               "frac": merge_ach / hbm_peak,
+                               # DRAM bytes of ONE captured launch (pass 76 of 150: launches grow with the pass number, the
+                               # average launch moves (n_old + n_new) / 2 + 5 B per insert = merge_bytes / merge_launches)
+                               "traffic": merge_traffic, "traffic_source": merge_traffic_src,
+                               "algorithmic_bytes_per_launch": idx_merge_bytes / max(idx_merge_launches, 1),
                                "merge_ms_per_build": idx_merge_ms / ((2 if world == 1 else 1) * isteps),
                                "floor_bytes_per_suffix": idx_suffix_bytes,
                                "floor_frac": idx_suffix_bytes * 2 * fi.n_suffixes / (idx_dev_ms / isteps * 1e-3) / 1e9 / hbm_peak}},

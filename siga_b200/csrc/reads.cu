@@ -2,6 +2,9 @@
 // std::vector<DNASeq> of std::strings (src/kseq.cpp:230-257).
 #include "reads.cuh"
 
+#include <chrono>
+#include <string>
+
 #include "prims.cuh"
 
 namespace sgx {
@@ -100,7 +103,7 @@ sgx_reads* reads_pack(sgx_ctx* ctx, const char* ascii, const uint64_t* off, uint
   SGX_CUDA(cudaStreamSynchronize(ctx->stream));
   SGX_REQUIRE((flags[2] & 1u) == 0, SGX_EINVAL, "sgx_reads_pack: empty read or non-monotonic offsets");
   DevBuf<uint32_t> d_words;
-  d_words.alloc_owned(n_words + 4);  // padded: word-level readers may touch one word past a read
+  d_words.alloc(n_words + 4);  // padded: word-level readers may touch one word past a read
   SGX_CUDA(cudaMemsetAsync(d_words.p + n_words, 0, 4 * sizeof(uint32_t), ctx->stream));
   // the offsets handed to the pack kernel are relative to the uploaded slice
   const uint64_t base = off[0];
@@ -128,7 +131,8 @@ sgx_reads* reads_pack(sgx_ctx* ctx, const char* ascii, const uint64_t* off, uint
   r->n_words = n_words;
   r->min_len = flags[0];
   r->max_len = flags[1];
-  r->words = d_words.take();
+  r->words_buf.swap(d_words);
+  r->words = r->words_buf.p;
   r->woff = d_woff.take();
   r->len = d_len.take();
   return r;
@@ -144,6 +148,20 @@ sgx_reads* reads_pack_async(sgx_ctx* ctx, const char* ascii, const uint64_t* off
   SGX_REQUIRE(n > 0 && n < 0xffffffffull, SGX_EINVAL, "sgx_reads_pack: read count must be in [1, 2^32-1)");
   const uint64_t total = off[n] - off[0];
   SGX_REQUIRE(off[n] >= off[0] && total > 0, SGX_EINVAL, "sgx_reads_pack: bad offsets");
+  const bool trace = getenv("SGX_TRACE_PACK") != nullptr;  // diagnostics: host time of every phase, to stderr
+  struct Watch {
+    bool on;
+    std::chrono::steady_clock::time_point t;
+    std::string log;
+    void lap(const char* what) {
+      if (!on) return;
+      const auto now = std::chrono::steady_clock::now();
+      char b[64];
+      snprintf(b, sizeof(b), " %s %.2f", what, std::chrono::duration<double, std::milli>(now - t).count());
+      log += b;
+      t = now;
+    }
+  } watch{trace, std::chrono::steady_clock::now(), std::string()};
   sgx_reads* r = new sgx_reads();
   struct Guard {
     sgx_reads* r;
@@ -161,9 +179,12 @@ sgx_reads* reads_pack_async(sgx_ctx* ctx, const char* ascii, const uint64_t* off
   DevBuf<uint32_t> d_len;
   d_woff.alloc_owned(n + 1);
   d_len.alloc_owned(n);
+  watch.lap("alloc_small");
   r->staging.alloc(total);
+  watch.lap("alloc_staging");
   r->staging_off.alloc(n + 1);
   r->flags.alloc(4);
+  watch.lap("alloc_off");
   const uint64_t base = off[0];
   std::vector<uint64_t> rb;
   const uint64_t* off0 = off;
@@ -183,18 +204,20 @@ sgx_reads* reads_pack_async(sgx_ctx* ctx, const char* ascii, const uint64_t* off
   uint32_t flags[4];
   SGX_CUDA(cudaMemcpyAsync(&n_words, d_woff.p + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
   SGX_CUDA(cudaMemcpyAsync(flags, r->flags.p, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
+  watch.lap("enqueue_len");
   SGX_CUDA(cudaStreamSynchronize(ctx->stream));  // rb / init are stack or local storage; n_words sizes the store
+  watch.lap("sync");
   SGX_REQUIRE((flags[2] & 1u) == 0, SGX_EINVAL, "sgx_reads_pack: empty read or non-monotonic offsets");
-  DevBuf<uint32_t> d_words;
-  d_words.alloc_owned(n_words + 4);
-  SGX_CUDA(cudaMemsetAsync(d_words.p + n_words, 0, 4 * sizeof(uint32_t), ctx->stream));
+  r->words_buf.alloc(n_words + 4);
+  SGX_CUDA(cudaMemsetAsync(r->words_buf.p + n_words, 0, 4 * sizeof(uint32_t), ctx->stream));
   r->n_words = n_words;
   r->min_len = flags[0];
   r->max_len = flags[1];
-  r->words = d_words.take();
+  r->words = r->words_buf.p;
   r->woff = d_woff.take();
   r->len = d_len.take();
   // chunks of about 32 MB of bases on the second stream, which starts after the allocations above
+  watch.lap("alloc_words");
   sgx_ctx* aux = ctx_aux(ctx);
   cudaEvent_t ready;
   SGX_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
@@ -217,6 +240,8 @@ sgx_reads* reads_pack_async(sgx_ctx* ctx, const char* ascii, const uint64_t* off
     SGX_CUDA(cudaEventRecord(ev, aux->stream));
   }
   ctx->launches += nchunks;
+  watch.lap("enqueue_chunks");
+  if (trace) fprintf(stderr, "[sgx pack_async]%s\n", watch.log.c_str());
   guard.r = nullptr;
   return r;
 }
@@ -258,9 +283,9 @@ void reads_destroy(sgx_reads* r) {
     r->chunk_ev.clear();
     r->pending = false;
   }
-  if (r->staging.p || r->staging_off.p || r->flags.p) {
-    // the staging buffers go back to the pool / work-area cache of the store's own context, whatever context the
-    // calling thread last used
+  {
+    // the buffers go back to the pool / work-area cache of the store's own context, whatever context the calling
+    // thread last used
     sgx_ctx* saved_ctx = g_ctx;
     cudaStream_t saved_stream = g_stream;
     g_ctx = r->ctx;
@@ -268,10 +293,10 @@ void reads_destroy(sgx_reads* r) {
     r->staging.release();
     r->staging_off.release();
     r->flags.release();
+    r->words_buf.release();
     g_ctx = saved_ctx;
     g_stream = saved_stream;
   }
-  if (r->words) cudaFreeAsync(r->words, r->ctx->stream);
   if (r->woff) cudaFreeAsync(r->woff, r->ctx->stream);
   if (r->len) cudaFreeAsync(r->len, r->ctx->stream);
   delete r;

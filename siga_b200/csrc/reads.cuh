@@ -21,6 +21,9 @@ struct sgx_reads {
   mutable bool invalid = false;
   mutable std::vector<cudaEvent_t> chunk_ev;
   uint64_t chunk_reads = 0;
+  // The packed words come from the context's work-area cache when they are large (a stream-ordered pool allocation of
+  // ~100 MB was seen to stall the host for 50 - 230 ms every few calls, profiles/r2_summary.md); `words` points into it.
+  sgx::DevBuf<uint32_t> words_buf;
   mutable sgx::DevBuf<char> staging;        // uploaded ASCII, released when settled
   mutable sgx::DevBuf<uint64_t> staging_off;
   mutable sgx::DevBuf<uint32_t> flags;      // [0] min len, [1] max len, [2] bad bits, [3] first read with a bad base

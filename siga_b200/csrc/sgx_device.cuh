@@ -74,7 +74,7 @@ extern thread_local sgx_ctx* g_ctx;
 // Work areas of >= kWsMinBytes come from the context's cache (first use: cudaMalloc; afterwards reused, so a
 // repeated call allocates nothing); smaller ones from the stream-ordered pool.  Everything runs on the one stream
 // of the context, so handing a released area to the next user is ordered by the stream.
-static const size_t kWsMinBytes = (size_t)32 << 20;
+static const size_t kWsMinBytes = (size_t)4 << 20;
 void* ws_get(size_t bytes);
 void ws_put(void* p);
 
