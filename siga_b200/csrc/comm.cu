@@ -99,6 +99,29 @@ static void comm_init_staging(sgx_comm* cm) {
   cm->ag_host = nullptr;
   cm->ag_cap = 0;
   SGX_CUDA(cudaEventCreateWithFlags(&cm->ag_done, cudaEventDisableTiming));
+  cm->side = nullptr;
+  cm->side_go = nullptr;
+  if (!cm->local) {
+    SGX_CUDA(cudaStreamCreateWithFlags(&cm->side, cudaStreamNonBlocking));
+    SGX_CUDA(cudaEventCreateWithFlags(&cm->side_go, cudaEventDisableTiming));
+  }
+  cm->peer_state = 0;
+  cm->peer_bytes = 0;
+  cm->epoch = 0;
+  for (int i = 0; i < kMaxShards; ++i) cm->peer_mine[i] = cm->peer_addr[i] = nullptr;
+}
+
+static void peer_release(sgx_comm* cm) {
+  for (int g = 0; g < cm->world; ++g) {
+    const bool mine = cm->local || g == cm->rank;
+    if (!mine && cm->peer_addr[g]) cudaIpcCloseMemHandle(cm->peer_addr[g]);
+    cm->peer_addr[g] = nullptr;
+  }
+  for (int li = 0; li < cm->n_local(); ++li) {
+    if (cm->peer_mine[li]) cudaFree(cm->peer_mine[li]);
+    cm->peer_mine[li] = nullptr;
+  }
+  cm->peer_bytes = 0;
 }
 
 sgx_comm* comm_create_nccl(sgx_ctx* ctx, const uint8_t id[128], int rank, int world) {
@@ -132,7 +155,18 @@ sgx_comm* comm_create_local(sgx_ctx* ctx, int shards) {
 void comm_destroy(sgx_comm* cm) {
   if (!cm) return;
   cudaStreamSynchronize(cm->ctx->stream);
+  if (cm->side) cudaStreamSynchronize(cm->side);
+  // peers may still be storing into this shard's region or reading their mapping of it: leave together
+  if (cm->nccl && cm->peer_bytes) {
+    try {
+      comm_barrier(cm);
+    } catch (const Error&) {
+    }
+  }
+  peer_release(cm);
   if (cm->nccl) nccl_api().CommDestroy((ncclComm_t)cm->nccl);
+  if (cm->side) cudaStreamDestroy(cm->side);
+  if (cm->side_go) cudaEventDestroy(cm->side_go);
   if (cm->ag_dev) cudaFree(cm->ag_dev);
   if (cm->ag_host) cudaFreeHost(cm->ag_host);
   cudaEventDestroy(cm->ag_done);
@@ -162,11 +196,16 @@ void comm_allgather_u64_begin(sgx_comm* cm, const uint64_t* const* dev_vals, uin
   if (cm->local) {
     for (int s = 0; s < cm->world; ++s)
       SGX_CUDA(cudaMemcpyAsync(cm->ag_host + (uint64_t)s * n, dev_vals[s], n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    SGX_CUDA(cudaEventRecord(cm->ag_done, st));
   } else {
-    SGX_NCCL(nccl_api().AllGather(dev_vals[0], cm->ag_dev, n, ncclUint64, (ncclComm_t)cm->nccl, st));
-    SGX_CUDA(cudaMemcpyAsync(cm->ag_host, cm->ag_dev, total * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    // on the side stream, behind everything enqueued on the main stream so far: what the caller enqueues next on the
+    // main stream (the scatter and the push of a column pass) runs beside the collective instead of behind it
+    SGX_CUDA(cudaEventRecord(cm->side_go, st));
+    SGX_CUDA(cudaStreamWaitEvent(cm->side, cm->side_go, 0));
+    SGX_NCCL(nccl_api().AllGather(dev_vals[0], cm->ag_dev, n, ncclUint64, (ncclComm_t)cm->nccl, cm->side));
+    SGX_CUDA(cudaMemcpyAsync(cm->ag_host, cm->ag_dev, total * sizeof(uint64_t), cudaMemcpyDeviceToHost, cm->side));
+    SGX_CUDA(cudaEventRecord(cm->ag_done, cm->side));
   }
-  SGX_CUDA(cudaEventRecord(cm->ag_done, st));
 }
 
 void comm_allgather_u64_end(sgx_comm* cm, uint64_t n, uint64_t* out) {
@@ -272,6 +311,74 @@ void comm_allgatherv(sgx_comm* cm, const void* const* send, const uint64_t* coun
     if (counts[p]) SGX_NCCL(api.Recv(dst + off[p] * elem_bytes, counts[p] * elem_bytes, ncclUint8, p, (ncclComm_t)cm->nccl, st));
   }
   grp.end();
+}
+
+bool comm_peer_reserve(sgx_comm* cm, size_t bytes) {
+  if (cm->peer_state < 0) return false;
+  if (cm->peer_state == 0) {
+    const char* x = getenv("SGX_SHARD_XCHG");
+    if (x && !strcmp(x, "nccl")) {
+      cm->peer_state = -1;
+      return false;
+    }
+  }
+  if (cm->peer_bytes >= bytes) return true;
+  cudaStream_t st = cm->ctx->stream;
+  SGX_CUDA(cudaStreamSynchronize(st));
+  if (cm->peer_bytes) {
+    comm_barrier(cm);  // nobody is still using the old regions
+    peer_release(cm);
+  }
+  const size_t want = (bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+  for (int li = 0; li < cm->n_local(); ++li) {
+    SGX_CUDA(cudaMalloc((void**)&cm->peer_mine[li], want));
+    SGX_CUDA(cudaMemsetAsync(cm->peer_mine[li], 0, kPeerHeaderBytes, st));
+  }
+  SGX_CUDA(cudaStreamSynchronize(st));
+  if (cm->local) {
+    for (int g = 0; g < cm->world; ++g) cm->peer_addr[g] = cm->peer_mine[g];
+    cm->peer_bytes = want;
+    cm->peer_state = 1;
+    return true;
+  }
+  // exchange the IPC handles through the communicator and map every peer's region
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  const int W = cm->world, me = cm->rank;
+  const uint64_t hw = sizeof(cudaIpcMemHandle_t) / sizeof(uint64_t);
+  ag_reserve(cm, (uint64_t)(W + 1) * hw);
+  cudaIpcMemHandle_t mine;
+  uint64_t ok = cudaIpcGetMemHandle(&mine, cm->peer_mine[0]) == cudaSuccess ? 1 : 0;
+  cudaGetLastError();
+  std::vector<cudaIpcMemHandle_t> all(W);
+  SGX_CUDA(cudaMemcpyAsync(cm->ag_dev + (uint64_t)W * hw, &mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+  SGX_NCCL(nccl_api().AllGather(cm->ag_dev + (uint64_t)W * hw, cm->ag_dev, hw, ncclUint64, (ncclComm_t)cm->nccl, st));
+  SGX_CUDA(cudaMemcpyAsync(all.data(), cm->ag_dev, (uint64_t)W * sizeof(mine), cudaMemcpyDeviceToHost, st));
+  SGX_CUDA(cudaStreamSynchronize(st));
+  cm->peer_addr[me] = cm->peer_mine[0];
+  for (int g = 0; g < W && ok; ++g) {
+    if (g == me) continue;
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, all[g], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      ok = 0;
+      break;
+    }
+    cm->peer_addr[g] = (uint8_t*)p;
+  }
+  // everybody or nobody: the processes must agree on the transport
+  DevBuf<uint64_t> agree(1);
+  SGX_CUDA(cudaMemcpyAsync(agree.p, &ok, sizeof(ok), cudaMemcpyHostToDevice, st));
+  SGX_NCCL(nccl_api().AllReduce(agree.p, agree.p, 1, ncclUint64, ncclMin, (ncclComm_t)cm->nccl, st));
+  SGX_CUDA(cudaMemcpyAsync(&ok, agree.p, sizeof(ok), cudaMemcpyDeviceToHost, st));
+  SGX_CUDA(cudaStreamSynchronize(st));
+  cm->peer_bytes = want;
+  if (!ok) {
+    peer_release(cm);
+    cm->peer_state = -1;
+    return false;
+  }
+  cm->peer_state = 1;
+  return true;
 }
 
 void comm_barrier(sgx_comm* cm) {

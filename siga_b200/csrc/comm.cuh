@@ -14,6 +14,11 @@
 
 #include "sgx_device.cuh"
 
+namespace sgx {
+static const int kMaxShards = 16;
+static const size_t kPeerHeaderBytes = 4096;  // start of a peer region: one arrival flag (uint64) per sender
+}
+
 struct sgx_comm {
   sgx_ctx* ctx;
   int world;    // number of shards
@@ -25,13 +30,22 @@ struct sgx_comm {
   uint64_t* ag_host;
   uint64_t ag_cap;  // uint64 elements
   cudaEvent_t ag_done;
+  // NCCL mode: the per-pass count all-gather runs on a stream of its own, beside the scatter / push of the main stream
+  cudaStream_t side;
+  cudaEvent_t side_go;
+  // Peer-memory exchange (comm_peer_reserve): one region per shard, every region mapped into every process of the
+  // communicator (cudaIpc between processes; plain pointers between the virtual shards of local mode).  Senders store
+  // straight into the receiver's region over NVLink and raise the receiver's arrival flag; nothing goes through NCCL.
+  int peer_state;                          // 0 not tried yet, 1 mapped, -1 unavailable (the NCCL send/recv path is used)
+  uint8_t* peer_mine[sgx::kMaxShards];     // regions of the local shards (by local index)
+  uint8_t* peer_addr[sgx::kMaxShards];     // region of shard g as this process addresses it
+  size_t peer_bytes;
+  uint64_t epoch;                          // exchanges done on this communicator; the flag value of the next one
   int n_local() const { return local ? world : 1; }
   int shard_of(int li) const { return local ? li : rank; }  // global shard index of local shard li
 };
 
 namespace sgx {
-
-static const int kMaxShards = 16;
 
 void comm_unique_id(uint8_t id[128]);
 sgx_comm* comm_create_nccl(sgx_ctx* ctx, const uint8_t id[128], int rank, int world);
@@ -67,6 +81,15 @@ void comm_gatherv_bytes(sgx_comm* cm, const uint8_t* const* send, const uint64_t
 void comm_allgatherv(sgx_comm* cm, const void* const* send, const uint64_t* counts, size_t elem_bytes, void* recv);
 
 void comm_barrier(sgx_comm* cm);
+
+// Collective.  Makes sure every shard owns a peer region of at least `bytes` (kPeerHeaderBytes of flags + payload) that
+// all processes of the communicator can store into; returns false when peer mapping is not possible here (cudaIpc
+// refused, SGX_SHARD_XCHG=nccl): the caller then exchanges through comm_alltoallv.  Regions live until comm_destroy.
+bool comm_peer_reserve(sgx_comm* cm, size_t bytes);
+// The next exchange's flag value (all processes call this in lock step, so they agree on it).
+inline uint64_t comm_next_epoch(sgx_comm* cm) { return ++cm->epoch; }
+// Arrival flag of sender `s` in the region of shard `d`.
+inline uint64_t* comm_peer_flag(sgx_comm* cm, int d, int s) { return (uint64_t*)cm->peer_addr[d] + s; }
 
 }  // namespace sgx
 

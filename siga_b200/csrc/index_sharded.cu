@@ -27,6 +27,7 @@
 // The transport is sgx_comm: NCCL between processes, or device copies between virtual shards of one context
 // (the mode the single-GPU parity tests run).
 #include <algorithm>
+#include <chrono>
 
 #include "comm.cuh"
 #include "index_kernels.cuh"
@@ -40,6 +41,10 @@ static const uint32_t kKeyTop = kPlanKeyTop;      // 5^7
 static const int kSendBuckets = kPlanSendBuckets;  // (destination shard, first base of the new suffix)
 static const int kMetaN = kPlanMetaN;              // per-shard values gathered every pass: send counts + A/C/G/T totals
 static_assert(kPlanMaxShards == kMaxShards, "shard_plan.h and comm.cuh disagree on the shard limit");
+
+static inline double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 struct ShardBounds {
   uint32_t b[kMaxShards + 1];
@@ -135,12 +140,19 @@ __global__ void __launch_bounds__(256) shard_rank_kernel(const uint16_t* __restr
   tmpPos[k] = (PosT)(sc + rloc[k]);
 }
 
-// One insert on the wire: the sender-local rank part and the read.  (The bucket key of the new suffix is not sent: the
-// receiver reads it off the read store next to the symbol it fetches there anyway -- a third less all-to-all traffic.)
+// One insert on the wire: the sender-local rank part, the read, the bucket key of the new suffix (rolled from the key of
+// the suffix it extends, so neither side touches the read store for it) and the 16-base word of the read the walk is in
+// (the receiver takes the symbol of the new row out of it; a fresh word is fetched once every 16 passes).
 template <class PosT>
-struct WireItem {
-  PosT pos;
-  uint32_t id;
+struct WireItem;
+template <>
+struct __align__(16) WireItem<uint32_t> {
+  uint32_t pos, id, key, win;
+};
+template <>
+struct __align__(8) WireItem<uint64_t> {
+  uint64_t pos;
+  uint32_t id, key, win, pad;
 };
 
 struct DestDigit {
@@ -151,11 +163,16 @@ template <class PosT>
 struct SendMove {
   const uint32_t* ID;
   const PosT* tmpPos;
+  const uint8_t* SYM;
+  const uint32_t* KEY;
+  const uint32_t* WIN;
   WireItem<PosT>* send;
   __device__ __forceinline__ void operator()(uint64_t k, uint64_t dest) const {
     WireItem<PosT> w;
     w.pos = tmpPos[k];
     w.id = ID[k];
+    w.key = (uint32_t)SYM[k] * kKeyTop + KEY[k] / 5u;
+    w.win = WIN[k];
     send[dest] = w;
   }
 };
@@ -181,18 +198,89 @@ static __global__ void shard_meta_kernel(const uint64_t* __restrict__ bucket_sta
   }
 }
 
+// ---- exchange through peer memory -------------------------------------------------------------------------------------
+// Every shard owns a region that all processes of the communicator have mapped (comm_peer_reserve): a header of arrival
+// flags and, per parity of the pass, one slot per sender sized for the worst case (every read of the set), so a sender
+// needs nothing from its peers to know where its block goes.  The push kernel streams the partitioned send buffer --
+// ordered by (destination, c) -- into the destinations' slots with coalesced 16-byte stores over NVLink, and the CTA
+// that finishes last raises this sender's flag at every destination (release at system scope behind the CTAs' own
+// fences).  The receiver's stream holds a one-warp kernel that spins on its flags (acquire) before the placement
+// kernel: no NCCL call, no host round trip on the data path.  Two parities: a sender may be one pass ahead of a
+// receiver that is still placing the previous pass's block; it cannot be two ahead, because its own next pass needs
+// that receiver's block of the pass in between.
+struct PushPlan {
+  uint8_t* slot[kMaxShards];   // this sender's slot in the region of destination d (current parity)
+  uint64_t* flag[kMaxShards];  // this sender's arrival flag at destination d
+  int world;
+};
+
+template <class PosT>
+__global__ void __launch_bounds__(256) shard_push_kernel(const WireItem<PosT>* __restrict__ send,
+                                                         const uint64_t* __restrict__ bucket_start, uint32_t ptiles, int have_items,
+                                                         const uint64_t* __restrict__ kept, PushPlan pp, uint64_t epoch,
+                                                         unsigned* __restrict__ done) {
+  __shared__ uint64_t s_start[kMaxShards + 1];
+  __shared__ WireItem<PosT>* s_slot[kMaxShards];
+  const int W = pp.world;
+  if ((int)threadIdx.x <= W) {
+    uint64_t v = 0;
+    if (have_items) v = (int)threadIdx.x < W ? bucket_start[(uint64_t)(4 * threadIdx.x) * ptiles] : *kept;
+    s_start[threadIdx.x] = v;
+  }
+  if ((int)threadIdx.x < W) s_slot[threadIdx.x] = (WireItem<PosT>*)pp.slot[threadIdx.x];
+  __syncthreads();
+  const uint64_t n = s_start[W];
+  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (uint64_t)gridDim.x * blockDim.x) {
+    int d = 0;
+    for (int i = 1; i < W; ++i) d += q >= s_start[i] ? 1 : 0;
+    s_slot[d][q - s_start[d]] = send[q];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(done, 1u);
+    if (t == gridDim.x - 1) {
+      *done = 0;  // the next push on this stream starts from zero
+      __threadfence_system();
+      for (int d = 0; d < W; ++d) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(pp.flag[d]), "l"(epoch) : "memory");
+    }
+  }
+}
+
+// One warp: lane s waits until sender s has raised its flag to this pass's epoch.  A peer that never arrives (its
+// process died) must not hang the device: after kPushTimeoutNs the kernel traps and the build fails with a CUDA error.
+static const unsigned long long kPushTimeoutNs = 30ull * 1000000000ull;
+static __global__ void shard_wait_kernel(const uint64_t* __restrict__ flags, int world, uint64_t epoch) {
+  if ((int)threadIdx.x < world) {
+    const uint64_t* f = flags + threadIdx.x;
+    unsigned long long t0 = 0, now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+      uint64_t v;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+      if (v >= epoch) break;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (now - t0 > kPushTimeoutNs) __trap();
+      __nanosleep(200);
+    }
+  }
+  __syncwarp();
+  __threadfence_system();
+}
+
 // Receiver side.  Every sender's block arrives ordered by (c, sender row), so the inserts of this shard in row order
 // are, for c = A..T, the (sender 0, c) run, the (sender 1, c) run, ...: a permutation known from the gathered counts.
 // Entry e = c * world + s of the plan: first output slot, first receive-buffer slot, and the constant that turns the
 // sender-local rank part into a local row.
 
-// One thread per insert, in output (row) order: find its run, fetch the wire item, write id / local row / the symbol
-// its row holds (the base before the suffix, '$' when the read starts here).
+// One thread per insert, in output (row) order: find its run, fetch the wire item, write id / local row / key / the
+// symbol its row holds (the base before the suffix, '$' when the read starts here) / the word that symbol came from.
 template <class PosT>
 __global__ void __launch_bounds__(256) shard_place_kernel(ReadAcc acc, const WireItem<PosT>* __restrict__ recv, uint64_t n,
                                                           uint32_t j, uint32_t uniform_len, RecvPlan plan,
                                                           uint32_t* __restrict__ ID2, PosT* __restrict__ NP2,
-                                                          uint8_t* __restrict__ SYM2, uint32_t* __restrict__ KEY2) {
+                                                          uint8_t* __restrict__ SYM2, uint32_t* __restrict__ KEY2,
+                                                          uint32_t* __restrict__ WIN2) {
   // the plan (at most 64 runs) in shared memory: a search with thread-dependent indices into kernel parameters would go
   // through a local-memory copy of the whole structure in every thread
   __shared__ uint64_t s_out0[kSendBuckets + 1], s_src0[kSendBuckets];
@@ -218,8 +306,22 @@ __global__ void __launch_bounds__(256) shard_place_kernel(ReadAcc acc, const Wir
   const uint32_t l = uniform_len ? uniform_len : acc.rv.len[id];
   ID2[d] = id;
   NP2[d] = (PosT)((long long)w.pos + s_K[lo]);
-  KEY2[d] = suffix_key(acc, id, l - j, l);  // the suffix inserted in pass j starts at column l - j
-  SYM2[d] = (l == j) ? (uint8_t)0 : (uint8_t)(acc.code(id, l - j - 1, l) + 1);
+  KEY2[d] = w.key;
+  if (l == j) {  // the read starts here: its row holds '$' and nothing follows
+    SYM2[d] = 0;
+    return;
+  }
+  // stored position of column l - j - 1 (the walk goes down through a forward read, up through a reversed one); its
+  // word travelled with the item unless the walk has just entered a new one
+  const uint32_t p = acc.reversed ? j : l - j - 1;
+  const bool fresh = j == 1 || (acc.reversed ? (p & 15u) == 0u : (p & 15u) == 15u);
+  uint32_t word = w.win;
+  if (fresh) {
+    const uint64_t wo = uniform_len ? (uint64_t)id * ((uniform_len + 15u) >> 4) : acc.rv.woff[id];  // reads start on words
+    word = acc.rv.words[wo + (p >> 4)];
+  }
+  SYM2[d] = (uint8_t)(((word >> (2 * (p & 15u))) & 3u) + 1u);
+  WIN2[d] = word;
 }
 
 template <class PosT>
@@ -227,17 +329,20 @@ struct Shard {
   int g = 0;
   uint64_t rows_final = 0;
   DevBuf<uint8_t> B0, B1, SYM, tmpDest;
-  DevBuf<uint32_t> ID0, ID1, KEY0, KEY1;
+  DevBuf<uint32_t> ID0, ID1, KEY0, KEY1, WIN0, WIN1;
   DevBuf<PosT> NP0, NP1, tmpPos;
-  DevBuf<WireItem<PosT> > send, recv;
+  DevBuf<WireItem<PosT> > send, recv;  // recv: NCCL transport only (the peer transport receives in the shard's region)
   DevBuf<uint16_t> RL;  // tile-local rank of every held item's row
   DevBuf<uint64_t> tiletot, scan_ws, part_ws, tile_k0, meta, kept, sym_total;
+  DevBuf<unsigned> push_done;
   uint8_t* B = nullptr;
   uint8_t* Bn = nullptr;
   uint32_t* ID = nullptr;
   uint32_t* ID2 = nullptr;
   uint32_t* KEY = nullptr;
   uint32_t* KEY2 = nullptr;
+  uint32_t* WIN = nullptr;
+  uint32_t* WIN2 = nullptr;
   PosT* NP = nullptr;
   PosT* NP2 = nullptr;
   uint64_t n_cur = 0, nt = 1, held = 0;
@@ -245,7 +350,7 @@ struct Shard {
   DevBuf<uint8_t> rle;
   uint64_t rle_bytes = 0;
 
-  void alloc(sgx_ctx* ctx, uint64_t N) {
+  void alloc(sgx_ctx* ctx, uint64_t N, bool peer) {
     const uint64_t padded = bwt_array_bytes(rows_final);
     B0.alloc(padded);
     B1.alloc(padded);
@@ -257,9 +362,12 @@ struct Shard {
     ID1.alloc(N);
     KEY0.alloc(N);
     KEY1.alloc(N);
+    WIN0.alloc(N);
+    WIN1.alloc(N);
     SGX_CUDA(cudaMemsetAsync(KEY0.p, 0, N * sizeof(uint32_t), ctx->stream));  // the sentinel rows: key of "$"
+    SGX_CUDA(cudaMemsetAsync(WIN0.p, 0, N * sizeof(uint32_t), ctx->stream));  // pass 1 fetches its own words
     send.alloc(N);
-    recv.alloc(N);
+    if (!peer) recv.alloc(N);
     NP0.alloc(N);
     NP1.alloc(N);
     tmpPos.alloc(N);
@@ -272,12 +380,16 @@ struct Shard {
     meta.alloc(kMetaN);
     kept.alloc(1);
     sym_total.alloc(1);
+    push_done.alloc(1);
+    SGX_CUDA(cudaMemsetAsync(push_done.p, 0, sizeof(unsigned), ctx->stream));
     B = B0.p;
     Bn = B1.p;
     ID = ID0.p;
     ID2 = ID1.p;
     KEY = KEY0.p;
     KEY2 = KEY1.p;
+    WIN = WIN0.p;
+    WIN2 = WIN1.p;
     NP = NP0.p;
     NP2 = NP1.p;
   }
@@ -292,11 +404,17 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
   const uint32_t uniform_len = reads->min_len == lmax ? lmax : 0;
   const int W = cm->world;
   const int nl = cm->n_local();
+  // Transport of the inserts: peer memory when every process could map every region, NCCL send/recv otherwise.  A slot
+  // holds the worst case, all N reads going from one sender to one receiver (the first passes, whose keys are mostly
+  // '$', do send everything to a few shards).
+  const uint64_t slot_cap = N;
+  const size_t slot_bytes = (size_t)slot_cap * sizeof(WireItem<PosT>);
+  const bool peer = comm_peer_reserve(cm, kPeerHeaderBytes + 2 * (size_t)W * slot_bytes);
   std::vector<Shard<PosT> > sh(nl);
   for (int li = 0; li < nl; ++li) {
     sh[li].g = cm->shard_of(li);
     sh[li].rows_final = rows_final[sh[li].g];
-    sh[li].alloc(ctx, N);
+    sh[li].alloc(ctx, N, peer);
   }
   std::vector<uint64_t> n_cur_all(W, 0);
   n_cur_all[0] = N;
@@ -319,15 +437,17 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
   const char* tr = getenv("SGX_SHARD_TRACE");
   const bool trace = tr && tr[0] == '1';
   KernelClock k_send(ctx->stream), k_gather(ctx->stream), k_xchg(ctx->stream), k_recv(ctx->stream);
+  double host_wait_ms = 0;
 #define SGX_TRACE_TICK(clock) \
   if (trace) (clock).tick()
   std::vector<uint64_t> M((size_t)W * kMetaN), cntm((size_t)W * W), soff((size_t)W * W), roff((size_t)W * W);
   std::vector<const uint64_t*> meta_ptr(nl);
   std::vector<const void*> send_ptr(nl);
   std::vector<void*> recv_ptr(nl);
+  const unsigned push_grid_max = (unsigned)ctx->sm_count * 8;
   for (uint32_t j = 1; j <= lmax; ++j) {
     // ---- sender side: ranks + destinations, bucket sizes; the sizes travel (all-gather, copy to the host) while
-    //      the scatter into the send buffer runs
+    //      the scatter into the send buffer and the push into the peers' regions run
     SGX_TRACE_TICK(k_send);
     for (int li = 0; li < nl; ++li) {
       Shard<PosT>& s = sh[li];
@@ -347,25 +467,51 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
     SGX_TRACE_TICK(k_send);
     SGX_TRACE_TICK(k_gather);
     comm_allgather_u64_begin(cm, meta_ptr.data(), kMetaN);
+    const uint64_t epoch = peer ? comm_next_epoch(cm) : 0;
+    const size_t parity_off = kPeerHeaderBytes + (size_t)(epoch & 1) * W * slot_bytes;
     for (int li = 0; li < nl; ++li) {
       Shard<PosT>& s = sh[li];
-      if (!s.held) continue;
-      DestDigit dg{s.tmpDest.p};
-      SendMove<PosT> mv{s.ID, s.tmpPos.p, s.send.p};
-      partition_scatter<kSendBuckets, DestDigit, SendMove<PosT> >(ctx, dg, mv, s.held, s.part_ws.p);
+      if (s.held) {
+        DestDigit dg{s.tmpDest.p};
+        SendMove<PosT> mv{s.ID, s.tmpPos.p, s.SYM.p, s.KEY, s.WIN, s.send.p};
+        partition_scatter<kSendBuckets, DestDigit, SendMove<PosT> >(ctx, dg, mv, s.held, s.part_ws.p);
+      }
+      if (peer) {  // a shard with nothing to send still raises its flags
+        PushPlan pp;
+        memset(&pp, 0, sizeof(pp));
+        pp.world = W;
+        for (int d = 0; d < W; ++d) {
+          pp.slot[d] = cm->peer_addr[d] + parity_off + (size_t)s.g * slot_bytes;
+          pp.flag[d] = comm_peer_flag(cm, d, s.g);
+        }
+        const unsigned grid = s.held ? std::min(grid_for(s.held, 256), push_grid_max) : 1u;
+        SGX_LAUNCH(ctx, (shard_push_kernel<PosT>), grid, 256, 0, (const WireItem<PosT>*)s.send.p, (const uint64_t*)s.part_ws.p,
+                   part_tiles(s.held ? s.held : 1), s.held ? 1 : 0, (const uint64_t*)s.kept.p, pp, epoch, s.push_done.p);
+      }
     }
     SGX_TRACE_TICK(k_gather);
+    const double hw0 = trace ? now_ms() : 0;
     comm_allgather_u64_end(cm, kMetaN, M.data());
+    if (trace) host_wait_ms += now_ms() - hw0;
     std::vector<uint64_t> n_in(W, 0), n_new(W, 0), first_row(W + 1, 0);
     const uint64_t moved = shard_pass_counts(M.data(), W, n_cur_all.data(), cntm.data(), soff.data(), roff.data(), n_in.data(),
                                              n_new.data(), first_row.data());
     if (moved == 0) break;  // every read has ended
-    for (int li = 0; li < nl; ++li) {
-      send_ptr[li] = sh[li].send.p;
-      recv_ptr[li] = sh[li].recv.p;
-    }
     SGX_TRACE_TICK(k_xchg);
-    comm_alltoallv(cm, send_ptr.data(), recv_ptr.data(), sizeof(WireItem<PosT>), cntm.data(), soff.data(), roff.data());
+    if (peer) {
+      // the receive "buffer" of shard d is the current parity of its region: sender s's block starts at slot s
+      for (int d = 0; d < W; ++d)
+        for (int q = 0; q < W; ++q) roff[d * W + q] = (uint64_t)q * slot_cap;
+      for (int li = 0; li < nl; ++li)
+        if (n_in[sh[li].g])
+          SGX_LAUNCH(ctx, shard_wait_kernel, 1, 32, 0, (const uint64_t*)cm->peer_mine[li], W, epoch);
+    } else {
+      for (int li = 0; li < nl; ++li) {
+        send_ptr[li] = sh[li].send.p;
+        recv_ptr[li] = sh[li].recv.p;
+      }
+      comm_alltoallv(cm, send_ptr.data(), recv_ptr.data(), sizeof(WireItem<PosT>), cntm.data(), soff.data(), roff.data());
+    }
     SGX_TRACE_TICK(k_xchg);
     SGX_TRACE_TICK(k_recv);
 
@@ -379,8 +525,9 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
         RecvPlan plan;
         const uint64_t out_run = shard_recv_plan(M.data(), W, g, N, roff.data(), first_row.data(), &plan);
         SGX_REQUIRE(out_run == held_new, SGX_ECUDA, "sharded index: receive plan does not cover the received inserts");
-        SGX_LAUNCH(ctx, (shard_place_kernel<PosT>), grid_for(held_new, 256), 256, 0, acc, (const WireItem<PosT>*)s.recv.p,
-                   held_new, j, uniform_len, plan, s.ID2, s.NP2, s.SYM.p, s.KEY2);
+        const WireItem<PosT>* rbuf = peer ? (const WireItem<PosT>*)(cm->peer_mine[li] + parity_off) : (const WireItem<PosT>*)s.recv.p;
+        SGX_LAUNCH(ctx, (shard_place_kernel<PosT>), grid_for(held_new, 256), 256, 0, acc, rbuf, held_new, j, uniform_len, plan,
+                   s.ID2, s.NP2, s.SYM.p, s.KEY2, s.WIN2);
         const uint64_t rows_new = s.n_cur + held_new;
         const uint64_t ntiles = (rows_new + kMergeTile - 1) / kMergeTile;
         SGX_LAUNCH(ctx, (bcr_tile_bounds_kernel<PosT>), grid_for(held_new + 1, 256), 256, 0, (const PosT*)s.NP2, held_new,
@@ -397,6 +544,7 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
         std::swap(s.ID, s.ID2);
         std::swap(s.NP, s.NP2);
         std::swap(s.KEY, s.KEY2);
+        std::swap(s.WIN, s.WIN2);
         s.n_cur = rows_new;
         s.nt = ntiles;
       }
@@ -412,8 +560,9 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
   if (trace) {
     SGX_CUDA(cudaStreamSynchronize(ctx->stream));
     // an unmatched tick is left when the loop ended on `moved == 0`; total_ms() only sums complete pairs
-    fprintf(stderr, "[sgx shard %d/%d] passes: sender %.2f ms, counts gather+scatter %.2f ms, all-to-all %.2f ms, receiver %.2f ms (merge %.2f ms)\n",
-            cm->shard_of(0), W, k_send.total_ms(), k_gather.total_ms(), k_xchg.total_ms(), k_recv.total_ms(), k_merge.total_ms());
+    fprintf(stderr, "[sgx shard %d/%d] %s transport, passes: sender %.2f ms, scatter+push %.2f ms, %s %.2f ms, receiver %.2f ms (merge %.2f ms); host waited %.2f ms for counts\n",
+            cm->shard_of(0), W, peer ? "peer-memory" : "NCCL", k_send.total_ms(), k_gather.total_ms(), peer ? "flag wait" : "all-to-all",
+            k_xchg.total_ms(), k_recv.total_ms(), k_merge.total_ms(), host_wait_ms);
   }
 #undef SGX_TRACE_TICK
 
