@@ -506,13 +506,17 @@ def main():
             return list(ctx.index_build_pair(rd, order=api.ORDER_SAIS2, copy=copy))
         if sub_comm is None:
             return [ctx.index_build(rd, order=api.ORDER_SAIS2, reversed=bool(group), copy=copy)]
-        return [ctx.index_build_sharded(sub_comm, rd, order=api.ORDER_SAIS2, reversed=bool(group), copy=copy)]
+        # no gather: every rank of the group ends up with the run bytes of its own shard (sgx_index_build_sharded_segments)
+        return [ctx.index_build_sharded_segments(sub_comm, rd, order=api.ORDER_SAIS2, reversed=bool(group), copy=copy)]
 
     res = build_index(r_dev)  # warm-up + parity at full size
     refs = [fi, ri] if world == 1 else [ri if group else fi]
     for o, ref_idx in zip(res, refs):
         assert np.array_equal(o.sai, ref_idx.sai)
-        if sub_rank == 0:
+        if sub_comm is not None:  # this rank's segment against its place in the single-GPU build's run bytes
+            assert o.n_runs_total == len(ref_idx.runs) and \
+                np.array_equal(o.runs, ref_idx.runs[o.seg_offset:o.seg_offset + len(o.runs)]), "index segment differs from the single-GPU build"
+        elif sub_rank == 0:
             assert np.array_equal(o.runs, ref_idx.runs), "index differs from the single-GPU build"
     if golden:
         parity["timed_index_build_identical_to_reference"] = True  # == the setup build, which matched the hashes above
@@ -779,7 +783,7 @@ def cfg4_object(args, ctx, api, formats, torch, dist, rank, world, local, barrie
             return list(ctx.index_build_pair(r_dev, order=api.ORDER_SAIS2, copy=False))
         if comm is None:
             return [ctx.index_build(r_dev, order=api.ORDER_SAIS2, reversed=bool(group), copy=False)]
-        return [ctx.index_build_sharded(comm, r_dev, order=api.ORDER_SAIS2, reversed=bool(group), copy=False)]
+        return [ctx.index_build_sharded_segments(comm, r_dev, order=api.ORDER_SAIS2, reversed=bool(group), copy=False)]
 
     times = []
     mine = []
@@ -795,13 +799,36 @@ def cfg4_object(args, ctx, api, formats, torch, dist, rank, world, local, barrie
     out["index_ms_runs"] = times
     out["index_gbases_per_s"] = n * L / (out["index_ms"] * 1e-3) / 1e9
     out["index_path"] = "one group of %d GPU(s) per strand, %d of them building%s" % (
-        group_size, sub_world, " (rows sharded by k-mer bucket over NCCL)" if sub_world > 1 else " (strand below the sharding threshold)")
+        group_size, sub_world, " (rows sharded by k-mer bucket, inserts exchanged through peer memory over NVLink)" if sub_world > 1 else " (strand below the sharding threshold)")
     # the finished indices travel through tmpfs: run bytes are complete on each group's leader, .sai everywhere in the group
     runs_path, sai_path = "/dev/shm/siga_b200_" + cfg + "_runs_%d.npy", "/dev/shm/siga_b200_" + cfg + "_sai_%d.npy"
+    seg_path = "/dev/shm/siga_b200_" + cfg + "_seg_%d_%d.npy"
+    if comm is not None:  # every rank of a strand group holds the run bytes of its own shard (nothing was gathered)
+        np.save(seg_path % (group, sub_rank), mine[0].runs)
+        seg_at = torch.tensor([mine[0].seg_offset, len(mine[0].runs), mine[0].n_runs_total], dtype=torch.int64, device="cuda")
+    else:
+        seg_at = torch.zeros(3, dtype=torch.int64, device="cuda")
+    seg_all = [seg_at]
+    if world > 1:
+        seg_all = [torch.zeros(3, dtype=torch.int64, device="cuda") for _ in range(world)]
+        dist.all_gather(seg_all, seg_at)
+    barrier()
     if sub_rank == 0:
         for k, o in enumerate(mine):
             rv = k if world == 1 else group
-            np.save(runs_path % rv, o.runs)
+            if comm is not None:  # the group's segments laid end to end are the run bytes of the strand
+                parts, at = [], 0
+                for q in range(sub_world):
+                    off_q, len_q, tot_q = (int(x) for x in seg_all[group * group_size + q].tolist())
+                    assert off_q == at, "%s: the shards' segments do not tile the run bytes" % cfg
+                    parts.append(np.load(seg_path % (group, q)))
+                    assert len(parts[-1]) == len_q
+                    at += len_q
+                assert at == tot_q
+                np.save(runs_path % rv, np.concatenate(parts))
+                del parts
+            else:
+                np.save(runs_path % rv, o.runs)
             np.save(sai_path % rv, o.sai)
     n_suffixes = n * (L + 1)
     for o in mine:
@@ -868,7 +895,8 @@ def cfg4_object(args, ctx, api, formats, torch, dist, rank, world, local, barrie
         ctx.free_comm(comm)
     del reads, flat
     if rank == 0:
-        for f in [shm] + [runs_path % rv for rv in (0, 1)] + [sai_path % rv for rv in (0, 1)]:
+        for f in [shm] + [runs_path % rv for rv in (0, 1)] + [sai_path % rv for rv in (0, 1)] + \
+                [seg_path % (gq, q) for gq in (0, 1) for q in range(group_size)]:
             try:
                 os.remove(f)
             except OSError:

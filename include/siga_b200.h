@@ -101,6 +101,8 @@ typedef struct sgx_index_out {
   uint64_t merge_launches; /* launches of the dominant (merge) kernel                                          */
   double ms_merge;     /* device time spent in the merge kernel                                                */
   uint64_t merge_bytes;/* bytes it read + wrote (algorithmic traffic of the merge passes)                      */
+  uint64_t seg_offset; /* sgx_index_build_sharded_segments: `rle` holds seg_bytes run bytes that belong at byte   */
+  uint64_t seg_bytes;  /* seg_offset of the n_runs run bytes of the whole index; elsewhere 0 and n_runs          */
 } sgx_index_out;
 
 /*
@@ -147,6 +149,16 @@ int sgx_comm_rank(const sgx_comm* comm);
  */
 int sgx_index_build_sharded(sgx_ctx* ctx, sgx_comm* comm, const sgx_reads* reads, int order, int reversed,
                             sgx_index_out* out);
+/*
+ * Same build without the final concatenation on rank 0: every rank gets the run bytes of its own shard
+ * (`out->rle`, `out->seg_bytes` bytes) and the place they take in the index (`out->seg_offset`; `out->n_runs` is the
+ * length of the whole).  The segments of ranks 0, 1, ... laid end to end are the run bytes sgx_index_build returns, so
+ * the ranks can write one .bwt file together (header by rank 0, every segment with pwrite at 30 + seg_offset) and
+ * nothing is gathered.  `out->sai` on every rank.  With a local communicator the one process holds all shards and the
+ * result is that of sgx_index_build_sharded.
+ */
+int sgx_index_build_sharded_segments(sgx_ctx* ctx, sgx_comm* comm, const sgx_reads* reads, int order, int reversed,
+                                     sgx_index_out* out);
 
 /* ---- FM-index (`FMIndex::load`, rank queries) ----------------------------------------------------------- */
 

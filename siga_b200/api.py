@@ -22,7 +22,7 @@ ABI_SYMBOLS = [
     "sgx_reads_pack", "sgx_reads_pack_async", "sgx_reads_wait", "sgx_reads_free", "sgx_reads_count", "sgx_reads_bases",
     "sgx_index_build", "sgx_index_build_pair", "sgx_index_out_free",
     "sgx_comm_unique_id", "sgx_comm_init", "sgx_comm_init_local", "sgx_comm_free", "sgx_comm_world", "sgx_comm_rank",
-    "sgx_index_build_sharded", "sgx_edges_gather",
+    "sgx_index_build_sharded", "sgx_index_build_sharded_segments", "sgx_edges_gather",
     "sgx_fm_create", "sgx_fm_free", "sgx_fm_attach_reads", "sgx_fm_length", "sgx_fm_pred", "sgx_fm_occ", "sgx_fm_count",
     "sgx_overlap_batch", "sgx_overlap_host", "sgx_hits_free", "sgx_overlap_edges", "sgx_edges_free",
     "sgx_correct_batch", "sgx_corrected_free",
@@ -41,7 +41,8 @@ class _IndexOut(ctypes.Structure):
                 ("rle", ctypes.POINTER(ctypes.c_uint8)), ("sai", ctypes.POINTER(ctypes.c_uint32)),
                 ("ms_total", ctypes.c_double), ("ms_sort", ctypes.c_double), ("ms_bcr", ctypes.c_double),
                 ("ms_emit", ctypes.c_double), ("launches", ctypes.c_uint64), ("merge_launches", ctypes.c_uint64),
-                ("ms_merge", ctypes.c_double), ("merge_bytes", ctypes.c_uint64)]
+                ("ms_merge", ctypes.c_double), ("merge_bytes", ctypes.c_uint64), ("seg_offset", ctypes.c_uint64),
+                ("seg_bytes", ctypes.c_uint64)]
 
 
 class _Hits(ctypes.Structure):
@@ -118,6 +119,7 @@ def load_library():
     lib.sgx_comm_world.argtypes = [vp]
     lib.sgx_comm_rank.argtypes = [vp]
     lib.sgx_index_build_sharded.argtypes = [vp, vp, vp, i32, i32, ctypes.POINTER(_IndexOut)]
+    lib.sgx_index_build_sharded_segments.argtypes = [vp, vp, vp, i32, i32, ctypes.POINTER(_IndexOut)]
     lib.sgx_fm_create.argtypes = [vp, vp, u64, u64, ctypes.POINTER(vp)]
     lib.sgx_fm_free.argtypes = [vp]
     lib.sgx_fm_free.restype = None
@@ -352,6 +354,19 @@ class Context:
             o.n_runs = 0
         res = self._index_result(o, copy)
         res.n_runs_total = n_runs
+        return res
+
+    def index_build_sharded_segments(self, comm, reads, order=ORDER_SAIS2, reversed=False, copy=True):
+        """Collective bucket-sharded build without the final gather: `runs` holds this rank's segment of the run bytes,
+        which belongs at byte `seg_offset` of the `n_runs_total` bytes of the whole index; `sai` everywhere."""
+        o = _IndexOut()
+        self._check(self.lib.sgx_index_build_sharded_segments(self.h, comm, reads, int(order), 1 if reversed else 0,
+                                                              ctypes.byref(o)))
+        n_runs, seg_offset, seg_bytes = int(o.n_runs), int(o.seg_offset), int(o.seg_bytes)
+        o.n_runs = seg_bytes  # IndexResult views n_runs bytes of rle
+        res = self._index_result(o, copy)
+        res.n_runs_total = n_runs
+        res.seg_offset = seg_offset
         return res
 
     # ---- FM-index

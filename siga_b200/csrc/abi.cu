@@ -375,7 +375,17 @@ int sgx_index_build_sharded(sgx_ctx* ctx, sgx_comm* comm, const sgx_reads* reads
   SGX_ENTRY_BEGIN(ctx)
   SGX_REQUIRE(order == SGX_ORDER_SAIS || order == SGX_ORDER_SAIS2, SGX_EINVAL, "sgx_index_build_sharded: unknown order");
   reads_settle(reads);
-  index_build_sharded(ctx, comm, reads, order, reversed != 0, out);
+  index_build_sharded(ctx, comm, reads, order, reversed != 0, false, out);
+  SGX_ENTRY_END(ctx)
+}
+
+int sgx_index_build_sharded_segments(sgx_ctx* ctx, sgx_comm* comm, const sgx_reads* reads, int order, int reversed,
+                            sgx_index_out* out) {
+  if (!ctx || !comm || !reads || !out || comm->ctx != ctx) return SGX_EINVAL;
+  SGX_ENTRY_BEGIN(ctx)
+  SGX_REQUIRE(order == SGX_ORDER_SAIS || order == SGX_ORDER_SAIS2, SGX_EINVAL, "sgx_index_build_sharded_segments: unknown order");
+  reads_settle(reads);
+  index_build_sharded(ctx, comm, reads, order, reversed != 0, true, out);
   SGX_ENTRY_END(ctx)
 }
 

@@ -477,6 +477,35 @@ bool write_bwt(const std::string& path, uint64_t n_strings, uint64_t n_suffixes,
   return fclose(f) == 0 && ok;
 }
 
+bool write_bwt_segment(const std::string& path, uint64_t n_strings, uint64_t n_suffixes, uint64_t n_runs, const uint8_t* seg,
+                       uint64_t seg_offset, uint64_t seg_bytes, bool header) {
+  const int fd = open(path.c_str(), O_WRONLY | O_CREAT, 0644);
+  if (fd < 0) return false;
+  bool ok = true;
+  auto put = [&](const void* p, uint64_t n, uint64_t at) {
+    const uint8_t* b = (const uint8_t*)p;
+    while (n && ok) {
+      const ssize_t w = pwrite(fd, b, (size_t)std::min<uint64_t>(n, (uint64_t)1 << 30), (off_t)at);
+      if (w <= 0) ok = false;
+      else b += w, n -= (uint64_t)w, at += (uint64_t)w;
+    }
+  };
+  if (header) {
+    uint8_t h[30];
+    const uint16_t magic = 0xCACA;
+    const int32_t flag = 0;  // BWF_NOFMI
+    memcpy(h, &magic, 2);
+    memcpy(h + 2, &n_strings, 8);
+    memcpy(h + 10, &n_suffixes, 8);
+    memcpy(h + 18, &n_runs, 8);
+    memcpy(h + 26, &flag, 4);
+    ok = ftruncate(fd, (off_t)(30 + n_runs)) == 0;
+    put(h, 30, 0);
+  }
+  put(seg, seg_bytes, 30 + seg_offset);
+  return close(fd) == 0 && ok;
+}
+
 bool write_sai(const std::string& path, const uint32_t* ids, uint64_t n) {
   FILE* f = fopen(path.c_str(), "wb");
   if (!f) return false;

@@ -85,6 +85,11 @@ bool read_sequences_serial(const std::string& path, ReadSet* out, std::string* e
 std::string stem(const std::string& path);
 
 bool write_bwt(const std::string& path, uint64_t n_strings, uint64_t n_suffixes, const uint8_t* runs, uint64_t n_runs);
+// One .bwt file written by several processes together (sgx_index_build_sharded_segments): each writes its `seg_bytes` run
+// bytes at their place behind the 30-byte header; the one with `header` set also writes the header and gives the file its
+// final length (so a longer stale file of the same name does not survive).  No truncation on open: the writers race.
+bool write_bwt_segment(const std::string& path, uint64_t n_strings, uint64_t n_suffixes, uint64_t n_runs, const uint8_t* seg,
+                       uint64_t seg_offset, uint64_t seg_bytes, bool header);
 bool write_sai(const std::string& path, const uint32_t* ids, uint64_t n);
 bool read_bwt(const std::string& path, uint64_t* n_strings, uint64_t* n_suffixes, std::vector<uint8_t>* runs);
 bool read_sai(const std::string& path, std::vector<uint32_t>* ids);

@@ -698,6 +698,26 @@ int cmd_index(int argc, char** argv) {
       wrote[pass] = a && b;
     });
   };
+  // sharded build: every GPU of the strand group writes the run bytes of its own shard into the one .bwt file
+  // (sgx_index_build_sharded_segments: nothing is gathered); the group's first rank adds the header and the .sai
+  auto start_segment_writer = [&](int pass, bool leader) {
+    sgx_index_out& out = outs[pass];
+    const std::string sa = output + (pass == 0 ? ".sai" : ".rsai"), bw = output + (pass == 0 ? ".bwt" : ".rbwt");
+    if (leader)
+      info("%s: %llu strings, %llu suffixes, %llu runs; device %.1f ms (read order %.1f, column passes %.1f, run-length coding + copy "
+           "out %.1f; %llu kernel launches)", bw.c_str(), (unsigned long long)out.n_strings, (unsigned long long)out.n_suffixes,
+           (unsigned long long)out.n_runs, out.ms_total, out.ms_sort, out.ms_bcr, out.ms_emit, (unsigned long long)out.launches);
+    writers[pass] = std::thread([&outs, &wrote, pass, sa, bw, leader]() {
+      const sgx_index_out& o2 = outs[pass];
+      bool a = true, b = false;
+      std::thread t([&]() {
+        if (leader) a = write_sai(sa, o2.sai, o2.n_strings);
+      });
+      b = write_bwt_segment(bw, o2.n_strings, o2.n_suffixes, o2.n_runs, o2.rle, o2.seg_offset, o2.seg_bytes, leader);
+      t.join();
+      wrote[pass] = a && b;
+    });
+  };
   if (world == 1 && fwd && rev) {
     info("building forward and reverse index side by side on device %d", o.device);
     rc = sgx_index_build_pair(ctx, reads, order, &outs[0], &outs[1]);
@@ -711,15 +731,19 @@ int cmd_index(int argc, char** argv) {
       if (sub_rank == 0)
         info("building %s index on %d GPU(s) from device %d", pass == 0 ? "forward" : "reverse", sub_world, o.device + my);
       sgx_index_out& out = outs[pass];
-      rc = comm ? sgx_index_build_sharded(ctx, comm, reads, order, pass, &out) : sgx_index_build(ctx, reads, order, pass, &out);
+      rc = comm ? sgx_index_build_sharded_segments(ctx, comm, reads, order, pass, &out) : sgx_index_build(ctx, reads, order, pass, &out);
       if (rc != SGX_OK) {
         for (auto& w : writers)
           if (w.joinable()) w.join();
-        fail(ctx, comm ? "sgx_index_build_sharded" : "sgx_index_build", rc);
+        fail(ctx, comm ? "sgx_index_build_sharded_segments" : "sgx_index_build", rc);
         if (my) _exit(1);
         return -1;
       }
-      if (sub_rank) {  // only a group's first rank holds the concatenated run bytes and writes the files
+      if (comm) {
+        start_segment_writer(pass, sub_rank == 0);
+        continue;
+      }
+      if (sub_rank) {  // a strand below the sharding threshold is built by its group's first rank alone
         sgx_index_out_free(&out);
         continue;
       }

@@ -290,6 +290,7 @@ void index_build(sgx_ctx* ctx, const sgx_reads* reads, int order, bool reversed,
   out->n_strings = N;
   out->n_suffixes = S;
   out->n_runs = n_bytes;
+  out->seg_bytes = n_bytes;
   out->rle = (uint8_t*)pinned_get(ctx, n_bytes ? n_bytes : 1);
   out->sai = (uint32_t*)pinned_get(ctx, N * sizeof(uint32_t));
   SGX_CUDA(cudaMemcpyAsync(out->rle, d_rle.p, n_bytes, cudaMemcpyDeviceToHost, ctx->stream));

@@ -214,35 +214,105 @@ struct PushPlan {
   int world;
 };
 
+// Scatter half of the send partition, fused with the push.  Same tile walk as part_scatter_kernel (prims.cuh) and the
+// same stable (destination, c) order, but the tile's 2048 wire items are first laid out in bucket order in shared
+// memory and then written by consecutive threads: every run of one bucket becomes one stretch of coalesced 16-byte
+// stores straight into the destination's slot (a warp of the plain scatter spreads its 32 items over up to 16 buckets,
+// which is tolerable in local HBM and wasteful over NVLink).  No send buffer, no second pass over the items.
 template <class PosT>
-__global__ void __launch_bounds__(256) shard_push_kernel(const WireItem<PosT>* __restrict__ send,
-                                                         const uint64_t* __restrict__ bucket_start, uint32_t ptiles, int have_items,
-                                                         const uint64_t* __restrict__ kept, PushPlan pp, uint64_t epoch,
-                                                         unsigned* __restrict__ done) {
-  __shared__ uint64_t s_start[kMaxShards + 1];
+__global__ void __launch_bounds__(kPartThreads) shard_send_kernel(const uint8_t* __restrict__ tmpDest, const uint32_t* __restrict__ ID,
+                                                                  const PosT* __restrict__ tmpPos, const uint8_t* __restrict__ SYM,
+                                                                  const uint32_t* __restrict__ KEY, const uint32_t* __restrict__ WIN,
+                                                                  uint64_t n, const uint64_t* __restrict__ tileoff, uint32_t ntiles,
+                                                                  PushPlan pp, uint64_t epoch, unsigned* __restrict__ done) {
+  extern __shared__ __align__(16) uint8_t send_smem[];
+  WireItem<PosT>* stage = (WireItem<PosT>*)send_smem;  // kPartTile items
+  __shared__ uint32_t wc[kPartThreads / 32][kSendBuckets];
+  __shared__ uint32_t boff[kSendBuckets + 1];
+  __shared__ uint64_t gbase[kSendBuckets];  // slot-relative position of the tile's first item of bucket e
+  __shared__ uint8_t bkt[kPartTile];
   __shared__ WireItem<PosT>* s_slot[kMaxShards];
-  const int W = pp.world;
-  if ((int)threadIdx.x <= W) {
-    uint64_t v = 0;
-    if (have_items) v = (int)threadIdx.x < W ? bucket_start[(uint64_t)(4 * threadIdx.x) * ptiles] : *kept;
-    s_start[threadIdx.x] = v;
-  }
-  if ((int)threadIdx.x < W) s_slot[threadIdx.x] = (WireItem<PosT>*)pp.slot[threadIdx.x];
+  for (int i = threadIdx.x; i < (kPartThreads / 32) * kSendBuckets; i += kPartThreads) (&wc[0][0])[i] = 0;
+  if ((int)threadIdx.x < pp.world) s_slot[threadIdx.x] = (WireItem<PosT>*)pp.slot[threadIdx.x];
   __syncthreads();
-  const uint64_t n = s_start[W];
-  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (uint64_t)gridDim.x * blockDim.x) {
-    int d = 0;
-    for (int i = 1; i < W; ++i) d += q >= s_start[i] ? 1 : 0;
-    s_slot[d][q - s_start[d]] = send[q];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint64_t wbase = (uint64_t)blockIdx.x * kPartTile + (uint64_t)w * (kPartRounds * 32);
+  int dg[kPartRounds];
+  uint32_t lr[kPartRounds];
+#pragma unroll
+  for (int r = 0; r < kPartRounds; ++r) {
+    const uint64_t k = wbase + r * 32 + lane;
+    int d = kSendBuckets;
+    if (k < n) d = (int)tmpDest[k];  // 255: the read has ended, nothing to send
+    dg[r] = d;
+    lr[r] = 0;
+    const unsigned act = __ballot_sync(0xffffffffu, d < kSendBuckets);
+    if (d < kSendBuckets) {
+      const unsigned m = __match_any_sync(act, d);
+      const uint32_t before = wc[w][d];
+      lr[r] = before + __popc(m & ((1u << lane) - 1u));
+      __syncwarp(m);
+      if (lane == __ffs(m) - 1) wc[w][d] = before + __popc(m);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (threadIdx.x < kSendBuckets) {
+    const int e = threadIdx.x;
+    uint32_t run = 0;
+#pragma unroll
+    for (int q = 0; q < kPartThreads / 32; ++q) {
+      const uint32_t t = wc[q][e];
+      wc[q][e] = run;
+      run += t;
+    }
+    boff[e + 1] = run;  // bucket total of the tile, scanned below
+    gbase[e] = n ? tileoff[(uint64_t)e * ntiles + blockIdx.x] - tileoff[(uint64_t)(e & ~3) * ntiles] : 0;
+  }
+  __syncthreads();
+  if (w == 0) {  // exclusive scan of the 64 bucket totals (two per lane)
+    const uint32_t a = boff[2 * lane + 1], b2 = boff[2 * lane + 2];
+    uint32_t x = a + b2;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    __syncwarp();
+    boff[2 * lane + 1] = x - b2;
+    boff[2 * lane + 2] = x;
+    if (lane == 0) boff[0] = 0;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kPartRounds; ++r) {
+    const int d = dg[r];
+    if (d < kSendBuckets) {
+      const uint64_t k = wbase + r * 32 + lane;
+      const uint32_t t = boff[d] + wc[w][d] + lr[r];
+      WireItem<PosT> it;
+      it.pos = tmpPos[k];
+      it.id = ID[k];
+      it.key = (uint32_t)SYM[k] * kKeyTop + KEY[k] / 5u;
+      it.win = WIN[k];
+      stage[t] = it;
+      bkt[t] = (uint8_t)d;
+    }
+  }
+  __syncthreads();
+  const uint32_t total = boff[kSendBuckets];
+  for (uint32_t t = threadIdx.x; t < total; t += kPartThreads) {
+    const int e = bkt[t];
+    s_slot[e >> 2][gbase[e] + (t - boff[e])] = stage[t];
   }
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned t = atomicAdd(done, 1u);
     if (t == gridDim.x - 1) {
-      *done = 0;  // the next push on this stream starts from zero
+      *done = 0;  // the next pass on this stream starts from zero
       __threadfence_system();
-      for (int d = 0; d < W; ++d) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(pp.flag[d]), "l"(epoch) : "memory");
+      for (int d = 0; d < pp.world; ++d) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(pp.flag[d]), "l"(epoch) : "memory");
     }
   }
 }
@@ -331,7 +401,7 @@ struct Shard {
   DevBuf<uint8_t> B0, B1, SYM, tmpDest;
   DevBuf<uint32_t> ID0, ID1, KEY0, KEY1, WIN0, WIN1;
   DevBuf<PosT> NP0, NP1, tmpPos;
-  DevBuf<WireItem<PosT> > send, recv;  // recv: NCCL transport only (the peer transport receives in the shard's region)
+  DevBuf<WireItem<PosT> > send, recv;  // NCCL transport only (the peer transport scatters into the receivers' regions)
   DevBuf<uint16_t> RL;  // tile-local rank of every held item's row
   DevBuf<uint64_t> tiletot, scan_ws, part_ws, tile_k0, meta, kept, sym_total;
   DevBuf<unsigned> push_done;
@@ -366,8 +436,10 @@ struct Shard {
     WIN1.alloc(N);
     SGX_CUDA(cudaMemsetAsync(KEY0.p, 0, N * sizeof(uint32_t), ctx->stream));  // the sentinel rows: key of "$"
     SGX_CUDA(cudaMemsetAsync(WIN0.p, 0, N * sizeof(uint32_t), ctx->stream));  // pass 1 fetches its own words
-    send.alloc(N);
-    if (!peer) recv.alloc(N);
+    if (!peer) {
+      send.alloc(N);
+      recv.alloc(N);
+    }
     NP0.alloc(N);
     NP1.alloc(N);
     tmpPos.alloc(N);
@@ -398,7 +470,8 @@ struct Shard {
 template <class PosT>
 static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, const ReadAcc& acc, const uint32_t* d_sord,
                           const ShardBounds& bounds, const std::vector<uint64_t>& rows_final, sgx_index_out* out,
-                          KernelClock& k_merge, EventTimer& t_bcr, EventTimer& t_emit, uint8_t** rle_host, uint64_t* rle_total) {
+                          KernelClock& k_merge, EventTimer& t_bcr, EventTimer& t_emit, bool segments, uint8_t** rle_host,
+                          uint64_t* rle_total, uint64_t* seg_offset, uint64_t* seg_len) {
   const uint64_t N = reads->n;
   const uint32_t lmax = reads->max_len;
   const uint32_t uniform_len = reads->min_len == lmax ? lmax : 0;
@@ -444,7 +517,9 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
   std::vector<const uint64_t*> meta_ptr(nl);
   std::vector<const void*> send_ptr(nl);
   std::vector<void*> recv_ptr(nl);
-  const unsigned push_grid_max = (unsigned)ctx->sm_count * 8;
+  const size_t send_smem = (size_t)kPartTile * sizeof(WireItem<PosT>);
+  if (peer)
+    SGX_CUDA(cudaFuncSetAttribute(shard_send_kernel<PosT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)send_smem));
   for (uint32_t j = 1; j <= lmax; ++j) {
     // ---- sender side: ranks + destinations, bucket sizes; the sizes travel (all-gather, copy to the host) while
     //      the scatter into the send buffer and the push into the peers' regions run
@@ -471,23 +546,26 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
     const size_t parity_off = kPeerHeaderBytes + (size_t)(epoch & 1) * W * slot_bytes;
     for (int li = 0; li < nl; ++li) {
       Shard<PosT>& s = sh[li];
-      if (s.held) {
-        DestDigit dg{s.tmpDest.p};
-        SendMove<PosT> mv{s.ID, s.tmpPos.p, s.SYM.p, s.KEY, s.WIN, s.send.p};
-        partition_scatter<kSendBuckets, DestDigit, SendMove<PosT> >(ctx, dg, mv, s.held, s.part_ws.p);
-      }
-      if (peer) {  // a shard with nothing to send still raises its flags
-        PushPlan pp;
-        memset(&pp, 0, sizeof(pp));
-        pp.world = W;
-        for (int d = 0; d < W; ++d) {
-          pp.slot[d] = cm->peer_addr[d] + parity_off + (size_t)s.g * slot_bytes;
-          pp.flag[d] = comm_peer_flag(cm, d, s.g);
+      if (!peer) {
+        if (s.held) {
+          DestDigit dg{s.tmpDest.p};
+          SendMove<PosT> mv{s.ID, s.tmpPos.p, s.SYM.p, s.KEY, s.WIN, s.send.p};
+          partition_scatter<kSendBuckets, DestDigit, SendMove<PosT> >(ctx, dg, mv, s.held, s.part_ws.p);
         }
-        const unsigned grid = s.held ? std::min(grid_for(s.held, 256), push_grid_max) : 1u;
-        SGX_LAUNCH(ctx, (shard_push_kernel<PosT>), grid, 256, 0, (const WireItem<PosT>*)s.send.p, (const uint64_t*)s.part_ws.p,
-                   part_tiles(s.held ? s.held : 1), s.held ? 1 : 0, (const uint64_t*)s.kept.p, pp, epoch, s.push_done.p);
+        continue;
       }
+      // peer transport: scatter straight into the destinations' slots; a shard with nothing to send still raises its flags
+      PushPlan pp;
+      memset(&pp, 0, sizeof(pp));
+      pp.world = W;
+      for (int d = 0; d < W; ++d) {
+        pp.slot[d] = cm->peer_addr[d] + parity_off + (size_t)s.g * slot_bytes;
+        pp.flag[d] = comm_peer_flag(cm, d, s.g);
+      }
+      SGX_LAUNCH(ctx, (shard_send_kernel<PosT>), part_tiles(s.held ? s.held : 1), kPartThreads, send_smem, (const uint8_t*)s.tmpDest.p,
+                 (const uint32_t*)s.ID, (const PosT*)s.tmpPos.p, (const uint8_t*)s.SYM.p, (const uint32_t*)s.KEY,
+                 (const uint32_t*)s.WIN, s.held, (const uint64_t*)s.part_ws.p, part_tiles(s.held ? s.held : 1), pp, epoch,
+                 s.push_done.p);
     }
     SGX_TRACE_TICK(k_gather);
     const double hw0 = trace ? now_ms() : 0;
@@ -606,7 +684,17 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
   for (int g = 0; g < W; ++g) total += seg_bytes[g];
   *rle_total = total;
   *rle_host = nullptr;
-  {
+  *seg_offset = 0;
+  *seg_len = total;
+  if (segments && !cm->local) {
+    // every rank keeps its own segment: nothing is gathered, the copies to the hosts run side by side
+    const int g = cm->rank;
+    for (int q = 0; q < g; ++q) *seg_offset += seg_bytes[q];
+    *seg_len = seg_bytes[g];
+    *rle_host = (uint8_t*)pinned_get(ctx, seg_bytes[g] ? seg_bytes[g] : 1);
+    if (seg_bytes[g]) SGX_CUDA(cudaMemcpyAsync(*rle_host, sh[0].rle.p, seg_bytes[g], cudaMemcpyDeviceToHost, ctx->stream));
+    SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+  } else {
     const bool root_here = cm->local || cm->rank == 0;
     DevBuf<uint8_t> d_all;
     if (root_here) d_all.alloc(total ? total : 1);
@@ -616,6 +704,8 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
     if (root_here) {
       *rle_host = (uint8_t*)pinned_get(ctx, total ? total : 1);
       SGX_CUDA(cudaMemcpyAsync(*rle_host, d_all.p, total, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+      *seg_len = 0;
     }
     SGX_CUDA(cudaStreamSynchronize(ctx->stream));
   }
@@ -773,7 +863,8 @@ static void sharded_read_order(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* read
   SGX_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
-void index_build_sharded(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, int order, bool reversed, sgx_index_out* out) {
+void index_build_sharded(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, int order, bool reversed, bool segments,
+                         sgx_index_out* out) {
   memset(out, 0, sizeof(*out));
   const uint64_t N = reads->n;
   const uint64_t S = reads->bases + N;
@@ -838,7 +929,7 @@ void index_build_sharded(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, int
   t_sort.stop();
 
   uint8_t* rle_host = nullptr;
-  uint64_t rle_total = 0;
+  uint64_t rle_total = 0, seg_offset = 0, seg_len = 0;
   // Positions inside the sharded build are shard-local rows and sender-local rank parts (the global offsets live in
   // the 64-bit constants of the receive plan), so 32 bits suffice whenever every SHARD has < 2^32 rows -- config 4
   // (5.03 G symbols) runs the 32-bit kernels on 2+ GPUs.  SGX_FORCE_WIDE=1 (tests) takes the 64-bit path anyway.
@@ -846,13 +937,17 @@ void index_build_sharded(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, int
   for (int g = 0; g < W; ++g) max_rows = std::max(max_rows, rows_final[g]);
   const char* fw = getenv("SGX_FORCE_WIDE");
   if (max_rows < 0xffffff00ull && !(fw && fw[0] == '1')) {
-    sharded_build<uint32_t>(ctx, cm, reads, acc, d_sord.p, bounds, rows_final, out, k_merge, t_bcr, t_emit, &rle_host, &rle_total);
+    sharded_build<uint32_t>(ctx, cm, reads, acc, d_sord.p, bounds, rows_final, out, k_merge, t_bcr, t_emit, segments, &rle_host, &rle_total,
+                            &seg_offset, &seg_len);
   } else {
-    sharded_build<uint64_t>(ctx, cm, reads, acc, d_sord.p, bounds, rows_final, out, k_merge, t_bcr, t_emit, &rle_host, &rle_total);
+    sharded_build<uint64_t>(ctx, cm, reads, acc, d_sord.p, bounds, rows_final, out, k_merge, t_bcr, t_emit, segments, &rle_host, &rle_total,
+                            &seg_offset, &seg_len);
   }
   out->n_strings = N;
   out->n_suffixes = S;
   out->n_runs = rle_total;
+  out->seg_offset = seg_offset;
+  out->seg_bytes = seg_len;
   out->rle = rle_host ? rle_host : (uint8_t*)pinned_get(ctx, 1);  // only shard 0 holds the concatenated run bytes
   out->sai = (uint32_t*)pinned_get(ctx, N * sizeof(uint32_t));
   SGX_CUDA(cudaMemcpyAsync(out->sai, d_sai.p, N * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));

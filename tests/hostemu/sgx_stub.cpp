@@ -308,6 +308,7 @@ int sgx_index_build(sgx_ctx* ctx, const sgx_reads* reads, int order, int reverse
     out->n_strings = n;
     out->n_suffixes = reads->ascii.size() + n;
     out->n_runs = out->n_suffixes / 5;
+    out->seg_bytes = out->n_runs;
     out->rle = (uint8_t*)malloc(out->n_runs ? out->n_runs : 1);
     memset(out->rle, 0x41, out->n_runs);
     out->sai = (uint32_t*)malloc((n ? n : 1) * sizeof(uint32_t));
@@ -369,6 +370,7 @@ int sgx_index_build(sgx_ctx* ctx, const sgx_reads* reads, int order, int reverse
   out->n_strings = n;
   out->n_suffixes = S;
   out->n_runs = rle.size();
+  out->seg_bytes = out->n_runs;
   out->rle = (uint8_t*)malloc(rle.size() ? rle.size() : 1);
   memcpy(out->rle, rle.data(), rle.size());
   out->sai = (uint32_t*)malloc((n ? n : 1) * sizeof(uint32_t));
@@ -394,6 +396,9 @@ int sgx_comm_init(sgx_ctx* ctx, const uint8_t*, int, int, sgx_comm**) { return n
 void sgx_comm_free(sgx_comm*) {}
 int sgx_index_build_sharded(sgx_ctx* ctx, sgx_comm*, const sgx_reads*, int, int, sgx_index_out*) {
   return no_device(ctx, "sgx_index_build_sharded");
+}
+int sgx_index_build_sharded_segments(sgx_ctx* ctx, sgx_comm*, const sgx_reads*, int, int, sgx_index_out*) {
+  return no_device(ctx, "sgx_index_build_sharded_segments");
 }
 
 }  // extern "C"

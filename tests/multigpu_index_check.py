@@ -75,8 +75,33 @@ def main():
             out["sharded_rev%d" % rev] = dict(zip(["wall_ms", "ms_total", "ms_sort", "ms_bcr", "ms_emit", "ms_merge"],
                                                   [round(float(x), 2) for x in t.tolist()]), identical=bool(same),
                                               run_bytes=int(len(res.runs)), launches=res.stats["launches"])
-        else:
-            assert np.array_equal(res.sai, res.sai)
+        # the same build without the final gather: every rank's segment must be the slice of the single-GPU run bytes
+        # at its offset, and the segments must tile the whole
+        ctx.free_index(res)
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        seg = ctx.index_build_sharded_segments(comm, r, reversed=rev, copy=False)
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        t = torch.tensor([wall, seg.stats["ms_total"], seg.stats["ms_emit"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        mine = (int(seg.seg_offset), int(len(seg.runs)), hashlib.sha256(seg.runs.tobytes()).hexdigest(), int(seg.n_runs_total),
+                hashlib.sha256(seg.sai.tobytes()).hexdigest())
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
+        if rank == 0:
+            at, seg_ok = 0, True
+            for off, ln, dig, tot, sdig in parts:
+                seg_ok = seg_ok and off == at and tot == len(one.runs) and \
+                    hashlib.sha256(one.runs[off:off + ln].tobytes()).hexdigest() == dig and \
+                    sdig == hashlib.sha256(one.sai.tobytes()).hexdigest()
+                at += ln
+            seg_ok = seg_ok and at == len(one.runs)
+            ok = ok and seg_ok
+            out["segments_rev%d" % rev] = dict(wall_ms=round(float(t[0]), 2), ms_total=round(float(t[1]), 2),
+                                               ms_emit=round(float(t[2]), 2), identical=bool(seg_ok))
+        ctx.free_index(seg)
     ctx.free_comm(comm)
     ctx.free_reads(r)
     ctx.close()

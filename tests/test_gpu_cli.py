@@ -189,6 +189,10 @@ def test_cli_multi_gpu_outputs_equal_single_gpu():
         for ext in (".bwt", ".rbwt", ".sai", ".rsai"):
             assert open(os.path.join(one, "reads" + ext), "rb").read() == open(os.path.join(two, "reads" + ext), "rb").read(), ext
         # one strand sharded over both GPUs (rows by k-mer bucket, NCCL): forced below the size threshold
+        # (the GPUs write one .bwt together, each its own segment: a longer stale file of that name must not survive)
+        for ext in (".bwt", ".rbwt"):
+            with open(os.path.join(two, "sharded" + ext), "wb") as f:
+                f.write(b"\xff" * (os.path.getsize(os.path.join(one, "reads" + ext)) + 100000))
         for flag, exts in (("--no-reverse", (".bwt", ".sai")), ("--no-forward", (".rbwt", ".rsai"))):
             r = subprocess.run([CLI, "index", "--gpus", "2", flag, "-p", "sharded", src], cwd=two, capture_output=True, text=True,
                                env=dict(os.environ, SIGA_SHARD_MIN_ROWS="0"))

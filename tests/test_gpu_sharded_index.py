@@ -37,6 +37,10 @@ def _check_sharded(ctx, reads, shards, label, oracle=True):
                     bad = np.flatnonzero(a[:n] != b[:n])
                     raise AssertionError((label, shards, model, rev, "rows", len(a), len(b),
                                           "first bad row", int(bad[0]) if len(bad) else None, "run bytes", len(res.runs), len(one.runs)))
+                # without the final gather: one process holds every shard of a local communicator, so its "segment" is the whole
+                seg = ctx.index_build_sharded_segments(comm, r, order=order, reversed=rev)
+                assert seg.seg_offset == 0 and seg.n_runs_total == len(one.runs)
+                assert np.array_equal(seg.runs, one.runs) and np.array_equal(seg.sai, one.sai), (label, shards, model, rev, "segments")
                 if oracle:
                     bwt, sai = pyoracle.bwt_and_sai(reads, model, reversed_reads=rev)
                     assert np.array_equal(res.runs, formats.encode_runs(bwt)), (label, shards, model, rev, "oracle")
@@ -90,18 +94,26 @@ def _gpu_count():
 
 
 @pytest.mark.skipif(_gpu_count() < 2, reason="needs two GPUs (run under gpurun --gpus 2)")
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
 @pytest.mark.parametrize("cfg,scale", [("cfg4", 0.01), ("cfg5", 0.01)])
-def test_sharded_index_over_nccl_matches_reference(cfg, scale):
-    """The NCCL transport (one process per GPU, ncclSend/ncclRecv all-to-all per column pass): run bytes and .sai of the
-    sharded build equal the single-GPU build AND the reference's hashes (tests/golden/fullsize)."""
+def test_sharded_index_over_nccl_matches_reference(cfg, scale, transport):
+    """One process per GPU, both transports of the inserts -- peer memory (cudaIpc-mapped receive regions, stores over
+    NVLink, arrival flags) and the fall-back (ncclSend/ncclRecv all-to-all per column pass): run bytes and .sai of the
+    sharded build equal the single-GPU build AND the reference's hashes (tests/golden/fullsize); the per-rank segments of
+    sgx_index_build_sharded_segments tile the same bytes."""
     here = os.path.dirname(os.path.abspath(__file__))
     n = min(_gpu_count(), 8)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
            "--master-port", "29517", os.path.join(here, "multigpu_index_check.py"), cfg, str(scale), "1"]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    env = dict(os.environ, SGX_SHARD_TRACE="1")
+    if transport == "nccl":
+        env["SGX_SHARD_XCHG"] = "nccl"
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     assert p.returncode == 0, p.stderr[-3000:]
+    assert ("peer-memory transport" if transport == "peer" else "NCCL transport") in p.stderr, p.stderr[-2000:]
     line = [l for l in p.stdout.splitlines() if l.startswith("{")][-1]
     out = json.loads(line)
     assert out["ok"] and out["world"] == n
     assert out["sharded_rev0"]["identical"] and out["sharded_rev1"]["identical"]
+    assert out["segments_rev0"]["identical"] and out["segments_rev1"]["identical"]
     assert out["reference_identical_rev0"] and out["reference_identical_rev1"]
