@@ -419,34 +419,55 @@ __global__ void bcr_tile_bounds_kernel(const PosT* __restrict__ NP, uint64_t nac
 // is a chain of dependent global accesses (tile bounds -> old rows / insert rows -> symbols) and the first version,
 // one CTA per tile, spent its time waiting on that chain (1.6 TB/s):
 //   * the insert bounds of the tile after next are loaded while the current tile is processed,
-//   * the old rows of the next tile are copied global -> shared with cp.async into the other half of a double buffer,
+//   * the old rows of the next tile are copied global -> shared by one bulk copy (cp.async.bulk, completion on an
+//     mbarrier) into the other half of a double buffer,
 //   * the first insert (row, symbol) of every thread for the next tile is loaded into registers.
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+// Bulk asynchronous copy global -> shared (the non-tensor form of TMA: one instruction moves the whole stretch, the
+// copy engine generates the addresses) completing on an mbarrier, and the mbarrier calls around it.
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(a),
+      "r"(phase)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* smem, const void* gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(smem)),
+               "l"(gmem), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+               : "memory");
 }
 
 static const int kMergeOldWords = kMergeTile / 8 + 16;  // staged old rows of a tile, 32-bit words
 
-// cp.async of the old rows of the tile whose inserts are [k0, k1): 16-byte vectors from the 32-row-aligned position at
-// or below its first old row (the arrays are padded).
+// Stages the old rows of the tile whose inserts are [k0, k1): ONE bulk copy, issued by one thread, from the 32-row-aligned
+// position at or below the tile's first old row (the arrays are padded) -- 16-byte granules, at most kMergeTile / 32 + 1 of
+// them.  The copy completes on `bar` (expect_tx = its bytes), which every thread of the CTA waits on before it reads.
 __device__ __forceinline__ void merge_stage_old(const uint8_t* __restrict__ Bo, uint64_t tile, uint64_t n_new, uint64_t k0,
-                                                uint64_t k1, uint32_t* dst) {
+                                                uint64_t k1, uint32_t* dst, uint64_t* bar) {
+  if (threadIdx.x != 0) return;
   const uint64_t t0 = tile * kMergeTile;
   const uint64_t t1 = min(t0 + (uint64_t)kMergeTile, n_new);
   const uint64_t a0 = t0 - k0;
   const uint32_t nold = (uint32_t)((t1 - t0) - (k1 - k0));
   const uint64_t a0al = a0 & ~(uint64_t)31;
-  const uint32_t nvec = (nold + (uint32_t)(a0 - a0al) + 31) / 32;  // <= kMergeTile / 32 + 1 = 257: two rounds of 256 threads
-  const uint8_t* src = Bo + a0al / 2;
-  if (threadIdx.x < nvec) cp_async16(dst + 4 * threadIdx.x, src + threadIdx.x * 16u);
-  if (threadIdx.x + kMergeThreads < nvec)
-    cp_async16(dst + 4 * (threadIdx.x + kMergeThreads), src + (threadIdx.x + kMergeThreads) * 16u);
+  const uint32_t nvec = (nold + (uint32_t)(a0 - a0al) + 31) / 32;
+  mbar_arrive_expect_tx(bar, nvec * 16u);
+  if (nvec) bulk_copy_g2s(dst, Bo + a0al / 2, nvec * 16u, bar);
 }
 
 template <class PosT>
@@ -463,9 +484,17 @@ __global__ void __launch_bounds__(kMergeThreads, 8) bcr_merge_kernel(const uint8
   __shared__ uint32_t sh[8];
   __shared__ uint32_t outsm[kMergeTile / 8];  // the finished tile (for the tile-local ranks)
   __shared__ uint2 presm[kMergeThreads];      // symbol counts of the tile before each thread's rows
+  __shared__ __align__(8) uint64_t stage_bar[2];  // completion of the bulk copy into oldw[0] / oldw[1]
   const uint64_t G = gridDim.x;
   uint64_t tile = blockIdx.x;
   if (tile >= ntiles) return;
+  if (threadIdx.x == 0) {
+    mbar_init(&stage_bar[0], 1);
+    mbar_init(&stage_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t phases = 0;  // bit s = parity to wait for on stage_bar[s]
   // prologue: bounds of my first two tiles, old rows + first insert of the first
   uint64_t k0 = tile_k0[tile], k1 = tile_k0[tile + 1];
   uint64_t kn0 = 0, kn1 = 0;
@@ -473,8 +502,7 @@ __global__ void __launch_bounds__(kMergeThreads, 8) bcr_merge_kernel(const uint8
     kn0 = tile_k0[tile + G];
     kn1 = tile_k0[tile + G + 1];
   }
-  merge_stage_old(Bo, tile, n_new, k0, k1, oldw[0]);
-  cp_async_commit();
+  merge_stage_old(Bo, tile, n_new, k0, k1, oldw[0], &stage_bar[0]);
   uint64_t pre_np = 0;
   uint32_t pre_sym = 0;
   if (k0 + threadIdx.x < k1) {
@@ -486,8 +514,7 @@ __global__ void __launch_bounds__(kMergeThreads, 8) bcr_merge_kernel(const uint8
     const uint64_t tn = tile + G;
     const bool have_next = tn < ntiles;
     // next tile: stage its old rows into the other buffer (free since the end of the previous iteration)
-    if (have_next) merge_stage_old(Bo, tn, n_new, kn0, kn1, oldw[s ^ 1]);
-    cp_async_commit();
+    if (have_next) merge_stage_old(Bo, tn, n_new, kn0, kn1, oldw[s ^ 1], &stage_bar[s ^ 1]);
     // bounds of the tile after next; first insert of the next tile
     uint64_t knn0 = 0, knn1 = 0;
     if (tn + G < ntiles) {
@@ -518,7 +545,8 @@ __global__ void __launch_bounds__(kMergeThreads, 8) bcr_merge_kernel(const uint8
       atomicOr(&mask[r >> 5], 1u << (r & 31));
       symsh[k - k0] = SYM[k];
     }
-    cp_async_wait<1>();  // the current tile's old rows (the group committed one iteration ago) have landed
+    mbar_wait(&stage_bar[s], (phases >> s) & 1u);  // the current tile's old rows (copy issued one iteration ago) have landed
+    phases ^= 1u << s;
     __syncthreads();
     const uint32_t m = mask[threadIdx.x];
     const uint32_t pre = block_excl_scan32((uint32_t)__popc(m), sh);  // inserts before my first row
@@ -604,7 +632,6 @@ __global__ void __launch_bounds__(kMergeThreads, 8) bcr_merge_kernel(const uint8
     pre_np = nxt_np;
     pre_sym = nxt_sym;
   }
-  cp_async_wait<0>();
 }
 
 // ---- 3. run-length encoding ------------------------------------------------------------------------------------------

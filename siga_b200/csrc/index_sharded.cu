@@ -767,6 +767,18 @@ static void sharded_read_order(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* read
                                const ShardBounds& bounds, uint32_t* d_sai, uint32_t* d_sord) {
   const uint64_t N = reads->n;
   const int W = cm->world, nl = cm->n_local();
+  // SGX_SHARD_TRACE=1: wall time per phase (the stream is drained at every mark; diagnostics only)
+  const char* tr = getenv("SGX_SHARD_TRACE");
+  const bool trace = tr && tr[0] == '1';
+  double t_mark = trace ? now_ms() : 0, t_select = 0, t_content = 0, t_publish = 0, t_double = 0;
+  int rounds = 0;
+  auto mark = [&](double& acc_ms) {
+    if (!trace) return;
+    cudaStreamSynchronize(ctx->stream);
+    const double t = now_ms();
+    acc_ms += t - t_mark;
+    t_mark = t;
+  };
   std::vector<OrderShard> sh(nl);
   std::vector<uint64_t> cnt(W, 0), distinct(W, 0);
   std::vector<const uint64_t*> u64_ptr(nl);
@@ -798,6 +810,7 @@ static void sharded_read_order(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* read
   uint64_t sum = 0;
   for (int g = 0; g < W; ++g) sum += cnt[g];
   SGX_REQUIRE(sum == N, SGX_ECUDA, "sharded index: the shards' read sets do not add up to the read count");
+  mark(t_select);
   // ---- content order + dense content ranks
   for (int li = 0; li < nl; ++li) {
     OrderShard& s = sh[li];
@@ -805,6 +818,7 @@ static void sharded_read_order(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* read
     if (s.n) SGX_LAUNCH(ctx, read_heads_kernel, grid_for(s.n, 256), 256, 0, acc.rv, (const uint32_t*)s.ids.p, s.n, s.heads.p);
     scan_exclusive(ctx, s.heads.p, s.n, s.scan_ws.p, s.total.p);
   }
+  mark(t_content);
   DevBuf<uint32_t> rank, ranks_by_pos;
   uint32_t* order_ids = d_sai;  // concatenation of the shards' sorted ids = the global order
   auto publish = [&](bool need_ranks) {
@@ -839,6 +853,7 @@ static void sharded_read_order(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* read
   rank.alloc(N);
   ranks_by_pos.alloc(N);
   uint64_t n_distinct = publish(true);
+  mark(t_publish);
   int bits = 1;
   while (((uint64_t)1 << bits) <= N) ++bits;  // ranks are in [0, N]
   for (uint64_t h = 1; n_distinct < N; h <<= 1) {
@@ -854,13 +869,23 @@ static void sharded_read_order(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* read
       }
       scan_exclusive(ctx, s.heads.p, s.n, s.scan_ws.p, s.total.p);
     }
+    mark(t_double);
+    ++rounds;
     n_distinct = publish(true);
+    mark(t_publish);
     SGX_REQUIRE(h < ((uint64_t)1 << 40), SGX_ECUDA, "index: read-rank doubling did not converge");
   }
   uint64_t* k0 = sh[0].total.p;  // scratch
   SGX_LAUNCH(ctx, find_zero_kernel, grid_for(N, 256), 256, 0, (const uint32_t*)d_sai, N, k0);
   SGX_LAUNCH(ctx, sentinel_order_kernel, grid_for(N, 256), 256, 0, (const uint32_t*)d_sai, N, (const uint64_t*)k0, d_sord);
   SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (trace) {
+    double t_final = 0;
+    mark(t_final);
+    fprintf(stderr, "[sgx shard %d/%d] read order: select own reads %.2f ms, content sort %.2f ms, %d doubling round(s) %.2f ms, "
+            "publish (all-gather ids + ranks) %.2f ms, sentinel order %.2f ms\n", cm->shard_of(0), W, t_select, t_content, rounds,
+            t_double, t_publish, t_final);
+  }
 }
 
 void index_build_sharded(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, int order, bool reversed, bool segments,
@@ -878,6 +903,7 @@ void index_build_sharded(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, int
 
   t_all.start();
   t_sort.start();
+  const double t_host0 = now_ms();
   DevBuf<uint32_t> d_sai(N), d_sord(N);
   // ---- bucket bounds from the k-mer histogram of a read sample; exact rows per shard
   const int nslices = cm->local ? 1 : W;
@@ -923,6 +949,10 @@ void index_build_sharded(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, int
       sum += hr[g];
     }
     SGX_REQUIRE(sum == S, SGX_ECUDA, "sharded index: shard row counts do not add up to the number of suffixes");
+  }
+  {
+    const char* tr = getenv("SGX_SHARD_TRACE");
+    if (tr && tr[0] == '1') fprintf(stderr, "[sgx shard %d/%d] bucket bounds + rows per shard: %.2f ms\n", cm->shard_of(0), W, now_ms() - t_host0);
   }
   // ---- read order (.sai) and sentinel order, the reads sharded by the same bounds
   sharded_read_order(ctx, cm, reads, acc, order, bounds, d_sai.p, d_sord.p);
