@@ -414,6 +414,7 @@ void sgx_fm_free(sgx_fm* fm) {
   cudaFreeAsync(fm->blocks, fm->ctx->stream);
   if (fm->sai) cudaFreeAsync(fm->sai, fm->ctx->stream);
   if (fm->inv) cudaFreeAsync(fm->inv, fm->ctx->stream);
+  if (fm->ktab) cudaFreeAsync(fm->ktab, fm->ctx->stream);
   delete fm;
 }
 

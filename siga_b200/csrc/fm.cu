@@ -156,7 +156,74 @@ sgx_fm* fm_build_from_symbols(sgx_ctx* ctx, const uint8_t* sym_dev, uint64_t n) 
   fm->pred[0] = 0;
   for (int c = 1; c <= 5; ++c) fm->pred[c] = fm->pred[c - 1] + cntc[c - 1];
   fm->blocks = blocks.take();
+  fm->ktab = nullptr;
+  fm->ktab_k = 0;
+  // k-mer start table -- an EXPERIMENT, off unless SGX_KTAB=k (2..13) asks for it: measured at config 2 with k = 12 it
+  // removes 22 % of the fetched rank-block lines and 1 % of the search time (45.5 -> 45.0 ms): the first steps of a chain
+  // walk the top of the index, which stays in L2, and cost next to nothing (profiles/r2_summary.md).
+  if (n < 0xffffff00ull) {
+    int k = 0;
+    if (const char* e = getenv("SGX_KTAB")) k = std::max(0, std::min(13, atoi(e)));
+    while (k > 1 && ((uint64_t)1 << (2 * k)) > 4 * n + 64) --k;  // never much larger than the index itself
+    if (k >= 2) {
+      try {
+        fm_build_ktab(ctx, fm, k);
+      } catch (...) {
+        cudaFreeAsync(fm->blocks, ctx->stream);
+        delete fm;
+        throw;
+      }
+    }
+  }
   return fm;
+}
+
+// Level t of the k-mer table from level t - 1: one 8-lane group per parent string, two rank queries (all four symbols
+// at once), four children.  child[4 p + c] extends parent p by base c on the left.
+__global__ void __launch_bounds__(256) ktab_level_kernel(FmView fm, const uint2* __restrict__ parent, uint64_t nparent,
+                                                         uint2* __restrict__ child) {
+  const DevGroup g;
+  const uint64_t gid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / kGroup;
+  if (gid >= nparent) return;
+  const uint2 pe = parent[gid];
+  uint64_t L[5] = {0, 0, 0, 0, 0}, U[5] = {0, 0, 0, 0, 0};
+  if (pe.y) {  // group-uniform
+    fm_occ(fm, (pos_t)pe.x - 1, L, g);
+    fm_occ(fm, (pos_t)pe.x + pe.y - 1, U, g);
+  }
+  if (g.lane < 4) {
+    const int c = g.lane + 1;
+    uint2 ce = make_uint2(1u, 0u);  // empty
+    if (pe.y && U[c] > L[c]) ce = make_uint2((uint32_t)(fm.pred[c] + L[c]), (uint32_t)(U[c] - L[c]));
+    child[4 * gid + g.lane] = ce;
+  }
+}
+
+void fm_build_ktab(sgx_ctx* ctx, sgx_fm* fm, int k) {
+  SGX_REQUIRE(k >= 1 && k <= 13 && fm->n < 0xffffff00ull, SGX_EINVAL, "fm_build_ktab: k out of range or index too large");
+  const uint64_t n_final = (uint64_t)1 << (2 * k);
+  DevBuf<uint2> tab, tmp;
+  tab.alloc_owned(n_final);
+  tmp.alloc(std::max<uint64_t>(n_final / 4, 4));
+  // level t lands in `tab` when k - t is even, so that level k does
+  uint2 l1[4];
+  for (int c = 1; c <= 4; ++c) {
+    const uint64_t rows = fm->pred[c + 1] - fm->pred[c];
+    l1[c - 1] = rows ? make_uint2((uint32_t)fm->pred[c], (uint32_t)rows) : make_uint2(1u, 0u);
+  }
+  uint2* cur = ((k - 1) % 2 == 0) ? tab.p : tmp.p;
+  SGX_CUDA(cudaMemcpyAsync(cur, l1, sizeof(l1), cudaMemcpyHostToDevice, ctx->stream));
+  SGX_CUDA(cudaStreamSynchronize(ctx->stream));  // l1 is a stack array
+  const FmView v = fm->view();
+  for (int t = 2; t <= k; ++t) {
+    uint2* nxt = ((k - t) % 2 == 0) ? tab.p : tmp.p;
+    const uint64_t nparent = (uint64_t)1 << (2 * (t - 1));
+    SGX_LAUNCH(ctx, ktab_level_kernel, grid_for(nparent * kGroup, 256), 256, 0, v, (const uint2*)cur, nparent, nxt);
+    cur = nxt;
+  }
+  if (fm->ktab) cudaFreeAsync(fm->ktab, ctx->stream);
+  fm->ktab = tab.take();
+  fm->ktab_k = k;
 }
 
 

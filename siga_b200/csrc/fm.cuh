@@ -17,6 +17,11 @@ struct sgx_fm {
   uint32_t* inv;   // device, inv[sai[k]] = k
   uint64_t n_strings;
   const sgx_reads* indexed;
+  // k-mer start table (fm_build_ktab): interval {first row, rows} of every string of ktab_k bases, indexed by the string
+  // read backwards as a base-4 number (last base most significant) -- the state of a backward search after its first
+  // ktab_k steps.  Only for indices with < 2^32 rows; nullptr / 0 otherwise.
+  uint2* ktab;
+  int ktab_k;
   sgx::FmView view() const {
     sgx::FmView v;
     v.blocks = blocks;
@@ -33,6 +38,8 @@ sgx_fm* fm_build_from_symbols(sgx_ctx* ctx, const uint8_t* sym_dev, uint64_t n);
 // Expands run bytes (device) into a fresh device symbol array of n_suffixes bytes.
 void rle_expand(sgx_ctx* ctx, const uint8_t* rle_dev, uint64_t n_runs, uint64_t n_suffixes, uint8_t* sym_dev);
 
+// Builds fm->ktab for strings of k bases (k >= 1; level by level, 4^k / 3 pairs of rank queries in all).
+void fm_build_ktab(sgx_ctx* ctx, sgx_fm* fm, int k);
 // Uploads the read-start order and builds its inverse.
 void fm_attach(sgx_ctx* ctx, sgx_fm* fm, const uint32_t* sai, uint64_t n, const sgx_reads* indexed);
 // Batched FMIndex::getOcc(i): host positions in, host counts (5 per position) out.

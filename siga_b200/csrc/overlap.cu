@@ -178,6 +178,9 @@ struct OvPlan {
     fmp.blocks[1] = vr.blocks;
     fmp.inv[0] = f->inv;
     fmp.inv[1] = r->inv;
+    fmp.ktab[0] = f->ktab;
+    fmp.ktab[1] = r->ktab;
+    fmp.ktab_k = (f->ktab && r->ktab && f->ktab_k == r->ktab_k) ? f->ktab_k : 0;
     for (int i = 0; i < 6; ++i) {
       fmp.pred[0][i] = vf.pred[i];
       fmp.pred[1][i] = vr.pred[i];
@@ -267,10 +270,12 @@ struct OvPlan {
       }
       if (uni && !env_u64("SGX_LEAN_LOCKSTEP", 0)) {  // reads of one length: persistent quads
         const uint32_t ul = reads->max_len, uw = (reads->max_len + 15) / 16;
+        // start table: usable when no '$' probe falls inside the skipped steps and a step is left after them
+        const int ktk = (fmp.ktab_k >= 2 && min_ov >= (uint32_t)fmp.ktab_k && ul > (uint32_t)fmp.ktab_k && sizeof(IdxT) == 4) ? fmp.ktab_k : 0;
         if (env_u64("SGX_LEAN_PQ2", 1)) {  // cold state in shared memory (default; 0 = the register-heavy variant)
-          if (minb == 6) SGX_LAUNCH(ctx, (ov_search_pq2_kernel<IdxT, 6>), grid, kOvThreads, 0, fmp, rv, ul, uw, rfirst, n, min_ov, rc, bt, list, d_look.p, only);
-          else if (minb == 5) SGX_LAUNCH(ctx, (ov_search_pq2_kernel<IdxT, 5>), grid, kOvThreads, 0, fmp, rv, ul, uw, rfirst, n, min_ov, rc, bt, list, d_look.p, only);
-          else SGX_LAUNCH(ctx, (ov_search_pq2_kernel<IdxT, 4>), grid, kOvThreads, 0, fmp, rv, ul, uw, rfirst, n, min_ov, rc, bt, list, d_look.p, only);
+          if (minb == 6) SGX_LAUNCH(ctx, (ov_search_pq2_kernel<IdxT, 6>), grid, kOvThreads, 0, fmp, rv, ul, uw, rfirst, n, min_ov, rc, bt, list, d_look.p, only, ktk);
+          else if (minb == 5) SGX_LAUNCH(ctx, (ov_search_pq2_kernel<IdxT, 5>), grid, kOvThreads, 0, fmp, rv, ul, uw, rfirst, n, min_ov, rc, bt, list, d_look.p, only, ktk);
+          else SGX_LAUNCH(ctx, (ov_search_pq2_kernel<IdxT, 4>), grid, kOvThreads, 0, fmp, rv, ul, uw, rfirst, n, min_ov, rc, bt, list, d_look.p, only, ktk);
         } else if (minb == 6) SGX_LAUNCH(ctx, (ov_search_pq_kernel<IdxT, 6>), grid, kOvThreads, 0, fmp, rv, ul, uw, rfirst, n, min_ov, rc, bt, list, d_look.p, only);
         else if (minb == 5) SGX_LAUNCH(ctx, (ov_search_pq_kernel<IdxT, 5>), grid, kOvThreads, 0, fmp, rv, ul, uw, rfirst, n, min_ov, rc, bt, list, d_look.p, only);
         else SGX_LAUNCH(ctx, (ov_search_pq_kernel<IdxT, 4>), grid, kOvThreads, 0, fmp, rv, ul, uw, rfirst, n, min_ov, rc, bt, list, d_look.p, only);

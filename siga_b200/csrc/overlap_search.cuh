@@ -34,6 +34,8 @@ struct FmPair {
   const FmBlockLane* blocks[2];  // 0 = forward index, 1 = reverse index
   uint64_t pred[2][6];
   const uint32_t* inv[2];        // read id -> row of its '$' block entry (inverse .sai / .rsai), when reads are attached
+  const uint2* ktab[2];          // k-mer start tables of the two indices (sgx_fm::ktab), or nullptr
+  int ktab_k;                    // their k (0: no table)
 };
 
 // LEAN: write 12-byte LeanCand records (capped[0], length, flags) instead of full 72-byte blocks.
@@ -750,14 +752,15 @@ struct PqCold {
   unsigned long long nlines;  // rank-block lines those lookups touched
   uint32_t rd;                // read of the pair in flight
   uint32_t n;                 // candidates emitted so far
-  uint32_t extra;             // steps whose interval ends lay in different blocks
-  uint32_t pad;
+  uint32_t extra;             // steps whose interval ends lay in different blocks (+ 1 for a start-table fetch)
+  uint32_t i0;                // step count the pair started with
 };
 
 template <class IdxT, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 ov_search_pq2_kernel(FmPair fm, ReadsView reads, uint32_t ulen, uint32_t uwords, uint64_t first, uint64_t count, uint32_t min_ov,
-                     int rc, OvBatch bt, const uint32_t* __restrict__ list, unsigned long long* __restrict__ lookups, int only_pi) {
+                     int rc, OvBatch bt, const uint32_t* __restrict__ list, unsigned long long* __restrict__ lookups, int only_pi,
+                     int ktk /* > 0: start every pair from the k-mer table (the caller checked min_ov >= ktk and ulen > ktk) */) {
   __shared__ PqCold cold[256 / kQuad];
   const unsigned kFull = 0xffffffffu;
   const int q = threadIdx.x & (kQuad - 1);
@@ -822,7 +825,7 @@ ov_search_pq2_kernel(FmPair fm, ReadsView reads, uint32_t ulen, uint32_t uwords,
         }
         bt.ncand[slot] = cs.n < bt.find_cap ? cs.n : bt.find_cap;
         bt.ncontain[slot] = ((fl & 4u) || tail) ? 1u : 0u;
-        const uint32_t steps = (l - 1) - i;
+        const uint32_t steps = cs.i0 - i;
         cs.nlook += 2ull * steps;
         cs.nlines += (unsigned long long)steps + cs.extra;
       }
@@ -848,11 +851,29 @@ ov_search_pq2_kernel(FmPair fm, ReadsView reads, uint32_t ulen, uint32_t uwords,
         mypc = (IdxT)fm.pred[pi][q + 1];
         const uint32_t* rw = reads.words + rd * uwords;
         fl = 2u | ((mode == 1 || mode == 2) ? 8u : 0u) | ((mode & 1) ? 16u : 0u) | (pi << 5);
-        const int c = ov_sym(rw, l, mode, l - 1);
-        lo0 = (IdxT)fm.pred[pi][c];
-        hi0 = (IdxT)(fm.pred[pi][c + 1] - 1);
-        i = l - 1;
-        if (i > 0 && hi0 != kNone && hi0 >= lo0) {
+        bool alone = false;
+        if (ktk > 0) {
+          // The first ktk - 1 steps of every chain walk the top of the index, which all chains share; their result depends
+          // on the last ktk symbols only and is tabulated (sgx_fm::ktab): ONE fetch instead of ktk - 1 dependent ones.
+          // No '$' probe is skipped, because probes start at overlap length min_ov >= ktk.
+          uint32_t key = 0;
+          for (int t = 0; t < ktk; ++t) key = key * 4u + (uint32_t)(ov_sym(rw, l, mode, l - 1 - (uint32_t)t) - 1);
+          const uint2 e = __ldg(fm.ktab[pi] + key);
+          lo0 = (IdxT)e.x;
+          hi0 = (IdxT)(e.x + e.y - 1u);  // empty entries are {1, 0}
+          i = l - (uint32_t)ktk;
+          alone = !(fl & 16u) && e.y == 1u;  // modes 0 and 2: only the read itself is left (same rule as after a step)
+          if (q == 0) cs.extra = 1;
+        } else {
+          const int c = ov_sym(rw, l, mode, l - 1);
+          lo0 = (IdxT)fm.pred[pi][c];
+          hi0 = (IdxT)(fm.pred[pi][c + 1] - 1);
+          i = l - 1;
+        }
+        if (q == 0) cs.i0 = i;
+        if (alone) {
+          fl |= 4u;
+        } else if (i > 0 && hi0 != kNone && hi0 >= lo0) {
           fl |= 1u;
           const uint32_t j = (fl & 8u) ? l - i : i - 1;  // base index of string position i - 1
           word = rw[j >> 4] ^ ((fl & 16u) ? 0xffffffffu : 0u);

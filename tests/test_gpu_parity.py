@@ -435,6 +435,15 @@ def test_config1_full_pipeline_multibatch(ctx, monkeypatch, hook):
     test_config1_full_pipeline_bit_exact(ctx)
 
 
+@pytest.mark.skipif(not refrun.have_ref(), reason="compiled reference (oracle/_ref/siga) not present")
+@pytest.mark.parametrize("k", ["2", "7", "10"])
+def test_config1_with_kmer_start_table(ctx, monkeypatch, k):
+    """The opt-in k-mer start table of the lean search (SGX_KTAB=k, fm.cu: fm_build_ktab): every chain starts from the
+    tabulated interval of its last k symbols; same files as the reference."""
+    monkeypatch.setenv("SGX_KTAB", k)
+    test_config1_full_pipeline_bit_exact(ctx)
+
+
 @pytest.mark.parametrize("batch", ["1", "7"])
 def test_golden_fixtures_multibatch(ctx, monkeypatch, batch):
     monkeypatch.setenv("SGX_MAX_BATCH", batch)
