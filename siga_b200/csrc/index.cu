@@ -189,22 +189,18 @@ void rle_heads(sgx_ctx* ctx, const uint8_t* B, uint64_t n, RleSegment* seg) {
   seg->n_rows = n;
   seg->n_runs = 0;
   if (n == 0) return;
-  DevBuf<uint64_t> ws_h(part_ws_elems(n, 2));
-  // run heads: positions k with B[k] != B[k-1]  (count first so that the heads array is sized exactly)
-  const uint32_t ntiles = part_tiles(n);
-  HeadDigit hd{B};
-  SGX_LAUNCH(ctx, (part_count_kernel<2, HeadDigit>), ntiles, kPartThreads, 0, hd, n, ws_h.p, ntiles);
-  // bucket 0 = heads: total heads = start offset of bucket 1 after the scan
-  DevBuf<uint64_t> ws_s(scan_ws_elems((uint64_t)2 * ntiles));
-  scan_exclusive(ctx, ws_h.p, (uint64_t)2 * ntiles, ws_s.p, (uint64_t*)nullptr);
+  // run heads: rows k with B[k] != B[k-1], found 32 rows per thread (count per 8192-row tile first, so that the heads
+  // array is sized exactly; then the same masks again, written at the scanned offsets)
+  const uint64_t ntiles = (n + kMergeTile - 1) / kMergeTile;
+  DevBuf<uint64_t> tilecnt(ntiles), ws_s(scan_ws_elems(ntiles)), d_total(1);
+  SGX_LAUNCH(ctx, head_count_kernel, (unsigned)ntiles, 256, 0, B, n, tilecnt.p);
+  scan_exclusive(ctx, tilecnt.p, ntiles, ws_s.p, d_total.p);
   uint64_t n_runs = 0;
-  SGX_CUDA(cudaMemcpyAsync(&n_runs, ws_h.p + ntiles, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  SGX_CUDA(cudaMemcpyAsync(&n_runs, d_total.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
   SGX_CUDA(cudaStreamSynchronize(ctx->stream));
   seg->n_runs = n_runs;
   seg->heads.alloc(n_runs + 1);
-  HeadOnlyMove hm{seg->heads.p, n_runs};
-  SGX_LAUNCH(ctx, (part_scatter_kernel<2, HeadDigit, HeadOnlyMove>), ntiles, kPartThreads, 0, hd, hm, n,
-             (const uint64_t*)ws_h.p, ntiles);
+  SGX_LAUNCH(ctx, head_write_kernel, (unsigned)ntiles, 256, 0, B, n, (const uint64_t*)tilecnt.p, seg->heads.p);
   // ends of the segment: symbols of the first / last row, start of the second / last run
   uint64_t second = n, last_head = 0;
   uint8_t b0 = 0, b1 = 0;

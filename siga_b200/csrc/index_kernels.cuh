@@ -636,19 +636,62 @@ __global__ void __launch_bounds__(kMergeThreads, 8) bcr_merge_kernel(const uint8
 
 // ---- 3. run-length encoding ------------------------------------------------------------------------------------------
 
-struct HeadDigit {
-  const uint8_t* B;
-  __device__ __forceinline__ int operator()(uint64_t k) const {
-    return (k == 0 || nib_get(B, k) != nib_get(B, k - 1)) ? 0 : 1;
+// Run heads of a nibble array, 32 rows (one 16-byte vector) per thread: bit i of the returned mask is set when row
+// 32 t + i starts a run (differs from the row before it; row 0 always does).  Rows at or past n are never heads.
+__device__ __forceinline__ uint32_t head_mask32(const uint8_t* __restrict__ B, uint64_t t, uint64_t n) {
+  const uint64_t row0 = t * 32;
+  if (row0 >= n) return 0u;
+  const uint4 v = *reinterpret_cast<const uint4*>(B + row0 / 2);
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  uint32_t prev = t ? (uint32_t)(B[row0 / 2 - 1] >> 4) : 0xfu;  // 0xf is no symbol: row 0 is a head
+  uint32_t m = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t x = w[i] ^ ((w[i] << 4) | prev);  // nibble k: row k of the word against the row before it
+    prev = w[i] >> 28;
+    x |= x >> 1;
+    x |= x >> 2;
+    x &= 0x11111111u;                 // bit 4 k = row k differs
+    x = (x | (x >> 3)) & 0x03030303u; // gather the eight flags of the word into its low byte: pairs ...
+    x = (x | (x >> 6)) & 0x000f000fu; // ... nibbles ...
+    x = (x | (x >> 12)) & 0xffu;      // ... byte
+    m |= x << (8 * i);
   }
-};
-struct HeadOnlyMove {
-  uint64_t* heads;
-  uint64_t n_heads;
-  __device__ __forceinline__ void operator()(uint64_t k, uint64_t dest) const {
-    if (dest < n_heads) heads[dest] = k;  // bucket 1 (non-heads) lands at dest >= n_heads and is dropped
+  const uint64_t left = n - row0;
+  if (left < 32) m &= (1u << (uint32_t)left) - 1u;
+  return m;
+}
+
+// heads per 8192-row tile (256 threads x 32 rows)
+static __global__ void __launch_bounds__(256) head_count_kernel(const uint8_t* __restrict__ B, uint64_t n,
+                                                                 uint64_t* __restrict__ tilecnt) {
+  __shared__ uint32_t sh[8];
+  const uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+  uint32_t c = (uint32_t)__popc(head_mask32(B, t, n));
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t s = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += sh[q];
+    tilecnt[blockIdx.x] = s;
   }
-};
+}
+
+// heads[tileoff[tile] + ...] = rows that start a run, in row order
+static __global__ void __launch_bounds__(256) head_write_kernel(const uint8_t* __restrict__ B, uint64_t n,
+                                                                 const uint64_t* __restrict__ tileoff, uint64_t* __restrict__ heads) {
+  __shared__ uint32_t sh[8];
+  const uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+  uint32_t m = head_mask32(B, t, n);
+  uint64_t at = tileoff[blockIdx.x] + block_excl_scan32((uint32_t)__popc(m), sh);
+  while (m) {
+    const uint32_t i = (uint32_t)__ffs(m) - 1;
+    m &= m - 1;
+    heads[at++] = t * 32 + i;
+  }
+}
 
 // Length of run r of a segment of n rows.  Seams of the bucket-sharded build: a run that continues from the previous
 // segment belongs to the segment where it starts, so a segment may skip its first run (skip_first) and its last run

@@ -77,11 +77,18 @@ static __global__ void __launch_bounds__(256) key_hist_kernel(ReadAcc acc, uint6
   if (id64 >= n) return;
   const uint32_t id = (uint32_t)id64;
   const uint32_t l = acc.rv.len[id];
+  const int lane = threadIdx.x & 31;
+  // one atomic per distinct key among the lanes that are here together: the keys of the shortest suffixes ("$", "c$",
+  // ...) are the same in every lane, and a million atomics on one address serialise
+  auto add = [&](uint32_t key) {
+    const unsigned m = __match_any_sync(__activemask(), key);
+    if (lane == __ffs(m) - 1) atomicAdd(&hist[key], (unsigned long long)__popc(m));
+  };
   uint32_t key = 0;
-  atomicAdd(&hist[0], 1ull);
+  add(0u);
   for (uint32_t col = l; col-- > 0;) {
     key = (acc.code(id, col, l) + 1u) * kKeyTop + key / 5u;
-    atomicAdd(&hist[key], 1ull);
+    add(key);
   }
 }
 
@@ -915,7 +922,7 @@ void index_build_sharded(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, int
   {
     DevBuf<uint64_t> hist(kKeySpace);
     SGX_CUDA(cudaMemsetAsync(hist.p, 0, kKeySpace * sizeof(uint64_t), ctx->stream));
-    const uint64_t stride = std::max<uint64_t>(1, N >> 21);  // about two million sampled reads in total
+    const uint64_t stride = std::max<uint64_t>(1, N >> 19);  // about half a million sampled reads in total
     const uint64_t n_sample = (N + stride - 1) / stride;
     const uint64_t mine = (n_sample + nslices - 1 - slice) / nslices;  // samples slice, slice + nslices, ...
     if (mine)
