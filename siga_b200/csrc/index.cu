@@ -70,7 +70,11 @@ static void bcr_passes(sgx_ctx* ctx, const sgx_reads* reads, const ReadAcc& acc,
     if (nact == 0) break;
     SymDigit dg{SYM};
     BcrMove<PosT> mv{acc, ID, WIN, j, uniform_len, ID2, NP2, SYM2, WIN2, tiletot.p, nt, N, SYM, NP, RL};
-    partition_pass<4>(ctx, dg, mv, nact_prev, part_ws.p, (uint64_t*)nullptr);
+    if (nact_prev) {
+      partition_count<4, SymDigit>(ctx, dg, nact_prev, part_ws.p, (uint64_t*)nullptr);
+      SGX_LAUNCH(ctx, (bcr_scatter_kernel<PosT>), part_tiles(nact_prev), kPartThreads, 0, mv, nact_prev,
+                 (const uint64_t*)part_ws.p, part_tiles(nact_prev));
+    }
     const uint64_t n_new = n_cur + nact;
     const uint64_t ntiles = (n_new + kMergeTile - 1) / kMergeTile;
     SGX_LAUNCH(ctx, (bcr_tile_bounds_kernel<PosT>), grid_for(nact + 1, 256), 256, 0, (const PosT*)NP2, nact, ntiles,

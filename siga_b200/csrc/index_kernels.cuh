@@ -375,26 +375,121 @@ struct BcrMove {
   const uint8_t* SYM;
   const PosT* NP;
   const uint16_t* rloc;
-  __device__ __forceinline__ void operator()(uint64_t k, uint64_t dest) const {
+  struct Item {
+    uint32_t id, win;
+    PosT np;
+    uint8_t sym;
+  };
+  __device__ __forceinline__ Item compute(uint64_t k) const {
+    Item it;
     const uint32_t id = ID[k];
     const uint32_t c = (uint32_t)SYM[k] - 1;  // SYM is 1..4 here: ended reads are dropped by the partition digit
     const uint64_t tile = (uint64_t)NP[k] / kMergeTile;
     const uint64_t sc = __ldg(scanned + (uint64_t)c * ntiles + tile);
     const uint32_t l = uniform_len ? uniform_len : acc.rv.len[id];
-    ID2[dest] = id;
-    NP2[dest] = (PosT)(base + sc + rloc[k]);
-    if (l == j) {
-      SYM2[dest] = 0;
-      return;
-    }
+    it.id = id;
+    it.np = (PosT)(base + sc + rloc[k]);
+    it.sym = 0;
+    it.win = 0;
+    if (l == j) return it;
     // stored position of column l - j - 1: the walk goes down through a forward read, up through a reversed one
     const uint32_t p = acc.reversed ? j : l - j - 1;
     const bool fresh = j == 1 || (acc.reversed ? (p & 15u) == 0u : (p & 15u) == 15u);
     const uint32_t w = fresh ? acc.rv.words[acc.rv.woff[id] + (p >> 4)] : WIN[k];
-    SYM2[dest] = (uint8_t)(((w >> (2 * (p & 15u))) & 3u) + 1u);
-    WIN2[dest] = w;
+    it.sym = (uint8_t)(((w >> (2 * (p & 15u))) & 3u) + 1u);
+    it.win = w;
+    return it;
+  }
+  __device__ __forceinline__ void operator()(uint64_t k, uint64_t dest) const {
+    const Item it = compute(k);
+    ID2[dest] = it.id;
+    NP2[dest] = it.np;
+    SYM2[dest] = it.sym;
+    WIN2[dest] = it.win;
   }
 };
+
+// Scatter half of a column pass's partition (same tile walk and order as part_scatter_kernel<4, SymDigit, BcrMove>), with
+// the tile's items laid out in bucket order in shared memory first: the four output arrays are then written by consecutive
+// threads at consecutive slots -- whole sectors of the byte array instead of eight bytes per warp and bucket.
+template <class PosT>
+__global__ void __launch_bounds__(kPartThreads) bcr_scatter_kernel(BcrMove<PosT> mv, uint64_t n, const uint64_t* __restrict__ tileoff,
+                                                                   uint32_t ntiles) {
+  __shared__ uint32_t wc[kPartThreads / 32][4];
+  __shared__ uint32_t boff[5];
+  __shared__ uint32_t s_id[kPartTile], s_win[kPartTile];
+  __shared__ PosT s_np[kPartTile];
+  __shared__ uint8_t s_sym[kPartTile];
+  if (threadIdx.x < (kPartThreads / 32) * 4) (&wc[0][0])[threadIdx.x] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint64_t wbase = (uint64_t)blockIdx.x * kPartTile + (uint64_t)w * (kPartRounds * 32);
+  int dg[kPartRounds];
+  uint32_t lr[kPartRounds];
+#pragma unroll
+  for (int r = 0; r < kPartRounds; ++r) {
+    const uint64_t k = wbase + r * 32 + lane;
+    int d = 4;
+    if (k < n) {
+      const int sy = (int)mv.SYM[k];
+      d = sy ? sy - 1 : 4;  // ended reads are dropped
+    }
+    dg[r] = d;
+    lr[r] = 0;
+    const unsigned act = __ballot_sync(0xffffffffu, d < 4);
+    if (d < 4) {
+      const unsigned m = __match_any_sync(act, d);
+      const uint32_t before = wc[w][d];
+      lr[r] = before + __popc(m & ((1u << lane) - 1u));
+      __syncwarp(m);
+      if (lane == __ffs(m) - 1) wc[w][d] = before + __popc(m);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    const int d = threadIdx.x;
+    uint32_t run = 0;
+#pragma unroll
+    for (int q = 0; q < kPartThreads / 32; ++q) {
+      const uint32_t t = wc[q][d];
+      wc[q][d] = run;
+      run += t;
+    }
+    boff[d + 1] = run;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    boff[0] = 0;
+    boff[2] += boff[1];
+    boff[3] += boff[2];
+    boff[4] += boff[3];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kPartRounds; ++r) {
+    const int d = dg[r];
+    if (d < 4) {
+      const uint64_t k = wbase + r * 32 + lane;
+      const uint32_t t = boff[d] + wc[w][d] + lr[r];
+      const typename BcrMove<PosT>::Item it = mv.compute(k);
+      s_id[t] = it.id;
+      s_np[t] = it.np;
+      s_win[t] = it.win;
+      s_sym[t] = it.sym;
+    }
+  }
+  __syncthreads();
+  const uint32_t b1 = boff[1], b2 = boff[2], b3 = boff[3], total = boff[4];
+  for (uint32_t t = threadIdx.x; t < total; t += kPartThreads) {
+    const int d = (t >= b1) + (t >= b2) + (t >= b3);
+    const uint64_t dest = tileoff[(uint64_t)d * ntiles + blockIdx.x] + (t - boff[d]);
+    mv.ID2[dest] = s_id[t];
+    mv.NP2[dest] = s_np[t];
+    mv.SYM2[dest] = s_sym[t];
+    mv.WIN2[dest] = s_win[t];
+  }
+}
 
 // tile_k0[t] = number of inserts with row < t*kMergeTile, for t in [0, ntiles] (ntiles+1 entries).
 template <class PosT>

@@ -123,6 +123,26 @@ static __global__ void scan_tile_apply_direct_kernel(uint64_t* __restrict__ data
   if (total_out && blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) *total_out = run;
 }
 
+// Whole array in one CTA (n <= kScanSmall): a thread sums its contiguous stretch, the stretch sums are scanned across the
+// block, the stretch is rewritten.  One launch instead of two for the short counter arrays of a column pass.
+static const uint64_t kScanSmall = 16384;
+static __global__ void __launch_bounds__(kScanThreads) scan_small_kernel(uint64_t* __restrict__ data, uint64_t n,
+                                                                        uint64_t* __restrict__ total_out) {
+  __shared__ uint64_t sh[9];
+  const uint32_t ipt = (uint32_t)((n + kScanThreads - 1) / kScanThreads);
+  const uint64_t b = (uint64_t)threadIdx.x * ipt, e = min(b + ipt, n);
+  uint64_t s = 0;
+  for (uint64_t i = b; i < e; ++i) s += data[i];
+  uint64_t total;
+  uint64_t run = block_excl_scan(s, sh, total);
+  for (uint64_t i = b; i < e; ++i) {
+    const uint64_t v = data[i];
+    data[i] = run;
+    run += v;
+  }
+  if (total_out && threadIdx.x == 0) *total_out = total;
+}
+
 // Number of uint64 workspace elements scan_exclusive needs for an n-element array.
 inline uint64_t scan_ws_elems(uint64_t n) {
   uint64_t ws = 0;
@@ -142,6 +162,10 @@ inline void scan_exclusive(sgx_ctx* ctx, uint64_t* data, uint64_t n, uint64_t* w
   const uint64_t ntiles = (n + kScanTile - 1) / kScanTile;
   if (ntiles == 1) {
     SGX_LAUNCH(ctx, scan_tile_apply_kernel, 1, kScanThreads, 0, data, n, (const uint64_t*)nullptr, total_dev);
+    return;
+  }
+  if (n <= kScanSmall) {
+    SGX_LAUNCH(ctx, scan_small_kernel, 1, kScanThreads, 0, data, n, total_dev);
     return;
   }
   SGX_LAUNCH(ctx, scan_tile_reduce_kernel, (unsigned)ntiles, kScanThreads, 0, data, n, ws);
