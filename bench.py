@@ -479,8 +479,9 @@ def main():
     # ---- index build (fwd + rev), resident and end to end.  N = 1: sgx_index_build_pair (both strands side by side on two
     #      streams).  N > 1: ONE index pair of the same read set built by all N GPUs together (strong scaling): the ranks
     #      split into two groups, one per strand -- the two indices are independent jobs, so the first factor of two costs
-    #      no communication -- and inside a group of N/2 > 1 GPUs the rows are sharded by leading k-mer bucket with an NCCL
-    #      all-to-all of the inserts every column pass (sgx_index_build_sharded).  Checked byte for byte against the
+    #      no communication -- and inside a group of N/2 > 1 GPUs the rows are sharded by leading k-mer bucket, the
+    #      inserts of every column pass written straight into the receivers' memory over NVLink (peer-memory exchange, NCCL
+    #      send/recv as the fall-back) and every rank keeping the run bytes of its shard (sgx_index_build_sharded_segments).  Checked byte for byte against the
     #      single-GPU build of the setup phase (itself checked against the reference's hashes above).
     isteps = args.index_steps or min(args.steps, 3)
     group = 0 if world == 1 else rank // (world // 2)   # which strand this rank works on
@@ -660,8 +661,8 @@ def main():
                   "ms_per_step": idx_ms, "steps": isteps, "device_ms_per_step": idx_dev_ms / isteps,
                   "scaling": "strong" if world > 1 else "single GPU",
                   "path": ("one cfg2 index pair built by %d GPUs: one group of %d per strand, %d of them building%s; byte-identical to "
-                           "the single-GPU build" % (world, group_size, sub_world, " (rows sharded by k-mer bucket, sgx_index_build_sharded "
-                           "over NCCL)" if sub_world > 1 else " (sgx_index_build, no collective: a strand of %d rows is below the sharding "
+                           "the single-GPU build" % (world, group_size, sub_world, " (rows sharded by k-mer bucket, inserts exchanged through "
+                           "peer memory over NVLink, sgx_index_build_sharded_segments)" if sub_world > 1 else " (sgx_index_build, no collective: a strand of %d rows is below the sharding "
                            "threshold of %d)" % (fi.n_suffixes, SHARD_MIN_ROWS))) if world > 1
                           else "sgx_index_build_pair (both strands side by side on two streams)",
                   "e2e": {"value": bases / (idx_e2e_ms * 1e-3) / 1e9, "unit": "Gbases/s", "ms_per_step": idx_e2e_ms,
@@ -735,7 +736,7 @@ def main():
 def cfg4_object(args, ctx, api, formats, torch, dist, rank, world, local, barrier, max_over_ranks, sum_over_ranks, cfg="cfg4"):
     """BASELINE.json configs[3] (cfg4: 100 Mbp genome, 50x 150 bp reads, 33.3 M reads, 5.03 G symbols per index) or
     configs[4] (cfg5: 64 Mbp, 40x 250 bp, 10.2 M reads, 2.57 G symbols): the index built by all ranks together (strand
-    groups, rows sharded by k-mer bucket with an NCCL all-to-all per column pass) and the overlap stage sharded by read
+    groups, rows sharded by k-mer bucket, inserts exchanged through peer memory over NVLink every column pass) and the overlap stage sharded by read
     range, each next to the time ONE GPU takes for the same job with the same kernels (rank 0, the others idle)."""
     scale = args.cfg4_scale
     shm = "/dev/shm/siga_b200_%s_%g.u8" % (cfg, scale)
