@@ -182,7 +182,7 @@ __device__ __forceinline__ uint32_t nib_sum(uint32_t acc) {
 // nibbles past the end of the array are zero.
 __device__ __forceinline__ void tile_checkpoints(const uint32_t out[4], uint64_t tile, uint64_t ntiles, uint32_t* sh_w /* 64 */,
                                                  uint2* __restrict__ blk, uint64_t* __restrict__ tiletot, uint32_t& pre1,
-                                                 uint32_t& pre2) {
+                                                 uint32_t& pre2, uint2* inblock_sm = nullptr /* optional, shared, 256 entries */) {
   // bit planes of the 32 nibbles packed into one word each (word i's plane shifted to bit i of every nibble): symbol
   // ranks are A=1 C=2 G=3 T=4, so A = b0 & ~b1, C = b1 & ~b0, G = b0 & b1, T = b2 -- four popcounts per thread
   const uint32_t M = 0x11111111u;
@@ -205,6 +205,9 @@ __device__ __forceinline__ void tile_checkpoints(const uint32_t out[4], uint64_t
     sh_w[threadIdx.x >> 3] = i1;
     sh_w[32 + (threadIdx.x >> 3)] = i2;
   }
+  // counts of the thread's 256-row block before its 32 rows: with sh_w (after the second barrier) any thread can
+  // rebuild the tile prefix of any other thread -- pre of thread i = sh_w[i >> 3] + inblock_sm[i]
+  if (inblock_sm) inblock_sm[threadIdx.x] = make_uint2(i1 - w1, i2 - w2);
   __syncthreads();
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
@@ -578,7 +581,7 @@ __global__ void __launch_bounds__(kMergeThreads, 8) bcr_merge_kernel(const uint8
   __shared__ uint32_t ckpt[64];
   __shared__ uint32_t sh[8];
   __shared__ uint32_t outsm[kMergeTile / 8];  // the finished tile (for the tile-local ranks)
-  __shared__ uint2 presm[kMergeThreads];      // symbol counts of the tile before each thread's rows
+  __shared__ uint2 presm[kMergeThreads];      // symbol counts of each thread's 256-row block before its rows
   __shared__ __align__(8) uint64_t stage_bar[2];  // completion of the bulk copy into oldw[0] / oldw[1]
   const uint64_t G = gridDim.x;
   uint64_t tile = blockIdx.x;
@@ -588,6 +591,7 @@ __global__ void __launch_bounds__(kMergeThreads, 8) bcr_merge_kernel(const uint8
     mbar_init(&stage_bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  mask[threadIdx.x] = 0;
   __syncthreads();
   uint32_t phases = 0;  // bit s = parity to wait for on stage_bar[s]
   // prologue: bounds of my first two tiles, old rows + first insert of the first
@@ -627,8 +631,8 @@ __global__ void __launch_bounds__(kMergeThreads, 8) bcr_merge_kernel(const uint8
     const uint64_t t1 = min(t0 + (uint64_t)kMergeTile, n_new);
     const uint64_t a0 = t0 - k0;  // first old row of this tile
     const uint32_t shift = (uint32_t)(a0 & 31);  // nibbles between the staged vector start and a0
-    mask[threadIdx.x] = 0;
-    __syncthreads();
+    // (mask[] is all zero here: every thread clears its word right after reading it, before the barrier that ends the
+    //  iteration; the prologue clears it once)
     // insert mask + symbols by ordinal (the first insert of every thread is already in registers)
     if (k0 + threadIdx.x < k1) {
       const uint32_t r = (uint32_t)(pre_np - t0);
@@ -644,6 +648,7 @@ __global__ void __launch_bounds__(kMergeThreads, 8) bcr_merge_kernel(const uint8
     phases ^= 1u << s;
     __syncthreads();
     const uint32_t m = mask[threadIdx.x];
+    mask[threadIdx.x] = 0;  // for the next tile (its atomicOrs come after the barrier at the end of this iteration)
     const uint32_t pre = block_excl_scan32((uint32_t)__popc(m), sh);  // inserts before my first row
     // the 32 old nibbles starting at the one that lands on my first row
     const uint32_t* ow = oldw[s];
@@ -690,25 +695,25 @@ __global__ void __launch_bounds__(kMergeThreads, 8) bcr_merge_kernel(const uint8
     }
     if (valid) *reinterpret_cast<uint4*>(Bn + row0 / 2) = make_uint4(out[0], out[1], out[2], out[3]);
     uint32_t cp1, cp2;
-    tile_checkpoints(out, tile, ntiles, ckpt, blk, tiletot, cp1, cp2);
+    if (rloc) {  // the finished tile, for the tile-local ranks below (visible after the barriers inside tile_checkpoints)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) outsm[4 * threadIdx.x + i] = out[i];
+    }
+    tile_checkpoints(out, tile, ntiles, ckpt, blk, tiletot, cp1, cp2, rloc ? presm : nullptr);
     if (rloc) {
       // Tile-local rank of every insert of the tile: rows of the tile before it that hold the same symbol = the count
       // before its thread's 32 rows (cp1 / cp2) + the matches among the rows of that thread below it.  The inserts are
       // taken by ordinal, one per thread and round, from the finished tile in shared memory: a thread looping over its
       // OWN inserts would leave most lanes idle (a tile holds 8192 / (pass + 1) inserts, under one per thread after
       // pass 31, but the busiest lane of a warp still has two or three).
-#pragma unroll
-      for (int i = 0; i < 4; ++i) outsm[4 * threadIdx.x + i] = out[i];
-      presm[threadIdx.x] = make_uint2(cp1, cp2);
-      __syncthreads();
       for (uint64_t o = threadIdx.x; o < k1 - k0; o += kMergeThreads) {
         const uint32_t r = (uint32_t)((uint64_t)NP[k0 + o] - t0);
         const uint32_t sy = symsh[o];
         uint32_t v = 0;
         if (sy) {
           const uint32_t owner = r >> 5, p = r & 31u, c = sy - 1;
-          const uint2 pf = presm[owner];
-          const uint32_t f = c < 2 ? pf.x : pf.y;
+          const uint2 pf = presm[owner];  // counts inside the owner's 256-row block; ckpt[] holds the blocks before it
+          const uint32_t f = c < 2 ? ckpt[owner >> 3] + pf.x : ckpt[32 + (owner >> 3)] + pf.y;
           const uint32_t* ow4 = outsm + 4 * owner;
           const uint32_t pat = sy * 0x11111111u, wq = p >> 3;
           uint32_t cnt = nib_eq_count(ow4[wq], pat, p & 7);
