@@ -80,9 +80,8 @@ static void bcr_passes(sgx_ctx* ctx, const sgx_reads* reads, const ReadAcc& acc,
     SGX_LAUNCH(ctx, (bcr_tile_bounds_kernel<PosT>), grid_for(nact + 1, 256), 256, 0, (const PosT*)NP2, nact, ntiles,
                tile_k0.p);
     k_merge.tick();
-    SGX_LAUNCH(ctx, (bcr_merge_kernel<PosT>), merge_grid<PosT>(ctx, ntiles), kMergeThreads, 0, (const uint8_t*)B, n_cur,
-               (const PosT*)NP2, (const uint8_t*)SYM2, nact, (const uint64_t*)tile_k0.p, Bn, n_new, ntiles, (uint2*)nullptr,
-               tiletot.p, RL2);
+    launch_merge<PosT>(ctx, (const uint8_t*)B, n_cur, (const PosT*)NP2, (const uint8_t*)SYM2, nact, (const uint64_t*)tile_k0.p, Bn,
+                       n_new, ntiles, tiletot.p, RL2);
     k_merge.tick();
     out->merge_launches++;
     out->merge_bytes += (n_cur + n_new) / 2 + nact * (sizeof(PosT) + 1);

@@ -734,6 +734,239 @@ __global__ void __launch_bounds__(kMergeThreads, 8) bcr_merge_kernel(const uint8
   }
 }
 
+// ---- merge, 64 rows per thread ------------------------------------------------------------------------------------------
+//
+// bcr_merge_kernel is bound by issue slots (70 % busy, profiles/r2_summary.md), and most of what it issues per tile does
+// not depend on the rows: the block-wide scan of the insert counts, the scan of the symbol counts, the pipeline
+// bookkeeping (bounds of the tiles ahead, first insert of the next tile, staging), the barriers.  Here a thread owns 64
+// rows -- two 32-row groups treated exactly as above, one after the other (old nibbles by funnel shifts, a gap per
+// insert) -- so a tile is walked by 128 threads and all of that is paid once per 64 rows instead of once per 32.  The
+// per-256-row checkpoints (blk) of the first kernel are not produced (no caller uses them any more).
+static const int kM64Threads = 128;
+
+// The 32 old nibbles that land on a 32-row group when it has no inserts, then a gap opened for each insert (mask m, lowest
+// row first; kk = ordinal of the group's first insert among the tile's inserts).
+__device__ __forceinline__ void merge_rows32(const uint32_t* __restrict__ ow, uint32_t o, uint32_t m, uint32_t kk,
+                                             const uint8_t* __restrict__ symsh, uint32_t out[4]) {
+  const uint32_t wi = o >> 3, sft = 4 * (o & 7);
+  {
+    const uint32_t w0 = ow[wi], w1 = ow[wi + 1], w2 = ow[wi + 2], w3 = ow[wi + 3], w4 = ow[wi + 4];
+    out[0] = __funnelshift_r(w0, w1, sft);
+    out[1] = __funnelshift_r(w1, w2, sft);
+    out[2] = __funnelshift_r(w2, w3, sft);
+    out[3] = __funnelshift_r(w3, w4, sft);
+  }
+  while (m) {
+    const uint32_t p = (uint32_t)__ffs(m) - 1;
+    m &= m - 1;
+    const uint32_t sy = symsh[kk++];
+    const uint32_t wq = p >> 3, bit = 4 * (p & 7);
+    // words above the insert's word move up by a nibble
+    if (wq < 3) out[3] = __funnelshift_l(out[2], out[3], 4);
+    if (wq < 2) out[2] = __funnelshift_l(out[1], out[2], 4);
+    if (wq < 1) out[1] = __funnelshift_l(out[0], out[1], 4);
+    // the insert's word: the nibbles from `bit` on move up by one, the symbol takes their place
+    const uint32_t w = wq == 0 ? out[0] : wq == 1 ? out[1] : wq == 2 ? out[2] : out[3];
+    const uint32_t lowm = (1u << bit) - 1u;
+    const uint32_t nw = (w & lowm) | (sy << bit) | ((w & ~lowm) << 4);
+    if (wq == 0) out[0] = nw;
+    if (wq == 1) out[1] = nw;
+    if (wq == 2) out[2] = nw;
+    if (wq == 3) out[3] = nw;
+  }
+}
+
+// A | C<<16 and G | T<<16 counts of the 32 nibbles of four words (bit planes, see tile_checkpoints)
+__device__ __forceinline__ void plane_counts32(const uint32_t out[4], uint32_t& w1, uint32_t& w2) {
+  const uint32_t M = 0x11111111u;
+  const uint32_t p0 = (out[0] & M) | ((out[1] << 1) & (M << 1)) | ((out[2] << 2) & (M << 2)) | ((out[3] << 3) & (M << 3));
+  const uint32_t p1 = ((out[0] >> 1) & M) | (out[1] & (M << 1)) | ((out[2] << 1) & (M << 2)) | ((out[3] << 2) & (M << 3));
+  const uint32_t p2 = ((out[0] >> 2) & M) | ((out[1] >> 1) & (M << 1)) | (out[2] & (M << 2)) | ((out[3] << 1) & (M << 3));
+  w1 = (uint32_t)__popc(p0 & ~p1) | ((uint32_t)__popc(p1 & ~p0) << 16);
+  w2 = (uint32_t)__popc(p0 & p1) | ((uint32_t)__popc(p2) << 16);
+}
+
+template <class PosT>
+__global__ void __launch_bounds__(kM64Threads, 12) bcr_merge64_kernel(const uint8_t* __restrict__ Bo, uint64_t n_old,
+                                                                      const PosT* __restrict__ NP, const uint8_t* __restrict__ SYM,
+                                                                      uint64_t nact, const uint64_t* __restrict__ tile_k0,
+                                                                      uint8_t* __restrict__ Bn, uint64_t n_new, uint64_t ntiles,
+                                                                      uint64_t* __restrict__ tiletot, uint16_t* __restrict__ rloc) {
+  __shared__ __align__(16) uint32_t oldw[2][kMergeOldWords];
+  __shared__ uint32_t mask[kMergeTile / 32];   // thread t owns words 2 t and 2 t + 1
+  __shared__ uint8_t symsh[kMergeTile];        // symbols of the tile's inserts, by ordinal
+  __shared__ uint32_t sh[4];                   // insert counts of the warps
+  __shared__ uint32_t wtot[2][4];              // symbol counts of the warps (A | C << 16, G | T << 16)
+  __shared__ uint32_t outsm[kMergeTile / 8];   // the finished tile (for the tile-local ranks)
+  __shared__ uint2 presm[kM64Threads];         // symbol counts of each thread's warp before its 64 rows
+  __shared__ __align__(8) uint64_t stage_bar[2];
+  (void)n_old;
+  (void)nact;
+  const uint32_t G = gridDim.x;
+  const uint32_t T = threadIdx.x, lane = T & 31, wp = T >> 5;
+  uint64_t tile = blockIdx.x;
+  if (tile >= ntiles) return;
+  if (T == 0) {
+    mbar_init(&stage_bar[0], 1);
+    mbar_init(&stage_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  mask[2 * T] = 0;
+  mask[2 * T + 1] = 0;
+  __syncthreads();
+  uint32_t phases = 0;
+  uint64_t k0 = tile_k0[tile], k1 = tile_k0[tile + 1];
+  uint64_t kn0 = 0, kn1 = 0;
+  if (tile + G < ntiles) {
+    kn0 = tile_k0[tile + G];
+    kn1 = tile_k0[tile + G + 1];
+  }
+  merge_stage_old(Bo, tile, n_new, k0, k1, oldw[0], &stage_bar[0]);
+  uint64_t pre_np = 0;
+  uint32_t pre_sym = 0;
+  if (k0 + T < k1) {
+    pre_np = (uint64_t)NP[k0 + T];
+    pre_sym = SYM[k0 + T];
+  }
+  int s = 0;
+  for (;; tile += G, s ^= 1) {
+    const uint64_t tn = tile + G;
+    const bool have_next = tn < ntiles;
+    if (have_next) merge_stage_old(Bo, tn, n_new, kn0, kn1, oldw[s ^ 1], &stage_bar[s ^ 1]);
+    uint64_t knn0 = 0, knn1 = 0;
+    if (tn + G < ntiles) {
+      knn0 = tile_k0[tn + G];
+      knn1 = tile_k0[tn + G + 1];
+    }
+    uint64_t nxt_np = 0;
+    uint32_t nxt_sym = 0;
+    if (have_next && kn0 + T < kn1) {
+      nxt_np = (uint64_t)NP[kn0 + T];
+      nxt_sym = SYM[kn0 + T];
+    }
+    const uint64_t t0 = tile * kMergeTile;
+    const uint64_t t1 = min(t0 + (uint64_t)kMergeTile, n_new);
+    const uint32_t nins = (uint32_t)(k1 - k0);
+    const uint32_t shift = (uint32_t)((t0 - k0) & 31);  // nibbles between the staged vector start and the tile's first old row
+    // insert mask + symbols by ordinal (mask[] is all zero here; the first insert of every thread is in registers)
+    if (T < nins) {
+      const uint32_t r = (uint32_t)(pre_np - t0);
+      atomicOr(&mask[r >> 5], 1u << (r & 31));
+      symsh[T] = (uint8_t)pre_sym;
+    }
+    for (uint32_t o = T + kM64Threads; o < nins; o += kM64Threads) {
+      const uint32_t r = (uint32_t)((uint64_t)NP[k0 + o] - t0);
+      atomicOr(&mask[r >> 5], 1u << (r & 31));
+      symsh[o] = SYM[k0 + o];
+    }
+    mbar_wait(&stage_bar[s], (phases >> s) & 1u);
+    phases ^= 1u << s;
+    __syncthreads();
+    const uint32_t m0 = mask[2 * T], m1 = mask[2 * T + 1];
+    mask[2 * T] = 0;  // for the next tile (its atomicOrs come after the barrier at the end of this iteration)
+    mask[2 * T + 1] = 0;
+    const uint32_t c0 = (uint32_t)__popc(m0), c1 = (uint32_t)__popc(m1);
+    // inserts before my first row: scan across the warp, warp sums through shared memory
+    uint32_t incl = c0 + c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((int)lane >= o) incl += y;
+    }
+    if (lane == 31) sh[wp] = incl;
+    __syncthreads();
+    uint32_t pre = incl - (c0 + c1);
+#pragma unroll
+    for (uint32_t q = 0; q < 3; ++q)
+      if (q < wp) pre += sh[q];
+    const uint32_t* ow = oldw[s];
+    uint32_t outA[4], outB[4];
+    merge_rows32(ow, shift + T * 64 - pre, m0, pre, symsh, outA);
+    merge_rows32(ow, shift + T * 64 + 32 - (pre + c0), m1, pre + c0, symsh, outB);
+    const uint64_t row0 = t0 + (uint64_t)T * 64;
+    if (t1 - t0 != (uint64_t)kMergeTile) {  // only the last tile of the array is partial: rows past the end stay zero
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t* out = h ? outB : outA;
+        const uint64_t r = row0 + 32 * h;
+        const uint32_t valid = r >= t1 ? 0u : (uint32_t)min((uint64_t)32, t1 - r);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t vw = valid >= 8u * (i + 1) ? 8u : (valid > 8u * i ? valid - 8u * i : 0u);
+          out[i] &= vw >= 8 ? 0xffffffffu : ((1u << (4 * vw)) - 1u);
+        }
+      }
+    }
+    if (row0 < t1) {
+      uint4* dst = reinterpret_cast<uint4*>(Bn + row0 / 2);
+      dst[0] = make_uint4(outA[0], outA[1], outA[2], outA[3]);
+      if (row0 + 32 < t1) dst[1] = make_uint4(outB[0], outB[1], outB[2], outB[3]);
+    }
+    // symbol counts: per thread, scanned across the warp; warp sums through shared memory
+    uint32_t a1, a2, b1, b2;
+    plane_counts32(outA, a1, a2);
+    plane_counts32(outB, b1, b2);
+    const uint32_t w1 = a1 + b1, w2 = a2 + b2;  // packed 16-bit fields: a tile holds at most 8192 of one symbol
+    uint32_t i1 = w1, i2 = w2;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y1 = __shfl_up_sync(0xffffffffu, i1, o), y2 = __shfl_up_sync(0xffffffffu, i2, o);
+      if ((int)lane >= o) {
+        i1 += y1;
+        i2 += y2;
+      }
+    }
+    if (lane == 31) {
+      wtot[0][wp] = i1;
+      wtot[1][wp] = i2;
+    }
+    if (rloc) {
+      reinterpret_cast<uint4*>(outsm)[2 * T] = make_uint4(outA[0], outA[1], outA[2], outA[3]);
+      reinterpret_cast<uint4*>(outsm)[2 * T + 1] = make_uint4(outB[0], outB[1], outB[2], outB[3]);
+      presm[T] = make_uint2(i1 - w1, i2 - w2);
+    }
+    __syncthreads();
+    if (T == 0) {
+      const uint32_t x1 = wtot[0][0] + wtot[0][1] + wtot[0][2] + wtot[0][3], x2 = wtot[1][0] + wtot[1][1] + wtot[1][2] + wtot[1][3];
+      tiletot[0 * ntiles + tile] = x1 & 0xffffu;
+      tiletot[1 * ntiles + tile] = x1 >> 16;
+      tiletot[2 * ntiles + tile] = x2 & 0xffffu;
+      tiletot[3 * ntiles + tile] = x2 >> 16;
+    }
+    if (rloc) {
+      // tile-local rank of every insert, one insert per thread and round, from the finished tile in shared memory
+      const uint32_t e1[4] = {0u, wtot[0][0], wtot[0][0] + wtot[0][1], wtot[0][0] + wtot[0][1] + wtot[0][2]};
+      const uint32_t e2[4] = {0u, wtot[1][0], wtot[1][0] + wtot[1][1], wtot[1][0] + wtot[1][1] + wtot[1][2]};
+      for (uint32_t o = T; o < nins; o += kM64Threads) {
+        const uint32_t r = (uint32_t)((uint64_t)NP[k0 + o] - t0);
+        const uint32_t sy = symsh[o];
+        uint32_t v = 0;
+        if (sy) {
+          const uint32_t owner = r >> 6, p = r & 63u, c = sy - 1, ow_wp = owner >> 5;
+          const uint2 pf = presm[owner];
+          const uint32_t base1 = ow_wp == 0 ? e1[0] : ow_wp == 1 ? e1[1] : ow_wp == 2 ? e1[2] : e1[3];
+          const uint32_t base2 = ow_wp == 0 ? e2[0] : ow_wp == 1 ? e2[1] : ow_wp == 2 ? e2[2] : e2[3];
+          const uint32_t f = c < 2 ? base1 + pf.x : base2 + pf.y;
+          const uint32_t* ow8 = outsm + 8 * owner;
+          const uint32_t pat = sy * 0x11111111u, wq = p >> 3;
+          uint32_t cnt = nib_eq_count(ow8[wq], pat, p & 7);
+          for (uint32_t i = 0; i < wq; ++i) cnt += nib_eq_count(ow8[i], pat, 8);
+          v = ((c & 1) ? (f >> 16) : (f & 0xffffu)) + cnt;
+        }
+        rloc[k0 + o] = (uint16_t)v;
+      }
+    }
+    __syncthreads();  // symsh / oldw[s] / sh / wtot / outsm / presm are free for the next iteration
+    if (!have_next) break;
+    k0 = kn0;
+    k1 = kn1;
+    kn0 = knn0;
+    kn1 = knn1;
+    pre_np = nxt_np;
+    pre_sym = nxt_sym;
+  }
+}
+
 // ---- 3. run-length encoding ------------------------------------------------------------------------------------------
 
 // Run heads of a nibble array, 32 rows (one 16-byte vector) per thread: bit i of the returned mask is set when row
@@ -850,6 +1083,37 @@ inline unsigned merge_grid(const sgx_ctx* ctx, uint64_t ntiles) {
   }
   const uint64_t cap = (uint64_t)ctx->sm_count * (uint64_t)per_sm;
   return (unsigned)(ntiles < cap ? (ntiles ? ntiles : 1) : cap);
+}
+
+template <class PosT>
+inline unsigned merge64_grid(const sgx_ctx* ctx, uint64_t ntiles) {
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bcr_merge64_kernel<PosT>, kM64Threads, 0) != cudaSuccess || n < 1) n = 8;
+    per_sm = n;
+  }
+  const uint64_t cap = (uint64_t)ctx->sm_count * (uint64_t)per_sm;
+  return (unsigned)(ntiles < cap ? (ntiles ? ntiles : 1) : cap);
+}
+
+// The merge of one column pass.  SGX_MERGE=32 selects the first kernel (32 rows per thread), the default is the
+// 64-rows-per-thread kernel.
+template <class PosT>
+inline void launch_merge(sgx_ctx* ctx, const uint8_t* Bo, uint64_t n_old, const PosT* NP, const uint8_t* SYM, uint64_t nact,
+                         const uint64_t* tile_k0, uint8_t* Bn, uint64_t n_new, uint64_t ntiles, uint64_t* tiletot, uint16_t* rloc) {
+  static int which = 0;
+  if (which == 0) {
+    const char* e = getenv("SGX_MERGE");
+    which = (e && atoi(e) == 32) ? 32 : 64;
+  }
+  if (which == 32) {
+    SGX_LAUNCH(ctx, (bcr_merge_kernel<PosT>), merge_grid<PosT>(ctx, ntiles), kMergeThreads, 0, Bo, n_old, NP, SYM, nact, tile_k0, Bn,
+               n_new, ntiles, (uint2*)nullptr, tiletot, rloc);
+  } else {
+    SGX_LAUNCH(ctx, (bcr_merge64_kernel<PosT>), merge64_grid<PosT>(ctx, ntiles), kM64Threads, 0, Bo, n_old, NP, SYM, nact, tile_k0,
+               Bn, n_new, ntiles, tiletot, rloc);
+  }
 }
 
 // ---- host helpers defined in index.cu, shared with index_sharded.cu ------------------------------------------------

@@ -618,9 +618,8 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
         SGX_LAUNCH(ctx, (bcr_tile_bounds_kernel<PosT>), grid_for(held_new + 1, 256), 256, 0, (const PosT*)s.NP2, held_new,
                    ntiles, s.tile_k0.p);
         k_merge.tick();
-        SGX_LAUNCH(ctx, (bcr_merge_kernel<PosT>), merge_grid<PosT>(ctx, ntiles), kMergeThreads, 0, (const uint8_t*)s.B, s.n_cur,
-                   (const PosT*)s.NP2, (const uint8_t*)s.SYM.p, held_new, (const uint64_t*)s.tile_k0.p, s.Bn, rows_new, ntiles,
-                   (uint2*)nullptr, s.tiletot.p, s.RL.p);
+        launch_merge<PosT>(ctx, (const uint8_t*)s.B, s.n_cur, (const PosT*)s.NP2, (const uint8_t*)s.SYM.p, held_new,
+                           (const uint64_t*)s.tile_k0.p, s.Bn, rows_new, ntiles, s.tiletot.p, s.RL.p);
         k_merge.tick();
         out->merge_launches++;
         out->merge_bytes += (s.n_cur + rows_new) / 2 + held_new * (sizeof(PosT) + 1);
