@@ -100,26 +100,96 @@ static void bcr_passes(sgx_ctx* ctx, const sgx_reads* reads, const ReadAcc& acc,
   *final_B = B;
 }
 
-// Content sort of n read ids (stable): LSD radix sort of the reads as strings of 32-base (64-bit) key chunks, last chunk
-// first.  One gather per read and chunk builds the keys; the 8-bit passes inside a chunk stream (key, id) pairs.  Bases
-// past the end of a read count as 'A' in the key, and the read length is the least significant key, so that a read
-// that is a proper prefix of another sorts first ('$' < 'A').  The result is in `ids`.
+// Content sort of n read ids (stable).  The reads are strings of 32-base (64-bit) key chunks; bases past the end of a read
+// count as 'A' in the key, and the read length is the least significant key, so that a read that is a proper prefix of
+// another sorts first ('$' < 'A').  A plain LSD radix sort walks all chunks of all reads (38 eight-bit passes at 150
+// bases).  Here ALL reads are sorted by their first chunk only; what that leaves tied -- reads that share their first 32
+// bases, a quarter of a 100x read set -- is pulled out, sorted LSD by (length,) the remaining chunks and finally by tie
+// group, and put back into the places the tied reads held (the groups are contiguous and in order, so the sorted tied
+// list maps one to one onto the tied places).  One gather per read and chunk builds the keys; the 8-bit passes inside a
+// chunk stream (key, id) pairs.  The result is in `ids`; `keys` holds nothing useful afterwards.
+struct TiedDigit {
+  const uint64_t* keys;
+  uint64_t n;
+  __device__ __forceinline__ int operator()(uint64_t k) const {
+    const uint64_t v = keys[k];
+    return ((k > 0 && keys[k - 1] == v) || (k + 1 < n && keys[k + 1] == v)) ? 0 : 255;
+  }
+};
+struct PlaceMove {
+  uint32_t* P;
+  __device__ __forceinline__ void operator()(uint64_t k, uint64_t dest) const { P[dest] = (uint32_t)k; }
+};
+static __global__ void tied_take_kernel(const uint32_t* __restrict__ ids, const uint64_t* __restrict__ keys,
+                                        const uint32_t* __restrict__ P, uint64_t nt, uint32_t* __restrict__ T,
+                                        uint64_t* __restrict__ heads) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nt) return;
+  T[k] = ids[P[k]];
+  heads[k] = (k == 0 || keys[P[k]] != keys[P[k - 1]]) ? 1 : 0;  // neighbours in the tied list with one key = one group
+}
+static __global__ void tied_group_kernel(const uint64_t* __restrict__ excl, const uint64_t* __restrict__ total,
+                                         const uint32_t* __restrict__ T, uint64_t nt, uint32_t* __restrict__ group_of) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nt) return;
+  const uint64_t incl = k + 1 < nt ? excl[k + 1] : *total;
+  group_of[T[k]] = (uint32_t)(incl - 1);
+}
+static __global__ void group_keys_kernel(const uint32_t* __restrict__ group_of, const uint32_t* __restrict__ T, uint64_t nt,
+                                         uint64_t* __restrict__ keys) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < nt) keys[k] = group_of[T[k]];
+}
+static __global__ void tied_put_kernel(const uint32_t* __restrict__ P, const uint32_t* __restrict__ T, uint64_t nt,
+                                       uint32_t* __restrict__ ids) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < nt) ids[P[k]] = T[k];
+}
+
 void index_content_sort(sgx_ctx* ctx, const sgx_reads* reads, const ReadAcc& acc, uint32_t* ids, uint32_t* ids_alt,
                         uint64_t* keys, uint64_t* keys_alt, uint64_t n, uint64_t* part_ws) {
   if (n == 0) return;
   const uint32_t lmax = reads->max_len;
-  if (reads->min_len != lmax) {
+  const bool variable = reads->min_len != lmax;
+  const uint32_t nchunks = (lmax + 31) / 32;
+  // ---- everything by the first chunk
+  const uint32_t nb0 = std::min<uint32_t>(32, lmax);
+  SGX_LAUNCH(ctx, chunk_keys_kernel, grid_for(n, 256), 256, 0, acc, (const uint32_t*)ids, n, 0u, nb0, keys);
+  radix_sort_pairs(ctx, keys, ids, keys_alt, ids_alt, n, 2 * (int)nb0, part_ws);
+  if (nchunks == 1 && !variable) return;
+  // ---- the places of the reads that are still tied
+  DevBuf<uint32_t> P(n), T2(n), group_of(reads->n);
+  DevBuf<uint64_t> heads(n + 1), scan_ws(scan_ws_elems(n + 1)), d_cnt(1);
+  TiedDigit td{keys, n};
+  PlaceMove pm{P.p};
+  partition_pass<1>(ctx, td, pm, n, part_ws, d_cnt.p);
+  uint64_t nt = 0;
+  SGX_CUDA(cudaMemcpyAsync(&nt, d_cnt.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  SGX_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (nt == 0) return;
+  uint32_t* T = ids_alt;
+  SGX_LAUNCH(ctx, tied_take_kernel, grid_for(nt, 256), 256, 0, (const uint32_t*)ids, (const uint64_t*)keys, (const uint32_t*)P.p, nt, T,
+             heads.p);
+  scan_exclusive(ctx, heads.p, nt, scan_ws.p, d_cnt.p);
+  SGX_LAUNCH(ctx, tied_group_kernel, grid_for(nt, 256), 256, 0, (const uint64_t*)heads.p, (const uint64_t*)d_cnt.p, (const uint32_t*)T,
+             nt, group_of.p);
+  // ---- the tied reads: LSD by length, chunks last to second, tie group
+  if (variable) {
     int lbits = 1;
     while ((1u << lbits) <= lmax) ++lbits;
-    SGX_LAUNCH(ctx, len_keys_kernel, grid_for(n, 256), 256, 0, acc.rv, (const uint32_t*)ids, n, keys);
-    radix_sort_pairs(ctx, keys, ids, keys_alt, ids_alt, n, lbits, part_ws);
+    SGX_LAUNCH(ctx, len_keys_kernel, grid_for(nt, 256), 256, 0, acc.rv, (const uint32_t*)T, nt, keys);
+    radix_sort_pairs(ctx, keys, T, keys_alt, T2.p, nt, lbits, part_ws);
   }
-  const uint32_t nchunks = (lmax + 31) / 32;
-  for (uint32_t ch = nchunks; ch-- > 0;) {
+  for (uint32_t ch = nchunks; ch-- > 1;) {
     const uint32_t nbases = std::min<uint32_t>(32, lmax - 32 * ch);
-    SGX_LAUNCH(ctx, chunk_keys_kernel, grid_for(n, 256), 256, 0, acc, (const uint32_t*)ids, n, 32 * ch, nbases, keys);
-    radix_sort_pairs(ctx, keys, ids, keys_alt, ids_alt, n, 2 * (int)nbases, part_ws);
+    SGX_LAUNCH(ctx, chunk_keys_kernel, grid_for(nt, 256), 256, 0, acc, (const uint32_t*)T, nt, 32 * ch, nbases, keys);
+    radix_sort_pairs(ctx, keys, T, keys_alt, T2.p, nt, 2 * (int)nbases, part_ws);
   }
+  int gbits = 1;
+  while (((uint64_t)1 << gbits) < nt) ++gbits;  // group indices are below nt
+  SGX_LAUNCH(ctx, group_keys_kernel, grid_for(nt, 256), 256, 0, (const uint32_t*)group_of.p, (const uint32_t*)T, nt, keys);
+  radix_sort_pairs(ctx, keys, T, keys_alt, T2.p, nt, gbits, part_ws);
+  SGX_LAUNCH(ctx, tied_put_kernel, grid_for(nt, 256), 256, 0, (const uint32_t*)P.p, (const uint32_t*)T, nt, ids);
 }
 
 void index_read_order(sgx_ctx* ctx, const sgx_reads* reads, const ReadAcc& acc, int order, uint32_t* d_sai,
