@@ -92,32 +92,51 @@ static __global__ void __launch_bounds__(256) key_hist_kernel(ReadAcc acc, uint6
   }
 }
 
-// rows[g] += number of suffixes of reads [r0, r1) owned by shard g
+// rows[g] += number of suffixes of reads [r0, r1) owned by shard g.  A read has at most 2^16 suffixes here (longer reads
+// take the 64-bit counters of the tail loop), so the sixteen per-thread counters are 16-bit fields of four registers.
 static __global__ void __launch_bounds__(256) shard_rows_kernel(ReadAcc acc, uint64_t r0, uint64_t r1, ShardBounds bounds,
                                                                 unsigned long long* __restrict__ rows) {
+  __shared__ unsigned long long s_rows[kMaxShards];
+  if (threadIdx.x < kMaxShards) s_rows[threadIdx.x] = 0;
+  __syncthreads();
   const uint64_t id64 = r0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t cnt[kMaxShards];
-#pragma unroll
-  for (int g = 0; g < kMaxShards; ++g) cnt[g] = 0;
+  const int world = bounds.world;
+  uint64_t c4[4] = {0, 0, 0, 0};  // counter g = bits [16 (g & 3), 16 (g & 3) + 16) of c4[g >> 2]
   if (id64 < r1) {
     const uint32_t id = (uint32_t)id64;
     const uint32_t l = acc.rv.len[id];
     uint32_t key = 0;
-    cnt[0] = 1;  // the '$' suffix
+    c4[0] = 1;  // the '$' suffix
+    uint32_t since = 1;
     for (uint32_t col = l; col-- > 0;) {
       key = (acc.code(id, col, l) + 1u) * kKeyTop + key / 5u;
-      const int o = bounds.owner(key);
+      int o = 0;
+      for (int i = 1; i < world; ++i) o += key >= bounds.b[i] ? 1 : 0;
+      const uint64_t inc = 1ull << (16 * (o & 3));
+      const int w = o >> 2;
+      c4[0] += w == 0 ? inc : 0ull;
+      c4[1] += w == 1 ? inc : 0ull;
+      c4[2] += w == 2 ? inc : 0ull;
+      c4[3] += w == 3 ? inc : 0ull;
+      if (++since == 0xffffu) {  // flush before a field can overflow
 #pragma unroll
-      for (int g = 0; g < kMaxShards; ++g) cnt[g] += (o == g) ? 1u : 0u;
+        for (int g = 0; g < kMaxShards; ++g) {
+          const unsigned long long v = (c4[g >> 2] >> (16 * (g & 3))) & 0xffffull;
+          if (v) atomicAdd(&s_rows[g], v);
+        }
+        c4[0] = c4[1] = c4[2] = c4[3] = 0;
+        since = 0;
+      }
     }
   }
 #pragma unroll
   for (int g = 0; g < kMaxShards; ++g) {
-    uint32_t v = cnt[g];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&rows[g], (unsigned long long)v);
+    uint32_t v = (uint32_t)((c4[g >> 2] >> (16 * (g & 3))) & 0xffffull);
+    v = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_rows[g], (unsigned long long)v);
   }
+  __syncthreads();
+  if (threadIdx.x < kMaxShards && s_rows[threadIdx.x]) atomicAdd(&rows[threadIdx.x], s_rows[threadIdx.x]);
 }
 
 // Column pass, sender side: for every suffix inserted here by the previous pass, the destination shard of the suffix
@@ -221,16 +240,50 @@ struct PushPlan {
   int world;
 };
 
+// What the peer transport reads of a held item.  Destination bucket and sender-local rank part are computed where they
+// are needed -- in the count kernel (bucket only) and in the send kernel -- instead of by a kernel of their own that
+// writes them out for the other two to read back (shard_rank_kernel, which the NCCL transport still uses).
+template <class PosT>
+struct HeldItems {
+  const uint32_t* ID;
+  const PosT* NP;
+  const uint8_t* SYM;
+  const uint32_t* KEY;
+  const uint32_t* WIN;
+  const uint16_t* rloc;
+  const uint64_t* scanned;  // scanned tile totals of the shard's rows, [4][ntiles]
+  uint64_t ntiles;
+  ShardBounds bounds;
+  // send bucket (destination-major, then c) of item k, 255 when the read ended in the previous pass; key = rolled key
+  __device__ __forceinline__ int bucket(uint64_t k, uint32_t& key) const {
+    const uint32_t sym = (uint32_t)SYM[k];
+    if (!sym) return 255;
+    key = sym * kKeyTop + KEY[k] / 5u;
+    int o = 0;
+    for (int i = 1; i < bounds.world; ++i) o += key >= bounds.b[i] ? 1 : 0;
+    return o * 4 + (int)sym - 1;
+  }
+  __device__ __forceinline__ PosT rank_part(uint64_t k, int c) const {
+    return (PosT)(__ldg(scanned + (uint64_t)c * ntiles + (uint64_t)NP[k] / kMergeTile) + rloc[k]);
+  }
+};
+template <class PosT>
+struct HeldDigit {
+  HeldItems<PosT> h;
+  __device__ __forceinline__ int operator()(uint64_t k) const {
+    uint32_t key;
+    return h.bucket(k, key);
+  }
+};
+
 // Scatter half of the send partition, fused with the push.  Same tile walk as part_scatter_kernel (prims.cuh) and the
 // same stable (destination, c) order, but the tile's 2048 wire items are first laid out in bucket order in shared
 // memory and then written by consecutive threads: every run of one bucket becomes one stretch of coalesced 16-byte
 // stores straight into the destination's slot (a warp of the plain scatter spreads its 32 items over up to 16 buckets,
 // which is tolerable in local HBM and wasteful over NVLink).  No send buffer, no second pass over the items.
 template <class PosT>
-__global__ void __launch_bounds__(kPartThreads) shard_send_kernel(const uint8_t* __restrict__ tmpDest, const uint32_t* __restrict__ ID,
-                                                                  const PosT* __restrict__ tmpPos, const uint8_t* __restrict__ SYM,
-                                                                  const uint32_t* __restrict__ KEY, const uint32_t* __restrict__ WIN,
-                                                                  uint64_t n, const uint64_t* __restrict__ tileoff, uint32_t ntiles,
+__global__ void __launch_bounds__(kPartThreads) shard_send_kernel(HeldItems<PosT> held, uint64_t n,
+                                                                  const uint64_t* __restrict__ tileoff, uint32_t ntiles,
                                                                   PushPlan pp, uint64_t epoch, unsigned* __restrict__ done) {
   extern __shared__ __align__(16) uint8_t send_smem[];
   WireItem<PosT>* stage = (WireItem<PosT>*)send_smem;  // kPartTile items
@@ -245,12 +298,13 @@ __global__ void __launch_bounds__(kPartThreads) shard_send_kernel(const uint8_t*
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint64_t wbase = (uint64_t)blockIdx.x * kPartTile + (uint64_t)w * (kPartRounds * 32);
   int dg[kPartRounds];
-  uint32_t lr[kPartRounds];
+  uint32_t lr[kPartRounds], keys[kPartRounds];
 #pragma unroll
   for (int r = 0; r < kPartRounds; ++r) {
     const uint64_t k = wbase + r * 32 + lane;
     int d = kSendBuckets;
-    if (k < n) d = (int)tmpDest[k];  // 255: the read has ended, nothing to send
+    keys[r] = 0;
+    if (k < n) d = held.bucket(k, keys[r]);  // 255: the read has ended, nothing to send
     dg[r] = d;
     lr[r] = 0;
     const unsigned act = __ballot_sync(0xffffffffu, d < kSendBuckets);
@@ -298,10 +352,10 @@ __global__ void __launch_bounds__(kPartThreads) shard_send_kernel(const uint8_t*
       const uint64_t k = wbase + r * 32 + lane;
       const uint32_t t = boff[d] + wc[w][d] + lr[r];
       WireItem<PosT> it;
-      it.pos = tmpPos[k];
-      it.id = ID[k];
-      it.key = (uint32_t)SYM[k] * kKeyTop + KEY[k] / 5u;
-      it.win = WIN[k];
+      it.pos = held.rank_part(k, d & 3);
+      it.id = held.ID[k];
+      it.key = keys[r];
+      it.win = held.WIN[k];
       stage[t] = it;
       bkt[t] = (uint8_t)d;
     }
@@ -434,7 +488,7 @@ struct Shard {
     SGX_CUDA(cudaMemsetAsync(B0.p, 0, padded, ctx->stream));
     SGX_CUDA(cudaMemsetAsync(B1.p, 0, padded, ctx->stream));
     SYM.alloc(N);
-    tmpDest.alloc(N);
+    if (!peer) tmpDest.alloc(N);
     ID0.alloc(N);
     ID1.alloc(N);
     KEY0.alloc(N);
@@ -449,7 +503,7 @@ struct Shard {
     }
     NP0.alloc(N);
     NP1.alloc(N);
-    tmpPos.alloc(N);
+    if (!peer) tmpPos.alloc(N);
     const uint64_t nt_max = rows_final / kMergeTile + 2;
     RL.alloc(N);
     tiletot.alloc(4 * nt_max);
@@ -534,7 +588,11 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
     for (int li = 0; li < nl; ++li) {
       Shard<PosT>& s = sh[li];
       uint32_t ntiles = 1;
-      if (s.held) {
+      if (s.held && peer) {
+        HeldDigit<PosT> hd{HeldItems<PosT>{s.ID, s.NP, s.SYM.p, s.KEY, s.WIN, s.RL.p, s.tiletot.p, s.nt, bounds}};
+        partition_count<kSendBuckets, HeldDigit<PosT> >(ctx, hd, s.held, s.part_ws.p, s.kept.p);
+        ntiles = part_tiles(s.held);
+      } else if (s.held) {
         SGX_LAUNCH(ctx, (shard_rank_kernel<PosT>), grid_for(s.held, 256), 256, 0, (const uint16_t*)s.RL.p,
                    (const uint64_t*)s.tiletot.p, s.nt, bounds, (const PosT*)s.NP, (const uint8_t*)s.SYM.p,
                    (const uint32_t*)s.KEY, s.held, s.tmpDest.p, s.tmpPos.p);
@@ -569,10 +627,9 @@ static void sharded_build(sgx_ctx* ctx, sgx_comm* cm, const sgx_reads* reads, co
         pp.slot[d] = cm->peer_addr[d] + parity_off + (size_t)s.g * slot_bytes;
         pp.flag[d] = comm_peer_flag(cm, d, s.g);
       }
-      SGX_LAUNCH(ctx, (shard_send_kernel<PosT>), part_tiles(s.held ? s.held : 1), kPartThreads, send_smem, (const uint8_t*)s.tmpDest.p,
-                 (const uint32_t*)s.ID, (const PosT*)s.tmpPos.p, (const uint8_t*)s.SYM.p, (const uint32_t*)s.KEY,
-                 (const uint32_t*)s.WIN, s.held, (const uint64_t*)s.part_ws.p, part_tiles(s.held ? s.held : 1), pp, epoch,
-                 s.push_done.p);
+      SGX_LAUNCH(ctx, (shard_send_kernel<PosT>), part_tiles(s.held ? s.held : 1), kPartThreads, send_smem,
+                 (HeldItems<PosT>{s.ID, s.NP, s.SYM.p, s.KEY, s.WIN, s.RL.p, s.tiletot.p, s.nt, bounds}), s.held,
+                 (const uint64_t*)s.part_ws.p, part_tiles(s.held ? s.held : 1), pp, epoch, s.push_done.p);
     }
     SGX_TRACE_TICK(k_gather);
     const double hw0 = trace ? now_ms() : 0;
