@@ -668,7 +668,7 @@ def main():
                   "e2e": {"value": bases / (idx_e2e_ms * 1e-3) / 1e9, "unit": "Gbases/s", "ms_per_step": idx_e2e_ms,
                           "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(len(fi.runs) + len(ri.runs) + 8 * n_reads)},
                   "gpu_launches": int(idx_launches),
-                  "roofline": {"bound": "hbm", "kernel": "bcr_merge_kernel", "achieved": merge_ach, "peak": hbm_peak, "unit": "GB/s",
+                  "roofline": {"bound": "hbm", "kernel": "bcr_merge64_kernel", "achieved": merge_ach, "peak": hbm_peak, "unit": "GB/s",
                                "frac": merge_ach / hbm_peak,
                                # DRAM bytes of ONE captured launch (pass 76 of 150: launches grow with the pass number, the
                                # average launch moves (n_old + n_new) / 2 + 5 B per insert = merge_bytes / merge_launches)
