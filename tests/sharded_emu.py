@@ -70,7 +70,7 @@ class GlooNet:
         return {me: [out[s][me] for s in range(self.world)]}
 
 
-def sharded_bwt_runs(reads, sord, net):
+def sharded_bwt_runs(reads, sord, net, slots=False):
     """Run bytes of the BWT of `reads` (list of bytes, already in the indexed orientation) given the sentinel order.
     Returns (segments per local shard {g: bytes}, rows per shard)."""
     K = consts()
@@ -125,6 +125,17 @@ def sharded_bwt_runs(reads, sord, net):
             assert len(buf) == int(n_in[g])
             for s in range(W):  # the offsets the NCCL path would use match the sender-major concatenation
                 assert int(roff[g * W + s]) == sum(len(recv[g][q]) for q in range(s))
+            if slots:
+                # the peer-memory transport (index_sharded.cu): the receive "buffer" is the shard's region, one slot of
+                # `slot_cap` items per sender (worst case: every read), whatever the counts -- the plan only needs to
+                # be told where each sender's block starts
+                slot_cap = N
+                buf = []
+                for q in range(W):
+                    buf += list(recv[g][q]) + [None] * (slot_cap - len(recv[g][q]))
+                roff = roff.copy()
+                for q in range(W):
+                    roff[g * W + q] = q * slot_cap
             out0 = np.zeros(K["send_buckets"] + 1, dtype=np.uint64)
             src0 = np.zeros(K["send_buckets"], dtype=np.uint64)
             Kc = np.zeros(K["send_buckets"], dtype=np.int64)

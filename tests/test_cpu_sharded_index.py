@@ -38,14 +38,18 @@ def _expected(reads, model):
     return formats.encode_runs(bwt).tobytes(), sai
 
 
+@pytest.mark.parametrize("slots", [False, True], ids=["packed_receive_buffer", "per_sender_slots"])
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
 @pytest.mark.parametrize("name", ["fixed", "varlen", "lowcomplexity"])
-def test_sharded_column_passes_match_oracle(world, name):
+def test_sharded_column_passes_match_oracle(world, name, slots):
+    """`slots`: the receive layout of the peer-memory transport (one worst-case-sized slot per sender in the receiver's
+    region) instead of the packed buffer of the send/recv transport; the same planning code places the inserts."""
     import sharded_emu
     reads = _read_sets()[name]
     for model in ("B", "A"):
         want, sai = _expected(reads, model)
-        segs, rows = sharded_emu.sharded_bwt_runs(reads, sharded_emu.sentinel_order(sai, model), sharded_emu.LocalNet(world))
+        segs, rows = sharded_emu.sharded_bwt_runs(reads, sharded_emu.sentinel_order(sai, model), sharded_emu.LocalNet(world),
+                                                  slots=slots)
         assert sum(rows.values()) == sum(len(r) + 1 for r in reads)
         assert b"".join(segs[g] for g in range(world)) == want, (name, model, world)
 
