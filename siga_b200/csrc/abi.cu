@@ -363,7 +363,13 @@ int sgx_comm_init_local(sgx_ctx* ctx, int shards, sgx_comm** out) {
 void sgx_comm_free(sgx_comm* comm) {
   if (!comm) return;
   cudaSetDevice(comm->ctx->device);
-  comm_destroy(comm);
+  sgx::g_stream = comm->ctx->stream;  // comm_destroy's farewell barrier allocates a scratch word on the context's stream
+  sgx::g_ctx = comm->ctx;
+  try {
+    comm_destroy(comm);
+  } catch (const sgx::Error&) {
+    cudaGetLastError();
+  }
 }
 
 int sgx_comm_world(const sgx_comm* comm) { return comm ? comm->world : 0; }

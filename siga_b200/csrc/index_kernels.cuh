@@ -798,7 +798,7 @@ __global__ void __launch_bounds__(kM64Threads, 12) bcr_merge64_kernel(const uint
   __shared__ uint32_t sh[4];                   // insert counts of the warps
   __shared__ uint32_t wtot[2][4];              // symbol counts of the warps (A | C << 16, G | T << 16)
   __shared__ uint32_t outsm[kMergeTile / 8];   // the finished tile (for the tile-local ranks)
-  __shared__ uint2 presm[kM64Threads];         // symbol counts of each thread's warp before its 64 rows
+  __shared__ uint2 presm[2 * kM64Threads];     // symbol counts of the owner's warp before each 32-row group
   __shared__ __align__(8) uint64_t stage_bar[2];
   (void)n_old;
   (void)nact;
@@ -923,7 +923,8 @@ __global__ void __launch_bounds__(kM64Threads, 12) bcr_merge64_kernel(const uint
     if (rloc) {
       reinterpret_cast<uint4*>(outsm)[2 * T] = make_uint4(outA[0], outA[1], outA[2], outA[3]);
       reinterpret_cast<uint4*>(outsm)[2 * T + 1] = make_uint4(outB[0], outB[1], outB[2], outB[3]);
-      presm[T] = make_uint2(i1 - w1, i2 - w2);
+      presm[2 * T] = make_uint2(i1 - w1, i2 - w2);
+      presm[2 * T + 1] = make_uint2(i1 - w1 + a1, i2 - w2 + a2);
     }
     __syncthreads();
     if (T == 0) {
@@ -942,15 +943,15 @@ __global__ void __launch_bounds__(kM64Threads, 12) bcr_merge64_kernel(const uint
         const uint32_t sy = symsh[o];
         uint32_t v = 0;
         if (sy) {
-          const uint32_t owner = r >> 6, p = r & 63u, c = sy - 1, ow_wp = owner >> 5;
-          const uint2 pf = presm[owner];
+          const uint32_t grp = r >> 5, p = r & 31u, c = sy - 1, ow_wp = grp >> 6;  // 32-row group, its thread's warp
+          const uint2 pf = presm[grp];
           const uint32_t base1 = ow_wp == 0 ? e1[0] : ow_wp == 1 ? e1[1] : ow_wp == 2 ? e1[2] : e1[3];
           const uint32_t base2 = ow_wp == 0 ? e2[0] : ow_wp == 1 ? e2[1] : ow_wp == 2 ? e2[2] : e2[3];
           const uint32_t f = c < 2 ? base1 + pf.x : base2 + pf.y;
-          const uint32_t* ow8 = outsm + 8 * owner;
+          const uint32_t* ow4 = outsm + 4 * grp;
           const uint32_t pat = sy * 0x11111111u, wq = p >> 3;
-          uint32_t cnt = nib_eq_count(ow8[wq], pat, p & 7);
-          for (uint32_t i = 0; i < wq; ++i) cnt += nib_eq_count(ow8[i], pat, 8);
+          uint32_t cnt = nib_eq_count(ow4[wq], pat, p & 7);
+          for (uint32_t i = 0; i < wq; ++i) cnt += nib_eq_count(ow4[i], pat, 8);
           v = ((c & 1) ? (f >> 16) : (f & 0xffffu)) + cnt;
         }
         rloc[k0 + o] = (uint16_t)v;
