@@ -43,8 +43,15 @@ static void bcr_passes(sgx_ctx* ctx, const sgx_reads* reads, const ReadAcc& acc,
   DevBuf<uint8_t> SYM0(N), SYM1(N);
   DevBuf<uint32_t> WIN0(N), WIN1(N);
   DevBuf<uint16_t> RL0(N), RL1(N);  // tile-local rank of every item's row (see tile_checkpoints)
-  DevBuf<uint64_t> tiletot(4 * nt_max), scan_ws(scan_ws_elems(4 * nt_max)), part_ws(part_ws_elems(N, 4)),
-      tile_k0(S / kMergeTile + 4);
+  DevBuf<uint64_t> tiletot(4 * nt_max), scan_ws(scan_ws_elems(4 * nt_max)), tile_k0(S / kMergeTile + 4);
+  // partition counters of the column passes, three buffers in rotation: pass j reads pw[j % 3] (counted by pass j - 1's
+  // scatter, or by the count kernel for the first pass), its scatter accumulates pass j + 1's into pw[(j + 1) % 3] and
+  // clears pw[(j + 2) % 3]
+  const uint64_t pw_elems = part_ws_elems(N, 4);
+  const uint32_t pw_counters = 4 * part_tiles(N ? N : 1);
+  DevBuf<uint64_t> pw_all(3 * pw_elems);
+  uint64_t* pw[3] = {pw_all.p, pw_all.p + pw_elems, pw_all.p + 2 * pw_elems};
+  SGX_CUDA(cudaMemsetAsync(pw[2], 0, pw_counters * sizeof(uint64_t), ctx->stream));
   uint32_t* ID = ID0.p;
   uint32_t* ID2 = ID1.p;
   PosT* NP = NP0.p;
@@ -71,9 +78,18 @@ static void bcr_passes(sgx_ctx* ctx, const sgx_reads* reads, const ReadAcc& acc,
     SymDigit dg{SYM};
     BcrMove<PosT> mv{acc, ID, WIN, j, uniform_len, ID2, NP2, SYM2, WIN2, tiletot.p, nt, N, SYM, NP, RL};
     if (nact_prev) {
-      partition_count<4, SymDigit>(ctx, dg, nact_prev, part_ws.p, (uint64_t*)nullptr);
-      SGX_LAUNCH(ctx, (bcr_scatter_kernel<PosT>), part_tiles(nact_prev), kPartThreads, 0, mv, nact_prev,
-                 (const uint64_t*)part_ws.p, part_tiles(nact_prev));
+      uint64_t* cur = pw[j % 3];
+      const uint32_t pt = part_tiles(nact_prev);
+      if (j == 1) {
+        partition_count<4, SymDigit>(ctx, dg, nact_prev, cur, (uint64_t*)nullptr);
+      } else {  // counted by the previous pass's scatter
+        const uint64_t c = (uint64_t)4 * pt;
+        scan_exclusive(ctx, cur, c, cur + c, (uint64_t*)nullptr);
+      }
+      const bool more = j < lmax && nact_by_pass[j + 1] > 0;
+      SGX_LAUNCH(ctx, (bcr_scatter_kernel<PosT>), pt, kPartThreads, 0, mv, nact_prev, (const uint64_t*)cur, pt,
+                 more ? (unsigned long long*)pw[(j + 1) % 3] : (unsigned long long*)nullptr, part_tiles(nact ? nact : 1),
+                 pw[(j + 2) % 3], pw_counters);
     }
     const uint64_t n_new = n_cur + nact;
     const uint64_t ntiles = (n_new + kMergeTile - 1) / kMergeTile;

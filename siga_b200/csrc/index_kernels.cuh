@@ -415,9 +415,15 @@ struct BcrMove {
 // Scatter half of a column pass's partition (same tile walk and order as part_scatter_kernel<4, SymDigit, BcrMove>), with
 // the tile's items laid out in bucket order in shared memory first: the four output arrays are then written by consecutive
 // threads at consecutive slots -- whole sectors of the byte array instead of eight bytes per warp and bucket.
+// The kernel also prepares the NEXT pass's partition: the items it writes are that pass's input, so while writing them it
+// counts their symbols per 2048-item tile of the output order (one atomic per distinct (tile, symbol) and warp) into
+// cnt_next -- the next pass then only scans those counters, its count kernel is gone -- and clears the counter buffer
+// of the pass after next (three buffers rotate: read, accumulate, clear).
 template <class PosT>
 __global__ void __launch_bounds__(kPartThreads) bcr_scatter_kernel(BcrMove<PosT> mv, uint64_t n, const uint64_t* __restrict__ tileoff,
-                                                                   uint32_t ntiles) {
+                                                                   uint32_t ntiles, unsigned long long* __restrict__ cnt_next,
+                                                                   uint32_t ntiles_next, uint64_t* __restrict__ clear_buf,
+                                                                   uint32_t clear_n) {
   __shared__ uint32_t wc[kPartThreads / 32][4];
   __shared__ uint32_t boff[5];
   __shared__ uint32_t s_id[kPartTile], s_win[kPartTile];
@@ -483,14 +489,32 @@ __global__ void __launch_bounds__(kPartThreads) bcr_scatter_kernel(BcrMove<PosT>
     }
   }
   __syncthreads();
+  for (uint32_t i = blockIdx.x * kPartThreads + threadIdx.x; i < clear_n; i += gridDim.x * kPartThreads) clear_buf[i] = 0;
   const uint32_t b1 = boff[1], b2 = boff[2], b3 = boff[3], total = boff[4];
-  for (uint32_t t = threadIdx.x; t < total; t += kPartThreads) {
-    const int d = (t >= b1) + (t >= b2) + (t >= b3);
-    const uint64_t dest = tileoff[(uint64_t)d * ntiles + blockIdx.x] + (t - boff[d]);
-    mv.ID2[dest] = s_id[t];
-    mv.NP2[dest] = s_np[t];
-    mv.SYM2[dest] = s_sym[t];
-    mv.WIN2[dest] = s_win[t];
+  for (uint32_t base = 0; base < total; base += kPartThreads) {  // warp-uniform trip count (the ballots below)
+    const uint32_t t = base + threadIdx.x;
+    const bool valid = t < total;
+    uint32_t sym = 0;
+    uint64_t dest = 0;
+    if (valid) {
+      const int d = (t >= b1) + (t >= b2) + (t >= b3);
+      dest = tileoff[(uint64_t)d * ntiles + blockIdx.x] + (t - boff[d]);
+      sym = s_sym[t];
+      mv.ID2[dest] = s_id[t];
+      mv.NP2[dest] = s_np[t];
+      mv.SYM2[dest] = (uint8_t)sym;
+      mv.WIN2[dest] = s_win[t];
+    }
+    if (cnt_next) {
+      const bool counts = valid && sym != 0;  // ended reads are dropped by the next partition
+      const unsigned act = __ballot_sync(0xffffffffu, counts);
+      if (counts) {
+        const uint32_t key = (uint32_t)(dest / kPartTile) * 4u + (sym - 1u);
+        const unsigned m = __match_any_sync(act, key);
+        if (lane == __ffs(m) - 1)
+          atomicAdd(&cnt_next[(uint64_t)(sym - 1u) * ntiles_next + dest / kPartTile], (unsigned long long)__popc(m));
+      }
+    }
   }
 }
 
