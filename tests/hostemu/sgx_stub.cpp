@@ -26,7 +26,7 @@ struct sgx_fm {
   std::vector<uint32_t> sai;  // sgx_fm_attach_reads
 };
 struct sgx_comm {
-  int unused;
+  int rank, world;
 };
 
 namespace {
@@ -36,10 +36,6 @@ namespace {
 bool fake_mode() {
   static const bool f = getenv("SGX_STUB_FAKE") && getenv("SGX_STUB_FAKE")[0] == '1';
   return f;
-}
-int no_device(sgx_ctx* ctx, const char* what) {
-  if (ctx) ctx->err = std::string(what) + ": not available in the host stand-in (needs a B200)";
-  return SGX_ENODEV;
 }
 }  // namespace
 
@@ -391,14 +387,39 @@ void sgx_index_out_free(sgx_index_out* o) {
   o->rle = nullptr;
   o->sai = nullptr;
 }
-int sgx_comm_unique_id(uint8_t*) { return SGX_ENODEV; }
-int sgx_comm_init(sgx_ctx* ctx, const uint8_t*, int, int, sgx_comm**) { return no_device(ctx, "sgx_comm_init"); }
-void sgx_comm_free(sgx_comm*) {}
-int sgx_index_build_sharded(sgx_ctx* ctx, sgx_comm*, const sgx_reads*, int, int, sgx_index_out*) {
-  return no_device(ctx, "sgx_index_build_sharded");
+// Stand-in communicator: no transport at all -- every rank computes the whole index and keeps its share of it.  Enough to
+// run the front-end's --gpus N code of `siga index` (id hand-out over pipes, all ranks of a strand group writing one .bwt
+// together with pwrite) on CPU processes.
+int sgx_comm_unique_id(uint8_t* id) {
+  memset(id, 0x5a, 128);
+  return SGX_OK;
 }
-int sgx_index_build_sharded_segments(sgx_ctx* ctx, sgx_comm*, const sgx_reads*, int, int, sgx_index_out*) {
-  return no_device(ctx, "sgx_index_build_sharded_segments");
+int sgx_comm_init(sgx_ctx* ctx, const uint8_t* id, int rank, int world, sgx_comm** out) {
+  if (!ctx || !id || !out || world < 1 || rank < 0 || rank >= world || id[0] != 0x5a) return SGX_EINVAL;
+  *out = new sgx_comm{rank, world};
+  return SGX_OK;
+}
+void sgx_comm_free(sgx_comm* c) { delete c; }
+int sgx_index_build_sharded(sgx_ctx* ctx, sgx_comm* comm, const sgx_reads* reads, int order, int reversed, sgx_index_out* out) {
+  if (!comm) return SGX_EINVAL;
+  const int rc = sgx_index_build(ctx, reads, order, reversed, out);
+  if (rc == SGX_OK && comm->rank != 0) {  // the run bytes are complete on rank 0 only
+    out->seg_bytes = 0;
+    out->rle[0] = 0;
+  }
+  return rc;
+}
+int sgx_index_build_sharded_segments(sgx_ctx* ctx, sgx_comm* comm, const sgx_reads* reads, int order, int reversed,
+                                     sgx_index_out* out) {
+  if (!comm) return SGX_EINVAL;
+  const int rc = sgx_index_build(ctx, reads, order, reversed, out);
+  if (rc != SGX_OK) return rc;
+  // rank r keeps bytes [n r / W, n (r + 1) / W) of the run bytes (uneven on purpose when n is not a multiple of W)
+  const uint64_t n = out->n_runs, a = n * (uint64_t)comm->rank / comm->world, b = n * (uint64_t)(comm->rank + 1) / comm->world;
+  memmove(out->rle, out->rle + a, b - a);
+  out->seg_offset = a;
+  out->seg_bytes = b - a;
+  return SGX_OK;
 }
 
 }  // extern "C"

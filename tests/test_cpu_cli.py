@@ -259,6 +259,19 @@ def test_index_front_end_equals_reference_files(algo):
         _cli(["index", "-a", algo, "-p", "two", "--gpus", "2", src], ours)
         for ext in (".bwt", ".rbwt", ".sai", ".rsai"):
             assert open(os.path.join(ours, "two" + ext), "rb").read() == open(os.path.join(ref, "reads" + ext), "rb").read(), ext
+        # a strand sharded over the workers of its group (forced below the size threshold): every worker writes the run
+        # bytes of its own share into the one .bwt (pwrite at its offset, header and final length by the group's first
+        # worker) -- three workers on one strand, then two groups of two; a longer stale file must not survive
+        for prefix, extra, exts in (("s3", ["--gpus", "3", "--no-reverse"], (".bwt", ".sai")),
+                                    ("s4", ["--gpus", "4"], (".bwt", ".rbwt", ".sai", ".rsai"))):
+            for ext in exts:
+                if "bwt" in ext:
+                    with open(os.path.join(ours, prefix + ext), "wb") as f:
+                        f.write(b"\xff" * (os.path.getsize(os.path.join(ref, "reads" + ext)) + 4096))
+            _cli(["index", "-a", algo, "-p", prefix] + extra + [src], ours, env=dict(os.environ, SIGA_SHARD_MIN_ROWS="0"))
+            assert sorted(f for f in os.listdir(ours) if f.startswith(prefix)) == sorted(prefix + e for e in exts)
+            for ext in exts:
+                assert open(os.path.join(ours, prefix + ext), "rb").read() == open(os.path.join(ref, "reads" + ext), "rb").read(), (prefix, ext)
 
 
 def test_whole_pipeline_through_the_front_end_gives_the_reference_contigs():
