@@ -12,20 +12,25 @@
 //   * The packed reads are replicated.  The read-start order (.sai) and the sentinel order are computed sharded too
 //     (sharded_read_order below: every shard sorts the reads whose first 8-mer it owns) and then all-gathered.
 //   * Column pass j: every shard LF-maps the suffixes it inserted in pass j-1 through ITS rows (local rank of the
-//     preceding base c), finds the owner of the new suffix from its key, and partitions (id, local rank part) by
-//     (destination shard, c).  One small all-gather carries the send counts and each shard's A/C/G/T totals; one
-//     all-to-all carries the inserts.  The receiver turns the sender-local rank part into its own local row with a
-//     per-(sender, symbol) constant
+//     preceding base c), finds the owner of the new suffix from its key, and partitions the inserts by (destination
+//     shard, c).  One small all-gather (NCCL, on a side stream) carries the send counts and each shard's A/C/G/T totals
+//     to the hosts; the inserts themselves are written by the scatter kernel of that partition STRAIGHT INTO THE
+//     RECEIVERS' MEMORY over NVLink -- every shard owns a receive region that all processes have mapped (cudaIpc), with
+//     one worst-case-sized slot per sender -- followed by the sender's arrival flag; the receiver's stream spins on its
+//     flags and goes on (section "exchange through peer memory" below).  Where the regions cannot be mapped, all ranks
+//     fall back to a send buffer + grouped ncclSend/ncclRecv.  The receiver turns the sender-local rank part into its
+//     own local row with a per-(sender, symbol) constant
 //         row = part + N + sum_{c'<c} T[c'] + sum_{s'<s} tot[s'][c] - sum_{c'<c} tot[s][c'] - first_row_of(receiver)
 //     The send partition is by (destination, c), so every sender's block arrives ordered by (c, sender row) and the
 //     receiver's row order -- for one c the new row grows with the old global row, i.e. with (sender, sender row) --
 //     is a permutation known from the gathered counts: one placement kernel, no counting pass.  Then the same
 //     streaming merge.
 //   * Run-length encoding per shard; a run crossing a seam belongs to the shard where it starts (run_length() in
-//     index_kernels.cuh), the segments are concatenated on shard 0.
+//     index_kernels.cuh); the segments are concatenated on shard 0 (sgx_index_build_sharded) or stay where they are,
+//     each with its offset (sgx_index_build_sharded_segments).
 //
-// The transport is sgx_comm: NCCL between processes, or device copies between virtual shards of one context
-// (the mode the single-GPU parity tests run).
+// The communicator is sgx_comm: one process per GPU, or virtual shards of one context (the mode the single-GPU parity
+// tests run: same kernels, the "peers" in the same HBM).
 #include <algorithm>
 #include <chrono>
 
