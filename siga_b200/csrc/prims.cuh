@@ -123,24 +123,50 @@ static __global__ void scan_tile_apply_direct_kernel(uint64_t* __restrict__ data
   if (total_out && blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) *total_out = run;
 }
 
-// Whole array in one CTA (n <= kScanSmall): a thread sums its contiguous stretch, the stretch sums are scanned across the
-// block, the stretch is rewritten.  One launch instead of two for the short counter arrays of a column pass.
+// Whole array in one CTA of 1024 threads (n <= kScanSmall): a thread sums its contiguous stretch (at most 16 values, all
+// loads issued before the first add), the stretch sums are scanned across the block (warp shuffles, the 32 warp sums by
+// the first warp), the stretch is rewritten.  One launch instead of two for the short counter arrays of a column pass.
 static const uint64_t kScanSmall = 16384;
-static __global__ void __launch_bounds__(kScanThreads) scan_small_kernel(uint64_t* __restrict__ data, uint64_t n,
-                                                                        uint64_t* __restrict__ total_out) {
-  __shared__ uint64_t sh[9];
-  const uint32_t ipt = (uint32_t)((n + kScanThreads - 1) / kScanThreads);
-  const uint64_t b = (uint64_t)threadIdx.x * ipt, e = min(b + ipt, n);
+static const int kScanSmallThreads = 1024;
+static const int kScanSmallIpt = (int)(kScanSmall / kScanSmallThreads);  // 16
+static __global__ void __launch_bounds__(kScanSmallThreads) scan_small_kernel(uint64_t* __restrict__ data, uint64_t n,
+                                                                             uint64_t* __restrict__ total_out) {
+  __shared__ uint64_t wsum[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t ipt = (uint32_t)((n + kScanSmallThreads - 1) / kScanSmallThreads);  // <= kScanSmallIpt
+  const uint64_t b = (uint64_t)threadIdx.x * ipt;
+  uint64_t v[kScanSmallIpt];
+#pragma unroll
+  for (int i = 0; i < kScanSmallIpt; ++i) v[i] = ((uint32_t)i < ipt && b + i < n) ? data[b + i] : 0;
   uint64_t s = 0;
-  for (uint64_t i = b; i < e; ++i) s += data[i];
-  uint64_t total;
-  uint64_t run = block_excl_scan(s, sh, total);
-  for (uint64_t i = b; i < e; ++i) {
-    const uint64_t v = data[i];
-    data[i] = run;
-    run += v;
+#pragma unroll
+  for (int i = 0; i < kScanSmallIpt; ++i) s += v[i];
+  uint64_t x = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
   }
-  if (total_out && threadIdx.x == 0) *total_out = total;
+  if (lane == 31) wsum[w] = x;
+  __syncthreads();
+  if (w == 0) {
+    const uint64_t t = wsum[lane];
+    uint64_t z = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint64_t y = __shfl_up_sync(0xffffffffu, z, o);
+      if (lane >= o) z += y;
+    }
+    wsum[lane] = z - t;  // exclusive warp offsets
+    if (lane == 31 && total_out) *total_out = z;
+  }
+  __syncthreads();
+  uint64_t run = wsum[w] + x - s;
+#pragma unroll
+  for (int i = 0; i < kScanSmallIpt; ++i) {
+    if ((uint32_t)i < ipt && b + i < n) data[b + i] = run;
+    run += v[i];
+  }
 }
 
 // Number of uint64 workspace elements scan_exclusive needs for an n-element array.
@@ -165,7 +191,7 @@ inline void scan_exclusive(sgx_ctx* ctx, uint64_t* data, uint64_t n, uint64_t* w
     return;
   }
   if (n <= kScanSmall) {
-    SGX_LAUNCH(ctx, scan_small_kernel, 1, kScanThreads, 0, data, n, total_dev);
+    SGX_LAUNCH(ctx, scan_small_kernel, 1, kScanSmallThreads, 0, data, n, total_dev);
     return;
   }
   SGX_LAUNCH(ctx, scan_tile_reduce_kernel, (unsigned)ntiles, kScanThreads, 0, data, n, ws);
