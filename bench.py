@@ -121,6 +121,75 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+class Lifeline:
+    """Keeps the one JSON line printable while an OPTIONAL multi-rank object (cfg4 / cfg5 at N = 8) runs.
+
+    Those objects are long chains of collectives: a rank that throws leaves its peers inside a collective that never
+    completes, and the line with the headline numbers -- complete by then -- would be lost with them.  Every rank runs a
+    watcher thread; a rank that fails drops a flag file (tmpfs, keyed by the job); a watcher that sees the flag, or whose
+    object overruns its deadline, ends its process with status 0 -- rank 0 first prints the line, with
+    {"error": ...} in the object's place.  Nothing here touches a timed region."""
+
+    def __init__(self, rank, line, key, poll_s=0.25, out=None):
+        self.rank, self.line, self.poll_s = rank, line, poll_s
+        self.out = out if out is not None else sys.stdout
+        d = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+        self.flag = os.path.join(d, "siga_b200_bench_abort_%s" % key)
+        self.lock = threading.Lock()
+        self.name, self.deadline = None, None
+        if rank == 0:
+            self.clear()
+        threading.Thread(target=self._watch, daemon=True).start()
+
+    def clear(self):
+        try:
+            os.remove(self.flag)
+        except OSError:
+            pass
+
+    def failed(self):
+        return os.path.exists(self.flag)
+
+    def arm(self, name, seconds):
+        with self.lock:
+            self.name, self.deadline = name, time.monotonic() + seconds
+
+    def disarm(self):
+        with self.lock:
+            self.name, self.deadline = None, None
+
+    def fail(self, name, text):
+        """Called by the rank whose object raised: publishes the failure and waits for its own watcher to end the process."""
+        tmp = "%s.%d" % (self.flag, os.getpid())
+        with open(tmp, "w") as f:
+            f.write("%s: rank %d: %s" % (name, self.rank, text[:800]))
+        os.replace(tmp, self.flag)
+        while True:
+            time.sleep(1.0)
+
+    def _watch(self):
+        while True:
+            time.sleep(self.poll_s)
+            with self.lock:  # disarm() waits while the decision below is being made: the line is printed once
+                if self.name is None:
+                    continue
+                why = None
+                if os.path.exists(self.flag):
+                    try:
+                        why = open(self.flag).read()
+                    except OSError:
+                        why = "%s: a rank failed" % self.name
+                elif time.monotonic() > self.deadline:
+                    why = "%s: rank %d gave up waiting (deadline)" % (self.name, self.rank)
+                if why is None:
+                    continue
+                if self.rank == 0:
+                    self.line[self.name] = {"error": why}
+                    self.out.write(json.dumps(self.line) + "\n")
+                    self.out.flush()
+                os._exit(0)
+
+
 def run_reference_sample(scale, threads, workdir, want_index=True):
     """Times the compiled reference (`siga index`, `siga overlap -m 45 -t threads`) on a scaled-down cfg2 sample."""
     ref = os.path.join(REPO, "oracle", "_ref", "siga")
@@ -259,6 +328,9 @@ def cli_object(reads, golden, min_overlap):
     return out
 
 
+T_START = time.monotonic()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -272,6 +344,8 @@ def main():
     ap.add_argument("--no-correct", action="store_true")
     ap.add_argument("--cfg4", default="auto", choices=["auto", "on", "off"], help="the 100 Mbp and 64 Mbp configs 4 and 5 (auto: at 8 GPUs)")
     ap.add_argument("--cfg4-scale", type=float, default=1.0)
+    ap.add_argument("--big-deadline", type=float, default=420.0, help="seconds one of the cfg4 / cfg5 objects may take before the line is printed without it")
+    ap.add_argument("--big-budget", type=float, default=600.0, help="a cfg4 / cfg5 object is skipped when the run is already this many seconds old")
     ap.add_argument("--index-steps", type=int, default=0, help="timed index builds (default: min(steps, 3))")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -699,6 +773,7 @@ def main():
             line["cli"] = {"error": str(ex)[:500]}
 
     want_cfg4 = args.cfg4 == "on" or (args.cfg4 == "auto" and world == 8)
+    life = None
     if want_cfg4:
         if fwd is not None:
             ctx.free_fm(fwd)
@@ -706,9 +781,25 @@ def main():
             ctx.free_reads(r_dev)
             fwd = rev = r_dev = None
         del host, flat
+        # the line is complete without these two objects: a failure or a hang inside them must not take it along
+        life = Lifeline(rank, line, "%s_%d" % (os.environ.get("MASTER_PORT", "0"), os.getppid()))
+        barrier()  # rank 0 has removed a stale flag before anybody can raise a new one
         for big in ("cfg4", "cfg5"):  # BASELINE.json configs[3] and configs[4]
-            line[big] = cfg4_object(args, ctx, api, formats, torch, dist, rank, world, local, barrier, max_over_ranks,
-                                    sum_over_ranks, cfg=big)
+            life.arm(big, args.big_deadline)  # armed before the first collective: a peer may be gone since the last object
+            late = torch.tensor([1 if time.monotonic() - T_START > args.big_budget else 0], device="cuda")
+            if world > 1:
+                dist.broadcast(late, 0)  # one decision for all ranks
+            if int(late.item()):
+                line[big] = {"skipped": "%.0f s had passed when this object was due (--big-budget %g)" % (time.monotonic() - T_START, args.big_budget)}
+                continue
+            try:
+                obj = cfg4_object(args, ctx, api, formats, torch, dist, rank, world, local, barrier, max_over_ranks,
+                                  sum_over_ranks, cfg=big)
+                with life.lock:  # the watcher serialises the line under the same lock
+                    line[big] = obj
+            except BaseException as ex:  # noqa: B036 -- the peers sit in collectives this rank will never join
+                life.fail(big, "%s: %s" % (type(ex).__name__, ex))
+        life.disarm()
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         with tempfile.TemporaryDirectory() as d:
@@ -728,6 +819,9 @@ def main():
     ctx.close()
     if rank == 0:
         print(json.dumps(line))
+    if life is not None and life.failed():  # a peer went away after its last collective: do not wait for it
+        sys.stdout.flush()
+        os._exit(0)
     if world > 1:
         dist.destroy_process_group()
     return 0
