@@ -62,6 +62,15 @@ int fail(sgx_ctx* ctx, const char* what, int rc) {
 }
 
 // After sgx_reads_pack has refused the input: name the first read with a byte other than A/C/G/T.
+// Success exit of a sub-command, called once its output files are closed and checked.  Leaving right here skips the
+// destructors of the read set (millions of strings), the explicit release of device and pinned memory and the tear-down
+// of the CUDA context by the runtime's exit handlers: a quarter of a second and more at config-2 size that frees nothing
+// the end of the process does not free anyway.
+[[noreturn]] void finish_ok() {
+  fflush(nullptr);
+  _exit(0);
+}
+
 void explain_bad_bases(const ReadSet& rs, uint64_t first = 0, uint64_t count = (uint64_t)-1) {
   const uint64_t end = count == (uint64_t)-1 ? rs.size() : first + count;
   for (uint64_t i = first; i < end; ++i)
@@ -300,6 +309,40 @@ void append_uint(std::string* s, uint64_t v) {
   s->append(p, tmp + sizeof(tmp) - p);
 }
 
+// Decimal digits of v at p, returns the end; values below 10 000 (coordinates inside a read) take no division loop.
+inline char* put_uint(char* p, uint64_t v) {
+  static const char kPairs[201] =
+      "0001020304050607080910111213141516171819202122232425262728293031323334353637383940414243444546474849"
+      "5051525354555657585960616263646566676869707172737475767778798081828384858687888990919293949596979899";
+  if (v < 10) {
+    *p++ = (char)('0' + v);
+    return p;
+  }
+  if (v < 100) {
+    memcpy(p, kPairs + 2 * v, 2);
+    return p + 2;
+  }
+  if (v < 1000) {
+    *p++ = (char)('0' + v / 100);
+    memcpy(p, kPairs + 2 * (v % 100), 2);
+    return p + 2;
+  }
+  if (v < 10000) {
+    memcpy(p, kPairs + 2 * (v / 100), 2);
+    memcpy(p + 2, kPairs + 2 * (v % 100), 2);
+    return p + 4;
+  }
+  char tmp[24];
+  char* q = tmp + sizeof(tmp);
+  do {
+    *--q = (char)('0' + v % 10);
+    v /= 10;
+  } while (v);
+  const size_t n = (size_t)(tmp + sizeof(tmp) - q);
+  memcpy(p, q, n);
+  return p + n;
+}
+
 // CR:i / BX:Z / EX:Z tags carried in the read comment (src/overlap_builder.cpp:304-316, src/asqg.h:29-60).
 void append_comment_tags(const std::string& comment, std::string* line) {
   if (comment.empty()) return;
@@ -411,6 +454,19 @@ bool write_asqg(const std::string& path, const CommonOpts& o, const ReadSet& rs,
   const size_t vt_chunk = 1 << 16, ed_chunk = 1 << 18;
   const size_t n_ht = with_ht ? 1 : 0;
   const size_t n_vt = (n + vt_chunk - 1) / vt_chunk, n_ed = with_ed ? (ed.n_edges + ed_chunk - 1) / ed_chunk : 0;
+  // worst-case bytes of one ED record: "ED\t" + two names + separator + six numbers no longer than the longest read's
+  // length (coordinates inside a read) + the flags
+  size_t ed_bound = 0, max_name = 0;
+  if (n_ed) {
+    uint64_t max_len = 0;
+    for (size_t i = 0; i < rs.size(); ++i) {
+      max_name = std::max(max_name, rs.names[i].size());
+      max_len = std::max<uint64_t>(max_len, rs.off[i + 1] - rs.off[i]);
+    }
+    char digits[24];
+    const size_t nd = (size_t)(put_uint(digits, max_len) - digits);
+    ed_bound = 3 + 2 * max_name + 1 + 6 * (1 + nd) + 5;
+  }
   const bool wrote = gz.write_chunks(n_ht + n_vt + n_ed, [&](size_t ci, std::string* text) {
     if (ci < n_ht) {
       *text = "HT\tVN:i:1\tOL:i:" + std::to_string(min_overlap) + "\tCN:i:1\n";  // IN/ER/TE are never set on this path
@@ -429,8 +485,27 @@ bool write_asqg(const std::string& path, const CommonOpts& o, const ReadSet& rs,
       }
     } else {
       const size_t b = (ci - n_ht - n_vt) * ed_chunk, e = std::min<size_t>(ed.n_edges, b + ed_chunk);
-      text->reserve((e - b) * 48);
+      // Written through a raw pointer into a buffer sized for the worst case: the target's name and length are two
+      // random accesses per record (prefetched a few records ahead), everything else is digits.
+      const size_t any_record = 3 + 2 * max_name + 1 + 6 * 21 + 5;  // whatever the six numbers are
+      text->resize((e - b) * ed_bound + any_record);
+      char* p0 = &(*text)[0];
+      char* p = p0;
+      const size_t ahead = 16;
       for (size_t k = b; k < e; ++k) {
+        // never true for edges whose coordinates lie inside their reads (every record then fits ed_bound); an edge that
+        // broke that promise gets room instead of running over the buffer
+        if ((size_t)(p - p0) + any_record > text->size()) {
+          const size_t at = (size_t)(p - p0);
+          text->resize(text->size() * 2);
+          p0 = &(*text)[0];
+          p = p0 + at;
+        }
+        if (k + ahead < e) {
+          const uint32_t t = ed.edges[k + ahead].target;
+          __builtin_prefetch(&rs.names[t]);
+          __builtin_prefetch(&rs.off[t]);
+        }
         const sgx_edge& g = ed.edges[k];
         const uint64_t lq = rs.off[g.query + 1] - rs.off[g.query], lt = rs.off[g.target + 1] - rs.off[g.target];
         uint64_t s0 = lq - g.length, e0 = lq - 1, s1 = 0, e1 = g.length - 1;
@@ -444,16 +519,24 @@ bool write_asqg(const std::string& path, const CommonOpts& o, const ReadSet& rs,
           s1 = lt - 1 - e1;
           e1 = lt - 1 - t;
         }
-        *text += "ED\t";
-        *text += rs.names[g.query];
-        *text += ' ';
-        *text += rs.names[g.target];
-        for (uint64_t v : {s0, e0, lq, s1, e1, lt}) {
-          *text += ' ';
-          append_uint(text, v);
+        memcpy(p, "ED\t", 3);
+        p += 3;
+        const std::string& qn = rs.names[g.query];
+        memcpy(p, qn.data(), qn.size());
+        p += qn.size();
+        *p++ = ' ';
+        const std::string& tn = rs.names[g.target];
+        memcpy(p, tn.data(), tn.size());
+        p += tn.size();
+        const uint64_t v[6] = {s0, e0, lq, s1, e1, lt};
+        for (int q = 0; q < 6; ++q) {
+          *p++ = ' ';
+          p = put_uint(p, v[q]);
         }
-        *text += (g.af & SGX_AF_QUERYCOMP) ? " 1 0\n" : " 0 0\n";
+        memcpy(p, (g.af & SGX_AF_QUERYCOMP) ? " 1 0\n" : " 0 0\n", 5);
+        p += 5;
       }
+      text->resize((size_t)(p - p0));
     }
   }, [&](size_t ci) {  // VT records are mostly read sequence; HT / ED records repeat their fields
     if (!o.gzip_fast) return GzChunkWriter::kZlib;
@@ -772,11 +855,10 @@ int cmd_index(int argc, char** argv) {
     fprintf(stderr, "ERROR siga - a GPU worker process failed\n");
     return -1;
   }
-  sgx_reads_free(reads);
   const double t1 = now_s();
   info("wall: %.3f sec (load + CUDA start %.3f [CUDA start alone %.3f], pack + build %.3f, rest of the writes %.3f)", t1 - t0,
        t_load - t0, t_cuda, t_built - t_load, t1 - t_built);
-  return 0;
+  finish_ok();  // reads, context and host buffers go with the process
 }
 
 int cmd_overlap(int argc, char** argv) {
@@ -926,14 +1008,9 @@ int cmd_overlap(int argc, char** argv) {
     fprintf(stderr, "ERROR siga - write to %s.asqg.gz failed\n", output.c_str());
     return -1;
   }
-  sgx_edges_free(&ed);
-  sgx_fm_free(fwd);
-  sgx_fm_free(rev);
-  sgx_reads_free(reads);
-  // (the context goes with the process: see main)
   const double t1 = now_s();
   info("wall: %.3f sec (load %.3f, gpu %.3f, write %.3f)", t1 - t0, t_load - t0, t_search - t_load, t1 - t_search);
-  return 0;
+  finish_ok();  // edges, indices, reads, context and host buffers go with the process
 }
 
 int usage_rmdup() {
@@ -1060,14 +1137,9 @@ int cmd_rmdup(int argc, char** argv) {
     }
   }
   info("%zu reads kept, %llu duplicates / substrings removed", rs.size() - (size_t)n_dups, (unsigned long long)n_dups);
-  sgx_hits_free(&hits);
-  sgx_fm_free(fwd);
-  sgx_fm_free(rev);
-  sgx_reads_free(reads);
-  // (the context goes with the process: see main)
   const double t1 = now_s();
   info("wall: %.3f sec (load %.3f, gpu %.3f, write %.3f)", t1 - t0, t_load - t0, t_gpu - t_load, t1 - t_gpu);
-  return 0;
+  finish_ok();  // hits, indices, reads, context and host buffers go with the process
 }
 
 int usage_correct() {
@@ -1301,13 +1373,9 @@ int cmd_correct(int argc, char** argv) {
   for (size_t i = 0; i < count; ++i) written += res.valid[i] ? 1 : 0;
   info("%llu of %llu reads%s written to %s", (unsigned long long)written, (unsigned long long)count,
        world > 1 ? " of rank 0's range" : "", outfile.c_str());
-  sgx_corrected_free(&res);
-  sgx_fm_free(fm);
-  sgx_reads_free(reads);
-  // (the context goes with the process: see main)
   const double t1 = now_s();
   info("wall: %.3f sec (load %.3f, gpu %.3f, write %.3f)", t1 - t0, t_load - t0, t_gpu - t_load, t1 - t_gpu);
-  return 0;
+  finish_ok();  // results, index, reads, context and host buffers go with the process
 }
 
 int usage_match() {

@@ -96,7 +96,7 @@ def _asqg(path):
         return [l.rstrip("\n") for l in f]
 
 
-@pytest.mark.parametrize("case", ["fasta", "fastq_comments_exhaustive_norc"])
+@pytest.mark.parametrize("case", ["fasta", "fastq_comments_exhaustive_norc", "fasta_long_names_variable_length"])
 def test_overlap_front_end_single_and_sharded_equal_reference_asqg(case):
     """`siga overlap` host logic: index / read loading, name ranks, the ASQG writer (HT, VT in input order with SS / CR /
     BX tags, ED) and the --gpus N path (fork, read ranges, .vt / .ed part files concatenated)."""
@@ -111,6 +111,15 @@ def test_overlap_front_end_single_and_sharded_equal_reference_asqg(case):
         if case == "fasta":
             src = os.path.join(d, "reads.fa")
             synth.write_fasta(src, reads)
+            oargs = []
+        elif case == "fasta_long_names_variable_length":
+            # ED records of very different sizes (names of 2 .. 70 characters, coordinates of reads of 30 .. 50 bases):
+            # the writer sizes its record buffer from the longest name and the longest read
+            src = os.path.join(d, "reads.fa")
+            reads = [r[:int(rng.integers(30, 51))] for r in reads]
+            with open(src, "w") as f:
+                for i, r in enumerate(reads):
+                    f.write(">%s%d\n%s\n" % ("n" * (1 + (i * 7) % 64), i, r.tobytes().decode()))
             oargs = []
         else:
             src = os.path.join(d, "reads.fq")
