@@ -344,8 +344,8 @@ def main():
     ap.add_argument("--no-correct", action="store_true")
     ap.add_argument("--cfg4", default="auto", choices=["auto", "on", "off"], help="the 100 Mbp and 64 Mbp configs 4 and 5 (auto: at 8 GPUs)")
     ap.add_argument("--cfg4-scale", type=float, default=1.0)
-    ap.add_argument("--big-deadline", type=float, default=420.0, help="seconds one of the cfg4 / cfg5 objects may take before the line is printed without it")
-    ap.add_argument("--big-budget", type=float, default=600.0, help="a cfg4 / cfg5 object is skipped when the run is already this many seconds old")
+    ap.add_argument("--big-deadline", type=float, default=300.0, help="seconds one of the cfg4 / cfg5 objects may take before the line is printed without it")
+    ap.add_argument("--big-budget", type=float, default=480.0, help="a cfg4 / cfg5 object is skipped when the run is already this many seconds old")
     ap.add_argument("--index-steps", type=int, default=0, help="timed index builds (default: min(steps, 3))")
     args = ap.parse_args()
     if args.warmup < 3:
