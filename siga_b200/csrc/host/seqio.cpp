@@ -113,22 +113,26 @@ bool read_sequences_serial(const std::string& path, ReadSet* out, std::string* e
   const int first = in.peek();
   std::string line;
   if (first == '>') {
+    // FASTAReader::read (src/kseq.cpp:191-228) keys everything on the text behind '>' being non-empty: a header that
+    // follows a named record without sequence ends the input (207-210); a bare ">" is no name at all -- the sequence lines
+    // behind it stay in the buffer and join the NEXT named record, and are dropped at the end of the file.
     std::string name, seq;
-    bool have = false;
     while (in.getline(line)) {
       trim(line);
       if (line.empty()) continue;
       if (line[0] == '>') {
-        if (have && !seq.empty()) push(out, name, seq);
-        else if (have) break;  // the reference stops at a header that follows an empty record (src/kseq.cpp:207-210)
+        if (!seq.empty() && !name.empty()) {
+          push(out, name, seq);
+          seq.clear();
+        } else if (!name.empty()) {
+          break;
+        }
         name = line.substr(1);
-        seq.clear();
-        have = true;
       } else {
         seq += line;
       }
     }
-    if (have && !seq.empty()) push(out, name, seq);
+    if (!seq.empty() && !name.empty()) push(out, name, seq);
     return true;
   }
   if (first == '@') {
@@ -198,6 +202,7 @@ bool scan_fasta_range(const char* p, const char* end, Sink& sink) {
   bool have = false, any_seq = false;
   while (next_line(p, end, &ln)) {
     if (*ln.b == '>') {
+      if (ln.e - ln.b == 1) return false;  // a bare ">": the serial reader has the reference's rule for it
       if (have && any_seq) sink.done();
       else if (have) return false;
       sink.header(ln.b + 1, ln.e);

@@ -234,6 +234,36 @@ def test_reference_assembler_reads_our_asqg_and_builds_the_same_contigs():
         assert a == b and sum(len(c) for c in a) > 4000
 
 
+IRREGULAR_FASTA = {
+    # FASTAReader::read (src/kseq.cpp:191-228) keys its records on the text behind '>' being non-empty
+    "bare_header_first": ">\nACGTACGTAC\n>b\nGGGTTTAAAC\n",                     # the orphan lines join record b
+    "bare_header_mid": ">a\nACGTACGTAC\n>\nGGGTTTAAAC\n>c\nTTTTACGTAA\n>d\nCCCCCAAAAA\n",
+    "bare_header_last": ">a\nACGTACGTAC\n>b\nGGGTTTAAAC\n>\nTTTTACGTAA\n",    # ... or are dropped at the end
+    "bare_header_without_lines": ">a\nACGTACGTAC\n>\n>c\nTTTTACGTAA\n",
+    "named_record_without_lines": ">a\nACGTACGTAC\n>e\n>c\nTTTTACGTAA\n",       # the reference stops reading here
+    "name_is_all_comment": "> only a comment\nACGTACGTAC\n>b\nGGGTTTAAAC\n",
+    "crlf_blank_lines_no_final_newline": ">a x\r\nACGTAC\r\n\r\nGTAC\r\n>b\r\nGGGTTTAAAC\r\n>c\r\nTTTTACGTAA",
+}
+
+
+@pytest.mark.parametrize("case", sorted(IRREGULAR_FASTA))
+def test_irregular_fasta_is_read_like_the_reference_reads_it(case):
+    """Index files and ASQG of inputs the reference's reader treats in its own way: same records, same files."""
+    with tempfile.TemporaryDirectory() as d:
+        ours, ref = os.path.join(d, "ours"), os.path.join(d, "ref")
+        os.mkdir(ours)
+        os.mkdir(ref)
+        src = os.path.join(d, "reads.fa")
+        with open(src, "w", newline="") as f:
+            f.write(IRREGULAR_FASTA[case])
+        for run, cwd in ((lambda a: refrun.run_ref(a, ref), ref), (lambda a: _cli(a, ours), ours)):
+            run(["index", src])
+            run(["overlap", "-m", "3", src])
+        for ext in (".bwt", ".rbwt", ".sai", ".rsai"):
+            assert open(os.path.join(ours, "reads" + ext), "rb").read() == open(os.path.join(ref, "reads" + ext), "rb").read(), ext
+        assert sorted(_asqg(os.path.join(ours, "reads.asqg.gz"))) == sorted(_asqg(os.path.join(ref, "reads.asqg.gz")))
+
+
 @pytest.mark.parametrize("algo", ["sais2", "sais"])
 def test_index_front_end_equals_reference_files(algo):
     """`siga index` host logic (reads in, .bwt/.sai/.rbwt/.rsai writers, -a / -p / --no-forward / --no-reverse) with the

@@ -223,6 +223,8 @@ def test_parallel_sequence_reader_equals_serial_reader(tmp_path):
                                      for i, s in ((i, seq(50)) for i in range(2500)))
     files["empty_record.fa"] = files["plain.fa"][:40000] + ">empty\n>next\nACGT\n" + files["plain.fa"][40000:]
     files["truncated.fq"] = files["quality_at.fq"][:-30]
+    cut = files["plain.fa"].index("\n>", 50000) + 1
+    files["bare_header.fa"] = files["plain.fa"][:cut] + ">\nACGT\n" + files["plain.fa"][cut:]  # its line joins the next record
     paths = []
     for name, text in files.items():
         p = tmp_path / name
@@ -233,6 +235,7 @@ def test_parallel_sequence_reader_equals_serial_reader(tmp_path):
     lines = r.stdout.strip().splitlines()
     assert r.returncode == 0 and len(lines) == len(paths) and all(" same " in l for l in lines), r.stdout + r.stderr
     assert int(lines[0].split()[2]) == 3000 and int(lines[2].split()[2]) == 2500
+    assert int(lines[5].split()[2]) == 3000  # the bare header adds no record
     assert lines[2].endswith(" q") and not lines[0].endswith(" q")  # qualities kept for FASTQ only
 
 
