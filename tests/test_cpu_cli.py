@@ -264,6 +264,70 @@ def test_irregular_fasta_is_read_like_the_reference_reads_it(case):
         assert sorted(_asqg(os.path.join(ours, "reads.asqg.gz"))) == sorted(_asqg(os.path.join(ref, "reads.asqg.gz")))
 
 
+def _random_fasta(rnd):
+    seq = lambda n: "".join(rnd.choice("ACGT") for _ in range(n))  # noqa: E731
+    out = []
+    for i in range(rnd.randint(1, 12)):
+        k, nl = rnd.random(), rnd.choice(["\n", "\n", "\r\n"])
+        if k < 0.55:
+            out.append(">r%d%s%s" % (i, rnd.choice(["", " c", " CR:i:3 x", "\tt"]), nl))
+        elif k < 0.75:
+            out.append(rnd.choice([">", "> ", "> lead"]) + nl)
+        for _ in range(rnd.randint(0, 3)):
+            r = rnd.random()
+            out.append(rnd.choice(["", " ", "  "]) + seq(rnd.randint(1, 25)) + rnd.choice(["", " ", "\t"]) + nl if r < 0.7 else
+                       nl if r < 0.85 else "  " + nl)
+    s = "".join(out)
+    if rnd.random() < 0.3:
+        s = s.rstrip("\r\n")
+    return s if s.startswith(">") else ">first\n" + s
+
+
+def _random_fastq(rnd):
+    out = []
+    for i in range(rnd.randint(1, 10)):
+        s = "".join(rnd.choice("ACGT") for _ in range(rnd.randint(1, 25)))
+        name, nl = "q%d%s" % (i, rnd.choice(["", " c1", " BX:Z:a"])), rnd.choice(["\n", "\n", "\r\n"])
+        q, k = "".join(rnd.choice("I@+>5") for _ in s), rnd.random()
+        plus = "-" if k < 0.07 else "+other" if 0.12 < k < 0.16 else "+" if rnd.random() < 0.6 else "+" + name
+        rec = ["@" + name, s, plus, q[:-1] if 0.07 < k < 0.12 else q]
+        if rnd.random() < 0.1:
+            rec.insert(rnd.randint(0, 4), "")
+        if rnd.random() < 0.05:
+            rec = rec[:rnd.randint(1, 3)]
+        out.append(nl.join(rec) + nl)
+    return "".join(out)
+
+
+def test_random_irregular_inputs_parse_like_the_reference():
+    """Seeded fuzz of the FASTA / FASTQ reader: bare and comment-only headers, records without lines, padded lines, blank
+    lines, CRLF, missing final newline; FASTQ with a wrong separator, a short quality line, a repeated or foreign name
+    behind '+', cut records.  Wherever the reference builds an index, ours is byte-identical; where the reference gives
+    up (it aborts on an empty read set), ours exits with an error."""
+    import random
+    rnd = random.Random(7)
+    compared = 0
+    with tempfile.TemporaryDirectory() as d:
+        for it in range(80):
+            fq = rnd.random() < 0.4
+            src = os.path.join(d, "in%d.%s" % (it, "fq" if fq else "fa"))
+            with open(src, "w", newline="") as f:
+                f.write(_random_fastq(rnd) if fq else _random_fasta(rnd))
+            ours, ref = os.path.join(d, "ours%d" % it), os.path.join(d, "ref%d" % it)
+            os.mkdir(ours)
+            os.mkdir(ref)
+            r = subprocess.run([refrun.REF_BIN, "index", "-p", "x", src], cwd=ref, capture_output=True)
+            o = subprocess.run([CLI, "index", "-p", "x", src], cwd=ours, capture_output=True)
+            if r.returncode != 0 or not os.path.isfile(os.path.join(ref, "x.sai")):
+                assert o.returncode != 0, open(src).read()
+                continue
+            assert o.returncode == 0, open(src).read()
+            for ext in (".bwt", ".rbwt", ".sai", ".rsai"):
+                assert open(os.path.join(ours, "x" + ext), "rb").read() == open(os.path.join(ref, "x" + ext), "rb").read(), open(src).read()
+            compared += 1
+    assert compared >= 40
+
+
 @pytest.mark.parametrize("algo", ["sais2", "sais"])
 def test_index_front_end_equals_reference_files(algo):
     """`siga index` host logic (reads in, .bwt/.sai/.rbwt/.rsai writers, -a / -p / --no-forward / --no-reverse) with the
