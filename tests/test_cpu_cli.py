@@ -264,6 +264,74 @@ def test_irregular_fasta_is_read_like_the_reference_reads_it(case):
         assert sorted(_asqg(os.path.join(ours, "reads.asqg.gz"))) == sorted(_asqg(os.path.join(ref, "reads.asqg.gz")))
 
 
+def _rc(s):
+    return s[::-1].translate(str.maketrans("ACGT", "TGCA"))
+
+
+def _nasty_genome(rnd):
+    kind, n = rnd.random(), rnd.randint(30, 400)
+    if kind < 0.3:
+        return "".join(rnd.choice("ACGT") for _ in range(n))
+    if kind < 0.55:  # tandem repeats with a few substitutions
+        unit = "".join(rnd.choice("ACGT") for _ in range(rnd.randint(1, 7)))
+        g = list((unit * (n // len(unit) + 1))[:n])
+        for _ in range(rnd.randint(0, 4)):
+            g[rnd.randrange(n)] = rnd.choice("ACGT")
+        return "".join(g)
+    if kind < 0.8:  # low complexity
+        return "".join(rnd.choice("AC") if rnd.random() < 0.9 else rnd.choice("GT") for _ in range(n))
+    seg = "".join(rnd.choice("ACGT") for _ in range(rnd.randint(10, 40)))  # long repeats and a palindrome
+    return seg + "".join(rnd.choice("ACGT") for _ in range(10)) + seg + _rc(seg) + seg[:len(seg) // 2]
+
+
+def _nasty_reads(rnd, g):
+    fixed, l0, out = rnd.random() < 0.4, rnd.randint(6, min(40, len(g))), []
+    for _ in range(rnd.randint(2, 120)):
+        ln = l0 if fixed else rnd.randint(4, min(45, len(g)))
+        p = rnd.randrange(0, len(g) - ln + 1)
+        s = g[p:p + ln]
+        if rnd.random() < 0.4:
+            s = _rc(s)
+        if out and rnd.random() < 0.1:
+            s = rnd.choice(out)          # duplicate
+        if out and rnd.random() < 0.05:
+            s = _rc(rnd.choice(out))     # reverse-complement duplicate
+        if rnd.random() < 0.1:
+            k = rnd.randrange(len(s))
+            s = s[:k] + rnd.choice("ACGT") + s[k + 1:]
+        out.append(s)
+    return out
+
+
+def test_overlap_logic_on_repetitive_read_sets_equals_the_reference():
+    """Seeded fuzz of the whole front-end on read sets made to hurt: tandem repeats, two-letter sequence, long repeats with
+    a palindrome, duplicates and reverse-complement duplicates, reads of 4 .. 45 bases, min-overlap 3 .. 16, -x,
+    --no-opposite-strand, both ordering models.  The host stand-in runs the SAME overlap_logic.h (find / filter / resolve /
+    extract) the general path of the CUDA post kernel compiles: index files byte-identical, ASQG set-identical."""
+    import random
+    rnd = random.Random(23)
+    with tempfile.TemporaryDirectory() as d:
+        for it in range(60):
+            reads = _nasty_reads(rnd, _nasty_genome(rnd))
+            src = os.path.join(d, "in%d.fa" % it)
+            pre = rnd.choice(["r", "x9", "Z", "a_"])
+            with open(src, "w") as f:
+                f.write("".join(">%s%d\n%s\n" % (pre, i, s) for i, s in enumerate(reads)))
+            opts = ["-m", str(rnd.randint(3, 16))] + (["-x"] if rnd.random() < 0.3 else []) + \
+                (["--no-opposite-strand"] if rnd.random() < 0.25 else [])
+            algo = rnd.choice(["sais", "sais2"])
+            ours, ref = os.path.join(d, "ours%d" % it), os.path.join(d, "ref%d" % it)
+            os.mkdir(ours)
+            os.mkdir(ref)
+            for tool, cwd in ((refrun.REF_BIN, ref), (CLI, ours)):
+                for args in (["index", "-a", algo, "-p", "x", src], ["overlap", "-p", "x", "-t", "2"] + opts + [src]):
+                    r = subprocess.run([tool] + args, cwd=cwd, capture_output=True, text=True)
+                    assert r.returncode == 0, (it, args, r.stderr[-500:])
+            for ext in (".bwt", ".rbwt", ".sai", ".rsai"):
+                assert open(os.path.join(ours, "x" + ext), "rb").read() == open(os.path.join(ref, "x" + ext), "rb").read(), (it, ext)
+            assert sorted(_asqg(os.path.join(ours, "x.asqg.gz"))) == sorted(_asqg(os.path.join(ref, "x.asqg.gz"))), (it, opts, algo)
+
+
 def _random_fasta(rnd):
     seq = lambda n: "".join(rnd.choice("ACGT") for _ in range(n))  # noqa: E731
     out = []
