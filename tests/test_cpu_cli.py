@@ -332,6 +332,51 @@ def test_overlap_logic_on_repetitive_read_sets_equals_the_reference():
             assert sorted(_asqg(os.path.join(ours, "x.asqg.gz"))) == sorted(_asqg(os.path.join(ref, "x.asqg.gz"))), (it, opts, algo)
 
 
+def test_correct_and_rmdup_on_random_read_sets_equal_the_reference():
+    """Seeded fuzz of `siga correct` (k 3 .. 31, threshold 1 .. 5, 0 .. 12 rounds, count offset 0 .. 3; FASTA and FASTQ with
+    low qualities; error rates up to 8 %; random, tandem-repeat and two-letter genomes; fixed and variable read length)
+    and `siga rmdup` on the same sets.  The host stand-in runs the SAME correct_logic.h the CUDA kernel compiles:
+    corrected files byte-identical, kept / duplicate record sets identical."""
+    import random
+    rnd = random.Random(31)
+    with tempfile.TemporaryDirectory() as d:
+        for it in range(40):
+            n_g, kind = rnd.randint(60, 500), rnd.random()
+            if kind < 0.6:
+                g = "".join(rnd.choice("ACGT") for _ in range(n_g))
+            elif kind < 0.8:
+                u = "".join(rnd.choice("ACGT") for _ in range(rnd.randint(2, 9)))
+                g = (u * (n_g // len(u) + 1))[:n_g]
+            else:
+                g = "".join(rnd.choice("AC") if rnd.random() < 0.85 else rnd.choice("GT") for _ in range(n_g))
+            fixed, l0, err = rnd.random() < 0.5, rnd.randint(12, min(60, n_g)), rnd.choice([0.0, 0.01, 0.03, 0.08])
+            reads = []
+            for _ in range(max(2, n_g * rnd.randint(3, 25) // l0)):
+                ln = l0 if fixed else rnd.randint(6, min(60, n_g))
+                p = rnd.randrange(0, n_g - ln + 1)
+                s = g[p:p + ln] if rnd.random() < 0.5 else _rc(g[p:p + ln])
+                reads.append("".join(c if rnd.random() >= err else rnd.choice("ACGT") for c in s))
+            fq = rnd.random() < 0.5
+            src = os.path.join(d, "in%d.%s" % (it, "fq" if fq else "fa"))
+            with open(src, "w") as f:
+                for i, s in enumerate(reads):
+                    f.write("@r%d%s\n%s\n+\n%s\n" % (i, rnd.choice(["", " c"]), s, "".join(rnd.choice("#+5?I") for _ in s)) if fq
+                            else ">r%d\n%s\n" % (i, s))
+            opts = ["-k", str(rnd.randint(3, min(31, l0 if fixed else 12))), "-x", str(rnd.randint(1, 5)),
+                    "-i", str(rnd.randint(0, 12)), "-O", str(rnd.randint(0, 3))]
+            ours, ref = os.path.join(d, "ours%d" % it), os.path.join(d, "ref%d" % it)
+            os.mkdir(ours)
+            os.mkdir(ref)
+            for tool, cwd in ((refrun.REF_BIN, ref), (CLI, ours)):
+                for args in (["index", "-p", "x", src], ["correct", "-p", "x", "-o", "out.fa", "-t", "2"] + opts + [src],
+                             ["rmdup", "-p", "x", src]):
+                    r = subprocess.run([tool] + args, cwd=cwd, capture_output=True, text=True)
+                    assert r.returncode == 0, (it, args, r.stderr[-500:])
+            assert open(os.path.join(ours, "out.fa")).read() == open(os.path.join(ref, "out.fa")).read(), (it, opts)
+            for f in ("x.rmdup.fa", "x.rmdup.dups.fa"):
+                assert _fasta_records(os.path.join(ours, f)) == _fasta_records(os.path.join(ref, f)), (it, f)
+
+
 def _random_fasta(rnd):
     seq = lambda n: "".join(rnd.choice("ACGT") for _ in range(n))  # noqa: E731
     out = []
