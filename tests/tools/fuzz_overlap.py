@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE: random-input comparison of a `siga` front-end binary with the compiled reference (oracle/_ref/siga).
 
-    python tests/tools/fuzz_overlap.py [SEED] [CASES] [--cli PATH]
+    python tests/tools/fuzz_overlap.py [SEED] [CASES] [--cli PATH] [--multi]
 
 --cli defaults to build/siga_hostemu (the front-end sources on the host stand-in of the C ABI, CPU only); on a GPU box
 pass siga_b200/bin/siga to run the same inputs through the CUDA library.  Mismatching cases are kept under
@@ -14,6 +14,8 @@ REPO=os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF=os.path.join(REPO,"oracle","_ref","siga"); OURS=os.path.join(REPO,"build","siga_hostemu")
 if "--cli" in sys.argv:
     k=sys.argv.index("--cli"); OURS=os.path.abspath(sys.argv[k+1]); del sys.argv[k:k+2]
+GPUS="--multi" in sys.argv  # --multi: a third of our overlap runs use --gpus 2 / 3 (needs that many devices, or the host stand-in)
+if GPUS: sys.argv.remove("--multi")
 rnd=random.Random(int(sys.argv[1]) if len(sys.argv)>1 else 1)
 N=int(sys.argv[2]) if len(sys.argv)>2 else 100
 def rc(s): return s[::-1].translate(str.maketrans("ACGT","TGCA"))
@@ -58,10 +60,11 @@ for it in range(N):
     if rnd.random()<0.3: opts.append("-x")
     if rnd.random()<0.25: opts.append("--no-opposite-strand")
     algo=rnd.choice(["sais","sais2"])
+    gp=["--gpus",str(rnd.choice([2,3]))] if GPUS and rnd.random()<0.3 else []  # ours only: one forked worker per "GPU"
     ok=True
     for tool,sub in ((REF,"ref"),(OURS,"ours")):
         a=subprocess.run([tool,"index","-a",algo,"-p","x",src],cwd=d+"/"+sub,capture_output=True,text=True)
-        b=subprocess.run([tool,"overlap","-p","x","-t","2"]+opts+[src],cwd=d+"/"+sub,capture_output=True,text=True)
+        b=subprocess.run([tool,"overlap","-p","x","-t","2"]+opts+(gp if tool==OURS else [])+[src],cwd=d+"/"+sub,capture_output=True,text=True)
         if a.returncode or b.returncode:
             print(it,sub,"rc",a.returncode,b.returncode,(a.stderr+b.stderr)[-300:]); ok=False
     if not ok: continue
