@@ -377,6 +377,30 @@ def test_correct_and_rmdup_on_random_read_sets_equal_the_reference():
                 assert _fasta_records(os.path.join(ours, f)) == _fasta_records(os.path.join(ref, f)), (it, f)
 
 
+@pytest.mark.parametrize("lengths,works", [(range(10, 41), True), (range(10, 47), False)], ids=["31_groups", "37_groups"])
+def test_known_limit_of_the_duplicate_map_in_resolve(lengths, works):
+    """KNOWN LIMITATION, pinned so that it stays loud (DESIGN.md section 7): SubMaximalBlockFilter::resolve hands out the
+    forward rows of duplicated reads through a std::map (src/overlap_builder.cpp:1018-1059); overlap_logic.h:ov_resolve
+    keeps 32 entries per call.  Homopolymer reads of N different lengths, each one twice, put N duplicate groups into one
+    resolve: up to 32 the ASQG equals the reference's, beyond that the call fails with SGX_EOVERFLOW -- it never writes
+    a different graph.  (`siga rmdup`, which the pipeline runs before `overlap`, removes such reads.)"""
+    with tempfile.TemporaryDirectory() as d:
+        ours, ref = os.path.join(d, "ours"), os.path.join(d, "ref")
+        os.mkdir(ours)
+        os.mkdir(ref)
+        src = os.path.join(d, "reads.fa")
+        with open(src, "w") as f:
+            f.write("".join(">r%d\n%s\n" % (i, "A" * ln) for i, ln in enumerate(l for l in lengths for _ in (0, 1))))
+        refrun.run_ref(["index", src], ref)
+        refrun.run_ref(["overlap", "-m", "8", src], ref)
+        _cli(["index", src], ours)
+        r = _cli(["overlap", "-m", "8", src], ours, ok=works)
+        if works:
+            assert sorted(_asqg(os.path.join(ours, "reads.asqg.gz"))) == sorted(_asqg(os.path.join(ref, "reads.asqg.gz")))
+        else:
+            assert "sgx_overlap_edges failed (-5)" in r.stderr and not os.path.exists(os.path.join(ours, "reads.asqg.gz"))
+
+
 def _random_fasta(rnd):
     seq = lambda n: "".join(rnd.choice("ACGT") for _ in range(n))  # noqa: E731
     out = []
